@@ -1,0 +1,166 @@
+/*
+ * parelag_b200.h -- C ABI of the B200-native AMGe solve-and-coarsen path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or
+ * torch types.  ParElag's C++ classes (re-created under parelag_b200/src with the
+ * reference's names and signatures) call these functions from Mult()/BuildSolver();
+ * a maintainer of the reference would call them from the same places -- see
+ * INTEGRATION.md.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - all functions return 0 on success, non-zero on error; pe_last_error() returns
+ *     the message of the last failing call on this thread.  No exception crosses
+ *     the ABI.
+ *   - pointers are HOST pointers unless the parameter is an opaque handle;
+ *     handles own device memory (HBM) and are freed by the matching *_free.
+ *   - HYPRE_Int is 32-bit in all reference usage (src/hypreExtension/parcsr-add.c:32-41):
+ *     indices are int32, values are FP64, global ids are int64.
+ *   - work is enqueued on the context's stream; calls that return host scalars or
+ *     copy to host synchronise that stream.
+ *   - there is NO CPU fallback: if no CUDA device is usable pe_ctx_create fails.
+ */
+#ifndef PARELAG_B200_H
+#define PARELAG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pe_ctx pe_ctx;             /* device, streams, NCCL communicator    */
+typedef struct pe_mat pe_mat;             /* device ParCSR matrix (diag+offd+halo) */
+typedef struct pe_vec pe_vec;             /* device FP64 vector                    */
+typedef struct pe_smoother pe_smoother;   /* hypre-type relaxation on one matrix   */
+typedef struct pe_graph pe_graph;         /* captured CUDA graph                   */
+
+/* Host-side description of a ParCSR matrix: the fields of hypre_ParCSRMatrix the
+ * path reads (hypre_ParCSRMatrixMatvecBoolInt.c:148-196, parcsr-add.c:31-41,
+ * hypre_CSRFactory.c:186-247).  All arrays are borrowed for the duration of the
+ * call only.  A single-rank matrix has num_cols_offd = 0 and no comm package. */
+typedef struct pe_parcsr_host {
+    int64_t global_num_rows, global_num_cols;
+    int64_t first_row_index, first_col_diag;
+    int32_t num_rows;         /* local rows                                   */
+    int32_t num_cols_diag;    /* local (owned) columns                        */
+    int32_t num_cols_offd;    /* ghost columns                                */
+    const int32_t *diag_i, *diag_j;
+    const double *diag_data;
+    const int32_t *offd_i, *offd_j;      /* may be NULL when num_cols_offd==0 */
+    const double *offd_data;
+    const int64_t *col_map_offd;         /* global ids, ascending             */
+    /* hypre_ParCSRCommPkg */
+    int32_t num_sends;
+    const int32_t *send_procs, *send_map_starts, *send_map_elmts;
+    int32_t num_recvs;
+    const int32_t *recv_procs, *recv_vec_starts;
+} pe_parcsr_host;
+
+/* ---- context (replaces parelag::mpi_session, src/utilities/mpiUtils.cpp:23-31) */
+/* nccl_unique_id: 128 bytes from pe_nccl_get_unique_id on rank 0 (broadcast by the
+ * launcher), or NULL when nranks == 1. */
+int pe_ctx_create(int rank, int nranks, int device, const void *nccl_unique_id, pe_ctx **out);
+int pe_ctx_destroy(pe_ctx *ctx);
+int pe_ctx_sync(pe_ctx *ctx);
+int pe_nccl_get_unique_id(void *id128);
+const char *pe_last_error(void);
+int pe_ctx_rank(const pe_ctx *ctx);
+int pe_ctx_nranks(const pe_ctx *ctx);
+/* number of kernels this library has launched on ctx since creation */
+int64_t pe_ctx_launch_count(const pe_ctx *ctx);
+/* stream-ordered CUDA-event timer on the context's stream (milliseconds) */
+int pe_ctx_timer_start(pe_ctx *ctx);
+int pe_ctx_timer_stop(pe_ctx *ctx, float *ms);
+/* write a scratch buffer larger than L2 (bench hygiene) */
+int pe_ctx_flush_l2(pe_ctx *ctx);
+
+/* ---- CUDA graphs (Hierarchy::Mult replays a captured V-cycle) */
+int pe_graph_begin(pe_ctx *ctx);
+int pe_graph_end(pe_ctx *ctx, pe_graph **out);
+int pe_graph_launch(pe_ctx *ctx, pe_graph *g);
+int pe_graph_free(pe_graph *g);
+
+/* ---- vectors (replace mfem::Vector on the path) */
+int pe_vec_create(pe_ctx *ctx, int64_t n, pe_vec **out);
+int pe_vec_free(pe_vec *v);
+int64_t pe_vec_size(const pe_vec *v);
+int pe_vec_upload(pe_vec *v, const double *host);       /* n doubles, H2D   */
+int pe_vec_download(const pe_vec *v, double *host);     /* n doubles, D2H   */
+int pe_vec_fill(pe_vec *v, double value);
+int pe_vec_copy(const pe_vec *src, pe_vec *dst);
+int pe_vec_axpby(double a, const pe_vec *x, double b, pe_vec *y);          /* y=a x+b y */
+int pe_vec_add3(double a, const pe_vec *x, double b, const pe_vec *y, pe_vec *z); /* z=a x+b y */
+int pe_vec_scale(pe_vec *x, double a);
+int pe_vec_mul(const pe_vec *d, pe_vec *x);                                 /* x .*= d */
+/* global dot (sum over ranks via ncclAllReduce); deterministic two-stage reduce.
+ * Replaces mfem::CGSolver::Dot / MPI_Allreduce (ParELAG_StationarySolver.cpp:64). */
+int pe_vec_dot(const pe_vec *x, const pe_vec *y, double *out);
+/* raw device pointer, for callers that own a CUDA stream themselves */
+void *pe_vec_device_ptr(pe_vec *v);
+
+/* ---- matrices (ParCSR in/out; replaces mfem::HypreParMatrix on the path) */
+int pe_mat_upload(pe_ctx *ctx, const pe_parcsr_host *A, pe_mat **out);
+/* query sizes, then download into caller-allocated arrays (NULL = skip) */
+int pe_mat_info(const pe_mat *A, int32_t *num_rows, int32_t *num_cols_diag,
+                int32_t *num_cols_offd, int64_t *nnz_diag, int64_t *nnz_offd);
+int pe_mat_download(const pe_mat *A, int32_t *diag_i, int32_t *diag_j, double *diag_data,
+                    int32_t *offd_i, int32_t *offd_j, double *offd_data,
+                    int64_t *col_map_offd);
+int pe_mat_free(pe_mat *A);
+/* explicit local transpose (counting-sort order: ascending columns per row).
+ * mfem::Transpose / hypre_ParCSRMatrixTranspose2 (src/hypreExtension/par_Tmatmul.c:41-79) */
+int pe_mat_transpose(pe_ctx *ctx, const pe_mat *A, pe_mat **out);
+/* diag(A) and inverse-scaled rows (SchurComplementFactory.cpp:51-166 InvScaleRows) */
+int pe_mat_get_diag(const pe_mat *A, pe_vec *d);
+int pe_mat_scale_rows(pe_mat *A, const pe_vec *d, int invert);
+
+/* ---- K1/K2/K7: SpMV, SpMV^T, residual
+ * y = alpha*A*x + beta*y : hypre_ParCSRMatrixMatvec via mfem::HypreParMatrix::Mult,
+ *   src/linalg/solver_ops/ParELAG_Hierarchy.cpp:193,234.
+ * y = alpha*A^T*x + beta*y : hypre_ParCSRMatrixMatvecT via P->MultTranspose,
+ *   Hierarchy.cpp:202, HiptmairSmoother.cpp:63.  The explicit transpose is built
+ *   on first use and cached on A (no atomics on the solve path).
+ * r = b - A*x : mg_utils::ComputeResidual, src/linalg/utilities/ParELAG_MG_Utils.hpp:405-467. */
+int pe_spmv(pe_ctx *ctx, double alpha, pe_mat *A, const pe_vec *x, double beta, pe_vec *y);
+int pe_spmv_t(pe_ctx *ctx, double alpha, pe_mat *A, const pe_vec *x, double beta, pe_vec *y);
+int pe_residual(pe_ctx *ctx, pe_mat *A, const pe_vec *x, const pe_vec *b, pe_vec *r);
+
+/* ---- K3/K4/K5: hypre relaxation (mfem::HypreSmoother behind
+ * parelag::HypreSmootherWrapper, src/linalg/solver_ops/ParELAG_HypreSmootherWrapper.cpp:20-35;
+ * type ids as in src/linalg/factories/ParELAG_HypreSmootherFactory.cpp:92-109:
+ * 0 Jacobi, 1 l1-Jacobi, 2 l1-GS, 4 truncated l1-GS, 5 lumped Jacobi, 6 GS, 16 Chebyshev).
+ * ordering: how the sequential Gauss-Seidel order of hypre is realised on the GPU */
+enum { PE_GS_ORDER_NATURAL = 0,     /* exact natural row order via level scheduling */
+       PE_GS_ORDER_MULTICOLOR = 1   /* greedy first-fit colouring, colour by colour  */ };
+int pe_smoother_create(pe_ctx *ctx, pe_mat *A, int type, int sweeps, double damping,
+                       double omega, int cheby_order, double cheby_fraction,
+                       int gs_ordering, pe_smoother **out);
+/* x <- smoothed x (iterative_mode != 0) or smoother applied to zero initial guess */
+int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int iterative_mode);
+int pe_smoother_free(pe_smoother *s);
+/* introspection for parity tests: l1 norms, GS row order (sets concatenated),
+ * number of sets, Chebyshev eigenvalue estimates */
+int pe_smoother_get_l1(const pe_smoother *s, double *l1_host);
+int pe_smoother_get_order(const pe_smoother *s, int32_t *order_host, int32_t *num_sets,
+                          int32_t *set_starts_host /* num_sets+1, may be NULL */);
+int pe_smoother_get_eig(const pe_smoother *s, double *max_eig, double *min_eig);
+
+/* ---- K8/K9: sparse products
+ * C = A*B (mfem::ParMult / hypre_ParMatmul; SchurComplementFactory.cpp:51-166)
+ * Ac = P^T*A*P  (R == NULL)  or  R^T*A*P : mfem::RAP -> hypre_BoomerAMGBuildCoarseOperator,
+ *   Hierarchy.cpp:365,511-513; HiptmairSmootherFactory.cpp:160-161.
+ * Two-pass symbolic/numeric hash SpGEMM; rows of the result have ascending columns,
+ * explicit zeros are kept.
+ * pe_fix_zero_rows: hypre_ParCSRMatrixFixZeroRows (Hierarchy.cpp:366-371).
+ * pe_spadd: C = a*A + b*B, hypre_ParCSRMatrixAdd2 (src/hypreExtension/parcsr-add.c:199-245). */
+int pe_spgemm(pe_ctx *ctx, const pe_mat *A, const pe_mat *B, pe_mat **C);
+int pe_rap(pe_ctx *ctx, const pe_mat *R_or_null, const pe_mat *A, const pe_mat *P, pe_mat **Ac);
+int pe_fix_zero_rows(pe_ctx *ctx, pe_mat *A, int32_t *num_fixed);
+int pe_spadd(pe_ctx *ctx, double a, const pe_mat *A, double b, const pe_mat *B, pe_mat **C);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARELAG_B200_H */

@@ -1,0 +1,362 @@
+"""Oracle (TEST INFRASTRUCTURE ONLY) for ParElag's AMGe *solve* path.
+
+CPU restatement, single threaded and deterministic, of
+  * the V-cycle        src/linalg/solver_ops/ParELAG_Hierarchy.cpp:109-253
+  * the hierarchy      src/linalg/solver_ops/ParELAG_Hierarchy.cpp:282-383
+  * Hiptmair smoother  src/linalg/solver_ops/ParELAG_HiptmairSmoother.cpp:48-109,
+                       src/linalg/factories/ParELAG_HiptmairSmootherFactory.cpp:52-179
+  * hypre relaxation   behind src/linalg/solver_ops/ParELAG_HypreSmootherWrapper.cpp:20-35
+  * PCG                mfem::CGSolver::Mult behind src/linalg/solver_ops/ParELAG_KrylovSolver.cpp:23-96
+The arithmetic kernels are the plain-C functions of oracle/solve_oracle.c (hypre /
+MFEM algorithms restated from their published form -- those libraries are not
+vendored in the reference tree; "parity unpinned" at kernel level).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+may import this module.  The product (parelag_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libsolve_oracle.so")
+_lib = None
+
+
+def build():
+    src = os.path.join(_HERE, "solve_oracle.c")
+    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-shared",
+                               "-o", _SO, src, "-lm"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _csr(A):
+    A = A.tocsr()
+    return (A.shape[0], np.ascontiguousarray(A.indptr, dtype=np.int32),
+            np.ascontiguousarray(A.indices, dtype=np.int32),
+            np.ascontiguousarray(A.data, dtype=np.float64))
+
+
+def matvec(A, x, alpha=1.0, beta=0.0, y=None, threads=False):
+    n, I, J, D = _csr(A)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros(n) if y is None else np.ascontiguousarray(y, dtype=np.float64).copy()
+    f = lib().orc_csr_matvec_mt if threads else lib().orc_csr_matvec
+    f(n, _p(I), _p(J), _p(D), C.c_double(alpha), _p(x), C.c_double(beta), _p(y))
+    return y
+
+
+def matvec_t(A, x, alpha=1.0, beta=0.0, y=None):
+    n, I, J, D = _csr(A)
+    m = A.shape[1]
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros(m) if y is None else np.ascontiguousarray(y, dtype=np.float64).copy()
+    lib().orc_csr_matvec_t(n, m, _p(I), _p(J), _p(D), C.c_double(alpha), _p(x), C.c_double(beta), _p(y))
+    return y
+
+
+def l1_norms(A, option):
+    n, I, J, D = _csr(A)
+    l1 = np.empty(n)
+    lib().orc_l1_norms(n, _p(I), _p(J), _p(D), None, None, option, _p(l1))
+    return l1
+
+
+def greedy_colors(A):
+    """First-fit colouring, rows visited in natural order, smallest colour not used
+    by an already-coloured neighbour in the row pattern (spec shared with the GPU)."""
+    n, I, J, _ = _csr(A)
+    color = -np.ones(n, dtype=np.int32)
+    ncol = 0
+    mark = []
+    for i in range(n):
+        if len(mark) < ncol + 1:
+            mark += [-1] * (ncol + 1 - len(mark))
+        for j in J[I[i]:I[i + 1]]:
+            if j != i and color[j] >= 0:
+                mark[color[j]] = i
+        c = 0
+        while c < ncol and mark[c] == i:
+            c += 1
+        color[i] = c
+        if c == ncol:
+            ncol += 1
+    return color, ncol
+
+
+def multicolor_order(A):
+    color, ncol = greedy_colors(A)
+    return np.argsort(color, kind="stable").astype(np.int32), ncol
+
+
+def natural_levels(A):
+    """level(i) = 1 + max level(j), j<i coupled: the DAG schedule that reproduces a
+    sequential natural-order sweep."""
+    n, I, J, _ = _csr(A)
+    level = np.zeros(n, dtype=np.int32)
+    for i in range(n):
+        l = 0
+        for j in J[I[i]:I[i + 1]]:
+            if j < i and level[j] + 1 > l:
+                l = level[j] + 1
+        level[i] = l
+    return level
+
+
+def fix_zero_rows(A):
+    n, I, J, D = _csr(A)
+    D = D.copy()
+    nf = lib().orc_fix_zero_rows(n, _p(I), _p(J), _p(D), None, None)
+    return sp.csr_matrix((D, J, I), shape=A.shape), nf
+
+
+def spgemm(A, B):
+    """C = A*B with sorted columns, explicit zeros kept."""
+    n, AI, AJ, AA = _csr(A)
+    _, BI, BJ, BA = _csr(B)
+    CI = np.zeros(n + 1, dtype=np.int32)
+    nnz = lib().orc_spgemm_symbolic(n, _p(AI), _p(AJ), _p(BI), _p(BJ), B.shape[1], _p(CI))
+    CJ = np.zeros(max(nnz, 1), dtype=np.int32)
+    CA = np.zeros(max(nnz, 1))
+    lib().orc_spgemm_numeric(n, _p(AI), _p(AJ), _p(AA), _p(BI), _p(BJ), _p(BA), B.shape[1],
+                             _p(CI), _p(CJ), _p(CA))
+    return _raw_csr(CA[:nnz], CJ[:nnz], CI, (n, B.shape[1]))
+
+
+def _raw_csr(data, indices, indptr, shape):
+    # build without scipy's canonicalisation so explicit zeros / order survive
+    M = sp.csr_matrix(shape)
+    M.data, M.indices, M.indptr = data, indices, indptr
+    return M
+
+
+def transpose(A):
+    n, I, J, D = _csr(A)
+    m = A.shape[1]
+    TI = np.zeros(m + 1, dtype=np.int32)
+    TJ = np.zeros(max(len(J), 1), dtype=np.int32)
+    TA = np.zeros(max(len(J), 1))
+    lib().orc_csr_transpose(n, m, _p(I), _p(J), _p(D), _p(TI), _p(TJ), _p(TA))
+    return _raw_csr(TA[:len(J)], TJ[:len(J)], TI, (m, n))
+
+
+def rap(A, P, R=None):
+    """R^T A P (R = P when None): mfem::RAP, Hierarchy.cpp:365."""
+    Rt = transpose(P if R is None else R)
+    return spgemm(Rt, spgemm(A, P))
+
+
+def hypre_rand_vector(n, seed=1):
+    v = np.empty(n)
+    lib().orc_hypre_rand_vector(n, seed, _p(v))
+    return v
+
+
+class Smoother:
+    """mfem::HypreSmoother as configured by parelag::HypreSmootherWrapper."""
+
+    def __init__(self, A, type=2, sweeps=1, damping=1.0, omega=1.0, cheby_order=2,
+                 cheby_fraction=0.3, order=None):
+        self.A = A.tocsr()
+        self.n, self.I, self.J, self.D = _csr(self.A)
+        self.type, self.sweeps, self.w, self.omega = type, sweeps, damping, omega
+        l1opt = 0 if type in (0, 6, 16) else type
+        self.l1 = l1_norms(self.A, l1opt)
+        self.order = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+        self.rank_of_row = None
+        if self.order is not None:
+            self.rank_of_row = np.empty(self.n, dtype=np.int32)
+            self.rank_of_row[self.order] = np.arange(self.n, dtype=np.int32)
+        if type == 16:
+            self.max_eig, self.min_eig = self._eig_estimate_cg(10)
+            self.coefs = np.zeros(5)
+            self.cheby_order = lib().orc_cheby_coefs(C.c_double(self.max_eig), C.c_double(self.min_eig),
+                                                     C.c_double(cheby_fraction), cheby_order, _p(self.coefs))
+
+    def _eig_estimate_cg(self, max_iter):
+        """hypre_ParCSRMaxEigEstimateCG(A, scale=1, max_iter)."""
+        n = self.n
+        max_iter = min(max_iter, n)
+        ds = 1.0 / np.sqrt(self.A.diagonal())
+        r = hypre_rand_vector(n, 1)
+        tridiag = np.zeros(max_iter + 1)
+        trioffd = np.zeros(max_iter + 1)
+        gamma = float(r @ r)
+        p = None
+        for i in range(max_iter):
+            s = r.copy()
+            gamma_old = gamma
+            gamma = float(r @ s)
+            if i == 0:
+                beta = 1.0
+                p = s.copy()
+            else:
+                beta = gamma / gamma_old
+                p = s + beta * p
+            s = ds * matvec(self.A, ds * p)
+            sdotp = float(s @ p)
+            alpha = gamma / sdotp
+            alphainv = 1.0 / alpha
+            tridiag[i + 1] = alphainv
+            tridiag[i] *= beta
+            tridiag[i] += alphainv
+            trioffd[i + 1] = alphainv
+            trioffd[i] *= np.sqrt(beta)
+            r = r - alpha * s
+        T = np.diag(tridiag[:max_iter]) + np.diag(trioffd[1:max_iter], 1) + np.diag(trioffd[1:max_iter], -1)
+        ev = np.linalg.eigvalsh(T)
+        return float(ev[-1]), float(ev[0])
+
+    def apply(self, b, x, iterative_mode=True):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64).copy()
+        if not iterative_mode:
+            x[:] = 0.0
+        n = self.n
+        for _ in range(self.sweeps):
+            if self.type in (0, 1, 5):
+                v = np.empty(n)
+                lib().orc_relax_jacobi(n, _p(self.I), _p(self.J), _p(self.D), None, None, None,
+                                       _p(self.l1), C.c_double(self.w), _p(b), _p(x), None, _p(v))
+            elif self.type in (2, 4, 6):
+                uold = np.empty(n)
+                lib().orc_relax_gs(n, _p(self.I), _p(self.J), _p(self.D), None, None, None,
+                                   _p(self.l1), C.c_double(self.w), C.c_double(self.omega),
+                                   _p(self.order), _p(self.rank_of_row), _p(b), _p(x), None, _p(uold))
+            elif self.type == 16:
+                work = np.empty(5 * n)
+                lib().orc_relax_cheby(n, _p(self.I), _p(self.J), _p(self.D), _p(self.coefs),
+                                      self.cheby_order, _p(b), _p(x), _p(work))
+            else:
+                raise ValueError("unsupported smoother type %d" % self.type)
+        return x
+
+
+class Hiptmair:
+    """parelag::HiptmairSmoother (HiptmairSmoother.cpp:48-76): primary smooth, residual,
+    D^T r, auxiliary smooth from zero, x += D x_aux.  A_aux = D^T A D + FixZeroRows
+    (HiptmairSmootherFactory.cpp:143-165)."""
+
+    def __init__(self, A, D, primary_kw, aux_kw):
+        self.A, self.Dm = A.tocsr(), D.tocsr()
+        Aaux, _ = fix_zero_rows(rap(self.A, self.Dm))
+        self.A_aux = Aaux
+        self.primary = Smoother(self.A, **primary_kw(self.A))
+        self.aux = Smoother(self.A_aux, **aux_kw(self.A_aux))
+
+    def apply(self, b, x, iterative_mode=True):
+        if not iterative_mode:
+            x = np.zeros_like(x)
+        x = self.primary.apply(b, x, True)
+        r = matvec(self.A, x, alpha=-1.0, beta=1.0, y=b)
+        auxb = matvec_t(self.Dm, r)
+        auxx = self.aux.apply(auxb, np.zeros(self.Dm.shape[1]), False)
+        return x + matvec(self.Dm, auxx)
+
+
+class Hierarchy:
+    """parelag::Hierarchy: levels[l] = dict(A=, P= (to level l from l+1, stored on l+1
+    in the reference; here stored on the finer level l as 'P'), pre=, post=), coarsest
+    level has 'coarse'.  Mult == one V-cycle from a zero initial guess (Hierarchy.cpp:109-136)."""
+
+    def __init__(self, levels):
+        self.levels = levels
+
+    def iterate(self, rhs, sol, l=0):
+        L = self.levels[l]
+        if l == len(self.levels) - 1:
+            return L["coarse"](rhs, sol)
+        if L.get("pre") is not None:
+            sol = L["pre"].apply(rhs, sol, True)
+        resid = matvec(L["A"], sol, alpha=-1.0, beta=1.0, y=rhs)
+        crhs = matvec_t(L["P"], resid)
+        csol = self.iterate(crhs, np.zeros(L["P"].shape[1]), l + 1)
+        sol = sol + matvec(L["P"], csol)
+        if L.get("post") is not None:
+            sol = L["post"].apply(rhs, sol, True)
+        return sol
+
+    def mult(self, rhs):
+        return self.iterate(np.asarray(rhs, dtype=np.float64), np.zeros(len(rhs)), 0)
+
+
+def pcg(A, prec, b, rtol=1e-6, atol=1e-6, max_iter=300, x0=None):
+    """mfem::CGSolver::Mult (iterative_mode=false unless x0 is given).  Returns
+    (x, iterations, converged, history) with history[i] = (B r, r) after iteration
+    i (history[0] is the initial value) -- the quantity MFEM prints and the parity
+    contract compares."""
+    Amul = (lambda v: matvec(A, v)) if sp.issparse(A) else A
+    b = np.asarray(b, dtype=np.float64)
+    if x0 is None:
+        x = np.zeros_like(b)
+        r = b.copy()
+    else:
+        x = np.array(x0, dtype=np.float64)
+        r = b - Amul(x)
+    z = prec(r) if prec is not None else r.copy()
+    d = z.copy()
+    nom0 = nom = float(d @ r)
+    hist = [nom]
+    if nom < 0:
+        return x, 0, False, hist
+    r0 = max(nom * rtol * rtol, atol * atol)
+    if nom <= r0:
+        return x, 0, True, hist
+    z = Amul(d)
+    den = float(z @ d)
+    if den <= 0:
+        return x, 0, False, hist
+    i = 1
+    converged = False
+    while True:
+        alpha = nom / den
+        x = x + alpha * d
+        r = r - alpha * z
+        z = prec(r) if prec is not None else r.copy()
+        betanom = float(r @ z)
+        hist.append(betanom)
+        if betanom < r0:
+            converged = True
+            break
+        i += 1
+        if i > max_iter:
+            break
+        beta = betanom / nom
+        d = z + beta * d
+        z = Amul(d)
+        den = float(d @ z)
+        if den <= 0:
+            break
+        nom = betanom
+    return x, min(i, max_iter), converged, hist
+
+
+def build_hierarchy(A0, Ps, make_smoother, make_coarse):
+    """buildHierarchyFromDeRhamSequence (Hierarchy.cpp:282-383): A_{l+1} = P_l^T A_l P_l,
+    then FixZeroRows; smoothers per AMGeSolverFactory.cpp:74-166."""
+    levels = []
+    A = A0.tocsr()
+    for l, P in enumerate(Ps):
+        levels.append({"A": A, "P": P.tocsr()})
+        A, _ = fix_zero_rows(rap(A, P.tocsr()))
+    levels.append({"A": A})
+    for l, L in enumerate(levels[:-1]):
+        L["pre"] = make_smoother(l, L["A"])
+        L["post"] = L["pre"]
+    levels[-1]["coarse"] = make_coarse(levels[-1]["A"])
+    return Hierarchy(levels)

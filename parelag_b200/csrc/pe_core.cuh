@@ -1,0 +1,112 @@
+// pe_core.cuh -- internal structures shared by the CUDA translation units.
+// Data layout in HBM: every ParCSR matrix is two CSR blocks
+// (diag: owned columns, offd: compressed ghost columns) with int32 indices and FP64
+// values, plus device-resident halo index lists.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/parelag_b200.h"
+
+#define PE_SM_COUNT 148
+
+void pe_set_error(const std::string &msg);
+
+#define PE_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            pe_set_error(std::string(#call) + " failed: " + cudaGetErrorString(e_) \
+                         + " at " + __FILE__ + ":" + std::to_string(__LINE__));    \
+            return 1;                                                              \
+        }                                                                          \
+    } while (0)
+
+#define PE_CHECK(cond, msg)                                     \
+    do {                                                        \
+        if (!(cond)) {                                          \
+            pe_set_error(std::string(msg) + " (" #cond ")");    \
+            return 2;                                           \
+        }                                                       \
+    } while (0)
+
+#define PE_TRY(expr)              \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_) return rc_;      \
+    } while (0)
+
+// count one kernel launch on ctx and check the launch status
+#define PE_LAUNCHED(ctx)                                     \
+    do {                                                     \
+        (ctx)->launches++;                                   \
+        PE_CUDA(cudaPeekAtLastError());                      \
+    } while (0)
+
+struct pe_ctx {
+    int rank = 0, nranks = 1, device = 0;
+    cudaStream_t stream = nullptr;       // compute stream
+    cudaStream_t comm_stream = nullptr;  // halo exchange stream
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
+    void *nccl = nullptr;                // ncclComm_t (opaque; resolved by dlopen)
+    int64_t launches = 0;
+    double *partials_d = nullptr;        // reduction scratch (PE_MAX_PARTIALS doubles)
+    double *scalar_d = nullptr;          // 8 device scalars
+    double *scalar_h = nullptr;          // pinned host mirror
+    void *flush_d = nullptr;
+    size_t flush_bytes = 0;
+    bool capturing = false;
+};
+#define PE_MAX_PARTIALS 4096
+
+struct DevCSR {
+    int32_t nrows = 0, ncols = 0;
+    int64_t nnz = 0;
+    int32_t *I = nullptr, *J = nullptr;
+    double *A = nullptr;
+};
+int devcsr_alloc(DevCSR &m, int32_t nrows, int32_t ncols, int64_t nnz);
+void devcsr_free(DevCSR &m);
+
+struct pe_vec {
+    pe_ctx *ctx;
+    int64_t n;
+    double *d;
+};
+
+struct pe_mat {
+    pe_ctx *ctx = nullptr;
+    int64_t global_num_rows = 0, global_num_cols = 0, first_row_index = 0, first_col_diag = 0;
+    DevCSR diag, offd;
+    std::vector<int64_t> col_map_offd;
+    // comm package (host copies + device send map)
+    std::vector<int32_t> send_procs, send_map_starts, send_map_elmts, recv_procs, recv_vec_starts;
+    int32_t *send_map_d = nullptr;
+    double *send_buf_d = nullptr;
+    double *x_ext_d = nullptr;
+    pe_mat *T = nullptr;     // cached explicit transpose (owned)
+    int tpr = 0;             // threads per row chosen for SpMV (power of two <= 32)
+};
+
+// ---- internal helpers used across translation units
+int pe_halo_exchange(pe_mat *A, const double *x_d);   // fills A->x_ext_d (no-op single rank)
+int pe_halo_wait(pe_mat *A);                           // compute stream waits for halo
+int pe_devcsr_transpose(pe_ctx *ctx, const DevCSR &A, DevCSR &T);
+int pe_devcsr_spgemm(pe_ctx *ctx, const DevCSR &A, const DevCSR &B, DevCSR &C);
+int pe_choose_tpr(int64_t nnz, int32_t nrows);
+int pe_mat_wrap_local(pe_ctx *ctx, DevCSR &diag, pe_mat **out);  // takes ownership of diag
+int pe_allreduce_sum(pe_ctx *ctx, double *d, int count);
+
+// spmv launcher on raw pointers: yout = alpha*(diag*x + offd*xext) + beta*yin
+int pe_launch_spmv(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, int tpr,
+                   double alpha, const double *x, const double *xext,
+                   double beta, const double *yin, double *yout);
+
+static inline int pe_grid_for(int64_t work_items, int per_block)
+{
+    int64_t g = (work_items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    return (int)g;
+}
