@@ -1,0 +1,1205 @@
+"""Oracle (TEST INFRASTRUCTURE ONLY) for ParElag's AMGe *coarsen* path.
+
+CPU restatement in numpy/scipy (+ LAPACK dsytrf/dsytrs/dgesvd/dgetrf/dgetrs through
+scipy, the same routines the reference calls) of
+
+  * AgglomeratedTopology::CoarsenLocalPartitioning   src/topology/Topology.cpp:685-828
+    with findMinimalIntersectionSets               src/structures/minimalIntersectionSet.cpp:43-130
+  * MFEMRefinedMeshPartitioner::Partition            src/partitioning/MFEMRefinedMeshPartitioner.cpp:48-90
+  * DofAgglomeration                                 src/amge/DOFAgglomeration.cpp:33-315,503-645
+  * DofHandlerALG numbering / tables                 src/amge/DofHandler.cpp:694-1463
+  * DeRhamSequence::Coarsen and helpers              src/amge/DeRhamSequence.cpp:572-692,1416-3048
+  * FacetSaddlePoint / RidgePeakSaddlePoint          src/linalg/solver_core/ParELAG_SaddlePointSolver.cpp:49-189
+  * CochainProjector                                 src/amge/CochainProjector.cpp:53-261,416-441
+  * SVD_Calculator::ComputeON, Deflate               src/linalg/dense/ParELAG_SVDCalculator.cpp:192-284,
+                                                     src/linalg/dense/ParELAG_InnerProduct.cpp:157-169
+  * ComputeTrueP / ComputeTrueD / GetP(ess)          src/amge/DeRhamSequence.cpp:1082-1253
+  * the fine level (DeRhamSequence3D_FE for lowest-order spaces on an axis-aligned
+    structured hexahedral mesh: H1 / Nedelec / Raviart-Thomas / L2 with MFEM's dof
+    conventions -- point values, circulations, fluxes, cell values)
+                                                     src/amge/DeRhamSequenceFE.cpp:184-227,311-335,633-722,799-925
+
+Numbering conventions are this oracle's own and documented here (MFEM's mesh
+numbering is not reproducible offline): entities of the structured
+mesh are numbered lexicographically with x fastest; all topology / dof tables are
+kept in canonical CSR form (ascending column indices per row); agglomerates are
+numbered lexicographically on the derefined grid.  Integer parity of the CUDA path is
+checked against THESE tables.
+
+PARITY PIN: `upscaling_errors()` reproduces the reference's numbering- and
+sign-invariant golden values of testsuite/CMakeLists.txt:114-176 (form0, form1,
+form2); see tests/test_oracle_goldens.py.
+
+SVD sign convention (both oracle and CUDA path): every retained left singular vector
+is scaled so that its largest-magnitude entry (first one on ties) is positive.
+
+Single rank only: dof == true dof (SharingMap is the identity).
+"""
+import numpy as np
+import scipy.sparse as sp
+from scipy.linalg import lapack
+
+RANGET, NULLSPACE = 1, 2
+M1D = np.array([[1.0 / 3.0, 1.0 / 6.0], [1.0 / 6.0, 1.0 / 3.0]])
+
+
+# ----------------------------------------------------------------------------
+# small sparse helpers (canonical CSR)
+# ----------------------------------------------------------------------------
+def _canon(A):
+    A = sp.csr_matrix(A)
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
+
+
+def mult_orientation(A, B):
+    """TopologyTable MultOrientation: product, drop |.|<1e-10, keep the sign
+    (src/topology/TopologyTable.cpp:130-139)."""
+    C = _canon(A @ B)
+    C.data[np.abs(C.data) < 1e-10] = 0.0
+    C.eliminate_zeros()
+    C.data = np.sign(C.data)
+    return C
+
+
+def row(A, i):
+    return A.indices[A.indptr[i]:A.indptr[i + 1]]
+
+
+def rowvals(A, i):
+    return A.data[A.indptr[i]:A.indptr[i + 1]]
+
+
+def block_diag_csr(blocks):
+    """ElementalMatricesContainer::GetAsSparseMatrix
+    (src/amge/ElementalMatricesContainer.cpp:55-212): one dense block per entity."""
+    sizes = np.array([b.shape[0] for b in blocks], dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    n = int(offs[-1])
+    if n == 0:
+        return sp.csr_matrix((0, 0))
+    rows, cols, vals = [], [], []
+    for b, o in zip(blocks, offs[:-1]):
+        m = b.shape[0]
+        if m == 0:
+            continue
+        r, c = np.meshgrid(np.arange(m), np.arange(m), indexing="ij")
+        rows.append((r + o).ravel())
+        cols.append((c + o).ravel())
+        vals.append(np.asarray(b, dtype=np.float64).ravel())
+    M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+    return M
+
+
+# ----------------------------------------------------------------------------
+# topology
+# ----------------------------------------------------------------------------
+def find_minimal_intersection_sets(Z, skip_diag_less_than=0.5):
+    """findMinimalIntersectionSets: entity x MIS table with +-1 orientation."""
+    tol = 1e-10
+    Z = _canon(Z)
+    n = Z.shape[0]
+    diag = Z.diagonal()
+    member = diag - skip_diag_less_than > -tol
+    mis_of = -np.ones(n, dtype=np.int64)
+    sign_of = np.zeros(n)
+    cur = 0
+    for i in range(n):
+        if member[i] and mis_of[i] == -1:
+            Zii = diag[i]
+            cols, vals = row(Z, i), rowvals(Z, i)
+            for j, Zij in zip(cols, vals):
+                if abs(diag[j] - Zii) < tol and (abs(Zij - Zii) < tol or abs(Zij + Zii) < tol):
+                    mis_of[j] = cur
+                    sign_of[j] = Zij / Zii
+            cur += 1
+    idx = np.nonzero(mis_of >= 0)[0]
+    return _canon(sp.csr_matrix((sign_of[idx], (idx, mis_of[idx])), shape=(n, cur)))
+
+
+class Topology:
+    """AgglomeratedTopology: B[c] = signed incidence (entities of codim c) x (codim c+1)."""
+
+    def __init__(self, B, facet_bdr=None, ndim=3):
+        self.ndim = ndim
+        self.B = [_canon(b) for b in B]
+        self.n = [self.B[0].shape[0]] + [b.shape[1] for b in self.B]
+        self.facet_bdr = None if facet_bdr is None else _canon(facet_bdr)
+        self.AE_entity = None       # set on the FINE topology by coarsen()
+        self.coarser = None
+        self.partition = None
+        self._conn = {}
+
+    def conn(self, big, small):
+        """GetConnectivity(big, small): boolean entity->sub-entity table."""
+        if (big, small) not in self._conn:
+            C = abs(self.B[big])
+            for c in range(big + 1, small):
+                C = C @ abs(self.B[c])
+            C = _canon(C)
+            C.data[:] = 1.0
+            self._conn[(big, small)] = C
+        return self._conn[(big, small)]
+
+    def coarsen(self, partition):
+        """CoarsenLocalPartitioning(partition, check_topology=0, preserve_material=0)."""
+        partition = np.asarray(partition, dtype=np.int64)
+        nAE = int(partition.max()) + 1
+        self.partition = partition
+        AE_el = _canon(sp.csr_matrix((np.ones(len(partition)), (partition, np.arange(len(partition)))),
+                                     shape=(nAE, len(partition))))
+        AEe = [AE_el]
+        cB = []
+        for icodim in range(self.ndim):
+            AE_fc = mult_orientation(AEe[icodim], self.B[icodim])
+            Z = _canon(AE_fc.T @ AE_fc)
+            if icodim == 0 and self.facet_bdr is not None:
+                Z = _canon(Z + self.facet_bdr @ self.facet_bdr.T)
+            fc_AF = find_minimal_intersection_sets(Z, 0.5)
+            AEe.append(_canon(fc_AF.T))
+            cB.append(mult_orientation(AE_fc, fc_AF))
+        cbdr = None
+        if self.facet_bdr is not None:
+            cbdr = mult_orientation(AEe[1], self.facet_bdr)
+        self.AE_entity = AEe
+        self.coarser = Topology(cB, cbdr, self.ndim)
+        return self.coarser
+
+
+def refined_partition(dims_fine):
+    """MFEMRefinedMeshPartitioner: agglomerate = parent element of one uniform
+    refinement.  On the lexicographic structured grid: AE(i,j,k) = (i//2, j//2, k//2)."""
+    nx, ny, nz = dims_fine
+    assert nx % 2 == 0 and ny % 2 == 0 and nz % 2 == 0
+    cx, cy = nx // 2, ny // 2
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    return (((k // 2) * cy + (j // 2)) * cx + (i // 2)).ravel()
+
+
+# ----------------------------------------------------------------------------
+# structured hexahedral mesh + lowest-order fine de Rham sequence
+# ----------------------------------------------------------------------------
+class HexMesh:
+    """nx x ny x nz axis-aligned cells of size (hx,hy,hz) on [0,Lx]x[0,Ly]x[0,Lz].
+    Numbering (x fastest): element (i,j,k) -> i + nx*(j + ny*k);
+    facets: x-normal faces, then y-normal, then z-normal; ridges: x-, y-, z-edges;
+    peaks: vertices.  Global orientation of every facet/ridge is the positive axis.
+    Boundary attributes follow mfem::Mesh::Make3D: z=0:1, y=0:2, x=L:3, y=L:4, x=0:5, z=L:6."""
+
+    def __init__(self, nx, ny, nz, L=(1.0, 1.0, 1.0)):
+        self.dims = (nx, ny, nz)
+        self.h = (L[0] / nx, L[1] / ny, L[2] / nz)
+        self.nel = nx * ny * nz
+        self.nf = ((nx + 1) * ny * nz, nx * (ny + 1) * nz, nx * ny * (nz + 1))
+        self.ne = (nx * (ny + 1) * (nz + 1), (nx + 1) * ny * (nz + 1), (nx + 1) * (ny + 1) * nz)
+        self.nv = (nx + 1) * (ny + 1) * (nz + 1)
+
+    # -- index maps
+    def el(self, i, j, k):
+        nx, ny, nz = self.dims
+        return i + nx * (j + ny * k)
+
+    def fx(self, i, j, k):
+        nx, ny, nz = self.dims
+        return i + (nx + 1) * (j + ny * k)
+
+    def fy(self, i, j, k):
+        nx, ny, nz = self.dims
+        return self.nf[0] + i + nx * (j + (ny + 1) * k)
+
+    def fz(self, i, j, k):
+        nx, ny, nz = self.dims
+        return self.nf[0] + self.nf[1] + i + nx * (j + ny * k)
+
+    def ex(self, i, j, k):
+        nx, ny, nz = self.dims
+        return i + nx * (j + (ny + 1) * k)
+
+    def ey(self, i, j, k):
+        nx, ny, nz = self.dims
+        return self.ne[0] + i + (nx + 1) * (j + ny * k)
+
+    def ez(self, i, j, k):
+        nx, ny, nz = self.dims
+        return self.ne[0] + self.ne[1] + i + (nx + 1) * (j + (ny + 1) * k)
+
+    def vx(self, i, j, k):
+        nx, ny, nz = self.dims
+        return i + (nx + 1) * (j + (ny + 1) * k)
+
+    def _grid(self, ni, nj, nk):
+        k, j, i = np.meshgrid(np.arange(nk), np.arange(nj), np.arange(ni), indexing="ij")
+        return i.ravel(), j.ravel(), k.ravel()
+
+    def topology(self):
+        nx, ny, nz = self.dims
+        nf, ne = sum(self.nf), sum(self.ne)
+        # B0: element x facet, +1 if the facet's +axis normal points out of the element
+        i, j, k = self._grid(nx, ny, nz)
+        e = self.el(i, j, k)
+        r = np.concatenate([e] * 6)
+        c = np.concatenate([self.fx(i, j, k), self.fx(i + 1, j, k), self.fy(i, j, k), self.fy(i, j + 1, k),
+                            self.fz(i, j, k), self.fz(i, j, k + 1)])
+        v = np.concatenate([-np.ones(len(e)), np.ones(len(e))] * 3)
+        B0 = sp.csr_matrix((v, (r, c)), shape=(self.nel, nf))
+        # B1: facet x ridge (discrete curl): right-hand rule around the +axis normal
+        rows, cols, vals = [], [], []
+
+        def add(f, edges_signs):
+            for ed, s in edges_signs:
+                rows.append(f); cols.append(ed); vals.append(np.full(len(f), s))
+        i, j, k = self._grid(nx + 1, ny, nz)      # x-faces: dEz/dy - dEy/dz
+        add(self.fx(i, j, k), [(self.ez(i, j + 1, k), 1.0), (self.ez(i, j, k), -1.0),
+                               (self.ey(i, j, k + 1), -1.0), (self.ey(i, j, k), 1.0)])
+        i, j, k = self._grid(nx, ny + 1, nz)      # y-faces: dEx/dz - dEz/dx
+        add(self.fy(i, j, k), [(self.ex(i, j, k + 1), 1.0), (self.ex(i, j, k), -1.0),
+                               (self.ez(i + 1, j, k), -1.0), (self.ez(i, j, k), 1.0)])
+        i, j, k = self._grid(nx, ny, nz + 1)      # z-faces: dEy/dx - dEx/dy
+        add(self.fz(i, j, k), [(self.ey(i + 1, j, k), 1.0), (self.ey(i, j, k), -1.0),
+                               (self.ex(i, j + 1, k), -1.0), (self.ex(i, j, k), 1.0)])
+        B1 = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nf, ne))
+        # B2: ridge x peak (discrete gradient): -1 at the tail, +1 at the head
+        rows, cols, vals = [], [], []
+        i, j, k = self._grid(nx, ny + 1, nz + 1)
+        rows += [self.ex(i, j, k)] * 2; cols += [self.vx(i, j, k), self.vx(i + 1, j, k)]
+        vals += [-np.ones(len(i)), np.ones(len(i))]
+        i, j, k = self._grid(nx + 1, ny, nz + 1)
+        rows += [self.ey(i, j, k)] * 2; cols += [self.vx(i, j, k), self.vx(i, j + 1, k)]
+        vals += [-np.ones(len(i)), np.ones(len(i))]
+        i, j, k = self._grid(nx + 1, ny + 1, nz)
+        rows += [self.ez(i, j, k)] * 2; cols += [self.vx(i, j, k), self.vx(i, j, k + 1)]
+        vals += [-np.ones(len(i)), np.ones(len(i))]
+        B2 = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(ne, self.nv))
+        # facet -> boundary attribute (0-based column = attribute-1)
+        rows, cols = [], []
+        j, k = np.meshgrid(np.arange(ny), np.arange(nz), indexing="ij")
+        rows += [self.fx(0, j.ravel(), k.ravel()), self.fx(nx, j.ravel(), k.ravel())]
+        cols += [np.full(j.size, 4), np.full(j.size, 2)]
+        i, k = np.meshgrid(np.arange(nx), np.arange(nz), indexing="ij")
+        rows += [self.fy(i.ravel(), 0, k.ravel()), self.fy(i.ravel(), ny, k.ravel())]
+        cols += [np.full(i.size, 1), np.full(i.size, 3)]
+        i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        rows += [self.fz(i.ravel(), j.ravel(), 0), self.fz(i.ravel(), j.ravel(), nz)]
+        cols += [np.full(i.size, 0), np.full(i.size, 5)]
+        rows, cols = np.concatenate(rows), np.concatenate(cols)
+        fbdr = sp.csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(nf, 6))
+        return Topology([B0, B1, B2], fbdr, 3)
+
+    def facet_area(self):
+        hx, hy, hz = self.h
+        return np.concatenate([np.full(self.nf[0], hy * hz), np.full(self.nf[1], hx * hz), np.full(self.nf[2], hx * hy)])
+
+    def ridge_length(self):
+        hx, hy, hz = self.h
+        return np.concatenate([np.full(self.ne[0], hx), np.full(self.ne[1], hy), np.full(self.ne[2], hz)])
+
+    def vertex_coords(self):
+        nx, ny, nz = self.dims
+        i, j, k = self._grid(nx + 1, ny + 1, nz + 1)
+        return np.stack([i * self.h[0], j * self.h[1], k * self.h[2]], axis=1)
+
+
+class DofHandler:
+    """Common part of DofHandlerFE / DofHandlerALG: entity_dof[c] for c <= max_codim_base."""
+
+    def __init__(self, max_codim_base, topo):
+        self.mcb = max_codim_base
+        self.topo = topo
+        self.entity_dof = [None] * (max_codim_base + 1)
+        self.ndofs = 0
+        # ALG only
+        self.dof_type = None
+        self.n_rangeT = [None] * (max_codim_base + 1)
+        self.n_null = [None] * (max_codim_base + 1)
+        self.int_offsets = [None] * (max_codim_base + 1)
+        self.type_ndofs = [0] * (max_codim_base + 2)
+
+    # ---- ALG (src/amge/DofHandler.cpp:878-1460)
+    def alg_init(self):
+        for c in range(self.mcb + 1):
+            self.n_rangeT[c] = np.zeros(self.topo.n[c], dtype=np.int64)
+            self.n_null[c] = np.zeros(self.topo.n[c], dtype=np.int64)
+        self.dof_type = {}
+
+    def build_entity_dof_table(self, c):
+        """computeOffset(c) + build{Peak,Ridge,Facet,Element}DofTable."""
+        counts = self.n_rangeT[c] + self.n_null[c]
+        start = self.type_ndofs[c + 1] if c < self.mcb else 0
+        assert self.ndofs == start
+        offs = start + np.concatenate([[0], np.cumsum(counts)])
+        self.int_offsets[c] = offs
+        self.ndofs = int(offs[-1])
+        self.type_ndofs[c] = self.ndofs
+        nent = self.topo.n[c]
+        rows, cols = [], []
+        for small in range(self.mcb, c, -1):     # PEAK first ... down to c+1
+            C = self.topo.conn(c, small)
+            so = self.int_offsets[small]
+            for e in range(nent):
+                for s in row(C, e):
+                    cols.extend(range(so[s], so[s + 1]))
+                    rows.extend([e] * int(so[s + 1] - so[s]))
+        for e in range(nent):
+            cols.extend(range(offs[e], offs[e + 1]))
+            rows.extend([e] * int(offs[e + 1] - offs[e]))
+        # rows keep the reference order [lower-dimensional carriers ..., own interior];
+        # with canonical conn tables this order is ascending
+        M = sp.csr_matrix((np.ones(len(rows)), (np.array(rows, dtype=np.int64), np.array(cols, dtype=np.int64))),
+                          shape=(nent, self.ndofs))
+        self.entity_dof[c] = _canon(M)
+        for cc in range(c + 1, self.mcb + 1):   # widen earlier tables
+            self.entity_dof[cc] = sp.csr_matrix((self.entity_dof[cc].data, self.entity_dof[cc].indices,
+                                                 self.entity_dof[cc].indptr), shape=(self.topo.n[cc], self.ndofs))
+
+    def interior_dofs(self, c, e):
+        o = self.int_offsets[c]
+        return np.arange(o[e], o[e + 1])
+
+    def dofs_on_bdr(self, c, e):
+        out = []
+        for small in range(self.mcb, c, -1):
+            for s in row(self.topo.conn(c, small), e):
+                out.extend(self.interior_dofs(small, s))
+        return np.array(out, dtype=np.int64)
+
+    def rangeT_dofs(self, c, e):
+        return [d for d in self.interior_dofs(c, e) if self.dof_type[d] == RANGET]
+
+    def null_dofs(self, c, e):
+        return [d for d in self.interior_dofs(c, e) if self.dof_type[d] == NULLSPACE]
+
+    def mark_bdr_dofs(self, ess_attr):
+        """MarkDofsOnSelectedBndr (DofHandler.cpp:812-853): dofs of facets whose boundary
+        attribute is selected.  (For the FE level MFEM's GetEssentialVDofs marks the same
+        set: all dofs in the closure of selected boundary faces.)"""
+        marker = np.zeros(self.ndofs, dtype=bool)
+        fb = self.topo.facet_bdr
+        ess_attr = np.asarray(ess_attr)
+        FD = self.entity_dof[1] if self.mcb >= 1 else None
+        if FD is None:
+            return marker
+        for f in range(fb.shape[0]):
+            a = row(fb, f)
+            if len(a) == 1 and ess_attr[a[0]]:
+                marker[row(FD, f)] = True
+        return marker
+
+
+class DofAgg:
+    """DofAgglomeration (DOFAgglomeration.cpp:33-315): AE -> dof rows with interior dofs
+    first (sorted by (separator type, dof id)); ADof = position in that CSR."""
+
+    def __init__(self, topo, dof):
+        self.topo, self.dof = topo, dof
+        ncod = dof.mcb + 1
+        AE_dof = [_canon(abs(topo.AE_entity[c]) @ abs(dof.entity_dof[c])) for c in range(ncod)]
+        sep = np.zeros(dof.ndofs, dtype=np.int64)
+        for c in range(1, ncod):
+            sep[AE_dof[c].indices] = c
+        self.sep = sep
+        self.I, self.J, self.nint = [], [], []
+        for c in range(ncod):
+            A = AE_dof[c]
+            J = A.indices.copy()
+            nint = np.zeros(A.shape[0], dtype=np.int64)
+            for a in range(A.shape[0]):
+                s, e = A.indptr[a], A.indptr[a + 1]
+                r = J[s:e]
+                if dof.mcb > c:
+                    order = np.lexsort((r, sep[r]))
+                    J[s:e] = r[order]
+                    nint[a] = int(np.sum(sep[r] == c))
+                else:
+                    nint[a] = e - s
+            self.I.append(A.indptr.astype(np.int64))
+            self.J.append(J.astype(np.int64))
+            self.nint.append(nint)
+        self._adof_rdof = {}
+
+    def nAE(self, c):
+        return len(self.I[c]) - 1
+
+    def rng(self, c, a):
+        """(start, start+nint, end) in ADof numbering."""
+        return int(self.I[c][a]), int(self.I[c][a] + self.nint[c][a]), int(self.I[c][a + 1])
+
+    def dofs(self, c, a):
+        s, m, e = self.rng(c, a)
+        return self.J[c][s:m], self.J[c][m:e]
+
+    def adof_dof(self, c):
+        n = len(self.J[c])
+        return sp.csr_matrix((np.ones(n), (np.arange(n), self.J[c])), shape=(n, self.dof.ndofs))
+
+    def adof_rdof(self, c):
+        """ADof_rDof: couples each agglomerated dof with the repeated dofs (entity-local
+        copies) of the fine entities that make up the agglomerate."""
+        if c in self._adof_rdof:
+            return self._adof_rdof[c]
+        ED = self.dof.entity_dof[c]
+        AEe = self.topo.AE_entity[c]
+        nrd = ED.nnz
+        ent_of_rdof = np.repeat(np.arange(ED.shape[0]), np.diff(ED.indptr))
+        AE_of_ent = -np.ones(ED.shape[0], dtype=np.int64)
+        ae_rows = np.repeat(np.arange(AEe.shape[0]), np.diff(AEe.indptr))
+        AE_of_ent[AEe.indices] = ae_rows
+        AE_of_rdof = AE_of_ent[ent_of_rdof]
+        keep = AE_of_rdof >= 0
+        nd = self.dof.ndofs
+        key_adof = np.repeat(np.arange(self.nAE(c)), np.diff(self.I[c])) * nd + self.J[c]
+        order = np.argsort(key_adof)
+        key_r = AE_of_rdof[keep] * nd + ED.indices[keep]
+        pos = np.searchsorted(key_adof[order], key_r)
+        adof = order[pos]
+        assert np.all(key_adof[adof] == key_r)
+        M = sp.csr_matrix((ED.data[keep], (adof, np.nonzero(keep)[0])), shape=(len(self.J[c]), nrd))
+        self._adof_rdof[c] = M
+        return M
+
+    def assemble_agg_matrix(self, c, M_e, other=None):
+        """AssembleAgglomerateMatrix: ADof_rDof * M_e * ADof_rDof^T (block diagonal)."""
+        R = self.adof_rdof(c)
+        Pm = (other or self).adof_rdof(c)
+        return _canon(R @ M_e @ Pm.T)
+
+    @staticmethod
+    def distribute(c, D_g, rng_agg, dom_agg):
+        """DistributeAgglomerateMatrix(range!=null, domain!=null) -> Distribute():
+        per-AE blocks D_g[AE range dofs, AE domain dofs] in ADof numbering."""
+        R, Cm = rng_agg.adof_dof(c), dom_agg.adof_dof(c)
+        T = (R @ D_g @ Cm.T).tocoo()
+        ae_r = np.repeat(np.arange(rng_agg.nAE(c)), np.diff(rng_agg.I[c]))
+        ae_c = np.repeat(np.arange(dom_agg.nAE(c)), np.diff(dom_agg.I[c]))
+        keep = ae_r[T.row] == ae_c[T.col]
+        return _canon(sp.csr_matrix((T.data[keep], (T.row[keep], T.col[keep])), shape=T.shape))
+
+
+# ----------------------------------------------------------------------------
+# dense helpers
+# ----------------------------------------------------------------------------
+def fix_sign(U):
+    """Canonical sign: largest-magnitude entry of each column positive (first on ties)."""
+    U = np.array(U, dtype=np.float64, copy=True)
+    for j in range(U.shape[1]):
+        col = U[:, j]
+        if col.size == 0:
+            continue
+        p = int(np.argmax(np.abs(col)))
+        if col[p] < 0:
+            U[:, j] = -col
+    return U
+
+
+def svd_on(A):
+    """SVD_Calculator::ComputeON (dgesvd JOBU='O', JOBVT='N'): returns (U, s) with
+    min(m,n) columns, canonical sign."""
+    A = np.asarray(A, dtype=np.float64)
+    if A.shape[0] == 0 or A.shape[1] == 0:
+        return np.zeros((A.shape[0], 0)), np.zeros(0)
+    u, s, vt, info = lapack.dgesvd(A, compute_uv=1, full_matrices=0)
+    assert info == 0
+    return fix_sign(u), s
+
+
+def svd_on_weighted(M, A):
+    """ComputeON(sqrt_w, A, s) for diagonal M, ComputeON(W, A, s) (symmetric square
+    root through dsyev) otherwise (SVDCalculator.cpp:247-284)."""
+    offd = M - np.diag(np.diag(M))
+    if not np.any(offd):
+        w = np.sqrt(np.diag(M))
+        U, s = svd_on(A * w[:, None])
+        return fix_sign(U / w[:, None]), s
+    ev, V = np.linalg.eigh(M)
+    sq = np.sqrt(ev)
+    X = (V * sq) @ V.T
+    U, s = svd_on(X @ A)
+    Xi = (V / sq) @ V.T
+    return fix_sign(Xi @ U), s
+
+
+class LDL:
+    """LDLCalculator: dsytrf('L') / dsytrs (src/linalg/dense/ParELAG_LDLCalculator.cpp:32-93)."""
+
+    def __init__(self, A):
+        self.n = A.shape[0]
+        if self.n:
+            self.ldu, self.ipiv, info = lapack.dsytrf(np.asfortranarray(A), lower=1)
+            assert info == 0, "LDL factorization failed (singular local saddle point?)"
+
+    def solve(self, rhs):
+        if self.n == 0 or rhs.shape[1] == 0:
+            return np.zeros_like(rhs)
+        x, info = lapack.dsytrs(self.ldu, self.ipiv, np.asfortranarray(rhs), lower=1)
+        assert info == 0
+        return x
+
+
+def dof_functional(Ploc, Mii):
+    """CochainProjector::CreateDofFunctional: (P^T M P)^{-1} P^T M via dgetrf/dgetrs."""
+    nc = Ploc.shape[1]
+    if nc == 0:
+        return np.zeros((0, Ploc.shape[0]))
+    MlP = Mii @ Ploc
+    cM = Ploc.T @ MlP
+    lu, piv, info = lapack.dgetrf(np.asfortranarray(cM))
+    assert info == 0
+    x, info = lapack.dgetrs(lu, piv, np.asfortranarray(MlP.T))
+    assert info == 0
+    return x
+
+
+# ----------------------------------------------------------------------------
+# de Rham sequence
+# ----------------------------------------------------------------------------
+class Sequence:
+    """One level of the de Rham sequence (DeRhamSequenceFE on level 0, DeRhamSequenceAlg
+    below).  M[(j,c)] is the DG-like mass matrix of form j on entities of codim c in rDof
+    numbering; D[j] maps form j -> j+1; P[j]/Pi[j] connect to the coarser level."""
+
+    def __init__(self, topo, nforms=4):
+        self.topo = topo
+        self.nforms = nforms
+        self.ndim = nforms - 1
+        self.jstart = 0
+        self.dof = [None] * nforms
+        self.D = [None] * (nforms - 1)
+        self.M = {}
+        self.targets = [None] * nforms
+        self.P = [None] * nforms
+        self.Pi = [None] * nforms
+        self.l2_const = None
+        self.svd_tol = 1e-9
+        self.smallest_entry = np.finfo(float).eps
+        self.coarser = None
+        self.finer = None
+        self.mesh = None       # fine level only
+        self.stats = {}
+
+    # --- operators handed to the solver layer
+    def mass_operator(self, j):
+        """ComputeMassOperator(j): assemble the element mass matrices, rDof_dof^T M_e rDof_dof
+        (DofHandler.cpp:270-281)."""
+        ED = self.dof[j].entity_dof[0]
+        n = ED.nnz
+        R = sp.csr_matrix((ED.data, (np.arange(n), ED.indices)), shape=(n, self.dof[j].ndofs))
+        return _canon(R.T @ self.M[(j, 0)] @ R)
+
+    def get_P(self, j, ess_attr=None):
+        """GetP(j, ess): copy of P with the columns of essential COARSE dofs zeroed; the
+        zeros stay in the pattern (SparseMatrix::EliminateCols)."""
+        P = self.P[j].copy()
+        if ess_attr is not None:
+            marker = self.coarser.dof[j].mark_bdr_dofs(ess_attr)
+            P.data[marker[P.indices]] = 0.0
+        return P
+
+    def get_D(self, j, ess_attr=None):
+        D = self.D[j].copy()
+        if ess_attr is not None:
+            marker = self.dof[j].mark_bdr_dofs(ess_attr)
+            D.data[marker[D.indices]] = 0.0
+        return D
+
+    # --- PV traces
+    def pv_traces(self, c):
+        j = self.nforms - 1 - c
+        nd = self.dof[j].ndofs
+        AEe = self.topo.AE_entity[c]
+        if self.mesh is not None:       # DeRhamSequence3D_FE::computePVTraces
+            if c == 0:
+                return np.ones(nd)
+            pv = np.zeros(nd)
+            if c == 1:
+                pv[AEe.indices] = AEe.data * self.mesh.facet_area()[AEe.indices]
+            elif c == 2:
+                pv[AEe.indices] = AEe.data * self.mesh.ridge_length()[AEe.indices]
+            else:
+                pv[AEe.indices] = 1.0
+            return pv
+        # DeRhamSequenceAlg::computePVTraces: +-1 on the first dof of every member entity
+        pv = np.zeros(nd)
+        ED = self.dof[j].entity_dof[c]
+        pv[ED.indices[ED.indptr[AEe.indices]]] = AEe.data
+        return pv
+
+    # --- Coarsen
+    def coarsen(self):
+        topo, ctopo = self.topo, self.topo.coarser
+        assert ctopo is not None, "coarsen the topology first"
+        cs = Sequence(ctopo, self.nforms)
+        cs.jstart = self.jstart
+        cs.svd_tol = self.svd_tol
+        self.coarser, cs.finer = cs, self
+        self.agg = [None] * self.nforms
+        for j in range(self.jstart, self.nforms):
+            self.agg[j] = DofAgg(topo, self.dof[j])
+        self._Pcoo = [None] * self.nforms
+        self._func = [None] * self.nforms
+        for codim in range(self.nforms):
+            j = self.nforms - codim - 1
+            if j < self.jstart:
+                break
+            cs.dof[j] = DofHandler(codim, ctopo)
+            cs.dof[j].alg_init()
+            self._Pcoo[j] = ([], [], [])
+            self._func[j] = [dict() for _ in range(codim + 1)]
+            self._coarse_traces(j)
+            if codim > 0:
+                self._h_facet_extension(j)
+                if codim > 1:
+                    self._h_ridge_peak_extension(j, self.nforms - j - 3)
+                    if codim > 2:
+                        self._h_ridge_peak_extension(j, self.nforms - j - 4)
+            self.P[j] = self._P_csr(j, cs.dof[j].ndofs)
+            if codim > 0:
+                r, c, v = self._Dcoo[j]
+                cs.D[j] = _raw_coo(np.concatenate(r), np.concatenate(c), np.concatenate(v),
+                                   (cs.dof[j + 1].ndofs, cs.dof[j].ndofs))
+            self.Pi[j] = self._compute_projector(j)
+        cs.targets = [None] * self.nforms
+        for j in range(self.jstart, self.nforms):
+            cs.targets[j] = self.Pi[j] @ self.targets[j]
+        cs.l2_const = self.Pi[self.nforms - 1] @ self.l2_const
+        return cs
+
+    def _P_csr(self, j, ncols):
+        r, c, v = self._Pcoo[j]
+        if len(r) == 0:
+            return sp.csr_matrix((self.dof[j].ndofs, ncols))
+        return _raw_coo(np.concatenate(r), np.concatenate(c), np.concatenate(v), (self.dof[j].ndofs, ncols))
+
+    def _P_add(self, j, rows, cols, block):
+        rows, cols = np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64)
+        if len(rows) == 0 or len(cols) == 0:
+            return
+        rr, cc = np.meshgrid(rows, cols, indexing="ij")
+        r, c, v = self._Pcoo[j]
+        r.append(rr.ravel()); c.append(cc.ravel()); v.append(np.asarray(block, dtype=np.float64).ravel())
+
+    def _midx(self, j, c):
+        return (j, c)
+
+    # ---- traces (DeRhamSequence.cpp:1521-2085)
+    def _coarse_traces(self, j):
+        cs = self.coarser
+        codim = self.ndim - j
+        agg = self.agg[j]
+        cdof = cs.dof[j]
+        nAE = agg.nAE(codim)
+        pv = self.pv_traces(codim)
+        if j == 0:      # Compute0formCoarseTraces
+            for a in range(nAE):
+                ints, _ = agg.dofs(codim, a)
+                assert len(ints) == 1, "topology error: disconnected coarse peak"
+                self._P_add(0, ints, [a], np.ones((1, 1)))
+                cdof.dof_type[a] = RANGET
+                cdof.n_rangeT[codim][a] = 1
+                self._func[0][codim][a] = np.ones((1, 1))
+            cdof.build_entity_dof_table(codim)
+            cs.M[(0, codim)] = sp.identity(nAE, format="csr")
+            return
+        M_d = agg.assemble_agg_matrix(codim, self.M[(j, codim)])
+        T = self.targets[j]
+        nT = 0 if T is None else T.shape[1]
+        ploc, masses, ndofs = [None] * nAE, [None] * nAE, np.zeros(nAE, dtype=np.int64)
+        for a in range(nAE):
+            s, m, e = agg.rng(codim, a)
+            dofs = agg.J[codim][s:e]
+            loc_pv = pv[dofs]
+            Mloc = M_d[s:e, s:e].toarray()
+            pvMpv = float(loc_pv @ (Mloc @ loc_pv))
+            if nT > 0:
+                lt = T[dofs, :].copy()
+                # Deflate(targets, pv, M-inner product)
+                sc = -1.0 / pvMpv
+                for t in range(nT):
+                    lt[:, t] = lt[:, t] + (float(loc_pv @ (Mloc @ lt[:, t])) * sc) * loc_pv
+                U, sv = svd_on_weighted(Mloc, lt)
+            else:
+                U, sv = np.zeros((len(dofs), 0)), np.zeros(0)
+            s_max_tol = pvMpv * self.svd_tol
+            k = 0
+            while k < len(sv) and not (sv[k] < s_max_tol):
+                k += 1
+            ndofs[a] = k + 1
+            p = np.empty((len(dofs), k + 1))
+            p[:, 0] = loc_pv
+            p[:, 1:] = U[:, :k] * np.sqrt(pvMpv)
+            cm = p.T @ (Mloc @ p)
+            masses[a] = 0.5 * (cm + cm.T)
+            ploc[a] = p
+            self._func[j][codim][a] = dof_functional(p, Mloc)
+        cnt = 0
+        for a in range(nAE):
+            cdof.dof_type[cnt] = RANGET
+            for q in range(1, ndofs[a]):
+                cdof.dof_type[cnt + q] = NULLSPACE
+            cnt += int(ndofs[a])
+            cdof.n_rangeT[codim][a] = 1
+            cdof.n_null[codim][a] = ndofs[a] - 1
+        cdof.build_entity_dof_table(codim)
+        ED = cdof.entity_dof[codim]
+        for a in range(nAE):
+            s, m, e = agg.rng(codim, a)
+            self._P_add(j, agg.J[codim][s:e], row(ED, a), ploc[a])
+        cs.M[(j, codim)] = block_diag_csr(masses)
+        self.stats[("trace_null", j)] = int(ndofs.sum() - nAE)
+
+    # ---- local matrices shared by the extension stages
+    def _local_setup(self, j, cdom):
+        agg, aggp = self.agg[j], self.agg[j + 1]
+        M_d = agg.assemble_agg_matrix(cdom, self.M[(j, cdom)])
+        D_d = DofAgg.distribute(cdom, self.D[j], aggp, agg)
+        W_d = aggp.assemble_agg_matrix(cdom, self.M[(j + 1, cdom)])
+        return M_d, D_d, W_d
+
+    def _current_Rt(self, j):
+        """TransposeAbstractSparseMatrix(P_[j]) at the start of a stage."""
+        r, c, v = self._Pcoo[j]
+        ncol = self.coarser.dof[j].ndofs
+        if len(r) == 0:
+            return sp.csr_matrix((ncol, self.dof[j].ndofs))
+        P = _raw_coo(np.concatenate(r), np.concatenate(c), np.concatenate(v), (self.dof[j].ndofs, ncol))
+        return sp.csr_matrix(P.T)
+
+    # ---- hFacetExtension (DeRhamSequence.cpp:2214-2581)
+    def _h_facet_extension(self, j):
+        cs = self.coarser
+        cbdr, cdom = self.nforms - j - 1, self.nforms - j - 2
+        agg, aggp = self.agg[j], self.agg[j + 1]
+        ucd, pcd = cs.dof[j], cs.dof[j + 1]
+        M_d, D_d, W_d = self._local_setup(j, cdom)
+        Rt = self._current_Rt(j)
+        Pp = self.P[j + 1].tocsc()
+        nAE = cs.topo.n[cdom]
+        Bc = cs.topo.B[cdom]
+        EDb = ucd.entity_dof[cbdr]
+        self._Dcoo = getattr(self, "_Dcoo", [None] * self.nforms)
+        Dr, Dc, Dv = [], [], []
+        T = self.targets[j]
+        nT = 0 if T is None else T.shape[1]
+        counter = Rt.shape[0]
+        masses = [None] * nAE
+        n_rt = n_null = 0
+        for a in range(nAE):
+            us, um, ue = agg.rng(cdom, a)
+            ps, pm, pe = aggp.rng(cdom, a)
+            nu, npi = um - us, pm - ps
+            u_int, u_bdr = agg.J[cdom][us:um], agg.J[cdom][um:ue]
+            p_int = aggp.J[cdom][ps:pm]
+            Mall = M_d[us:ue, us:ue].toarray()
+            Mloc, Mib = Mall[:nu, :nu], Mall[:nu, nu:]
+            Dall = D_d[ps:pe, us:ue].toarray()
+            Wall = W_d[ps:pe, ps:pe].toarray()
+            Ball = Wall @ Dall
+            Bloc, Bib = Ball[:npi, :nu], Ball[:npi, nu:]
+            Wloc = Wall[:npi, :npi]
+            # PV dof of form j+1 on this AE and the T block
+            pv_c = pcd.rangeT_dofs(cdom, a)
+            assert len(pv_c) >= 1
+            pvloc = Pp[:, [pv_c[0]]].toarray()[p_int, 0]
+            tloc = Wloc @ pvloc
+            n = nu + npi + 1
+            A = np.zeros((n, n))
+            A[:nu, :nu] = Mloc
+            A[nu:nu + npi, :nu] = Bloc
+            A[:nu, nu:nu + npi] = Bloc.T
+            A[nu + npi, nu:nu + npi] = tloc
+            A[nu:nu + npi, nu + npi] = tloc
+            ldl = LDL(A)
+            # (3) harmonic extension of the boundary traces
+            cb = np.concatenate([row(EDb, f) for f in row(Bc, a)]).astype(np.int64) if len(row(Bc, a)) else np.zeros(0, dtype=np.int64)
+            Rb = Rt[cb][:, u_bdr].toarray().T          # (bdr fine dofs) x (bdr coarse dofs)
+            rhs = np.zeros((n, len(cb)))
+            rhs[:nu] = -(Mib @ Rb)
+            rhs[nu:nu + npi] = -(Bib @ Rb)
+            sol = ldl.solve(rhs)
+            ext = sol[:nu]
+            self._P_add(j, u_int, cb, ext)
+            lam = sol[nu + npi]
+            drow = np.where(np.abs(lam) > self.smallest_entry, -lam, 0.0)
+            Dr.append(np.full(len(cb), pv_c[0])); Dc.append(cb); Dv.append(drow)
+            # (4) RangeT bubbles: one per NullSpace dof of form j+1 on this AE
+            pnull = pcd.null_dofs(cdom, a)
+            nrt = len(pnull)
+            ucd.n_rangeT[cdom][a] = nrt
+            n_rt += nrt
+            c_rt = np.arange(counter, counter + nrt, dtype=np.int64)
+            counter += nrt
+            bub = np.zeros((nu, 0))
+            if nrt:
+                sub = Pp[:, pnull].toarray()[p_int, :]
+                rhs = np.zeros((n, nrt))
+                rhs[nu:nu + npi] = Wloc @ sub
+                bub = ldl.solve(rhs)[:nu]
+                self._P_add(j, u_int, c_rt, bub)
+                for q in range(nrt):
+                    Dr.append(np.array([pnull[q]])); Dc.append(np.array([c_rt[q]])); Dv.append(np.array([1.0]))
+                    ucd.dof_type[int(c_rt[q])] = RANGET
+            # (5) NullSpace dofs: targets minus their extension, SVD, truncate
+            nul = np.zeros((nu, 0))
+            if nu > nrt and nT > 0:
+                tint, tbdr = T[u_int, :].copy(), T[u_bdr, :]
+                rhs = np.zeros((n, nT))
+                rhs[:nu] = -(Mib @ tbdr)
+                rhs[nu:nu + npi] = Bloc @ tint
+                sol = ldl.solve(rhs)
+                tint = tint - sol[:nu]
+                U, sv = svd_on(tint)
+                k = 0
+                while k < len(sv) and not (sv[k] < self.svd_tol):
+                    k += 1
+                nul = U[:, :k]
+            k = nul.shape[1]
+            c_nu = np.arange(counter, counter + k, dtype=np.int64)
+            counter += k
+            for d in c_nu:
+                ucd.dof_type[int(d)] = NULLSPACE
+            ucd.n_null[cdom][a] = k
+            n_null += k
+            if k:
+                self._P_add(j, u_int, c_nu, nul)
+            # (5') dof functionals of the interior coarse dofs
+            self._func[j][cdom][a] = dof_functional(np.hstack([bub, nul]), Mloc)
+            # (6) coarse element mass: [bdr | RangeT | Null]
+            basis = np.zeros((ue - us, len(cb) + nrt + k))
+            basis[:nu, :len(cb)] = ext
+            basis[nu:, :len(cb)] = Rb
+            basis[:nu, len(cb):len(cb) + nrt] = bub
+            basis[:nu, len(cb) + nrt:] = nul
+            cm = basis.T @ (Mall @ basis)
+            masses[a] = 0.5 * (cm + cm.T)
+        ucd.build_entity_dof_table(cdom)
+        cs.M[(j, cdom)] = block_diag_csr(masses)
+        self._Dcoo[j] = [Dr, Dc, Dv]
+        self.stats[("facet_ext", j)] = (n_rt, n_null)
+
+    # ---- hRidgePeakExtension (DeRhamSequence.cpp:2629-3048)
+    def _h_ridge_peak_extension(self, j, cdom):
+        cs = self.coarser
+        ridge_stuff = (cdom == self.nforms - j - 3)
+        agg, aggp, aggq = self.agg[j], self.agg[j + 1], self.agg[j + 2]
+        ucd, pcd = cs.dof[j], cs.dof[j + 1]
+        M_d, D_d, W_d = self._local_setup(j, cdom)
+        # minusC = -(D2_d^T W2_d D2_d), GetMinusC (DeRhamSequence.cpp:2583-2607)
+        D2_d = DofAgg.distribute(cdom, self.D[j + 1], aggq, aggp)
+        W2_d = aggq.assemble_agg_matrix(cdom, self.M[(j + 2, cdom)])
+        mC_d = _canon(-(D2_d.T @ W2_d @ D2_d))
+        # PDc = P_{j+1} * coarse D_j (as built so far)
+        Dr, Dc, Dv = self._Dcoo[j]
+        Dcoarse = _raw_coo(np.concatenate(Dr), np.concatenate(Dc), np.concatenate(Dv),
+                           (pcd.ndofs, ucd.ndofs)) if len(Dr) else sp.csr_matrix((pcd.ndofs, ucd.ndofs))
+        PDc = sp.csr_matrix(self.P[j + 1] @ Dcoarse).tocsc()
+        Rt = self._current_Rt(j)
+        Pp = self.P[j + 1].tocsc()
+        nAE = cs.topo.n[cdom]
+        T = self.targets[j]
+        nT = 0 if T is None else T.shape[1]
+        counter = Rt.shape[0]
+        masses = [None] * nAE
+        n_rt = n_null = 0
+        for a in range(nAE):
+            us, um, ue = agg.rng(cdom, a)
+            ps, pm, pe = aggp.rng(cdom, a)
+            nu, npi = um - us, pm - ps
+            u_int, u_bdr = agg.J[cdom][us:um], agg.J[cdom][um:ue]
+            p_all = aggp.J[cdom][ps:pe]
+            p_int = p_all[:npi]
+            Mall = M_d[us:ue, us:ue].toarray()
+            Mloc, Mib = Mall[:nu, :nu], Mall[:nu, nu:]
+            Dall = D_d[ps:pe, us:ue].toarray()
+            Wall = W_d[ps:pe, ps:pe].toarray()
+            Ball = Wall @ Dall
+            Bloc = Ball[:npi, :nu]
+            W_iA = Wall[:npi, :]
+            Wloc = Wall[:npi, :npi]
+            mC = mC_d[ps:pm, ps:pm].toarray()
+            n = nu + npi
+            A = np.zeros((n, n))
+            A[:nu, :nu] = Mloc
+            A[nu:, :nu] = Bloc
+            A[:nu, nu:] = Bloc.T
+            A[nu:, nu:] = mC
+            ldl = LDL(A) if nu > 0 else None
+            cb = ucd.dofs_on_bdr(cdom, a)
+            Rb = Rt[cb][:, u_bdr].toarray().T if len(cb) else np.zeros((len(u_bdr), 0))
+            rhs = np.zeros((n, len(cb)))
+            rhs[:nu] = -(Mib @ Rb)
+            # -W_iA * (D_loc P_bdr) + W_iA * (P_{j+1} D_c)_loc
+            DRb = Dall[:, nu:] @ Rb
+            PDloc = PDc[:, cb].toarray()[p_all, :] if len(cb) else np.zeros((len(p_all), 0))
+            rhs[nu:] = W_iA @ (PDloc - DRb)
+            ext = ldl.solve(rhs)[:nu] if nu > 0 else np.zeros((0, len(cb)))
+            self._P_add(j, u_int, cb, ext)
+            # (4) RangeT bubbles
+            pnull = pcd.null_dofs(cdom, a)
+            nrt = len(pnull)
+            ucd.n_rangeT[cdom][a] = nrt
+            n_rt += nrt
+            c_rt = np.arange(counter, counter + nrt, dtype=np.int64)
+            counter += nrt
+            bub = np.zeros((nu, 0))
+            if nrt:
+                sub = Pp[:, pnull].toarray()[p_int, :]
+                rhs = np.zeros((n, nrt))
+                rhs[nu:] = Wloc @ sub
+                bub = ldl.solve(rhs)[:nu] if nu > 0 else np.zeros((0, nrt))
+                self._P_add(j, u_int, c_rt, bub)
+                for q in range(nrt):
+                    Dr.append(np.array([pnull[q]])); Dc.append(np.array([c_rt[q]])); Dv.append(np.array([1.0]))
+                    ucd.dof_type[int(c_rt[q])] = RANGET
+            # (5) NullSpace dofs (ridge extension only)
+            nul = np.zeros((nu, 0))
+            if ridge_stuff and nu > nrt and nT > 0:
+                tint, tbdr = T[u_int, :].copy(), T[u_bdr, :]
+                rhs = np.zeros((n, nT))
+                rhs[:nu] = -(Mib @ tbdr)
+                rhs[nu:] = Bloc @ tint
+                sol = ldl.solve(rhs)
+                tint = tint - sol[:nu]
+                U, sv = svd_on(tint)
+                k = 0
+                while k < len(sv) and not (sv[k] < self.svd_tol):
+                    k += 1
+                nul = U[:, :k]
+            k = nul.shape[1]
+            c_nu = np.arange(counter, counter + k, dtype=np.int64)
+            counter += k
+            for d in c_nu:
+                ucd.dof_type[int(d)] = NULLSPACE
+            ucd.n_null[cdom][a] = k
+            n_null += k
+            if k:
+                self._P_add(j, u_int, c_nu, nul)
+            self._func[j][cdom][a] = dof_functional(np.hstack([bub, nul]), Mloc)
+            basis = np.zeros((ue - us, len(cb) + nrt + k))
+            basis[:nu, :len(cb)] = ext
+            basis[nu:, :len(cb)] = Rb
+            basis[:nu, len(cb):len(cb) + nrt] = bub
+            basis[:nu, len(cb) + nrt:] = nul
+            cm = basis.T @ (Mall @ basis)
+            masses[a] = 0.5 * (cm + cm.T)
+        ucd.build_entity_dof_table(cdom)
+        cs.M[(j, cdom)] = block_diag_csr(masses)
+        self.stats[("ridgepeak_ext", j, cdom)] = (n_rt, n_null)
+
+    # ---- CochainProjector::ComputeProjector (CochainProjector.cpp:219-261,416-441)
+    def _compute_projector(self, j):
+        cs = self.coarser
+        cdof, agg = cs.dof[j], self.agg[j]
+        nf, nc = self.dof[j].ndofs, cdof.ndofs
+        P = self.P[j]
+
+        def hat(c):
+            rows, cols, vals = [], [], []
+            for e in range(cs.topo.n[c]):
+                F = self._func[j][c][e]
+                fi, _ = agg.dofs(c, e)
+                ci = cdof.interior_dofs(c, e)
+                if F.size == 0:
+                    continue
+                rr, cc = np.meshgrid(ci, fi, indexing="ij")
+                rows.append(rr.ravel()); cols.append(cc.ravel()); vals.append(F.ravel())
+            if not rows:
+                return sp.csr_matrix((nc, nf))
+            return _raw_coo(np.concatenate(rows), np.concatenate(cols), np.concatenate(vals), (nc, nf))
+
+        base = cdof.mcb
+        Pi = hat(base)
+        for c in range(base - 1, -1, -1):
+            h = hat(c)
+            Pi = _canon(Pi + h - h @ (P @ Pi))
+        return Pi
+
+
+def _raw_coo(r, c, v, shape):
+    """COO -> CSR keeping explicit zeros (no duplicate entries are ever produced by
+    the callers: every (row, col) pair is written once, like SparseMatrix::Set)."""
+    M = sp.coo_matrix((v, (r, c)), shape=shape).tocsr()
+    M.sort_indices()
+    return M
+
+
+# ----------------------------------------------------------------------------
+# fine level
+# ----------------------------------------------------------------------------
+def fine_sequence(mesh, topo=None, upscaling_order=0, alpha=None, beta=None, jstart=0):
+    """DeRhamSequence3D_FE at lowest order on a structured hex mesh + upscaling targets
+    (SetUpscalingTargets).  alpha / beta: optional per-element weights of the L2 and
+    H(div) element mass matrices (ReplaceMassIntegrator in the drivers)."""
+    topo = topo or mesh.topology()
+    seq = Sequence(topo, 4)
+    seq.mesh = mesh
+    seq.jstart = jstart
+    hx, hy, hz = mesh.h
+    vol = hx * hy * hz
+    nel = mesh.nel
+    ent_dim = {0: 3, 1: 2, 2: 1, 3: 0}
+    # dof handlers: dof of form j == entity of codim 3-j; entity_dof[c] = closure table
+    for j in range(4):
+        dh = DofHandler(3 - j, topo)
+        dh.ndofs = topo.n[3 - j]
+        for c in range(3 - j + 1):
+            if c == 3 - j:
+                dh.entity_dof[c] = sp.identity(topo.n[c], format="csr")
+            else:
+                dh.entity_dof[c] = topo.conn(c, 3 - j)
+        seq.dof[j] = dh
+    seq.D = [topo.B[2].copy(), topo.B[1].copy(), _canon(topo.B[0] * (1.0 / vol))]
+    a_el = np.ones(nel) if alpha is None else np.asarray(alpha, dtype=np.float64)
+    b_el = np.ones(nel) if beta is None else np.asarray(beta, dtype=np.float64)
+
+    def rep(block, n, w=None):
+        m = block.shape[0]
+        data = np.tile(block.ravel(), n)
+        if w is not None:
+            data = data * np.repeat(w, m * m)
+        rr = (np.arange(n)[:, None] * m + np.repeat(np.arange(m), m)[None, :]).ravel()
+        cc = (np.arange(n)[:, None] * m + np.tile(np.arange(m), m)[None, :]).ravel()
+        return sp.csr_matrix((data, (rr, cc)), shape=(n * m, n * m))
+
+    def bd(*blocks):
+        return np.asarray(sp.block_diag(blocks).todense())
+
+    # form 3 (L2, cell values)
+    seq.M[(3, 0)] = rep(np.array([[vol]]), nel, a_el)
+    # form 2 (RT0, fluxes): element (local order x-,x+,y-,y+,z-,z+), facet
+    seq.M[(2, 0)] = rep(bd(hx / (hy * hz) * M1D, hy / (hx * hz) * M1D, hz / (hx * hy) * M1D), nel, b_el)
+    seq.M[(2, 1)] = sp.diags(1.0 / mesh.facet_area()).tocsr()
+    # form 1 (Nedelec, circulations): element (4 x-edges, 4 y-edges, 4 z-edges), facet, ridge
+    K = np.kron(M1D, M1D)
+    seq.M[(1, 0)] = rep(bd(hy * hz / hx * K, hx * hz / hy * K, hx * hy / hz * K), nel)
+    fm = []
+    # x-face: its edges in ascending id are 2 y-edges (at k, k+1) then 2 z-edges (at j, j+1)
+    fm.append(rep(bd(hz / hy * M1D, hy / hz * M1D), mesh.nf[0]))
+    # y-face: 2 x-edges (k,k+1), 2 z-edges (i,i+1)
+    fm.append(rep(bd(hz / hx * M1D, hx / hz * M1D), mesh.nf[1]))
+    # z-face: 2 x-edges (j,j+1), 2 y-edges (i,i+1)
+    fm.append(rep(bd(hy / hx * M1D, hx / hy * M1D), mesh.nf[2]))
+    seq.M[(1, 1)] = sp.block_diag(fm).tocsr()
+    seq.M[(1, 2)] = sp.diags(1.0 / mesh.ridge_length()).tocsr()
+    # form 0 (H1, vertex values)
+    seq.M[(0, 0)] = rep(vol * np.kron(M1D, K), nel)
+    seq.M[(0, 1)] = sp.block_diag([rep(hy * hz * K, mesh.nf[0]), rep(hx * hz * K, mesh.nf[1]),
+                                   rep(hx * hy * K, mesh.nf[2])]).tocsr()
+    seq.M[(0, 2)] = sp.block_diag([rep(hx * M1D, mesh.ne[0]), rep(hy * M1D, mesh.ne[1]),
+                                   rep(hz * M1D, mesh.ne[2])]).tocsr()
+    seq.M[(0, 3)] = sp.identity(mesh.nv, format="csr")
+    seq.l2_const = np.ones(nel)
+    # targets (Coefficient.cpp:20-274): scalar monomials / vector monomials e_c x^a y^b z^c
+    X = mesh.vertex_coords()
+
+    def monos(order):
+        out = []
+        for om in range(order + 1):
+            for ox in range(om + 1):
+                for oy in range(om - ox + 1):
+                    out.append((ox, oy, om - ox - oy))
+        return out
+    assert upscaling_order == 0, "oracle fine level implements upscaling order 0"
+    seq.targets[3] = np.ones((nel, 1))
+    area, length = mesh.facet_area(), mesh.ridge_length()
+    T2 = np.zeros((sum(mesh.nf), 3))
+    T2[:mesh.nf[0], 0] = area[:mesh.nf[0]]
+    T2[mesh.nf[0]:mesh.nf[0] + mesh.nf[1], 1] = area[mesh.nf[0]:mesh.nf[0] + mesh.nf[1]]
+    T2[mesh.nf[0] + mesh.nf[1]:, 2] = area[mesh.nf[0] + mesh.nf[1]:]
+    seq.targets[2] = T2
+    T1 = np.zeros((sum(mesh.ne), 3))
+    T1[:mesh.ne[0], 0] = length[:mesh.ne[0]]
+    T1[mesh.ne[0]:mesh.ne[0] + mesh.ne[1], 1] = length[mesh.ne[0]:mesh.ne[0] + mesh.ne[1]]
+    T1[mesh.ne[0] + mesh.ne[1]:, 2] = length[mesh.ne[0] + mesh.ne[1]:]
+    seq.targets[1] = T1
+    seq.targets[0] = np.stack([X[:, 0] ** a * X[:, 1] ** b * X[:, 2] ** c for (a, b, c) in monos(1)], axis=1)
+    return seq
+
+
+def build_hierarchy(dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9):
+    """Drivers' steps 3-4 (examples/MultigridTest2Form.cpp:248-375): agglomerate the
+    topology nlevels-1 times by derefinement, then Coarsen() level by level."""
+    mesh = HexMesh(*dims, L=L)
+    topos = [mesh.topology()]
+    d = dims
+    for _ in range(nlevels - 1):
+        topos.append(topos[-1].coarsen(refined_partition(d)))
+        d = (d[0] // 2, d[1] // 2, d[2] // 2)
+    seqs = [fine_sequence(mesh, topos[0], alpha=alpha, beta=beta, jstart=jstart)]
+    for l in range(nlevels - 1):
+        seqs[l].svd_tol = svd_tol
+        seqs.append(seqs[l].coarsen())
+    return mesh, seqs
+
+
+# ----------------------------------------------------------------------------
+# checks and golden reproduction
+# ----------------------------------------------------------------------------
+def check_invariants(seq, tol=1e-9):
+    """DeRhamSequence::CheckInvariants (DeRhamSequence.cpp:694-970): M_c = P^T M_f P,
+    D_{j+1} D_j = 0, D_f P_j = P_{j+1} D_c, Pi P = I, Pi reproduces targets."""
+    cs = seq.coarser
+    out = {}
+    for j in range(seq.jstart, seq.nforms):
+        Mf, Mc = seq.mass_operator(j), cs.mass_operator(j)
+        P = seq.P[j]
+        out[("M", j)] = abs(Mc - P.T @ Mf @ P).max() / max(abs(Mc).max(), 1e-300)
+        PiP = (seq.Pi[j] @ P).toarray()
+        out[("PiP", j)] = np.abs(PiP - np.eye(PiP.shape[0])).max()
+        out[("target", j)] = np.abs(P @ cs.targets[j] - seq.targets[j]).max()
+        if j < seq.nforms - 1:
+            out[("DP", j)] = abs(seq.D[j] @ P - seq.P[j + 1] @ cs.D[j]).max()
+        if j < seq.nforms - 2:
+            out[("DD", j)] = abs(cs.D[j + 1] @ cs.D[j]).max()
+    return out
+
+
+def upscaling_errors(form, nref=1, base=(2, 2, 2)):
+    """testsuite/UpscalingGeneralForm.cpp (--form F --nref_parallel nref, default cube of
+    2x2x2 hexes): A = M_F + D^T W D with essential (zero) data on attributes 2-5, a
+    natural boundary term -1 on attribute 1; solve on every level; report
+    ||u_h - P u_H||_M and ||D(u_h - P u_H)||_W on the finest level for the coarsest."""
+    import scipy.sparse.linalg as spl
+    dims = tuple(b * 2 ** nref for b in base)
+    mesh, seqs = build_hierarchy(dims, nref + 1)
+    ess = np.array([0, 1, 1, 1, 1, 0])
+    nx, ny, nz = dims
+    hx, hy, hz = mesh.h
+    f = seqs[0]
+    nd = f.dof[form].ndofs
+    b = np.zeros(nd)
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    i, j = i.ravel(), j.ravel()
+    if form == 0:      # BoundaryLFIntegrator(-1) on z=0
+        for di in (0, 1):
+            for dj in (0, 1):
+                np.add.at(b, mesh.vx(i + di, j + dj, 0), -hx * hy / 4.0)
+    elif form == 1:    # (n x f, v) on z=0, f=(1,1,1), n=(0,0,-1): n x f = (1,-1,0)
+        for dj in (0, 1):
+            np.add.at(b, mesh.ex(i, j + dj, 0), 1.0 * hy / 2.0)
+        for di in (0, 1):
+            np.add.at(b, mesh.ey(i + di, j, 0), -1.0 * hx / 2.0)
+    else:              # (f, v.n) with f=-1 on z=0 (outward normal -z, dof oriented +z)
+        b[mesh.fz(i, j, 0)] = 1.0
+    sols, Ms, Ws, Ds = [], [], [], []
+    rhs = b
+    for k, s in enumerate(seqs):
+        M, W, D = s.mass_operator(form), s.mass_operator(form + 1), s.D[form]
+        A = _canon(M + D.T @ W @ D).tolil()
+        marker = s.dof[form].mark_bdr_dofs(ess)
+        r = rhs.copy()
+        idx = np.nonzero(marker)[0]
+        A = A.tocsr()
+        keep = sp.diags((~marker).astype(float))
+        A = keep @ A @ keep + sp.diags(marker.astype(float))
+        r[idx] = 0.0
+        sols.append(spl.spsolve(A.tocsc(), r))
+        Ms.append(M); Ws.append(W); Ds.append(D)
+        if k + 1 < len(seqs):
+            rhs = s.P[form].T @ rhs
+    uH = sols[-1]
+    for k in range(len(seqs) - 2, -1, -1):
+        uH = seqs[k].P[form] @ uH
+    diff = uH - sols[0]
+    e_l2 = float(np.sqrt(diff @ (Ms[0] @ diff)))
+    dd = Ds[0] @ diff
+    e_en = float(np.sqrt(dd @ (Ws[0] @ dd)))
+    return e_l2, e_en, seqs
