@@ -1,0 +1,73 @@
+/*
+ * parelag_b200_api.h -- C facade over the C++ mirror of ParElag's solver API
+ * (parelag_b200/src/*.hpp: ParameterList-driven SolverLibrary / SolverFactory,
+ * mfem::Solver::Mult, DeRhamSequence coarse-operator interface).  It exists so that
+ * non-C++ hosts (the ctypes tests, bench.py, a C driver) can drive exactly the code
+ * path a C++ ParElag driver drives:
+ *
+ *     lib   = SolverLibrary::CreateLibrary(master_list.Sublist("Preconditioner Library"))
+ *     fact  = lib->GetSolverFactory(name)              examples/MultigridTest2Form.cpp:519-523
+ *     state->SetDeRhamSequence / SetBoundaryLabels / SetForms
+ *     solver = fact->BuildSolver(A, *state)            :537
+ *     solver->Mult(B, X)                               :578
+ *
+ * Return codes and pe_last_error() as in parelag_b200.h; C++ exceptions are caught
+ * at this boundary and turned into error codes.
+ */
+#ifndef PARELAG_B200_API_H
+#define PARELAG_B200_API_H
+#include "parelag_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pe_sequence pe_sequence; /* a chain of DeRhamSequence levels (fine -> coarse) */
+typedef struct pe_solver pe_solver;     /* an mfem::Solver built by a SolverFactory          */
+
+/* process-wide session (parelag::mpi_session): one rank <-> one GPU */
+int pe_api_session_create(int rank, int nranks, int device, const void *nccl_unique_id);
+int pe_api_session_destroy(void);
+pe_ctx *pe_api_session_ctx(void);
+
+/* DeRhamSequence levels with externally supplied operators (the role
+ * DeRhamSequenceAlg plays for levels produced by Coarsen()).  P(level, form) maps
+ * level+1 -> level; D(level, form) maps form -> form+1 on that level; bdr_mask bit a
+ * marks dofs lying on facets with boundary attribute a+1 (DofHandler::MarkDofsOnSelectedBndr). */
+int pe_api_sequence_create(int nforms, int nlevels, pe_sequence **out);
+int pe_api_sequence_set_P(pe_sequence *s, int level, int form, int nrows, int ncols,
+                          const int32_t *I, const int32_t *J, const double *A);
+int pe_api_sequence_set_D(pe_sequence *s, int level, int form, int nrows, int ncols,
+                          const int32_t *I, const int32_t *J, const double *A);
+int pe_api_sequence_set_bdr_mask(pe_sequence *s, int level, int form, int ndofs, const uint32_t *mask);
+int pe_api_sequence_free(pe_sequence *s);
+
+/* SolverLibrary::CreateLibrary(xml) -> GetSolverFactory(name) -> BuildSolver(A, state).
+ * xml: a <ParameterList name="Preconditioner Library"> document.  seq may be NULL for
+ * solvers that need no sequence.  ess_attr[nattr]: essential boundary attribute marker
+ * (SolverState::SetBoundaryLabels), may be NULL. */
+int pe_api_solver_build(const char *xml_library, const char *solver_name, const pe_parcsr_host *A,
+                        pe_sequence *seq, int start_level, int form, const int32_t *ess_attr, int nattr,
+                        pe_solver **out);
+/* solver->Mult(B, X) with HOST buffers (H2D of b, D2H of x inside the call);
+ * iterative_mode != 0 uses x as initial guess */
+int pe_api_solver_mult(pe_solver *s, const double *b_host, double *x_host, int n, int iterative_mode);
+/* solver->Mult on device-resident vectors (no copies) */
+int pe_api_solver_mult_device(pe_solver *s, const pe_vec *b, pe_vec *x, int iterative_mode);
+/* Krylov solvers: "(B r, r)" history (what MFEM prints), iteration count, convergence flag */
+int pe_api_solver_get_history(const pe_solver *s, double *hist, int capacity, int *count,
+                              int *iterations, int *converged);
+/* Hierarchy solvers: number of levels, and size / nnz of A on a level */
+int pe_api_solver_num_levels(const pe_solver *s, int *nlevels);
+int pe_api_solver_level_info(const pe_solver *s, int level, int64_t *nrows, int64_t *nnz, int64_t *nnz_P);
+/* download A (diag block) of a hierarchy level for parity tests; arrays sized from level_info */
+int pe_api_solver_level_matrix(const pe_solver *s, int level, int32_t *I, int32_t *J, double *A);
+int pe_api_solver_free(pe_solver *s);
+
+/* TimeManager: seconds accumulated under a timer name; clear all timers */
+int pe_api_timer_get(const char *name, double *seconds);
+int pe_api_timer_clear(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,94 @@
+"""Oracle-side restatement of the example drivers' algebra (TEST INFRASTRUCTURE ONLY):
+system assembly as in examples/MultigridTest{0,1,2}Form.cpp:443-475 and the nested
+solver "PCG o AMGe(Hiptmair or l1-GS smoothers, PCG-GS coarse solver)" that the
+ParameterList library of examples/testing_helpers/Create{0,1,2}FormParameterList.hpp
+describes (coarse solver replaced by the hot-path-only "PCG-GS" of
+examples/example_parameterlists/spe10_example_parameters.xml:147-162)."""
+import numpy as np
+import scipy.sparse as sp
+
+from . import solve as orc
+
+
+def system_matrix(seq, form, ess_attr):
+    """A = M_form + D^T M_{form+1} D (form 0: D^T M_1 D), essential rows/cols
+    eliminated with unit diagonal (SparseMatrix::EliminateRowCol, DIAG_ONE)."""
+    D = seq.D[form]
+    W = seq.mass_operator(form + 1)
+    A = (D.T @ W @ D)
+    if form > 0:
+        A = A + seq.mass_operator(form)
+    A = sp.csr_matrix(A)
+    marker = seq.dof[form].mark_bdr_dofs(ess_attr)
+    keep = sp.diags((~marker).astype(float))
+    A = sp.csr_matrix(keep @ A @ keep + sp.diags(marker.astype(float)))
+    A.sum_duplicates(); A.sort_indices()
+    return A, marker
+
+
+def bdr_mask(dofhandler):
+    """bit a set <=> dof lies on a facet with boundary attribute a+1"""
+    mask = np.zeros(dofhandler.ndofs, dtype=np.uint32)
+    fb = dofhandler.topo.facet_bdr
+    if dofhandler.mcb < 1:
+        return mask
+    FD = dofhandler.entity_dof[1]
+    for f in range(fb.shape[0]):
+        a = fb.indices[fb.indptr[f]:fb.indptr[f + 1]]
+        if len(a) == 1:
+            mask[FD.indices[FD.indptr[f]:FD.indptr[f + 1]]] |= np.uint32(1 << int(a[0]))
+    return mask
+
+
+def gs_order(A, ordering):
+    return None if ordering == "natural" else orc.multicolor_order(A)[0]
+
+
+def amge_pcg_solver(seqs, form, ess_attr, A, ordering="natural", smoother_type=2,
+                    coarse_its=3, coarse_tol=1e-4, hiptmair=None):
+    """Returns (prec, info): prec(r) = one AMGe V-cycle.  hiptmair defaults to form>0."""
+    hiptmair = (form > 0) if hiptmair is None else hiptmair
+    nl = len(seqs)
+    Ps = [seqs[l].get_P(form, ess_attr) for l in range(nl - 1)]
+
+    def hypre(Al):
+        return orc.Smoother(Al, type=smoother_type, order=gs_order(Al, ordering))
+
+    def make_smoother(l, Al):
+        if not hiptmair:
+            return hypre(Al)
+        Dl = seqs[l].get_D(form - 1, ess_attr)
+        kw = lambda M: dict(type=smoother_type, order=gs_order(M, ordering))
+        return orc.Hiptmair(Al, Dl, kw, kw)
+
+    def make_coarse(Ac):
+        S = make_smoother(nl - 1, Ac)
+
+        def solve(b, x):
+            return orc.pcg(Ac, lambda r: S.apply(r, np.zeros_like(r), False), b, rtol=coarse_tol,
+                           atol=coarse_tol, max_iter=coarse_its)[0]
+        return solve
+    H = orc.build_hierarchy(A, Ps, make_smoother, make_coarse)
+    return H
+
+
+def library_entries(form, ordering="natural", smoother="L1 Gauss-Seidel", coarse_its=3, coarse_tol=1e-4,
+                    rtol=1e-6, atol=1e-6, max_iter=300):
+    """The same solver as a ParElag 'Preconditioner Library' (dict for api.library_xml)."""
+    hyp = ("Hypre", {"Type": smoother, "Sweeps": 1, "Damping Factor": 1.0, "Omega": 1.0,
+                     "Cheby Poly Order": 2, "Cheby Poly Fraction": 0.3, "GS ordering": ordering})
+    lib = {"Gauss-Seidel": hyp}
+    if form > 0:
+        lib["Hiptmair-GS-GS"] = ("Hiptmair", {"Primary Smoother": "Gauss-Seidel", "Auxiliary Smoother": "Gauss-Seidel"})
+        smoo = "Hiptmair-GS-GS"
+    else:
+        smoo = "Gauss-Seidel"
+    lib["PCG-GS"] = ("Krylov", {"Solver name": "PCG", "Preconditioner": smoo, "Print level": -1,
+                                "Maximum iterations": coarse_its, "Relative tolerance": coarse_tol,
+                                "Absolute tolerance": coarse_tol})
+    lib["AMGe"] = ("AMGe", {"Maximum levels": -1, "Forms": [form], "PreSmoother": smoo, "PostSmoother": smoo,
+                            "Coarse solver": "PCG-GS", "Cycle type": "V-cycle"})
+    lib["PCG-AMGe"] = ("Krylov", {"Solver name": "PCG", "Preconditioner": "AMGe", "Print level": -1,
+                                  "Maximum iterations": max_iter, "Relative tolerance": rtol,
+                                  "Absolute tolerance": atol})
+    return lib

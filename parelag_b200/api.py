@@ -1,0 +1,140 @@
+"""ctypes binding of include/parelag_b200_api.h: the ParameterList-driven solver API
+(SolverLibrary -> SolverFactory -> BuildSolver -> Mult) and the DeRhamSequence
+operator interface, as a ParElag driver uses them."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import _chk, _ptr, _i32, _f64, lib
+
+
+def session(rank=0, nranks=1, device=0, nccl_id=None):
+    _chk(lib().pe_api_session_create(rank, nranks, device, nccl_id))
+    lib().pe_api_session_ctx.restype = C.c_void_p
+    ctx = capi.Ctx.__new__(capi.Ctx)
+    ctx.h = C.c_void_p(lib().pe_api_session_ctx())
+    ctx.close = lambda: None          # owned by the session
+    return ctx
+
+
+def session_destroy():
+    _chk(lib().pe_api_session_destroy())
+
+
+def _csr_args(M):
+    M = M.tocsr()
+    return (M.shape[0], M.shape[1], np.ascontiguousarray(M.indptr, dtype=np.int32),
+            np.ascontiguousarray(M.indices, dtype=np.int32), np.ascontiguousarray(M.data, dtype=np.float64))
+
+
+class Sequence:
+    """A chain of DeRhamSequence levels with supplied operators."""
+
+    def __init__(self, nforms, nlevels):
+        self.h = C.c_void_p()
+        _chk(lib().pe_api_sequence_create(nforms, nlevels, C.byref(self.h)))
+
+    def set_P(self, level, form, P):
+        nr, nc, I, J, A = _csr_args(P)
+        _chk(lib().pe_api_sequence_set_P(self.h, level, form, nr, nc, _ptr(I), _ptr(J), _ptr(A)))
+
+    def set_D(self, level, form, D):
+        nr, nc, I, J, A = _csr_args(D)
+        _chk(lib().pe_api_sequence_set_D(self.h, level, form, nr, nc, _ptr(I), _ptr(J), _ptr(A)))
+
+    def set_bdr_mask(self, level, form, mask):
+        mask = np.ascontiguousarray(mask, dtype=np.uint32)
+        _chk(lib().pe_api_sequence_set_bdr_mask(self.h, level, form, len(mask), _ptr(mask)))
+
+    def free(self):
+        if self.h:
+            lib().pe_api_sequence_free(self.h)
+            self.h = None
+
+
+def library_xml(entries):
+    """entries: {name: (type, {param: value})} -> <ParameterList name="Preconditioner Library">"""
+    def ptype(v):
+        if isinstance(v, bool):
+            return "bool", "true" if v else "false"
+        if isinstance(v, int):
+            return "int", str(v)
+        if isinstance(v, float):
+            return "double", repr(v)
+        if isinstance(v, (list, tuple)):
+            return "vector(int)", " ".join(str(int(x)) for x in v)
+        return "string", str(v)
+    out = ['<ParameterList name="Preconditioner Library">']
+    for name, (typ, params) in entries.items():
+        out.append('  <ParameterList name="%s">' % name)
+        out.append('    <Parameter name="Type" type="string" value="%s"/>' % typ)
+        out.append('    <ParameterList name="Solver Parameters">')
+        for k, v in params.items():
+            t, s = ptype(v)
+            out.append('      <Parameter name="%s" type="%s" value="%s"/>' % (k, t, s))
+        out.append('    </ParameterList>')
+        out.append('  </ParameterList>')
+    out.append('</ParameterList>')
+    return "\n".join(out)
+
+
+class Solver:
+    def __init__(self, xml, name, A, seq=None, start_level=0, form=0, ess_attr=None):
+        A = A.tocsr()
+        self.n = A.shape[0]
+        keep = [_i32(A.indptr), _i32(A.indices), _f64(A.data)]
+        H = capi.ParCSRHost()
+        H.global_num_rows = H.num_rows = A.shape[0]
+        H.global_num_cols = H.num_cols_diag = A.shape[1]
+        H.diag_i, H.diag_j, H.diag_data = [_ptr(a) for a in keep]
+        ess = None if ess_attr is None else _i32(ess_attr)
+        self.h = C.c_void_p()
+        _chk(lib().pe_api_solver_build(xml.encode(), name.encode(), C.byref(H), None if seq is None else seq.h,
+                                       start_level, form, _ptr(ess), 0 if ess is None else len(ess), C.byref(self.h)))
+
+    def mult(self, b, x0=None):
+        b = _f64(b)
+        x = np.zeros(self.n) if x0 is None else _f64(x0).copy()
+        _chk(lib().pe_api_solver_mult(self.h, _ptr(b), _ptr(x), self.n, 0 if x0 is None else 1))
+        return x
+
+    def mult_device(self, b, x, iterative_mode=False):
+        _chk(lib().pe_api_solver_mult_device(self.h, b.h, x.h, 1 if iterative_mode else 0))
+
+    def history(self):
+        cnt, it, conv = C.c_int(), C.c_int(), C.c_int()
+        _chk(lib().pe_api_solver_get_history(self.h, None, 0, C.byref(cnt), C.byref(it), C.byref(conv)))
+        h = np.zeros(cnt.value)
+        _chk(lib().pe_api_solver_get_history(self.h, _ptr(h), cnt.value, C.byref(cnt), C.byref(it), C.byref(conv)))
+        return h, it.value, bool(conv.value)
+
+    def num_levels(self):
+        n = C.c_int()
+        _chk(lib().pe_api_solver_num_levels(self.h, C.byref(n)))
+        return n.value
+
+    def level_info(self, l):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(lib().pe_api_solver_level_info(self.h, l, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def level_matrix(self, l):
+        import scipy.sparse as sp
+        n, nnz, _ = self.level_info(l)
+        I, J, A = np.empty(n + 1, dtype=np.int32), np.empty(nnz, dtype=np.int32), np.empty(nnz)
+        _chk(lib().pe_api_solver_level_matrix(self.h, l, _ptr(I), _ptr(J), _ptr(A)))
+        M = sp.csr_matrix((n, n))
+        M.data, M.indices, M.indptr = A, J, I
+        return M
+
+    def free(self):
+        if self.h:
+            lib().pe_api_solver_free(self.h)
+            self.h = None
+
+
+def timer(name):
+    s = C.c_double()
+    _chk(lib().pe_api_timer_get(name.encode(), C.byref(s)))
+    return s.value

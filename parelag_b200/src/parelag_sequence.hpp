@@ -1,0 +1,137 @@
+// parelag_sequence.hpp -- the DeRhamSequence *coarse-operator interface* the solver
+// layer consumes (src/amge/DeRhamSequence.hpp:116-468, .cpp:1082-1253): per level and
+// form the interpolator P_, the derivative D_, the dof handler's boundary marking, and
+// links to the coarser / finer sequence.  Operators are kept as host CSR (they are
+// setup-time objects); ComputeTrueP / ComputeTrueD hand the solver layer device ParCSR
+// matrices with the essential columns zeroed *in the pattern* exactly as
+// SparseMatrix::EliminateCols does in the reference.
+//
+// One rank <-> one mesh partition <-> one GPU; on a single rank dof == true dof
+// (SharingMap is the identity), which is the case implemented in this round.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <vector>
+#include "parelag_core.hpp"
+
+namespace parelag
+{
+struct HostCSR
+{
+    int nrows = 0, ncols = 0;
+    std::vector<int> I, J;
+    std::vector<double> A;
+    HostCSR() : I(1, 0) {}
+    HostCSR(int nr, int nc, const int *i, const int *j, const double *a)
+        : nrows(nr), ncols(nc), I(i, i + nr + 1), J(j, j + i[nr]), A(a, a + i[nr]) {}
+    int64_t nnz() const { return I.empty() ? 0 : I.back(); }
+    pe_parcsr_host View() const
+    {
+        pe_parcsr_host H{};
+        H.global_num_rows = nrows; H.global_num_cols = ncols;
+        H.num_rows = nrows; H.num_cols_diag = ncols; H.num_cols_offd = 0;
+        H.diag_i = I.data(); H.diag_j = J.data(); H.diag_data = A.data();
+        return H;
+    }
+};
+
+/// the part of DofHandler the solver layer needs (src/amge/DofHandler.cpp:315-333,812-853)
+class DofHandler
+{
+public:
+    int GetNDofs() const { return (int)BdrMask_.size(); }
+    /// bit (a) of mask[d] set <=> dof d lies on a facet carrying boundary attribute a+1
+    void SetBoundaryMask(std::vector<uint32_t> mask) { BdrMask_ = std::move(mask); }
+    const std::vector<uint32_t> &GetBoundaryMask() const { return BdrMask_; }
+    int MarkDofsOnSelectedBndr(const mfem::Array<int> &bndrAttributesMarker, mfem::Array<int> &dofMarker) const
+    {
+        PARELAG_TEST_FOR_EXCEPTION(dofMarker.Size() != GetNDofs(), std::runtime_error,
+                                   "DofHandler::MarkDofsOnSelectedBndr(...): Incorrect array size!");
+        uint32_t sel = 0;
+        for (int a = 0; a < bndrAttributesMarker.Size() && a < 32; ++a)
+            if (bndrAttributesMarker[a]) sel |= (1u << a);
+        int n = 0;
+        for (int d = 0; d < GetNDofs(); ++d)
+        {
+            dofMarker[d] = (BdrMask_[d] & sel) ? 1 : 0;
+            n += dofMarker[d];
+        }
+        return n;
+    }
+private:
+    std::vector<uint32_t> BdrMask_;
+};
+
+class DeRhamSequence : public std::enable_shared_from_this<DeRhamSequence>
+{
+public:
+    explicit DeRhamSequence(int nforms) : nForms_(nforms), Dof_(nforms), P_(nforms), D_(nforms) {}
+    virtual ~DeRhamSequence() = default;
+
+    int GetNumberOfForms() const noexcept { return nForms_; }
+    int GetNumberOfDofs(int jform) const { return Dof_.at(jform) ? Dof_[jform]->GetNDofs() : 0; }
+    int GetNumberOfTrueDofs(int jform) const { return GetNumberOfDofs(jform); }
+    DofHandler *GetDofHandler(int jform) const { return Dof_.at(jform).get(); }
+    void SetDofHandler(int jform, std::unique_ptr<DofHandler> d) { Dof_.at(jform) = std::move(d); }
+
+    /// P_[j] maps the COARSER level's form j to this level (stored on the finer
+    /// sequence, DeRhamSequence.hpp:696-704)
+    void SetP(int jform, HostCSR P) { P_.at(jform) = std::make_shared<HostCSR>(std::move(P)); }
+    void SetD(int jform, HostCSR D) { D_.at(jform) = std::make_shared<HostCSR>(std::move(D)); }
+    const HostCSR *GetP(int jform) const { return P_.at(jform).get(); }
+    const HostCSR *GetDerivativeOperator(int jform) const { return D_.at(jform).get(); }
+
+    std::shared_ptr<DeRhamSequence> CoarserSequence() const { return CoarserSequence_.lock(); }
+    std::shared_ptr<DeRhamSequence> ViewCoarserSequence() const { return CoarserSequence_.lock(); }
+    std::shared_ptr<DeRhamSequence> FinerSequence() const { return FinerSequence_.lock(); }
+    void SetCoarserSequence(const std::shared_ptr<DeRhamSequence> &c)
+    {
+        CoarserSequence_ = c;
+        if (c) c->FinerSequence_ = shared_from_this();
+    }
+
+    /// GetP(jform, ess) + IgnoreNonLocalRange: columns of marked COARSE dofs are zeroed
+    /// but kept in the pattern (DeRhamSequence.cpp:1142-1153,1241-1253)
+    std::unique_ptr<mfem::HypreParMatrix> ComputeTrueP(int jform, mfem::Array<int> &ess_label) const
+    {
+        auto coarser = CoarserSequence_.lock();
+        PARELAG_ASSERT(coarser);
+        PARELAG_TEST_FOR_EXCEPTION(!P_.at(jform), std::runtime_error, "DeRhamSequence::ComputeTrueP(): P_[" << jform << "] is not available");
+        HostCSR P = *P_[jform];
+        mfem::Array<int> marker(P.ncols);
+        marker = 0;
+        coarser->GetDofHandler(jform)->MarkDofsOnSelectedBndr(ess_label, marker);
+        for (size_t k = 0; k < P.J.size(); ++k)
+            if (marker[P.J[k]]) P.A[k] = 0.0;
+        return make_unique<mfem::HypreParMatrix>(P.View());
+    }
+    std::unique_ptr<mfem::HypreParMatrix> ComputeTrueP(int jform) const
+    {
+        PARELAG_TEST_FOR_EXCEPTION(!P_.at(jform), std::runtime_error, "DeRhamSequence::ComputeTrueP(): P_[" << jform << "] is not available");
+        return make_unique<mfem::HypreParMatrix>(P_[jform]->View());
+    }
+    /// ComputeDerivativeOperator(jform, ess) + IgnoreNonLocalRange (DeRhamSequence.cpp:1082-1099,1225-1239)
+    std::unique_ptr<mfem::HypreParMatrix> ComputeTrueD(int jform, mfem::Array<int> &ess_label) const
+    {
+        PARELAG_TEST_FOR_EXCEPTION(!D_.at(jform), std::runtime_error, "DeRhamSequence::ComputeTrueD(): D_[" << jform << "] is not available");
+        HostCSR D = *D_[jform];
+        mfem::Array<int> marker(D.ncols);
+        marker = 0;
+        GetDofHandler(jform)->MarkDofsOnSelectedBndr(ess_label, marker);
+        for (size_t k = 0; k < D.J.size(); ++k)
+            if (marker[D.J[k]]) D.A[k] = 0.0;
+        return make_unique<mfem::HypreParMatrix>(D.View());
+    }
+    std::unique_ptr<mfem::HypreParMatrix> ComputeTrueD(int jform) const
+    {
+        PARELAG_TEST_FOR_EXCEPTION(!D_.at(jform), std::runtime_error, "DeRhamSequence::ComputeTrueD(): D_[" << jform << "] is not available");
+        return make_unique<mfem::HypreParMatrix>(D_[jform]->View());
+    }
+
+protected:
+    int nForms_;
+    std::vector<std::unique_ptr<DofHandler>> Dof_;
+    std::vector<std::shared_ptr<HostCSR>> P_, D_;
+    std::weak_ptr<DeRhamSequence> CoarserSequence_, FinerSequence_;
+};
+} // namespace parelag

@@ -1,0 +1,622 @@
+// parelag_solvers.hpp -- solver operators and factories of the AMGe solve path, with
+// the reference's class names and parameter names; every Mult() runs on the GPU
+// through the C ABI (include/parelag_b200.h).
+//   HypreSmootherWrapper    src/linalg/solver_ops/ParELAG_HypreSmootherWrapper.{hpp:69-83,cpp:20-35}
+//   HypreSmootherFactory    src/linalg/factories/ParELAG_HypreSmootherFactory.cpp:21-43,92-109
+//   HiptmairSmoother        src/linalg/solver_ops/ParELAG_HiptmairSmoother.cpp:48-109
+//   HiptmairSmootherFactory src/linalg/factories/ParELAG_HiptmairSmootherFactory.cpp:52-179
+//   KrylovSolver            src/linalg/solver_ops/ParELAG_KrylovSolver.{cpp:23-96,hpp:68-110} (mfem::CGSolver::Mult)
+//   KrylovSolverFactory     src/linalg/factories/ParELAG_KrylovSolverFactory.cpp:25-118
+//   Hierarchy               src/linalg/solver_ops/ParELAG_Hierarchy.cpp:109-267,282-383
+//   AMGeSolverFactory       src/linalg/factories/ParELAG_AMGeSolverFactory.cpp:26-209
+//   StationarySolver        src/linalg/solver_ops/ParELAG_StationarySolver.cpp:41-147
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include "parelag_core.hpp"
+#include "parelag_sequence.hpp"
+
+namespace parelag
+{
+using Op_Ptr = std::shared_ptr<mfem::Operator>;
+
+namespace mg_utils
+{
+/// -(A x - b), bitwise equal to b - A x (src/linalg/utilities/ParELAG_MG_Utils.hpp:405-467)
+inline void ComputeResidual(const mfem::Operator &A, const mfem::Vector &x, const mfem::Vector &b, mfem::Vector &r)
+{
+    auto A_hyp = dynamic_cast<const mfem::HypreParMatrix *>(&A);
+    PARELAG_TEST_FOR_EXCEPTION(!A_hyp, std::runtime_error, "ComputeResidual(): operator is not a HypreParMatrix");
+    r.SetSize(b.Size());
+    PE_CALL(pe_residual(Device::Get(), A_hyp->Handle(), x.Read(), b.Read(), r.Write()));
+}
+} // namespace mg_utils
+
+// ------------------------------------------------------------------ Hypre smoother
+class HypreSmootherWrapper : public Solver
+{
+public:
+    HypreSmootherWrapper(const Op_Ptr &A, int type, ParameterList &params)
+        : Solver(A->Height(), A->Width(), true), A_(std::dynamic_pointer_cast<mfem::HypreParMatrix>(A))
+    {
+        PARELAG_TEST_FOR_EXCEPTION(!A_, std::runtime_error, "HypreSmootherWrapper: operator must be a HypreParMatrix");
+        const int sweeps = params.Get("Sweeps", 1);
+        const double damping = params.Get("Damping Factor", 1.0);
+        const double omega = params.Get("Omega", 1.0);
+        const int cheby_order = params.Get("Cheby Poly Order", 2);
+        const double cheby_frac = params.Get("Cheby Poly Fraction", 0.3);
+        // how hypre's sequential row order is realised on the GPU:
+        // "natural" reproduces hypre exactly (level scheduling), "multicolor" is the fast mode
+        const std::string ordering = params.Get("GS ordering", "natural");
+        PARELAG_TEST_FOR_EXCEPTION(ordering != "natural" && ordering != "multicolor", std::runtime_error,
+                                   "HypreSmootherWrapper: \"GS ordering\" must be \"natural\" or \"multicolor\"");
+        PE_CALL(pe_smoother_create(Device::Get(), A_->Handle(), type, sweeps, damping, omega, cheby_order, cheby_frac,
+                                   ordering == "natural" ? PE_GS_ORDER_NATURAL : PE_GS_ORDER_MULTICOLOR, &smoo_));
+    }
+    ~HypreSmootherWrapper() override { pe_smoother_free(smoo_); }
+    void Mult(const mfem::Vector &rhs, mfem::Vector &sol) const override
+    {
+        PE_CALL(pe_smoother_apply(smoo_, rhs.Read(), this->iterative_mode ? sol.ReadWrite() : sol.Write(),
+                                  this->iterative_mode ? 1 : 0));
+    }
+    /// all supported relaxations are symmetric operators
+    void MultTranspose(const mfem::Vector &rhs, mfem::Vector &sol) const override { Mult(rhs, sol); }
+private:
+    void _do_set_operator(const Op_Ptr &) override { PARELAG_NOT_IMPLEMENTED(); }
+    std::shared_ptr<mfem::HypreParMatrix> A_;
+    pe_smoother *smoo_ = nullptr;
+};
+
+class HypreSmootherFactory : public SolverFactory
+{
+    std::unique_ptr<mfem::Solver> _do_build_solver(const Op_Ptr &op, SolverState &) const override
+    {
+        auto &params = GetParameters();
+        const std::string name = params.Get("Type", "L1 Gauss-Seidel");
+        return make_unique<HypreSmootherWrapper>(op, TypeFromName(name), params);
+    }
+    void _do_set_default_parameters() override
+    {
+        auto &p = GetParameters();
+        p.Get("Type", "L1 Gauss-Seidel"); p.Get("Sweeps", 1); p.Get("Damping Factor", 1.0); p.Get("Omega", 1.0);
+        p.Get("Cheby Poly Order", 2); p.Get("Cheby Poly Fraction", 0.3);
+    }
+    void _do_initialize(const ParameterList &) override {}
+public:
+    static int TypeFromName(const std::string &n)
+    {
+        if (n == "Jacobi") return 0;
+        if (n == "L1 Jacobi") return 1;
+        if (n == "L1 Gauss-Seidel") return 2;
+        if (n == "L1 Gauss-Seidel Truncated") return 4;
+        if (n == "Lumped Jacobi") return 5;
+        if (n == "Gauss-Seidel") return 6;
+        if (n == "Chebyshev") return 16;
+        PARELAG_TEST_FOR_EXCEPTION(true, std::runtime_error,
+                                   "HypreSmootherFactory: smoother type \"" << n << "\" is not supported on the GPU path "
+                                   "(supported: Jacobi, L1 Jacobi, L1 Gauss-Seidel, L1 Gauss-Seidel Truncated, Lumped Jacobi, Gauss-Seidel, Chebyshev)");
+        return -1;
+    }
+};
+
+// ------------------------------------------------------------------ Hiptmair
+class HiptmairSmoother : public Solver
+{
+public:
+    HiptmairSmoother(Op_Ptr A, Op_Ptr A_Aux, Op_Ptr D_Op, std::shared_ptr<mfem::Solver> PrimarySolver,
+                     std::shared_ptr<mfem::Solver> AuxiliarySolver)
+        : Solver(A->Height(), A->Width(), true), A_(std::move(A)), A_aux_(std::move(A_Aux)), D_op_(std::move(D_Op)),
+          PrimarySolver_(std::move(PrimarySolver)), AuxiliarySolver_(std::move(AuxiliarySolver))
+    {
+        PARELAG_ASSERT(A_); PARELAG_ASSERT(D_op_); PARELAG_ASSERT(PrimarySolver_); PARELAG_ASSERT(AuxiliarySolver_);
+        AuxB_.SetSize(D_op_->Width());
+        AuxX_.SetSize(D_op_->Width());
+        PrimaryVec_.SetSize(A_->Height());
+    }
+    void Mult(const mfem::Vector &B, mfem::Vector &X) const override
+    {
+        if (this->IsPreconditioner()) X = 0.0;
+        PARELAG_ASSERT(PrimarySolver_->iterative_mode);
+        PrimarySolver_->Mult(B, X);
+        mg_utils::ComputeResidual(*A_, X, B, PrimaryVec_);
+        D_op_->MultTranspose(PrimaryVec_, AuxB_);
+        PARELAG_ASSERT(!AuxiliarySolver_->iterative_mode);
+        AuxiliarySolver_->Mult(AuxB_, AuxX_);
+        D_op_->Mult(AuxX_, PrimaryVec_);
+        X += PrimaryVec_;
+    }
+    void MultTranspose(const mfem::Vector &B, mfem::Vector &X) const override
+    {
+        if (this->IsPreconditioner()) { X = 0.0; D_op_->MultTranspose(B, AuxB_); }
+        else { mg_utils::ComputeResidual(*A_, X, B, PrimaryVec_); D_op_->MultTranspose(PrimaryVec_, AuxB_); }
+        AuxiliarySolver_->Mult(AuxB_, AuxX_);
+        D_op_->Mult(AuxX_, PrimaryVec_);
+        X += PrimaryVec_;
+        PrimarySolver_->Mult(B, X);
+    }
+    Op_Ptr GetAuxiliaryOperator() const { return A_aux_; }
+private:
+    void _do_set_operator(const Op_Ptr &) override { PARELAG_NOT_IMPLEMENTED(); }
+    Op_Ptr A_, A_aux_, D_op_;
+    std::shared_ptr<mfem::Solver> PrimarySolver_, AuxiliarySolver_;
+    mutable mfem::Vector AuxB_, AuxX_, PrimaryVec_;
+};
+
+class HiptmairSmootherFactory : public SolverFactory
+{
+    std::unique_ptr<mfem::Solver> _do_build_solver(const Op_Ptr &op, SolverState &state) const override
+    {
+        auto my_state = dynamic_cast<NestedSolverState *>(&state);
+        PARELAG_ASSERT(my_state);
+        auto primary_state = std::shared_ptr<SolverState>{PrimaryFact_->GetDefaultState()};
+        auto aux_state = std::shared_ptr<SolverState>{AuxiliaryFact_->GetDefaultState()};
+        if (my_state->IsSubState("Primary")) primary_state->MergeState(*my_state->GetSubState("Primary"));
+        if (my_state->IsSubState("Auxiliary")) aux_state->MergeState(*my_state->GetSubState("Auxiliary"));
+        primary_state->MergeState(*my_state);
+        std::vector<int> aux_forms;
+        for (int f : primary_state->GetForms()) aux_forms.push_back(f - 1);
+        aux_state->SetForms(std::move(aux_forms));      // aux space is one form lower
+        aux_state->MergeState(*my_state);
+
+        auto d_op = my_state->GetOperator("D");
+        if (!d_op)
+        {
+            Timer d_timer = TimeManager::AddTimer("Hiptmair: Build D");
+            auto &sequence = state.GetDeRhamSequence();
+            auto form = state.GetForms().front();
+            PARELAG_ASSERT(form > 0);
+            auto ess_attr = state.GetBoundaryLabels(0);
+            if (ess_attr.size() > 0)
+            {
+                mfem::Array<int> label_ess(ess_attr.data(), (int)ess_attr.size());
+                d_op = sequence.ComputeTrueD(form - 1, label_ess);
+            }
+            else
+                d_op = sequence.ComputeTrueD(form - 1);
+        }
+        PARELAG_ASSERT(d_op);
+        Timer pri_timer = TimeManager::AddTimer("Hiptmair: Build primary smoother");
+        auto PrimarySmoo = std::shared_ptr<mfem::Solver>{PrimaryFact_->BuildSolver(op, *primary_state)};
+        PrimarySmoo->iterative_mode = true;
+        pri_timer.Stop();
+        Timer aux_op_timer = TimeManager::AddTimer("Hiptmair: Build auxiliary operator");
+        auto aux_op = my_state->GetOperator("Auxiliary A");
+        if (!aux_op) aux_op = _do_compute_aux_operator(*op, *d_op);
+        aux_op_timer.Stop();
+        PARELAG_ASSERT(aux_op);
+        Timer aux_timer = TimeManager::AddTimer("Hiptmair: Build auxiliary smoother");
+        auto AuxiliarySmoo = std::shared_ptr<mfem::Solver>{AuxiliaryFact_->BuildSolver(aux_op, *aux_state)};
+        AuxiliarySmoo->iterative_mode = false;
+        aux_timer.Stop();
+        return make_unique<HiptmairSmoother>(op, aux_op, d_op, PrimarySmoo, AuxiliarySmoo);
+    }
+    /// D^T A D followed by FixZeroRows (HiptmairSmootherFactory.cpp:143-165)
+    Op_Ptr _do_compute_aux_operator(mfem::Operator &A, mfem::Operator &D) const
+    {
+        PARELAG_TEST_FOR_EXCEPTION(A.Width() != D.Height(), std::runtime_error,
+                                   "A and D do not have compatible sizes to compute D^T*A*D!\nA = " << A.Height() << "x" << A.Width()
+                                   << "\nD = " << D.Height() << "x" << D.Width());
+        auto A_hyp = dynamic_cast<mfem::HypreParMatrix *>(&A);
+        auto D_hyp = dynamic_cast<mfem::HypreParMatrix *>(&D);
+        PARELAG_TEST_FOR_EXCEPTION(!A_hyp || !D_hyp, std::runtime_error, "Hiptmair: A and D must be HypreParMatrix");
+        std::shared_ptr<mfem::HypreParMatrix> ret{mfem::RAP(A_hyp, D_hyp)};
+        hypre_ParCSRMatrixFixZeroRows(*ret);
+        return ret;
+    }
+    void _do_set_default_parameters() override {}
+    void _do_initialize(const ParameterList &) override
+    {
+        PARELAG_ASSERT(HasValidSolverLibrary());
+        PrimaryFact_ = GetSolverLibrary().GetSolverFactory(GetParameters().Get<std::string>("Primary Smoother"));
+        AuxiliaryFact_ = GetSolverLibrary().GetSolverFactory(GetParameters().Get<std::string>("Auxiliary Smoother"));
+    }
+    std::shared_ptr<SolverFactory> PrimaryFact_, AuxiliaryFact_;
+};
+
+// ------------------------------------------------------------------ Krylov (PCG)
+/// mfem::CGSolver::Mult restated (preconditioned CG with MFEM's stopping rule and
+/// its "(B r, r)" monitor); dots are device reductions + ncclAllReduce.
+class KrylovSolver : public Solver
+{
+public:
+    KrylovSolver(Op_Ptr A, std::shared_ptr<mfem::Solver> Prec, ParameterList &params)
+        : Solver(A->Height(), A->Width(), false), A_(std::move(A)), Prec_(std::move(Prec))
+    {
+        const std::string name = params.Get("Solver name", "PCG");
+        PARELAG_TEST_FOR_EXCEPTION(name != "PCG" && name != "CG", std::runtime_error,
+                                   "KrylovSolver: solver \"" << name << "\" is not available on the GPU path in this round (PCG only)");
+        print_level_ = params.Get("Print level", -1);
+        rel_tol_ = params.Get("Relative tolerance", 0.0);
+        abs_tol_ = params.Get("Absolute tolerance", 0.0);
+        max_iter_ = params.Get("Maximum iterations", 10);
+        final_paragraph_ = params.Get("Print final paragraph", false);
+    }
+    void Mult(const mfem::Vector &b, mfem::Vector &x) const override
+    {
+        const int n = Height();
+        r_.SetSize(n); d_.SetSize(n); z_.SetSize(n);
+        history_.clear();
+        converged_ = false; final_iter_ = 0;
+        if (this->iterative_mode) { A_->Mult(x, r_); mfem::add(b, -1.0, r_, r_); }
+        else { r_ = b; x = 0.0; }
+        if (Prec_) { Prec_->Mult(r_, z_); d_ = z_; }
+        else d_ = r_;
+        double nom0, nom, betanom, alpha, beta, den;
+        nom0 = nom = d_ * r_;
+        history_.push_back(nom);
+        if (print_level_ == 1) std::printf("   Iteration : %3d  (B r, r) = %g\n", 0, nom);
+        if (nom < 0.0) { final_norm_ = nom; return; }
+        const double r0 = std::max(nom * rel_tol_ * rel_tol_, abs_tol_ * abs_tol_);
+        if (nom <= r0) { converged_ = true; final_norm_ = std::sqrt(nom); return; }
+        A_->Mult(d_, z_);
+        den = z_ * d_;
+        if (den <= 0.0) { final_norm_ = std::sqrt(nom); return; }
+        int i = 1;
+        while (true)
+        {
+            alpha = nom / den;
+            x.Add(alpha, d_);
+            r_.Add(-alpha, z_);
+            if (Prec_) { Prec_->Mult(r_, z_); betanom = r_ * z_; }
+            else betanom = r_ * r_;
+            history_.push_back(betanom);
+            if (print_level_ == 1) std::printf("   Iteration : %3d  (B r, r) = %g\n", i, betanom);
+            if (betanom < r0) { converged_ = true; final_iter_ = i; break; }
+            if (++i > max_iter_) break;
+            beta = betanom / nom;
+            if (Prec_) { d_ *= beta; d_ += z_; }        // d = z + beta d
+            else { d_ *= beta; d_ += r_; }
+            A_->Mult(d_, z_);
+            den = d_ * z_;
+            if (den <= 0.0) break;
+            nom = betanom;
+        }
+        if (!converged_) final_iter_ = max_iter_;
+        final_norm_ = std::sqrt(std::fabs(betanom));
+        if (final_paragraph_ || print_level_ >= 0)
+            std::printf("PCG: %s after %d iterations, (B r, r) = %g, (B r_0, r_0) = %g\n",
+                        converged_ ? "converged" : "NOT converged", final_iter_, betanom, nom0);
+    }
+    int GetNumIterations() const { return final_iter_; }
+    bool GetConverged() const { return converged_; }
+    double GetFinalNorm() const { return final_norm_; }
+    /// history[i] = (B r, r) after iteration i (history[0]: initial) -- what MFEM prints
+    const std::vector<double> &GetResidualHistory() const { return history_; }
+private:
+    void _do_set_operator(const Op_Ptr &op) override { A_ = op; }
+    Op_Ptr A_;
+    std::shared_ptr<mfem::Solver> Prec_;
+    int print_level_ = -1, max_iter_ = 10;
+    double rel_tol_ = 0.0, abs_tol_ = 0.0;
+    bool final_paragraph_ = false;
+    mutable mfem::Vector r_, d_, z_;
+    mutable std::vector<double> history_;
+    mutable bool converged_ = false;
+    mutable int final_iter_ = 0;
+    mutable double final_norm_ = 0.0;
+};
+
+class KrylovSolverFactory : public SolverFactory
+{
+    std::unique_ptr<mfem::Solver> _do_build_solver(const Op_Ptr &op, SolverState &state) const override
+    {
+        auto my_state = dynamic_cast<NestedSolverState *>(&state);
+        PARELAG_ASSERT(my_state);
+        std::shared_ptr<mfem::Solver> prec;
+        if (Prec_Factory_)
+        {
+            auto prec_state = std::shared_ptr<SolverState>{Prec_Factory_->GetDefaultState()};
+            if (my_state->IsSubState("Preconditioner")) prec_state->MergeState(*my_state->GetSubState("Preconditioner"));
+            prec_state->MergeState(*my_state);
+            prec = Prec_Factory_->BuildSolver(op, *prec_state);
+            prec->iterative_mode = false;
+        }
+        return make_unique<KrylovSolver>(op, prec, GetParameters());
+    }
+    void _do_set_default_parameters() override
+    {
+        auto &p = GetParameters();
+        p.Get<int>("Print level", -1); p.Get<double>("Relative tolerance", 0.0); p.Get<double>("Absolute tolerance", 0.0);
+        p.Get<int>("Maximum iterations", 10); p.Get<int>("Restart size", 50); p.Get<bool>("Print final paragraph", false);
+        p.Get<bool>("Time preconditioner setup", false); p.Get<std::string>("Timer name suffix", "");
+    }
+    void _do_initialize(const ParameterList &) override
+    {
+        PARELAG_ASSERT(HasValidSolverLibrary());
+        std::string prec_name = GetParameters().Get("Preconditioner", "None");
+        if (prec_name != "None") Prec_Factory_ = GetSolverLibrary().GetSolverFactory(prec_name);
+    }
+    std::shared_ptr<SolverFactory> Prec_Factory_;
+};
+
+// ------------------------------------------------------------------ Hierarchy
+class Hierarchy : public Solver
+{
+public:
+    Hierarchy(const Op_Ptr &A, int NumLevels)
+        : Solver(A->Height(), A->Width(), false), CoarseResids_(NumLevels), CoarseSols_(NumLevels), CycleMu_(NumLevels, 0)
+    {
+        for (int l = 0; l < NumLevels; ++l) Levels_.push_back(std::make_shared<Level>(l));
+        Levels_.front()->Set<Op_Ptr>("A", A);
+    }
+    int GetNumLevels() const noexcept { return (int)Levels_.size(); }
+    Level &GetLevel(int l) { return *Levels_.at(l); }
+    std::vector<std::shared_ptr<Level>>::const_iterator begin() const { return Levels_.begin(); }
+    std::vector<std::shared_ptr<Level>>::const_iterator end() const { return Levels_.end(); }
+    void SetImplicitTranspose(bool v) noexcept { ImplicitTranspose_ = v; }
+
+    /// one V-cycle (the "Cycle type" parameter is never read by the reference)
+    void Mult(const mfem::Vector &rhs, mfem::Vector &sol) const override
+    {
+        if (this->IsPreconditioner())
+        {
+            sol = 0.0;
+            Iterate(rhs, sol, 0, 1, false);
+        }
+        else
+        {
+            mfem::Vector rhs_view(rhs.Size()), sol_view(sol.Size());
+            Levels_.front()->Get<Op_Ptr>("A")->Mult(sol, rhs_view);
+            rhs_view *= -1.0;
+            rhs_view += rhs;
+            sol_view = 0.0;
+            Iterate(rhs_view, sol_view, 0, 1, false);
+            sol += sol_view;
+        }
+    }
+    void Iterate(const mfem::Vector &RHS, mfem::Vector &SOL, int StartLevel, int NumIterations, bool CycleThisLevel) const
+    {
+        for (int iteration = 1; iteration <= NumIterations; ++iteration)
+        {
+            if (StartLevel == (int)Levels_.size() - 1)
+            {
+                Level &Coarse = *Levels_[StartLevel];
+                if (Coarse.IsValidKey("CoarseSolver")) Coarse.Get<Op_Ptr>("CoarseSolver")->Mult(RHS, SOL);
+                else
+                {
+                    if (Coarse.IsValidKey("PreSmoother")) Coarse.Get<Op_Ptr>("PreSmoother")->Mult(RHS, SOL);
+                    if (Coarse.IsValidKey("PostSmoother")) Coarse.Get<Op_Ptr>("PostSmoother")->Mult(RHS, SOL);
+                }
+                continue;
+            }
+            Level &Fine = *Levels_[StartLevel];
+            Level &Coarse = *Levels_[StartLevel + 1];
+            if (Fine.IsValidKey("PreSmoother")) Fine.Get<Op_Ptr>("PreSmoother")->Mult(RHS, SOL);
+            // residual (K1+K7 fused: r = b - A x in one pass)
+            tmp_resid_[StartLevel].SetSize(RHS.Size());
+            mg_utils::ComputeResidual(*Fine.Get<Op_Ptr>("A"), SOL, RHS, tmp_resid_[StartLevel]);
+            auto &P = Coarse.Get<Op_Ptr>("P");
+            if (ImplicitTranspose_ || !Fine.IsKey("R")) P->MultTranspose(tmp_resid_[StartLevel], CoarseResids_[StartLevel + 1]);
+            else Fine.Get<Op_Ptr>("R")->Mult(tmp_resid_[StartLevel], CoarseResids_[StartLevel + 1]);
+            CoarseSols_[StartLevel + 1] = 0.0;
+            int cycle_times = 0;
+            if (CycleThisLevel && CycleMu_.size() > 1) cycle_times = CycleMu_[StartLevel];
+            for (int cycle = 0; cycle <= cycle_times; ++cycle)
+                Iterate(CoarseResids_[StartLevel + 1], CoarseSols_[StartLevel + 1], StartLevel + 1, 1, false);
+            // SOL += P * e  (K1 with beta = 1: prolongation and correction in one pass)
+            auto P_hyp = std::dynamic_pointer_cast<mfem::HypreParMatrix>(P);
+            if (P_hyp) P_hyp->Mult(1.0, CoarseSols_[StartLevel + 1], 1.0, SOL);
+            else
+            {
+                tmp_correct_[StartLevel].SetSize(P->Height());
+                P->Mult(CoarseSols_[StartLevel + 1], tmp_correct_[StartLevel]);
+                SOL += tmp_correct_[StartLevel];
+            }
+            if (Fine.IsValidKey("PostSmoother")) Fine.Get<Op_Ptr>("PostSmoother")->Mult(RHS, SOL);
+        }
+    }
+    void Finalize()
+    {
+        tmp_resid_.resize(Levels_.size());
+        tmp_correct_.resize(Levels_.size());
+        for (size_t l = 0; l < Levels_.size(); ++l)
+        {
+            const int n = Levels_[l]->Get<Op_Ptr>("A")->Height();
+            CoarseResids_[l].SetSize(n);
+            CoarseSols_[l].SetSize(n);
+        }
+    }
+private:
+    void _do_set_operator(const Op_Ptr &) override { PARELAG_NOT_IMPLEMENTED(); }
+    std::vector<std::shared_ptr<Level>> Levels_;
+    mutable std::vector<mfem::Vector> CoarseResids_, CoarseSols_, tmp_resid_, tmp_correct_;
+    std::vector<int> CycleMu_;
+    bool ImplicitTranspose_ = true;
+};
+
+/// Hierarchy.cpp:282-383: per coarse level P = ComputeTrueP(form, ess); A <- P^T A P; FixZeroRows
+inline std::unique_ptr<Hierarchy> buildHierarchyFromDeRhamSequence(const Op_Ptr &A_in, const DeRhamSequence &Sequence,
+                                                                   std::vector<int> &label_ess, int form, int MaxLevels)
+{
+    int NumLevels = 1;
+    {
+        auto seq = Sequence.ViewCoarserSequence();
+        while (seq && (MaxLevels < 0 || NumLevels < MaxLevels)) { ++NumLevels; seq = seq->ViewCoarserSequence(); }
+    }
+    auto H = make_unique<Hierarchy>(A_in, NumLevels);
+    H->SetImplicitTranspose(true);
+    auto A = std::dynamic_pointer_cast<mfem::HypreParMatrix>(A_in);
+    PARELAG_TEST_FOR_EXCEPTION(!A, std::runtime_error, "buildHierarchyFromDeRhamSequence(): operator must be a HypreParMatrix");
+    const DeRhamSequence *seq = &Sequence;
+    std::shared_ptr<DeRhamSequence> hold;
+    const bool have_ess = !label_ess.empty();
+    for (int l = 1; l < NumLevels; ++l)
+    {
+        Level &Coarse = H->GetLevel(l);
+        std::shared_ptr<mfem::HypreParMatrix> P;
+        if (have_ess)
+        {
+            mfem::Array<int> ess(label_ess.data(), (int)label_ess.size());
+            P = seq->ComputeTrueP(form, ess);
+        }
+        else P = seq->ComputeTrueP(form);
+        std::shared_ptr<mfem::HypreParMatrix> Ac{mfem::RAP(A.get(), P.get())};
+        if (have_ess) hypre_ParCSRMatrixFixZeroRows(*Ac);
+        Coarse.Set<Op_Ptr>("P", P);
+        Coarse.Set<Op_Ptr>("A", Ac);
+        A = Ac;
+        hold = seq->CoarserSequence();
+        seq = hold.get();
+    }
+    H->Finalize();
+    return H;
+}
+
+class AMGeSolverFactory : public SolverFactory
+{
+    std::unique_ptr<mfem::Solver> _do_build_solver(const Op_Ptr &op, SolverState &state) const override
+    {
+        auto my_state = dynamic_cast<NestedSolverState *>(&state);
+        PARELAG_ASSERT(my_state);
+        auto sequence = state.GetDeRhamSequencePtr();
+        PARELAG_TEST_FOR_EXCEPTION(!sequence, std::runtime_error, "AMGeSolverFactory: the state has no DeRhamSequence");
+        if (Forms_.size() == 0) Forms_ = state.GetForms();
+        PARELAG_ASSERT(Forms_.size() > 0);
+        PARELAG_TEST_FOR_EXCEPTION(Forms_.size() != 1, not_implemented_error,
+                                   "AMGeSolverFactory: blocked hierarchies (Forms.size() > 1) are not available in this round");
+        std::unique_ptr<Hierarchy> H;
+        {
+            Timer t = TimeManager::AddTimer("Build Hierarchy: build from deRham Sequence");
+            auto &ess_attr = state.GetBoundaryLabels(0);
+            H = buildHierarchyFromDeRhamSequence(op, *sequence, ess_attr, Forms_.front(), MaxLevels_);
+        }
+        const int CoarsestLevelID = H->GetNumLevels() - 1;
+        for (const auto &level : *H)
+        {
+            Level &lev = *level;
+            const int LevelID = lev.GetLevelID();
+            Timer fill = TimeManager::AddTimer("Build Hierarchy: fill level " + std::to_string(LevelID));
+            auto A_ptr = lev.Get<Op_Ptr>("A");
+            if (print_levels_)
+                if (auto A_hyp = std::dynamic_pointer_cast<mfem::HypreParMatrix>(A_ptr))
+                    std::cout << "Level " << LevelID << ": A = " << A_hyp->M() << "x" << A_hyp->N() << ", nnz = " << A_hyp->NNZ() << "\n";
+            if (LevelID < CoarsestLevelID)
+            {
+                auto pre_state = std::shared_ptr<SolverState>{PreSmootherFact_->GetDefaultState()};
+                auto post_state = std::shared_ptr<SolverState>{PostSmootherFact_->GetDefaultState()};
+                if (my_state->IsSubState("PreSmoother")) pre_state->MergeState(*my_state->GetSubState("PreSmoother"));
+                if (my_state->IsSubState("PostSmoother")) post_state->MergeState(*my_state->GetSubState("PostSmoother"));
+                pre_state->MergeState(state); post_state->MergeState(state);
+                pre_state->SetDeRhamSequence(sequence); post_state->SetDeRhamSequence(sequence);
+                Timer st = TimeManager::AddTimer("Build smoother: level " + std::to_string(LevelID));
+                std::shared_ptr<mfem::Solver> pre = PreSmootherFact_->BuildSolver(A_ptr, *pre_state);
+                // the reference builds the post-smoother separately even when the factories
+                // coincide; the operator is identical, so it is shared here
+                std::shared_ptr<mfem::Solver> post = (PreSmootherFact_ == PostSmootherFact_) ? pre
+                                                     : std::shared_ptr<mfem::Solver>(PostSmootherFact_->BuildSolver(A_ptr, *post_state));
+                st.Stop();
+                pre->iterative_mode = true; post->iterative_mode = true;
+                lev.Set<Op_Ptr>("PreSmoother", pre);
+                lev.Set<Op_Ptr>("PostSmoother", post);
+            }
+            else
+            {
+                auto coarse_state = std::shared_ptr<SolverState>{CoarseSolverFact_->GetDefaultState()};
+                if (my_state->IsSubState("Coarse solver")) coarse_state->MergeState(*my_state->GetSubState("Coarse solver"));
+                coarse_state->MergeState(state);
+                coarse_state->SetDeRhamSequence(sequence);
+                Timer ct = TimeManager::AddTimer("Build coarse solver: level " + std::to_string(LevelID));
+                lev.Set<Op_Ptr>("CoarseSolver", Op_Ptr(CoarseSolverFact_->BuildSolver(A_ptr, *coarse_state)));
+            }
+            sequence = sequence->CoarserSequence();
+        }
+        return H;
+    }
+    void _do_set_default_parameters() override {}
+    void _do_initialize(const ParameterList &) override
+    {
+        auto &params = GetParameters();
+        if (params.IsParameter("Smoother"))
+        {
+            PreSmootherFact_ = GetSolverLibrary().GetSolverFactory(params.Get<std::string>("Smoother"));
+            PostSmootherFact_ = PreSmootherFact_;
+        }
+        else
+        {
+            if (params.IsParameter("PreSmoother")) PreSmootherFact_ = GetSolverLibrary().GetSolverFactory(params.Get<std::string>("PreSmoother"));
+            if (params.IsParameter("PostSmoother")) PostSmootherFact_ = GetSolverLibrary().GetSolverFactory(params.Get<std::string>("PostSmoother"));
+        }
+        if (params.IsParameter("Coarse solver")) CoarseSolverFact_ = GetSolverLibrary().GetSolverFactory(params.Get<std::string>("Coarse solver"));
+        MaxLevels_ = params.Get("Maximum levels", -1);
+        Forms_ = params.Get("Forms", std::vector<int>());
+        print_levels_ = params.Get("Print level summary", false);
+    }
+    std::shared_ptr<SolverFactory> PreSmootherFact_, PostSmootherFact_, CoarseSolverFact_;
+    int MaxLevels_ = -1;
+    mutable std::vector<int> Forms_;
+    bool print_levels_ = false;
+};
+
+// ------------------------------------------------------------------ Stationary iteration
+class StationarySolver : public Solver
+{
+public:
+    StationarySolver(Op_Ptr A, std::shared_ptr<mfem::Solver> S, double rtol, double atol, int maxit, bool print)
+        : Solver(A->Height(), A->Width(), true), A_(std::move(A)), Solver_(std::move(S)), RelTol_(rtol), AbsTol_(atol), MaxIts_(maxit), Print_(print) {}
+    void Mult(const mfem::Vector &rhs, mfem::Vector &sol) const override
+    {
+        const int n = Height();
+        Resid_.SetSize(n); Corr_.SetSize(n);
+        if (this->IsPreconditioner()) sol = 0.0;
+        auto A_hyp = std::dynamic_pointer_cast<mfem::HypreParMatrix>(A_);
+        mg_utils::ComputeResidual(*A_hyp, sol, rhs, Resid_);
+        double r0 = std::sqrt(Resid_ * Resid_), r = r0;
+        int it = 0;
+        while (it < MaxIts_ && r > std::max(RelTol_ * r0, AbsTol_))
+        {
+            const bool mode = Solver_->iterative_mode;
+            Solver_->iterative_mode = false;
+            Solver_->Mult(Resid_, Corr_);
+            Solver_->iterative_mode = mode;
+            sol += Corr_;
+            mg_utils::ComputeResidual(*A_hyp, sol, rhs, Resid_);
+            r = std::sqrt(Resid_ * Resid_);
+            ++it;
+            if (Print_) std::printf("  Stationary iteration %3d : ||r|| = %g\n", it, r);
+        }
+        NumIts_ = it; FinalNorm_ = r;
+    }
+    int GetNumIterations() const { return NumIts_; }
+    double GetFinalNorm() const { return FinalNorm_; }
+private:
+    void _do_set_operator(const Op_Ptr &op) override { A_ = op; }
+    Op_Ptr A_;
+    std::shared_ptr<mfem::Solver> Solver_;
+    double RelTol_, AbsTol_;
+    int MaxIts_;
+    bool Print_;
+    mutable mfem::Vector Resid_, Corr_;
+    mutable int NumIts_ = 0;
+    mutable double FinalNorm_ = 0.0;
+};
+
+class StationarySolverFactory : public SolverFactory
+{
+    std::unique_ptr<mfem::Solver> _do_build_solver(const Op_Ptr &op, SolverState &state) const override
+    {
+        auto my_state = dynamic_cast<NestedSolverState *>(&state);
+        PARELAG_ASSERT(my_state);
+        auto s_state = std::shared_ptr<SolverState>{Fact_->GetDefaultState()};
+        s_state->MergeState(*my_state);
+        std::shared_ptr<mfem::Solver> s = Fact_->BuildSolver(op, *s_state);
+        auto &p = GetParameters();
+        return make_unique<StationarySolver>(op, s, p.Get("Relative tolerance", 0.0), p.Get("Absolute tolerance", 0.0),
+                                             p.Get("Maximum iterations", 10), p.Get("Print level", -1) > 0);
+    }
+    void _do_set_default_parameters() override {}
+    void _do_initialize(const ParameterList &) override
+    {
+        Fact_ = GetSolverLibrary().GetSolverFactory(GetParameters().Get<std::string>("Solver"));
+    }
+    std::shared_ptr<SolverFactory> Fact_;
+};
+
+inline void SolverLibrary::RegisterBuiltins()
+{
+    RegisterFactoryType("AMGe", [] { return std::make_shared<AMGeSolverFactory>(); });
+    RegisterFactoryType("Hypre", [] { return std::make_shared<HypreSmootherFactory>(); });
+    RegisterFactoryType("Hiptmair", [] { return std::make_shared<HiptmairSmootherFactory>(); });
+    RegisterFactoryType("Krylov", [] { return std::make_shared<KrylovSolverFactory>(); });
+    RegisterFactoryType("Stationary Iteration", [] { return std::make_shared<StationarySolverFactory>(); });
+}
+} // namespace parelag

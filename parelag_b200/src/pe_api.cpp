@@ -1,0 +1,187 @@
+// pe_api.cpp -- C facade over the C++ solver API (see include/parelag_b200_api.h).
+#include "parelag_b200_api.h"
+#include "parelag_solvers.hpp"
+#include <cstring>
+
+void pe_set_error(const std::string &msg);   // csrc/pe_core.cu
+
+using namespace parelag;
+
+struct pe_sequence { std::vector<std::shared_ptr<DeRhamSequence>> levels; };
+struct pe_solver
+{
+    std::shared_ptr<SolverLibrary> lib;
+    std::shared_ptr<mfem::HypreParMatrix> A;
+    std::unique_ptr<mfem::Solver> solver;
+    mfem::Vector b, x;
+};
+
+static std::unique_ptr<mpi_session> g_session;
+
+#define API_TRY try {
+#define API_CATCH                                                      \
+    }                                                                  \
+    catch (const std::exception &e) { pe_set_error(e.what()); return 10; } \
+    catch (...) { pe_set_error("unknown C++ exception"); return 11; }  \
+    return 0;
+
+extern "C" int pe_api_session_create(int rank, int nranks, int device, const void *id)
+{
+    API_TRY
+    if (!g_session) g_session = make_unique<mpi_session>(rank, nranks, device, id);
+    API_CATCH
+}
+extern "C" int pe_api_session_destroy(void)
+{
+    API_TRY
+    g_session.reset();
+    API_CATCH
+}
+extern "C" pe_ctx *pe_api_session_ctx(void) { return Device::Ctx(); }
+
+extern "C" int pe_api_sequence_create(int nforms, int nlevels, pe_sequence **out)
+{
+    API_TRY
+    auto s = new pe_sequence();
+    for (int l = 0; l < nlevels; ++l) s->levels.push_back(std::make_shared<DeRhamSequence>(nforms));
+    for (int l = 0; l + 1 < nlevels; ++l) s->levels[l]->SetCoarserSequence(s->levels[l + 1]);
+    *out = s;
+    API_CATCH
+}
+extern "C" int pe_api_sequence_set_P(pe_sequence *s, int level, int form, int nrows, int ncols,
+                                     const int32_t *I, const int32_t *J, const double *A)
+{
+    API_TRY
+    s->levels.at(level)->SetP(form, HostCSR(nrows, ncols, I, J, A));
+    API_CATCH
+}
+extern "C" int pe_api_sequence_set_D(pe_sequence *s, int level, int form, int nrows, int ncols,
+                                     const int32_t *I, const int32_t *J, const double *A)
+{
+    API_TRY
+    s->levels.at(level)->SetD(form, HostCSR(nrows, ncols, I, J, A));
+    API_CATCH
+}
+extern "C" int pe_api_sequence_set_bdr_mask(pe_sequence *s, int level, int form, int ndofs, const uint32_t *mask)
+{
+    API_TRY
+    auto d = make_unique<DofHandler>();
+    d->SetBoundaryMask(std::vector<uint32_t>(mask, mask + ndofs));
+    s->levels.at(level)->SetDofHandler(form, std::move(d));
+    API_CATCH
+}
+extern "C" int pe_api_sequence_free(pe_sequence *s) { delete s; return 0; }
+
+extern "C" int pe_api_solver_build(const char *xml, const char *name, const pe_parcsr_host *A, pe_sequence *seq,
+                                   int start_level, int form, const int32_t *ess_attr, int nattr, pe_solver **out)
+{
+    API_TRY
+    auto s = make_unique<pe_solver>();
+    SimpleXMLParameterListReader reader;
+    auto pl = reader.Parse(xml);
+    s->lib = SolverLibrary::CreateLibrary(*pl);
+    auto fact = s->lib->GetSolverFactory(name);
+    auto state = fact->GetDefaultState();
+    if (seq) state->SetDeRhamSequence(seq->levels.at(start_level));
+    std::vector<std::vector<int>> labels(1);
+    if (ess_attr) labels[0].assign(ess_attr, ess_attr + nattr);
+    state->SetBoundaryLabels(labels);
+    state->SetForms({form});
+    s->A = std::make_shared<mfem::HypreParMatrix>(*A);
+    {
+        Timer t = TimeManager::AddTimer(std::string("Build Solver ") + name);
+        s->solver = fact->BuildSolver(s->A, *state);
+    }
+    *out = s.release();
+    API_CATCH
+}
+extern "C" int pe_api_solver_mult(pe_solver *s, const double *b, double *x, int n, int iterative_mode)
+{
+    API_TRY
+    PARELAG_TEST_FOR_EXCEPTION(n != s->solver->Height(), std::runtime_error, "pe_api_solver_mult: wrong vector length");
+    s->b.SetSize(n); s->x.SetSize(n);
+    std::memcpy(s->b.HostWrite(), b, sizeof(double) * (size_t)n);
+    if (iterative_mode) std::memcpy(s->x.HostWrite(), x, sizeof(double) * (size_t)n);
+    const bool saved = s->solver->iterative_mode;
+    s->solver->iterative_mode = iterative_mode != 0;
+    s->solver->Mult(s->b, s->x);
+    s->solver->iterative_mode = saved;
+    std::memcpy(x, s->x.HostRead(), sizeof(double) * (size_t)n);
+    API_CATCH
+}
+namespace
+{
+// a non-owning mfem::Vector over an existing pe_vec
+struct VecAlias : mfem::Vector { };
+}
+extern "C" int pe_api_solver_mult_device(pe_solver *s, const pe_vec *b, pe_vec *x, int iterative_mode)
+{
+    API_TRY
+    const int n = s->solver->Height();
+    PARELAG_TEST_FOR_EXCEPTION(pe_vec_size(b) != n || pe_vec_size(x) != n, std::runtime_error, "pe_api_solver_mult_device: wrong vector length");
+    s->b.SetSize(n); s->x.SetSize(n);
+    PE_CALL(pe_vec_copy(b, s->b.Write()));
+    if (iterative_mode) PE_CALL(pe_vec_copy(x, s->x.Write()));
+    const bool saved = s->solver->iterative_mode;
+    s->solver->iterative_mode = iterative_mode != 0;
+    s->solver->Mult(s->b, s->x);
+    s->solver->iterative_mode = saved;
+    PE_CALL(pe_vec_copy(s->x.Read(), x));
+    API_CATCH
+}
+extern "C" int pe_api_solver_get_history(const pe_solver *s, double *hist, int capacity, int *count, int *iterations, int *converged)
+{
+    API_TRY
+    auto k = dynamic_cast<const KrylovSolver *>(s->solver.get());
+    PARELAG_TEST_FOR_EXCEPTION(!k, std::runtime_error, "pe_api_solver_get_history: not a Krylov solver");
+    const auto &h = k->GetResidualHistory();
+    if (count) *count = (int)h.size();
+    for (int i = 0; i < capacity && i < (int)h.size(); ++i) hist[i] = h[i];
+    if (iterations) *iterations = k->GetNumIterations();
+    if (converged) *converged = k->GetConverged() ? 1 : 0;
+    API_CATCH
+}
+static const Hierarchy *as_hierarchy(const pe_solver *s)
+{
+    auto h = dynamic_cast<const Hierarchy *>(s->solver.get());
+    PARELAG_TEST_FOR_EXCEPTION(!h, std::runtime_error, "solver is not a Hierarchy (AMGe) solver");
+    return h;
+}
+extern "C" int pe_api_solver_num_levels(const pe_solver *s, int *nlevels)
+{
+    API_TRY
+    *nlevels = as_hierarchy(s)->GetNumLevels();
+    API_CATCH
+}
+extern "C" int pe_api_solver_level_info(const pe_solver *s, int level, int64_t *nrows, int64_t *nnz, int64_t *nnz_P)
+{
+    API_TRY
+    auto h = const_cast<Hierarchy *>(as_hierarchy(s));
+    auto A = std::dynamic_pointer_cast<mfem::HypreParMatrix>(h->GetLevel(level).Get<Op_Ptr>("A"));
+    if (nrows) *nrows = A->M();
+    if (nnz) *nnz = A->NNZ();
+    if (nnz_P)
+    {
+        *nnz_P = 0;
+        if (h->GetLevel(level).IsKey("P"))
+            *nnz_P = std::dynamic_pointer_cast<mfem::HypreParMatrix>(h->GetLevel(level).Get<Op_Ptr>("P"))->NNZ();
+    }
+    API_CATCH
+}
+extern "C" int pe_api_solver_level_matrix(const pe_solver *s, int level, int32_t *I, int32_t *J, double *A)
+{
+    API_TRY
+    auto h = const_cast<Hierarchy *>(as_hierarchy(s));
+    auto M = std::dynamic_pointer_cast<mfem::HypreParMatrix>(h->GetLevel(level).Get<Op_Ptr>("A"));
+    PE_CALL(pe_mat_download(M->Handle(), I, J, A, nullptr, nullptr, nullptr, nullptr));
+    API_CATCH
+}
+extern "C" int pe_api_solver_free(pe_solver *s) { delete s; return 0; }
+
+extern "C" int pe_api_timer_get(const char *name, double *seconds)
+{
+    API_TRY
+    *seconds = TimeManager::Seconds(name);
+    API_CATCH
+}
+extern "C" int pe_api_timer_clear(void) { TimeManager::ClearAllData(); return 0; }

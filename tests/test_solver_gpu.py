@@ -1,0 +1,109 @@
+"""End-to-end parity of the ParameterList-driven solver (C++ SolverLibrary -> AMGe
+Hierarchy -> Hiptmair / hypre smoothers -> PCG, all on the GPU through the C ABI)
+against the CPU oracle on the same mesh and coefficients.
+
+Contract (BASELINE.json north_star): coarse-operator patterns bit-exact, values to
+1e-12 relative; per-iteration PCG "(B r, r)" to 1e-9 relative with the same iteration
+count +-1."""
+import numpy as np
+import pytest
+
+from parelag_b200 import api
+from oracle import amge, drivers, solve as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sess():
+    ctx = api.session()
+    yield ctx
+
+
+@pytest.fixture(scope="module")
+def hier():
+    mesh, seqs = amge.build_hierarchy((8, 8, 8), 3)
+    return mesh, seqs
+
+
+def make_sequence(seqs):
+    S = api.Sequence(4, len(seqs))
+    for l, s in enumerate(seqs):
+        for j in range(4):
+            S.set_bdr_mask(l, j, drivers.bdr_mask(s.dof[j]))
+            if j < 3:
+                S.set_D(l, j, s.D[j])
+            if l + 1 < len(seqs):
+                S.set_P(l, j, s.P[j])
+    return S
+
+
+@pytest.mark.parametrize("form,ordering", [(0, "natural"), (2, "natural"), (1, "natural"),
+                                           (2, "multicolor"), (0, "multicolor")])
+def test_pcg_amge_residual_history(sess, hier, form, ordering):
+    mesh, seqs = hier
+    ess = np.ones(6, dtype=np.int32)
+    A, marker = drivers.system_matrix(seqs[0], form, ess)
+    rng = np.random.default_rng(11 + form)
+    b = rng.standard_normal(A.shape[0])
+    b[marker] = 0.0
+    # oracle
+    H = drivers.amge_pcg_solver(seqs, form, ess, A, ordering=ordering)
+    xo, ito, convo, histo = orc.pcg(A, H.mult, b, rtol=1e-6, atol=1e-6, max_iter=300)
+    # product
+    xml = api.library_xml(drivers.library_entries(form, ordering=ordering))
+    S = make_sequence(seqs)
+    solver = api.Solver(xml, "PCG-AMGe", A, S, 0, form, ess)
+    x = solver.mult(b)
+    hist, it, conv = solver.history()
+    assert conv and convo
+    assert abs(it - ito) <= 1
+    m = min(len(hist), len(histo))
+    assert m >= 3
+    rel = np.abs(hist[:m] - np.array(histo[:m])) / np.abs(np.array(histo[:m]))
+    assert rel.max() < 1e-9, rel
+    assert np.linalg.norm(x - xo) <= 1e-8 * np.linalg.norm(xo)
+    solver.free(); S.free()
+
+
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_galerkin_hierarchy_matches_oracle(sess, hier, form):
+    """A_{l+1} = P^T A P + FixZeroRows: pattern bit-exact, values 1e-12 (relative to max)."""
+    mesh, seqs = hier
+    ess = np.ones(6, dtype=np.int32)
+    A, marker = drivers.system_matrix(seqs[0], form, ess)
+    xml = api.library_xml(drivers.library_entries(form))
+    S = make_sequence(seqs)
+    solver = api.Solver(xml, "AMGe", A, S, 0, form, ess)
+    assert solver.num_levels() == 3
+    Ao = A
+    for l in range(1, 3):
+        Ao, _ = orc.fix_zero_rows(orc.rap(Ao, seqs[l - 1].get_P(form, ess)))
+        Ag = solver.level_matrix(l)
+        assert np.array_equal(Ag.indptr, Ao.indptr)
+        assert np.array_equal(Ag.indices, Ao.indices)
+        assert np.max(np.abs(Ag.data - Ao.data)) <= 1e-12 * np.max(np.abs(Ao.data))
+    # one V-cycle applied to a vector
+    rng = np.random.default_rng(5)
+    r = rng.standard_normal(A.shape[0]); r[marker] = 0
+    H = drivers.amge_pcg_solver(seqs, form, ess, A)
+    zo = H.mult(r)
+    z = solver.mult(r)
+    assert np.linalg.norm(z - zo) <= 1e-11 * np.linalg.norm(zo)
+    solver.free(); S.free()
+
+
+def test_api_error_behaviour(sess, hier):
+    mesh, seqs = hier
+    ess = np.ones(6, dtype=np.int32)
+    A, _ = drivers.system_matrix(seqs[0], 0, ess)
+    xml = api.library_xml(drivers.library_entries(0))
+    from parelag_b200.capi import PEError
+    with pytest.raises(PEError, match="not in the library"):
+        api.Solver(xml, "No such solver", A, None, 0, 0, ess)
+    bad = xml.replace("L1 Gauss-Seidel", "Kaczmarz")
+    S = make_sequence(seqs)
+    with pytest.raises(PEError, match="not supported on the GPU path"):
+        api.Solver(bad, "PCG-AMGe", A, S, 0, 0, ess)
+    with pytest.raises(PEError, match="no DeRhamSequence"):
+        api.Solver(xml, "AMGe", A, None, 0, 0, ess)
