@@ -41,6 +41,26 @@ int pe_api_sequence_set_D(pe_sequence *s, int level, int form, int nrows, int nc
 int pe_api_sequence_set_bdr_mask(pe_sequence *s, int level, int form, int ndofs, const uint32_t *mask);
 int pe_api_sequence_free(pe_sequence *s);
 
+/* The full coarsening path on a structured hexahedral mesh (synthetic input of the named
+ * shape): AgglomeratedTopology + MFEMRefinedMeshPartitioner + CoarsenLocalPartitioning,
+ * DeRhamSequence3D_FE at lowest order with the upscaling targets, then
+ * sequence[i+1] = sequence[i]->Coarsen() (examples/MultigridTest2Form.cpp:248-375).
+ * alpha/beta: optional per-element weights of the L2 / H(div) element mass matrices.
+ * svd_tol < 0: build the topology hierarchy and the fine sequence only (host integer work,
+ * no GPU needed). */
+int pe_api_hexsequence_create(int nx, int ny, int nz, double Lx, double Ly, double Lz,
+                              const double *alpha, const double *beta, int jform_start, int nlevels,
+                              double svd_tol, pe_sequence **out);
+/* Introspection for parity tests.  what = "P" (a=form), "D" (a=form), "M" (a=form: assembled
+ * mass operator), "Me" (a=form, b=codim: block-diagonal entity mass matrices), "B" (a=codim),
+ * "AE" (a=codim: agglomerated entity -> entity), "ED" (a=form, b=codim: entity -> dof),
+ * "FB" (facet -> boundary attribute).  Call with I=J=A=NULL to get the sizes. */
+int pe_api_sequence_get_csr(pe_sequence *s, int level, const char *what, int a, int b,
+                            int32_t *nrows, int32_t *ncols, int64_t *nnz, int32_t *I, int32_t *J, double *A);
+int pe_api_sequence_get_targets(pe_sequence *s, int level, int form, int32_t *ndofs, int32_t *ntargets, double *out);
+int pe_api_sequence_get_bdr_mask(pe_sequence *s, int level, int form, int32_t *ndofs, uint32_t *mask);
+int pe_api_sequence_get_stat(pe_sequence *s, int level, const char *name, int64_t *value);
+
 /* SolverLibrary::CreateLibrary(xml) -> GetSolverFactory(name) -> BuildSolver(A, state).
  * xml: a <ParameterList name="Preconditioner Library"> document.  seq may be NULL for
  * solvers that need no sequence.  ess_attr[nattr]: essential boundary attribute marker

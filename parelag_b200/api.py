@@ -47,6 +47,51 @@ class Sequence:
         mask = np.ascontiguousarray(mask, dtype=np.uint32)
         _chk(lib().pe_api_sequence_set_bdr_mask(self.h, level, form, len(mask), _ptr(mask)))
 
+    @staticmethod
+    def hex(dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9):
+        """Full coarsening path on a structured hex mesh (svd_tol < 0: topology only)."""
+        S = Sequence.__new__(Sequence)
+        S.h = C.c_void_p()
+        a = None if alpha is None else _f64(alpha)
+        b = None if beta is None else _f64(beta)
+        _chk(lib().pe_api_hexsequence_create(dims[0], dims[1], dims[2], C.c_double(L[0]), C.c_double(L[1]),
+                                             C.c_double(L[2]), _ptr(a), _ptr(b), jstart, nlevels,
+                                             C.c_double(svd_tol), C.byref(S.h)))
+        return S
+
+    def get_csr(self, level, what, a=0, b=0):
+        import scipy.sparse as sp
+        nr, nc, nnz = C.c_int32(), C.c_int32(), C.c_int64()
+        _chk(lib().pe_api_sequence_get_csr(self.h, level, what.encode(), a, b, C.byref(nr), C.byref(nc),
+                                           C.byref(nnz), None, None, None))
+        I = np.empty(nr.value + 1, dtype=np.int32)
+        J = np.empty(nnz.value, dtype=np.int32)
+        A = np.empty(nnz.value)
+        _chk(lib().pe_api_sequence_get_csr(self.h, level, what.encode(), a, b, None, None, None,
+                                           _ptr(I), _ptr(J), _ptr(A)))
+        M = sp.csr_matrix((nr.value, nc.value))
+        M.data, M.indices, M.indptr = A, J, I
+        return M
+
+    def get_targets(self, level, form):
+        nd, nt = C.c_int32(), C.c_int32()
+        _chk(lib().pe_api_sequence_get_targets(self.h, level, form, C.byref(nd), C.byref(nt), None))
+        out = np.empty(nd.value * nt.value)
+        _chk(lib().pe_api_sequence_get_targets(self.h, level, form, None, None, _ptr(out)))
+        return out.reshape(nt.value, nd.value).T
+
+    def get_bdr_mask(self, level, form):
+        nd = C.c_int32()
+        _chk(lib().pe_api_sequence_get_bdr_mask(self.h, level, form, C.byref(nd), None))
+        m = np.empty(nd.value, dtype=np.uint32)
+        _chk(lib().pe_api_sequence_get_bdr_mask(self.h, level, form, None, _ptr(m)))
+        return m
+
+    def stat(self, level, name):
+        v = C.c_int64()
+        _chk(lib().pe_api_sequence_get_stat(self.h, level, name.encode(), C.byref(v)))
+        return v.value
+
     def free(self):
         if self.h:
             lib().pe_api_sequence_free(self.h)

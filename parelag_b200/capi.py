@@ -12,7 +12,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libparelag_b200.so")
-HEADER_PATHS = [os.path.join(os.path.dirname(_HERE), "include", "parelag_b200.h"),
+HEADER_PATHS = [os.path.join(os.path.dirname(_HERE), "include", "parelag_b200_local.h"),
+                os.path.join(os.path.dirname(_HERE), "include", "parelag_b200.h"),
                 os.path.join(os.path.dirname(_HERE), "include", "parelag_b200_api.h")]
 
 _lib = None

@@ -1,0 +1,831 @@
+// pe_local.cu -- K11/K12/K13: the per-agglomerate dense work of DeRhamSequence::Coarsen
+// as batched one-agglomerate-per-CTA kernels; every local matrix lives in shared memory.
+//
+//   pe_batched_traces      ComputeCoarseTracesWithTargets hot loop
+//                          (src/amge/DeRhamSequence.cpp:1818-1926): Deflate, weighted SVD,
+//                          rank truncation, p_loc = [pv | sqrt(pv.M.pv) U], coarse trace mass,
+//                          dof functional.
+//   pe_batched_extension   hFacetExtension hot loop (:2364-2556) with FacetSaddlePoint
+//                          [M B^T 0; B 0 T^T; 0 T 0]  (ParELAG_SaddlePointSolver.cpp:70-130) and
+//                          hRidgePeakExtension hot loop (:2779-3027) with RidgePeakSaddlePoint
+//                          [M B^T; B -C] (:150-189): local assembly of M, W, D blocks from the
+//                          entity matrices, all right-hand sides at once, pivoted LU, target
+//                          residual SVD, CochainProjector::CreateDofFunctional
+//                          (src/amge/CochainProjector.cpp:53-137) and CoarsenMassMatrixPart.
+//
+// The reference factors with dsytrf (Bunch-Kaufman) and uses dgesvd; here the small
+// systems (order 7..60) are solved by Gaussian elimination with partial pivoting and the
+// thin SVDs (<= 8 columns) by one-sided Jacobi, both in FP64 FMA -- far below DMMA tile
+// sizes, so no tensor cores.  SVD sign convention: largest-magnitude
+// entry of every retained singular vector is positive (first on ties).
+#include "pe_core.cuh"
+#include "../../include/parelag_b200_local.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#define LT 128   // threads per CTA in the extension kernel
+
+// ---------------------------------------------------------------------------
+// CTA-cooperative dense helpers (row-major, data in shared memory)
+// ---------------------------------------------------------------------------
+// Solve A X = R in place (A n x n, lda; R n x nrhs, ldr) by Gaussian elimination with
+// partial pivoting (ties -> smallest row index).  Returns 0, or k+1 if pivot k is zero.
+__device__ int cta_lu_solve(double *A, int n, int lda, double *R, int nrhs, int ldr, int *s_piv, int tid, int nt)
+{
+    __shared__ int s_info;
+    if (tid == 0) s_info = 0;
+    __syncthreads();
+    for (int k = 0; k < n; ++k)
+    {
+        if (tid < 32)
+        {
+            double best = -1.0; int bi = k;
+            for (int i = k + tid; i < n; i += 32) { double v = fabs(A[i * lda + k]); if (v > best) { best = v; bi = i; } }
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                double ob = __shfl_down_sync(0xffffffffu, best, o);
+                int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (tid == 0) { *s_piv = bi; if (!(best > 0.0) && s_info == 0) s_info = k + 1; }
+        }
+        __syncthreads();
+        const int p = *s_piv;
+        if (s_info) return s_info;
+        if (p != k)
+        {
+            for (int j = tid; j < n; j += nt) { double t = A[k * lda + j]; A[k * lda + j] = A[p * lda + j]; A[p * lda + j] = t; }
+            for (int j = tid; j < nrhs; j += nt) { double t = R[k * ldr + j]; R[k * ldr + j] = R[p * ldr + j]; R[p * ldr + j] = t; }
+            __syncthreads();
+        }
+        const double inv = 1.0 / A[k * lda + k];
+        for (int i = k + 1 + tid; i < n; i += nt) A[i * lda + k] *= inv;     // multipliers
+        __syncthreads();
+        const int rem = n - k - 1, wtot = rem + nrhs;
+        for (int idx = tid; idx < rem * wtot; idx += nt)
+        {
+            const int i = k + 1 + idx / wtot, c = idx % wtot;
+            const double l = A[i * lda + k];
+            if (c < rem) A[i * lda + k + 1 + c] -= l * A[k * lda + k + 1 + c];
+            else R[i * ldr + (c - rem)] -= l * R[k * ldr + (c - rem)];
+        }
+        __syncthreads();
+    }
+    for (int k = n - 1; k >= 0; --k)
+    {
+        const double inv = 1.0 / A[k * lda + k];
+        for (int j = tid; j < nrhs; j += nt) R[k * ldr + j] *= inv;
+        __syncthreads();
+        for (int idx = tid; idx < k * nrhs; idx += nt)
+        {
+            const int i = idx / nrhs, j = idx % nrhs;
+            R[i * ldr + j] -= A[i * lda + k] * R[k * ldr + j];
+        }
+        __syncthreads();
+    }
+    return 0;
+}
+
+// One-sided (Hestenes) Jacobi SVD of X (m x k, COLUMN-major, ldx >= m) by warp 0.
+// On exit: columns of X are the left singular vectors (sign-fixed) scaled to unit norm
+// where sigma > 0, ordered by descending sigma; sv[0..min(m,k)) the singular values.
+__device__ void warp_jacobi_svd(double *X, int m, int k, int ldx, double *sv, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    for (int sweep = 0; sweep < 40; ++sweep)
+    {
+        double off = 0.0;
+        for (int p = 0; p < k - 1; ++p)
+            for (int q = p + 1; q < k; ++q)
+            {
+                double a = 0, b = 0, g = 0;
+                for (int i = lane; i < m; i += 32) { double xp = X[p * ldx + i], xq = X[q * ldx + i]; a += xp * xp; b += xq * xq; g += xp * xq; }
+                for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); g += __shfl_xor_sync(FULL, g, o); }
+                if (a == 0.0 || b == 0.0) continue;
+                const double r = fabs(g) / sqrt(a * b);
+                if (r > off) off = r;
+                if (r < 1e-16) continue;
+                const double zeta = (b - a) / (2.0 * g);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                for (int i = lane; i < m; i += 32)
+                {
+                    double xp = X[p * ldx + i], xq = X[q * ldx + i];
+                    X[p * ldx + i] = c * xp - s * xq;
+                    X[q * ldx + i] = s * xp + c * xq;
+                }
+                __syncwarp();
+            }
+        if (off < 1e-15) break;
+    }
+    // norms
+    for (int p = 0; p < k; ++p)
+    {
+        double a = 0;
+        for (int i = lane; i < m; i += 32) a += X[p * ldx + i] * X[p * ldx + i];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(FULL, a, o);
+        if (lane == 0) sv[p] = sqrt(a);
+    }
+    __syncwarp();
+    // selection sort by descending sigma (k is tiny); stable for ties
+    for (int p = 0; p < k - 1; ++p)
+    {
+        int best = p;
+        for (int q = p + 1; q < k; ++q) if (sv[q] > sv[best]) best = q;
+        if (best != p)
+        {
+            for (int i = lane; i < m; i += 32) { double t = X[p * ldx + i]; X[p * ldx + i] = X[best * ldx + i]; X[best * ldx + i] = t; }
+            __syncwarp();
+            if (lane == 0) { double t = sv[p]; sv[p] = sv[best]; sv[best] = t; }
+            __syncwarp();
+        }
+    }
+    // normalise + canonical sign
+    for (int p = 0; p < k; ++p)
+    {
+        const double s = sv[p];
+        double best = -1.0; int bi = 0;
+        for (int i = lane; i < m; i += 32) { double v = fabs(X[p * ldx + i]); if (v > best) { best = v; bi = i; } }
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            double ob = __shfl_xor_sync(FULL, best, o); int oi = __shfl_xor_sync(FULL, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        const double sgn = (m > 0 && X[p * ldx + bi] < 0.0) ? -1.0 : 1.0;
+        const double sc = s > 0.0 ? sgn / s : 0.0;
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) X[p * ldx + i] *= sc;
+    }
+    __syncwarp();
+    // LAPACK returns min(m,k) singular values: the remaining ones are exactly zero
+    if (lane == 0) for (int p = (m < k ? m : k); p < k; ++p) sv[p] = 0.0;
+    __syncwarp();
+}
+
+// functional F = (P^T M P)^{-1} (M P)^T : P nu x nc column-major (ldp), M nu x nu row-major (ldm)
+// work: MP (nu*nc, column-major) + cM (nc*nc) ; F out row-major nc x nu (ldf = nu)
+__device__ int cta_dof_functional(const double *P, int nu, int nc, int ldp, const double *M, int ldm,
+                                  double *MP, double *cM, double *F, int *s_piv, int tid, int nt)
+{
+    if (nc == 0) return 0;
+    for (int idx = tid; idx < nu * nc; idx += nt)
+    {
+        const int i = idx % nu, c = idx / nu;
+        double s = 0.0;
+        for (int t = 0; t < nu; ++t) s += M[i * ldm + t] * P[c * ldp + t];
+        MP[c * nu + i] = s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nc * nc; idx += nt)
+    {
+        const int a = idx / nc, b = idx % nc;
+        double s = 0.0;
+        for (int t = 0; t < nu; ++t) s += P[a * ldp + t] * MP[b * nu + t];
+        cM[a * nc + b] = s;
+    }
+    for (int idx = tid; idx < nc * nu; idx += nt) F[idx] = MP[idx];   // (M P)^T row-major nc x nu == MP column-major
+    __syncthreads();
+    return cta_lu_solve(cM, nc, nc, F, nu, nu, s_piv, tid, nt);
+}
+
+// ---------------------------------------------------------------------------
+// traces
+// ---------------------------------------------------------------------------
+struct TraceArgs
+{
+    int nAE;
+    const int *I, *J;
+    const double *pv, *diagM;     // pv per fine dof; diagM per ADof
+    int nT, ldT;
+    const double *T;
+    double svd_tol;
+    const long long *out_off;
+    double *out;                  // per AE: p (m x (nT+1)) | mass ((nT+1)^2) | func ((nT+1) x m) | sv (nT)
+    int *ndofs_out, *info_out;
+    int max_m;
+};
+
+__global__ void __launch_bounds__(32) k_traces(TraceArgs a)
+{
+    extern __shared__ double sm[];
+    const int ae = blockIdx.x, lane = threadIdx.x;
+    if (ae >= a.nAE) return;
+    const int s = a.I[ae], m = a.I[ae + 1] - s, nT = a.nT, nc_max = nT + 1;
+    double *X = sm;                       // m x nT column-major (ld = max_m)
+    double *pvl = X + a.max_m * (nT > 0 ? nT : 1);
+    double *dg = pvl + a.max_m;
+    double *sv = dg + a.max_m;            // nT
+    double *Pl = sv + (nT > 0 ? nT : 1);  // m x nc_max column-major (ld = max_m)
+    double *MP = Pl + a.max_m * nc_max;
+    double *cM = MP + a.max_m * nc_max;
+    __shared__ int s_piv;
+    const int ld = a.max_m;
+    double pvMpv = 0.0;
+    for (int i = lane; i < m; i += 32)
+    {
+        const int d = a.J[s + i];
+        pvl[i] = a.pv[d]; dg[i] = a.diagM[s + i];
+        pvMpv += pvl[i] * dg[i] * pvl[i];
+        for (int t = 0; t < nT; ++t) X[t * ld + i] = a.T[(size_t)t * a.ldT + d];
+    }
+    for (int o = 16; o > 0; o >>= 1) pvMpv += __shfl_xor_sync(0xffffffffu, pvMpv, o);
+    __syncwarp();
+    // Deflate: t += (-(pv.M.t)/(pv.M.pv)) pv ; then scale rows by sqrt(diag M)
+    const double sc = -1.0 / pvMpv;
+    for (int t = 0; t < nT; ++t)
+    {
+        double dot = 0.0;
+        for (int i = lane; i < m; i += 32) dot += pvl[i] * dg[i] * X[t * ld + i];
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        for (int i = lane; i < m; i += 32) X[t * ld + i] = (X[t * ld + i] + (dot * sc) * pvl[i]) * sqrt(dg[i]);
+    }
+    __syncwarp();
+    if (nT > 0) warp_jacobi_svd(X, m, nT, ld, sv, lane);
+    const double s_max_tol = pvMpv * a.svd_tol;
+    int k = 0;
+    const int nsv = m < nT ? m : nT;
+    while (k < nsv && !(sv[k] < s_max_tol)) ++k;
+    const int nc = k + 1;
+    const double sq = sqrt(pvMpv);
+    for (int i = lane; i < m; i += 32)
+    {
+        Pl[i] = pvl[i];
+        for (int c = 0; c < k; ++c) Pl[(c + 1) * ld + i] = X[c * ld + i] / sqrt(dg[i]) * sq;
+    }
+    __syncwarp();
+    // canonical sign again after the inverse row scaling (largest |entry| may have moved)
+    for (int c = 1; c < nc; ++c)
+    {
+        double best = -1.0; int bi = 0;
+        for (int i = lane; i < m; i += 32) { double v = fabs(Pl[c * ld + i]); if (v > best) { best = v; bi = i; } }
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (Pl[c * ld + bi] < 0.0) for (int i = lane; i < m; i += 32) Pl[c * ld + i] = -Pl[c * ld + i];
+        __syncwarp();
+    }
+    double *out = a.out + a.out_off[ae];
+    double *p_out = out, *mass_out = out + (size_t)m * nc_max, *func_out = mass_out + nc_max * nc_max, *sv_out = func_out + (size_t)nc_max * m;
+    for (int idx = lane; idx < m * nc; idx += 32) { int i = idx % m, c = idx / m; p_out[c * m + i] = Pl[c * ld + i]; }
+    // mass = P^T diag(M) P (symmetrised), functional = (P^T M P)^{-1} P^T M
+    for (int idx = lane; idx < m * nc; idx += 32) { int i = idx % m, c = idx / m; MP[c * m + i] = dg[i] * Pl[c * ld + i]; }
+    __syncwarp();
+    for (int idx = lane; idx < nc * nc; idx += 32)
+    {
+        int x = idx / nc, y = idx % nc;
+        double v = 0.0, w = 0.0;
+        for (int i = 0; i < m; ++i) { v += Pl[x * ld + i] * MP[y * m + i]; w += Pl[y * ld + i] * MP[x * m + i]; }
+        cM[idx] = v;
+        mass_out[x * nc + y] = 0.5 * (v + w);
+    }
+    double *F = func_out;
+    for (int idx = lane; idx < nc * m; idx += 32) F[idx] = MP[idx];
+    __syncwarp();
+    // tiny LU by the warp (same routine, nt = 32)
+    int info = 0;
+    {
+        // cta_lu_solve uses __syncthreads: the CTA is exactly one warp here
+        info = cta_lu_solve(cM, nc, nc, F, m, m, &s_piv, lane, 32);
+    }
+    for (int t = lane; t < nT; t += 32) sv_out[t] = t < nsv ? sv[t] : 0.0;
+    if (lane == 0) { a.ndofs_out[ae] = nc; a.info_out[ae] = info; }
+}
+
+// ---------------------------------------------------------------------------
+// extension (facet / ridge / peak)
+// ---------------------------------------------------------------------------
+struct PoolV { const long long *off; const int *size, *rdoff; const double *vals; };
+struct CsrV { const int *I, *J; const double *A; };
+struct RowPoolV { const long long *start; const int *len, *J; const double *A; };
+
+struct ExtArgs
+{
+    int nAE, facet, compute_null;
+    const int *uI, *uJ, *uN, *pI, *pJ, *pN, *qI, *qJ;
+    const int *aeI, *aeJ;
+    PoolV Mu, Mp, Mq;
+    const int *slot_u, *slot_p, *slot_q;
+    CsrV Dj, Dj1;
+    const int *cbI, *cbJ;
+    RowPoolV Pj, Dc;
+    CsrV Pj1;
+    const int *pvc, *pnI, *pnJ;
+    int nT, ldT;
+    const double *T;
+    double svd_tol, smallest_entry;
+    const long long *out_off;
+    double *out;
+    int *k_out, *info_out;
+    int mxu, mxp, mxq, mxui, mxpi, mxcb, mxrt;   // max sizes (for the shared-memory carve-up)
+};
+
+__device__ __forceinline__ int find_lin(const int *list, int n, int key)
+{
+    for (int i = 0; i < n; ++i) if (list[i] == key) return i;
+    return -1;
+}
+__device__ __forceinline__ int find_bin(const int *list, int n, int key)
+{
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) { int mid = (lo + hi) >> 1; int v = list[mid]; if (v == key) return mid; if (v < key) lo = mid + 1; else hi = mid - 1; }
+    return -1;
+}
+// assemble the agglomerate matrix from the entity blocks (AssembleAgglomerateMatrix)
+__device__ void cta_assemble(double *Mall, int n, const PoolV &P, const int *slot, const int *ents, int nents, int tid)
+{
+    for (int i = tid; i < n * n; i += LT) Mall[i] = 0.0;
+    __syncthreads();
+    for (int q = 0; q < nents; ++q)
+    {
+        const int e = ents[q], m = P.size[e], rd0 = P.rdoff[e];
+        const double *blk = P.vals + P.off[e];
+        for (int idx = tid; idx < m * m; idx += LT)
+        {
+            const int la = slot[rd0 + idx / m], lb = slot[rd0 + idx % m];
+            Mall[la * n + lb] += blk[idx];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(LT) k_extension(ExtArgs a)
+{
+    extern __shared__ double sm[];
+    const int ae = blockIdx.x, tid = threadIdx.x;
+    if (ae >= a.nAE) return;
+    const int us = a.uI[ae], nua = a.uI[ae + 1] - us, nui = a.uN[ae], nub = nua - nui;
+    const int ps = a.pI[ae], npa = a.pI[ae + 1] - ps, npi = a.pN[ae];
+    const int qs = a.facet ? 0 : a.qI[ae], nqa = a.facet ? 0 : a.qI[ae + 1] - qs;
+    const int cbs = a.cbI[ae], ncb = a.cbI[ae + 1] - cbs;
+    const int nrt = a.pnI[ae + 1] - a.pnI[ae];
+    const int nT = (a.compute_null && nui > nrt) ? a.nT : 0;
+    const int n = a.facet ? nui + npi + 1 : nui + npi;
+    const int nrhs = ncb + nrt + nT;
+    const int nents = a.aeI[ae + 1] - a.aeI[ae];
+    const int *ents = a.aeJ + a.aeI[ae];
+    // ---- shared memory carve-up (upper bounds from the host)
+    const int nmax = a.mxui + a.mxpi + 1, rmax = a.mxcb + a.mxrt + a.nT, cmax = a.mxrt + a.nT, lbmax = a.mxcb + cmax;
+    double *Mall = sm;                                  // nua x nua
+    double *Wall = Mall + a.mxu * a.mxu;                // npa x npa
+    double *Dall = Wall + a.mxp * a.mxp;                // npa x nua
+    double *Brow = Dall + a.mxp * a.mxu;                // npi x nua
+    double *A = Brow + a.mxpi * a.mxu;                  // n x n
+    double *R = A + nmax * nmax;                        // n x nrhs
+    double *Rb = R + nmax * rmax;                       // nub x ncb
+    double *G = Rb + a.mxu * a.mxcb;                    // npa x ncb (ridge) / scratch
+    double *X = G + a.mxp * a.mxcb;                     // nui x nT column-major (target residual)
+    double *PL = X + a.mxui * (a.nT > 0 ? a.nT : 1);    // nui x (nrt+nT) column-major: [bub | nul]
+    double *MP = PL + a.mxui * (cmax > 0 ? cmax : 1);   // scratch nui x cmax
+    double *cM = MP + (a.mxu > a.mxp ? a.mxu : a.mxp) * (lbmax > 0 ? lbmax : 1);  // (MP is reused as MB: nua x lbmax)
+    double *W2 = cM + lbmax * lbmax;                    // nqa x nqa (ridge)
+    double *D2 = W2 + a.mxq * a.mxq;                    // nqa x npi
+    double *TMP = D2 + a.mxq * a.mxpi;                  // nqa x npi
+    double *sv = TMP + a.mxq * a.mxpi;                  // nT
+    int *su = reinterpret_cast<int *>(sv + (a.nT > 0 ? a.nT : 1));
+    int *sp = su + a.mxu;
+    int *sq = sp + a.mxp;
+    int *scb = sq + a.mxq;
+    __shared__ int s_piv, s_k;
+    for (int i = tid; i < nua; i += LT) su[i] = a.uJ[us + i];
+    for (int i = tid; i < npa; i += LT) sp[i] = a.pJ[ps + i];
+    for (int i = tid; i < nqa; i += LT) sq[i] = a.qJ[qs + i];
+    for (int i = tid; i < ncb; i += LT) scb[i] = a.cbJ[cbs + i];
+    __syncthreads();
+    // ---- local matrices
+    cta_assemble(Mall, nua, a.Mu, a.slot_u, ents, nents, tid);
+    cta_assemble(Wall, npa, a.Mp, a.slot_p, ents, nents, tid);
+    for (int i = tid; i < npa * nua; i += LT) Dall[i] = 0.0;
+    __syncthreads();
+    for (int r = tid; r < npa; r += LT)
+    {
+        const int row = sp[r];
+        for (int k = a.Dj.I[row]; k < a.Dj.I[row + 1]; ++k)
+        {
+            const int lu = find_lin(su, nua, a.Dj.J[k]);
+            if (lu >= 0) Dall[r * nua + lu] = a.Dj.A[k];
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < npi * nua; idx += LT)      // B = (W D) rows of interior p dofs
+    {
+        const int i = idx / nua, c = idx % nua;
+        double s = 0.0;
+        for (int t = 0; t < npa; ++t) s += Wall[i * npa + t] * Dall[t * nua + c];
+        Brow[idx] = s;
+    }
+    for (int i = tid; i < n * n; i += LT) A[i] = 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < nui * nui; idx += LT) A[(idx / nui) * n + idx % nui] = Mall[(idx / nui) * nua + idx % nui];
+    for (int idx = tid; idx < npi * nui; idx += LT)
+    {
+        const int i = idx / nui, c = idx % nui;
+        const double v = Brow[i * nua + c];
+        A[(nui + i) * n + c] = v; A[c * n + nui + i] = v;
+    }
+    if (a.facet)
+    {
+        // T block: tloc = Wloc * pvloc, pvloc = column pv of P_{j+1} on the interior p dofs
+        const int pvc = a.pvc[ae];
+        for (int i = tid; i < npi; i += LT)
+        {
+            const int row = sp[i];
+            double v = 0.0;
+            for (int k = a.Pj1.I[row]; k < a.Pj1.I[row + 1]; ++k) if (a.Pj1.J[k] == pvc) { v = a.Pj1.A[k]; break; }
+            G[i] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < npi; i += LT)
+        {
+            double s = 0.0;
+            for (int t = 0; t < npi; ++t) s += Wall[i * npa + t] * G[t];
+            A[(n - 1) * n + nui + i] = s; A[(nui + i) * n + n - 1] = s;
+        }
+        __syncthreads();
+    }
+    else
+    {
+        // -C = -(D2^T W2 D2) on the interior p dofs (GetMinusC)
+        cta_assemble(W2, nqa, a.Mq, a.slot_q, ents, nents, tid);
+        for (int i = tid; i < nqa * npi; i += LT) D2[i] = 0.0;
+        __syncthreads();
+        for (int r = tid; r < nqa; r += LT)
+        {
+            const int row = sq[r];
+            for (int k = a.Dj1.I[row]; k < a.Dj1.I[row + 1]; ++k)
+            {
+                const int lp = find_lin(sp, npi, a.Dj1.J[k]);
+                if (lp >= 0) D2[r * npi + lp] = a.Dj1.A[k];
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nqa * npi; idx += LT)
+        {
+            const int r = idx / npi, c = idx % npi;
+            double s = 0.0;
+            for (int t = 0; t < nqa; ++t) s += W2[r * nqa + t] * D2[t * npi + c];
+            TMP[idx] = s;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < npi * npi; idx += LT)
+        {
+            const int i = idx / npi, j = idx % npi;
+            double s = 0.0;
+            for (int t = 0; t < nqa; ++t) s += D2[t * npi + i] * TMP[t * npi + j];
+            A[(nui + i) * n + nui + j] = -s;
+        }
+        __syncthreads();
+    }
+    // ---- boundary traces R_b (nub x ncb) from the rows of P_j written by earlier stages
+    for (int i = tid; i < nub * ncb; i += LT) Rb[i] = 0.0;
+    __syncthreads();
+    for (int r = tid; r < nub; r += LT)
+    {
+        const int d = su[nui + r];
+        const long long st = a.Pj.start[d];
+        for (int k = 0; k < a.Pj.len[d]; ++k)
+        {
+            const int c = find_bin(scb, ncb, a.Pj.J[st + k]);
+            if (c >= 0) Rb[r * ncb + c] = a.Pj.A[st + k];
+        }
+    }
+    for (int i = tid; i < n * nrhs; i += LT) R[i] = 0.0;
+    __syncthreads();
+    // ---- right-hand sides: [extension of the boundary traces | bubbles | targets]
+    for (int idx = tid; idx < nui * ncb; idx += LT)
+    {
+        const int i = idx / ncb, c = idx % ncb;
+        double s = 0.0;
+        for (int t = 0; t < nub; ++t) s += Mall[i * nua + nui + t] * Rb[t * ncb + c];
+        R[i * nrhs + c] = -s;
+    }
+    if (a.facet)
+    {
+        for (int idx = tid; idx < npi * ncb; idx += LT)
+        {
+            const int i = idx / ncb, c = idx % ncb;
+            double s = 0.0;
+            for (int t = 0; t < nub; ++t) s += Brow[i * nua + nui + t] * Rb[t * ncb + c];
+            R[(nui + i) * nrhs + c] = -s;
+        }
+    }
+    else
+    {
+        // G = (P_{j+1} D_c)_loc - D_loc[:, bdr] R_b  on ALL p dofs of the agglomerate
+        for (int r = tid; r < npa; r += LT)
+        {
+            for (int c = 0; c < ncb; ++c) G[r * ncb + c] = 0.0;
+            const int row = sp[r];
+            for (int k = a.Pj1.I[row]; k < a.Pj1.I[row + 1]; ++k)
+            {
+                const int kc = a.Pj1.J[k];
+                const double v = a.Pj1.A[k];
+                const long long st = a.Dc.start[kc];
+                for (int t = 0; t < a.Dc.len[kc]; ++t)
+                {
+                    const int c = find_bin(scb, ncb, a.Dc.J[st + t]);
+                    if (c >= 0) G[r * ncb + c] += v * a.Dc.A[st + t];
+                }
+            }
+            for (int c = 0; c < ncb; ++c)
+            {
+                double s = 0.0;
+                for (int t = 0; t < nub; ++t) s += Dall[r * nua + nui + t] * Rb[t * ncb + c];
+                G[r * ncb + c] -= s;
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < npi * ncb; idx += LT)
+        {
+            const int i = idx / ncb, c = idx % ncb;
+            double s = 0.0;
+            for (int t = 0; t < npa; ++t) s += Wall[i * npa + t] * G[t * ncb + c];
+            R[(nui + i) * nrhs + c] = s;
+        }
+    }
+    // bubbles: rhs_p = Wloc * P_{j+1}[p_int, null coarse dofs]
+    if (nrt > 0)
+    {
+        __syncthreads();
+        const int *pn = a.pnJ + a.pnI[ae];
+        for (int idx = tid; idx < npi * nrt; idx += LT)     // sub -> MP scratch (npi x nrt row-major)
+        {
+            const int i = idx / nrt, q = idx % nrt, row = sp[i];
+            double v = 0.0;
+            for (int k = a.Pj1.I[row]; k < a.Pj1.I[row + 1]; ++k) if (a.Pj1.J[k] == pn[q]) { v = a.Pj1.A[k]; break; }
+            MP[idx] = v;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < npi * nrt; idx += LT)
+        {
+            const int i = idx / nrt, q = idx % nrt;
+            double s = 0.0;
+            for (int t = 0; t < npi; ++t) s += Wall[i * npa + t] * MP[t * nrt + q];
+            R[(nui + i) * nrhs + ncb + q] = s;
+        }
+    }
+    // targets: rhs_u = -M_ib T_bdr ; rhs_p = B_ii T_int
+    for (int idx = tid; idx < nui * nT; idx += LT)
+    {
+        const int i = idx / nT, t = idx % nT;
+        double s = 0.0;
+        for (int b = 0; b < nub; ++b) s += Mall[i * nua + nui + b] * a.T[(size_t)t * a.ldT + su[nui + b]];
+        R[i * nrhs + ncb + nrt + t] = -s;
+    }
+    for (int idx = tid; idx < npi * nT; idx += LT)
+    {
+        const int i = idx / nT, t = idx % nT;
+        double s = 0.0;
+        for (int c = 0; c < nui; ++c) s += Brow[i * nua + c] * a.T[(size_t)t * a.ldT + su[c]];
+        R[(nui + i) * nrhs + ncb + nrt + t] = s;
+    }
+    __syncthreads();
+    // ---- solve all right-hand sides at once
+    int info = 0;
+    if (nui > 0) info = cta_lu_solve(A, n, n, R, nrhs, nrhs, &s_piv, tid, LT);
+    __syncthreads();
+    // ---- outputs
+    double *out = a.out + a.out_off[ae];
+    double *ext_o = out;                                   // nui x ncb   (row-major)
+    double *bub_o = ext_o + (size_t)nui * ncb;             // nui x nrt
+    double *nul_o = bub_o + (size_t)nui * nrt;             // nui x a.nT  (first k columns valid)
+    double *lam_o = nul_o + (size_t)nui * a.nT;            // ncb
+    double *func_o = lam_o + ncb;                          // (nrt + a.nT) x nui
+    double *mass_o = func_o + (size_t)(nrt + a.nT) * nui;  // (ncb + nrt + a.nT)^2, leading (ncb+nrt+k)^2 valid
+    double *sv_o = mass_o + (size_t)(ncb + nrt + a.nT) * (ncb + nrt + a.nT);
+    for (int idx = tid; idx < nui * ncb; idx += LT) ext_o[idx] = R[(idx / ncb) * nrhs + idx % ncb];
+    for (int idx = tid; idx < nui * nrt; idx += LT) { const int i = idx / nrt, q = idx % nrt; const double v = R[i * nrhs + ncb + q]; bub_o[idx] = v; PL[q * nui + i] = v; }
+    if (a.facet)
+        for (int c = tid; c < ncb; c += LT) { const double l = R[(n - 1) * nrhs + c]; lam_o[c] = fabs(l) > a.smallest_entry ? -l : 0.0; }
+    // target residual -> SVD -> NullSpace dofs
+    for (int idx = tid; idx < nui * nT; idx += LT)
+    {
+        const int i = idx / nT, t = idx % nT;
+        X[t * nui + i] = a.T[(size_t)t * a.ldT + su[i]] - R[i * nrhs + ncb + nrt + t];
+    }
+    if (tid == 0) s_k = 0;
+    __syncthreads();
+    if (nT > 0 && tid < 32)
+    {
+        warp_jacobi_svd(X, nui, nT, nui, sv, tid);
+        if (tid == 0)
+        {
+            int k = 0;
+            const int nsv = nui < nT ? nui : nT;
+            while (k < nsv && !(sv[k] < a.svd_tol)) ++k;
+            s_k = k;
+        }
+    }
+    __syncthreads();
+    const int k = s_k, nc = nrt + k, nlb = ncb + nc;
+    for (int idx = tid; idx < nui * k; idx += LT) { const int i = idx % nui, c = idx / nui; const double v = X[c * nui + i]; PL[(nrt + c) * nui + i] = v; nul_o[i * a.nT + c] = v; }
+    for (int t = tid; t < a.nT; t += LT) sv_o[t] = (t < nT && t < (nui < nT ? nui : nT)) ? sv[t] : 0.0;
+    __syncthreads();
+    // dof functional of the interior coarse dofs [RangeT | Null] w.r.t. M_ii
+    int info2 = 0;
+    if (nc > 0)
+    {
+        // M_ii as a compact nui x nui matrix in A (the factorisation is no longer needed)
+        for (int idx = tid; idx < nui * nui; idx += LT) A[idx] = Mall[(idx / nui) * nua + idx % nui];
+        __syncthreads();
+        info2 = cta_dof_functional(PL, nui, nc, nui, A, nui, MP, cM, R, &s_piv, tid, LT);
+        __syncthreads();
+        for (int idx = tid; idx < nc * nui; idx += LT) func_o[idx] = R[idx];
+    }
+    __syncthreads();
+    // coarse mass: basis^T M_aa basis, basis = [[ext bub nul]; [Rb 0 0]]  (order [bdr | RangeT | Null])
+    double *MB = MP;     // nua x nlb row-major
+    for (int idx = tid; idx < nua * nlb; idx += LT)
+    {
+        const int i = idx / nlb, c = idx % nlb;
+        double s = 0.0;
+        for (int t = 0; t < nua; ++t)
+        {
+            double b;
+            if (t < nui) b = c < ncb ? ext_o[t * ncb + c] : PL[(c - ncb) * nui + t];
+            else b = c < ncb ? Rb[(t - nui) * ncb + c] : 0.0;
+            s += Mall[i * nua + t] * b;
+        }
+        MB[idx] = s;
+    }
+    __syncthreads();
+    const int ldm = ncb + nrt + a.nT;
+    for (int idx = tid; idx < nlb * nlb; idx += LT)
+    {
+        const int x = idx / nlb, y = idx % nlb;
+        double v = 0.0, w = 0.0;
+        for (int t = 0; t < nua; ++t)
+        {
+            double bx, by;
+            if (t < nui) { bx = x < ncb ? ext_o[t * ncb + x] : PL[(x - ncb) * nui + t]; by = y < ncb ? ext_o[t * ncb + y] : PL[(y - ncb) * nui + t]; }
+            else { bx = x < ncb ? Rb[(t - nui) * ncb + x] : 0.0; by = y < ncb ? Rb[(t - nui) * ncb + y] : 0.0; }
+            v += bx * MB[t * nlb + y];
+            w += by * MB[t * nlb + x];
+        }
+        mass_o[x * ldm + y] = 0.5 * (v + w);
+    }
+    if (tid == 0) { a.k_out[ae] = k; a.info_out[ae] = info ? info : (info2 ? 1000 + info2 : 0); }
+}
+
+// ---------------------------------------------------------------------------
+// host wrappers: upload the batch description, run, download the results
+// ---------------------------------------------------------------------------
+namespace
+{
+struct DevBuf
+{
+    std::vector<void *> ptrs;
+    cudaStream_t st;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
+    template <class T> int up(const T *h, size_t n, const T **out)
+    {
+        T *d = nullptr;
+        PE_CUDA(cudaMalloc(&d, sizeof(T) * (n > 0 ? n : 1)));
+        ptrs.push_back(d);
+        if (n > 0 && h) PE_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+        *out = d;
+        return 0;
+    }
+    template <class T> int alloc(size_t n, T **out)
+    {
+        PE_CUDA(cudaMalloc(out, sizeof(T) * (n > 0 ? n : 1)));
+        ptrs.push_back(*out);
+        return 0;
+    }
+};
+}
+
+extern "C" int pe_batched_traces(pe_ctx *ctx, const pe_trace_batch *b)
+{
+    PE_CHECK(ctx && b, "bad arguments");
+    if (b->nAE == 0) return 0;
+    cudaStream_t st = ctx->stream;
+    DevBuf D(st);
+    TraceArgs a{};
+    a.nAE = b->nAE; a.nT = b->nT; a.ldT = b->ldT; a.svd_tol = b->svd_tol;
+    const int nadof = b->I[b->nAE];
+    int max_m = 0;
+    for (int e = 0; e < b->nAE; ++e) max_m = std::max(max_m, b->I[e + 1] - b->I[e]);
+    a.max_m = max_m;
+    PE_TRY(D.up(b->I, (size_t)b->nAE + 1, &a.I));
+    PE_TRY(D.up(b->J, (size_t)nadof, &a.J));
+    PE_TRY(D.up(b->pv, (size_t)b->ndofs, &a.pv));
+    PE_TRY(D.up(b->diagM, (size_t)nadof, &a.diagM));
+    PE_TRY(D.up(b->T, (size_t)b->ldT * b->nT, &a.T));
+    PE_TRY(D.up(b->out_off, (size_t)b->nAE + 1, (const long long **)&a.out_off));
+    const size_t out_n = (size_t)b->out_off[b->nAE];
+    PE_TRY(D.alloc(out_n, &a.out));
+    PE_CUDA(cudaMemsetAsync(a.out, 0, sizeof(double) * out_n, st));
+    PE_TRY(D.alloc((size_t)b->nAE, &a.ndofs_out));
+    PE_TRY(D.alloc((size_t)b->nAE, &a.info_out));
+    const int nT1 = b->nT > 0 ? b->nT : 1, ncm = b->nT + 1;
+    size_t smem = sizeof(double) * ((size_t)max_m * nT1 + 2 * (size_t)max_m + nT1 + 2 * (size_t)max_m * ncm + (size_t)ncm * ncm + (size_t)max_m * ncm);
+    PE_CHECK(smem <= 200 * 1024, "pe_batched_traces: agglomerated entity too large for shared memory");
+    PE_CUDA(cudaFuncSetAttribute(k_traces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_traces<<<b->nAE, 32, smem, st>>>(a);
+    PE_LAUNCHED(ctx);
+    PE_CUDA(cudaMemcpyAsync(b->out, a.out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, st));
+    PE_CUDA(cudaMemcpyAsync(b->ndofs_out, a.ndofs_out, sizeof(int) * (size_t)b->nAE, cudaMemcpyDeviceToHost, st));
+    std::vector<int> info(b->nAE);
+    PE_CUDA(cudaMemcpyAsync(info.data(), a.info_out, sizeof(int) * (size_t)b->nAE, cudaMemcpyDeviceToHost, st));
+    PE_CUDA(cudaStreamSynchronize(st));
+    for (int e = 0; e < b->nAE; ++e)
+        PE_CHECK(info[e] == 0, "pe_batched_traces: singular local coarse mass matrix (agglomerate " + std::to_string(e) + ")");
+    return 0;
+}
+
+static int up_pool(DevBuf &D, const pe_blockpool_view &h, PoolV &d)
+{
+    PE_TRY(D.up(h.off, (size_t)h.n + 1, (const long long **)&d.off));
+    PE_TRY(D.up(h.size, (size_t)h.n, &d.size));
+    PE_TRY(D.up(h.rdoff, (size_t)h.n + 1, &d.rdoff));
+    PE_TRY(D.up(h.vals, (size_t)(h.n > 0 ? h.off[h.n] : 0), &d.vals));
+    return 0;
+}
+static int up_csr(DevBuf &D, const pe_csr_view &h, CsrV &d)
+{
+    PE_TRY(D.up(h.I, (size_t)h.nrows + 1, &d.I));
+    const size_t nnz = h.nrows > 0 && h.I ? (size_t)h.I[h.nrows] : 0;
+    PE_TRY(D.up(h.J, nnz, &d.J));
+    PE_TRY(D.up(h.A, nnz, &d.A));
+    return 0;
+}
+static int up_rowpool(DevBuf &D, const pe_rowpool_view &h, RowPoolV &d)
+{
+    PE_TRY(D.up(h.start, (size_t)h.nrows, (const long long **)&d.start));
+    PE_TRY(D.up(h.len, (size_t)h.nrows, &d.len));
+    PE_TRY(D.up(h.J, (size_t)h.pool_size, &d.J));
+    PE_TRY(D.up(h.A, (size_t)h.pool_size, &d.A));
+    return 0;
+}
+
+extern "C" int pe_batched_extension(pe_ctx *ctx, const pe_extension_batch *b)
+{
+    PE_CHECK(ctx && b, "bad arguments");
+    if (b->nAE == 0) return 0;
+    cudaStream_t st = ctx->stream;
+    DevBuf D(st);
+    ExtArgs a{};
+    const int nAE = b->nAE;
+    a.nAE = nAE; a.facet = b->facet; a.compute_null = b->compute_null;
+    a.nT = b->nT; a.ldT = b->ldT; a.svd_tol = b->svd_tol; a.smallest_entry = b->smallest_entry;
+    PE_TRY(D.up(b->uI, (size_t)nAE + 1, &a.uI)); PE_TRY(D.up(b->uJ, (size_t)b->uI[nAE], &a.uJ)); PE_TRY(D.up(b->uNint, (size_t)nAE, &a.uN));
+    PE_TRY(D.up(b->pI, (size_t)nAE + 1, &a.pI)); PE_TRY(D.up(b->pJ, (size_t)b->pI[nAE], &a.pJ)); PE_TRY(D.up(b->pNint, (size_t)nAE, &a.pN));
+    PE_TRY(D.up(b->aeI, (size_t)nAE + 1, &a.aeI)); PE_TRY(D.up(b->aeJ, (size_t)b->aeI[nAE], &a.aeJ));
+    PE_TRY(up_pool(D, b->Mu, a.Mu)); PE_TRY(up_pool(D, b->Mp, a.Mp));
+    PE_TRY(D.up(b->slot_u, (size_t)b->Mu.rdoff[b->Mu.n], &a.slot_u));
+    PE_TRY(D.up(b->slot_p, (size_t)b->Mp.rdoff[b->Mp.n], &a.slot_p));
+    PE_TRY(up_csr(D, b->Dj, a.Dj));
+    PE_TRY(D.up(b->cbI, (size_t)nAE + 1, &a.cbI)); PE_TRY(D.up(b->cbJ, (size_t)b->cbI[nAE], &a.cbJ));
+    PE_TRY(up_rowpool(D, b->Pj, a.Pj));
+    PE_TRY(up_csr(D, b->Pj1, a.Pj1));
+    PE_TRY(D.up(b->pnI, (size_t)nAE + 1, &a.pnI)); PE_TRY(D.up(b->pnJ, (size_t)b->pnI[nAE], &a.pnJ));
+    if (b->facet) PE_TRY(D.up(b->pvc, (size_t)nAE, &a.pvc));
+    else
+    {
+        PE_TRY(D.up(b->qI, (size_t)nAE + 1, &a.qI)); PE_TRY(D.up(b->qJ, (size_t)b->qI[nAE], &a.qJ));
+        PE_TRY(up_pool(D, b->Mq, a.Mq));
+        PE_TRY(D.up(b->slot_q, (size_t)b->Mq.rdoff[b->Mq.n], &a.slot_q));
+        PE_TRY(up_csr(D, b->Dj1, a.Dj1));
+        PE_TRY(up_rowpool(D, b->Dc, a.Dc));
+    }
+    PE_TRY(D.up(b->T, (size_t)b->ldT * b->nT, &a.T));
+    PE_TRY(D.up(b->out_off, (size_t)nAE + 1, (const long long **)&a.out_off));
+    const size_t out_n = (size_t)b->out_off[nAE];
+    PE_TRY(D.alloc(out_n, &a.out));
+    PE_CUDA(cudaMemsetAsync(a.out, 0, sizeof(double) * out_n, st));
+    PE_TRY(D.alloc((size_t)nAE, &a.k_out));
+    PE_TRY(D.alloc((size_t)nAE, &a.info_out));
+    for (int e = 0; e < nAE; ++e)
+    {
+        a.mxu = std::max(a.mxu, b->uI[e + 1] - b->uI[e]); a.mxui = std::max(a.mxui, b->uNint[e]);
+        a.mxp = std::max(a.mxp, b->pI[e + 1] - b->pI[e]); a.mxpi = std::max(a.mxpi, b->pNint[e]);
+        if (!b->facet) a.mxq = std::max(a.mxq, b->qI[e + 1] - b->qI[e]);
+        a.mxcb = std::max(a.mxcb, b->cbI[e + 1] - b->cbI[e]); a.mxrt = std::max(a.mxrt, b->pnI[e + 1] - b->pnI[e]);
+    }
+    const size_t nmax = (size_t)a.mxui + a.mxpi + 1, rmax = (size_t)a.mxcb + a.mxrt + a.nT, cmax = (size_t)a.mxrt + a.nT, lbmax = a.mxcb + cmax;
+    const size_t nT1 = a.nT > 0 ? a.nT : 1;
+    size_t nd = (size_t)a.mxu * a.mxu + (size_t)a.mxp * a.mxp + (size_t)a.mxp * a.mxu + (size_t)a.mxpi * a.mxu + nmax * nmax + nmax * rmax
+                + (size_t)a.mxu * a.mxcb + (size_t)a.mxp * a.mxcb + (size_t)a.mxui * nT1 + (size_t)a.mxui * (cmax > 0 ? cmax : 1)
+                + (size_t)std::max(a.mxu, a.mxp) * (lbmax > 0 ? lbmax : 1) + lbmax * lbmax + (size_t)a.mxq * a.mxq + 2 * (size_t)a.mxq * a.mxpi + nT1;
+    size_t smem = sizeof(double) * nd + sizeof(int) * ((size_t)a.mxu + a.mxp + a.mxq + a.mxcb) + 16;
+    // the functional / solve scratch reuses R (n x nrhs) for an nc x nui matrix and MP for nua x nlb: covered by
+    // nmax*rmax >= cmax*mxui only if rmax >= cmax (true) and nmax >= mxui (true)
+    PE_CHECK(smem <= 220 * 1024, "pe_batched_extension: agglomerate too large for shared memory ("
+                                     + std::to_string(smem) + " bytes needed)");
+    PE_CUDA(cudaFuncSetAttribute(k_extension, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_extension<<<nAE, LT, smem, st>>>(a);
+    PE_LAUNCHED(ctx);
+    PE_CUDA(cudaMemcpyAsync(b->out, a.out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, st));
+    PE_CUDA(cudaMemcpyAsync(b->k_out, a.k_out, sizeof(int) * (size_t)nAE, cudaMemcpyDeviceToHost, st));
+    std::vector<int> info(nAE);
+    PE_CUDA(cudaMemcpyAsync(info.data(), a.info_out, sizeof(int) * (size_t)nAE, cudaMemcpyDeviceToHost, st));
+    PE_CUDA(cudaStreamSynchronize(st));
+    for (int e = 0; e < nAE; ++e)
+        PE_CHECK(info[e] == 0, "pe_batched_extension: singular local system on agglomerate " + std::to_string(e)
+                                   + " (code " + std::to_string(info[e]) + "); a bad topology (e.g. a torus-shaped agglomerate) can cause this");
+    return 0;
+}

@@ -1,0 +1,490 @@
+// amge_coarsen.cpp -- DeRhamSequence::Coarsen() (src/amge/DeRhamSequence.cpp:572-692):
+// the host walks the forms (L2 -> H(div) -> H(curl) -> H1) and the stages
+//   ComputeCoarseTraces            :1521-2085
+//   hFacetExtension                :2214-2581
+//   hRidgePeakExtension            :2629-3048
+// builds the integer batch description of every stage (agglomerate -> dof lists, boundary
+// coarse dofs, ...), hands the per-agglomerate dense work to the batched CUDA kernels of
+// csrc/pe_local.cu through the C ABI (include/parelag_b200_local.h), and commits the
+// results: coarse dof numbering (DofHandlerALG), P_, the coarse D_, the coarse
+// element/facet/ridge mass matrices and the dof functionals of the cochain projector.
+// Single rank (dof == true dof).
+#include "amge_coarsen.hpp"
+#include "parelag_b200_local.h"
+#include <cstring>
+
+namespace parelag
+{
+namespace
+{
+/// rows written once, in any order (P_ under construction, coarse D_)
+struct RowPool
+{
+    std::vector<long long> start;
+    std::vector<int> len, J;
+    std::vector<double> A;
+    explicit RowPool(int nrows = 0) : start(nrows, 0), len(nrows, 0) {}
+    void set_row(int r, const int *cols, const double *vals, int n)
+    {
+        PARELAG_TEST_FOR_EXCEPTION(len[r] != 0, std::runtime_error, "RowPool: row " << r << " written twice");
+        start[r] = (long long)J.size(); len[r] = n;
+        J.insert(J.end(), cols, cols + n); A.insert(A.end(), vals, vals + n);
+    }
+    pe_rowpool_view view() const
+    {
+        pe_rowpool_view v{};
+        v.nrows = (int)start.size(); v.pool_size = (long long)J.size();
+        v.start = start.data(); v.len = len.data(); v.J = J.data(); v.A = A.data();
+        return v;
+    }
+    HostCSR to_csr(int ncols) const
+    {
+        HostCSR C;
+        C.nrows = (int)start.size(); C.ncols = ncols;
+        C.I.assign(C.nrows + 1, 0);
+        for (int r = 0; r < C.nrows; ++r) C.I[r + 1] = C.I[r] + len[r];
+        C.J.resize(C.I.back()); C.A.resize(C.I.back());
+        for (int r = 0; r < C.nrows; ++r)
+        {
+            std::copy(J.begin() + start[r], J.begin() + start[r] + len[r], C.J.begin() + C.I[r]);
+            std::copy(A.begin() + start[r], A.begin() + start[r] + len[r], C.A.begin() + C.I[r]);
+        }
+        return C;
+    }
+};
+
+struct PoolView
+{
+    std::vector<int> rdoff;
+    pe_blockpool_view v{};
+    explicit PoolView(const BlockPool &P) : rdoff(P.rdof_offsets())
+    {
+        v.n = P.n(); v.off = (const long long *)P.off.data(); v.size = P.size.data(); v.rdoff = rdoff.data(); v.vals = P.vals.data();
+    }
+};
+inline pe_csr_view csr_view(const HostCSR &M)
+{
+    pe_csr_view v{};
+    v.nrows = M.nrows; v.ncols = M.ncols; v.I = M.I.data(); v.J = M.J.data(); v.A = M.A.data();
+    return v;
+}
+
+/// PV trace vector of codimension c (DeRhamSequence3D_FE::computePVTraces on the fine
+/// level, DeRhamSequenceAlg::computePVTraces below)
+std::vector<double> pv_traces(const SequenceData &S, int c)
+{
+    const int j = S.nforms - 1 - c;
+    const int nd = S.dof[j]->ndofs;
+    const HostCSR &AEe = S.topo->AEntityEntity(c);
+    std::vector<double> pv(nd, 0.0);
+    if (S.is_fe)
+    {
+        if (c == 0) { std::fill(pv.begin(), pv.end(), 1.0); return pv; }
+        for (size_t k = 0; k < AEe.J.size(); ++k)
+        {
+            const int e = AEe.J[k];
+            pv[e] = c == 1 ? AEe.A[k] * S.facet_area[e] : (c == 2 ? AEe.A[k] * S.ridge_length[e] : 1.0);
+        }
+        return pv;
+    }
+    const HostCSR &ED = S.dof[j]->entity_dof[c];
+    for (size_t k = 0; k < AEe.J.size(); ++k) pv[ED.J[ED.I[AEe.J[k]]]] = AEe.A[k];
+    return pv;
+}
+
+struct Coarsener
+{
+    DeRhamSequence &fine;
+    SequenceData &S;
+    std::shared_ptr<DeRhamSequence> coarse;
+    std::shared_ptr<SequenceData> C;
+    std::vector<std::unique_ptr<DofAgglomeration>> agg;
+    std::vector<RowPool> Ppool;      // per form
+    std::vector<RowPool> Dcpool;     // per form j: rows = coarse dofs of form j+1
+    std::vector<HostCSR> Pfinal;
+    pe_ctx *ctx;
+
+    Coarsener(DeRhamSequence &f) : fine(f), S(*f.data), ctx(Device::Get()) {}
+
+    void run()
+    {
+        auto ctopo = S.topo->CoarserTopology();
+        PARELAG_TEST_FOR_EXCEPTION(!ctopo, std::runtime_error, "DeRhamSequence::Coarsen(): coarsen the topology first");
+        const int nf = S.nforms, ndim = nf - 1;
+        coarse = std::make_shared<DeRhamSequence>(nf);
+        C = std::make_shared<SequenceData>();
+        coarse->data = C;
+        C->topo = ctopo; C->nforms = nf; C->jstart = S.jstart; C->svd_tol = S.svd_tol; C->is_fe = false;
+        C->dof.resize(nf); C->targets.resize(nf); C->ntargets = S.ntargets;
+        agg.resize(nf); Ppool.resize(nf); Dcpool.resize(nf); Pfinal.resize(nf);
+        for (int j = S.jstart; j < nf; ++j) agg[j] = std::make_unique<DofAgglomeration>(S.topo, *S.dof[j]);
+        for (int codim = 0; codim < nf; ++codim)
+        {
+            const int j = nf - codim - 1;
+            if (j < S.jstart) break;
+            C->dof[j] = std::make_shared<DofHandlerX>(codim, ctopo);
+            Ppool[j] = RowPool(S.dof[j]->ndofs);
+            if (j < ndim) Dcpool[j] = RowPool(C->dof[j + 1]->ndofs);
+            traces(j);
+            if (codim > 0)
+            {
+                extension(j, nf - j - 2, true);
+                if (codim > 1)
+                {
+                    extension(j, nf - j - 3, false);
+                    if (codim > 2) extension(j, nf - j - 4, false);
+                }
+            }
+            Pfinal[j] = Ppool[j].to_csr(C->dof[j]->ndofs);
+            fine.SetP(j, Pfinal[j]);
+            if (codim > 0) coarse->SetD(j, Dcpool[j].to_csr(C->dof[j]->ndofs));
+            C->dof[j]->ComputeBoundaryMask();
+            coarse->SetDofHandlerRaw(j, C->dof[j].get());
+            project_targets(j);
+        }
+        // the constant-one representation in L2
+        C->l2const = project(nf - 1, S.l2const, 1);
+        fine.SetCoarserSequence(coarse);
+    }
+
+    // ------------------------------------------------------------------ traces
+    void traces(int j)
+    {
+        const int codim = S.nforms - 1 - j;
+        DofAgglomeration &ag = *agg[j];
+        DofHandlerX &cd = *C->dof[j];
+        const int nAE = ag.nAE(codim);
+        BlockPool &mass = C->M[{j, codim}];
+        auto &func = C_func(j, codim);
+        func.resize(nAE);
+        if (j == 0)
+        {
+            // Compute0formCoarseTraces: P(vertex, coarse peak) = 1
+            for (int a = 0; a < nAE; ++a)
+            {
+                PARELAG_TEST_FOR_EXCEPTION(ag.I[codim][a + 1] - ag.I[codim][a] != 1, std::runtime_error,
+                                           "DeRhamSequence::compute0formCoarseTraces: likely topology error, possibly disconnected edge.");
+                const int fd = ag.J[codim][ag.I[codim][a]];
+                const double one = 1.0;
+                Ppool[0].set_row(fd, &a, &one, 1);
+                cd.SetDofType(a, DOF_RANGET);
+                cd.n_rangeT[codim][a] = 1;
+                func[a] = {1, 1, {1.0}};
+                *mass.add(1) = 1.0;
+            }
+            cd.BuildEntityDofTable(codim);
+            return;
+        }
+        const std::vector<double> pv = pv_traces(S, codim);
+        // agglomerate mass matrix: the entities of codimension `codim` carry disjoint dofs,
+        // so M_d is block diagonal with the entity blocks; the GPU path needs it diagonal
+        const BlockPool &Me = S.M.at({j, codim});
+        const auto rdoff = Me.rdof_offsets();
+        std::vector<double> diagM(ag.J[codim].size(), 0.0);
+        const HostCSR &AEe = S.topo->AEntityEntity(codim);
+        for (int a = 0; a < nAE; ++a)
+            for (int k = AEe.I[a]; k < AEe.I[a + 1]; ++k)
+            {
+                const int e = AEe.J[k], m = Me.size[e];
+                const double *blk = Me.block(e);
+                for (int x = 0; x < m; ++x)
+                    for (int y = 0; y < m; ++y)
+                    {
+                        if (x == y) diagM[ag.I[codim][a] + ag.slot[codim][rdoff[e] + x]] += blk[x * m + x];
+                        else
+                            PARELAG_TEST_FOR_EXCEPTION(std::fabs(blk[x * m + y]) > 1e-10 * std::fabs(blk[x * m + x]), not_implemented_error,
+                                                       "ComputeCoarseTraces: non-diagonal trace mass matrix (dense-weighted SVD) is not available on the GPU path");
+                    }
+            }
+        const int nT = S.ntargets[j];
+        std::vector<long long> off(nAE + 1, 0);
+        for (int a = 0; a < nAE; ++a)
+        {
+            const long long m = ag.I[codim][a + 1] - ag.I[codim][a], c = nT + 1;
+            off[a + 1] = off[a] + m * c + c * c + c * m + nT;
+        }
+        std::vector<double> out(off[nAE]);
+        std::vector<int> ndofs(nAE);
+        pe_trace_batch b{};
+        b.nAE = nAE; b.ndofs = S.dof[j]->ndofs; b.I = ag.I[codim].data(); b.J = ag.J[codim].data();
+        b.pv = pv.data(); b.diagM = diagM.data(); b.nT = nT; b.ldT = S.dof[j]->ndofs; b.T = S.targets[j].data();
+        b.svd_tol = S.svd_tol; b.out_off = off.data(); b.out = out.data(); b.ndofs_out = ndofs.data();
+        PE_CALL(pe_batched_traces(ctx, &b));
+        // commit: dof types / counts, entity table, P rows, coarse trace mass, functionals
+        int cnt = 0;
+        for (int a = 0; a < nAE; ++a)
+        {
+            cd.SetDofType(cnt++, DOF_RANGET);
+            for (int q = 1; q < ndofs[a]; ++q) cd.SetDofType(cnt++, DOF_NULLSPACE);
+            cd.n_rangeT[codim][a] = 1;
+            cd.n_null[codim][a] = ndofs[a] - 1;
+        }
+        cd.BuildEntityDofTable(codim);
+        const HostCSR &ED = cd.entity_dof[codim];
+        std::vector<double> rowv;
+        long long nnull = 0;
+        for (int a = 0; a < nAE; ++a)
+        {
+            const int s = ag.I[codim][a], m = ag.I[codim][a + 1] - s, nc = ndofs[a], cmax = nT + 1;
+            const double *p = out.data() + off[a], *ms = p + (size_t)m * cmax, *fn = ms + cmax * cmax;
+            nnull += nc - 1;
+            rowv.resize(nc);
+            for (int i = 0; i < m; ++i)
+            {
+                for (int c = 0; c < nc; ++c) rowv[c] = p[c * m + i];
+                Ppool[j].set_row(ag.J[codim][s + i], ED.J.data() + ED.I[a], rowv.data(), nc);
+            }
+            double *mb = mass.add(nc);
+            std::copy(ms, ms + nc * nc, mb);
+            func[a] = {nc, m, std::vector<double>(fn, fn + (size_t)nc * m)};
+        }
+        C->stats["trace_null_" + std::to_string(j)] = nnull;
+    }
+
+    // ------------------------------------------------------------------ extensions
+    void extension(int j, int cdom, bool facet)
+    {
+        const int nf = S.nforms;
+        const bool ridge_stuff = (cdom == nf - j - 3);
+        DofAgglomeration &au = *agg[j], &ap = *agg[j + 1];
+        DofHandlerX &ucd = *C->dof[j], &pcd = *C->dof[j + 1];
+        const int nAE = C->topo->GetNumberLocalEntities(cdom);
+        const int nT = S.ntargets[j];
+        PoolView Mu(S.M.at({j, cdom})), Mp(S.M.at({j + 1, cdom}));
+        std::unique_ptr<PoolView> Mq;
+        pe_extension_batch b{};
+        b.nAE = nAE; b.facet = facet ? 1 : 0; b.compute_null = (facet || ridge_stuff) && nT > 0 ? 1 : 0;
+        b.uI = au.I[cdom].data(); b.uJ = au.J[cdom].data(); b.uNint = au.nint[cdom].data();
+        b.pI = ap.I[cdom].data(); b.pJ = ap.J[cdom].data(); b.pNint = ap.nint[cdom].data();
+        const HostCSR &AEe = S.topo->AEntityEntity(cdom);
+        b.aeI = AEe.I.data(); b.aeJ = AEe.J.data();
+        b.Mu = Mu.v; b.Mp = Mp.v; b.slot_u = au.slot[cdom].data(); b.slot_p = ap.slot[cdom].data();
+        const HostCSR &Dj = *fine.GetDerivativeOperator(j);
+        b.Dj = csr_view(Dj);
+        // coarse dofs on the boundary of every agglomerate, PV / NullSpace dofs of form j+1
+        std::vector<int> cbI(nAE + 1, 0), cbJ, pvc(nAE, -1), pnI(nAE + 1, 0), pnJ, tmp;
+        for (int a = 0; a < nAE; ++a)
+        {
+            ucd.GetDofsOnBdr(cdom, a, tmp);
+            PARELAG_ASSERT(std::is_sorted(tmp.begin(), tmp.end()));
+            cbJ.insert(cbJ.end(), tmp.begin(), tmp.end());
+            cbI[a + 1] = (int)cbJ.size();
+            if (facet)
+            {
+                pcd.GetTypedInteriorDofs(cdom, a, DOF_RANGET, tmp);
+                PARELAG_TEST_FOR_EXCEPTION(tmp.size() != 1, std::runtime_error, "hFacetExtension: expected exactly one PV dof of form " << j + 1 << " per agglomerate");
+                pvc[a] = tmp[0];
+            }
+            pcd.GetTypedInteriorDofs(cdom, a, DOF_NULLSPACE, tmp);
+            pnJ.insert(pnJ.end(), tmp.begin(), tmp.end());
+            pnI[a + 1] = (int)pnJ.size();
+        }
+        b.cbI = cbI.data(); b.cbJ = cbJ.data(); b.pvc = pvc.data(); b.pnI = pnI.data(); b.pnJ = pnJ.data();
+        b.Pj = Ppool[j].view();
+        b.Pj1 = csr_view(Pfinal[j + 1]);
+        if (!facet)
+        {
+            DofAgglomeration &aq = *agg[j + 2];
+            Mq = std::make_unique<PoolView>(S.M.at({j + 2, cdom}));
+            b.qI = aq.I[cdom].data(); b.qJ = aq.J[cdom].data();
+            b.Mq = Mq->v; b.slot_q = aq.slot[cdom].data();
+            b.Dj1 = csr_view(*fine.GetDerivativeOperator(j + 1));
+            b.Dc = Dcpool[j].view();
+        }
+        b.nT = nT; b.ldT = S.dof[j]->ndofs; b.T = S.targets[j].data();
+        b.svd_tol = S.svd_tol; b.smallest_entry = 2.220446049250313e-16;
+        std::vector<long long> off(nAE + 1, 0);
+        for (int a = 0; a < nAE; ++a)
+        {
+            const long long nu = au.nint[cdom][a], ncb = cbI[a + 1] - cbI[a], nrt = pnI[a + 1] - pnI[a], lb = ncb + nrt + nT;
+            off[a + 1] = off[a] + nu * ncb + nu * nrt + nu * nT + ncb + (nrt + nT) * nu + lb * lb + nT;
+        }
+        std::vector<double> out(off[nAE]);
+        std::vector<int> kout(nAE, 0);
+        b.out_off = off.data(); b.out = out.data(); b.k_out = kout.data();
+        PE_CALL(pe_batched_extension(ctx, &b));
+        // ---- commit
+        int counter = ucd.ndofs;
+        BlockPool &mass = C->M[{j, cdom}];
+        auto &func = C_func(j, cdom);
+        func.resize(nAE);
+        std::vector<int> cols;
+        std::vector<double> vals;
+        long long tot_rt = 0, tot_null = 0;
+        for (int a = 0; a < nAE; ++a)
+        {
+            const int us = au.I[cdom][a], nu = au.nint[cdom][a];
+            const int ncb = cbI[a + 1] - cbI[a], nrt = pnI[a + 1] - pnI[a], k = kout[a];
+            const int *cb = cbJ.data() + cbI[a];
+            const double *ext = out.data() + off[a], *bub = ext + (size_t)nu * ncb, *nul = bub + (size_t)nu * nrt, *lam = nul + (size_t)nu * nT;
+            const double *fn = lam + ncb, *ms = fn + (size_t)(nrt + nT) * nu;
+            const int ldm = ncb + nrt + nT, nlb = ncb + nrt + k;
+            ucd.n_rangeT[cdom][a] = nrt; ucd.n_null[cdom][a] = k;
+            tot_rt += nrt; tot_null += k;
+            const int c_rt = counter, c_nu = counter + nrt;
+            counter += nrt + k;
+            for (int q = 0; q < nrt; ++q) ucd.SetDofType(c_rt + q, DOF_RANGET);
+            for (int q = 0; q < k; ++q) ucd.SetDofType(c_nu + q, DOF_NULLSPACE);
+            cols.assign(cb, cb + ncb);
+            for (int q = 0; q < nrt + k; ++q) cols.push_back(c_rt + q);
+            vals.resize(nlb);
+            for (int i = 0; i < nu; ++i)
+            {
+                for (int c = 0; c < ncb; ++c) vals[c] = ext[i * ncb + c];
+                for (int q = 0; q < nrt; ++q) vals[ncb + q] = bub[i * nrt + q];
+                for (int q = 0; q < k; ++q) vals[ncb + nrt + q] = nul[i * nT + q];
+                Ppool[j].set_row(au.J[cdom][us + i], cols.data(), vals.data(), nlb);
+            }
+            if (facet) Dcpool[j].set_row(pvc[a], cb, lam, ncb);      // coarse exterior derivative of the PV dof
+            for (int q = 0; q < nrt; ++q)
+            {
+                const int col = c_rt + q; const double one = 1.0;
+                Dcpool[j].set_row(pnJ[pnI[a] + q], &col, &one, 1);
+            }
+            double *mb = mass.add(nlb);
+            for (int x = 0; x < nlb; ++x) for (int y = 0; y < nlb; ++y) mb[x * nlb + y] = ms[x * ldm + y];
+            func[a] = {nrt + k, nu, std::vector<double>(fn, fn + (size_t)(nrt + k) * nu)};
+        }
+        ucd.BuildEntityDofTable(cdom);
+        PARELAG_TEST_FOR_EXCEPTION(ucd.ndofs != counter, std::runtime_error, "extension: coarse dof counter mismatch");
+        const std::string tag = (facet ? "facet_ext_" : "ridgepeak_ext_") + std::to_string(j) + "_" + std::to_string(cdom);
+        C->stats[tag + "_rangeT"] = tot_rt; C->stats[tag + "_null"] = tot_null;
+    }
+
+    // ------------------------------------------------------------------ cochain projector
+    struct Rect { int rows = 0, cols = 0; std::vector<double> v; };
+    std::map<std::pair<int, int>, std::vector<Rect>> funcs;
+    std::vector<Rect> &C_func(int j, int c) { return funcs[{j, c}]; }
+
+    /// CochainProjector::Project (CochainProjector.cpp:147-217) for nv column vectors
+    std::vector<double> project(int j, const std::vector<double> &vFine, int nv)
+    {
+        const int nfd = S.dof[j]->ndofs, ncd = C->dof[j]->ndofs;
+        const DofHandlerX &cd = *C->dof[j];
+        const DofAgglomeration &ag = *agg[j];
+        const HostCSR &P = Pfinal[j];
+        std::vector<double> vC((size_t)ncd * nv, 0.0), res(vFine);
+        for (int codim = cd.mcb; codim >= 0; --codim)
+        {
+            const auto &F = funcs[{j, codim}];
+            for (int e = 0; e < C->topo->GetNumberLocalEntities(codim); ++e)
+            {
+                const Rect &f = F[e];
+                const int c0 = cd.int_offsets[codim][e];
+                const int *fd = ag.J[codim].data() + ag.I[codim][e];
+                for (int v = 0; v < nv; ++v)
+                    for (int r = 0; r < f.rows; ++r)
+                    {
+                        double s = 0.0;
+                        for (int c = 0; c < f.cols; ++c) s += f.v[(size_t)r * f.cols + c] * res[(size_t)v * nfd + fd[c]];
+                        vC[(size_t)v * ncd + c0 + r] = s;
+                    }
+            }
+            res = vFine;
+            for (int v = 0; v < nv; ++v)
+                for (int i = 0; i < nfd; ++i)
+                {
+                    double s = 0.0;
+                    for (int k = P.I[i]; k < P.I[i + 1]; ++k) s += P.A[k] * vC[(size_t)v * ncd + P.J[k]];
+                    res[(size_t)v * nfd + i] -= s;
+                }
+        }
+        return vC;
+    }
+    void project_targets(int j) { C->targets[j] = project(j, S.targets[j], S.ntargets[j]); }
+};
+} // namespace
+
+void DeRhamSequence::SetSVDTol(double tol) { PARELAG_ASSERT(data); data->svd_tol = tol; }
+void DeRhamSequence::SetjformStart(int jform) { PARELAG_ASSERT(data); data->jstart = jform; }
+
+std::shared_ptr<DeRhamSequence> DeRhamSequence::Coarsen()
+{
+    PARELAG_TEST_FOR_EXCEPTION(!data, std::runtime_error, "DeRhamSequence::Coarsen(): this sequence holds externally supplied operators only");
+    Coarsener c(*this);
+    c.run();
+    return c.coarse;
+}
+
+HostCSR DeRhamSequence::ComputeMassOperator(int jform) const
+{
+    PARELAG_ASSERT(data);
+    const BlockPool &Me = data->M.at({jform, 0});
+    const HostCSR &ED = data->dof[jform]->entity_dof[0];
+    // assemble sum_e R_e^T M_e R_e with a row-wise accumulator (canonical CSR)
+    const int nd = data->dof[jform]->ndofs;
+    std::vector<std::vector<std::pair<int, double>>> rows(nd);
+    for (int e = 0; e < ED.nrows; ++e)
+    {
+        const int m = Me.size[e];
+        const double *blk = Me.block(e);
+        const int *d = ED.J.data() + ED.I[e];
+        const double *sg = ED.A.data() + ED.I[e];
+        for (int x = 0; x < m; ++x) for (int y = 0; y < m; ++y) rows[d[x]].push_back({d[y], sg[x] * sg[y] * blk[x * m + y]});
+    }
+    HostCSR M;
+    M.nrows = M.ncols = nd; M.I.assign(nd + 1, 0);
+    for (int i = 0; i < nd; ++i)
+    {
+        auto &r = rows[i];
+        std::stable_sort(r.begin(), r.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
+        for (size_t k = 0; k < r.size();)
+        {
+            double s = 0.0; size_t q = k;
+            while (q < r.size() && r[q].first == r[k].first) s += r[q++].second;
+            M.J.push_back(r[k].first); M.A.push_back(s);
+            k = q;
+        }
+        M.I[i + 1] = (int)M.J.size();
+    }
+    return M;
+}
+
+std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchy(int nx, int ny, int nz, double Lx, double Ly, double Lz,
+                                                                        const double *alpha, const double *beta, int jstart,
+                                                                        int nlevels, double svd_tol)
+{
+    StructuredHexMesh mesh(nx, ny, nz, Lx, Ly, Lz);
+    std::vector<std::shared_ptr<AgglomeratedTopology>> topo(nlevels);
+    {
+        Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level 0");
+        topo[0] = mesh.Topology();
+    }
+    int dx = nx, dy = ny, dz = nz;
+    for (int l = 0; l + 1 < nlevels; ++l)
+    {
+        Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level " + std::to_string(l + 1));
+        topo[l + 1] = topo[l]->CoarsenLocalPartitioning(RefinedHexPartition(dx, dy, dz));
+        dx /= 2; dy /= 2; dz /= 2;
+    }
+    std::vector<std::shared_ptr<DeRhamSequence>> seq(nlevels);
+    {
+        Timer t = TimeManager::AddTimer("DeRhamSequence Construction -- Level 0");
+        seq[0] = std::make_shared<DeRhamSequence>(4);
+        seq[0]->data = std::make_shared<SequenceData>();
+        std::vector<HostCSR> D;
+        BuildFineHexSequence(mesh, topo[0], alpha, beta, jstart, *seq[0]->data, D);
+        for (int j = 0; j < 3; ++j) seq[0]->SetD(j, D[j]);
+        for (int j = 0; j < 4; ++j) seq[0]->SetDofHandlerRaw(j, seq[0]->data->dof[j].get());
+    }
+    if (svd_tol < 0.0)
+    {
+        // topology-only mode (host integer tables; used by the CPU tests): coarser levels carry
+        // their topology but no sequence
+        for (int l = 1; l < nlevels; ++l)
+        {
+            seq[l] = std::make_shared<DeRhamSequence>(4);
+            seq[l]->data = std::make_shared<SequenceData>();
+            seq[l]->data->topo = topo[l];
+        }
+        return seq;
+    }
+    for (int l = 0; l + 1 < nlevels; ++l)
+    {
+        Timer t = TimeManager::AddTimer("DeRhamSequence Construction -- Level " + std::to_string(l + 1));
+        seq[l]->SetSVDTol(svd_tol);
+        seq[l + 1] = seq[l]->Coarsen();
+    }
+    return seq;
+}
+} // namespace parelag

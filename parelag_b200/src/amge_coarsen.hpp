@@ -1,0 +1,14 @@
+// amge_coarsen.hpp -- entry points of the coarsening path (see amge_coarsen.cpp)
+#pragma once
+#include "amge_hex.hpp"
+
+namespace parelag
+{
+/// Steps 3-4 of the drivers (examples/MultigridTest2Form.cpp:248-375) on a structured hex
+/// mesh: fine topology, nlevels-1 derefinement agglomerations
+/// (MFEMRefinedMeshPartitioner + CoarsenLocalPartitioning), fine DeRhamSequence with the
+/// order-0 upscaling targets, then Coarsen() level by level.  Timers use the reference's names.
+std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchy(int nx, int ny, int nz, double Lx, double Ly, double Lz,
+                                                                        const double *alpha, const double *beta, int jstart,
+                                                                        int nlevels, double svd_tol);
+} // namespace parelag

@@ -1,0 +1,219 @@
+// amge_hex.hpp -- synthetic input producer: the fine-level de Rham sequence
+// (DeRhamSequence3D_FE, src/amge/DeRhamSequenceFE.cpp:633-722, at lowest order) on an
+// axis-aligned structured hexahedral mesh, with MFEM's dof conventions (H1: vertex
+// values, Nedelec: edge circulations, Raviart-Thomas: face fluxes, L2: cell values),
+// exact element / facet / ridge mass matrices, PV-trace geometry, and the order-0
+// upscaling targets of SetUpscalingTargets (DeRhamSequenceFE.cpp:927-982).
+// Numbering (x fastest): element (i,j,k) -> i + nx*(j + ny*k); facets: x-normal faces,
+// then y-, then z-normal; ridges: x-, y-, z-edges; peaks: vertices.  Every facet / ridge
+// is oriented along its positive axis.  Boundary attributes as mfem::Mesh::Make3D
+// (z=0:1, y=0:2, x=L:3, y=L:4, x=0:5, z=L:6).  Same conventions as oracle/amge.py.
+#pragma once
+#include "amge_dofs.hpp"
+
+namespace parelag
+{
+struct StructuredHexMesh
+{
+    int nx, ny, nz;
+    double hx, hy, hz;
+    StructuredHexMesh(int nx_, int ny_, int nz_, double Lx = 1.0, double Ly = 1.0, double Lz = 1.0)
+        : nx(nx_), ny(ny_), nz(nz_), hx(Lx / nx_), hy(Ly / ny_), hz(Lz / nz_) {}
+    int64_t nel() const { return (int64_t)nx * ny * nz; }
+    int nfx() const { return (nx + 1) * ny * nz; }
+    int nfy() const { return nx * (ny + 1) * nz; }
+    int nfz() const { return nx * ny * (nz + 1); }
+    int nf() const { return nfx() + nfy() + nfz(); }
+    int nex() const { return nx * (ny + 1) * (nz + 1); }
+    int ney() const { return (nx + 1) * ny * (nz + 1); }
+    int nez() const { return (nx + 1) * (ny + 1) * nz; }
+    int ne() const { return nex() + ney() + nez(); }
+    int nv() const { return (nx + 1) * (ny + 1) * (nz + 1); }
+    int el(int i, int j, int k) const { return i + nx * (j + ny * k); }
+    int fx(int i, int j, int k) const { return i + (nx + 1) * (j + ny * k); }
+    int fy(int i, int j, int k) const { return nfx() + i + nx * (j + (ny + 1) * k); }
+    int fz(int i, int j, int k) const { return nfx() + nfy() + i + nx * (j + ny * k); }
+    int ex(int i, int j, int k) const { return i + nx * (j + (ny + 1) * k); }
+    int ey(int i, int j, int k) const { return nex() + i + (nx + 1) * (j + ny * k); }
+    int ez(int i, int j, int k) const { return nex() + ney() + i + (nx + 1) * (j + (ny + 1) * k); }
+    int vx(int i, int j, int k) const { return i + (nx + 1) * (j + (ny + 1) * k); }
+
+    static void push_row(HostCSR &M, std::vector<std::pair<int, double>> &ent)
+    {
+        std::sort(ent.begin(), ent.end());
+        for (auto &p : ent) { M.J.push_back(p.first); M.A.push_back(p.second); }
+        M.I.push_back((int)M.J.size());
+        ent.clear();
+    }
+    std::shared_ptr<AgglomeratedTopology> Topology() const
+    {
+        std::vector<std::pair<int, double>> r;
+        HostCSR B0, B1, B2, fb;
+        B0.nrows = (int)nel(); B0.ncols = nf(); B0.I = {0};
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i)
+        {
+            r = {{fx(i, j, k), -1.0}, {fx(i + 1, j, k), 1.0}, {fy(i, j, k), -1.0}, {fy(i, j + 1, k), 1.0}, {fz(i, j, k), -1.0}, {fz(i, j, k + 1), 1.0}};
+            push_row(B0, r);
+        }
+        B1.nrows = nf(); B1.ncols = ne(); B1.I = {0};
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i <= nx; ++i)   // x-faces: dEz/dy - dEy/dz
+        { r = {{ez(i, j + 1, k), 1.0}, {ez(i, j, k), -1.0}, {ey(i, j, k + 1), -1.0}, {ey(i, j, k), 1.0}}; push_row(B1, r); }
+        for (int k = 0; k < nz; ++k) for (int j = 0; j <= ny; ++j) for (int i = 0; i < nx; ++i)   // y-faces: dEx/dz - dEz/dx
+        { r = {{ex(i, j, k + 1), 1.0}, {ex(i, j, k), -1.0}, {ez(i + 1, j, k), -1.0}, {ez(i, j, k), 1.0}}; push_row(B1, r); }
+        for (int k = 0; k <= nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i)   // z-faces: dEy/dx - dEx/dy
+        { r = {{ey(i + 1, j, k), 1.0}, {ey(i, j, k), -1.0}, {ex(i, j + 1, k), -1.0}, {ex(i, j, k), 1.0}}; push_row(B1, r); }
+        B2.nrows = ne(); B2.ncols = nv(); B2.I = {0};
+        for (int k = 0; k <= nz; ++k) for (int j = 0; j <= ny; ++j) for (int i = 0; i < nx; ++i)
+        { r = {{vx(i, j, k), -1.0}, {vx(i + 1, j, k), 1.0}}; push_row(B2, r); }
+        for (int k = 0; k <= nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i <= nx; ++i)
+        { r = {{vx(i, j, k), -1.0}, {vx(i, j + 1, k), 1.0}}; push_row(B2, r); }
+        for (int k = 0; k < nz; ++k) for (int j = 0; j <= ny; ++j) for (int i = 0; i <= nx; ++i)
+        { r = {{vx(i, j, k), -1.0}, {vx(i, j, k + 1), 1.0}}; push_row(B2, r); }
+        fb.nrows = nf(); fb.ncols = 6;
+        std::vector<int> attr(nf(), -1);
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) { attr[fx(0, j, k)] = 4; attr[fx(nx, j, k)] = 2; }
+        for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) { attr[fy(i, 0, k)] = 1; attr[fy(i, ny, k)] = 3; }
+        for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) { attr[fz(i, j, 0)] = 0; attr[fz(i, j, nz)] = 5; }
+        fb.I = {0};
+        for (int f = 0; f < nf(); ++f)
+        {
+            if (attr[f] >= 0) { fb.J.push_back(attr[f]); fb.A.push_back(1.0); }
+            fb.I.push_back((int)fb.J.size());
+        }
+        std::vector<HostCSR> B;
+        B.push_back(std::move(B0)); B.push_back(std::move(B1)); B.push_back(std::move(B2));
+        return std::make_shared<AgglomeratedTopology>(std::move(B), std::move(fb), 3);
+    }
+};
+
+namespace hexfe
+{
+inline void kron2(const double *A, int na, const double *B, int nb, double *C)   // C = A (x) B, row-major
+{
+    const int n = na * nb;
+    for (int ia = 0; ia < na; ++ia) for (int ib = 0; ib < nb; ++ib)
+        for (int ja = 0; ja < na; ++ja) for (int jb = 0; jb < nb; ++jb)
+            C[(ia * nb + ib) * n + (ja * nb + jb)] = A[ia * na + ja] * B[ib * nb + jb];
+}
+/// place the s-scaled m x m block B at (o,o) of the n x n row-major matrix C
+inline void place(double *C, int n, int o, const double *B, int m, double s)
+{
+    for (int a = 0; a < m; ++a) for (int b = 0; b < m; ++b) C[(o + a) * n + (o + b)] = s * B[a * m + b];
+}
+inline void fill_pool(BlockPool &P, int count, const double *blk, int m, const double *w = nullptr)
+{
+    for (int e = 0; e < count; ++e)
+    {
+        double *d = P.add(m);
+        const double s = w ? w[e] : 1.0;
+        for (int q = 0; q < m * m; ++q) d[q] = s * blk[q];
+    }
+}
+} // namespace hexfe
+
+/// fills SequenceData + D_ for the fine level; alpha / beta: optional per-element weights
+/// of the L2 and H(div) element mass matrices (ReplaceMassIntegrator in the drivers)
+inline void BuildFineHexSequence(const StructuredHexMesh &mesh, const std::shared_ptr<AgglomeratedTopology> &topo,
+                                 const double *alpha, const double *beta, int jstart, SequenceData &S, std::vector<HostCSR> &D)
+{
+    using namespace hexfe;
+    const double hx = mesh.hx, hy = mesh.hy, hz = mesh.hz, vol = hx * hy * hz;
+    const int nel = (int)mesh.nel();
+    S.topo = topo; S.nforms = 4; S.jstart = jstart; S.is_fe = true;
+    S.dof.resize(4);
+    for (int j = 0; j < 4; ++j)
+    {
+        auto dh = std::make_shared<DofHandlerX>(3 - j, topo);
+        dh->ndofs = topo->GetNumberLocalEntities(3 - j);
+        for (int c = 0; c <= 3 - j; ++c)
+            dh->entity_dof[c] = (c == 3 - j) ? hostcsr::Identity(topo->GetNumberLocalEntities(c)) : topo->GetConnectivity(c, 3 - j);
+        dh->ComputeBoundaryMask();
+        S.dof[j] = dh;
+    }
+    D.resize(3);
+    D[0] = topo->GetB(2);
+    D[1] = topo->GetB(1);
+    D[2] = topo->GetB(0);
+    for (auto &v : D[2].A) v *= (1.0 / vol);
+    const double M1[4] = {1.0 / 3.0, 1.0 / 6.0, 1.0 / 6.0, 1.0 / 3.0};
+    double K[16];
+    kron2(M1, 2, M1, 2, K);
+    // form 3
+    { double b = vol; fill_pool(S.M[{3, 0}], nel, &b, 1, alpha); }
+    // form 2: element (x-,x+,y-,y+,z-,z+), facet
+    {
+        double blk[36] = {0};
+        place(blk, 6, 0, M1, 2, hx / (hy * hz)); place(blk, 6, 2, M1, 2, hy / (hx * hz)); place(blk, 6, 4, M1, 2, hz / (hx * hy));
+        fill_pool(S.M[{2, 0}], nel, blk, 6, beta);
+        double ax = 1.0 / (hy * hz), ay = 1.0 / (hx * hz), az = 1.0 / (hx * hy);
+        fill_pool(S.M[{2, 1}], mesh.nfx(), &ax, 1); fill_pool(S.M[{2, 1}], mesh.nfy(), &ay, 1); fill_pool(S.M[{2, 1}], mesh.nfz(), &az, 1);
+    }
+    // form 1: element (4 x-edges, 4 y-edges, 4 z-edges), facet (2+2 edges), ridge
+    {
+        double blk[144] = {0};
+        place(blk, 12, 0, K, 4, hy * hz / hx); place(blk, 12, 4, K, 4, hx * hz / hy); place(blk, 12, 8, K, 4, hx * hy / hz);
+        fill_pool(S.M[{1, 0}], nel, blk, 12);
+        double f[16];
+        std::fill(f, f + 16, 0.0); place(f, 4, 0, M1, 2, hz / hy); place(f, 4, 2, M1, 2, hy / hz); fill_pool(S.M[{1, 1}], mesh.nfx(), f, 4);
+        std::fill(f, f + 16, 0.0); place(f, 4, 0, M1, 2, hz / hx); place(f, 4, 2, M1, 2, hx / hz); fill_pool(S.M[{1, 1}], mesh.nfy(), f, 4);
+        std::fill(f, f + 16, 0.0); place(f, 4, 0, M1, 2, hy / hx); place(f, 4, 2, M1, 2, hx / hy); fill_pool(S.M[{1, 1}], mesh.nfz(), f, 4);
+        double lx = 1.0 / hx, ly = 1.0 / hy, lz = 1.0 / hz;
+        fill_pool(S.M[{1, 2}], mesh.nex(), &lx, 1); fill_pool(S.M[{1, 2}], mesh.ney(), &ly, 1); fill_pool(S.M[{1, 2}], mesh.nez(), &lz, 1);
+    }
+    // form 0: element (8 vertices), facet (4), ridge (2), peak
+    {
+        double K3[64], tmp[64];
+        kron2(M1, 2, K, 4, K3);
+        for (int q = 0; q < 64; ++q) tmp[q] = vol * K3[q];
+        fill_pool(S.M[{0, 0}], nel, tmp, 8);
+        double f[16];
+        for (int q = 0; q < 16; ++q) f[q] = hy * hz * K[q]; fill_pool(S.M[{0, 1}], mesh.nfx(), f, 4);
+        for (int q = 0; q < 16; ++q) f[q] = hx * hz * K[q]; fill_pool(S.M[{0, 1}], mesh.nfy(), f, 4);
+        for (int q = 0; q < 16; ++q) f[q] = hx * hy * K[q]; fill_pool(S.M[{0, 1}], mesh.nfz(), f, 4);
+        double e[4];
+        for (int q = 0; q < 4; ++q) e[q] = hx * M1[q]; fill_pool(S.M[{0, 2}], mesh.nex(), e, 2);
+        for (int q = 0; q < 4; ++q) e[q] = hy * M1[q]; fill_pool(S.M[{0, 2}], mesh.ney(), e, 2);
+        for (int q = 0; q < 4; ++q) e[q] = hz * M1[q]; fill_pool(S.M[{0, 2}], mesh.nez(), e, 2);
+        double one = 1.0;
+        fill_pool(S.M[{0, 3}], mesh.nv(), &one, 1);
+    }
+    S.l2const.assign(nel, 1.0);
+    S.facet_area.assign(mesh.nf(), 0.0);
+    std::fill(S.facet_area.begin(), S.facet_area.begin() + mesh.nfx(), hy * hz);
+    std::fill(S.facet_area.begin() + mesh.nfx(), S.facet_area.begin() + mesh.nfx() + mesh.nfy(), hx * hz);
+    std::fill(S.facet_area.begin() + mesh.nfx() + mesh.nfy(), S.facet_area.end(), hx * hy);
+    S.ridge_length.assign(mesh.ne(), 0.0);
+    std::fill(S.ridge_length.begin(), S.ridge_length.begin() + mesh.nex(), hx);
+    std::fill(S.ridge_length.begin() + mesh.nex(), S.ridge_length.begin() + mesh.nex() + mesh.ney(), hy);
+    std::fill(S.ridge_length.begin() + mesh.nex() + mesh.ney(), S.ridge_length.end(), hz);
+    // targets (upscaling order 0): L2 {1}; H(div)/H(curl) {e_x,e_y,e_z}; H1 {1,z,y,x}
+    S.targets.resize(4); S.ntargets = {4, 3, 3, 1};
+    S.targets[3].assign(nel, 1.0);
+    {
+        const int n = mesh.nf();
+        S.targets[2].assign((size_t)3 * n, 0.0);
+        for (int f = 0; f < mesh.nfx(); ++f) S.targets[2][f] = S.facet_area[f];
+        for (int f = mesh.nfx(); f < mesh.nfx() + mesh.nfy(); ++f) S.targets[2][(size_t)n + f] = S.facet_area[f];
+        for (int f = mesh.nfx() + mesh.nfy(); f < n; ++f) S.targets[2][(size_t)2 * n + f] = S.facet_area[f];
+    }
+    {
+        const int n = mesh.ne();
+        S.targets[1].assign((size_t)3 * n, 0.0);
+        for (int e = 0; e < mesh.nex(); ++e) S.targets[1][e] = S.ridge_length[e];
+        for (int e = mesh.nex(); e < mesh.nex() + mesh.ney(); ++e) S.targets[1][(size_t)n + e] = S.ridge_length[e];
+        for (int e = mesh.nex() + mesh.ney(); e < n; ++e) S.targets[1][(size_t)2 * n + e] = S.ridge_length[e];
+    }
+    {
+        const int n = mesh.nv();
+        S.targets[0].assign((size_t)4 * n, 0.0);
+        for (int k = 0; k <= mesh.nz; ++k) for (int j = 0; j <= mesh.ny; ++j) for (int i = 0; i <= mesh.nx; ++i)
+        {
+            const int v = mesh.vx(i, j, k);
+            S.targets[0][v] = 1.0;
+            S.targets[0][(size_t)n + v] = k * hz;
+            S.targets[0][(size_t)2 * n + v] = j * hy;
+            S.targets[0][(size_t)3 * n + v] = i * hx;
+        }
+    }
+}
+} // namespace parelag

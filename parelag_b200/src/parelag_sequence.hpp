@@ -16,6 +16,7 @@
 
 namespace parelag
 {
+struct SequenceData;   // amge_dofs.hpp: topology, dof handlers, mass matrices, targets of one level
 struct HostCSR
 {
     int nrows = 0, ncols = 0;
@@ -65,13 +66,13 @@ private:
 class DeRhamSequence : public std::enable_shared_from_this<DeRhamSequence>
 {
 public:
-    explicit DeRhamSequence(int nforms) : nForms_(nforms), Dof_(nforms), P_(nforms), D_(nforms) {}
+    explicit DeRhamSequence(int nforms) : nForms_(nforms), Dof_(nforms), P_(nforms), D_(nforms), RawDof_(nforms, nullptr) {}
     virtual ~DeRhamSequence() = default;
 
     int GetNumberOfForms() const noexcept { return nForms_; }
-    int GetNumberOfDofs(int jform) const { return Dof_.at(jform) ? Dof_[jform]->GetNDofs() : 0; }
+    int GetNumberOfDofs(int jform) const { auto d = GetDofHandler(jform); return d ? d->GetNDofs() : 0; }
     int GetNumberOfTrueDofs(int jform) const { return GetNumberOfDofs(jform); }
-    DofHandler *GetDofHandler(int jform) const { return Dof_.at(jform).get(); }
+    DofHandler *GetDofHandler(int jform) const { return RawDof_.at(jform) ? RawDof_[jform] : Dof_.at(jform).get(); }
     void SetDofHandler(int jform, std::unique_ptr<DofHandler> d) { Dof_.at(jform) = std::move(d); }
 
     /// P_[j] maps the COARSER level's form j to this level (stored on the finer
@@ -128,10 +129,22 @@ public:
         return make_unique<mfem::HypreParMatrix>(D_[jform]->View());
     }
 
+    // ---- coarsening (src/amge/DeRhamSequence.cpp:572-692); implemented in amge_coarsen.cpp:
+    // integer tables on the host, the per-agglomerate dense work as batched CUDA kernels
+    void SetSVDTol(double tol);
+    void SetjformStart(int jform);
+    std::shared_ptr<DeRhamSequence> Coarsen();
+    /// ComputeMassOperator(jform): rDof_dof^T M_e rDof_dof (DofHandler.cpp:270-281), host CSR
+    HostCSR ComputeMassOperator(int jform) const;
+    std::shared_ptr<SequenceData> data;       // null for sequences with externally supplied operators
+    const DofHandler *GetDofHandlerRaw(int jform) const { return RawDof_.at(jform); }
+    void SetDofHandlerRaw(int jform, DofHandler *d) { RawDof_.at(jform) = d; }
+
 protected:
     int nForms_;
     std::vector<std::unique_ptr<DofHandler>> Dof_;
     std::vector<std::shared_ptr<HostCSR>> P_, D_;
     std::weak_ptr<DeRhamSequence> CoarserSequence_, FinerSequence_;
+    std::vector<DofHandler *> RawDof_;              // handlers owned by `data` (Coarsen path)
 };
 } // namespace parelag

@@ -1,6 +1,7 @@
 // pe_api.cpp -- C facade over the C++ solver API (see include/parelag_b200_api.h).
 #include "parelag_b200_api.h"
 #include "parelag_solvers.hpp"
+#include "amge_coarsen.hpp"
 #include <cstring>
 
 void pe_set_error(const std::string &msg);   // csrc/pe_core.cu
@@ -71,6 +72,87 @@ extern "C" int pe_api_sequence_set_bdr_mask(pe_sequence *s, int level, int form,
     API_CATCH
 }
 extern "C" int pe_api_sequence_free(pe_sequence *s) { delete s; return 0; }
+
+extern "C" int pe_api_hexsequence_create(int nx, int ny, int nz, double Lx, double Ly, double Lz, const double *alpha, const double *beta,
+                                         int jstart, int nlevels, double svd_tol, pe_sequence **out)
+{
+    API_TRY
+    auto s = new pe_sequence();
+    s->levels = BuildHexSequenceHierarchy(nx, ny, nz, Lx, Ly, Lz, alpha, beta, jstart, nlevels, svd_tol);
+    *out = s;
+    API_CATCH
+}
+static HostCSR pool_as_csr(const BlockPool &P)
+{
+    HostCSR M;
+    auto rd = P.rdof_offsets();
+    M.nrows = M.ncols = rd.back();
+    M.I.assign(1, 0);
+    for (int e = 0; e < P.n(); ++e)
+        for (int x = 0; x < P.size[e]; ++x)
+        {
+            for (int y = 0; y < P.size[e]; ++y) { M.J.push_back(rd[e] + y); M.A.push_back(P.block(e)[x * P.size[e] + y]); }
+            M.I.push_back((int)M.J.size());
+        }
+    return M;
+}
+extern "C" int pe_api_sequence_get_csr(pe_sequence *s, int level, const char *what, int a, int b, int32_t *nrows, int32_t *ncols,
+                                       int64_t *nnz, int32_t *I, int32_t *J, double *A)
+{
+    API_TRY
+    auto &seq = *s->levels.at(level);
+    const std::string w(what);
+    HostCSR tmp;
+    const HostCSR *M = nullptr;
+    if (w == "P") M = seq.GetP(a);
+    else if (w == "D") M = seq.GetDerivativeOperator(a);
+    else
+    {
+        PARELAG_TEST_FOR_EXCEPTION(!seq.data, std::runtime_error, "pe_api_sequence_get_csr: sequence has no coarsening data");
+        if (w == "M") { tmp = seq.ComputeMassOperator(a); M = &tmp; }
+        else if (w == "Me") { tmp = pool_as_csr(seq.data->M.at({a, b})); M = &tmp; }
+        else if (w == "B") M = &seq.data->topo->GetB(a);
+        else if (w == "AE") M = &seq.data->topo->AEntityEntity(a);
+        else if (w == "ED") M = &seq.data->dof.at(a)->entity_dof.at(b);
+        else if (w == "FB") M = &seq.data->topo->FacetBdrAttribute();
+    }
+    PARELAG_TEST_FOR_EXCEPTION(!M, std::runtime_error, "pe_api_sequence_get_csr: \"" << w << "\" is not available on level " << level);
+    if (nrows) *nrows = M->nrows;
+    if (ncols) *ncols = M->ncols;
+    if (nnz) *nnz = (int64_t)M->J.size();
+    if (I) std::copy(M->I.begin(), M->I.end(), I);
+    if (J) std::copy(M->J.begin(), M->J.end(), J);
+    if (A) std::copy(M->A.begin(), M->A.end(), A);
+    API_CATCH
+}
+extern "C" int pe_api_sequence_get_targets(pe_sequence *s, int level, int form, int32_t *ndofs, int32_t *ntargets, double *out)
+{
+    API_TRY
+    auto &seq = *s->levels.at(level);
+    PARELAG_ASSERT(seq.data);
+    if (ndofs) *ndofs = seq.data->dof.at(form)->ndofs;
+    if (ntargets) *ntargets = seq.data->ntargets.at(form);
+    if (out) std::copy(seq.data->targets.at(form).begin(), seq.data->targets.at(form).end(), out);
+    API_CATCH
+}
+extern "C" int pe_api_sequence_get_bdr_mask(pe_sequence *s, int level, int form, int32_t *ndofs, uint32_t *mask)
+{
+    API_TRY
+    auto d = s->levels.at(level)->GetDofHandler(form);
+    PARELAG_ASSERT(d);
+    if (ndofs) *ndofs = d->GetNDofs();
+    if (mask) std::copy(d->GetBoundaryMask().begin(), d->GetBoundaryMask().end(), mask);
+    API_CATCH
+}
+extern "C" int pe_api_sequence_get_stat(pe_sequence *s, int level, const char *name, int64_t *value)
+{
+    API_TRY
+    auto &seq = *s->levels.at(level);
+    PARELAG_ASSERT(seq.data);
+    auto it = seq.data->stats.find(name);
+    *value = it == seq.data->stats.end() ? -1 : it->second;
+    API_CATCH
+}
 
 extern "C" int pe_api_solver_build(const char *xml, const char *name, const pe_parcsr_host *A, pe_sequence *seq,
                                    int start_level, int form, const int32_t *ess_attr, int nattr, pe_solver **out)

@@ -1,0 +1,56 @@
+"""Host integer tables of the product (C++: amge_topology.hpp / amge_dofs.hpp /
+amge_hex.hpp) against the oracle -- bit-exact, no GPU needed."""
+import numpy as np
+import pytest
+
+from parelag_b200 import api
+from oracle import amge
+
+
+def same(A, B):
+    A.sort_indices(); B = B.tocsr(); B.sort_indices()
+    return (A.shape == B.shape and np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+            and np.array_equal(A.data, B.data))
+
+
+@pytest.mark.parametrize("dims,nlev", [((4, 4, 4), 3), ((4, 6, 2), 2), ((8, 4, 4), 3)])
+def test_topology_hierarchy_bit_exact(dims, nlev):
+    S = api.Sequence.hex(dims, nlev, svd_tol=-1.0)
+    mesh = amge.HexMesh(*dims)
+    topo = mesh.topology()
+    d = dims
+    for l in range(nlev):
+        for c in range(3):
+            assert same(S.get_csr(l, "B", c), topo.B[c]), (l, c)
+        assert same(S.get_csr(l, "FB"), topo.facet_bdr)
+        if l + 1 < nlev:
+            ctopo = topo.coarsen(amge.refined_partition(d))
+            for c in range(4):
+                assert same(S.get_csr(l, "AE", c), topo.AE_entity[c]), (l, c)
+            topo = ctopo
+            d = (d[0] // 2, d[1] // 2, d[2] // 2)
+    S.free()
+
+
+def test_fine_sequence_matrices_bit_exact():
+    dims, L = (4, 2, 6), (1.0, 2.0, 0.75)
+    rng = np.random.default_rng(3)
+    nel = 4 * 2 * 6
+    alpha, beta = rng.uniform(0.5, 2, nel), rng.uniform(0.1, 10, nel)
+    S = api.Sequence.hex(dims, 1, L=L, alpha=alpha, beta=beta, svd_tol=-1.0)
+    mesh = amge.HexMesh(*dims, L=L)
+    seq = amge.fine_sequence(mesh, alpha=alpha, beta=beta)
+    for j in range(3):
+        assert same(S.get_csr(0, "D", j), seq.D[j])
+    for j in range(4):
+        for c in range(4 - j):
+            Me = S.get_csr(0, "Me", j, c)
+            assert abs(Me - seq.M[(j, c)]).max() <= 1e-15 * abs(seq.M[(j, c)]).max(), (j, c)
+            assert same(S.get_csr(0, "ED", j, c), seq.dof[j].entity_dof[c])
+        M = S.get_csr(0, "M", j)
+        Mo = seq.mass_operator(j)
+        assert abs(M - Mo).max() <= 1e-14 * abs(Mo).max()
+        assert np.array_equal(S.get_targets(0, j), seq.targets[j])
+        from oracle import drivers
+        assert np.array_equal(S.get_bdr_mask(0, j), drivers.bdr_mask(seq.dof[j]))
+    S.free()
