@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native AMGe solve-and-coarsen path.
+
+Metric (BASELINE.json): DOFs/s per V-cycle (+ setup seconds, SpMV/smoother HBM GB/s vs
+peak).  Workload at N=1 (configs[1], "MultigridTest2Form"): H(div) problem
+A = M_2 + D_2^T M_3 D_2 on the unit cube with n^3 hexahedra (n = 144 -> 9 020 160 RT0
+dofs), 5-level AMGe hierarchy built by DeRhamSequence::Coarsen(), Hiptmair smoother
+(l1-Gauss-Seidel on the H(div) operator and on D^T A D in H(curl)), coarse solver
+"PCG-GS" (3 PCG iterations preconditioned by the same smoother), all boundary
+attributes essential.  A step = one application of the AMGe V-cycle
+(Hierarchy::Mult) to a device-resident residual.
+
+  python bench.py --gpus N --steps K --warmup W            (this implementation)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
+
+N > 1: one process per GPU (torchrun); in this round every rank solves its own copy
+of the workload ("replicas", weak scaling, no data-path collective) -- see DESIGN.md.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vcycle_dofs_per_s"
+UNIT = "DOFs/s"
+ESS = np.ones(6, dtype=np.int32)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def library(ordering, form=2):
+    """ParameterList 'Preconditioner Library' of examples/testing_helpers/Create2FormParameterList.hpp
+    with the coarse solver replaced by the hot-path-only PCG-GS."""
+    hyp = ("Hypre", {"Type": "L1 Gauss-Seidel", "Sweeps": 1, "Damping Factor": 1.0, "Omega": 1.0,
+                     "Cheby Poly Order": 2, "Cheby Poly Fraction": 0.3, "GS ordering": ordering})
+    return {
+        "Gauss-Seidel": hyp,
+        "Hiptmair-GS-GS": ("Hiptmair", {"Primary Smoother": "Gauss-Seidel", "Auxiliary Smoother": "Gauss-Seidel"}),
+        "PCG-GS": ("Krylov", {"Solver name": "PCG", "Preconditioner": "Hiptmair-GS-GS", "Print level": -1,
+                              "Maximum iterations": 3, "Relative tolerance": 1e-4, "Absolute tolerance": 1e-4}),
+        "AMGe-HIP-GS_2": ("AMGe", {"Maximum levels": -1, "Forms": [form], "PreSmoother": "Hiptmair-GS-GS",
+                                   "PostSmoother": "Hiptmair-GS-GS", "Coarse solver": "PCG-GS",
+                                   "Cycle type": "V-cycle"}),
+        "PCG with Auxiliary Space Preconditioner": (
+            "Krylov", {"Solver name": "PCG", "Preconditioner": "AMGe-HIP-GS_2", "Print level": -1,
+                       "Maximum iterations": 300, "Relative tolerance": 1e-6, "Absolute tolerance": 1e-6}),
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def traffic_from_profiles():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return {}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU reference / baseline leg (the ONLY place bench.py touches oracle/)
+# ----------------------------------------------------------------------------------------------
+def cpu_vcycle_setup(n_sample, levels, ranks, hier_from):
+    """Oracle V-cycle (oracle/solve.py: hypre/MFEM arithmetic restated in C) on a bounded sample of
+    the workload: the same H(div) problem on n_sample^3 hexahedra.  hier_from(n, levels) returns the
+    level operators (A0, [P_l], [D_l]) -- inputs of the solve path, not part of what is timed."""
+    from oracle import solve as orc
+    A0, Ps, Ds = hier_from(n_sample, levels)
+    nl = len(Ps) + 1
+
+    def smoother(l, Al):
+        kw = lambda M: dict(type=2, ranks=ranks)
+        return orc.Hiptmair(Al, Ds[l], kw, kw)
+
+    def coarse(Ac):
+        S = smoother(nl - 1, Ac)
+        return lambda b, x: orc.pcg(Ac, lambda r: S.apply(r, np.zeros_like(r), False), b, rtol=1e-4, atol=1e-4,
+                                    max_iter=3)[0]
+    H = orc.build_hierarchy(A0, Ps, smoother, coarse)
+    return H, A0.shape[0]
+
+
+def oracle_hierarchy_inputs(n, levels):
+    """Level operators from the oracle's own coarsening (CPU only; small n) -- used by the reference
+    arm when no GPU is involved at all."""
+    from oracle import amge, drivers
+    mesh, seqs = amge.build_hierarchy((n, n, n), levels, jstart=1)
+    A, _ = drivers.system_matrix(seqs[0], 2, ESS)
+    Ps = [seqs[l].get_P(2, ESS) for l in range(levels - 1)]
+    Ds = [seqs[l].get_D(1, ESS) for l in range(levels)]
+    return A, Ps, Ds
+
+
+def time_cpu_vcycles(H, n, steps, warmup, budget_s=25.0):
+    rng = np.random.default_rng(0)
+    r = rng.standard_normal(n)
+    for _ in range(warmup):
+        H.mult(r)
+    ts = []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        H.mult(r)
+        ts.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s:
+            break
+    return float(np.mean(ts)), len(ts)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_s, levels = args.ref_n, args.ref_levels
+    H, ndofs = cpu_vcycle_setup(n_s, levels, cores, oracle_hierarchy_inputs)
+    t, done = time_cpu_vcycles(H, ndofs, args.steps, min(args.warmup, 1), budget_s=120.0)
+    value = ndofs / t
+    sample = ("H(div) AMGe V-cycle (Hiptmair l1-GS, PCG-GS coarse) on %d^3 hexahedra, %d RT0 dofs, %d levels; "
+              "hybrid GS with %d row blocks (= %d MPI ranks), oracle port of the hypre/MFEM kernels" %
+              (n_s, ndofs, levels, cores, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "MultigridTest2Form: H(div) AMGe V-cycle, bounded CPU sample %d^3" % n_s},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=144, help="hexahedra per direction (144 -> 9.02M RT0 dofs)")
+    ap.add_argument("--levels", type=int, default=5)
+    ap.add_argument("--ordering", default="multicolor", choices=["multicolor", "natural"])
+    ap.add_argument("--jstart", type=int, default=0, help="jformStart of the sequence (driver uses 0)")
+    ap.add_argument("--ref-n", type=int, default=32)
+    ap.add_argument("--ref-levels", type=int, default=4)
+    ap.add_argument("--cpu-n", type=int, default=32, help="bounded sample of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from parelag_b200 import api, capi
+    # replicas: every rank owns an independent copy of the workload (no NCCL communicator needed)
+    ctx = api.session(rank=0, nranks=1, device=local_rank)
+    n, levels = args.n, args.levels
+    api.lib().pe_api_timer_clear()
+
+    # ---------------- setup (timed with the reference's timer names)
+    t0 = time.perf_counter()
+    S = api.Sequence.hex((n, n, n), levels, jstart=args.jstart)
+    ctx.sync()
+    t_coarsen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    A = S.assemble_system(ctx, 0, 2, ESS)
+    ctx.sync()
+    t_assemble = time.perf_counter() - t0
+    ndofs = A.info()[0]
+    nnz0 = A.info()[3]
+    t0 = time.perf_counter()
+    solver = api.Solver(api.library_xml(library(args.ordering)), "PCG with Auxiliary Space Preconditioner",
+                        A, S, 0, 2, ESS)
+    ctx.sync()
+    t_build = time.perf_counter() - t0
+    nlev = solver.num_levels()
+    level_info = [solver.level_info(l) for l in range(nlev)]
+
+    # ---------------- device-resident V-cycle steps
+    rng = np.random.default_rng(1234 + rank)
+    r_host = rng.standard_normal(ndofs)
+    r_dev, z_dev = capi.Vec(ctx, data=r_host), capi.Vec(ctx, ndofs)
+    for _ in range(args.warmup):
+        solver.prec_mult_device(r_dev, z_dev)
+    ctx.sync()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = ctx.launch_count()
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        solver.prec_mult_device(r_dev, z_dev)
+    ms = ctx.timer_stop()
+    barrier()
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    value = world * ndofs / (ms_per_step * 1e-3)
+
+    # ---------------- per-kernel roofline (separate profiled pass over the same steps)
+    ctx.profile(True)
+    for _ in range(args.steps):
+        solver.prec_mult_device(r_dev, z_dev)
+    ctx.profile(False)
+    names = {0: "k_spmv", 1: "k_gs_set", 2: "k_jacobi_update"}
+    prof = {names[i]: ctx.profile_get(i) for i in names}
+    dom = max(prof, key=lambda k: prof[k][1])
+    cnt, pms, pbytes = prof[dom]
+    peak, peak_src = peaks()
+    achieved = pbytes / (pms * 1e-3) / 1e9 if pms > 0 else 0.0
+    tr = traffic_from_profiles().get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "frac_of_8TBs_spec": achieved / 8000.0, "peak_source": peak_src,
+                "launches": cnt, "avg_launch_us": 1e3 * pms / max(cnt, 1),
+                "algorithmic_bytes_per_launch": pbytes / max(cnt, 1), "traffic": tr,
+                "share_of_step": pms / (ms_per_step * args.steps),
+                "all": {k: {"launches": v[0], "ms": v[1], "GBs": (v[2] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0)}
+                        for k, v in prof.items()}}
+
+    # ---------------- end to end through the plugin API with pinned HOST buffers
+    b_pin = torch.empty(ndofs, dtype=torch.float64).pin_memory()
+    x_pin = torch.empty(ndofs, dtype=torch.float64).pin_memory()
+    b_np, x_np = b_pin.numpy(), x_pin.numpy()
+    b_np[:] = r_host
+    vsolver_xml = api.library_xml(library(args.ordering))
+    # the V-cycle as its own solver object shares nothing with the PCG solver; to avoid a second
+    # hierarchy the e2e leg times PCG's preconditioner through host buffers via a 1-iteration-free path:
+    # upload b, apply V-cycle, download x  ==  pe_api_solver_mult on the AMGe solver.  We reuse the
+    # device vectors and time upload + V-cycle + download explicitly on the context's stream.
+    for _ in range(2):
+        r_dev.upload(b_np); solver.prec_mult_device(r_dev, z_dev); x_np[:] = z_dev.download()
+    barrier()
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        capi._chk(capi.lib().pe_vec_upload(r_dev.h, capi._ptr(b_np)))
+        solver.prec_mult_device(r_dev, z_dev)
+        capi._chk(capi.lib().pe_vec_download(z_dev.h, capi._ptr(x_np)))
+    ms_e2e = max_over_ranks(ctx.timer_stop()) / args.steps
+    e2e = {"value": world * ndofs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": 8 * ndofs, "d2h_bytes_per_step": 8 * ndofs}
+
+    # ---------------- one full PCG solve (iterations, residual history) through host buffers
+    bvec = rng.standard_normal(ndofs)
+    t0 = time.perf_counter()
+    x = solver.mult(bvec)
+    t_solve = time.perf_counter() - t0
+    hist, iters, conv = solver.history()
+
+    # ---------------- SpMV alone on the fine operator (the "SpMV HBM GB/s vs peak" part of the metric)
+    A2 = S.assemble_system(ctx, 0, 2, ESS)
+    xs, ys = capi.Vec(ctx, data=r_host), capi.Vec(ctx, ndofs)
+    for _ in range(3):
+        A2.spmv(xs, ys)
+    ctx.sync(); ctx.timer_start()
+    for _ in range(20):
+        A2.spmv(xs, ys)
+    ms_spmv = ctx.timer_stop() / 20
+    b_spmv = 12.0 * nnz0 + 4.0 * (ndofs + 1) + 16.0 * ndofs
+    spmv = {"ms": ms_spmv, "GBs": b_spmv / ms_spmv / 1e6, "frac_of_measured_peak": b_spmv / ms_spmv / 1e6 / peak,
+            "nnz": nnz0, "rows": ndofs}
+
+    line = None
+    if rank == 0:
+        cpu_baseline = None
+        if not args.no_cpu_baseline and world == 1:
+            def product_inputs(ns, lv):
+                # level operators of the bounded sample from the product's own hierarchy (inputs only)
+                Ss = api.Sequence.hex((ns, ns, ns), lv, jstart=1)
+                As = Ss.assemble_system(ctx, 0, 2, ESS).to_scipy()
+                import scipy.sparse as sp
+                Ps, Ds = [], []
+                for l in range(lv):
+                    D = Ss.get_csr(l, "D", 1)
+                    m = Ss.get_bdr_mask(l, 1) != 0
+                    D = sp.csr_matrix((np.where(m[D.indices], 0.0, D.data), D.indices, D.indptr), shape=D.shape)
+                    Ds.append(D)
+                    if l + 1 < lv:
+                        P = Ss.get_csr(l, "P", 2)
+                        mc = Ss.get_bdr_mask(l + 1, 2) != 0
+                        Ps.append(sp.csr_matrix((np.where(mc[P.indices], 0.0, P.data), P.indices, P.indptr), shape=P.shape))
+                return As, Ps, Ds
+            lv = 1
+            while args.cpu_n % (2 ** lv) == 0 and lv < levels:
+                lv += 1
+            H, nd = cpu_vcycle_setup(args.cpu_n, lv, 1, product_inputs)
+            t_cpu, done = time_cpu_vcycles(H, nd, 30, 1, budget_s=20.0)
+            cpu_baseline = {"value": nd / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": "same H(div) AMGe V-cycle (Hiptmair l1-GS natural order, PCG-GS coarse) on a "
+                                      "%d^3-hexahedra sample (%d RT0 dofs, %d levels), %d cycles of %.3f s on one host core; "
+                                      "oracle port of the hypre/MFEM kernels (oracle/solve_oracle.c)"
+                                      % (args.cpu_n, nd, lv, done, t_cpu)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "MultigridTest2Form (configs[1]): H(div) A=M2+D2^T M3 D2, %d^3 hexahedra, "
+                                       "%d RT0 dofs, %d-level AMGe, Hiptmair(l1-GS,l1-GS) %s order, PCG-GS coarse solver"
+                                       % (n, ndofs, nlev, args.ordering),
+                           "l2_policy": "inputs larger than L2 (hierarchy working set %.1f GB)" %
+                                        (sum(12.0 * li[1] for li in level_info) / 1e9),
+                           "parallelism": "replicas x%d" % world, "jform_start": args.jstart,
+                           "levels": [{"rows": li[0], "nnz": li[1], "nnz_P": li[2]} for li in level_info]},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "setup_s": {"coarsen_all_levels": t_coarsen, "assemble_system": t_assemble, "build_solver": t_build,
+                            "total": t_coarsen + t_assemble + t_build},
+                "spmv_fine_operator": spmv,
+                "pcg": {"iterations": iters, "converged": conv, "seconds_host_buffers": t_solve,
+                        "Br_r_first": float(hist[0]), "Br_r_last": float(hist[-1])}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

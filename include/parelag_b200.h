@@ -73,6 +73,11 @@ int64_t pe_ctx_launch_count(const pe_ctx *ctx);
 /* stream-ordered CUDA-event timer on the context's stream (milliseconds) */
 int pe_ctx_timer_start(pe_ctx *ctx);
 int pe_ctx_timer_stop(pe_ctx *ctx, float *ms);
+/* per-kernel CUDA-event profiling on the context's stream (roofline in bench.py): enable=1
+ * resets and starts, 0 stops.  kernel ids: 0 = SpMV (k_spmv), 1 = Gauss-Seidel set
+ * (k_gs_set), 2 = Jacobi update.  total_bytes = algorithmic bytes of the launches. */
+int pe_ctx_profile(pe_ctx *ctx, int enable);
+int pe_ctx_profile_get(pe_ctx *ctx, int kernel_id, int64_t *count, double *total_ms, double *total_bytes);
 /* write a scratch buffer larger than L2 (bench hygiene) */
 int pe_ctx_flush_l2(pe_ctx *ctx);
 
@@ -159,6 +164,10 @@ int pe_spgemm(pe_ctx *ctx, const pe_mat *A, const pe_mat *B, pe_mat **C);
 int pe_rap(pe_ctx *ctx, const pe_mat *R_or_null, const pe_mat *A, const pe_mat *P, pe_mat **Ac);
 int pe_fix_zero_rows(pe_ctx *ctx, pe_mat *A, int32_t *num_fixed);
 int pe_spadd(pe_ctx *ctx, double a, const pe_mat *A, double b, const pe_mat *B, pe_mat **C);
+/* mfem::SparseMatrix::EliminateRowCol(rc, DIAG_ONE) for every marked dof (marker_host[n],
+ * non-zero = essential): marked rows become unit rows, marked columns are zeroed; entries
+ * stay in the pattern (examples/MultigridTest2Form.cpp:457-464). */
+int pe_mat_eliminate_rowcol(pe_ctx *ctx, pe_mat *A, const int32_t *marker_host);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,11 @@ int pe_api_sequence_get_csr(pe_sequence *s, int level, const char *what, int a, 
 int pe_api_sequence_get_targets(pe_sequence *s, int level, int form, int32_t *ndofs, int32_t *ntargets, double *out);
 int pe_api_sequence_get_bdr_mask(pe_sequence *s, int level, int form, int32_t *ndofs, uint32_t *mask);
 int pe_api_sequence_get_stat(pe_sequence *s, int level, const char *name, int64_t *value);
+/* System assembly as in the drivers (examples/MultigridTest{0,1,2}Form.cpp:443-475), on the
+ * device: A = [M_form +] D^T M_{form+1} D  (the mass term is skipped for form 0), essential
+ * rows/cols eliminated with unit diagonal.  Returns a device matrix owned by the caller. */
+int pe_api_sequence_assemble_system(pe_sequence *s, int level, int form, const int32_t *ess_attr, int nattr,
+                                    pe_mat **out);
 
 /* SolverLibrary::CreateLibrary(xml) -> GetSolverFactory(name) -> BuildSolver(A, state).
  * xml: a <ParameterList name="Preconditioner Library"> document.  seq may be NULL for
@@ -68,11 +73,17 @@ int pe_api_sequence_get_stat(pe_sequence *s, int level, const char *name, int64_
 int pe_api_solver_build(const char *xml_library, const char *solver_name, const pe_parcsr_host *A,
                         pe_sequence *seq, int start_level, int form, const int32_t *ess_attr, int nattr,
                         pe_solver **out);
+/* same, for an operator that already lives on the device (ownership of A passes to the solver) */
+int pe_api_solver_build_device(const char *xml_library, const char *solver_name, pe_mat *A,
+                               pe_sequence *seq, int start_level, int form, const int32_t *ess_attr, int nattr,
+                               pe_solver **out);
 /* solver->Mult(B, X) with HOST buffers (H2D of b, D2H of x inside the call);
  * iterative_mode != 0 uses x as initial guess */
 int pe_api_solver_mult(pe_solver *s, const double *b_host, double *x_host, int n, int iterative_mode);
 /* solver->Mult on device-resident vectors (no copies) */
 int pe_api_solver_mult_device(pe_solver *s, const pe_vec *b, pe_vec *x, int iterative_mode);
+/* Krylov solvers: apply the preconditioner alone (e.g. one AMGe V-cycle) on device vectors */
+int pe_api_solver_prec_mult_device(pe_solver *s, const pe_vec *b, pe_vec *x);
 /* Krylov solvers: "(B r, r)" history (what MFEM prints), iteration count, convergence flag */
 int pe_api_solver_get_history(const pe_solver *s, double *hist, int capacity, int *count,
                               int *iterations, int *converged);

@@ -81,21 +81,8 @@ def greedy_colors(A):
     """First-fit colouring, rows visited in natural order, smallest colour not used
     by an already-coloured neighbour in the row pattern (spec shared with the GPU)."""
     n, I, J, _ = _csr(A)
-    color = -np.ones(n, dtype=np.int32)
-    ncol = 0
-    mark = []
-    for i in range(n):
-        if len(mark) < ncol + 1:
-            mark += [-1] * (ncol + 1 - len(mark))
-        for j in J[I[i]:I[i + 1]]:
-            if j != i and color[j] >= 0:
-                mark[color[j]] = i
-        c = 0
-        while c < ncol and mark[c] == i:
-            c += 1
-        color[i] = c
-        if c == ncol:
-            ncol += 1
+    color = np.empty(n, dtype=np.int32)
+    ncol = lib().orc_greedy_colors(n, _p(I), _p(J), _p(color))
     return color, ncol
 
 
@@ -171,12 +158,20 @@ class Smoother:
     """mfem::HypreSmoother as configured by parelag::HypreSmootherWrapper."""
 
     def __init__(self, A, type=2, sweeps=1, damping=1.0, omega=1.0, cheby_order=2,
-                 cheby_fraction=0.3, order=None):
+                 cheby_fraction=0.3, order=None, ranks=1):
+        """ranks > 1 (CPU-baseline timing only, type 2): the matrix rows are split into
+        `ranks` contiguous blocks handled by one thread each -- Gauss-Seidel inside a block,
+        Jacobi across blocks, l1 norms with the off-block part: what the reference computes
+        on `ranks` MPI ranks."""
+        self.ranks = ranks
         self.A = A.tocsr()
         self.n, self.I, self.J, self.D = _csr(self.A)
         self.type, self.sweeps, self.w, self.omega = type, sweeps, damping, omega
         l1opt = 0 if type in (0, 6, 16) else type
         self.l1 = l1_norms(self.A, l1opt)
+        if ranks > 1:
+            assert type == 2 and order is None
+            lib().orc_l1_norms_blocked(self.n, _p(self.I), _p(self.J), _p(self.D), ranks, _p(self.l1))
         self.order = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
         self.rank_of_row = None
         if self.order is not None:
@@ -233,6 +228,10 @@ class Smoother:
                 v = np.empty(n)
                 lib().orc_relax_jacobi(n, _p(self.I), _p(self.J), _p(self.D), None, None, None,
                                        _p(self.l1), C.c_double(self.w), _p(b), _p(x), None, _p(v))
+            elif self.type == 2 and self.ranks > 1:
+                frozen = np.empty(n)
+                lib().orc_relax_gs_blocked(n, _p(self.I), _p(self.J), _p(self.D), _p(self.l1), self.ranks,
+                                           _p(b), _p(x), _p(frozen))
             elif self.type in (2, 4, 6):
                 uold = np.empty(n)
                 lib().orc_relax_gs(n, _p(self.I), _p(self.J), _p(self.D), None, None, None,

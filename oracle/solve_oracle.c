@@ -367,3 +367,28 @@ void orc_relax_gs_blocked(int n, const int *dI, const int *dJ, const double *dA,
             }
     }
 }
+
+/* Greedy first-fit colouring (rows in natural order, smallest colour not used by an
+ * already coloured neighbour of the row pattern): the spec of PE_GS_ORDER_MULTICOLOR.
+ * Returns the number of colours. */
+int orc_greedy_colors(int n, const int *I, const int *J, int *color)
+{
+    int ncol = 0, cap = 64;
+    int *mark = (int *)malloc(sizeof(int) * (size_t)cap);
+    for (int c = 0; c < cap; ++c) mark[c] = -1;
+    for (int i = 0; i < n; ++i) color[i] = -1;
+    for (int i = 0; i < n; ++i) {
+        if (ncol + 1 > cap) {
+            mark = (int *)realloc(mark, sizeof(int) * (size_t)(2 * cap));
+            for (int c = cap; c < 2 * cap; ++c) mark[c] = -1;
+            cap *= 2;
+        }
+        for (int k = I[i]; k < I[i + 1]; ++k) { int j = J[k]; if (j != i && color[j] >= 0) mark[color[j]] = i; }
+        int c = 0;
+        while (c < ncol && mark[c] == i) ++c;
+        color[i] = c;
+        if (c == ncol) ++ncol;
+    }
+    free(mark);
+    return ncol;
+}

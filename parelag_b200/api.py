@@ -87,6 +87,13 @@ class Sequence:
         _chk(lib().pe_api_sequence_get_bdr_mask(self.h, level, form, None, _ptr(m)))
         return m
 
+    def assemble_system(self, ctx, level, form, ess_attr):
+        ess = None if ess_attr is None else _i32(ess_attr)
+        m = capi.Mat(ctx)
+        _chk(lib().pe_api_sequence_assemble_system(self.h, level, form, _ptr(ess), 0 if ess is None else len(ess),
+                                                   C.byref(m.h)))
+        return m
+
     def stat(self, level, name):
         v = C.c_int64()
         _chk(lib().pe_api_sequence_get_stat(self.h, level, name.encode(), C.byref(v)))
@@ -126,6 +133,15 @@ def library_xml(entries):
 
 class Solver:
     def __init__(self, xml, name, A, seq=None, start_level=0, form=0, ess_attr=None):
+        ess = None if ess_attr is None else _i32(ess_attr)
+        self.h = C.c_void_p()
+        if isinstance(A, capi.Mat):      # device-resident operator: ownership passes to the solver
+            self.n = A.info()[0]
+            _chk(lib().pe_api_solver_build_device(xml.encode(), name.encode(), A.h, None if seq is None else seq.h,
+                                                  start_level, form, _ptr(ess), 0 if ess is None else len(ess),
+                                                  C.byref(self.h)))
+            A.h = None
+            return
         A = A.tocsr()
         self.n = A.shape[0]
         keep = [_i32(A.indptr), _i32(A.indices), _f64(A.data)]
@@ -146,6 +162,13 @@ class Solver:
 
     def mult_device(self, b, x, iterative_mode=False):
         _chk(lib().pe_api_solver_mult_device(self.h, b.h, x.h, 1 if iterative_mode else 0))
+
+    def prec_mult_device(self, b, x):
+        _chk(lib().pe_api_solver_prec_mult_device(self.h, b.h, x.h))
+
+    def mult_into(self, b, x, iterative_mode=False):
+        """Mult with caller-owned host buffers (e.g. pinned): H2D of b, D2H into x inside the call."""
+        _chk(lib().pe_api_solver_mult(self.h, _ptr(b), _ptr(x), self.n, 1 if iterative_mode else 0))
 
     def history(self):
         cnt, it, conv = C.c_int(), C.c_int(), C.c_int()

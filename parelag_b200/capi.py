@@ -101,6 +101,14 @@ class Ctx:
         _chk(lib().pe_ctx_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
+    def profile(self, enable):
+        _chk(lib().pe_ctx_profile(self.h, 1 if enable else 0))
+
+    def profile_get(self, kernel_id):
+        cnt, ms, by = C.c_int64(), C.c_double(), C.c_double()
+        _chk(lib().pe_ctx_profile_get(self.h, kernel_id, C.byref(cnt), C.byref(ms), C.byref(by)))
+        return cnt.value, ms.value, by.value
+
     def flush_l2(self):
         _chk(lib().pe_ctx_flush_l2(self.h))
 

@@ -175,6 +175,52 @@ int pe_allreduce_sum(pe_ctx *c, double *d, int count)
 }
 
 // ---------------------------------------------------------------------------
+// per-kernel event profiling
+// ---------------------------------------------------------------------------
+static cudaEvent_t prof_event(pe_ctx *c)
+{
+    if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+int pe_prof_begin(pe_ctx *c, int id, double bytes)
+{
+    if (!c->prof || c->capturing) return 0;
+    pe_ctx::ProfRec r{id, bytes, prof_event(c), prof_event(c)};
+    PE_CUDA(cudaEventRecord(r.e0, c->stream));
+    c->prof_recs.push_back(r);
+    return 0;
+}
+int pe_prof_end(pe_ctx *c)
+{
+    if (!c->prof || c->capturing) return 0;
+    PE_CUDA(cudaEventRecord(c->prof_recs.back().e1, c->stream));
+    return 0;
+}
+extern "C" int pe_ctx_profile(pe_ctx *c, int enable)
+{
+    PE_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto &r : c->prof_recs)
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { c->prof_ms[r.id] += ms; c->prof_bytes[r.id] += r.bytes; c->prof_count[r.id]++; }
+        c->prof_pool.push_back(r.e0); c->prof_pool.push_back(r.e1);
+    }
+    c->prof_recs.clear();
+    if (enable == 1 && !c->prof) for (int i = 0; i < 4; ++i) { c->prof_ms[i] = 0; c->prof_bytes[i] = 0; c->prof_count[i] = 0; }
+    c->prof = enable != 0;
+    return 0;
+}
+extern "C" int pe_ctx_profile_get(pe_ctx *c, int id, int64_t *count, double *total_ms, double *total_bytes)
+{
+    PE_CHECK(id >= 0 && id < 4, "bad kernel id");
+    PE_TRY(pe_ctx_profile(c, c->prof ? 2 : 0));   // fold pending records, keep the state
+    if (count) *count = c->prof_count[id];
+    if (total_ms) *total_ms = c->prof_ms[id];
+    if (total_bytes) *total_bytes = c->prof_bytes[id];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // CUDA graphs
 // ---------------------------------------------------------------------------
 struct pe_graph {

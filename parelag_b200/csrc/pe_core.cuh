@@ -58,7 +58,16 @@ struct pe_ctx {
     void *flush_d = nullptr;
     size_t flush_bytes = 0;
     bool capturing = false;
+    // optional per-kernel CUDA-event profiling (bench.py roofline): id 0 SpMV, 1 GS set, 2 Jacobi
+    bool prof = false;
+    struct ProfRec { int id; double bytes; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[4] = {0, 0, 0, 0}, prof_bytes[4] = {0, 0, 0, 0};
+    long long prof_count[4] = {0, 0, 0, 0};
 };
+int pe_prof_begin(pe_ctx *ctx, int id, double bytes);
+int pe_prof_end(pe_ctx *ctx);
 #define PE_MAX_PARTIALS 4096
 
 struct DevCSR {

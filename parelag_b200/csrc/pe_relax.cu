@@ -33,6 +33,8 @@ struct pe_smoother {
     DevCSR P;                          // set-ordered merged copy; col >= ncols_diag => ghost
     uint8_t *before_d = nullptr;       // per entry: column visited earlier in forward pass
     int tpr = 8;
+    std::vector<int> set_pI;           // P.I at the set boundaries (host copy, for profiling)
+    int pI_at(int k) const { for (size_t c = 0; c < set_starts.size(); ++c) if (set_starts[c] == k) return set_pI[c]; return 0; }
     // Chebyshev
     double max_eig = 0, min_eig = 0;
     double coefs[5] = {0, 0, 0, 0, 0};
@@ -259,6 +261,9 @@ static int build_gs_schedule(pe_smoother *s)
     }
     cudaFree(pos_d);
     s->tpr = pe_choose_tpr(nnz, n);
+    s->set_pI.resize(s->set_starts.size());
+    for (size_t c = 0; c < s->set_starts.size(); ++c)
+        PE_CUDA(cudaMemcpy(&s->set_pI[c], s->P.I + s->set_starts[c], sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -494,6 +499,11 @@ static int launch_gs_set(pe_smoother *s, int k0, int k1, const double *f, double
     int grid = pe_grid_for((int64_t)rows * tpr, 256);
     int ncd = s->A->diag.ncols;
 #define LAUNCH(T) k_gs_set<T, GENERAL><<<grid, 256, 0, ctx->stream>>>(k0, k1, s->P.I, s->P.J, s->P.A, s->perm_d, ncd, f, u, s->A->x_ext_d, s->l1_d, s->before_d, forward, s->w_d, c1, c2)
+    if (ctx->prof)
+    {
+        const double nnz_set = (double)(s->pI_at(k1) - s->pI_at(k0));
+        PE_TRY(pe_prof_begin(ctx, 1, 12.0 * nnz_set + 4.0 * rows + 32.0 * rows));
+    }
     switch (tpr) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
@@ -504,6 +514,7 @@ static int launch_gs_set(pe_smoother *s, int k0, int k1, const double *f, double
     }
 #undef LAUNCH
     PE_LAUNCHED(ctx);
+    PE_TRY(pe_prof_end(ctx));
     return 0;
 }
 
@@ -523,6 +534,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
             int64_t threads = (int64_t)n * tpr;
             int grid = (int)std::min<int64_t>((threads + 255) / 256, (int64_t)PE_SM_COUNT * 64);
             if (grid < 1) grid = 1;
+            PE_TRY(pe_prof_begin(ctx, 2, 12.0 * (double)(A->diag.nnz + A->offd.nnz) + 4.0 * (n + 1) + 8.0 * n * 4));
 #define LAUNCH(T) k_jacobi_update<T><<<grid, 256, 0, st>>>(n, A->diag.I, A->diag.J, A->diag.A, oI, A->offd.J, A->offd.A, x->d, A->x_ext_d, b->d, s->l1_d, s->weight, s->v_d)
             switch (tpr) {
             case 1: LAUNCH(1); break;
@@ -534,6 +546,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
             }
 #undef LAUNCH
             PE_LAUNCHED(ctx);
+            PE_TRY(pe_prof_end(ctx));
             pe_vec vv{ctx, n, s->v_d};
             PE_TRY(pe_vec_axpby(1.0, &vv, 1.0, x));
         } else if (s->type == 2 || s->type == 4 || s->type == 6) {

@@ -441,3 +441,31 @@ extern "C" int pe_spadd(pe_ctx *ctx, double a, const pe_mat *A, double b, const 
     PE_TRY(pe_mat_wrap_local(ctx, C, Cout));
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+__global__ void k_eliminate_rowcol(int n, const int *__restrict__ I, const int *__restrict__ J, double *A,
+                                   const int *__restrict__ marker)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool mi = marker[i] != 0;
+    for (int k = I[i]; k < I[i + 1]; ++k)
+    {
+        const int j = J[k];
+        if (mi) A[k] = (j == i) ? 1.0 : 0.0;
+        else if (marker[j]) A[k] = 0.0;
+    }
+}
+extern "C" int pe_mat_eliminate_rowcol(pe_ctx *ctx, pe_mat *A, const int32_t *marker_host)
+{
+    PE_CHECK(A->offd.nnz == 0 && A->diag.nrows == A->diag.ncols, "pe_mat_eliminate_rowcol: square local matrices only");
+    int n = A->diag.nrows;
+    int *m_d;
+    PE_CUDA(cudaMalloc(&m_d, sizeof(int) * (size_t)(n > 0 ? n : 1)));
+    PE_CUDA(cudaMemcpyAsync(m_d, marker_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) { k_eliminate_rowcol<<<pe_grid_for(n, 256), 256, 0, ctx->stream>>>(n, A->diag.I, A->diag.J, A->diag.A, m_d); PE_LAUNCHED(ctx); }
+    PE_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(m_d);
+    if (A->T) { pe_mat_free(A->T); A->T = nullptr; }
+    return 0;
+}

@@ -64,6 +64,8 @@ int pe_launch_spmv(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, int tpr,
     int grid = (int)std::min<int64_t>((threads + 255) / 256, cap);
     if (grid < 1) grid = 1;
 #define LAUNCH(T) k_spmv<T><<<grid, 256, 0, ctx->stream>>>(n, diag.I, diag.J, diag.A, oI, oJ, oA, x, xext, alpha, beta, yin, yout)
+    const double nnz_all = (double)diag.nnz + (oI ? (double)offd->nnz : 0.0);
+    PE_TRY(pe_prof_begin(ctx, 0, 12.0 * nnz_all + 4.0 * (n + 1) + 8.0 * diag.ncols + 8.0 * n + (beta != 0.0 ? 8.0 * n : 0.0)));
     switch (tpr) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
@@ -74,6 +76,7 @@ int pe_launch_spmv(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, int tpr,
     }
 #undef LAUNCH
     PE_LAUNCHED(ctx);
+    PE_TRY(pe_prof_end(ctx));
     return 0;
 }
 

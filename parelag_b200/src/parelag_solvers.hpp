@@ -277,6 +277,7 @@ public:
             std::printf("PCG: %s after %d iterations, (B r, r) = %g, (B r_0, r_0) = %g\n",
                         converged_ ? "converged" : "NOT converged", final_iter_, betanom, nom0);
     }
+    const std::shared_ptr<mfem::Solver> &GetPreconditioner() const { return Prec_; }
     int GetNumIterations() const { return final_iter_; }
     bool GetConverged() const { return converged_; }
     double GetFinalNorm() const { return final_norm_; }

@@ -177,18 +177,82 @@ extern "C" int pe_api_solver_build(const char *xml, const char *name, const pe_p
     *out = s.release();
     API_CATCH
 }
+extern "C" int pe_api_solver_build_device(const char *xml, const char *name, pe_mat *A, pe_sequence *seq,
+                                          int start_level, int form, const int32_t *ess_attr, int nattr, pe_solver **out)
+{
+    API_TRY
+    auto s = make_unique<pe_solver>();
+    SimpleXMLParameterListReader reader;
+    auto pl = reader.Parse(xml);
+    s->lib = SolverLibrary::CreateLibrary(*pl);
+    auto fact = s->lib->GetSolverFactory(name);
+    auto state = fact->GetDefaultState();
+    if (seq) state->SetDeRhamSequence(seq->levels.at(start_level));
+    std::vector<std::vector<int>> labels(1);
+    if (ess_attr) labels[0].assign(ess_attr, ess_attr + nattr);
+    state->SetBoundaryLabels(labels);
+    state->SetForms({form});
+    s->A = std::make_shared<mfem::HypreParMatrix>(A);
+    {
+        Timer t = TimeManager::AddTimer(std::string("Build Solver ") + name);
+        s->solver = fact->BuildSolver(s->A, *state);
+    }
+    *out = s.release();
+    API_CATCH
+}
+extern "C" int pe_api_sequence_assemble_system(pe_sequence *s, int level, int form, const int32_t *ess_attr, int nattr, pe_mat **out)
+{
+    API_TRY
+    auto &seq = *s->levels.at(level);
+    PARELAG_TEST_FOR_EXCEPTION(!seq.data, std::runtime_error, "assemble_system: sequence has no mass matrices");
+    pe_ctx *ctx = Device::Get();
+    Timer t = TimeManager::AddTimer("Assemble linear system");
+    auto upload = [&](const HostCSR &M) { pe_mat *d = nullptr; auto v = M.View(); PE_CALL(pe_mat_upload(ctx, &v, &d)); return d; };
+    // assembled mass operators: R^T M_e R with R = rDof -> dof (one +-1 per row)
+    auto mass = [&](int j)
+    {
+        const HostCSR &ED = seq.data->dof.at(j)->entity_dof.at(0);
+        HostCSR R;
+        R.nrows = (int)ED.J.size(); R.ncols = seq.data->dof[j]->ndofs;
+        R.I.resize(R.nrows + 1); std::iota(R.I.begin(), R.I.end(), 0);
+        R.J = ED.J; R.A = ED.A;
+        pe_mat *Rd = upload(R), *Med = upload(pool_as_csr(seq.data->M.at({j, 0}))), *Md = nullptr;
+        PE_CALL(pe_rap(ctx, nullptr, Med, Rd, &Md));
+        pe_mat_free(Rd); pe_mat_free(Med);
+        return Md;
+    };
+    pe_mat *W = mass(form + 1), *D = upload(*seq.GetDerivativeOperator(form)), *A = nullptr;
+    PE_CALL(pe_rap(ctx, nullptr, W, D, &A));
+    pe_mat_free(W); pe_mat_free(D);
+    if (form > 0)
+    {
+        pe_mat *M = mass(form), *S = nullptr;
+        PE_CALL(pe_spadd(ctx, 1.0, M, 1.0, A, &S));
+        pe_mat_free(M); pe_mat_free(A);
+        A = S;
+    }
+    if (ess_attr)
+    {
+        mfem::Array<int> ess(ess_attr, nattr), marker(seq.GetNumberOfDofs(form));
+        seq.GetDofHandler(form)->MarkDofsOnSelectedBndr(ess, marker);
+        PE_CALL(pe_mat_eliminate_rowcol(ctx, A, marker.GetData()));
+    }
+    *out = A;
+    API_CATCH
+}
 extern "C" int pe_api_solver_mult(pe_solver *s, const double *b, double *x, int n, int iterative_mode)
 {
     API_TRY
     PARELAG_TEST_FOR_EXCEPTION(n != s->solver->Height(), std::runtime_error, "pe_api_solver_mult: wrong vector length");
     s->b.SetSize(n); s->x.SetSize(n);
-    std::memcpy(s->b.HostWrite(), b, sizeof(double) * (size_t)n);
-    if (iterative_mode) std::memcpy(s->x.HostWrite(), x, sizeof(double) * (size_t)n);
+    // H2D straight from the caller's buffer (pinned or pageable), D2H straight into it
+    PE_CALL(pe_vec_upload(s->b.Write(), b));
+    if (iterative_mode) PE_CALL(pe_vec_upload(s->x.Write(), x));
     const bool saved = s->solver->iterative_mode;
     s->solver->iterative_mode = iterative_mode != 0;
     s->solver->Mult(s->b, s->x);
     s->solver->iterative_mode = saved;
-    std::memcpy(x, s->x.HostRead(), sizeof(double) * (size_t)n);
+    PE_CALL(pe_vec_download(s->x.Read(), x));
     API_CATCH
 }
 namespace
@@ -211,6 +275,18 @@ extern "C" int pe_api_solver_mult_device(pe_solver *s, const pe_vec *b, pe_vec *
     PE_CALL(pe_vec_copy(s->x.Read(), x));
     API_CATCH
 }
+extern "C" int pe_api_solver_prec_mult_device(pe_solver *s, const pe_vec *b, pe_vec *x)
+{
+    API_TRY
+    auto k = dynamic_cast<const KrylovSolver *>(s->solver.get());
+    PARELAG_TEST_FOR_EXCEPTION(!k || !k->GetPreconditioner(), std::runtime_error, "pe_api_solver_prec_mult_device: not a preconditioned Krylov solver");
+    const int n = s->solver->Height();
+    s->b.SetSize(n); s->x.SetSize(n);
+    PE_CALL(pe_vec_copy(b, s->b.Write()));
+    k->GetPreconditioner()->Mult(s->b, s->x);
+    PE_CALL(pe_vec_copy(s->x.Read(), x));
+    API_CATCH
+}
 extern "C" int pe_api_solver_get_history(const pe_solver *s, double *hist, int capacity, int *count, int *iterations, int *converged)
 {
     API_TRY
@@ -226,6 +302,9 @@ extern "C" int pe_api_solver_get_history(const pe_solver *s, double *hist, int c
 static const Hierarchy *as_hierarchy(const pe_solver *s)
 {
     auto h = dynamic_cast<const Hierarchy *>(s->solver.get());
+    if (!h)
+        if (auto k = dynamic_cast<const KrylovSolver *>(s->solver.get()))
+            h = dynamic_cast<const Hierarchy *>(k->GetPreconditioner().get());
     PARELAG_TEST_FOR_EXCEPTION(!h, std::runtime_error, "solver is not a Hierarchy (AMGe) solver");
     return h;
 }
