@@ -447,10 +447,48 @@ int devcsr_alloc(DevCSR &m, int32_t nrows, int32_t ncols, int64_t nnz)
 }
 void devcsr_free(DevCSR &m)
 {
+    if (m.rb) cudaFree(m.rb);
     if (m.I) cudaFree(m.I);
     if (m.J) cudaFree(m.J);
     if (m.A) cudaFree(m.A);
     m = DevCSR();
+}
+
+// Row blocks for the streaming kernels.  Host pass over the row pointer (once per matrix):
+// greedy packing of consecutive rows up to PE_STREAM_NNZ non-zeros and 1024 rows; optional
+// forced breaks (Gauss-Seidel set boundaries).
+int pe_build_row_blocks(pe_ctx *ctx, DevCSR &m, const std::vector<int32_t> *forced_breaks)
+{
+    if (m.rb) { cudaFree(m.rb); m.rb = nullptr; }
+    m.nrb = 0;
+    const int n = m.nrows;
+    if (n == 0) return 0;
+    std::vector<int32_t> I(n + 1);
+    PE_CUDA(cudaMemcpyAsync(I.data(), m.I, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    PE_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> rb;
+    rb.push_back(0);
+    size_t fb = 0;
+    while (forced_breaks && fb < forced_breaks->size() && (*forced_breaks)[fb] <= 0) ++fb;
+    int start = 0;
+    for (int r = 0; r < n; ++r)
+    {
+        const int len = I[r + 1] - I[r];
+        if (len > PE_STREAM_MAXROW) { m.nrb = -1; return 0; }
+        const bool forced = forced_breaks && fb < forced_breaks->size() && (*forced_breaks)[fb] == r;
+        if (r > start && (forced || I[r + 1] - I[start] > PE_STREAM_NNZ || r - start >= 1024))
+        {
+            rb.push_back(r);
+            start = r;
+        }
+        if (forced) ++fb;
+    }
+    rb.push_back(n);
+    m.nrb = (int)rb.size() - 1;
+    PE_CUDA(cudaMalloc(&m.rb, sizeof(int32_t) * rb.size()));
+    PE_CUDA(cudaMemcpyAsync(m.rb, rb.data(), sizeof(int32_t) * rb.size(), cudaMemcpyHostToDevice, ctx->stream));
+    PE_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 int pe_choose_tpr(int64_t nnz, int32_t nrows)

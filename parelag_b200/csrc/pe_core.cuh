@@ -75,7 +75,15 @@ struct DevCSR {
     int64_t nnz = 0;
     int32_t *I = nullptr, *J = nullptr;
     double *A = nullptr;
+    // row blocks of the streaming kernels: block b owns rows [rb[b], rb[b+1]) holding <= PE_STREAM_CAP
+    // non-zeros (built lazily; nrb == -1: matrix has rows too long for the streaming kernel)
+    int32_t *rb = nullptr;
+    int32_t nrb = 0;
 };
+#define PE_STREAM_NNZ 2048      // target non-zeros per CTA
+#define PE_STREAM_CAP 2560      // shared-memory capacity (target + longest admissible row)
+#define PE_STREAM_MAXROW 512
+int pe_build_row_blocks(pe_ctx *ctx, DevCSR &m, const std::vector<int32_t> *forced_breaks);
 int devcsr_alloc(DevCSR &m, int32_t nrows, int32_t ncols, int64_t nnz);
 void devcsr_free(DevCSR &m);
 

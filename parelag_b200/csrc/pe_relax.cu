@@ -34,6 +34,7 @@ struct pe_smoother {
     uint8_t *before_d = nullptr;       // per entry: column visited earlier in forward pass
     int tpr = 8;
     std::vector<int> set_pI;           // P.I at the set boundaries (host copy, for profiling)
+    std::vector<int> set_rb;           // first row block of each set (streaming kernel)
     int pI_at(int k) const { for (size_t c = 0; c < set_starts.size(); ++c) if (set_starts[c] == k) return set_pI[c]; return 0; }
     // Chebyshev
     double max_eig = 0, min_eig = 0;
@@ -127,6 +128,45 @@ k_gs_set(int k0, int k1, const int *__restrict__ pI, const int *__restrict__ pJ,
             if (GENERAL) u[i] += (c1 * (f[i] - s) + c2 * s2) / d;
             else u[i] += (f[i] - s) / d;
         }
+    }
+}
+
+// Streaming variant of one GS set (same structure as k_spmv_stream): CTA b owns rows
+// [rb[b], rb[b+1]) of the set-ordered matrix; row blocks never straddle a set boundary.
+__global__ void __launch_bounds__(256)
+k_gs_set_stream(int b0, const int *__restrict__ rb, const int *__restrict__ pI, const int *__restrict__ pJ,
+                const double *__restrict__ pA, const int *__restrict__ perm, int ncd,
+                const double *__restrict__ f, double *u, const double *__restrict__ uext,
+                const double *__restrict__ l1)
+{
+    __shared__ double prod[PE_STREAM_CAP];
+    const int tid = threadIdx.x;
+    const int r0 = rb[b0 + blockIdx.x], r1 = rb[b0 + blockIdx.x + 1];
+    const int k0 = pI[r0], k1 = pI[r1];
+    for (int base = k0; base < k1; base += 256 * 8)
+    {
+        int c[8]; double a[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+        {
+            const int k = base + q * 256 + tid;
+            c[q] = k < k1 ? pJ[k] : -1;
+            a[q] = k < k1 ? pA[k] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (c[q] >= 0) a[q] *= (c[q] < ncd ? u[c[q]] : uext[c[q] - ncd]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int k = base + q * 256 + tid; if (k < k1) prod[k - k0] = a[q]; }
+    }
+    __syncthreads();
+    for (int r = r0 + tid; r < r1; r += 256)
+    {
+        const int lo = pI[r] - k0, hi = pI[r + 1] - k0;
+        double s = 0.0;
+        for (int q = lo; q < hi; ++q) s += prod[q];
+        const int i = perm[r];
+        const double d = l1[i];
+        if (d != 0.0) u[i] += (f[i] - s) / d;
     }
 }
 
@@ -261,6 +301,21 @@ static int build_gs_schedule(pe_smoother *s)
     }
     cudaFree(pos_d);
     s->tpr = pe_choose_tpr(nnz, n);
+    {
+        std::vector<int32_t> breaks(s->set_starts.begin(), s->set_starts.end());
+        PE_TRY(pe_build_row_blocks(ctx, s->P, &breaks));
+        // first row block of every set
+        s->set_rb.assign(s->set_starts.size(), 0);
+        if (s->P.nrb > 0)
+        {
+            std::vector<int32_t> rb(s->P.nrb + 1);
+            PE_CUDA(cudaMemcpy(rb.data(), s->P.rb, sizeof(int32_t) * rb.size(), cudaMemcpyDeviceToHost));
+            size_t c = 0;
+            for (int b = 0; b <= s->P.nrb; ++b)
+                while (c < s->set_starts.size() && s->set_starts[c] == rb[b]) s->set_rb[c++] = b;
+            for (; c < s->set_starts.size(); ++c) s->set_rb[c] = s->P.nrb;
+        }
+    }
     s->set_pI.resize(s->set_starts.size());
     for (size_t c = 0; c < s->set_starts.size(); ++c)
         PE_CUDA(cudaMemcpy(&s->set_pI[c], s->P.I + s->set_starts[c], sizeof(int), cudaMemcpyDeviceToHost));
@@ -495,6 +550,18 @@ static int launch_gs_set(pe_smoother *s, int k0, int k1, const double *f, double
     pe_ctx *ctx = s->ctx;
     int rows = k1 - k0;
     if (rows <= 0) return 0;
+    if (!GENERAL && s->P.nrb > 0)
+    {
+        int c = 0;
+        while (s->set_starts[c] != k0) ++c;
+        const int b0 = s->set_rb[c], b1 = s->set_rb[c + 1];
+        if (ctx->prof) PE_TRY(pe_prof_begin(ctx, 1, 12.0 * (double)(s->set_pI[c + 1] - s->set_pI[c]) + 4.0 * rows + 32.0 * rows));
+        k_gs_set_stream<<<b1 - b0, 256, 0, ctx->stream>>>(b0, s->P.rb, s->P.I, s->P.J, s->P.A, s->perm_d, s->A->diag.ncols,
+                                                         f, u, s->A->x_ext_d, s->l1_d);
+        PE_LAUNCHED(ctx);
+        PE_TRY(pe_prof_end(ctx));
+        return 0;
+    }
     int tpr = s->tpr;
     int grid = pe_grid_for((int64_t)rows * tpr, 256);
     int ncd = s->A->diag.ncols;

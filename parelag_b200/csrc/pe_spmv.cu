@@ -50,6 +50,47 @@ k_spmv(int n, const int *__restrict__ dI, const int *__restrict__ dJ, const doub
     }
 }
 
+// Streaming SpMV: CTA b owns the consecutive rows [rb[b], rb[b+1]) (<= PE_STREAM_CAP non-zeros).
+// Phase 1: the CTA streams its contiguous run of (col,val) pairs with fully coalesced,
+// independent loads (8 in flight per thread), gathers x and parks the products in shared
+// memory.  Phase 2: one thread per row sums its products and applies the alpha/beta epilogue.
+#define SU 8
+__global__ void __launch_bounds__(256)
+k_spmv_stream(const int *__restrict__ rb, const int *__restrict__ I, const int *__restrict__ J,
+              const double *__restrict__ A, const double *__restrict__ x, double alpha, double beta,
+              const double *yin, double *yout)
+{
+    __shared__ double prod[PE_STREAM_CAP];
+    const int tid = threadIdx.x;
+    const int r0 = rb[blockIdx.x], r1 = rb[blockIdx.x + 1];
+    const int k0 = I[r0], k1 = I[r1];
+    for (int base = k0; base < k1; base += 256 * SU)
+    {
+        int c[SU]; double a[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u)
+        {
+            const int k = base + u * 256 + tid;
+            c[u] = k < k1 ? ld_stream_s32(J + k) : -1;
+            a[u] = k < k1 ? ld_stream_f64(A + k) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) if (c[u] >= 0) a[u] *= __ldg(x + c[u]);
+#pragma unroll
+        for (int u = 0; u < SU; ++u) { const int k = base + u * 256 + tid; if (k < k1) prod[k - k0] = a[u]; }
+    }
+    __syncthreads();
+    for (int r = r0 + tid; r < r1; r += 256)
+    {
+        const int lo = I[r] - k0, hi = I[r + 1] - k0;
+        double s = 0.0;
+        for (int q = lo; q < hi; ++q) s += prod[q];
+        double v = alpha * s;
+        if (beta != 0.0) v += beta * yin[r];
+        yout[r] = v;
+    }
+}
+
 int pe_launch_spmv(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, int tpr,
                    double alpha, const double *x, const double *xext,
                    double beta, const double *yin, double *yout)
@@ -59,6 +100,15 @@ int pe_launch_spmv(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, int tpr,
     const int *oI = nullptr, *oJ = nullptr;
     const double *oA = nullptr;
     if (offd && offd->nnz > 0) { oI = offd->I; oJ = offd->J; oA = offd->A; }
+    if (!oI && diag.nrb == 0 && diag.nnz > 0) PE_TRY(pe_build_row_blocks(ctx, const_cast<DevCSR &>(diag), nullptr));
+    if (!oI && diag.nrb > 0)
+    {
+        PE_TRY(pe_prof_begin(ctx, 0, 12.0 * (double)diag.nnz + 4.0 * (n + 1) + 8.0 * diag.ncols + 8.0 * n + (beta != 0.0 ? 8.0 * n : 0.0)));
+        k_spmv_stream<<<diag.nrb, 256, 0, ctx->stream>>>(diag.rb, diag.I, diag.J, diag.A, x, alpha, beta, yin, yout);
+        PE_LAUNCHED(ctx);
+        PE_TRY(pe_prof_end(ctx));
+        return 0;
+    }
     int64_t threads = (int64_t)n * tpr;
     int64_t cap = (int64_t)PE_SM_COUNT * 8 * 8;     // 8 CTAs of 256 threads per SM, x8 waves
     int grid = (int)std::min<int64_t>((threads + 255) / 256, cap);

@@ -13,6 +13,8 @@
 #include <map>
 #include <memory>
 #include <numeric>
+#include <string>
+#include <unordered_map>
 #include <vector>
 #include "parelag_sequence.hpp"
 
@@ -136,6 +138,55 @@ inline HostCSR findMinimalIntersectionSets(const HostCSR &Z, double skipDiagEntr
     return E;
 }
 
+/// The same minimal intersection sets computed from membership signatures, in O(nnz):
+/// with Z = X^T X for a 0/+-1 table X (agglomerate x entity), entities i and j satisfy the
+/// MIS criterion (Z_ii == Z_jj and |Z_ij| == Z_ii) iff they belong to exactly the same
+/// agglomerates with one consistent relative orientation.  `memb` is X^T (entity x
+/// agglomerate, ascending columns).  Avoids forming Z, whose boundary-attribute part
+/// facet_bdr * facet_bdr^T grows quadratically (Topology.cpp:748-757 warns about it; at
+/// 144^3 hexahedra it has 2.6e9 entries).  MIS are numbered by their first entity, exactly
+/// like findMinimalIntersectionSets.
+inline HostCSR MinimalIntersectionSetsFromMembership(const HostCSR &memb)
+{
+    const int n = memb.nrows;
+    std::unordered_map<std::string, int> ids;
+    ids.reserve((size_t)n);
+    std::vector<int> mis_of(n, -1);
+    std::vector<double> sign_of(n, 0.0);
+    std::string key;
+    int current = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        const int lo = memb.I[i], hi = memb.I[i + 1];
+        if (hi == lo) continue;                       // diag(Z) < 0.5: belongs to no MIS
+        const double s0 = memb.A[lo] > 0 ? 1.0 : -1.0;
+        key.clear();
+        for (int k = lo; k < hi; ++k)
+        {
+            const int a = memb.J[k];
+            key.append(reinterpret_cast<const char *>(&a), sizeof(int));
+            key.push_back((memb.A[k] > 0 ? 1.0 : -1.0) * s0 > 0 ? '+' : '-');
+        }
+        auto it = ids.find(key);
+        if (it == ids.end()) { it = ids.emplace(key, current++).first; }
+        mis_of[i] = it->second;
+        sign_of[i] = s0;      // orientation relative to the first entity of the set (whose s0-normalised pattern is all '+' ... )
+    }
+    // orientation of entity i relative to the first entity f of its set: Z_fi / Z_ff = s0(i) * s0(f)
+    std::vector<double> first_sign(current, 0.0);
+    for (int i = 0; i < n; ++i)
+        if (mis_of[i] >= 0 && first_sign[mis_of[i]] == 0.0) first_sign[mis_of[i]] = sign_of[i];
+    HostCSR E;
+    E.nrows = n; E.ncols = current;
+    E.I.assign(n + 1, 0);
+    for (int i = 0; i < n; ++i)
+    {
+        if (mis_of[i] >= 0) { E.J.push_back(mis_of[i]); E.A.push_back(sign_of[i] * first_sign[mis_of[i]]); }
+        E.I[i + 1] = (int)E.J.size();
+    }
+    return E;
+}
+
 class AgglomeratedTopology : public std::enable_shared_from_this<AgglomeratedTopology>
 {
 public:
@@ -189,10 +240,17 @@ public:
         {
             HostCSR AE_fc = hostcsr::MultOrientation(AEntity_entity_[icodim], B_[icodim]);
             HostCSR fc_AE = hostcsr::Transpose(AE_fc);
-            HostCSR Z = hostcsr::Mult(fc_AE, AE_fc);
             if (icodim == 0 && HasBdrAttributes())
-                Z = hostcsr::Add(Z, hostcsr::Mult(facet_bdrAttribute_, hostcsr::Transpose(facet_bdrAttribute_)));
-            HostCSR fc_AF = findMinimalIntersectionSets(Z, 0.5);
+            {
+                // fc_AE_fc + fc_bdrAttr_fc == [AE_fc; bdrAttr^T]^T [AE_fc; bdrAttr^T]: the boundary
+                // attributes act as extra agglomerates (columns nAE + attribute)
+                HostCSR shifted = facet_bdrAttribute_;
+                for (auto &c : shifted.J) c += AE_fc.nrows;
+                shifted.ncols += AE_fc.nrows;
+                fc_AE.ncols = shifted.ncols;
+                fc_AE = hostcsr::Add(fc_AE, shifted);
+            }
+            HostCSR fc_AF = MinimalIntersectionSetsFromMembership(fc_AE);
             AEntity_entity_.push_back(hostcsr::Transpose(fc_AF));
             cB.push_back(hostcsr::MultOrientation(AE_fc, fc_AF));
         }
