@@ -193,6 +193,8 @@ def main():
     ap.add_argument("--ref-levels", type=int, default=4)
     ap.add_argument("--cpu-n", type=int, default=32, help="bounded sample of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket 2 extra V-cycles with cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -252,6 +254,15 @@ def main():
     for _ in range(args.warmup):
         solver.prec_mult_device(r_dev, z_dev)
     ctx.sync()
+    if args.profile_range:
+        rt = torch.cuda.cudart()
+        rt.cudaProfilerStart()
+        for _ in range(2):
+            solver.prec_mult_device(r_dev, z_dev)
+        ctx.sync()
+        rt.cudaProfilerStop()
+        print(json.dumps({"profile_range": "2 V-cycles", "ndofs": int(ndofs)}))
+        return
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = ctx.launch_count()

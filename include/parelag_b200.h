@@ -102,6 +102,30 @@ int pe_vec_mul(const pe_vec *d, pe_vec *x);                                 /* x
 /* global dot (sum over ranks via ncclAllReduce); deterministic two-stage reduce.
  * Replaces mfem::CGSolver::Dot / MPI_Allreduce (ParELAG_StationarySolver.cpp:64). */
 int pe_vec_dot(const pe_vec *x, const pe_vec *y, double *out);
+/* Device-resident scalars: short inner Krylov solves (the AMGe coarse solver) keep every
+ * scalar of the recurrence in HBM so that no host synchronisation interrupts the V-cycle and
+ * the whole cycle can be replayed as one CUDA graph.  pe_scalars_* manage a block of doubles;
+ * the *_dev variants read/write one of its slots.
+ *   pe_vec_dot_dev : slots[out_slot] = <x,y> (all ranks)
+ *   pe_vec_axpy_dev: y += sign * slots[a_slot] * x      (no-op when the scalar is 0)
+ *   pe_vec_xpby_dev: y  = x + slots[b_slot] * y
+ *   pe_pcg_scalar_step: the scalar part of one phase of mfem::CGSolver::Mult (same tests and
+ *     formulas as the host loop in parelag_solvers.hpp); after convergence or breakdown the step
+ *     lengths become 0, so the remaining fixed-trip iterations leave x unchanged.
+ *     slot layout: PE_PCG_* below; history of (B r, r) starts at PE_PCG_HIST. */
+enum { PE_PCG_DOT = 0, PE_PCG_NOM = 1, PE_PCG_DEN = 2, PE_PCG_BETANOM = 3, PE_PCG_ALPHA = 4, PE_PCG_BETA = 5,
+       PE_PCG_R0 = 6, PE_PCG_DONE = 7, PE_PCG_CONVERGED = 8, PE_PCG_FINAL_ITER = 9, PE_PCG_NOM0 = 10,
+       PE_PCG_NHIST = 11, PE_PCG_HIST = 16 };
+int pe_scalars_create(pe_ctx *ctx, int count, double **slots_d);
+int pe_scalars_free(double *slots_d);
+int pe_scalars_download(pe_ctx *ctx, const double *slots_d, int count, double *host);
+int pe_vec_dot_dev(const pe_vec *x, const pe_vec *y, double *slots_d, int out_slot);
+int pe_vec_axpy_dev(const double *slots_d, int a_slot, double sign, const pe_vec *x, pe_vec *y);
+int pe_vec_xpby_dev(const pe_vec *x, const double *slots_d, int b_slot, pe_vec *y);
+int pe_pcg_scalar_step(pe_ctx *ctx, double *slots_d, int phase, int iter, int max_iter, double rel_tol, double abs_tol);
+/* non-zero while a CUDA graph is being captured / while per-kernel profiling is on */
+int pe_ctx_is_capturing(const pe_ctx *ctx);
+int pe_ctx_is_profiling(const pe_ctx *ctx);
 /* raw device pointer, for callers that own a CUDA stream themselves */
 void *pe_vec_device_ptr(pe_vec *v);
 

@@ -228,6 +228,7 @@ struct pe_graph {
     cudaGraphExec_t exec = nullptr;
     int64_t launches = 0;   // kernels recorded in the graph (counted at capture)
 };
+extern "C" int pe_graph_free(pe_graph *g);
 extern "C" int pe_graph_begin(pe_ctx *c)
 {
     PE_CHECK(!c->capturing, "graph capture already active");
@@ -241,10 +242,17 @@ extern "C" int pe_graph_end(pe_ctx *c, pe_graph **out)
     PE_CHECK(c->capturing, "no graph capture active");
     pe_graph *g = new pe_graph();
     c->capturing = false;
-    PE_CUDA(cudaStreamEndCapture(c->stream, &g->graph));
-    PE_CUDA(cudaGraphInstantiate(&g->exec, g->graph, 0));
     g->launches = c->launches - (int64_t)c->scalar_h[7];
     c->launches = (int64_t)c->scalar_h[7];  // capture did not execute anything
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g->graph);
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e != cudaSuccess)
+    {
+        (void)cudaGetLastError();   // an invalidated capture leaves a sticky-looking error behind
+        pe_set_error(std::string("CUDA graph capture failed: ") + cudaGetErrorString(e));
+        pe_graph_free(g);
+        return 1;
+    }
     *out = g;
     return 0;
 }
@@ -435,6 +443,128 @@ extern "C" int pe_vec_dot(const pe_vec *x, const pe_vec *y, double *out)
 }
 
 // ---------------------------------------------------------------------------
+// device-resident scalars (graph-capturable inner Krylov solves)
+// ---------------------------------------------------------------------------
+extern "C" int pe_ctx_is_capturing(const pe_ctx *c) { return c->capturing ? 1 : 0; }
+extern "C" int pe_ctx_is_profiling(const pe_ctx *c) { return c->prof ? 1 : 0; }
+extern "C" int pe_scalars_create(pe_ctx *ctx, int count, double **slots_d)
+{
+    PE_CHECK(ctx && slots_d && count > 0, "bad arguments");
+    PE_CUDA(cudaMalloc(slots_d, sizeof(double) * (size_t)count));
+    PE_CUDA(cudaMemsetAsync(*slots_d, 0, sizeof(double) * (size_t)count, ctx->stream));
+    return 0;
+}
+extern "C" int pe_scalars_free(double *slots_d)
+{
+    if (slots_d) cudaFree(slots_d);
+    return 0;
+}
+extern "C" int pe_scalars_download(pe_ctx *ctx, const double *slots_d, int count, double *host)
+{
+    PE_CUDA(cudaMemcpyAsync(host, slots_d, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    PE_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int pe_vec_dot_dev(const pe_vec *x, const pe_vec *y, double *slots_d, int out_slot)
+{
+    PE_CHECK(x->n == y->n, "size mismatch");
+    pe_ctx *c = x->ctx;
+    int grid = ew_grid(x->n);
+    if (grid > PE_MAX_PARTIALS) grid = PE_MAX_PARTIALS;
+    k_dot_stage1<<<grid, DOT_THREADS, 0, c->stream>>>(x->n, x->d, y->d, c->partials_d);
+    PE_LAUNCHED(c);
+    k_dot_stage2<<<1, DOT_THREADS, 0, c->stream>>>(grid, c->partials_d, slots_d + out_slot);
+    PE_LAUNCHED(c);
+    return pe_allreduce_sum(c, slots_d + out_slot, 1);
+}
+__global__ void k_axpy_dev(int64_t n, const double *__restrict__ a, double sign, const double *__restrict__ x, double *__restrict__ y)
+{
+    const double s = sign * a[0];
+    if (s == 0.0) return;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) y[i] += s * x[i];
+}
+__global__ void k_xpby_dev(int64_t n, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ y)
+{
+    const double s = b[0];
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) y[i] = x[i] + s * y[i];
+}
+extern "C" int pe_vec_axpy_dev(const double *slots_d, int a_slot, double sign, const pe_vec *x, pe_vec *y)
+{
+    PE_CHECK(x->n == y->n, "size mismatch");
+    k_axpy_dev<<<ew_grid(x->n), 256, 0, y->ctx->stream>>>(x->n, slots_d + a_slot, sign, x->d, y->d);
+    PE_LAUNCHED(y->ctx);
+    return 0;
+}
+extern "C" int pe_vec_xpby_dev(const pe_vec *x, const double *slots_d, int b_slot, pe_vec *y)
+{
+    PE_CHECK(x->n == y->n, "size mismatch");
+    k_xpby_dev<<<ew_grid(x->n), 256, 0, y->ctx->stream>>>(x->n, x->d, slots_d + b_slot, y->d);
+    PE_LAUNCHED(y->ctx);
+    return 0;
+}
+// scalar recurrences of mfem::CGSolver::Mult, one phase per launch (single thread)
+//  phase 0: DOT = (d, r) before the loop        phase 1: DOT = (z, d) before the loop
+//  phase 2: DOT = (r, z) in iteration `iter`    phase 3: DOT = (d, z) in iteration `iter`
+__global__ void k_pcg_scalar_step(double *s, int phase, int iter, int max_iter, double rel, double abs_tol)
+{
+    const double dot = s[PE_PCG_DOT];
+    bool done = s[PE_PCG_DONE] != 0.0;
+    if (phase == 0)
+    {
+        s[PE_PCG_NOM] = s[PE_PCG_NOM0] = s[PE_PCG_BETANOM] = dot;
+        s[PE_PCG_HIST] = dot; s[PE_PCG_NHIST] = 1.0;
+        s[PE_PCG_CONVERGED] = 0.0; s[PE_PCG_FINAL_ITER] = 0.0; s[PE_PCG_ALPHA] = 0.0; s[PE_PCG_BETA] = 0.0;
+        const double r0 = fmax(dot * rel * rel, abs_tol * abs_tol);
+        s[PE_PCG_R0] = r0;
+        done = false;
+        if (dot < 0.0) done = true;
+        else if (dot <= r0) { done = true; s[PE_PCG_CONVERGED] = 1.0; }
+    }
+    else if (phase == 1)
+    {
+        if (!done)
+        {
+            s[PE_PCG_DEN] = dot;
+            if (dot <= 0.0) done = true;
+            else s[PE_PCG_ALPHA] = s[PE_PCG_NOM] / dot;
+        }
+    }
+    else if (phase == 2)
+    {
+        if (!done)
+        {
+            s[PE_PCG_BETANOM] = dot;
+            s[PE_PCG_HIST + iter] = dot; s[PE_PCG_NHIST] = (double)(iter + 1);
+            if (dot < s[PE_PCG_R0]) { done = true; s[PE_PCG_CONVERGED] = 1.0; s[PE_PCG_FINAL_ITER] = (double)iter; }
+            else if (iter + 1 > max_iter) { done = true; s[PE_PCG_FINAL_ITER] = (double)max_iter; }
+            else s[PE_PCG_BETA] = dot / s[PE_PCG_NOM];
+        }
+    }
+    else
+    {
+        if (!done)
+        {
+            s[PE_PCG_DEN] = dot;
+            if (dot <= 0.0) { done = true; s[PE_PCG_FINAL_ITER] = (double)max_iter; }
+            else { s[PE_PCG_NOM] = s[PE_PCG_BETANOM]; s[PE_PCG_ALPHA] = s[PE_PCG_BETANOM] / dot; }
+        }
+    }
+    if (done) { s[PE_PCG_ALPHA] = 0.0; s[PE_PCG_BETA] = 0.0; }
+    s[PE_PCG_DONE] = done ? 1.0 : 0.0;
+}
+extern "C" int pe_pcg_scalar_step(pe_ctx *ctx, double *slots_d, int phase, int iter, int max_iter, double rel_tol, double abs_tol)
+{
+    PE_CHECK(phase >= 0 && phase <= 3, "bad phase");
+    k_pcg_scalar_step<<<1, 1, 0, ctx->stream>>>(slots_d, phase, iter, max_iter, rel_tol, abs_tol);
+    PE_LAUNCHED(ctx);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // matrices
 // ---------------------------------------------------------------------------
 int devcsr_alloc(DevCSR &m, int32_t nrows, int32_t ncols, int64_t nnz)
@@ -448,6 +578,7 @@ int devcsr_alloc(DevCSR &m, int32_t nrows, int32_t ncols, int64_t nnz)
 void devcsr_free(DevCSR &m)
 {
     if (m.rb) cudaFree(m.rb);
+    if (m.sell) { pe_sell_free(*m.sell); delete m.sell; }
     if (m.I) cudaFree(m.I);
     if (m.J) cudaFree(m.J);
     if (m.A) cudaFree(m.A);
@@ -489,6 +620,16 @@ int pe_build_row_blocks(pe_ctx *ctx, DevCSR &m, const std::vector<int32_t> *forc
     PE_CUDA(cudaMemcpyAsync(m.rb, rb.data(), sizeof(int32_t) * rb.size(), cudaMemcpyHostToDevice, ctx->stream));
     PE_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+void pe_mat_values_changed(pe_mat *A)
+{
+    if (A->T) { pe_mat_free(A->T); A->T = nullptr; }
+    for (DevCSR *m : {&A->diag, &A->offd})
+    {
+        if (m->sell) { pe_sell_free(*m->sell); delete m->sell; m->sell = nullptr; }
+        m->sell_state = 0;
+    }
 }
 
 int pe_choose_tpr(int64_t nnz, int32_t nrows)

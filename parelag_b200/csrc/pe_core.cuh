@@ -70,6 +70,15 @@ int pe_prof_begin(pe_ctx *ctx, int id, double bytes);
 int pe_prof_end(pe_ctx *ctx);
 #define PE_MAX_PARTIALS 4096
 
+// sliced-ELL copy of a CSR block (pe_sell.cu): slices of 32 rows, column-major inside a slice
+struct DevSELL {
+    int32_t nslices = 0, nrows = 0;   // nrows: rows that receive output (<= nslices*32)
+    int64_t nstored = 0;              // stored entries incl. padding
+    int32_t *soff = nullptr;          // nslices+1 slice offsets, in units of 32 entries
+    int32_t *J = nullptr;
+    double *A = nullptr;
+};
+
 struct DevCSR {
     int32_t nrows = 0, ncols = 0;
     int64_t nnz = 0;
@@ -79,7 +88,21 @@ struct DevCSR {
     // non-zeros (built lazily; nrb == -1: matrix has rows too long for the streaming kernel)
     int32_t *rb = nullptr;
     int32_t nrb = 0;
+    // SELL-32 copy streamed by SpMV (built lazily; state 0 untested, 1 built, -1 rejected: too much padding)
+    DevSELL *sell = nullptr;
+    int sell_state = 0;
 };
+void pe_sell_free(DevSELL &m);
+int pe_sell_build(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, const int32_t *rowmap_d, int32_t nslices,
+                  const int32_t *colpos_d, int32_t ext_base, DevSELL &out);
+int pe_sell_for_spmv(pe_ctx *ctx, DevCSR &m);
+void pe_mat_values_changed(struct pe_mat *A);   // drop cached transposes / SELL copies after an in-place edit
+int pe_launch_sell_spmv(pe_ctx *ctx, const DevSELL &S, double alpha, const double *x, double beta,
+                        const double *yin, double *yout);
+int pe_launch_sell_gs(pe_ctx *ctx, const DevSELL &S, int s0, int s1, int ext_base, const double *f, double *u,
+                      const double *uext, const double *l1);
+int pe_launch_perm_in(pe_ctx *ctx, int n, const int *pos, const double *b, const double *x, double *fp, double *up);
+int pe_launch_perm_out(pe_ctx *ctx, int n, const int *pos, const double *up, double *x);
 #define PE_STREAM_NNZ 2048      // target non-zeros per CTA
 #define PE_STREAM_CAP 2560      // shared-memory capacity (target + longest admissible row)
 #define PE_STREAM_MAXROW 512

@@ -36,6 +36,15 @@ struct pe_smoother {
     std::vector<int> set_pI;           // P.I at the set boundaries (host copy, for profiling)
     std::vector<int> set_rb;           // first row block of each set (streaming kernel)
     int pI_at(int k) const { for (size_t c = 0; c < set_starts.size(); ++c) if (set_starts[c] == k) return set_pI[c]; return 0; }
+    // colour-ordered SELL path (multicolour ordering with weight = omega = 1): rows AND columns
+    // renumbered colour by colour, every colour padded to whole slices of 32 rows
+    bool use_sell = false;
+    DevSELL S;
+    int32_t npad = 0;                   // padded length of the colour-ordered vectors
+    std::vector<int32_t> slice_starts;  // nsets+1: first slice of every colour
+    std::vector<double> set_bytes;      // algorithmic bytes of one colour launch
+    int32_t *pos_d = nullptr;           // row -> colour-ordered position
+    double *l1p_d = nullptr, *fp_d = nullptr, *up_d = nullptr;
     // Chebyshev
     double max_eig = 0, min_eig = 0;
     double coefs[5] = {0, 0, 0, 0, 0};
@@ -272,6 +281,55 @@ static int build_gs_schedule(pe_smoother *s)
     for (int i = 0; i < n; ++i) { int p = next[key[i]]++; s->order[p] = i; pos[i] = p; }
 
     bool general = !(s->weight == 1.0 && s->omega == 1.0);
+    if (s->ordering == PE_GS_ORDER_MULTICOLOR && !general)
+    {
+        // colour-ordered, slice-padded numbering
+        s->slice_starts.assign(nsets + 1, 0);
+        for (int c = 0; c < nsets; ++c)
+            s->slice_starts[c + 1] = s->slice_starts[c] + (s->set_starts[c + 1] - s->set_starts[c] + 31) / 32;
+        const int nslices = s->slice_starts[nsets];
+        s->npad = nslices * 32;
+        std::vector<int32_t> rowmap((size_t)s->npad, -1), ppos(n);
+        std::vector<int> oIh;
+        if (A->offd.nnz > 0)
+        {
+            oIh.resize(n + 1);
+            PE_CUDA(cudaMemcpy(oIh.data(), A->offd.I, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost));
+        }
+        s->set_bytes.assign(nsets, 0.0);
+        for (int c = 0; c < nsets; ++c)
+        {
+            double nnz_c = 0;
+            for (int k = s->set_starts[c]; k < s->set_starts[c + 1]; ++k)
+            {
+                const int i = s->order[k], p = s->slice_starts[c] * 32 + (k - s->set_starts[c]);
+                rowmap[p] = i; ppos[i] = p;
+                nnz_c += I[i + 1] - I[i];
+                if (!oIh.empty()) nnz_c += oIh[i + 1] - oIh[i];
+            }
+            const double rows = s->set_starts[c + 1] - s->set_starts[c];
+            s->set_bytes[c] = 12.0 * nnz_c + 4.0 * rows + 32.0 * rows;
+        }
+        int32_t *rowmap_d = nullptr;
+        const size_t np = (size_t)(s->npad > 0 ? s->npad : 1);
+        PE_CUDA(cudaMalloc(&rowmap_d, sizeof(int32_t) * np));
+        PE_CUDA(cudaMalloc(&s->pos_d, sizeof(int32_t) * (size_t)(n > 0 ? n : 1)));
+        PE_CUDA(cudaMalloc(&s->l1p_d, sizeof(double) * np));
+        PE_CUDA(cudaMalloc(&s->fp_d, sizeof(double) * np));
+        PE_CUDA(cudaMalloc(&s->up_d, sizeof(double) * np));
+        PE_CUDA(cudaMemcpyAsync(rowmap_d, rowmap.data(), sizeof(int32_t) * (size_t)s->npad, cudaMemcpyHostToDevice, ctx->stream));
+        PE_CUDA(cudaMemcpyAsync(s->pos_d, ppos.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        PE_CUDA(cudaMemsetAsync(s->l1p_d, 0, sizeof(double) * np, ctx->stream));
+        PE_CUDA(cudaMemsetAsync(s->fp_d, 0, sizeof(double) * np, ctx->stream));
+        PE_CUDA(cudaMemsetAsync(s->up_d, 0, sizeof(double) * np, ctx->stream));
+        PE_TRY(pe_sell_build(ctx, A->diag, &A->offd, rowmap_d, nslices, s->pos_d, s->npad, s->S));
+        // l1 in colour order (padded rows keep 0 => never updated)
+        PE_TRY(pe_launch_perm_in(ctx, n, s->pos_d, s->l1_d, nullptr, s->l1p_d, s->up_d));
+        PE_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(rowmap_d);
+        s->use_sell = true;
+        return 0;
+    }
     int *pos_d = nullptr, *len_d = nullptr;
     PE_CUDA(cudaMalloc(&s->perm_d, sizeof(int) * (size_t)(n > 0 ? n : 1)));
     PE_CUDA(cudaMalloc(&pos_d, sizeof(int) * (size_t)(n > 0 ? n : 1)));
@@ -539,6 +597,11 @@ extern "C" int pe_smoother_free(pe_smoother *s)
     if (s->ds_d) cudaFree(s->ds_d);
     if (s->perm_d) cudaFree(s->perm_d);
     if (s->before_d) cudaFree(s->before_d);
+    if (s->pos_d) cudaFree(s->pos_d);
+    if (s->l1p_d) cudaFree(s->l1p_d);
+    if (s->fp_d) cudaFree(s->fp_d);
+    if (s->up_d) cudaFree(s->up_d);
+    pe_sell_free(s->S);
     devcsr_free(s->P);
     delete s;
     return 0;
@@ -592,6 +655,33 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
     int n = A->diag.nrows;
     PE_CHECK(b->n == n && x->n == n, "pe_smoother_apply: size mismatch");
     cudaStream_t st = ctx->stream;
+    if (s->use_sell)
+    {
+        // colour-ordered SELL path: f and u are carried in colour order across the whole sweep
+        const bool ghosts = A->offd.nnz > 0;
+        for (int sweep = 0; sweep < s->sweeps; ++sweep)
+        {
+            const bool zero_guess = !iterative_mode && sweep == 0;
+            if (ctx->nranks > 1)
+            {
+                if (zero_guess) PE_CUDA(cudaMemsetAsync(x->d, 0, sizeof(double) * (size_t)n, st));
+                PE_TRY(pe_halo_exchange(A, x->d)); PE_TRY(pe_halo_wait(A));
+            }
+            PE_TRY(pe_launch_perm_in(ctx, n, s->pos_d, b->d, zero_guess ? nullptr : x->d, s->fp_d, s->up_d));
+            for (int pass = 0; pass < 2; ++pass)
+                for (int cc = 0; cc < s->nsets; ++cc)
+                {
+                    const int c = pass == 0 ? cc : s->nsets - 1 - cc;
+                    if (s->slice_starts[c + 1] == s->slice_starts[c]) continue;
+                    if (ctx->prof) PE_TRY(pe_prof_begin(ctx, 1, s->set_bytes[c]));
+                    PE_TRY(pe_launch_sell_gs(ctx, s->S, s->slice_starts[c], s->slice_starts[c + 1], s->npad, s->fp_d, s->up_d,
+                                             ghosts ? A->x_ext_d : nullptr, s->l1p_d));
+                    PE_TRY(pe_prof_end(ctx));
+                }
+            PE_TRY(pe_launch_perm_out(ctx, n, s->pos_d, s->up_d, x->d));
+        }
+        return 0;
+    }
     if (!iterative_mode) PE_CUDA(cudaMemsetAsync(x->d, 0, sizeof(double) * (size_t)n, st));
     const int *oI = A->offd.nnz > 0 ? A->offd.I : nullptr;
     for (int sweep = 0; sweep < s->sweeps; ++sweep) {

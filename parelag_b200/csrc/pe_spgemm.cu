@@ -377,7 +377,7 @@ extern "C" int pe_fix_zero_rows(pe_ctx *ctx, pe_mat *A, int32_t *num_fixed)
     PE_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PE_CUDA(cudaStreamSynchronize(ctx->stream));
     if (num_fixed) *num_fixed = h;
-    if (h > 0 && A->T) { pe_mat_free(A->T); A->T = nullptr; }
+    if (h > 0) pe_mat_values_changed(A);
     return 0;
 }
 
@@ -466,6 +466,6 @@ extern "C" int pe_mat_eliminate_rowcol(pe_ctx *ctx, pe_mat *A, const int32_t *ma
     if (n > 0) { k_eliminate_rowcol<<<pe_grid_for(n, 256), 256, 0, ctx->stream>>>(n, A->diag.I, A->diag.J, A->diag.A, m_d); PE_LAUNCHED(ctx); }
     PE_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(m_d);
-    if (A->T) { pe_mat_free(A->T); A->T = nullptr; }
+    pe_mat_values_changed(A);
     return 0;
 }

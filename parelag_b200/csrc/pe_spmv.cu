@@ -100,6 +100,14 @@ int pe_launch_spmv(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, int tpr,
     const int *oI = nullptr, *oJ = nullptr;
     const double *oA = nullptr;
     if (offd && offd->nnz > 0) { oI = offd->I; oJ = offd->J; oA = offd->A; }
+    if (!oI && diag.sell_state == 0) PE_TRY(pe_sell_for_spmv(ctx, const_cast<DevCSR &>(diag)));
+    if (!oI && diag.sell)
+    {
+        PE_TRY(pe_prof_begin(ctx, 0, 12.0 * (double)diag.nnz + 4.0 * (n + 1) + 8.0 * diag.ncols + 8.0 * n + (beta != 0.0 ? 8.0 * n : 0.0)));
+        PE_TRY(pe_launch_sell_spmv(ctx, *diag.sell, alpha, x, beta, yin, yout));
+        PE_TRY(pe_prof_end(ctx));
+        return 0;
+    }
     if (!oI && diag.nrb == 0 && diag.nnz > 0) PE_TRY(pe_build_row_blocks(ctx, const_cast<DevCSR &>(diag), nullptr));
     if (!oI && diag.nrb > 0)
     {
@@ -269,6 +277,6 @@ extern "C" int pe_mat_scale_rows(pe_mat *A, const pe_vec *d, int invert)
         k_scale_rows<<<pe_grid_for(n, 256), 256, 0, A->ctx->stream>>>(n, A->offd.I, A->offd.A, d->d, invert);
         PE_LAUNCHED(A->ctx);
     }
-    if (A->T) { pe_mat_free(A->T); A->T = nullptr; }
+    pe_mat_values_changed(A);
     return 0;
 }

@@ -326,6 +326,9 @@ public:
     void SetOperator(const mfem::Operator &) final { throw not_implemented_error("Solver::SetOperator(const Operator&): use the shared_ptr overload"); }
     void SetOperator(const std::shared_ptr<mfem::Operator> &op) { _do_set_operator(op); }
     bool IsPreconditioner() const noexcept { return !this->iterative_mode; }
+    /// true when Mult() only enqueues device work (no host synchronisation, no allocation after the
+    /// first call), i.e. when it may be recorded into a CUDA graph by an enclosing Hierarchy
+    virtual bool CaptureSafe() const { return false; }
 private:
     virtual void _do_set_operator(const std::shared_ptr<mfem::Operator> &op) = 0;
 };

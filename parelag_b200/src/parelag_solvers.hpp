@@ -32,6 +32,12 @@ inline void ComputeResidual(const mfem::Operator &A, const mfem::Vector &x, cons
 }
 } // namespace mg_utils
 
+inline bool SolverCaptureSafe(const mfem::Solver *s)
+{
+    auto p = dynamic_cast<const Solver *>(s);
+    return p && p->CaptureSafe();
+}
+
 // ------------------------------------------------------------------ Hypre smoother
 class HypreSmootherWrapper : public Solver
 {
@@ -61,6 +67,7 @@ public:
     }
     /// all supported relaxations are symmetric operators
     void MultTranspose(const mfem::Vector &rhs, mfem::Vector &sol) const override { Mult(rhs, sol); }
+    bool CaptureSafe() const override { return true; }
 private:
     void _do_set_operator(const Op_Ptr &) override { PARELAG_NOT_IMPLEMENTED(); }
     std::shared_ptr<mfem::HypreParMatrix> A_;
@@ -135,6 +142,8 @@ public:
         PrimarySolver_->Mult(B, X);
     }
     Op_Ptr GetAuxiliaryOperator() const { return A_aux_; }
+    bool CaptureSafe() const override
+    { return SolverCaptureSafe(PrimarySolver_.get()) && SolverCaptureSafe(AuxiliarySolver_.get()); }
 private:
     void _do_set_operator(const Op_Ptr &) override { PARELAG_NOT_IMPLEMENTED(); }
     Op_Ptr A_, A_aux_, D_op_;
@@ -231,11 +240,25 @@ public:
         max_iter_ = params.Get("Maximum iterations", 10);
         final_paragraph_ = params.Get("Print final paragraph", false);
     }
+    ~KrylovSolver() override { pe_scalars_free(slots_); }
+    /// Short inner solves (the AMGe coarse solver: "Maximum iterations" <= 10, no printing) run
+    /// "device resident": a fixed number of iterations whose scalars (alpha, beta, the stopping
+    /// tests of mfem::CGSolver::Mult) live in HBM.  Once the stopping test fires the step lengths
+    /// become 0, so x equals the result of the early exit; there is no host synchronisation and
+    /// the enclosing V-cycle can be captured in a CUDA graph.
+    bool DeviceResident() const { return max_iter_ >= 1 && max_iter_ <= 10 && print_level_ < 0 && !final_paragraph_; }
+    bool CaptureSafe() const override
+    {
+        return DeviceResident() && (!Prec_ || SolverCaptureSafe(Prec_.get())) &&
+               dynamic_cast<const mfem::HypreParMatrix *>(A_.get()) != nullptr;
+    }
     void Mult(const mfem::Vector &b, mfem::Vector &x) const override
     {
+        if (DeviceResident()) { MultDeviceResident(b, x); return; }
         const int n = Height();
         r_.SetSize(n); d_.SetSize(n); z_.SetSize(n);
         history_.clear();
+        stats_on_device_ = false;
         converged_ = false; final_iter_ = 0;
         if (this->iterative_mode) { A_->Mult(x, r_); mfem::add(b, -1.0, r_, r_); }
         else { r_ = b; x = 0.0; }
@@ -278,12 +301,55 @@ public:
                         converged_ ? "converged" : "NOT converged", final_iter_, betanom, nom0);
     }
     const std::shared_ptr<mfem::Solver> &GetPreconditioner() const { return Prec_; }
-    int GetNumIterations() const { return final_iter_; }
-    bool GetConverged() const { return converged_; }
-    double GetFinalNorm() const { return final_norm_; }
+    int GetNumIterations() const { FetchStats(); return final_iter_; }
+    bool GetConverged() const { FetchStats(); return converged_; }
+    double GetFinalNorm() const { FetchStats(); return final_norm_; }
     /// history[i] = (B r, r) after iteration i (history[0]: initial) -- what MFEM prints
-    const std::vector<double> &GetResidualHistory() const { return history_; }
+    const std::vector<double> &GetResidualHistory() const { FetchStats(); return history_; }
 private:
+    void MultDeviceResident(const mfem::Vector &b, mfem::Vector &x) const
+    {
+        pe_ctx *ctx = Device::Get();
+        const int n = Height();
+        r_.SetSize(n); d_.SetSize(n); z_.SetSize(n);
+        if (!slots_) PE_CALL(pe_scalars_create(ctx, PE_PCG_HIST + max_iter_ + 2, &slots_));
+        stats_on_device_ = true;
+        if (this->iterative_mode) { A_->Mult(x, r_); mfem::add(b, -1.0, r_, r_); }
+        else { r_ = b; x = 0.0; }
+        if (Prec_) { Prec_->Mult(r_, z_); d_ = z_; }
+        else d_ = r_;
+        PE_CALL(pe_vec_dot_dev(d_.Read(), r_.Read(), slots_, PE_PCG_DOT));
+        PE_CALL(pe_pcg_scalar_step(ctx, slots_, 0, 0, max_iter_, rel_tol_, abs_tol_));
+        A_->Mult(d_, z_);
+        PE_CALL(pe_vec_dot_dev(z_.Read(), d_.Read(), slots_, PE_PCG_DOT));
+        PE_CALL(pe_pcg_scalar_step(ctx, slots_, 1, 0, max_iter_, rel_tol_, abs_tol_));
+        for (int i = 1; i <= max_iter_; ++i)
+        {
+            PE_CALL(pe_vec_axpy_dev(slots_, PE_PCG_ALPHA, 1.0, d_.Read(), x.ReadWrite()));
+            PE_CALL(pe_vec_axpy_dev(slots_, PE_PCG_ALPHA, -1.0, z_.Read(), r_.ReadWrite()));
+            if (Prec_) { Prec_->Mult(r_, z_); PE_CALL(pe_vec_dot_dev(r_.Read(), z_.Read(), slots_, PE_PCG_DOT)); }
+            else PE_CALL(pe_vec_dot_dev(r_.Read(), r_.Read(), slots_, PE_PCG_DOT));
+            PE_CALL(pe_pcg_scalar_step(ctx, slots_, 2, i, max_iter_, rel_tol_, abs_tol_));
+            if (i == max_iter_) break;
+            PE_CALL(pe_vec_xpby_dev(Prec_ ? z_.Read() : r_.Read(), slots_, PE_PCG_BETA, d_.ReadWrite()));   // d = z + beta d
+            A_->Mult(d_, z_);
+            PE_CALL(pe_vec_dot_dev(d_.Read(), z_.Read(), slots_, PE_PCG_DOT));
+            PE_CALL(pe_pcg_scalar_step(ctx, slots_, 3, i, max_iter_, rel_tol_, abs_tol_));
+        }
+    }
+    /// statistics of a device-resident solve are downloaded on demand only
+    void FetchStats() const
+    {
+        if (!stats_on_device_ || !slots_) return;
+        std::vector<double> h(PE_PCG_HIST + max_iter_ + 2);
+        PE_CALL(pe_scalars_download(Device::Get(), slots_, (int)h.size(), h.data()));
+        const int nh = (int)h[PE_PCG_NHIST];
+        history_.assign(h.begin() + PE_PCG_HIST, h.begin() + PE_PCG_HIST + nh);
+        converged_ = h[PE_PCG_CONVERGED] != 0.0;
+        final_iter_ = (int)h[PE_PCG_FINAL_ITER];
+        final_norm_ = std::sqrt(std::fabs(h[PE_PCG_BETANOM]));
+        stats_on_device_ = false;
+    }
     void _do_set_operator(const Op_Ptr &op) override { A_ = op; }
     Op_Ptr A_;
     std::shared_ptr<mfem::Solver> Prec_;
@@ -295,6 +361,8 @@ private:
     mutable bool converged_ = false;
     mutable int final_iter_ = 0;
     mutable double final_norm_ = 0.0;
+    mutable double *slots_ = nullptr;          // device scalars of the device-resident mode
+    mutable bool stats_on_device_ = false;
 };
 
 class KrylovSolverFactory : public SolverFactory
@@ -345,12 +413,25 @@ public:
     std::vector<std::shared_ptr<Level>>::const_iterator begin() const { return Levels_.begin(); }
     std::vector<std::shared_ptr<Level>>::const_iterator end() const { return Levels_.end(); }
     void SetImplicitTranspose(bool v) noexcept { ImplicitTranspose_ = v; }
+    ~Hierarchy() override { pe_graph_free(graph_); }
+    /// replay the V-cycle as one CUDA graph when every level solver is capture-safe (default on)
+    void SetUseGraph(bool v) noexcept { use_graph_ = v; }
+    bool UsesGraph() const noexcept { return graph_ != nullptr; }
+    bool CaptureSafe() const override
+    {
+        for (auto &lev : Levels_)
+            for (const char *key : {"PreSmoother", "PostSmoother", "CoarseSolver"})
+                if (lev->IsValidKey(key))
+                    if (!SolverCaptureSafe(dynamic_cast<const mfem::Solver *>(lev->Get<Op_Ptr>(key).get()))) return false;
+        return true;
+    }
 
     /// one V-cycle (the "Cycle type" parameter is never read by the reference)
     void Mult(const mfem::Vector &rhs, mfem::Vector &sol) const override
     {
         if (this->IsPreconditioner())
         {
+            if (ReplayGraph(rhs, sol)) return;
             sol = 0.0;
             Iterate(rhs, sol, 0, 1, false);
         }
@@ -418,11 +499,52 @@ public:
         }
     }
 private:
+    /// Preconditioner-mode V-cycle through a CUDA graph: the first call with a given (rhs, sol)
+    /// buffer pair runs directly (it allocates work vectors and builds lazy matrix formats), the
+    /// second call records the cycle, later calls replay it.  Returns false when the cycle has to
+    /// be run directly.
+    bool ReplayGraph(const mfem::Vector &rhs, mfem::Vector &sol) const
+    {
+        pe_ctx *ctx = Device::Get();
+        if (!use_graph_ || graph_failed_) return false;
+        if (pe_ctx_is_capturing(ctx) || pe_ctx_is_profiling(ctx) || pe_ctx_nranks(ctx) > 1) return false;
+        if (capture_safe_ < 0) capture_safe_ = CaptureSafe() ? 1 : 0;
+        if (!capture_safe_) return false;
+        const void *rp = pe_vec_device_ptr(const_cast<pe_vec *>(rhs.Read()));
+        const void *sp = pe_vec_device_ptr(sol.Write());
+        if (graph_ && graph_rhs_ == rp && graph_sol_ == sp)
+        {
+            PE_CALL(pe_graph_launch(ctx, graph_));
+            return true;
+        }
+        if (warm_rhs_ != rp || warm_sol_ != sp) { warm_rhs_ = rp; warm_sol_ = sp; return false; }
+        pe_graph_free(graph_);
+        graph_ = nullptr;
+        if (pe_graph_begin(ctx) != 0) { graph_failed_ = true; return false; }
+        bool ok = true;
+        try { sol = 0.0; Iterate(rhs, sol, 0, 1, false); }
+        catch (...) { ok = false; }
+        pe_graph *g = nullptr;
+        if (pe_graph_end(ctx, &g) != 0 || !ok)
+        {
+            pe_graph_free(g);
+            graph_failed_ = true;
+            return false;           // the caller runs the cycle directly
+        }
+        graph_ = g; graph_rhs_ = rp; graph_sol_ = sp;
+        PE_CALL(pe_graph_launch(ctx, graph_));
+        return true;
+    }
     void _do_set_operator(const Op_Ptr &) override { PARELAG_NOT_IMPLEMENTED(); }
     std::vector<std::shared_ptr<Level>> Levels_;
     mutable std::vector<mfem::Vector> CoarseResids_, CoarseSols_, tmp_resid_, tmp_correct_;
     std::vector<int> CycleMu_;
     bool ImplicitTranspose_ = true;
+    bool use_graph_ = true;
+    mutable bool graph_failed_ = false;
+    mutable int capture_safe_ = -1;
+    mutable pe_graph *graph_ = nullptr;
+    mutable const void *graph_rhs_ = nullptr, *graph_sol_ = nullptr, *warm_rhs_ = nullptr, *warm_sol_ = nullptr;
 };
 
 /// Hierarchy.cpp:282-383: per coarse level P = ComputeTrueP(form, ess); A <- P^T A P; FixZeroRows
@@ -521,6 +643,7 @@ class AMGeSolverFactory : public SolverFactory
             }
             sequence = sequence->CoarserSequence();
         }
+        H->SetUseGraph(use_graph_);
         return H;
     }
     void _do_set_default_parameters() override {}
@@ -541,11 +664,12 @@ class AMGeSolverFactory : public SolverFactory
         MaxLevels_ = params.Get("Maximum levels", -1);
         Forms_ = params.Get("Forms", std::vector<int>());
         print_levels_ = params.Get("Print level summary", false);
+        use_graph_ = params.Get("Use CUDA graph", true);   // extension: replay the V-cycle as one graph
     }
     std::shared_ptr<SolverFactory> PreSmootherFact_, PostSmootherFact_, CoarseSolverFact_;
     int MaxLevels_ = -1;
     mutable std::vector<int> Forms_;
-    bool print_levels_ = false;
+    bool print_levels_ = false, use_graph_ = true;
 };
 
 // ------------------------------------------------------------------ Stationary iteration
