@@ -87,6 +87,23 @@ int pe_graph_end(pe_ctx *ctx, pe_graph **out);
 int pe_graph_launch(pe_ctx *ctx, pe_graph *g);
 int pe_graph_free(pe_graph *g);
 
+/* ---- persistent programs: a recorded sequence of solve-path operations (a whole
+ * Hierarchy::Mult V-cycle) executed by ONE cooperative kernel, one CTA per SM, with
+ * grid-wide barriers between the operations instead of kernel boundaries.
+ * Between pe_program_begin and pe_program_end the solve-path entry points (pe_spmv,
+ * pe_residual, pe_smoother_apply, pe_vec_*, pe_pcg_scalar_step ...) record instead of
+ * executing; pe_program_end fails (non-zero) when an operation without a program
+ * equivalent was requested -- the caller then falls back to a CUDA graph.
+ * pe_program_profile runs the program once with a device timestamp after every barrier. */
+typedef struct pe_program pe_program;
+int pe_program_begin(pe_ctx *ctx);
+int pe_program_end(pe_ctx *ctx, pe_program **out);
+int pe_program_launch(pe_ctx *ctx, pe_program *p);
+int pe_program_free(pe_program *p);
+int pe_program_info(const pe_program *p, int32_t *nops, double *algorithmic_bytes);
+int pe_program_profile(pe_ctx *ctx, pe_program *p, int32_t *op_types, double *op_usec, double *op_bytes);
+int pe_ctx_is_recording(const pe_ctx *ctx);
+
 /* ---- vectors (replace mfem::Vector on the path) */
 int pe_vec_create(pe_ctx *ctx, int64_t n, pe_vec **out);
 int pe_vec_free(pe_vec *v);

@@ -89,6 +89,9 @@ int pe_api_solver_get_history(const pe_solver *s, double *hist, int capacity, in
                               int *iterations, int *converged);
 /* Hierarchy solvers: number of levels, and size / nnz of A on a level */
 int pe_api_solver_num_levels(const pe_solver *s, int *nlevels);
+/* Hierarchy solvers: the persistent program the V-cycle was recorded into (NULL until the third
+ * preconditioner application with the same buffers, or when recording was not possible) */
+int pe_api_solver_program(const pe_solver *s, pe_program **out);
 int pe_api_solver_level_info(const pe_solver *s, int level, int64_t *nrows, int64_t *nnz, int64_t *nnz_P);
 /* download A (diag block) of a hierarchy level for parity tests; arrays sized from level_info */
 int pe_api_solver_level_matrix(const pe_solver *s, int level, int32_t *I, int32_t *J, double *A);

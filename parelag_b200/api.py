@@ -187,6 +187,27 @@ class Solver:
         _chk(lib().pe_api_solver_level_info(self.h, l, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def program(self):
+        """(nops, algorithmic bytes) of the persistent program the V-cycle runs as, or None."""
+        h = C.c_void_p()
+        _chk(lib().pe_api_solver_program(self.h, C.byref(h)))
+        if not h.value:
+            return None
+        n, b = C.c_int32(), C.c_double()
+        _chk(lib().pe_program_info(h, C.byref(n), C.byref(b)))
+        return n.value, b.value
+
+    def program_profile(self, ctx):
+        """One extra program launch with per-op device timestamps: (types, usec, bytes) arrays."""
+        h = C.c_void_p()
+        _chk(lib().pe_api_solver_program(self.h, C.byref(h)))
+        if not h.value:
+            return None
+        n = self.program()[0]
+        t, us, by = np.empty(n, dtype=np.int32), np.empty(n), np.empty(n)
+        _chk(lib().pe_program_profile(ctx.h, h, _ptr(t), _ptr(us), _ptr(by)))
+        return t, us, by
+
     def level_matrix(self, l):
         import scipy.sparse as sp
         n, nnz, _ = self.level_info(l)

@@ -1,5 +1,6 @@
 // pe_core.cu -- context, vectors, matrix upload/download, halo exchange, CUDA graphs.
 #include "pe_core.cuh"
+#include "pe_stream.cuh"
 #include <dlfcn.h>
 #include <cstring>
 #include <cstdio>
@@ -184,7 +185,8 @@ static cudaEvent_t prof_event(pe_ctx *c)
 }
 int pe_prof_begin(pe_ctx *c, int id, double bytes)
 {
-    if (!c->prof || c->capturing) return 0;
+    c->pending_bytes = bytes;
+    if (!c->prof || c->capturing || c->rec) return 0;
     pe_ctx::ProfRec r{id, bytes, prof_event(c), prof_event(c)};
     PE_CUDA(cudaEventRecord(r.e0, c->stream));
     c->prof_recs.push_back(r);
@@ -192,7 +194,7 @@ int pe_prof_begin(pe_ctx *c, int id, double bytes)
 }
 int pe_prof_end(pe_ctx *c)
 {
-    if (!c->prof || c->capturing) return 0;
+    if (!c->prof || c->capturing || c->rec) return 0;
     PE_CUDA(cudaEventRecord(c->prof_recs.back().e1, c->stream));
     return 0;
 }
@@ -350,6 +352,13 @@ static inline int ew_grid(int64_t n)
 }
 extern "C" int pe_vec_fill(pe_vec *v, double value)
 {
+    if (v->ctx->rec)
+    {
+        if (v->n == 0) return 0;
+        PeOp o = pe_op(PE_OP_FILL); o.n = v->n; o.a = value; o.p[0] = v->d;
+        pe_rec_push(v->ctx, o, 8.0 * v->n);
+        return 0;
+    }
     if (value == 0.0) {
         PE_CUDA(cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)v->n, v->ctx->stream));
         return 0;
@@ -361,6 +370,13 @@ extern "C" int pe_vec_fill(pe_vec *v, double value)
 extern "C" int pe_vec_copy(const pe_vec *src, pe_vec *dst)
 {
     PE_CHECK(src->n == dst->n, "size mismatch");
+    if (dst->ctx->rec)
+    {
+        if (src->n == 0) return 0;
+        PeOp o = pe_op(PE_OP_COPY); o.n = src->n; o.p[0] = src->d; o.p[1] = dst->d;
+        pe_rec_push(dst->ctx, o, 16.0 * src->n);
+        return 0;
+    }
     PE_CUDA(cudaMemcpyAsync(dst->d, src->d, sizeof(double) * (size_t)src->n,
                             cudaMemcpyDeviceToDevice, dst->ctx->stream));
     return 0;
@@ -368,6 +384,13 @@ extern "C" int pe_vec_copy(const pe_vec *src, pe_vec *dst)
 extern "C" int pe_vec_axpby(double a, const pe_vec *x, double b, pe_vec *y)
 {
     PE_CHECK(x->n == y->n, "size mismatch");
+    if (y->ctx->rec)
+    {
+        if (x->n == 0) return 0;
+        PeOp o = pe_op(PE_OP_AXPBY); o.n = x->n; o.a = a; o.b = b; o.p[0] = x->d; o.p[1] = y->d;
+        pe_rec_push(y->ctx, o, (b == 0.0 ? 16.0 : 24.0) * x->n);
+        return 0;
+    }
     k_axpby<<<ew_grid(x->n), 256, 0, y->ctx->stream>>>(x->n, a, x->d, b, y->d);
     PE_LAUNCHED(y->ctx);
     return 0;
@@ -375,12 +398,26 @@ extern "C" int pe_vec_axpby(double a, const pe_vec *x, double b, pe_vec *y)
 extern "C" int pe_vec_add3(double a, const pe_vec *x, double b, const pe_vec *y, pe_vec *z)
 {
     PE_CHECK(x->n == y->n && x->n == z->n, "size mismatch");
+    if (z->ctx->rec)
+    {
+        if (x->n == 0) return 0;
+        PeOp o = pe_op(PE_OP_ADD3); o.n = x->n; o.a = a; o.b = b; o.p[0] = x->d; o.p[1] = y->d; o.p[2] = z->d;
+        pe_rec_push(z->ctx, o, 24.0 * x->n);
+        return 0;
+    }
     k_add3<<<ew_grid(x->n), 256, 0, z->ctx->stream>>>(x->n, a, x->d, b, y->d, z->d);
     PE_LAUNCHED(z->ctx);
     return 0;
 }
 extern "C" int pe_vec_scale(pe_vec *x, double a)
 {
+    if (x->ctx->rec)
+    {
+        if (x->n == 0) return 0;
+        PeOp o = pe_op(PE_OP_SCALE); o.n = x->n; o.a = a; o.p[0] = x->d;
+        pe_rec_push(x->ctx, o, 16.0 * x->n);
+        return 0;
+    }
     k_scale<<<ew_grid(x->n), 256, 0, x->ctx->stream>>>(x->n, a, x->d);
     PE_LAUNCHED(x->ctx);
     return 0;
@@ -388,6 +425,13 @@ extern "C" int pe_vec_scale(pe_vec *x, double a)
 extern "C" int pe_vec_mul(const pe_vec *d, pe_vec *x)
 {
     PE_CHECK(d->n == x->n, "size mismatch");
+    if (x->ctx->rec)
+    {
+        if (x->n == 0) return 0;
+        PeOp o = pe_op(PE_OP_MUL); o.n = x->n; o.p[0] = d->d; o.p[1] = x->d;
+        pe_rec_push(x->ctx, o, 24.0 * x->n);
+        return 0;
+    }
     k_mul<<<ew_grid(x->n), 256, 0, x->ctx->stream>>>(x->n, d->d, x->d);
     PE_LAUNCHED(x->ctx);
     return 0;
@@ -428,6 +472,7 @@ extern "C" int pe_vec_dot(const pe_vec *x, const pe_vec *y, double *out)
 {
     PE_CHECK(x->n == y->n, "size mismatch");
     pe_ctx *c = x->ctx;
+    if (c->rec) pe_rec_fail(c, "pe_vec_dot (host-synchronising)", 0);
     int grid = ew_grid(x->n);
     if (grid > PE_MAX_PARTIALS) grid = PE_MAX_PARTIALS;
     k_dot_stage1<<<grid, DOT_THREADS, 0, c->stream>>>(x->n, x->d, y->d, c->partials_d);
@@ -469,6 +514,14 @@ extern "C" int pe_vec_dot_dev(const pe_vec *x, const pe_vec *y, double *slots_d,
 {
     PE_CHECK(x->n == y->n, "size mismatch");
     pe_ctx *c = x->ctx;
+    if (c->rec)
+    {
+        PeOp o = pe_op(PE_OP_DOT); o.n = x->n; o.p[0] = x->d; o.p[1] = y->d; o.p[2] = c->partials_d;
+        pe_rec_push(c, o, 16.0 * x->n);
+        PeOp f = pe_op(PE_OP_DOT_FIN); f.p[0] = c->partials_d; f.p[1] = slots_d + out_slot;   // i0 = grid, set at program_end
+        pe_rec_push(c, f, 0.0);
+        return 0;
+    }
     int grid = ew_grid(x->n);
     if (grid > PE_MAX_PARTIALS) grid = PE_MAX_PARTIALS;
     k_dot_stage1<<<grid, DOT_THREADS, 0, c->stream>>>(x->n, x->d, y->d, c->partials_d);
@@ -495,6 +548,13 @@ __global__ void k_xpby_dev(int64_t n, const double *__restrict__ x, const double
 extern "C" int pe_vec_axpy_dev(const double *slots_d, int a_slot, double sign, const pe_vec *x, pe_vec *y)
 {
     PE_CHECK(x->n == y->n, "size mismatch");
+    if (y->ctx->rec)
+    {
+        if (x->n == 0) return 0;
+        PeOp o = pe_op(PE_OP_AXPY_DEV); o.n = x->n; o.a = sign; o.p[0] = slots_d + a_slot; o.p[1] = x->d; o.p[2] = y->d;
+        pe_rec_push(y->ctx, o, 24.0 * x->n);
+        return 0;
+    }
     k_axpy_dev<<<ew_grid(x->n), 256, 0, y->ctx->stream>>>(x->n, slots_d + a_slot, sign, x->d, y->d);
     PE_LAUNCHED(y->ctx);
     return 0;
@@ -502,63 +562,30 @@ extern "C" int pe_vec_axpy_dev(const double *slots_d, int a_slot, double sign, c
 extern "C" int pe_vec_xpby_dev(const pe_vec *x, const double *slots_d, int b_slot, pe_vec *y)
 {
     PE_CHECK(x->n == y->n, "size mismatch");
+    if (y->ctx->rec)
+    {
+        if (x->n == 0) return 0;
+        PeOp o = pe_op(PE_OP_XPBY_DEV); o.n = x->n; o.p[0] = x->d; o.p[1] = slots_d + b_slot; o.p[2] = y->d;
+        pe_rec_push(y->ctx, o, 24.0 * x->n);
+        return 0;
+    }
     k_xpby_dev<<<ew_grid(x->n), 256, 0, y->ctx->stream>>>(x->n, x->d, slots_d + b_slot, y->d);
     PE_LAUNCHED(y->ctx);
     return 0;
 }
-// scalar recurrences of mfem::CGSolver::Mult, one phase per launch (single thread)
-//  phase 0: DOT = (d, r) before the loop        phase 1: DOT = (z, d) before the loop
-//  phase 2: DOT = (r, z) in iteration `iter`    phase 3: DOT = (d, z) in iteration `iter`
 __global__ void k_pcg_scalar_step(double *s, int phase, int iter, int max_iter, double rel, double abs_tol)
 {
-    const double dot = s[PE_PCG_DOT];
-    bool done = s[PE_PCG_DONE] != 0.0;
-    if (phase == 0)
-    {
-        s[PE_PCG_NOM] = s[PE_PCG_NOM0] = s[PE_PCG_BETANOM] = dot;
-        s[PE_PCG_HIST] = dot; s[PE_PCG_NHIST] = 1.0;
-        s[PE_PCG_CONVERGED] = 0.0; s[PE_PCG_FINAL_ITER] = 0.0; s[PE_PCG_ALPHA] = 0.0; s[PE_PCG_BETA] = 0.0;
-        const double r0 = fmax(dot * rel * rel, abs_tol * abs_tol);
-        s[PE_PCG_R0] = r0;
-        done = false;
-        if (dot < 0.0) done = true;
-        else if (dot <= r0) { done = true; s[PE_PCG_CONVERGED] = 1.0; }
-    }
-    else if (phase == 1)
-    {
-        if (!done)
-        {
-            s[PE_PCG_DEN] = dot;
-            if (dot <= 0.0) done = true;
-            else s[PE_PCG_ALPHA] = s[PE_PCG_NOM] / dot;
-        }
-    }
-    else if (phase == 2)
-    {
-        if (!done)
-        {
-            s[PE_PCG_BETANOM] = dot;
-            s[PE_PCG_HIST + iter] = dot; s[PE_PCG_NHIST] = (double)(iter + 1);
-            if (dot < s[PE_PCG_R0]) { done = true; s[PE_PCG_CONVERGED] = 1.0; s[PE_PCG_FINAL_ITER] = (double)iter; }
-            else if (iter + 1 > max_iter) { done = true; s[PE_PCG_FINAL_ITER] = (double)max_iter; }
-            else s[PE_PCG_BETA] = dot / s[PE_PCG_NOM];
-        }
-    }
-    else
-    {
-        if (!done)
-        {
-            s[PE_PCG_DEN] = dot;
-            if (dot <= 0.0) { done = true; s[PE_PCG_FINAL_ITER] = (double)max_iter; }
-            else { s[PE_PCG_NOM] = s[PE_PCG_BETANOM]; s[PE_PCG_ALPHA] = s[PE_PCG_BETANOM] / dot; }
-        }
-    }
-    if (done) { s[PE_PCG_ALPHA] = 0.0; s[PE_PCG_BETA] = 0.0; }
-    s[PE_PCG_DONE] = done ? 1.0 : 0.0;
+    pe_pcg_scalar_step_dev(s, phase, iter, max_iter, rel, abs_tol);
 }
 extern "C" int pe_pcg_scalar_step(pe_ctx *ctx, double *slots_d, int phase, int iter, int max_iter, double rel_tol, double abs_tol)
 {
     PE_CHECK(phase >= 0 && phase <= 3, "bad phase");
+    if (ctx->rec)
+    {
+        PeOp o = pe_op(PE_OP_PCG_STEP); o.i0 = phase; o.i1 = iter; o.i2 = max_iter; o.a = rel_tol; o.b = abs_tol; o.p[0] = slots_d;
+        pe_rec_push(ctx, o, 0.0);
+        return 0;
+    }
     k_pcg_scalar_step<<<1, 1, 0, ctx->stream>>>(slots_d, phase, iter, max_iter, rel_tol, abs_tol);
     PE_LAUNCHED(ctx);
     return 0;

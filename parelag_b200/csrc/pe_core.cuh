@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../include/parelag_b200.h"
@@ -37,12 +38,36 @@ void pe_set_error(const std::string &msg);
         if (rc_) return rc_;      \
     } while (0)
 
-// count one kernel launch on ctx and check the launch status
+// count one kernel launch on ctx and check the launch status.  A launch that reaches this
+// macro while a program is being recorded (pe_prog.cu) has no op equivalent: the recording is
+// marked failed and the caller falls back to direct launches / a CUDA graph.
 #define PE_LAUNCHED(ctx)                                     \
     do {                                                     \
         (ctx)->launches++;                                   \
+        if ((ctx)->rec) pe_rec_fail((ctx), __FILE__, __LINE__); \
         PE_CUDA(cudaPeekAtLastError());                      \
     } while (0)
+
+// ---- persistent "program" kernel (pe_prog.cu): the ops a recorded V-cycle is made of
+enum PeOpType : int32_t {
+    PE_OP_SELL_SPMV = 1, PE_OP_SELL_GS, PE_OP_CSR_SPMV, PE_OP_PERM_IN, PE_OP_PERM_OUT, PE_OP_AXPBY, PE_OP_ADD3,
+    PE_OP_FILL, PE_OP_COPY, PE_OP_SCALE, PE_OP_MUL, PE_OP_DOT, PE_OP_DOT_FIN, PE_OP_AXPY_DEV, PE_OP_XPBY_DEV,
+    PE_OP_PCG_STEP
+};
+struct PeOp {               // 128 bytes, copied to shared memory by the interpreter
+    int32_t type, i0, i1, i2, i3, i4, i5, flags;
+    int64_t n;
+    double a, b;
+    const void *p[9];
+};
+struct pe_recorder {
+    std::vector<PeOp> ops;
+    std::vector<double> bytes;     // algorithmic bytes per op
+    bool failed = false;
+    std::string why;
+};
+struct pe_ctx;
+void pe_rec_fail(pe_ctx *ctx, const char *file, int line);
 
 struct pe_ctx {
     int rank = 0, nranks = 1, device = 0;
@@ -58,6 +83,8 @@ struct pe_ctx {
     void *flush_d = nullptr;
     size_t flush_bytes = 0;
     bool capturing = false;
+    pe_recorder *rec = nullptr;          // non-null while a program is being recorded
+    double pending_bytes = 0.0;          // algorithmic bytes announced by the last pe_prof_begin
     // optional per-kernel CUDA-event profiling (bench.py roofline): id 0 SpMV, 1 GS set, 2 Jacobi
     bool prof = false;
     struct ProfRec { int id; double bytes; cudaEvent_t e0, e1; };
@@ -66,6 +93,22 @@ struct pe_ctx {
     double prof_ms[4] = {0, 0, 0, 0}, prof_bytes[4] = {0, 0, 0, 0};
     long long prof_count[4] = {0, 0, 0, 0};
 };
+// record an op instead of launching (returns true when ctx is recording)
+// bytes < 0: use the figure announced by the enclosing pe_prof_begin
+static inline bool pe_rec_push(pe_ctx *ctx, const PeOp &op, double bytes)
+{
+    if (!ctx->rec) return false;
+    ctx->rec->ops.push_back(op);
+    ctx->rec->bytes.push_back(bytes < 0.0 ? ctx->pending_bytes : bytes);
+    ctx->pending_bytes = 0.0;
+    return true;
+}
+static inline PeOp pe_op(int32_t type)
+{
+    PeOp o{};
+    o.type = type;
+    return o;
+}
 int pe_prof_begin(pe_ctx *ctx, int id, double bytes);
 int pe_prof_end(pe_ctx *ctx);
 #define PE_MAX_PARTIALS 4096

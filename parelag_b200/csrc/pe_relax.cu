@@ -673,7 +673,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
                 {
                     const int c = pass == 0 ? cc : s->nsets - 1 - cc;
                     if (s->slice_starts[c + 1] == s->slice_starts[c]) continue;
-                    if (ctx->prof) PE_TRY(pe_prof_begin(ctx, 1, s->set_bytes[c]));
+                    PE_TRY(pe_prof_begin(ctx, 1, s->set_bytes[c]));
                     PE_TRY(pe_launch_sell_gs(ctx, s->S, s->slice_starts[c], s->slice_starts[c + 1], s->npad, s->fp_d, s->up_d,
                                              ghosts ? A->x_ext_d : nullptr, s->l1p_d));
                     PE_TRY(pe_prof_end(ctx));

@@ -13,28 +13,8 @@
 // the C ABI (upload/download/SpGEMM).  Algorithmic bytes are counted on the CSR figures
 // (12 B per true non-zero), see DESIGN.md.
 #include "pe_core.cuh"
+#include "pe_stream.cuh"
 #include <cub/cub.cuh>
-
-// Matrix streams are read once per launch: no L1 allocation, and an L2 evict-first policy so
-// that the vectors (u, f, l1 -- re-read by every colour) are what stays resident in the 126 MB L2.
-__device__ __forceinline__ uint64_t l2_evict_first_policy()
-{
-    uint64_t pol;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ double ld_stream_f64(const double *p, uint64_t pol)
-{
-    double v;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ int ld_stream_s32(const int *p, uint64_t pol)
-{
-    int v;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
 
 // ---------------------------------------------------------------------------
 // build
@@ -186,6 +166,13 @@ int pe_launch_sell_spmv(pe_ctx *ctx, const DevSELL &S, double alpha, const doubl
                         const double *yin, double *yout)
 {
     if (S.nslices == 0) return 0;
+    if (ctx->rec)
+    {
+        PeOp o = pe_op(PE_OP_SELL_SPMV); o.i0 = S.nslices; o.i1 = S.nrows; o.a = alpha; o.b = beta;
+        o.p[0] = S.soff; o.p[1] = S.J; o.p[2] = S.A; o.p[3] = x; o.p[4] = yin; o.p[5] = yout;
+        pe_rec_push(ctx, o, -1.0);
+        return 0;
+    }
     k_sell_spmv<<<pe_grid_for((int64_t)S.nslices * 32, 256), 256, 0, ctx->stream>>>(S.nslices, S.nrows, S.soff, S.J, S.A,
                                                                                    x, alpha, beta, yin, yout);
     PE_LAUNCHED(ctx);
@@ -245,6 +232,13 @@ int pe_launch_sell_gs(pe_ctx *ctx, const DevSELL &S, int s0, int s1, int ext_bas
                       const double *uext, const double *l1)
 {
     if (s1 <= s0) return 0;
+    if (ctx->rec)
+    {
+        PeOp o = pe_op(PE_OP_SELL_GS); o.i0 = s0; o.i1 = s1; o.i2 = ext_base;
+        o.p[0] = S.soff; o.p[1] = S.J; o.p[2] = S.A; o.p[3] = f; o.p[4] = u; o.p[5] = uext; o.p[6] = l1;
+        pe_rec_push(ctx, o, -1.0);
+        return 0;
+    }
     const int grid = pe_grid_for((int64_t)(s1 - s0) * 32, 256);
     if (uext) k_sell_gs<true><<<grid, 256, 0, ctx->stream>>>(s0, s1, S.soff, S.J, S.A, ext_base, f, u, uext, l1);
     else k_sell_gs<false><<<grid, 256, 0, ctx->stream>>>(s0, s1, S.soff, S.J, S.A, ext_base, f, u, uext, l1);
@@ -270,6 +264,12 @@ __global__ void k_sell_perm_out(int n, const int *__restrict__ pos, const double
 int pe_launch_perm_in(pe_ctx *ctx, int n, const int *pos, const double *b, const double *x, double *fp, double *up)
 {
     if (n == 0) return 0;
+    if (ctx->rec)
+    {
+        PeOp o = pe_op(PE_OP_PERM_IN); o.n = n; o.p[0] = pos; o.p[1] = b; o.p[2] = x; o.p[3] = fp; o.p[4] = up;
+        pe_rec_push(ctx, o, 0.0);   // renumbering is our overhead, not algorithmic traffic
+        return 0;
+    }
     k_sell_perm_in<<<pe_grid_for(n, 256), 256, 0, ctx->stream>>>(n, pos, b, x, fp, up);
     PE_LAUNCHED(ctx);
     return 0;
@@ -277,6 +277,12 @@ int pe_launch_perm_in(pe_ctx *ctx, int n, const int *pos, const double *b, const
 int pe_launch_perm_out(pe_ctx *ctx, int n, const int *pos, const double *up, double *x)
 {
     if (n == 0) return 0;
+    if (ctx->rec)
+    {
+        PeOp o = pe_op(PE_OP_PERM_OUT); o.n = n; o.p[0] = pos; o.p[1] = up; o.p[2] = x;
+        pe_rec_push(ctx, o, 0.0);
+        return 0;
+    }
     k_sell_perm_out<<<pe_grid_for(n, 256), 256, 0, ctx->stream>>>(n, pos, up, x);
     PE_LAUNCHED(ctx);
     return 0;

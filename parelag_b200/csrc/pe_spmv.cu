@@ -108,6 +108,14 @@ int pe_launch_spmv(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, int tpr,
         PE_TRY(pe_prof_end(ctx));
         return 0;
     }
+    if (ctx->rec && !oI)
+    {
+        // persistent program: CSR-vector op (the CTA-tiled streaming kernel has no op equivalent)
+        PeOp o = pe_op(PE_OP_CSR_SPMV); o.i0 = n; o.i1 = pe_choose_tpr(diag.nnz, n); o.a = alpha; o.b = beta;
+        o.p[0] = diag.I; o.p[1] = diag.J; o.p[2] = diag.A; o.p[3] = x; o.p[4] = yin; o.p[5] = yout;
+        pe_rec_push(ctx, o, 12.0 * (double)diag.nnz + 4.0 * (n + 1) + 8.0 * diag.ncols + 8.0 * n + (beta != 0.0 ? 8.0 * n : 0.0));
+        return 0;
+    }
     if (!oI && diag.nrb == 0 && diag.nnz > 0) PE_TRY(pe_build_row_blocks(ctx, const_cast<DevCSR &>(diag), nullptr));
     if (!oI && diag.nrb > 0)
     {

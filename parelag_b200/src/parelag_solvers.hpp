@@ -413,10 +413,14 @@ public:
     std::vector<std::shared_ptr<Level>>::const_iterator begin() const { return Levels_.begin(); }
     std::vector<std::shared_ptr<Level>>::const_iterator end() const { return Levels_.end(); }
     void SetImplicitTranspose(bool v) noexcept { ImplicitTranspose_ = v; }
-    ~Hierarchy() override { pe_graph_free(graph_); }
-    /// replay the V-cycle as one CUDA graph when every level solver is capture-safe (default on)
+    ~Hierarchy() override { pe_graph_free(graph_); pe_program_free(program_); }
+    /// replay the V-cycle as one persistent program kernel (preferred) or one CUDA graph when
+    /// every level solver is capture-safe (both default on)
     void SetUseGraph(bool v) noexcept { use_graph_ = v; }
+    void SetUseProgram(bool v) noexcept { use_program_ = v; }
     bool UsesGraph() const noexcept { return graph_ != nullptr; }
+    bool UsesProgram() const noexcept { return program_ != nullptr; }
+    pe_program *GetProgram() const noexcept { return program_; }
     bool CaptureSafe() const override
     {
         for (auto &lev : Levels_)
@@ -506,12 +510,17 @@ private:
     bool ReplayGraph(const mfem::Vector &rhs, mfem::Vector &sol) const
     {
         pe_ctx *ctx = Device::Get();
-        if (!use_graph_ || graph_failed_) return false;
-        if (pe_ctx_is_capturing(ctx) || pe_ctx_is_profiling(ctx) || pe_ctx_nranks(ctx) > 1) return false;
+        if ((!use_graph_ || graph_failed_) && (!use_program_ || program_failed_)) return false;
+        if (pe_ctx_is_capturing(ctx) || pe_ctx_is_recording(ctx) || pe_ctx_is_profiling(ctx) || pe_ctx_nranks(ctx) > 1) return false;
         if (capture_safe_ < 0) capture_safe_ = CaptureSafe() ? 1 : 0;
         if (!capture_safe_) return false;
         const void *rp = pe_vec_device_ptr(const_cast<pe_vec *>(rhs.Read()));
         const void *sp = pe_vec_device_ptr(sol.Write());
+        if (program_ && graph_rhs_ == rp && graph_sol_ == sp)
+        {
+            PE_CALL(pe_program_launch(ctx, program_));
+            return true;
+        }
         if (graph_ && graph_rhs_ == rp && graph_sol_ == sp)
         {
             PE_CALL(pe_graph_launch(ctx, graph_));
@@ -520,6 +529,25 @@ private:
         if (warm_rhs_ != rp || warm_sol_ != sp) { warm_rhs_ = rp; warm_sol_ = sp; return false; }
         pe_graph_free(graph_);
         graph_ = nullptr;
+        pe_program_free(program_);
+        program_ = nullptr;
+        if (use_program_ && !program_failed_ && pe_program_begin(ctx) == 0)
+        {
+            // record the cycle: every C-ABI call below appends an op instead of launching
+            bool rec_ok = true;
+            try { sol = 0.0; Iterate(rhs, sol, 0, 1, false); }
+            catch (...) { rec_ok = false; }
+            pe_program *p = nullptr;
+            if (pe_program_end(ctx, &p) == 0 && rec_ok)
+            {
+                program_ = p; graph_rhs_ = rp; graph_sol_ = sp;
+                PE_CALL(pe_program_launch(ctx, program_));
+                return true;
+            }
+            pe_program_free(p);
+            program_failed_ = true;
+        }
+        if (!use_graph_ || graph_failed_) return false;
         if (pe_graph_begin(ctx) != 0) { graph_failed_ = true; return false; }
         bool ok = true;
         try { sol = 0.0; Iterate(rhs, sol, 0, 1, false); }
@@ -540,8 +568,9 @@ private:
     mutable std::vector<mfem::Vector> CoarseResids_, CoarseSols_, tmp_resid_, tmp_correct_;
     std::vector<int> CycleMu_;
     bool ImplicitTranspose_ = true;
-    bool use_graph_ = true;
-    mutable bool graph_failed_ = false;
+    bool use_graph_ = true, use_program_ = false;
+    mutable bool graph_failed_ = false, program_failed_ = false;
+    mutable pe_program *program_ = nullptr;
     mutable int capture_safe_ = -1;
     mutable pe_graph *graph_ = nullptr;
     mutable const void *graph_rhs_ = nullptr, *graph_sol_ = nullptr, *warm_rhs_ = nullptr, *warm_sol_ = nullptr;
@@ -644,6 +673,7 @@ class AMGeSolverFactory : public SolverFactory
             sequence = sequence->CoarserSequence();
         }
         H->SetUseGraph(use_graph_);
+        H->SetUseProgram(use_program_);
         return H;
     }
     void _do_set_default_parameters() override {}
@@ -665,11 +695,12 @@ class AMGeSolverFactory : public SolverFactory
         Forms_ = params.Get("Forms", std::vector<int>());
         print_levels_ = params.Get("Print level summary", false);
         use_graph_ = params.Get("Use CUDA graph", true);   // extension: replay the V-cycle as one graph
+        use_program_ = params.Get("Use persistent program", false);  // extension: the V-cycle as one persistent kernel (experimental)
     }
     std::shared_ptr<SolverFactory> PreSmootherFact_, PostSmootherFact_, CoarseSolverFact_;
     int MaxLevels_ = -1;
     mutable std::vector<int> Forms_;
-    bool print_levels_ = false, use_graph_ = true;
+    bool print_levels_ = false, use_graph_ = true, use_program_ = false;
 };
 
 // ------------------------------------------------------------------ Stationary iteration

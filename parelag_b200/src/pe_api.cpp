@@ -314,6 +314,12 @@ extern "C" int pe_api_solver_num_levels(const pe_solver *s, int *nlevels)
     *nlevels = as_hierarchy(s)->GetNumLevels();
     API_CATCH
 }
+extern "C" int pe_api_solver_program(const pe_solver *s, pe_program **out)
+{
+    API_TRY
+    *out = as_hierarchy(s)->GetProgram();
+    API_CATCH
+}
 extern "C" int pe_api_solver_level_info(const pe_solver *s, int level, int64_t *nrows, int64_t *nnz, int64_t *nnz_P)
 {
     API_TRY
