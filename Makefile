@@ -13,11 +13,11 @@ $(LIB): $(OBJ)
 	@mkdir -p $(dir $@)
 	$(NVCC) -shared $(ARCH) -o $@ $(OBJ) -lcudart -ldl
 
-build/%.o: %.cu $(wildcard parelag_b200/csrc/*.cuh) include/parelag_b200.h
+build/%.o: %.cu $(wildcard parelag_b200/csrc/*.cuh) $(wildcard include/*.h)
 	@mkdir -p $(dir $@)
 	$(NVCC) $(NVFLAGS) -Iinclude -c $< -o $@ 2> build/$(notdir $<).ptxas.log || (cat build/$(notdir $<).ptxas.log; false)
 
-build/%.o: %.cpp $(wildcard parelag_b200/src/*.hpp) include/parelag_b200.h
+build/%.o: %.cpp $(wildcard parelag_b200/src/*.hpp) $(wildcard include/*.h)
 	@mkdir -p $(dir $@)
 	g++ -O2 -std=c++17 -fPIC -Wall -Iinclude -Iparelag_b200/src -c $< -o $@
 

@@ -151,6 +151,8 @@ int pe_mat_upload(pe_ctx *ctx, const pe_parcsr_host *A, pe_mat **out);
 /* query sizes, then download into caller-allocated arrays (NULL = skip) */
 int pe_mat_info(const pe_mat *A, int32_t *num_rows, int32_t *num_cols_diag,
                 int32_t *num_cols_offd, int64_t *nnz_diag, int64_t *nnz_offd);
+int pe_mat_global_info(const pe_mat *A, int64_t *global_num_rows, int64_t *global_num_cols,
+                       int64_t *first_row_index, int64_t *first_col_diag);
 int pe_mat_download(const pe_mat *A, int32_t *diag_i, int32_t *diag_j, double *diag_data,
                     int32_t *offd_i, int32_t *offd_j, double *offd_data,
                     int64_t *col_map_offd);

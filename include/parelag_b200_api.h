@@ -17,6 +17,7 @@
 #ifndef PARELAG_B200_API_H
 #define PARELAG_B200_API_H
 #include "parelag_b200.h"
+#include "parelag_b200_par.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -51,6 +52,22 @@ int pe_api_sequence_free(pe_sequence *s);
 int pe_api_hexsequence_create(int nx, int ny, int nz, double Lx, double Ly, double Lz,
                               const double *alpha, const double *beta, int jform_start, int nlevels,
                               double svd_tol, pe_sequence **out);
+/* ---- multi-rank (one rank <-> one box of a P0 x P1 x P2 box decomposition <-> one GPU).
+ * pe_api_session_set_host_comm: the setup-time host communicator (MPI_Comm in the reference).
+ * pe_api_hexsequence_create_par: as pe_api_hexsequence_create for THIS rank's box (nx,ny,nz hexahedra
+ *   of extent Lx,Ly,Lz); builds the dof <-> true-dof SharingMaps of every level.
+ * pe_api_sequence_get_dofmap: DofHandler::GetDofTrueDof -- global true id / owner / global key of
+ *   every local dof (arrays may be NULL).
+ * pe_api_sequence_true_operator: DeRhamSequence::ComputeTrueP / ComputeTrueD as a device ParCSR. */
+int pe_api_session_set_host_comm(const pe_host_comm *comm);
+int pe_api_hexsequence_create_par(const int32_t *procs, int nx, int ny, int nz, double Lx, double Ly, double Lz,
+                                  const double *alpha, const double *beta, int jform_start, int nlevels,
+                                  double svd_tol, pe_sequence **out);
+int pe_api_sequence_get_dofmap(pe_sequence *s, int level, int form, int32_t *ndofs, int64_t *gid, int32_t *owner,
+                               int64_t *key, int64_t *true_start, int64_t *true_count, int64_t *global_count);
+int pe_api_sequence_true_operator(pe_sequence *s, int level, const char *what, int form, const int32_t *ess_attr,
+                                  int nattr, pe_mat **out);
+
 /* Introspection for parity tests.  what = "P" (a=form), "D" (a=form), "M" (a=form: assembled
  * mass operator), "Me" (a=form, b=codim: block-diagonal entity mass matrices), "B" (a=codim),
  * "AE" (a=codim: agglomerated entity -> entity), "ED" (a=form, b=codim: entity -> dof),

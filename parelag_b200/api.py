@@ -22,6 +22,16 @@ def session_destroy():
     _chk(lib().pe_api_session_destroy())
 
 
+_host_comm = None
+
+
+def set_host_comm(comm):
+    """Install the setup-time host communicator (parelag_b200.par.HostComm); kept alive here."""
+    global _host_comm
+    _host_comm = comm
+    _chk(lib().pe_api_session_set_host_comm(comm.ptr()))
+
+
 def _csr_args(M):
     M = M.tocsr()
     return (M.shape[0], M.shape[1], np.ascontiguousarray(M.indptr, dtype=np.int32),
@@ -58,6 +68,36 @@ class Sequence:
                                              C.c_double(L[2]), _ptr(a), _ptr(b), jstart, nlevels,
                                              C.c_double(svd_tol), C.byref(S.h)))
         return S
+
+    @staticmethod
+    def hex_par(procs, dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9):
+        """The same on THIS rank's box (dims hexahedra of extent L) of a procs[0] x procs[1] x procs[2] box
+        decomposition; needs set_host_comm()."""
+        S = Sequence.__new__(Sequence)
+        S.h = C.c_void_p()
+        a = None if alpha is None else _f64(alpha)
+        b = None if beta is None else _f64(beta)
+        P = _i32(procs)
+        _chk(lib().pe_api_hexsequence_create_par(_ptr(P), dims[0], dims[1], dims[2], C.c_double(L[0]), C.c_double(L[1]),
+                                                 C.c_double(L[2]), _ptr(a), _ptr(b), jstart, nlevels,
+                                                 C.c_double(svd_tol), C.byref(S.h)))
+        return S
+
+    def dofmap(self, level, form):
+        """DofHandler::GetDofTrueDof: dict(gid, owner, key, start, ntrue, nglobal) of the local dofs"""
+        nd, st, nt, ng = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(lib().pe_api_sequence_get_dofmap(self.h, level, form, C.byref(nd), None, None, None, C.byref(st), C.byref(nt), C.byref(ng)))
+        gid, owner, key = np.empty(nd.value, dtype=np.int64), np.empty(nd.value, dtype=np.int32), np.empty(nd.value, dtype=np.int64)
+        _chk(lib().pe_api_sequence_get_dofmap(self.h, level, form, None, _ptr(gid), _ptr(owner), _ptr(key), None, None, None))
+        return dict(gid=gid, owner=owner, key=key, start=st.value, ntrue=nt.value, nglobal=ng.value)
+
+    def true_operator(self, ctx, level, what, form, ess_attr=None):
+        """ComputeTrueP / ComputeTrueD (what = "P" | "D") as a device ParCSR matrix"""
+        ess = None if ess_attr is None else _i32(ess_attr)
+        m = capi.Mat(ctx)
+        _chk(lib().pe_api_sequence_true_operator(self.h, level, what.encode(), form, _ptr(ess), 0 if ess is None else len(ess),
+                                                 C.byref(m.h)))
+        return m
 
     def get_csr(self, level, what, a=0, b=0):
         import scipy.sparse as sp

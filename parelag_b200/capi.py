@@ -236,6 +236,20 @@ class Mat:
         _chk(lib().pe_mat_download(self.h, _ptr(I), _ptr(J), _ptr(A), None, None, None, None))
         return sp.csr_matrix((A, J, I), shape=(nr, ncd))
 
+    def download_parcsr(self):
+        """All blocks of a (distributed) ParCSR matrix: dict as parelag_b200.par.OwnedParCSR.arrays()."""
+        nr, ncd, nco, nd, no = self.info()
+        gr, gc, fr, fc = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(lib().pe_mat_global_info(self.h, C.byref(gr), C.byref(gc), C.byref(fr), C.byref(fc)))
+        d = dict(first_row=fr.value, first_col=fc.value, nrows=nr, ncols_diag=ncd, global_rows=gr.value, global_cols=gc.value,
+                 diag_i=np.empty(nr + 1, dtype=np.int32), diag_j=np.empty(nd, dtype=np.int32), diag_a=np.empty(nd),
+                 offd_i=np.zeros(nr + 1, dtype=np.int32), offd_j=np.empty(no, dtype=np.int32), offd_a=np.empty(no),
+                 col_map_offd=np.empty(nco, dtype=np.int64))
+        _chk(lib().pe_mat_download(self.h, _ptr(d["diag_i"]), _ptr(d["diag_j"]), _ptr(d["diag_a"]), _ptr(d["offd_i"]),
+                                   _ptr(d["offd_j"]) if no else None, _ptr(d["offd_a"]) if no else None,
+                                   _ptr(d["col_map_offd"]) if nco else None))
+        return d
+
     def transpose(self):
         out = Mat(self.ctx)
         _chk(lib().pe_mat_transpose(self.ctx.h, self.h, C.byref(out.h)))

@@ -652,6 +652,7 @@ int pe_build_row_blocks(pe_ctx *ctx, DevCSR &m, const std::vector<int32_t> *forc
 void pe_mat_values_changed(pe_mat *A)
 {
     if (A->T) { pe_mat_free(A->T); A->T = nullptr; }
+    if (A->offdT_built) { devcsr_free(A->offdT); A->offdT_built = false; }
     for (DevCSR *m : {&A->diag, &A->offd})
     {
         if (m->sell) { pe_sell_free(*m->sell); delete m->sell; m->sell = nullptr; }
@@ -723,6 +724,8 @@ extern "C" int pe_mat_upload(pe_ctx *ctx, const pe_parcsr_host *H, pe_mat **out)
         PE_CUDA(cudaMalloc(&M->send_buf_d, sizeof(double) * (size_t)(nsend > 0 ? nsend : 1)));
     }
     M->tpr = pe_choose_tpr(M->diag.nnz + M->offd.nnz, M->diag.nrows);
+    M->distributed = ctx->nranks > 1 && (H->global_num_rows != H->num_rows || H->global_num_cols != H->num_cols_diag ||
+                                         H->num_cols_offd > 0 || H->num_sends > 0);
     PE_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = M;
     return 0;
@@ -753,6 +756,15 @@ extern "C" int pe_mat_info(const pe_mat *A, int32_t *num_rows, int32_t *num_cols
     return 0;
 }
 
+extern "C" int pe_mat_global_info(const pe_mat *A, int64_t *gr, int64_t *gc, int64_t *fr, int64_t *fc)
+{
+    if (gr) *gr = A->global_num_rows;
+    if (gc) *gc = A->global_num_cols;
+    if (fr) *fr = A->first_row_index;
+    if (fc) *fc = A->first_col_diag;
+    return 0;
+}
+
 extern "C" int pe_mat_download(const pe_mat *A, int32_t *diag_i, int32_t *diag_j, double *diag_data,
                                int32_t *offd_i, int32_t *offd_j, double *offd_data,
                                int64_t *col_map_offd)
@@ -780,6 +792,10 @@ extern "C" int pe_mat_free(pe_mat *A)
     if (A->send_buf_d) cudaFree(A->send_buf_d);
     if (A->x_ext_d) cudaFree(A->x_ext_d);
     if (A->T) pe_mat_free(A->T);
+    devcsr_free(A->offdT);
+    if (A->unpack_rows_d) cudaFree(A->unpack_rows_d);
+    if (A->unpack_I_d) cudaFree(A->unpack_I_d);
+    if (A->unpack_pos_d) cudaFree(A->unpack_pos_d);
     delete A;
     return 0;
 }
@@ -831,4 +847,30 @@ int pe_halo_wait(pe_mat *A)
     if (c->nranks == 1) return 0;
     PE_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
     return 0;
+}
+
+// reverse exchange (MatvecT): the partial sums in x_ext_d travel to the owners of the ghost
+// columns (recv_procs), land in send_buf_d (slots ordered like send_map_elmts) and are added to y.
+int pe_reverse_halo_add(pe_mat *A, double alpha, double *y_d)
+{
+    pe_ctx *c = A->ctx;
+    if (c->nranks == 1) return 0;
+    int nsend = A->send_map_starts.empty() ? 0 : A->send_map_starts.back();
+    int nrecv = A->recv_vec_starts.empty() ? 0 : A->recv_vec_starts.back();
+    if (nsend == 0 && nrecv == 0) return 0;
+    PE_CUDA(cudaEventRecord(c->ev_pack, c->stream));
+    PE_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+    PE_NCCL(g_nccl.GroupStart());
+    for (size_t r = 0; r < A->recv_procs.size(); ++r) {
+        int lo = A->recv_vec_starts[r], hi = A->recv_vec_starts[r + 1];
+        PE_NCCL(g_nccl.Send(A->x_ext_d + lo, (size_t)(hi - lo), PE_NCCL_FLOAT64, A->recv_procs[r], c->nccl, c->comm_stream));
+    }
+    for (size_t s = 0; s < A->send_procs.size(); ++s) {
+        int lo = A->send_map_starts[s], hi = A->send_map_starts[s + 1];
+        PE_NCCL(g_nccl.Recv(A->send_buf_d + lo, (size_t)(hi - lo), PE_NCCL_FLOAT64, A->send_procs[s], c->nccl, c->comm_stream));
+    }
+    PE_NCCL(g_nccl.GroupEnd());
+    PE_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+    PE_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+    return pe_launch_unpack_add(c, A, alpha, y_d);
 }

@@ -85,6 +85,7 @@ struct pe_ctx {
     bool capturing = false;
     pe_recorder *rec = nullptr;          // non-null while a program is being recorded
     double pending_bytes = 0.0;          // algorithmic bytes announced by the last pe_prof_begin
+    const struct pe_host_comm *hcomm = nullptr;   // setup-time host communicator (borrowed)
     // optional per-kernel CUDA-event profiling (bench.py roofline): id 0 SpMV, 1 GS set, 2 Jacobi
     bool prof = false;
     struct ProfRec { int id; double bytes; cudaEvent_t e0, e1; };
@@ -169,9 +170,19 @@ struct pe_mat {
     int32_t *send_map_d = nullptr;
     double *send_buf_d = nullptr;
     double *x_ext_d = nullptr;
-    pe_mat *T = nullptr;     // cached explicit transpose (owned)
+    pe_mat *T = nullptr;     // cached explicit transpose (owned); distributed: transpose of the diag block
     int tpr = 0;             // threads per row chosen for SpMV (power of two <= 32)
+    // multi-rank: rows/columns are a slice of a global matrix (set at upload)
+    bool distributed = false;
+    DevCSR offdT;            // transpose of the offd block (ghost col x local row), built on first MatvecT
+    bool offdT_built = false, unpack_built = false;
+    int n_unpack = 0;        // reverse exchange: distinct target rows, CSR of receive-buffer slots per row
+    int *unpack_rows_d = nullptr, *unpack_I_d = nullptr, *unpack_pos_d = nullptr;
 };
+int pe_rap_distributed(pe_ctx *ctx, const pe_mat *A, const pe_mat *P, pe_mat **Ac);
+int pe_spmv_t_distributed(pe_ctx *ctx, double alpha, pe_mat *A, const pe_vec *x, double beta, pe_vec *y);
+int pe_launch_unpack_add(pe_ctx *ctx, pe_mat *A, double alpha, double *y_d);
+int pe_reverse_halo_add(pe_mat *A, double alpha, double *y_d);
 
 // ---- internal helpers used across translation units
 int pe_halo_exchange(pe_mat *A, const double *x_d);   // fills A->x_ext_d (no-op single rank)

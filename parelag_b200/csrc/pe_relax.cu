@@ -475,7 +475,7 @@ static int spmv_full(pe_ctx *ctx, pe_mat *A, double alpha, const double *x, doub
         PE_TRY(pe_halo_wait(A));
         return pe_launch_spmv(ctx, A->offd, nullptr, pe_choose_tpr(A->offd.nnz, A->offd.nrows), alpha, A->x_ext_d, nullptr, 1.0, yout, yout);
     }
-    if (ctx->nranks > 1) PE_TRY(pe_halo_exchange(A, x));
+    if (ctx->nranks > 1) { PE_TRY(pe_halo_exchange(A, x)); PE_TRY(pe_halo_wait(A)); }
     return pe_launch_spmv(ctx, A->diag, nullptr, A->tpr, alpha, x, nullptr, beta, yin, yout);
 }
 

@@ -333,7 +333,12 @@ extern "C" int pe_spgemm(pe_ctx *ctx, const pe_mat *A, const pe_mat *B, pe_mat *
 
 extern "C" int pe_rap(pe_ctx *ctx, const pe_mat *R, const pe_mat *A, const pe_mat *P, pe_mat **Ac)
 {
-    PE_CHECK(A->offd.nnz == 0 && P->offd.nnz == 0, "pe_rap: distributed RAP not supported yet (local blocks only)");
+    if (A->distributed || P->distributed)
+    {
+        PE_CHECK(A->distributed && P->distributed, "pe_rap: A and P must both be distributed matrices");
+        PE_CHECK(!R || R == P, "pe_rap: the distributed product supports R == P only");
+        return pe_rap_distributed(ctx, A, P, Ac);
+    }
     const pe_mat *Rm = R ? R : P;
     PE_CHECK(Rm->diag.nrows == A->diag.nrows && A->diag.ncols == P->diag.nrows, "pe_rap: size mismatch");
     DevCSR AP, Rt, C;

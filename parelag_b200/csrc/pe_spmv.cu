@@ -159,7 +159,7 @@ extern "C" int pe_spmv(pe_ctx *ctx, double alpha, pe_mat *A, const pe_vec *x, do
         PE_TRY(pe_launch_spmv(ctx, A->offd, nullptr, otpr, alpha, A->x_ext_d, nullptr, 1.0, y->d, y->d));
         return 0;
     }
-    if (ctx->nranks > 1) PE_TRY(pe_halo_exchange(A, x->d));  // others may need our values
+    if (ctx->nranks > 1) { PE_TRY(pe_halo_exchange(A, x->d)); PE_TRY(pe_halo_wait(A)); }  // others may need our values
     return pe_launch_spmv(ctx, A->diag, nullptr, A->tpr, alpha, x->d, nullptr, beta, y->d, y->d);
 }
 
@@ -173,7 +173,7 @@ extern "C" int pe_residual(pe_ctx *ctx, pe_mat *A, const pe_vec *x, const pe_vec
         int otpr = pe_choose_tpr(A->offd.nnz, A->offd.nrows);
         return pe_launch_spmv(ctx, A->offd, nullptr, otpr, -1.0, A->x_ext_d, nullptr, 1.0, r->d, r->d);
     }
-    if (ctx->nranks > 1) PE_TRY(pe_halo_exchange(A, x->d));
+    if (ctx->nranks > 1) { PE_TRY(pe_halo_exchange(A, x->d)); PE_TRY(pe_halo_wait(A)); }
     return pe_launch_spmv(ctx, A->diag, nullptr, A->tpr, -1.0, x->d, nullptr, 1.0, b->d, r->d);
 }
 
@@ -247,6 +247,7 @@ extern "C" int pe_mat_transpose(pe_ctx *ctx, const pe_mat *A, pe_mat **out)
 extern "C" int pe_spmv_t(pe_ctx *ctx, double alpha, pe_mat *A, const pe_vec *x, double beta, pe_vec *y)
 {
     PE_CHECK(x->n == A->diag.nrows && y->n == A->diag.ncols, "pe_spmv_t: size mismatch");
+    if (A->distributed) return pe_spmv_t_distributed(ctx, alpha, A, x, beta, y);
     if (!A->T) PE_TRY(pe_mat_transpose(ctx, A, &A->T));
     return pe_spmv(ctx, alpha, A->T, x, beta, y);
 }

@@ -10,6 +10,7 @@
 // element/facet/ridge mass matrices and the dof functionals of the cochain projector.
 // Single rank (dof == true dof).
 #include "amge_coarsen.hpp"
+#include "amge_par.hpp"
 #include "parelag_b200_local.h"
 #include <cstring>
 
@@ -444,7 +445,25 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchy(int nx, i
                                                                         const double *alpha, const double *beta, int jstart,
                                                                         int nlevels, double svd_tol)
 {
+    return BuildHexSequenceHierarchyPar(nullptr, nullptr, nx, ny, nz, Lx, Ly, Lz, alpha, beta, jstart, nlevels, svd_tol);
+}
+
+std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const pe_host_comm *comm, const int *procs, int nx, int ny, int nz,
+                                                                           double Lx, double Ly, double Lz, const double *alpha,
+                                                                           const double *beta, int jstart, int nlevels, double svd_tol)
+{
+    const bool parallel = comm && comm->size > 1;
+    const int one[3] = {1, 1, 1};
+    BoxDecomposition box(parallel ? procs : one, parallel ? comm->rank : 0, nx, ny, nz);
+    PARELAG_TEST_FOR_EXCEPTION(parallel && box.nranks() != comm->size, std::runtime_error,
+                               "BuildHexSequenceHierarchyPar: the process grid does not match the communicator size");
+    // Lx, Ly, Lz: extent of THIS rank's box (every box has the same shape)
     StructuredHexMesh mesh(nx, ny, nz, Lx, Ly, Lz);
+    if (parallel)
+    {
+        for (int a = 0; a < 3; ++a) for (int sd = 0; sd < 2; ++sd) mesh.iface[2 * a + sd] = box.interface(a, sd);
+        mesh.x0 = Lx * box.r[0]; mesh.y0 = Ly * box.r[1]; mesh.z0 = Lz * box.r[2];
+    }
     std::vector<std::shared_ptr<AgglomeratedTopology>> topo(nlevels);
     {
         Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level 0");
@@ -477,13 +496,29 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchy(int nx, i
             seq[l]->data = std::make_shared<SequenceData>();
             seq[l]->data->topo = topo[l];
         }
-        return seq;
     }
-    for (int l = 0; l + 1 < nlevels; ++l)
+    else
+        for (int l = 0; l + 1 < nlevels; ++l)
+        {
+            Timer t = TimeManager::AddTimer("DeRhamSequence Construction -- Level " + std::to_string(l + 1));
+            seq[l]->SetSVDTol(svd_tol);
+            seq[l + 1] = seq[l]->Coarsen();
+        }
+    if (parallel)
     {
-        Timer t = TimeManager::AddTimer("DeRhamSequence Construction -- Level " + std::to_string(l + 1));
-        seq[l]->SetSVDTol(svd_tol);
-        seq[l + 1] = seq[l]->Coarsen();
+        // entity and dof sharing on every level (SharingMap); levels without dof handlers
+        // (topology-only mode) get the entity tables only
+        Timer t = TimeManager::AddTimer("SharingMap construction");
+        std::vector<EntitySharing> ent = FineEntitySharing(box);
+        for (int l = 0; l < nlevels; ++l)
+        {
+            if (l > 0) ent = CoarseEntitySharing(*topo[l - 1], ent);
+            seq[l]->SetComm(comm);
+            seq[l]->data->entity_sharing = ent;
+            if (svd_tol < 0.0 && l > 0) continue;
+            for (int j = jstart; j < 4; ++j)
+                seq[l]->SetDofTrueDof(j, BuildDofSharingMap(comm, *seq[l]->data->dof[j], ent, l == 0));
+        }
     }
     return seq;
 }

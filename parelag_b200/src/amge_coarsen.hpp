@@ -11,4 +11,11 @@ namespace parelag
 std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchy(int nx, int ny, int nz, double Lx, double Ly, double Lz,
                                                                         const double *alpha, const double *beta, int jstart,
                                                                         int nlevels, double svd_tol);
+/// The same on one box of a P[0] x P[1] x P[2] box decomposition (one rank <-> one box <-> one GPU,
+/// the reference's one-MPI-rank-per-partition model): nx, ny, nz and Lx, Ly, Lz describe THIS
+/// rank's box; every rank coarsens its own box (elements never migrate) and the levels are glued
+/// by the dof <-> true-dof SharingMaps built at the end (amge_par.hpp).  comm == NULL: serial.
+std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const pe_host_comm *comm, const int *procs, int nx, int ny, int nz,
+                                                                           double Lx, double Ly, double Lz, const double *alpha,
+                                                                           const double *beta, int jstart, int nlevels, double svd_tol);
 } // namespace parelag

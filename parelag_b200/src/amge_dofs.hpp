@@ -198,6 +198,20 @@ public:
     std::vector<int> sep;
 };
 
+/// global key + holders of every local entity of one codimension on one level
+struct EntitySharing
+{
+    std::vector<int64_t> key;
+    std::vector<int32_t> sI{0}, sJ;
+    void push(int64_t k, const std::vector<int32_t> &ranks)
+    {
+        key.push_back(k);
+        sJ.insert(sJ.end(), ranks.begin(), ranks.end());
+        std::sort(sJ.begin() + sI.back(), sJ.end());
+        sI.push_back((int32_t)sJ.size());
+    }
+};
+
 /// everything one level of the sequence owns besides P_/D_ (see parelag_sequence.hpp)
 struct SequenceData
 {
@@ -212,5 +226,6 @@ struct SequenceData
     std::vector<double> facet_area, ridge_length;
     double svd_tol = 1e-9;
     std::map<std::string, int64_t> stats;
+    std::vector<EntitySharing> entity_sharing;   // multi-rank: per codimension (amge_par.hpp)
 };
 } // namespace parelag

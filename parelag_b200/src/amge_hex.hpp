@@ -17,8 +17,15 @@ struct StructuredHexMesh
 {
     int nx, ny, nz;
     double hx, hy, hz;
+    /// multi-rank: this mesh is one box of a larger one.  iface[2*axis+side]: that box face is an
+    /// interface with another rank -- its facets carry the pseudo boundary attribute 7 + 2*axis + side
+    /// (never essential; it only makes the minimal intersection sets split there, amge_par.hpp);
+    /// x0/y0/z0: origin of the box
+    bool iface[6] = {false, false, false, false, false, false};
+    double x0 = 0.0, y0 = 0.0, z0 = 0.0;
     StructuredHexMesh(int nx_, int ny_, int nz_, double Lx = 1.0, double Ly = 1.0, double Lz = 1.0)
         : nx(nx_), ny(ny_), nz(nz_), hx(Lx / nx_), hy(Ly / ny_), hz(Lz / nz_) {}
+    bool any_interface() const { for (bool b : iface) if (b) return true; return false; }
     int64_t nel() const { return (int64_t)nx * ny * nz; }
     int nfx() const { return (nx + 1) * ny * nz; }
     int nfy() const { return nx * (ny + 1) * nz; }
@@ -69,11 +76,13 @@ struct StructuredHexMesh
         { r = {{vx(i, j, k), -1.0}, {vx(i, j + 1, k), 1.0}}; push_row(B2, r); }
         for (int k = 0; k < nz; ++k) for (int j = 0; j <= ny; ++j) for (int i = 0; i <= nx; ++i)
         { r = {{vx(i, j, k), -1.0}, {vx(i, j, k + 1), 1.0}}; push_row(B2, r); }
-        fb.nrows = nf(); fb.ncols = 6;
+        fb.nrows = nf(); fb.ncols = any_interface() ? 12 : 6;
         std::vector<int> attr(nf(), -1);
-        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) { attr[fx(0, j, k)] = 4; attr[fx(nx, j, k)] = 2; }
-        for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) { attr[fy(i, 0, k)] = 1; attr[fy(i, ny, k)] = 3; }
-        for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) { attr[fz(i, j, 0)] = 0; attr[fz(i, j, nz)] = 5; }
+        const int ax0 = iface[0] ? 6 : 4, ax1 = iface[1] ? 7 : 2, ay0 = iface[2] ? 8 : 1, ay1 = iface[3] ? 9 : 3;
+        const int az0 = iface[4] ? 10 : 0, az1 = iface[5] ? 11 : 5;
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) { attr[fx(0, j, k)] = ax0; attr[fx(nx, j, k)] = ax1; }
+        for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) { attr[fy(i, 0, k)] = ay0; attr[fy(i, ny, k)] = ay1; }
+        for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) { attr[fz(i, j, 0)] = az0; attr[fz(i, j, nz)] = az1; }
         fb.I = {0};
         for (int f = 0; f < nf(); ++f)
         {
@@ -210,9 +219,9 @@ inline void BuildFineHexSequence(const StructuredHexMesh &mesh, const std::share
         {
             const int v = mesh.vx(i, j, k);
             S.targets[0][v] = 1.0;
-            S.targets[0][(size_t)n + v] = k * hz;
-            S.targets[0][(size_t)2 * n + v] = j * hy;
-            S.targets[0][(size_t)3 * n + v] = i * hx;
+            S.targets[0][(size_t)n + v] = mesh.z0 + k * hz;
+            S.targets[0][(size_t)2 * n + v] = mesh.y0 + j * hy;
+            S.targets[0][(size_t)3 * n + v] = mesh.x0 + i * hx;
         }
     }
 }

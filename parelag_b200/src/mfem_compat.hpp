@@ -287,6 +287,8 @@ public:
     int64_t N() const { return width; }
     int64_t NNZ() const { return nnz_diag_ + nnz_offd_; }
     pe_mat *Handle() const { return A_; }
+    /// give up ownership of the device matrix
+    pe_mat *Release() { pe_mat *a = A_; A_ = nullptr; return a; }
 
 private:
     pe_mat *A_ = nullptr;

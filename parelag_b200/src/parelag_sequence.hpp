@@ -13,6 +13,7 @@
 #include <memory>
 #include <vector>
 #include "parelag_core.hpp"
+#include "par_host.hpp"
 
 namespace parelag
 {
@@ -66,12 +67,35 @@ private:
 class DeRhamSequence : public std::enable_shared_from_this<DeRhamSequence>
 {
 public:
-    explicit DeRhamSequence(int nforms) : nForms_(nforms), Dof_(nforms), P_(nforms), D_(nforms), RawDof_(nforms, nullptr) {}
+    explicit DeRhamSequence(int nforms) : nForms_(nforms), Dof_(nforms), P_(nforms), D_(nforms), RawDof_(nforms, nullptr), DofTrueDof_(nforms) {}
     virtual ~DeRhamSequence() = default;
 
     int GetNumberOfForms() const noexcept { return nForms_; }
     int GetNumberOfDofs(int jform) const { auto d = GetDofHandler(jform); return d ? d->GetNDofs() : 0; }
-    int GetNumberOfTrueDofs(int jform) const { return GetNumberOfDofs(jform); }
+    int GetNumberOfTrueDofs(int jform) const
+    {
+        return DofTrueDof_.at(jform) ? DofTrueDof_[jform]->GetTrueLocalSize() : GetNumberOfDofs(jform);
+    }
+    /// multi-rank: dof <-> true dof map of a form (DofHandler::GetDofTrueDof) and the host communicator
+    void SetDofTrueDof(int jform, std::shared_ptr<par::SharingMap> m) { DofTrueDof_.at(jform) = std::move(m); }
+    const par::SharingMap *GetDofTrueDof(int jform) const { return DofTrueDof_.at(jform).get(); }
+    void SetComm(const pe_host_comm *c) { Comm_ = c; }
+    const pe_host_comm *GetComm() const { return Comm_; }
+    bool IsParallel() const { return Comm_ && Comm_->size > 1; }
+    /// IgnoreNonLocalRange(range map, A, domain map) (SharingMap.cpp:930-946): the rows this rank owns,
+    /// columns in global true numbering, as a device ParCSR matrix
+    std::unique_ptr<mfem::HypreParMatrix> IgnoreNonLocalRange(const par::SharingMap &range, const HostCSR &A, const par::SharingMap &domain) const
+    {
+        pe_parcsr_owned *M = nullptr;
+        PE_CALL(pe_par_assemble(Comm_, 1, A.nrows, A.ncols, A.I.data(), A.J.data(), A.A.data(), range.gid.data(), range.owner.data(),
+                                domain.gid.data(), domain.owner.data(), range.start, range.start + range.ntrue, range.global,
+                                domain.start, domain.start + domain.ntrue, domain.global, &M));
+        std::unique_ptr<mfem::HypreParMatrix> out;
+        try { out = make_unique<mfem::HypreParMatrix>(*pe_parcsr_owned_view(M)); }
+        catch (...) { pe_parcsr_owned_free(M); throw; }
+        pe_parcsr_owned_free(M);
+        return out;
+    }
     DofHandler *GetDofHandler(int jform) const { return RawDof_.at(jform) ? RawDof_[jform] : Dof_.at(jform).get(); }
     void SetDofHandler(int jform, std::unique_ptr<DofHandler> d) { Dof_.at(jform) = std::move(d); }
 
@@ -104,11 +128,13 @@ public:
         coarser->GetDofHandler(jform)->MarkDofsOnSelectedBndr(ess_label, marker);
         for (size_t k = 0; k < P.J.size(); ++k)
             if (marker[P.J[k]]) P.A[k] = 0.0;
+        if (IsParallel()) return IgnoreNonLocalRange(*DofTrueDof_.at(jform), P, *coarser->DofTrueDof_.at(jform));
         return make_unique<mfem::HypreParMatrix>(P.View());
     }
     std::unique_ptr<mfem::HypreParMatrix> ComputeTrueP(int jform) const
     {
         PARELAG_TEST_FOR_EXCEPTION(!P_.at(jform), std::runtime_error, "DeRhamSequence::ComputeTrueP(): P_[" << jform << "] is not available");
+        if (IsParallel()) return IgnoreNonLocalRange(*DofTrueDof_.at(jform), *P_[jform], *CoarserSequence_.lock()->DofTrueDof_.at(jform));
         return make_unique<mfem::HypreParMatrix>(P_[jform]->View());
     }
     /// ComputeDerivativeOperator(jform, ess) + IgnoreNonLocalRange (DeRhamSequence.cpp:1082-1099,1225-1239)
@@ -121,11 +147,13 @@ public:
         GetDofHandler(jform)->MarkDofsOnSelectedBndr(ess_label, marker);
         for (size_t k = 0; k < D.J.size(); ++k)
             if (marker[D.J[k]]) D.A[k] = 0.0;
+        if (IsParallel()) return IgnoreNonLocalRange(*DofTrueDof_.at(jform + 1), D, *DofTrueDof_.at(jform));
         return make_unique<mfem::HypreParMatrix>(D.View());
     }
     std::unique_ptr<mfem::HypreParMatrix> ComputeTrueD(int jform) const
     {
         PARELAG_TEST_FOR_EXCEPTION(!D_.at(jform), std::runtime_error, "DeRhamSequence::ComputeTrueD(): D_[" << jform << "] is not available");
+        if (IsParallel()) return IgnoreNonLocalRange(*DofTrueDof_.at(jform + 1), *D_[jform], *DofTrueDof_.at(jform));
         return make_unique<mfem::HypreParMatrix>(D_[jform]->View());
     }
 
@@ -146,5 +174,7 @@ protected:
     std::vector<std::shared_ptr<HostCSR>> P_, D_;
     std::weak_ptr<DeRhamSequence> CoarserSequence_, FinerSequence_;
     std::vector<DofHandler *> RawDof_;              // handlers owned by `data` (Coarsen path)
+    std::vector<std::shared_ptr<par::SharingMap>> DofTrueDof_;   // per form; null on a single rank
+    const pe_host_comm *Comm_ = nullptr;
 };
 } // namespace parelag

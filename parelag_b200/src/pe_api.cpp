@@ -18,6 +18,8 @@ struct pe_solver
 };
 
 static std::unique_ptr<mpi_session> g_session;
+static pe_host_comm g_host_comm{};       // copy of the caller's table (function pointers + user)
+static bool g_have_host_comm = false;
 
 #define API_TRY try {
 #define API_CATCH                                                      \
@@ -40,6 +42,59 @@ extern "C" int pe_api_session_destroy(void)
 }
 extern "C" pe_ctx *pe_api_session_ctx(void) { return Device::Ctx(); }
 
+extern "C" int pe_api_session_set_host_comm(const pe_host_comm *comm)
+{
+    API_TRY
+    PARELAG_TEST_FOR_EXCEPTION(!comm || !comm->allgather || !comm->alltoallv, std::runtime_error, "pe_api_session_set_host_comm: incomplete callback table");
+    g_host_comm = *comm;
+    g_have_host_comm = true;
+    if (Device::Ctx()) PE_CALL(pe_ctx_set_host_comm(Device::Ctx(), &g_host_comm));
+    API_CATCH
+}
+extern "C" int pe_api_hexsequence_create_par(const int32_t *procs, int nx, int ny, int nz, double Lx, double Ly, double Lz,
+                                             const double *alpha, const double *beta, int jstart, int nlevels, double svd_tol,
+                                             pe_sequence **out)
+{
+    API_TRY
+    PARELAG_TEST_FOR_EXCEPTION(!g_have_host_comm, std::runtime_error, "pe_api_hexsequence_create_par: call pe_api_session_set_host_comm first");
+    auto s = new pe_sequence();
+    const int P[3] = {procs[0], procs[1], procs[2]};
+    s->levels = BuildHexSequenceHierarchyPar(&g_host_comm, P, nx, ny, nz, Lx, Ly, Lz, alpha, beta, jstart, nlevels, svd_tol);
+    *out = s;
+    API_CATCH
+}
+extern "C" int pe_api_sequence_get_dofmap(pe_sequence *s, int level, int form, int32_t *ndofs, int64_t *gid, int32_t *owner,
+                                          int64_t *key, int64_t *true_start, int64_t *true_count, int64_t *global_count)
+{
+    API_TRY
+    auto &seq = *s->levels.at(level);
+    const par::SharingMap *m = seq.GetDofTrueDof(form);
+    PARELAG_TEST_FOR_EXCEPTION(!m, std::runtime_error, "pe_api_sequence_get_dofmap: no dof <-> true dof map on level " << level << ", form " << form);
+    if (ndofs) *ndofs = m->GetLocalSize();
+    if (gid) std::copy(m->gid.begin(), m->gid.end(), gid);
+    if (owner) std::copy(m->owner.begin(), m->owner.end(), owner);
+    if (key) std::copy(m->key.begin(), m->key.end(), key);
+    if (true_start) *true_start = m->start;
+    if (true_count) *true_count = m->ntrue;
+    if (global_count) *global_count = m->global;
+    API_CATCH
+}
+/// ComputeTrueP / ComputeTrueD as device ParCSR matrices (what = "P" or "D")
+extern "C" int pe_api_sequence_true_operator(pe_sequence *s, int level, const char *what, int form, const int32_t *ess_attr, int nattr,
+                                             pe_mat **out)
+{
+    API_TRY
+    auto &seq = *s->levels.at(level);
+    std::unique_ptr<mfem::HypreParMatrix> M;
+    if (ess_attr)
+    {
+        mfem::Array<int> ess(ess_attr, nattr);
+        M = std::string(what) == "P" ? seq.ComputeTrueP(form, ess) : seq.ComputeTrueD(form, ess);
+    }
+    else M = std::string(what) == "P" ? seq.ComputeTrueP(form) : seq.ComputeTrueD(form);
+    *out = M->Release();
+    API_CATCH
+}
 extern "C" int pe_api_sequence_create(int nforms, int nlevels, pe_sequence **out)
 {
     API_TRY
@@ -236,6 +291,25 @@ extern "C" int pe_api_sequence_assemble_system(pe_sequence *s, int level, int fo
         mfem::Array<int> ess(ess_attr, nattr), marker(seq.GetNumberOfDofs(form));
         seq.GetDofHandler(form)->MarkDofsOnSelectedBndr(ess, marker);
         PE_CALL(pe_mat_eliminate_rowcol(ctx, A, marker.GetData()));
+    }
+    if (seq.IsParallel())
+    {
+        // A = Assemble(dofTrueDof, spA, dofTrueDof) (examples/MultigridTest2Form.cpp:560): the local
+        // contributions of all holders of a shared dof are summed on its owner
+        const par::SharingMap &map = *seq.GetDofTrueDof(form);
+        int32_t nr = 0, nc = 0; int64_t nnz = 0;
+        PE_CALL(pe_mat_info(A, &nr, &nc, nullptr, &nnz, nullptr));
+        HostCSR L;
+        L.nrows = nr; L.ncols = nc; L.I.resize(nr + 1); L.J.resize(nnz); L.A.resize(nnz);
+        PE_CALL(pe_mat_download(A, L.I.data(), L.J.data(), L.A.data(), nullptr, nullptr, nullptr, nullptr));
+        pe_mat_free(A); A = nullptr;
+        pe_parcsr_owned *M = nullptr;
+        PE_CALL(pe_par_assemble(seq.GetComm(), 0, L.nrows, L.ncols, L.I.data(), L.J.data(), L.A.data(), map.gid.data(), map.owner.data(),
+                                map.gid.data(), map.owner.data(), map.start, map.start + map.ntrue, map.global,
+                                map.start, map.start + map.ntrue, map.global, &M));
+        const int rc = pe_mat_upload(ctx, pe_parcsr_owned_view(M), &A);
+        pe_parcsr_owned_free(M);
+        PE_CALL(rc);
     }
     *out = A;
     API_CATCH

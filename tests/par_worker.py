@@ -1,0 +1,130 @@
+"""Worker of the world_size-2 host-logic tests (launched by tests/test_par_cpu.py through
+torch.distributed.run, gloo backend, CPU only): SharingMap numbering, box-decomposed topology
+hierarchy, Assemble / IgnoreNonLocalRange into hypre's ParCSR layout, comm package -- all checked
+against the oracle's single-domain objects on the undecomposed mesh."""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from parelag_b200 import api, par          # noqa: E402
+from oracle import amge, drivers           # noqa: E402
+
+
+def gather(obj):
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, size = dist.get_rank(), dist.get_world_size()
+    comm = par.HostComm()
+    api.set_host_comm(comm)
+
+    # ---- T1: true numbering of shared items
+    keys = [100, 101, 102, 200 + rank]                      # 100..102 held by both ranks, one private item each
+    sharers = [[0, 1], [0, 1], [0, 1], [rank]]
+    if rank == 1:
+        keys = keys[::-1]; sharers = sharers[::-1]           # different local order
+    gid, owner, start, cnt, tot = par.number_items(comm, keys, sharers)
+    assert tot == 5 and cnt == (4 if rank == 0 else 1), (cnt, tot)
+    allk = gather(dict(zip(keys, gid.tolist())))
+    assert all(allk[0][k] == allk[1][k] for k in (100, 101, 102))
+    assert sorted(set(allk[0].values()) | set(allk[1].values())) == list(range(5))
+    assert all(o == 0 for k, o in zip(keys, owner) if k < 200)
+
+    # ---- T2: box-decomposed hierarchy (topology + fine dof maps), 2 x 1 x 1 boxes of 4^3 hexahedra
+    n, lev = 4, 3
+    procs = (2, 1, 1)
+    S = api.Sequence.hex_par(procs, (n, n, n), lev, L=(1.0, 1.0, 1.0), jstart=1, svd_tol=-1.0)
+    N = (2 * n, n, n)
+    expect = {1: N[0] * (N[1] + 1) * (N[2] + 1) + (N[0] + 1) * N[1] * (N[2] + 1) + (N[0] + 1) * (N[1] + 1) * N[2],
+              2: (N[0] + 1) * N[1] * N[2] + N[0] * (N[1] + 1) * N[2] + N[0] * N[1] * (N[2] + 1),
+              3: N[0] * N[1] * N[2]}
+    maps = {}
+    for form in (1, 2, 3):
+        m = S.dofmap(0, form)
+        maps[form] = m
+        assert m["nglobal"] == expect[form], (form, m["nglobal"], expect[form])
+        counts = gather(m["ntrue"])
+        assert sum(counts) == expect[form]
+        assert m["start"] == sum(counts[:rank])
+        both = gather(dict(zip(m["key"].tolist(), m["gid"].tolist())))
+        for k, g in both[rank].items():
+            if k in both[1 - rank]:
+                assert both[1 - rank][k] == g
+        allg = set(both[0].values()) | set(both[1].values())
+        assert allg == set(range(expect[form]))
+        # interface faces / edges are owned by rank 0
+        shared = set(both[0]) & set(both[1])
+        assert len(shared) == {1: 2 * n * (n + 1), 2: n * n, 3: 0}[form]
+        assert all(m["owner"][i] == 0 for i, k in enumerate(m["key"].tolist()) if k in shared)
+    # pseudo boundary attribute on the interface: the coarse facets of both sides match one to one
+    FB = S.get_csr(1, "FB")
+    iface_attr = 7 if rank == 0 else 6                        # x+ face of rank 0, x- face of rank 1
+    ncf = int((FB.indices == iface_attr).sum())
+    assert ncf == (n // 2) ** 2 and FB.shape[1] == 12, (ncf, FB.shape)
+
+    # ---- T3: Assemble(dofTrueDof, A_local, dofTrueDof) == the single-domain operator
+    mesh_loc = amge.HexMesh(n, n, n, L=(1.0, 1.0, 1.0))
+    seq_loc = amge.fine_sequence(mesh_loc, jstart=1)
+    A_loc, _ = drivers.system_matrix(seq_loc, 2, np.zeros(6, dtype=np.int32))
+    m = maps[2]
+    rr = (m["start"], m["start"] + m["ntrue"])
+    M = par.assemble(comm, 0, A_loc, m["gid"], m["owner"], m["gid"], m["owner"], rr, m["nglobal"], rr, m["nglobal"])
+    d = M.arrays()
+    assert np.all(np.diff(d["col_map_offd"]) > 0)
+    _, blk = par.parcsr_rows_to_global(d)
+    blocks = gather((d["first_row"], blk))
+    A_true = sp.vstack([b for _, b in sorted(blocks, key=lambda t: t[0])]).tocsr()
+    mesh_g = amge.HexMesh(*N, L=(2.0, 1.0, 1.0))
+    seq_g = amge.fine_sequence(mesh_g, jstart=1)
+    A_g, _ = drivers.system_matrix(seq_g, 2, np.zeros(6, dtype=np.int32))
+    # true id -> global face number of the undecomposed mesh (the dof key carries it)
+    perm = np.empty(m["nglobal"], dtype=np.int64)
+    for mm in gather((m["gid"], (m["key"] >> 8) & ((1 << 52) - 1))):
+        perm[mm[0]] = mm[1]
+    Pm = sp.csr_matrix((np.ones(len(perm)), (np.arange(len(perm)), perm)), shape=(len(perm), len(perm)))
+    A_perm = (Pm.T @ A_true @ Pm).tocsr()
+    A_perm.sort_indices(); A_g.sort_indices()
+    assert np.array_equal(A_perm.indptr, A_g.indptr) and np.array_equal(A_perm.indices, A_g.indices)
+    assert np.abs(A_perm.data - A_g.data).max() <= 1e-13 * np.abs(A_g.data).max()
+    # comm package: what I receive is what the neighbour sends, ghost by ghost
+    sends = gather({int(p): (d["send_map_elmts"][d["send_map_starts"][k]:d["send_map_starts"][k + 1]] + d["first_col"]).tolist()
+                    for k, p in enumerate(d["send_procs"])})
+    for k, p in enumerate(d["recv_procs"]):
+        want = d["col_map_offd"][d["recv_vec_starts"][k]:d["recv_vec_starts"][k + 1]].tolist()
+        assert sends[int(p)][rank] == want
+    M.free()
+
+    # ---- T4: IgnoreNonLocalRange keeps the owner's rows only (D_2 : H(div) -> L2)
+    D = sp.csr_matrix(seq_loc.D[2])
+    m3 = maps[3]
+    Dm = par.assemble(comm, 1, D, m3["gid"], m3["owner"], m["gid"], m["owner"], (m3["start"], m3["start"] + m3["ntrue"]),
+                      m3["nglobal"], rr, m["nglobal"])
+    dd = Dm.arrays()
+    _, blk = par.parcsr_rows_to_global(dd)
+    D_true = sp.vstack([b for _, b in sorted(gather((dd["first_row"], blk)), key=lambda t: t[0])]).tocsr()
+    perm3 = np.empty(m3["nglobal"], dtype=np.int64)
+    for mm in gather((m3["gid"], (m3["key"] >> 8) & ((1 << 52) - 1))):
+        perm3[mm[0]] = mm[1]
+    P3 = sp.csr_matrix((np.ones(len(perm3)), (np.arange(len(perm3)), perm3)), shape=(len(perm3), len(perm3)))
+    D_perm = (P3.T @ D_true @ Pm).tocsr()
+    D_g = sp.csr_matrix(seq_g.D[2])
+    assert abs(D_perm - D_g).max() <= 1e-13 * abs(D_g).max()
+    Dm.free()
+    S.free()
+    dist.barrier()
+    if rank == 0:
+        print("PAR_WORKER_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
