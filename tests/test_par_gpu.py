@@ -1,0 +1,28 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box): tests/par_gpu_worker.py, one process per GPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_box_decomposed_hierarchy_matches_single_domain(nranks):
+    if _ngpus() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nranks, "--master-addr",
+           "127.0.0.1", "--master-port", str(29540 + nranks), os.path.join(ROOT, "tests", "par_gpu_worker.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "PAR_GPU_WORKER_OK" in r.stdout, r.stdout[-4000:] + r.stderr[-4000:]
