@@ -13,8 +13,10 @@ attributes essential.  A step = one application of the AMGe V-cycle
   python bench.py --gpus N --steps K --warmup W            (this implementation)
   python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
 
-N > 1: one process per GPU (torchrun); in this round every rank solves its own copy
-of the workload ("replicas", weak scaling, no data-path collective) -- see DESIGN.md.
+N > 1: one process per GPU (torchrun), one mesh box per GPU (2x1x1, 2x2x1, 2x2x2 boxes of n^3
+hexahedra each -- the 3DHdivWeakScaling layout, configs[4]): every rank coarsens its own box, the
+levels are glued by SharingMaps, and the V-cycle exchanges the ParCSR halo with NCCL send/recv
+(weak scaling: per-GPU work is fixed, value = global dofs / max-over-ranks time).
 """
 import argparse
 import json
@@ -185,7 +187,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=144, help="hexahedra per direction (144 -> 9.02M RT0 dofs)")
+    ap.add_argument("--size", "--n", dest="n", type=int, default=144, help="hexahedra per direction (144 -> 9.02M RT0 dofs)")
     ap.add_argument("--levels", type=int, default=5)
     ap.add_argument("--ordering", default="multicolor", choices=["multicolor", "natural"])
     ap.add_argument("--jstart", type=int, default=0, help="jformStart of the sequence (driver uses 0)")
@@ -223,22 +225,58 @@ def main():
         return float(t.item())
 
     from parelag_b200 import api, capi
-    # replicas: every rank owns an independent copy of the workload (no NCCL communicator needed)
-    ctx = api.session(rank=0, nranks=1, device=local_rank)
     n, levels = args.n, args.levels
+    procs = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world)
+    if procs is None:
+        raise SystemExit("bench.py: --gpus must be 1, 2, 4 or 8")
+    if world > 1:
+        # one box per GPU: the library's own NCCL communicator carries the data path, a gloo group the
+        # setup-time host exchanges (MPI in the reference)
+        from parelag_b200 import par
+        ids = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx = api.session(rank=rank, nranks=world, device=local_rank, nccl_id=ids[0])
+        api.set_host_comm(par.HostComm(dist.new_group(backend="gloo")))
+    else:
+        ctx = api.session(rank=0, nranks=1, device=local_rank)
     api.lib().pe_api_timer_clear()
 
     # ---------------- setup (timed with the reference's timer names)
     t0 = time.perf_counter()
-    S = api.Sequence.hex((n, n, n), levels, jstart=args.jstart)
+    if world > 1:
+        S = api.Sequence.hex_par(procs, (n, n, n), levels, L=(1.0, 1.0, 1.0), jstart=args.jstart)
+    else:
+        S = api.Sequence.hex((n, n, n), levels, jstart=args.jstart)
     ctx.sync()
     t_coarsen = time.perf_counter() - t0
     t0 = time.perf_counter()
     A = S.assemble_system(ctx, 0, 2, ESS)
     ctx.sync()
     t_assemble = time.perf_counter() - t0
-    ndofs = A.info()[0]
-    nnz0 = A.info()[3]
+    ndofs = A.info()[0]                       # true dofs owned by this rank
+    nnz0 = A.info()[3] + A.info()[4]
+
+    def sum_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+    ndofs_global = int(round(sum_over_ranks(ndofs)))
+    peak, peak_src = peaks()
+    # ---------------- SpMV alone on the fine operator (the "SpMV HBM GB/s vs peak" part of the metric)
+    A2 = A
+    xs, ys = capi.Vec(ctx, data=np.random.default_rng(99 + rank).standard_normal(ndofs)), capi.Vec(ctx, ndofs)
+    for _ in range(3):
+        A2.spmv(xs, ys)
+    ctx.sync(); ctx.timer_start()
+    for _ in range(20):
+        A2.spmv(xs, ys)
+    ms_spmv = ctx.timer_stop() / 20
+    b_spmv = 12.0 * nnz0 + 4.0 * (ndofs + 1) + 16.0 * ndofs
+    spmv = {"ms": ms_spmv, "GBs": b_spmv / ms_spmv / 1e6, "frac_of_measured_peak": b_spmv / ms_spmv / 1e6 / peak,
+            "nnz": nnz0, "rows": ndofs}
+
     t0 = time.perf_counter()
     solver = api.Solver(api.library_xml(library(args.ordering)), "PCG with Auxiliary Space Preconditioner",
                         A, S, 0, 2, ESS)
@@ -285,7 +323,7 @@ def main():
     clocks = sampler.stop() if sampler else None
     ms = max_over_ranks(ms)
     ms_per_step = ms / args.steps
-    value = world * ndofs / (ms_per_step * 1e-3)
+    value = ndofs_global / (ms_per_step * 1e-3)
 
     # ---------------- roofline of the dominant kernel
     peak, peak_src = peaks()
@@ -353,8 +391,8 @@ def main():
         solver.prec_mult_device(r_dev, z_dev)
         capi._chk(capi.lib().pe_vec_download(z_dev.h, capi._ptr(x_np)))
     ms_e2e = max_over_ranks(ctx.timer_stop()) / args.steps
-    e2e = {"value": world * ndofs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-           "h2d_bytes_per_step": 8 * ndofs, "d2h_bytes_per_step": 8 * ndofs}
+    e2e = {"value": ndofs_global / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": 8 * ndofs_global, "d2h_bytes_per_step": 8 * ndofs_global}
 
     # ---------------- one full PCG solve (iterations, residual history) through host buffers
     bvec = rng.standard_normal(ndofs)
@@ -362,19 +400,6 @@ def main():
     x = solver.mult(bvec)
     t_solve = time.perf_counter() - t0
     hist, iters, conv = solver.history()
-
-    # ---------------- SpMV alone on the fine operator (the "SpMV HBM GB/s vs peak" part of the metric)
-    A2 = S.assemble_system(ctx, 0, 2, ESS)
-    xs, ys = capi.Vec(ctx, data=r_host), capi.Vec(ctx, ndofs)
-    for _ in range(3):
-        A2.spmv(xs, ys)
-    ctx.sync(); ctx.timer_start()
-    for _ in range(20):
-        A2.spmv(xs, ys)
-    ms_spmv = ctx.timer_stop() / 20
-    b_spmv = 12.0 * nnz0 + 4.0 * (ndofs + 1) + 16.0 * ndofs
-    spmv = {"ms": ms_spmv, "GBs": b_spmv / ms_spmv / 1e6, "frac_of_measured_peak": b_spmv / ms_spmv / 1e6 / peak,
-            "nnz": nnz0, "rows": ndofs}
 
     line = None
     if rank == 0:
@@ -409,12 +434,18 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "MultigridTest2Form (configs[1]): H(div) A=M2+D2^T M3 D2, %d^3 hexahedra, "
-                                       "%d RT0 dofs, %d-level AMGe, Hiptmair(l1-GS,l1-GS) %s order, PCG-GS coarse solver"
-                                       % (n, ndofs, nlev, args.ordering),
+                "config": {"workload": ("MultigridTest2Form (configs[1]): H(div) A=M2+D2^T M3 D2, %d^3 hexahedra, "
+                                        "%d RT0 dofs, %d-level AMGe, Hiptmair(l1-GS,l1-GS) %s order, PCG-GS coarse solver"
+                                        % (n, ndofs, nlev, args.ordering)) if world == 1 else
+                                       ("3DHdivWeakScaling layout (configs[4]): %dx%dx%d boxes of %d^3 hexahedra, one box per GPU, "
+                                        "H(div) A=M2+D2^T M3 D2, %d RT0 true dofs in total, %d-level AMGe, Hiptmair(hybrid l1-GS,"
+                                        "hybrid l1-GS) %s order, PCG-GS coarse solver, NCCL ParCSR halo exchange"
+                                        % (procs + (n, ndofs_global, nlev, args.ordering))),
                            "l2_policy": "inputs larger than L2 (hierarchy working set %.1f GB)" %
                                         (sum(12.0 * li[1] for li in level_info) / 1e9),
-                           "parallelism": "replicas x%d" % world, "jform_start": args.jstart,
+                           "parallelism": ("single GPU" if world == 1 else
+                                           "domain decomposition, %d ranks = %d GPUs, one mesh box each" % (world, world)),
+                           "jform_start": args.jstart,
                            "levels": [{"rows": li[0], "nnz": li[1], "nnz_P": li[2]} for li in level_info]},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
@@ -423,9 +454,13 @@ def main():
                 "spmv_fine_operator": spmv,
                 "pcg": {"iterations": iters, "converged": conv, "seconds_host_buffers": t_solve,
                         "Br_r_first": float(hist[0]), "Br_r_last": float(hist[-1])}}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.destroy_process_group()
+        # leave without running interpreter teardown: destroying torch's NCCL group while this library's
+        # own communicator still owns captured graphs was observed to hang at exit
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

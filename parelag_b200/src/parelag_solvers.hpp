@@ -511,7 +511,10 @@ private:
     {
         pe_ctx *ctx = Device::Get();
         if ((!use_graph_ || graph_failed_) && (!use_program_ || program_failed_)) return false;
-        if (pe_ctx_is_capturing(ctx) || pe_ctx_is_recording(ctx) || pe_ctx_is_profiling(ctx) || pe_ctx_nranks(ctx) > 1) return false;
+        if (pe_ctx_is_capturing(ctx) || pe_ctx_is_recording(ctx) || pe_ctx_is_profiling(ctx)) return false;
+        // multi-rank: the NCCL halo exchanges and all-reduces are captured with the kernels (every
+        // rank captures and replays the same sequence); the persistent program is single-rank only
+        const bool multi = pe_ctx_nranks(ctx) > 1;
         if (capture_safe_ < 0) capture_safe_ = CaptureSafe() ? 1 : 0;
         if (!capture_safe_) return false;
         const void *rp = pe_vec_device_ptr(const_cast<pe_vec *>(rhs.Read()));
@@ -531,7 +534,7 @@ private:
         graph_ = nullptr;
         pe_program_free(program_);
         program_ = nullptr;
-        if (use_program_ && !program_failed_ && pe_program_begin(ctx) == 0)
+        if (!multi && use_program_ && !program_failed_ && pe_program_begin(ctx) == 0)
         {
             // record the cycle: every C-ABI call below appends an op instead of launching
             bool rec_ok = true;
