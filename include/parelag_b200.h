@@ -107,6 +107,9 @@ int pe_ctx_is_recording(const pe_ctx *ctx);
 /* ---- vectors (replace mfem::Vector on the path) */
 int pe_vec_create(pe_ctx *ctx, int64_t n, pe_vec **out);
 int pe_vec_free(pe_vec *v);
+/* non-owning view of n entries of base starting at offset (block vectors, mfem::BlockVector::GetBlock);
+ * free it with pe_vec_free before the base */
+int pe_vec_view(const pe_vec *base, int64_t offset, int64_t n, pe_vec **out);
 int64_t pe_vec_size(const pe_vec *v);
 int pe_vec_upload(pe_vec *v, const double *host);       /* n doubles, H2D   */
 int pe_vec_download(const pe_vec *v, double *host);     /* n doubles, D2H   */

@@ -279,7 +279,7 @@ extern "C" int pe_graph_free(pe_graph *g)
 extern "C" int pe_vec_create(pe_ctx *ctx, int64_t n, pe_vec **out)
 {
     PE_CHECK(ctx && out && n >= 0, "bad arguments");
-    pe_vec *v = new pe_vec{ctx, n, nullptr};
+    pe_vec *v = new pe_vec{ctx, n, nullptr, false};
     PE_CUDA(cudaMalloc(&v->d, sizeof(double) * (size_t)(n > 0 ? n : 1)));
     PE_CUDA(cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
     *out = v;
@@ -288,9 +288,18 @@ extern "C" int pe_vec_create(pe_ctx *ctx, int64_t n, pe_vec **out)
 extern "C" int pe_vec_free(pe_vec *v)
 {
     if (!v) return 0;
-    cudaStreamSynchronize(v->ctx->stream);
-    cudaFree(v->d);
+    if (!v->view)
+    {
+        cudaStreamSynchronize(v->ctx->stream);
+        cudaFree(v->d);
+    }
     delete v;
+    return 0;
+}
+extern "C" int pe_vec_view(const pe_vec *base, int64_t offset, int64_t n, pe_vec **out)
+{
+    PE_CHECK(base && out && offset >= 0 && n >= 0 && offset + n <= base->n, "pe_vec_view: range outside the base vector");
+    *out = new pe_vec{base->ctx, n, base->d + offset, true};
     return 0;
 }
 extern "C" int64_t pe_vec_size(const pe_vec *v) { return v->n; }

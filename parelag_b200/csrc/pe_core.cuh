@@ -158,6 +158,7 @@ struct pe_vec {
     pe_ctx *ctx;
     int64_t n;
     double *d;
+    bool view = false;      // aliases another vector's buffer (pe_vec_view)
 };
 
 struct pe_mat {

@@ -122,6 +122,16 @@ public:
         dev_ = base.dev_; size_ = base.size_; owns_ = false;
         dev_valid_ = true; host_valid_ = false;
     }
+    /// alias of base[offset, offset + n) (mfem::BlockVector::GetBlock)
+    void MakeRef(Vector &base, int offset, int n)
+    {
+        Destroy();
+        base.ReadWrite();
+        PE_CALL(pe_vec_view(base.dev_, offset, n, &dev_));
+        size_ = n; owns_ = true;     // owns the view handle, not the memory
+        dev_valid_ = true; host_valid_ = false;
+    }
+    void MakeRef(const Vector &base, int offset, int n) { MakeRef(const_cast<Vector &>(base), offset, n); }
     void SetSize(int n)
     {
         if (n == size_ && dev_) return;
