@@ -166,6 +166,10 @@ int pe_mat_transpose(pe_ctx *ctx, const pe_mat *A, pe_mat **out);
 /* diag(A) and inverse-scaled rows (SchurComplementFactory.cpp:51-166 InvScaleRows) */
 int pe_mat_get_diag(const pe_mat *A, pe_vec *d);
 int pe_mat_scale_rows(pe_mat *A, const pe_vec *d, int invert);
+/* A *= a (HypreParMatrix::operator*=, Block2x2JacobiSolverFactory.cpp:86-91); d_i = sum_j |a_ij| over
+ * diag and offd ("ABSROWSUM", SchurComplementFactory.cpp:70-96) */
+int pe_mat_scale(pe_mat *A, double a);
+int pe_mat_abs_row_sums(const pe_mat *A, pe_vec *d);
 
 /* ---- K1/K2/K7: SpMV, SpMV^T, residual
  * y = alpha*A*x + beta*y : hypre_ParCSRMatrixMatvec via mfem::HypreParMatrix::Mult,

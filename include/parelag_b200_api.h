@@ -83,6 +83,16 @@ int pe_api_sequence_get_stat(pe_sequence *s, int level, const char *name, int64_
 int pe_api_sequence_assemble_system(pe_sequence *s, int level, int form, const int32_t *ess_attr, int nattr,
                                     pe_mat **out);
 
+/* Mixed (Darcy) system [[M Bt][B 0]] (examples/MultigridTestDarcy.cpp): M = mass of H(div), B = W D_2 with
+ * W = mass of L2, Bt = B^T, as device matrices owned by the caller (single rank). */
+int pe_api_sequence_assemble_darcy(pe_sequence *s, int level, pe_mat **M, pe_mat **B, pe_mat **Bt);
+/* BuildSolver on an MfemBlockOperator: blocks[nblocks*nblocks] row-major, NULL = zero block; ownership of the
+ * device matrices passes to the solver (the array entries are set to NULL).  forms[nblocks];
+ * ess_attr[nblocks*nattr] (one marker row per block) or NULL. */
+int pe_api_solver_build_block(const char *xml_library, const char *solver_name, int nblocks, pe_mat **blocks,
+                              pe_sequence *seq, int start_level, const int32_t *forms, const int32_t *ess_attr,
+                              int nattr, pe_solver **out);
+
 /* SolverLibrary::CreateLibrary(xml) -> GetSolverFactory(name) -> BuildSolver(A, state).
  * xml: a <ParameterList name="Preconditioner Library"> document.  seq may be NULL for
  * solvers that need no sequence.  ess_attr[nattr]: essential boundary attribute marker

@@ -92,3 +92,64 @@ def library_entries(form, ordering="natural", smoother="L1 Gauss-Seidel", coarse
                                   "Maximum iterations": max_iter, "Relative tolerance": rtol,
                                   "Absolute tolerance": atol})
     return lib
+
+
+# ----------------------------------------------------------------------------
+# mixed Darcy system (configs[1] "MultigridTestDarcy", configs[3] SPE10-shaped)
+# ----------------------------------------------------------------------------
+def darcy_blocks(seq):
+    """[[M B^T][B 0]] with M = mass(H(div)), B = W D_2, W = mass(L2) (examples/MultigridTestDarcy.cpp)."""
+    M = sp.csr_matrix(seq.mass_operator(2))
+    B = orc.spgemm(sp.csr_matrix(seq.mass_operator(3)), sp.csr_matrix(seq.D[2]))
+    return M, B
+
+
+def darcy_library_entries(block="Block Jacobi", ordering="natural", coarse_its=5, coarse_tol=1e-4, rtol=1e-6, atol=1e-6,
+                          max_iter=300, restart=50, amge=True):
+    """Parameter list modelled on examples/example_parameterlists/darcy_example_parameters.xml with the
+    hypre black boxes (BoomerAMG) replaced by the hot-path l1-Gauss-Seidel smoother."""
+    lib = {"Gauss-Seidel": ("Hypre", {"Type": "L1 Gauss-Seidel", "Sweeps": 1, "Damping Factor": 1.0, "Omega": 1.0,
+                                      "GS ordering": ordering})}
+    if block == "Block LDU":
+        lib["Blk"] = ("Block LDU", {"Damping Factor": 1.0, "A00_1 Inverse": "Gauss-Seidel", "A00_2 Inverse": "Gauss-Seidel",
+                                    "A00_3 Inverse": "Gauss-Seidel", "S Inverse": "Gauss-Seidel", "Alpha": 1.0, "S Type": "Diagonal"})
+    else:
+        lib["Blk"] = (block, {"A00 Inverse": "Gauss-Seidel", "A11 Inverse": "Gauss-Seidel", "Alpha": 1.0, "S Type": "Diagonal"})
+    lib["GMRES-Blk"] = ("Krylov", {"Solver name": "GMRES", "Preconditioner": "Blk", "Print level": -1, "Maximum iterations": coarse_its,
+                                   "Relative tolerance": coarse_tol, "Absolute tolerance": coarse_tol, "Restart size": restart})
+    lib["AMGe-Blk"] = ("AMGe", {"Maximum levels": -1, "Forms": [2, 3], "PreSmoother": "Blk", "PostSmoother": "Blk",
+                                "Coarse solver": "GMRES-Blk", "Cycle type": "V-cycle"})
+    lib["GMRES-AMGe-Blk"] = ("Krylov", {"Solver name": "GMRES", "Preconditioner": "AMGe-Blk" if amge else "Blk", "Print level": -1,
+                                        "Maximum iterations": max_iter, "Relative tolerance": rtol, "Absolute tolerance": atol,
+                                        "Restart size": restart})
+    return lib
+
+
+def darcy_solver(seqs, block="Block Jacobi", ordering="natural", coarse_its=5, coarse_tol=1e-4, restart=50, amge=True):
+    """The same solver on the oracle side: returns (A: BlockOp, prec: r -> z)."""
+    M, B = darcy_blocks(seqs[0])
+    A0 = orc.BlockOp([[M, sp.csr_matrix(B.T)], [B, None]])
+
+    def gs(Mx):
+        S = orc.Smoother(Mx, type=2, order=gs_order(Mx, ordering))
+        return lambda r: S.apply(r, np.zeros_like(r), False)
+
+    def make_smoother(l, A):
+        A00, A01, A10, A11 = A.blocks[0][0], A.blocks[0][1], A.blocks[1][0], A.blocks[1][1]
+        negS = sp.csr_matrix(orc.schur_complement(A00, A01, A10, A11, 1.0, "DIAGONAL") * (-1.0))
+        if block == "Block Jacobi":
+            return orc.BlockJacobi(A, [gs(A00), gs(negS)])
+        if block == "Block GS":
+            return orc.BlockGS(A, [gs(A00), gs(negS)])
+        return orc.BlockLDU(A, gs(A00), gs(A00), gs(A00), gs(negS), 1.0)
+    if not amge:
+        S = make_smoother(0, A0)
+        return A0, (lambda r: S.apply(r, np.zeros_like(r), False))
+
+    def make_coarse(Ac):
+        S = make_smoother(len(seqs) - 1, Ac)
+        return lambda b, x: orc.gmres(Ac.mult, lambda r: S.apply(r, np.zeros_like(r), False), b, rtol=coarse_tol, atol=coarse_tol,
+                                      max_iter=coarse_its, restart=restart)[0]
+    Ps = [[sp.csr_matrix(seqs[l].get_P(2)), sp.csr_matrix(seqs[l].get_P(3))] for l in range(len(seqs) - 1)]
+    H = orc.build_block_hierarchy(A0, Ps, [False, False], make_smoother, make_coarse)
+    return A0, H.mult

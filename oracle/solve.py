@@ -359,3 +359,219 @@ def build_hierarchy(A0, Ps, make_smoother, make_coarse):
         L["post"] = L["pre"]
     levels[-1]["coarse"] = make_coarse(levels[-1]["A"])
     return Hierarchy(levels)
+
+
+# ----------------------------------------------------------------------------
+# mixed (Darcy) path: GMRES, block preconditioners, Schur complement, blocked hierarchy
+# ----------------------------------------------------------------------------
+def gmres(A, prec, b, rtol=1e-6, atol=1e-6, max_iter=300, restart=50, x0=None):
+    """mfem::GMRESSolver::Mult (left preconditioning, modified Gram-Schmidt, Givens rotations; "the
+    algorithm on p. 20 of the SIAM Templates book").  MFEM is third-party and not vendored in the
+    reference: restated from the published algorithm, parity unpinned.  Returns
+    (x, iterations, converged, history) with history[i] = ||B r|| after iteration i."""
+    Amul = (lambda v: matvec(A, v)) if sp.issparse(A) else A
+    b = np.asarray(b, dtype=np.float64)
+    n, m = len(b), restart
+    x = np.zeros(n) if x0 is None else np.array(x0, dtype=np.float64)
+    if x0 is None:
+        r = prec(b) if prec is not None else b.copy()
+    else:
+        w = b - Amul(x)
+        r = prec(w) if prec is not None else w
+    beta = float(np.sqrt(r @ r))
+    hist = [beta]
+    final_norm = max(rtol * beta, atol)
+    if beta <= final_norm:
+        return x, 0, True, hist
+
+    def gen_rot(dx, dy):
+        if dy == 0.0:
+            return 1.0, 0.0
+        if abs(dy) > abs(dx):
+            t = dx / dy
+            sn = 1.0 / np.sqrt(1.0 + t * t)
+            return t * sn, sn
+        t = dy / dx
+        cs = 1.0 / np.sqrt(1.0 + t * t)
+        return cs, t * cs
+
+    def app_rot(dx, dy, cs, sn):
+        return cs * dx + sn * dy, -sn * dx + cs * dy
+
+    def update(x, k, H, s, V):
+        y = s[:k + 1].copy()
+        for i in range(k, -1, -1):
+            y[i] /= H[i, i]
+            for j in range(i - 1, -1, -1):
+                y[j] -= H[j, i] * y[i]
+        for j in range(k + 1):
+            x = x + y[j] * V[j]
+        return x
+    j = 1
+    while j <= max_iter:
+        H = np.zeros((m + 1, m)); s = np.zeros(m + 1); cs = np.zeros(m + 1); sn = np.zeros(m + 1)
+        V = [r / beta]
+        s[0] = beta
+        i = 0
+        while i < m and j <= max_iter:
+            w = Amul(V[i])
+            if prec is not None:
+                w = prec(w)
+            for k in range(i + 1):
+                H[k, i] = float(w @ V[k])
+                w = w - H[k, i] * V[k]
+            H[i + 1, i] = float(np.sqrt(w @ w))
+            V.append(w / H[i + 1, i])
+            for k in range(i):
+                H[k, i], H[k + 1, i] = app_rot(H[k, i], H[k + 1, i], cs[k], sn[k])
+            cs[i], sn[i] = gen_rot(H[i, i], H[i + 1, i])
+            H[i, i], H[i + 1, i] = app_rot(H[i, i], H[i + 1, i], cs[i], sn[i])
+            s[i], s[i + 1] = app_rot(s[i], s[i + 1], cs[i], sn[i])
+            resid = abs(s[i + 1])
+            hist.append(float(resid))
+            if resid <= final_norm:
+                return update(x, i, H, s, V), j, True, hist
+            i += 1; j += 1
+        x = update(x, i - 1, H, s, V)
+        w = b - Amul(x)
+        r = prec(w) if prec is not None else w
+        beta = float(np.sqrt(r @ r))
+        if beta <= final_norm:
+            return x, j, True, hist
+    return x, max_iter, False, hist
+
+
+def schur_complement(A00, A01, A10, A11=None, alpha=1.0, kind="DIAGONAL"):
+    """SchurComplementFactory::BuildOperator (SchurComplementFactory.cpp:51-166):
+    A11 - alpha A10 diag(A00)^{-1} A01 (DIAGONAL) or with absolute row sums (ABSROWSUM)."""
+    d = A00.diagonal() if kind.upper() == "DIAGONAL" else np.asarray(abs(A00).sum(axis=1)).ravel()
+    prod = spgemm(A10.tocsr(), sp.csr_matrix(sp.diags(1.0 / d) @ A01.tocsr()))
+    if A11 is None:
+        return sp.csr_matrix(prod * (-alpha))
+    return sp.csr_matrix(A11 - alpha * prod)
+
+
+class BlockOp:
+    """MfemBlockOperator: blocks[i][j] scipy matrices or None; offsets from the block sizes."""
+
+    def __init__(self, blocks):
+        self.blocks = [[None if b is None else b.tocsr() for b in row] for row in blocks]
+        nb = len(blocks)
+        sizes = []
+        for i in range(nb):
+            h = next((b.shape[0] for b in self.blocks[i] if b is not None), None)
+            if h is None:
+                h = next(self.blocks[j][i].shape[1] for j in range(nb) if self.blocks[j][i] is not None)
+            sizes.append(h)
+        self.off = np.concatenate([[0], np.cumsum(sizes)])
+        self.shape = (self.off[-1], self.off[-1])
+
+    def blk(self, v, i):
+        return v[self.off[i]:self.off[i + 1]]
+
+    def mult(self, x):
+        y = np.zeros(self.off[-1])
+        for i, row in enumerate(self.blocks):
+            for j, b in enumerate(row):
+                if b is not None:
+                    y[self.off[i]:self.off[i + 1]] += matvec(b, self.blk(x, j))
+        return y
+
+
+class BlockJacobi:
+    """BlockDiagonalSolver with the Block2x2JacobiSolverFactory wiring (S = -Schur complement when
+    use_negative_s).  inv[i](r) applies the block inverse from a zero guess."""
+
+    def __init__(self, A, inv):
+        self.A, self.inv = A, inv
+
+    def apply(self, b, x, iterative_mode=True):
+        if not iterative_mode:
+            r, base = np.asarray(b, dtype=np.float64), np.zeros_like(b)
+        else:
+            r, base = b - self.A.mult(x), x
+        c = np.zeros_like(r)
+        for i, f in enumerate(self.inv):
+            c[self.A.off[i]:self.A.off[i + 1]] = f(self.A.blk(r, i))
+        return base + c
+
+
+class BlockGS:
+    """BlockTriangularSolver, lower triangle (Block2x2GaussSeidelSolverFactory)."""
+
+    def __init__(self, A, inv):
+        self.A, self.inv = A, inv
+
+    def apply(self, b, x, iterative_mode=True):
+        if not iterative_mode:
+            r, base = np.asarray(b, dtype=np.float64), np.zeros_like(b)
+        else:
+            r, base = b - self.A.mult(x), x
+        c = np.zeros_like(r)
+        for i, f in enumerate(self.inv):
+            t = self.A.blk(r, i).copy()
+            for j in range(i):
+                if self.A.blocks[i][j] is not None:
+                    t -= matvec(self.A.blocks[i][j], self.A.blk(c, j))
+            c[self.A.off[i]:self.A.off[i + 1]] = f(t)
+        return base + c
+
+
+class BlockLDU:
+    """Block2x2LDUInverseOperator::Mult (Block2x2LDUInverseOperator.cpp:73-135)."""
+
+    def __init__(self, A, inv1, inv2, inv3, invS, damping=1.0):
+        self.A, self.inv1, self.inv2, self.inv3, self.invS, self.damping = A, inv1, inv2, inv3, invS, damping
+
+    def apply(self, b, x, iterative_mode=True):
+        A = self.A
+        r = np.asarray(b, dtype=np.float64).copy() if not iterative_mode else b - A.mult(x)
+        r0, r1 = A.blk(r, 0), A.blk(r, 1).copy()
+        t0 = self.inv2(r0)
+        r1 -= matvec(A.blocks[1][0], t0)
+        dp = self.invS(r1)
+        t = self.inv3(matvec(A.blocks[0][1], dp))
+        du = self.inv1(r0) - t
+        c = self.damping * np.concatenate([du, dp])
+        return c if not iterative_mode else x + c
+
+
+def build_block_hierarchy(A0, P_blocks_per_level, ess_flags, make_smoother, make_coarse):
+    """buildBlockedHierarchyFromDeRhamSequence (Hierarchy.cpp:400-544): A_c(i,j) = P_i^T A(i,j) P_j,
+    FixZeroRows on diagonal blocks that carry essential conditions; P = blockdiag(P_i)."""
+    levels = []
+    A = A0
+    for Pb in P_blocks_per_level:
+        nb = len(Pb)
+        Ac = [[None] * nb for _ in range(nb)]
+        for i in range(nb):
+            for j in range(nb):
+                if A.blocks[i][j] is not None:
+                    t = rap(A.blocks[i][j], Pb[j].tocsr(), R=Pb[i].tocsr())
+                    if i == j and ess_flags[i]:
+                        t, _ = fix_zero_rows(t)
+                    Ac[i][j] = t
+        levels.append({"A": A, "P": sp.block_diag([p.tocsr() for p in Pb], format="csr")})
+        A = BlockOp(Ac)
+    levels.append({"A": A})
+    for l, L in enumerate(levels[:-1]):
+        L["pre"] = make_smoother(l, L["A"])
+        L["post"] = L["pre"]
+    levels[-1]["coarse"] = make_coarse(levels[-1]["A"])
+    return BlockHierarchy(levels)
+
+
+class BlockHierarchy(Hierarchy):
+    def iterate(self, rhs, sol, l=0):
+        L = self.levels[l]
+        if l == len(self.levels) - 1:
+            return L["coarse"](rhs, sol)
+        if L.get("pre") is not None:
+            sol = L["pre"].apply(rhs, sol, True)
+        resid = rhs - L["A"].mult(sol)
+        crhs = matvec_t(L["P"], resid)
+        csol = self.iterate(crhs, np.zeros(L["P"].shape[1]), l + 1)
+        sol = sol + matvec(L["P"], csol)
+        if L.get("post") is not None:
+            sol = L["post"].apply(rhs, sol, True)
+        return sol

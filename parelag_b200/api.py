@@ -134,6 +134,12 @@ class Sequence:
                                                    C.byref(m.h)))
         return m
 
+    def assemble_darcy(self, ctx, level=0):
+        """(M, B, Bt) of the mixed system [[M Bt][B 0]] as device matrices"""
+        M, B, Bt = capi.Mat(ctx), capi.Mat(ctx), capi.Mat(ctx)
+        _chk(lib().pe_api_sequence_assemble_darcy(self.h, level, C.byref(M.h), C.byref(B.h), C.byref(Bt.h)))
+        return M, B, Bt
+
     def stat(self, level, name):
         v = C.c_int64()
         _chk(lib().pe_api_sequence_get_stat(self.h, level, name.encode(), C.byref(v)))
@@ -261,6 +267,34 @@ class Solver:
         if self.h:
             lib().pe_api_solver_free(self.h)
             self.h = None
+
+
+class BlockSolver(Solver):
+    """BuildSolver on an MfemBlockOperator; blocks: nested list of capi.Mat or None (ownership passes)."""
+
+    def __init__(self, xml, name, blocks, seq, start_level, forms, ess_attr=None):
+        nb = len(blocks)
+        arr = (C.c_void_p * (nb * nb))()
+        self.n = 0
+        for i in range(nb):
+            h = None
+            for j in range(nb):
+                b = blocks[i][j]
+                arr[i * nb + j] = None if b is None else b.h
+                if b is not None and h is None:
+                    h = b.info()[0]
+            if h is None:
+                h = next(blocks[j][i].info()[1] for j in range(nb) if blocks[j][i] is not None)
+            self.n += h
+        f = _i32(forms)
+        ess = None if ess_attr is None else _i32(np.asarray(ess_attr).reshape(nb, -1))
+        self.h = C.c_void_p()
+        _chk(lib().pe_api_solver_build_block(xml.encode(), name.encode(), nb, arr, None if seq is None else seq.h, start_level,
+                                             _ptr(f), _ptr(ess), 0 if ess is None else ess.shape[1], C.byref(self.h)))
+        for row in blocks:
+            for b in row:
+                if b is not None:
+                    b.h = None
 
 
 def timer(name):

@@ -289,3 +289,39 @@ extern "C" int pe_mat_scale_rows(pe_mat *A, const pe_vec *d, int invert)
     pe_mat_values_changed(A);
     return 0;
 }
+
+__global__ void k_scale_all(int64_t nnz, double *A, double a)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nnz) A[i] *= a;
+}
+extern "C" int pe_mat_scale(pe_mat *A, double a)
+{
+    for (DevCSR *m : {&A->diag, &A->offd})
+        if (m->nnz > 0)
+        {
+            k_scale_all<<<pe_grid_for(m->nnz, 256), 256, 0, A->ctx->stream>>>(m->nnz, m->A, a);
+            PE_LAUNCHED(A->ctx);
+        }
+    pe_mat_values_changed(A);
+    return 0;
+}
+__global__ void k_abs_row_sums(int n, const int *__restrict__ dI, const double *__restrict__ dA, const int *__restrict__ oI,
+                               const double *__restrict__ oA, double *d)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double s = 0.0;
+    for (int k = dI[r]; k < dI[r + 1]; ++k) s += fabs(dA[k]);
+    if (oI) for (int k = oI[r]; k < oI[r + 1]; ++k) s += fabs(oA[k]);
+    d[r] = s;
+}
+extern "C" int pe_mat_abs_row_sums(const pe_mat *A, pe_vec *d)
+{
+    PE_CHECK(d->n == A->diag.nrows, "size mismatch");
+    const int n = A->diag.nrows;
+    if (n == 0) return 0;
+    k_abs_row_sums<<<pe_grid_for(n, 256), 256, 0, A->ctx->stream>>>(n, A->diag.I, A->diag.A, A->offd.nnz > 0 ? A->offd.I : nullptr, A->offd.A, d->d);
+    PE_LAUNCHED(A->ctx);
+    return 0;
+}

@@ -176,6 +176,13 @@ public:
         if (size_) PE_CALL(pe_vec_scale(ReadWrite(), a));
         return *this;
     }
+    /// *this = a * x
+    Vector &Set(double a, const Vector &x)
+    {
+        SetSize(x.Size());
+        if (size_) PE_CALL(pe_vec_axpby(a, x.Read(), 0.0, Write()));
+        return *this;
+    }
     /// *this += a * x
     Vector &Add(double a, const Vector &x)
     {

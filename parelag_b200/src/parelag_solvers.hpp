@@ -15,10 +15,10 @@
 #include <cstdio>
 #include "parelag_core.hpp"
 #include "parelag_sequence.hpp"
+#include "parelag_block.hpp"
 
 namespace parelag
 {
-using Op_Ptr = std::shared_ptr<mfem::Operator>;
 
 namespace mg_utils
 {
@@ -26,7 +26,7 @@ namespace mg_utils
 inline void ComputeResidual(const mfem::Operator &A, const mfem::Vector &x, const mfem::Vector &b, mfem::Vector &r)
 {
     auto A_hyp = dynamic_cast<const mfem::HypreParMatrix *>(&A);
-    PARELAG_TEST_FOR_EXCEPTION(!A_hyp, std::runtime_error, "ComputeResidual(): operator is not a HypreParMatrix");
+    if (!A_hyp) { ComputeResidualGeneric(A, x, b, r); return; }     // block operators
     r.SetSize(b.Size());
     PE_CALL(pe_residual(Device::Get(), A_hyp->Handle(), x.Read(), b.Read(), r.Write()));
 }
@@ -232,8 +232,10 @@ public:
         : Solver(A->Height(), A->Width(), false), A_(std::move(A)), Prec_(std::move(Prec))
     {
         const std::string name = params.Get("Solver name", "PCG");
-        PARELAG_TEST_FOR_EXCEPTION(name != "PCG" && name != "CG", std::runtime_error,
-                                   "KrylovSolver: solver \"" << name << "\" is not available on the GPU path in this round (PCG only)");
+        PARELAG_TEST_FOR_EXCEPTION(name != "PCG" && name != "CG" && name != "GMRES", std::runtime_error,
+                                   "KrylovSolver: solver \"" << name << "\" is not available on the GPU path in this round (PCG, GMRES)");
+        gmres_ = name == "GMRES";
+        restart_ = params.Get("Restart size", 50);
         print_level_ = params.Get("Print level", -1);
         rel_tol_ = params.Get("Relative tolerance", 0.0);
         abs_tol_ = params.Get("Absolute tolerance", 0.0);
@@ -246,7 +248,7 @@ public:
     /// tests of mfem::CGSolver::Mult) live in HBM.  Once the stopping test fires the step lengths
     /// become 0, so x equals the result of the early exit; there is no host synchronisation and
     /// the enclosing V-cycle can be captured in a CUDA graph.
-    bool DeviceResident() const { return max_iter_ >= 1 && max_iter_ <= 10 && print_level_ < 0 && !final_paragraph_; }
+    bool DeviceResident() const { return !gmres_ && max_iter_ >= 1 && max_iter_ <= 10 && print_level_ < 0 && !final_paragraph_; }
     bool CaptureSafe() const override
     {
         return DeviceResident() && (!Prec_ || SolverCaptureSafe(Prec_.get())) &&
@@ -254,6 +256,7 @@ public:
     }
     void Mult(const mfem::Vector &b, mfem::Vector &x) const override
     {
+        if (gmres_) { MultGMRES(b, x); return; }
         if (DeviceResident()) { MultDeviceResident(b, x); return; }
         const int n = Height();
         r_.SetSize(n); d_.SetSize(n); z_.SetSize(n);
@@ -307,6 +310,88 @@ public:
     /// history[i] = (B r, r) after iteration i (history[0]: initial) -- what MFEM prints
     const std::vector<double> &GetResidualHistory() const { FetchStats(); return history_; }
 private:
+    /// mfem::GMRESSolver::Mult restated: left-preconditioned restarted GMRES with Givens rotations
+    /// ("Generalized Minimum Residual method following the algorithm on p. 20 of the SIAM Templates
+    /// book"); monitor ||B r||; history[i] = that norm after iteration i
+    void MultGMRES(const mfem::Vector &b, mfem::Vector &x) const
+    {
+        const int n = Height(), m = restart_;
+        r_.SetSize(n); z_.SetSize(n);
+        mfem::Vector &r = r_, &w = z_;
+        history_.clear(); stats_on_device_ = false; converged_ = false; final_iter_ = 0;
+        std::vector<double> H((size_t)(m + 1) * m, 0.0), s(m + 1), cs(m + 1), sn(m + 1);
+        auto h = [&](int i, int j) -> double & { return H[(size_t)j * (m + 1) + i]; };
+        auto norm = [](const mfem::Vector &v) { return std::sqrt(v * v); };
+        if (this->iterative_mode) A_->Mult(x, r); else x = 0.0;
+        if (Prec_)
+        {
+            if (this->iterative_mode) { mfem::add(b, -1.0, r, w); Prec_->Mult(w, r); }
+            else Prec_->Mult(b, r);
+        }
+        else
+        {
+            if (this->iterative_mode) mfem::add(b, -1.0, r, r); else r = b;
+        }
+        double beta = norm(r), resid = beta;
+        history_.push_back(beta);
+        double final_norm = std::max(rel_tol_ * beta, abs_tol_);
+        if (print_level_ == 1) std::printf("   Pass : %2d   Iteration : %3d  ||B r|| = %g\n", 1, 0, beta);
+        if (beta <= final_norm) { final_norm_ = beta; final_iter_ = 0; converged_ = true; return; }
+        if ((int)v_.size() < m + 1) v_.resize(m + 1);
+        auto update = [&](int k)
+        {
+            std::vector<double> y(s.begin(), s.begin() + k + 1);
+            for (int i = k; i >= 0; --i)
+            {
+                y[i] /= h(i, i);
+                for (int j = i - 1; j >= 0; --j) y[j] -= h(j, i) * y[i];
+            }
+            for (int j = 0; j <= k; ++j) x.Add(y[j], v_[j]);
+        };
+        for (int j = 1; j <= max_iter_;)
+        {
+            v_[0].Set(1.0 / beta, r);
+            std::fill(s.begin(), s.end(), 0.0);
+            s[0] = beta;
+            int i;
+            for (i = 0; i < m && j <= max_iter_; ++i, ++j)
+            {
+                if (Prec_) { A_->Mult(v_[i], r); Prec_->Mult(r, w); }
+                else A_->Mult(v_[i], w);
+                for (int k = 0; k <= i; ++k) { h(k, i) = w * v_[k]; w.Add(-h(k, i), v_[k]); }
+                h(i + 1, i) = norm(w);
+                v_[i + 1].Set(1.0 / h(i + 1, i), w);
+                for (int k = 0; k < i; ++k) ApplyPlaneRotation(h(k, i), h(k + 1, i), cs[k], sn[k]);
+                GeneratePlaneRotation(h(i, i), h(i + 1, i), cs[i], sn[i]);
+                ApplyPlaneRotation(h(i, i), h(i + 1, i), cs[i], sn[i]);
+                ApplyPlaneRotation(s[i], s[i + 1], cs[i], sn[i]);
+                resid = std::fabs(s[i + 1]);
+                history_.push_back(resid);
+                if (print_level_ == 1) std::printf("   Pass : %2d   Iteration : %3d  ||B r|| = %g\n", (j - 1) / m + 1, j, resid);
+                if (resid <= final_norm) { update(i); final_norm_ = resid; final_iter_ = j; converged_ = true; return; }
+            }
+            if (print_level_ == 1 && j <= max_iter_) std::printf("Restarting...\n");
+            update(i - 1);
+            A_->Mult(x, r);
+            if (Prec_) { mfem::add(b, -1.0, r, w); Prec_->Mult(w, r); }
+            else mfem::add(b, -1.0, r, r);
+            beta = norm(r);
+            if (beta <= final_norm) { final_norm_ = beta; final_iter_ = j; converged_ = true; return; }
+        }
+        final_norm_ = beta; final_iter_ = max_iter_; converged_ = false;
+    }
+    static void GeneratePlaneRotation(double &dx, double &dy, double &cs, double &sn)
+    {
+        if (dy == 0.0) { cs = 1.0; sn = 0.0; }
+        else if (std::fabs(dy) > std::fabs(dx)) { const double t = dx / dy; sn = 1.0 / std::sqrt(1.0 + t * t); cs = t * sn; }
+        else { const double t = dy / dx; cs = 1.0 / std::sqrt(1.0 + t * t); sn = t * cs; }
+    }
+    static void ApplyPlaneRotation(double &dx, double &dy, double cs, double sn)
+    {
+        const double t = cs * dx + sn * dy;
+        dy = -sn * dx + cs * dy;
+        dx = t;
+    }
     void MultDeviceResident(const mfem::Vector &b, mfem::Vector &x) const
     {
         pe_ctx *ctx = Device::Get();
@@ -355,7 +440,9 @@ private:
     std::shared_ptr<mfem::Solver> Prec_;
     int print_level_ = -1, max_iter_ = 10;
     double rel_tol_ = 0.0, abs_tol_ = 0.0;
-    bool final_paragraph_ = false;
+    bool final_paragraph_ = false, gmres_ = false;
+    int restart_ = 50;
+    mutable std::vector<mfem::Vector> v_;       // Krylov basis of GMRES
     mutable mfem::Vector r_, d_, z_;
     mutable std::vector<double> history_;
     mutable bool converged_ = false;
@@ -617,6 +704,73 @@ inline std::unique_ptr<Hierarchy> buildHierarchyFromDeRhamSequence(const Op_Ptr 
     return H;
 }
 
+/// Hierarchy.cpp:400-544: per block P_i = ComputeTrueP(forms[i], ess_i); A_c(i,j) = P_i^T A(i,j) P_j;
+/// FixZeroRows on the diagonal blocks with essential conditions
+inline std::unique_ptr<Hierarchy> buildBlockedHierarchyFromDeRhamSequence(const Op_Ptr &A_in, const DeRhamSequence &Sequence,
+                                                                          std::vector<std::vector<int>> &label_ess,
+                                                                          const std::vector<int> &forms, int MaxNumLevels)
+{
+    auto A = A_in;
+    auto A_blocked = std::dynamic_pointer_cast<MfemBlockOperator>(A);
+    PARELAG_TEST_FOR_EXCEPTION(!A_blocked, std::runtime_error, "buildBlockedHierarchyFromDeRhamSequence(...): A is not a MfemBlockOperator.");
+    const int NumBlockRows = (int)A_blocked->GetNumBlockRows(), NumBlockCols = (int)A_blocked->GetNumBlockCols();
+    PARELAG_TEST_FOR_EXCEPTION(NumBlockRows != NumBlockCols, std::runtime_error, "buildBlockedHierarchyFromDeRhamSequence(...): A is not block-square!");
+    PARELAG_TEST_FOR_EXCEPTION((int)forms.size() != NumBlockRows, std::runtime_error,
+                               "buildBlockedHierarchyFromDeRhamSequence(...): The forms vector has the wrong size (" << forms.size()
+                               << "). Should be " << NumBlockRows << ".");
+    PARELAG_TEST_FOR_EXCEPTION(forms.size() != label_ess.size(), std::runtime_error,
+                               "buildBlockedHierarchyFromDeRhamSequence(...): Forms vector and boundary condition information are inconsistent.");
+    int NumLevels = MaxNumLevels;
+    {
+        int actual = 0;
+        std::shared_ptr<DeRhamSequence> tmp;
+        const DeRhamSequence *p = &Sequence;
+        while (p) { tmp = p->ViewCoarserSequence(); p = tmp.get(); ++actual; }
+        if (MaxNumLevels < 1 || MaxNumLevels > actual) NumLevels = actual;
+    }
+    auto H = make_unique<Hierarchy>(A, NumLevels);
+    H->SetImplicitTranspose(true);
+    const DeRhamSequence *seq = &Sequence;
+    std::shared_ptr<DeRhamSequence> hold;
+    for (int l = 1; l < NumLevels; ++l)
+    {
+        Level &Coarse = H->GetLevel(l);
+        auto cseq = seq->CoarserSequence();
+        std::vector<int> CoarseOffSets(NumBlockRows + 1, 0);
+        for (int ii = 0; ii < NumBlockRows; ++ii) CoarseOffSets[ii + 1] = CoarseOffSets[ii] + cseq->GetNumberOfTrueDofs(forms[ii]);
+        auto Ac = std::make_shared<MfemBlockOperator>(CoarseOffSets);
+        auto P = std::make_shared<MfemBlockOperator>(A_blocked->CopyRowOffsets(), Ac->CopyRowOffsets());
+        std::vector<std::shared_ptr<mfem::HypreParMatrix>> P_blocks(NumBlockRows);
+        for (int ii = 0; ii < NumBlockRows; ++ii)
+        {
+            if (label_ess[ii].size() > 0)
+            {
+                mfem::Array<int> tmp(label_ess[ii].data(), (int)label_ess[ii].size());
+                P_blocks[ii] = seq->ComputeTrueP(forms[ii], tmp);
+            }
+            else P_blocks[ii] = seq->ComputeTrueP(forms[ii]);
+        }
+        for (int row = 0; row < NumBlockRows; ++row)
+            for (int col = 0; col < NumBlockCols; ++col)
+                if (!A_blocked->IsZeroBlock(row, col))
+                {
+                    auto &Aij = dynamic_cast<mfem::HypreParMatrix &>(A_blocked->GetBlock(row, col));
+                    auto tmp = std::shared_ptr<mfem::HypreParMatrix>{mfem::RAP(P_blocks[row].get(), &Aij, P_blocks[col].get())};
+                    if (row == col && label_ess[row].size() > 0) hypre_ParCSRMatrixFixZeroRows(*tmp);
+                    Ac->SetBlock(row, col, std::move(tmp));
+                }
+        for (int row = 0; row < NumBlockRows; ++row) P->SetBlock(row, row, P_blocks[row]);
+        A = Ac;
+        A_blocked = Ac;
+        Coarse.Set<Op_Ptr>("P", P);
+        Coarse.Set<Op_Ptr>("A", Ac);
+        hold = cseq;
+        seq = hold.get();
+    }
+    H->Finalize();
+    return H;
+}
+
 class AMGeSolverFactory : public SolverFactory
 {
     std::unique_ptr<mfem::Solver> _do_build_solver(const Op_Ptr &op, SolverState &state) const override
@@ -627,13 +781,15 @@ class AMGeSolverFactory : public SolverFactory
         PARELAG_TEST_FOR_EXCEPTION(!sequence, std::runtime_error, "AMGeSolverFactory: the state has no DeRhamSequence");
         if (Forms_.size() == 0) Forms_ = state.GetForms();
         PARELAG_ASSERT(Forms_.size() > 0);
-        PARELAG_TEST_FOR_EXCEPTION(Forms_.size() != 1, not_implemented_error,
-                                   "AMGeSolverFactory: blocked hierarchies (Forms.size() > 1) are not available in this round");
         std::unique_ptr<Hierarchy> H;
         {
             Timer t = TimeManager::AddTimer("Build Hierarchy: build from deRham Sequence");
-            auto &ess_attr = state.GetBoundaryLabels(0);
-            H = buildHierarchyFromDeRhamSequence(op, *sequence, ess_attr, Forms_.front(), MaxLevels_);
+            if (Forms_.size() == 1)
+            {
+                auto &ess_attr = state.GetBoundaryLabels(0);
+                H = buildHierarchyFromDeRhamSequence(op, *sequence, ess_attr, Forms_.front(), MaxLevels_);
+            }
+            else H = buildBlockedHierarchyFromDeRhamSequence(op, *sequence, state.GetBoundaryLabels(), Forms_, MaxLevels_);
         }
         const int CoarsestLevelID = H->GetNumLevels() - 1;
         for (const auto &level : *H)
@@ -777,5 +933,8 @@ inline void SolverLibrary::RegisterBuiltins()
     RegisterFactoryType("Hiptmair", [] { return std::make_shared<HiptmairSmootherFactory>(); });
     RegisterFactoryType("Krylov", [] { return std::make_shared<KrylovSolverFactory>(); });
     RegisterFactoryType("Stationary Iteration", [] { return std::make_shared<StationarySolverFactory>(); });
+    RegisterFactoryType("Block GS", [] { return std::make_shared<Block2x2GaussSeidelSolverFactory>(); });
+    RegisterFactoryType("Block Jacobi", [] { return std::make_shared<Block2x2JacobiSolverFactory>(); });
+    RegisterFactoryType("Block LDU", [] { return std::make_shared<Block2x2LDUSolverFactory>(); });
 }
 } // namespace parelag

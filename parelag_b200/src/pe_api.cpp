@@ -12,7 +12,7 @@ struct pe_sequence { std::vector<std::shared_ptr<DeRhamSequence>> levels; };
 struct pe_solver
 {
     std::shared_ptr<SolverLibrary> lib;
-    std::shared_ptr<mfem::HypreParMatrix> A;
+    std::shared_ptr<mfem::Operator> A;
     std::unique_ptr<mfem::Solver> solver;
     mfem::Vector b, x;
 };
@@ -248,6 +248,83 @@ extern "C" int pe_api_solver_build_device(const char *xml, const char *name, pe_
     state->SetBoundaryLabels(labels);
     state->SetForms({form});
     s->A = std::make_shared<mfem::HypreParMatrix>(A);
+    {
+        Timer t = TimeManager::AddTimer(std::string("Build Solver ") + name);
+        s->solver = fact->BuildSolver(s->A, *state);
+    }
+    *out = s.release();
+    API_CATCH
+}
+/// mixed (Darcy) system blocks as in examples/MultigridTestDarcy.cpp: M = mass(H(div)) (weights folded into
+/// the element matrices), B = W D with W = mass(L2), Bt = B^T; the driver solves [[M Bt][B 0]]
+extern "C" int pe_api_sequence_assemble_darcy(pe_sequence *s, int level, pe_mat **M_out, pe_mat **B_out, pe_mat **Bt_out)
+{
+    API_TRY
+    auto &seq = *s->levels.at(level);
+    PARELAG_TEST_FOR_EXCEPTION(!seq.data, std::runtime_error, "assemble_darcy: sequence has no mass matrices");
+    PARELAG_TEST_FOR_EXCEPTION(seq.IsParallel(), not_implemented_error, "assemble_darcy: single rank only in this round");
+    pe_ctx *ctx = Device::Get();
+    Timer t = TimeManager::AddTimer("Assemble linear system");
+    const int nf = seq.GetNumberOfForms(), uform = nf - 2, pform = nf - 1;
+    auto upload = [&](const HostCSR &M) { pe_mat *d = nullptr; auto v = M.View(); PE_CALL(pe_mat_upload(ctx, &v, &d)); return d; };
+    auto mass = [&](int j)
+    {
+        const HostCSR &ED = seq.data->dof.at(j)->entity_dof.at(0);
+        HostCSR R;
+        R.nrows = (int)ED.J.size(); R.ncols = seq.data->dof[j]->ndofs;
+        R.I.resize(R.nrows + 1); std::iota(R.I.begin(), R.I.end(), 0);
+        R.J = ED.J; R.A = ED.A;
+        pe_mat *Rd = upload(R), *Med = upload(pool_as_csr(seq.data->M.at({j, 0}))), *Md = nullptr;
+        PE_CALL(pe_rap(ctx, nullptr, Med, Rd, &Md));
+        pe_mat_free(Rd); pe_mat_free(Med);
+        return Md;
+    };
+    pe_mat *M = mass(uform), *W = mass(pform), *D = upload(*seq.GetDerivativeOperator(uform)), *B = nullptr, *Bt = nullptr;
+    PE_CALL(pe_spgemm(ctx, W, D, &B));
+    pe_mat_free(W); pe_mat_free(D);
+    PE_CALL(pe_mat_transpose(ctx, B, &Bt));
+    *M_out = M; *B_out = B; *Bt_out = Bt;
+    API_CATCH
+}
+/// BuildSolver on an MfemBlockOperator: blocks[nblocks*nblocks] row-major, NULL = zero block (ownership of
+/// the device matrices passes to the solver); forms[nblocks]; ess_attr[nblocks*nattr] or NULL
+extern "C" int pe_api_solver_build_block(const char *xml, const char *name, int nblocks, pe_mat **blocks, pe_sequence *seq,
+                                         int start_level, const int32_t *forms, const int32_t *ess_attr, int nattr, pe_solver **out)
+{
+    API_TRY
+    auto s = make_unique<pe_solver>();
+    SimpleXMLParameterListReader reader;
+    auto pl = reader.Parse(xml);
+    s->lib = SolverLibrary::CreateLibrary(*pl);
+    auto fact = s->lib->GetSolverFactory(name);
+    auto state = fact->GetDefaultState();
+    if (seq) state->SetDeRhamSequence(seq->levels.at(start_level));
+    std::vector<std::vector<int>> labels(nblocks);
+    if (ess_attr) for (int b = 0; b < nblocks; ++b) labels[b].assign(ess_attr + (size_t)b * nattr, ess_attr + (size_t)(b + 1) * nattr);
+    state->SetBoundaryLabels(labels);
+    state->SetForms(std::vector<int>(forms, forms + nblocks));
+    std::vector<std::shared_ptr<mfem::HypreParMatrix>> mats((size_t)nblocks * nblocks);
+    std::vector<int> offsets(nblocks + 1, 0);
+    for (int i = 0; i < nblocks; ++i)
+        for (int j = 0; j < nblocks; ++j)
+            if (blocks[i * nblocks + j])
+            {
+                mats[i * nblocks + j] = std::make_shared<mfem::HypreParMatrix>(blocks[i * nblocks + j]);
+                blocks[i * nblocks + j] = nullptr;
+            }
+    for (int i = 0; i < nblocks; ++i)
+    {
+        int h = -1;
+        for (int j = 0; j < nblocks; ++j) if (mats[i * nblocks + j]) h = mats[i * nblocks + j]->Height();
+        for (int j = 0; j < nblocks && h < 0; ++j) if (mats[j * nblocks + i]) h = mats[j * nblocks + i]->Width();
+        PARELAG_TEST_FOR_EXCEPTION(h < 0, std::runtime_error, "pe_api_solver_build_block: block row " << i << " is empty");
+        offsets[i + 1] = offsets[i] + h;
+    }
+    auto blop = std::make_shared<MfemBlockOperator>(offsets);
+    for (int i = 0; i < nblocks; ++i)
+        for (int j = 0; j < nblocks; ++j)
+            if (mats[i * nblocks + j]) blop->SetBlock(i, j, mats[i * nblocks + j]);
+    s->A = blop;
     {
         Timer t = TimeManager::AddTimer(std::string("Build Solver ") + name);
         s->solver = fact->BuildSolver(s->A, *state);
