@@ -292,7 +292,14 @@ def main():
             v = api.timer(nm)
             if v > 0:
                 timers[nm] = v
-    timers["Build Hierarchy: build from deRham Sequence"] = api.timer("Build Hierarchy: build from deRham Sequence")
+    for nm in ("Build Hierarchy: build from deRham Sequence", "SharingMap construction", "Assemble linear system",
+               "Coarsen: DofAgglomeration", "Coarsen: traces prepare (host)", "Coarsen: batched traces (H2D + kernels + D2H)",
+               "Coarsen: traces commit (host)", "Coarsen: extension prepare (host)",
+               "Coarsen: batched extension (H2D + kernels + D2H)", "Coarsen: extension commit (host)",
+               "Coarsen: finalize P and D", "Coarsen: project targets"):
+        v = api.timer(nm)
+        if v > 0:
+            timers[nm] = v
 
     # ---------------- device-resident V-cycle steps
     rng = np.random.default_rng(1234 + rank)

@@ -118,7 +118,10 @@ struct Coarsener
         C->topo = ctopo; C->nforms = nf; C->jstart = S.jstart; C->svd_tol = S.svd_tol; C->is_fe = false;
         C->dof.resize(nf); C->targets.resize(nf); C->ntargets = S.ntargets;
         agg.resize(nf); Ppool.resize(nf); Dcpool.resize(nf); Pfinal.resize(nf);
-        for (int j = S.jstart; j < nf; ++j) agg[j] = std::make_unique<DofAgglomeration>(S.topo, *S.dof[j]);
+        {
+            Timer t = TimeManager::AddTimer("Coarsen: DofAgglomeration");
+            for (int j = S.jstart; j < nf; ++j) agg[j] = std::make_unique<DofAgglomeration>(S.topo, *S.dof[j]);
+        }
         for (int codim = 0; codim < nf; ++codim)
         {
             const int j = nf - codim - 1;
@@ -136,12 +139,18 @@ struct Coarsener
                     if (codim > 2) extension(j, nf - j - 4, false);
                 }
             }
-            Pfinal[j] = Ppool[j].to_csr(C->dof[j]->ndofs);
-            fine.SetP(j, Pfinal[j]);
-            if (codim > 0) coarse->SetD(j, Dcpool[j].to_csr(C->dof[j]->ndofs));
-            C->dof[j]->ComputeBoundaryMask();
-            coarse->SetDofHandlerRaw(j, C->dof[j].get());
-            project_targets(j);
+            {
+                Timer t = TimeManager::AddTimer("Coarsen: finalize P and D");
+                Pfinal[j] = Ppool[j].to_csr(C->dof[j]->ndofs);
+                fine.SetP(j, Pfinal[j]);
+                if (codim > 0) coarse->SetD(j, Dcpool[j].to_csr(C->dof[j]->ndofs));
+                C->dof[j]->ComputeBoundaryMask();
+                coarse->SetDofHandlerRaw(j, C->dof[j].get());
+            }
+            {
+                Timer t = TimeManager::AddTimer("Coarsen: project targets");
+                project_targets(j);
+            }
         }
         // the constant-one representation in L2
         C->l2const = project(nf - 1, S.l2const, 1);
@@ -176,6 +185,7 @@ struct Coarsener
             cd.BuildEntityDofTable(codim);
             return;
         }
+        Timer tprep = TimeManager::AddTimer("Coarsen: traces prepare (host)");
         const std::vector<double> pv = pv_traces(S, codim);
         // agglomerate mass matrix: the entities of codimension `codim` carry disjoint dofs,
         // so M_d is block diagonal with the entity blocks; the GPU path needs it diagonal
@@ -210,7 +220,12 @@ struct Coarsener
         b.nAE = nAE; b.ndofs = S.dof[j]->ndofs; b.I = ag.I[codim].data(); b.J = ag.J[codim].data();
         b.pv = pv.data(); b.diagM = diagM.data(); b.nT = nT; b.ldT = S.dof[j]->ndofs; b.T = S.targets[j].data();
         b.svd_tol = S.svd_tol; b.out_off = off.data(); b.out = out.data(); b.ndofs_out = ndofs.data();
-        PE_CALL(pe_batched_traces(ctx, &b));
+        tprep.Stop();
+        {
+            Timer t = TimeManager::AddTimer("Coarsen: batched traces (H2D + kernels + D2H)");
+            PE_CALL(pe_batched_traces(ctx, &b));
+        }
+        Timer tcommit = TimeManager::AddTimer("Coarsen: traces commit (host)");
         // commit: dof types / counts, entity table, P rows, coarse trace mass, functionals
         int cnt = 0;
         for (int a = 0; a < nAE; ++a)
@@ -245,6 +260,7 @@ struct Coarsener
     // ------------------------------------------------------------------ extensions
     void extension(int j, int cdom, bool facet)
     {
+        Timer tprep = TimeManager::AddTimer("Coarsen: extension prepare (host)");
         const int nf = S.nforms;
         const bool ridge_stuff = (cdom == nf - j - 3);
         DofAgglomeration &au = *agg[j], &ap = *agg[j + 1];
@@ -303,7 +319,12 @@ struct Coarsener
         std::vector<double> out(off[nAE]);
         std::vector<int> kout(nAE, 0);
         b.out_off = off.data(); b.out = out.data(); b.k_out = kout.data();
-        PE_CALL(pe_batched_extension(ctx, &b));
+        tprep.Stop();
+        {
+            Timer t = TimeManager::AddTimer("Coarsen: batched extension (H2D + kernels + D2H)");
+            PE_CALL(pe_batched_extension(ctx, &b));
+        }
+        Timer tcommit = TimeManager::AddTimer("Coarsen: extension commit (host)");
         // ---- commit
         int counter = ucd.ndofs;
         BlockPool &mass = C->M[{j, cdom}];

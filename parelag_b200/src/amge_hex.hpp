@@ -111,6 +111,10 @@ inline void place(double *C, int n, int o, const double *B, int m, double s)
 }
 inline void fill_pool(BlockPool &P, int count, const double *blk, int m, const double *w = nullptr)
 {
+    // one allocation per pool: the fine element pools are gigabytes at 144^3 hexahedra
+    P.vals.reserve(P.vals.size() + (size_t)count * m * m);
+    P.size.reserve(P.size.size() + (size_t)count);
+    P.off.reserve(P.off.size() + (size_t)count);
     for (int e = 0; e < count; ++e)
     {
         double *d = P.add(m);
