@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--ref-levels", type=int, default=4)
     ap.add_argument("--cpu-n", type=int, default=32, help="bounded sample of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sell-min-rows", type=int, default=None,
+                    help="tuning: levels with fewer rows use the lanes-per-row CSR Gauss-Seidel kernel (library default 200000)")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket 2 extra V-cycles with cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     args = ap.parse_args()
@@ -240,6 +242,8 @@ def main():
     else:
         ctx = api.session(rank=0, nranks=1, device=local_rank)
     api.lib().pe_api_timer_clear()
+    if args.sell_min_rows is not None:
+        capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, args.sell_min_rows)
 
     # ---------------- setup (timed with the reference's timer names)
     t0 = time.perf_counter()

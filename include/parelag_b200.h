@@ -78,6 +78,12 @@ int pe_ctx_timer_stop(pe_ctx *ctx, float *ms);
  * (k_gs_set), 2 = Jacobi update.  total_bytes = algorithmic bytes of the launches. */
 int pe_ctx_profile(pe_ctx *ctx, int enable);
 int pe_ctx_profile_get(pe_ctx *ctx, int kernel_id, int64_t *count, double *total_ms, double *total_bytes);
+/* process-wide tuning knobs (tests force either kernel family; defaults in brackets):
+ * PE_TUNE_SELL_MIN_ROWS [200000]: multicolour Gauss-Seidel uses the colour-ordered SELL-32 streaming
+ * kernel for matrices with at least this many rows and the lanes-per-row CSR kernel below it. */
+enum { PE_TUNE_SELL_MIN_ROWS = 0, PE_TUNE_COUNT = 4 };
+int pe_set_tuning(int key, int value);
+int pe_get_tuning(int key);
 /* write a scratch buffer larger than L2 (bench hygiene) */
 int pe_ctx_flush_l2(pe_ctx *ctx);
 

@@ -129,6 +129,17 @@ class Ctx:
             self.h = None
 
 
+TUNE_SELL_MIN_ROWS = 0
+
+
+def set_tuning(key, value):
+    _chk(lib().pe_set_tuning(key, int(value)))
+
+
+def get_tuning(key):
+    return lib().pe_get_tuning(key)
+
+
 def nccl_unique_id():
     buf = C.create_string_buffer(128)
     _chk(lib().pe_nccl_get_unique_id(buf))

@@ -127,6 +127,15 @@ extern "C" int pe_ctx_destroy(pe_ctx *c)
     return 0;
 }
 
+static int g_tuning[PE_TUNE_COUNT] = {200000, 0, 0, 0};
+extern "C" int pe_set_tuning(int key, int value)
+{
+    PE_CHECK(key >= 0 && key < PE_TUNE_COUNT, "bad tuning key");
+    g_tuning[key] = value;
+    return 0;
+}
+extern "C" int pe_get_tuning(int key) { return key >= 0 && key < PE_TUNE_COUNT ? g_tuning[key] : 0; }
+
 extern "C" int pe_ctx_sync(pe_ctx *c)
 {
     PE_CUDA(cudaStreamSynchronize(c->stream));

@@ -43,6 +43,7 @@ struct pe_smoother {
     int32_t npad = 0;                   // padded length of the colour-ordered vectors
     std::vector<int32_t> slice_starts;  // nsets+1: first slice of every colour
     std::vector<double> set_bytes;      // algorithmic bytes of one colour launch
+    bool skip_turn = false;             // the backward pass may start at the second-to-last colour (see build_gs_schedule)
     int32_t *pos_d = nullptr;           // row -> colour-ordered position
     double *l1p_d = nullptr, *fp_d = nullptr, *up_d = nullptr;
     // Chebyshev
@@ -280,8 +281,35 @@ static int build_gs_schedule(pe_smoother *s)
     std::vector<int> next(s->set_starts.begin(), s->set_starts.end() - 1), pos(n);
     for (int i = 0; i < n; ++i) { int p = next[key[i]]++; s->order[p] = i; pos[i] = p; }
 
+    // The forward pass ends and the backward pass starts with the LAST set.  Its rows are mutually
+    // independent, so right after the forward update row i has residual f_i - sum_j a_ij u_j =
+    // (1 - a_ii / d_i) r_i, which is exactly 0 when d_i == a_ii: the repeated update adds only the
+    // rounding error of that zero.  When every row of the last set has d_i == a_ii (no ghost entries,
+    // l1 == diagonal) the second visit is skipped -- 1/nsets of the matrix traffic of a sweep.
+    if (nsets >= 2 && s->type == 2 && s->ordering == PE_GS_ORDER_MULTICOLOR && s->weight == 1.0 && s->omega == 1.0)
+    {
+        std::vector<double> l1h(n), Ah((size_t)A->diag.nnz);
+        std::vector<int> oIt;
+        PE_CUDA(cudaMemcpy(l1h.data(), s->l1_d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+        if (A->diag.nnz) PE_CUDA(cudaMemcpy(Ah.data(), A->diag.A, sizeof(double) * (size_t)A->diag.nnz, cudaMemcpyDeviceToHost));
+        if (A->offd.nnz > 0) { oIt.resize(n + 1); PE_CUDA(cudaMemcpy(oIt.data(), A->offd.I, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost)); }
+        bool ok = true;
+        for (int k = s->set_starts[nsets - 1]; k < s->set_starts[nsets] && ok; ++k)
+        {
+            const int i = s->order[k];
+            double aii = 0.0;
+            for (int q = I[i]; q < I[i + 1]; ++q) if (J[q] == i) aii = Ah[q];
+            ok = aii > 0.0 && l1h[i] == aii && (oIt.empty() || oIt[i + 1] == oIt[i]);
+        }
+        s->skip_turn = ok;
+    }
+
     bool general = !(s->weight == 1.0 && s->omega == 1.0);
-    if (s->ordering == PE_GS_ORDER_MULTICOLOR && !general)
+    // Colour-ordered SELL streaming (thread per row) for bandwidth-bound levels; below
+    // PE_TUNE_SELL_MIN_ROWS rows a colour is a few thousand rows and latency-bound, where the
+    // lanes-per-row CSR kernel (k_gs_set<TPR>: one coalesced load of the row, shuffle reduction, no
+    // renumbering passes) has the shorter dependent chain.
+    if (s->ordering == PE_GS_ORDER_MULTICOLOR && !general && n >= pe_get_tuning(PE_TUNE_SELL_MIN_ROWS))
     {
         // colour-ordered, slice-padded numbering
         s->slice_starts.assign(nsets + 1, 0);
@@ -323,6 +351,7 @@ static int build_gs_schedule(pe_smoother *s)
         PE_CUDA(cudaMemsetAsync(s->fp_d, 0, sizeof(double) * np, ctx->stream));
         PE_CUDA(cudaMemsetAsync(s->up_d, 0, sizeof(double) * np, ctx->stream));
         PE_TRY(pe_sell_build(ctx, A->diag, &A->offd, rowmap_d, nslices, s->pos_d, s->npad, s->S));
+
         // l1 in colour order (padded rows keep 0 => never updated)
         PE_TRY(pe_launch_perm_in(ctx, n, s->pos_d, s->l1_d, nullptr, s->l1p_d, s->up_d));
         PE_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -613,7 +642,7 @@ static int launch_gs_set(pe_smoother *s, int k0, int k1, const double *f, double
     pe_ctx *ctx = s->ctx;
     int rows = k1 - k0;
     if (rows <= 0) return 0;
-    if (!GENERAL && s->P.nrb > 0)
+    if (!GENERAL && s->P.nrb > 0 && s->A->diag.nrows >= pe_get_tuning(PE_TUNE_SELL_MIN_ROWS))
     {
         int c = 0;
         while (s->set_starts[c] != k0) ++c;
@@ -669,7 +698,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
             }
             PE_TRY(pe_launch_perm_in(ctx, n, s->pos_d, b->d, zero_guess ? nullptr : x->d, s->fp_d, s->up_d));
             for (int pass = 0; pass < 2; ++pass)
-                for (int cc = 0; cc < s->nsets; ++cc)
+                for (int cc = (pass == 1 && s->skip_turn) ? 1 : 0; cc < s->nsets; ++cc)
                 {
                     const int c = pass == 0 ? cc : s->nsets - 1 - cc;
                     if (s->slice_starts[c + 1] == s->slice_starts[c]) continue;
@@ -712,7 +741,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
             double c1 = s->omega * s->weight, c2 = s->omega * (1.0 - s->weight);
             for (int pass = 0; pass < 2; ++pass) {
                 if (general) PE_CUDA(cudaMemcpyAsync(s->w_d, x->d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-                for (int cc = 0; cc < s->nsets; ++cc) {
+                for (int cc = (pass == 1 && s->skip_turn) ? 1 : 0; cc < s->nsets; ++cc) {
                     int c = pass == 0 ? cc : s->nsets - 1 - cc;
                     if (general) PE_TRY(launch_gs_set<true>(s, s->set_starts[c], s->set_starts[c + 1], b->d, x->d, pass == 0, c1, c2));
                     else PE_TRY(launch_gs_set<false>(s, s->set_starts[c], s->set_starts[c + 1], b->d, x->d, pass == 0, c1, c2));

@@ -158,33 +158,37 @@ def main():
     vo = Do @ zo
     assert np.abs(v.download() - vo[mine2]).max() <= 1e-12 * np.abs(vo).max()
 
-    # ---- hybrid symmetric l1-Gauss-Seidel (one rank-local multicolour sweep with frozen ghosts)
-    sm = capi.Smoother(ctx, A, type=2, ordering=capi.GS_MULTICOLOR)
-    order, starts = sm.order()
-    bg = rng.standard_normal(len(xg)); bg[marker] = 0.0
-    u0 = rng.standard_normal(len(xg)); u0[marker] = 0.0
-    bv, uv = capi.Vec(ctx, data=bg[mine2]), capi.Vec(ctx, data=u0[mine2])
-    sm.apply(bv, uv, True)
-    # per-rank hypre relax restated by the oracle (orc_relax_gs with offd block and ghost values)
-    dI, dJ, dA = Ad["diag_i"], Ad["diag_j"], Ad["diag_a"]
-    oI, oJ, oA = Ad["offd_i"], Ad["offd_j"], Ad["offd_a"]
-    inv = np.empty(len(perms[2][0]), dtype=np.int64)         # true id -> oracle number is perms; ghosts by true id
-    uext = u0[perms[2][0][Ad["col_map_offd"]]] if len(Ad["col_map_offd"]) else np.empty(0)
-    nloc = Ad["nrows"]
-    l1 = np.abs(sp.csr_matrix((dA, dJ, dI), shape=(nloc, nloc)).diagonal())
-    if len(oA):
-        l1 = l1 + np.asarray(abs(sp.csr_matrix((oA, oJ, oI), shape=(nloc, len(Ad["col_map_offd"])))).sum(axis=1)).ravel()
-    assert np.abs(sm.l1() - l1).max() <= 1e-13 * l1.max()
-    uo = u0[mine2].copy()
-    rank_of_row = np.empty(nloc, dtype=np.int32); rank_of_row[order] = np.arange(nloc, dtype=np.int32)
-    uold = np.empty(nloc)
-    P_ = orc._p
-    orc.lib().orc_relax_gs(nloc, P_(dI), P_(dJ), P_(dA), P_(oI) if len(oA) else None, P_(oJ) if len(oA) else None,
-                           P_(oA) if len(oA) else None, P_(l1), orc.C.c_double(1.0), orc.C.c_double(1.0),
-                           P_(np.ascontiguousarray(order, dtype=np.int32)), P_(rank_of_row), P_(np.ascontiguousarray(bg[mine2])),
-                           P_(uo), P_(np.ascontiguousarray(uext)) if len(oA) else None, P_(uold))
-    assert np.abs(uv.download() - uo).max() <= 1e-12 * np.abs(uo).max(), "hybrid GS"
-    sm.free()
+    # ---- hybrid symmetric l1-Gauss-Seidel (one rank-local multicolour sweep with frozen ghosts), both kernel families
+    for min_rows in (0, 1 << 30):
+        capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, min_rows)
+        sm = capi.Smoother(ctx, A, type=2, ordering=capi.GS_MULTICOLOR)
+        order, starts = sm.order()
+        bg = rng.standard_normal(len(xg)); bg[marker] = 0.0
+        u0 = rng.standard_normal(len(xg)); u0[marker] = 0.0
+        bv, uv = capi.Vec(ctx, data=bg[mine2]), capi.Vec(ctx, data=u0[mine2])
+        sm.apply(bv, uv, True)
+        # per-rank hypre relax restated by the oracle (orc_relax_gs with offd block and ghost values)
+        dI, dJ, dA = Ad["diag_i"], Ad["diag_j"], Ad["diag_a"]
+        oI, oJ, oA = Ad["offd_i"], Ad["offd_j"], Ad["offd_a"]
+        inv = np.empty(len(perms[2][0]), dtype=np.int64)         # true id -> oracle number is perms; ghosts by true id
+        uext = u0[perms[2][0][Ad["col_map_offd"]]] if len(Ad["col_map_offd"]) else np.empty(0)
+        nloc = Ad["nrows"]
+        l1 = np.abs(sp.csr_matrix((dA, dJ, dI), shape=(nloc, nloc)).diagonal())
+        if len(oA):
+            l1 = l1 + np.asarray(abs(sp.csr_matrix((oA, oJ, oI), shape=(nloc, len(Ad["col_map_offd"])))).sum(axis=1)).ravel()
+        assert np.abs(sm.l1() - l1).max() <= 1e-13 * l1.max()
+        uo = u0[mine2].copy()
+        rank_of_row = np.empty(nloc, dtype=np.int32); rank_of_row[order] = np.arange(nloc, dtype=np.int32)
+        uold = np.empty(nloc)
+        P_ = orc._p
+        orc.lib().orc_relax_gs(nloc, P_(dI), P_(dJ), P_(dA), P_(oI) if len(oA) else None, P_(oJ) if len(oA) else None,
+                               P_(oA) if len(oA) else None, P_(l1), orc.C.c_double(1.0), orc.C.c_double(1.0),
+                               P_(np.ascontiguousarray(order, dtype=np.int32)), P_(rank_of_row), P_(np.ascontiguousarray(bg[mine2])),
+                               P_(uo), P_(np.ascontiguousarray(uext)) if len(oA) else None, P_(uold))
+        assert np.abs(uv.download() - uo).max() <= 1e-12 * np.abs(uo).max(), "hybrid GS"
+        sm.free()
+
+    capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, 200000)
 
     # ---- distributed Galerkin hierarchy == single-domain hierarchy; PCG history with an
     # order-independent smoother (Hiptmair with l1-Jacobi) == single-domain oracle history

@@ -120,8 +120,17 @@ def test_gauss_seidel_natural_order_is_hypre_order(ctx, stype, maker):
     assert _rel(dx.download(), so.apply(b, x0, True)) < 1e-13
 
 
+@pytest.fixture(params=["sell", "csr"])
+def gs_kernel(request):
+    """force the colour-ordered SELL-32 streaming kernel or the lanes-per-row CSR kernel"""
+    old = capi.get_tuning(capi.TUNE_SELL_MIN_ROWS)
+    capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, 0 if request.param == "sell" else 1 << 30)
+    yield request.param
+    capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, old)
+
+
 @pytest.mark.parametrize("weights", [(1.0, 1.0), (0.9, 1.2)])
-def test_gauss_seidel_multicolor(ctx, weights):
+def test_gauss_seidel_multicolor(ctx, weights, gs_kernel):
     A = laplace3d(11, 6, 7)
     n = A.shape[0]
     rng = np.random.default_rng(5)

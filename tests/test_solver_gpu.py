@@ -38,9 +38,19 @@ def make_sequence(seqs):
     return S
 
 
-@pytest.mark.parametrize("form,ordering", [(0, "natural"), (2, "natural"), (1, "natural"),
-                                           (2, "multicolor"), (0, "multicolor")])
-def test_pcg_amge_residual_history(sess, hier, form, ordering):
+@pytest.fixture
+def gs_kernel(request):
+    from parelag_b200 import capi
+    old = capi.get_tuning(capi.TUNE_SELL_MIN_ROWS)
+    capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, 0 if request.param == "sell" else 1 << 30)
+    yield request.param
+    capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, old)
+
+
+@pytest.mark.parametrize("form,ordering,gs_kernel", [(0, "natural", "csr"), (2, "natural", "csr"), (1, "natural", "csr"),
+                                                     (2, "multicolor", "sell"), (0, "multicolor", "sell"),
+                                                     (2, "multicolor", "csr"), (1, "multicolor", "csr")], indirect=["gs_kernel"])
+def test_pcg_amge_residual_history(sess, hier, form, ordering, gs_kernel):
     mesh, seqs = hier
     ess = np.ones(6, dtype=np.int32)
     A, marker = drivers.system_matrix(seqs[0], form, ess)
@@ -109,7 +119,8 @@ def test_api_error_behaviour(sess, hier):
         api.Solver(xml, "AMGe", A, None, 0, 0, ess)
 
 
-def test_vcycle_persistent_program_matches_direct(sess, hier):
+@pytest.mark.parametrize("gs_kernel", ["sell"], indirect=True)
+def test_vcycle_persistent_program_matches_direct(sess, hier, gs_kernel):
     """Hierarchy::Mult recorded into the persistent program kernel (pe_prog.cu) must reproduce the
     V-cycle executed kernel by kernel: same arithmetic per row, only the dot-product reduction
     tree differs (1e-13), and it must actually be the path that runs."""
