@@ -129,9 +129,10 @@ def gs_kernel(request):
     capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, old)
 
 
+@pytest.mark.parametrize("dims", [(11, 6, 7), (21, 20, 19)])
 @pytest.mark.parametrize("weights", [(1.0, 1.0), (0.9, 1.2)])
-def test_gauss_seidel_multicolor(ctx, weights, gs_kernel):
-    A = laplace3d(11, 6, 7)
+def test_gauss_seidel_multicolor(ctx, weights, gs_kernel, dims):
+    A = laplace3d(*dims)
     n = A.shape[0]
     rng = np.random.default_rng(5)
     b, x0 = rng.standard_normal(n), rng.standard_normal(n)
