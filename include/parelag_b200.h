@@ -225,6 +225,21 @@ int pe_spadd(pe_ctx *ctx, double a, const pe_mat *A, double b, const pe_mat *B, 
  * stay in the pattern (examples/MultigridTest2Form.cpp:457-464). */
 int pe_mat_eliminate_rowcol(pe_ctx *ctx, pe_mat *A, const int32_t *marker_host);
 
+/* ---- src/hypreExtension utilities on device matrices
+ * pe_mat_delete_zeros : hypre_ParCSRMatrixDeleteZeros (deleteZeros.c:16-47), in place, |a| < tol dropped
+ * pe_mat_sign         : hypre_ParCSRDataTransformationSign (entries -> -1 / 0 / +1 with threshold tol)
+ * pe_mat_diagonal     : hypre_IdentityCSRMatrix (d == NULL) / hypre_DiagonalCSRMatrix (hypre_CSRFactory.c:16-250)
+ * pe_mat_norms        : {l1, linf, max, Frobenius} (hypre_ParCSRMatrixNorms.c:18-195), all-reduced over ranks
+ * pe_mat_compare      : hypre_ParCSRMatrixCompare bit flags (1 rows, 2 cols, 4/8 first/last row, 16/32 first/last
+ *                       diag column, 64 ||A - B||_max > tol) -- the parity comparator
+ * pe_rdp              : hypre_RDP, R^T diag(d) P (par_Tmatmul.c:17-39), rank-local */
+int pe_mat_delete_zeros(pe_ctx *ctx, pe_mat *A, double tol);
+int pe_mat_sign(pe_ctx *ctx, pe_mat *A, double tol);
+int pe_mat_diagonal(pe_ctx *ctx, int32_t n, const pe_vec *d_or_null, pe_mat **out);
+int pe_mat_norms(pe_ctx *ctx, pe_mat *A, double *out4);
+int pe_mat_compare(pe_ctx *ctx, const pe_mat *A, const pe_mat *B, double tol, int32_t *flags);
+int pe_rdp(pe_ctx *ctx, const pe_mat *R, const pe_vec *d, const pe_mat *P, pe_mat **out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -280,10 +280,39 @@ class Mat:
         _chk(lib().pe_fix_zero_rows(self.ctx.h, self.h, C.byref(n)))
         return n.value
 
+    # ---- src/hypreExtension utilities
+    def delete_zeros(self, tol):
+        _chk(lib().pe_mat_delete_zeros(self.ctx.h, self.h, C.c_double(tol)))
+
+    def sign(self, tol=1e-9):
+        _chk(lib().pe_mat_sign(self.ctx.h, self.h, C.c_double(tol)))
+
+    def norms(self):
+        out = np.zeros(4)
+        _chk(lib().pe_mat_norms(self.ctx.h, self.h, _ptr(out)))
+        return dict(l1=out[0], linf=out[1], max=out[2], fro=out[3])
+
+    def compare(self, other, tol):
+        f = C.c_int32()
+        _chk(lib().pe_mat_compare(self.ctx.h, self.h, other.h, C.c_double(tol), C.byref(f)))
+        return f.value
+
+    @staticmethod
+    def diagonal(ctx, n, d=None):
+        out = Mat(ctx)
+        _chk(lib().pe_mat_diagonal(ctx.h, n, None if d is None else d.h, C.byref(out.h)))
+        return out
+
     def free(self):
         if self.h:
             lib().pe_mat_free(self.h)
             self.h = None
+
+
+def rdp(ctx, R, d, P):
+    out = Mat(ctx)
+    _chk(lib().pe_rdp(ctx.h, R.h, d.h, P.h, C.byref(out.h)))
+    return out
 
 
 def spgemm(ctx, A, B):

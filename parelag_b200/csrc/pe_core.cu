@@ -183,6 +183,13 @@ int pe_allreduce_sum(pe_ctx *c, double *d, int count)
     PE_NCCL(g_nccl.AllReduce(d, d, (size_t)count, PE_NCCL_FLOAT64, PE_NCCL_SUM, c->nccl, c->stream));
     return 0;
 }
+// op: ncclRedOp_t (0 sum, 2 max)
+int pe_allreduce(pe_ctx *c, double *d, int count, int op)
+{
+    if (c->nranks == 1) return 0;
+    PE_NCCL(g_nccl.AllReduce(d, d, (size_t)count, PE_NCCL_FLOAT64, op, c->nccl, c->stream));
+    return 0;
+}
 
 // ---------------------------------------------------------------------------
 // per-kernel event profiling

@@ -677,6 +677,21 @@ static int launch_gs_set(pe_smoother *s, int k0, int k1, const double *f, double
     return 0;
 }
 
+// ghost values for one sweep: a zero initial guess is zero on every rank, so the exchange is replaced
+// by clearing the ghost buffer (all ranks take the same branch: iterative_mode is a collective argument)
+static int sweep_halo(pe_mat *A, const double *x_d, bool all_zero)
+{
+    pe_ctx *ctx = A->ctx;
+    if (ctx->nranks == 1) return 0;
+    if (all_zero)
+    {
+        if (A->offd.ncols > 0) PE_CUDA(cudaMemsetAsync(A->x_ext_d, 0, sizeof(double) * (size_t)A->offd.ncols, ctx->stream));
+        return 0;
+    }
+    PE_TRY(pe_halo_exchange(A, x_d));
+    return pe_halo_wait(A);
+}
+
 extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int iterative_mode)
 {
     pe_ctx *ctx = s->ctx;
@@ -691,11 +706,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
         for (int sweep = 0; sweep < s->sweeps; ++sweep)
         {
             const bool zero_guess = !iterative_mode && sweep == 0;
-            if (ctx->nranks > 1)
-            {
-                if (zero_guess) PE_CUDA(cudaMemsetAsync(x->d, 0, sizeof(double) * (size_t)n, st));
-                PE_TRY(pe_halo_exchange(A, x->d)); PE_TRY(pe_halo_wait(A));
-            }
+            PE_TRY(sweep_halo(A, x->d, zero_guess));
             PE_TRY(pe_launch_perm_in(ctx, n, s->pos_d, b->d, zero_guess ? nullptr : x->d, s->fp_d, s->up_d));
             for (int pass = 0; pass < 2; ++pass)
                 for (int cc = (pass == 1 && s->skip_turn) ? 1 : 0; cc < s->nsets; ++cc)
@@ -715,7 +726,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
     const int *oI = A->offd.nnz > 0 ? A->offd.I : nullptr;
     for (int sweep = 0; sweep < s->sweeps; ++sweep) {
         if (s->type == 0 || s->type == 1 || s->type == 5) {
-            if (ctx->nranks > 1) { PE_TRY(pe_halo_exchange(A, x->d)); PE_TRY(pe_halo_wait(A)); }
+            PE_TRY(sweep_halo(A, x->d, !iterative_mode && sweep == 0));
             int tpr = A->tpr;
             int64_t threads = (int64_t)n * tpr;
             int grid = (int)std::min<int64_t>((threads + 255) / 256, (int64_t)PE_SM_COUNT * 64);
@@ -736,7 +747,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
             pe_vec vv{ctx, n, s->v_d};
             PE_TRY(pe_vec_axpby(1.0, &vv, 1.0, x));
         } else if (s->type == 2 || s->type == 4 || s->type == 6) {
-            if (ctx->nranks > 1) { PE_TRY(pe_halo_exchange(A, x->d)); PE_TRY(pe_halo_wait(A)); }
+            PE_TRY(sweep_halo(A, x->d, !iterative_mode && sweep == 0));
             bool general = !(s->weight == 1.0 && s->omega == 1.0);
             double c1 = s->omega * s->weight, c2 = s->omega * (1.0 - s->weight);
             for (int pass = 0; pass < 2; ++pass) {

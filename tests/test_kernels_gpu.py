@@ -210,3 +210,41 @@ def test_fix_zero_rows_and_spadd(ctx):
     assert np.array_equal(G.data, Zo.data)
     S = capi.spadd(ctx, 2.0, dZ, -3.0, capi.Mat.from_scipy(ctx, B)).to_scipy()
     assert abs(S - (2.0 * Zo - 3.0 * B)).max() < 1e-14
+
+
+def test_hypre_extension_utilities(ctx):
+    """src/hypreExtension on device matrices: delete-zeros, sign, identity/diagonal, norms, compare, RDP"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(21)
+    A = sp.random(60, 45, density=0.15, random_state=3, format="csr")
+    A.data = rng.standard_normal(A.nnz)
+    A.data[::5] *= 1e-12
+    dA = capi.Mat.from_scipy(ctx, A)
+    nm = dA.norms()
+    assert abs(nm["l1"] - abs(A).sum(axis=0).max()) < 1e-12 and abs(nm["linf"] - abs(A).sum(axis=1).max()) < 1e-12
+    assert abs(nm["max"] - abs(A).max()) < 1e-14 and abs(nm["fro"] - np.sqrt((A.data ** 2).sum())) < 1e-12
+    # compare: identical, perturbed, different shape
+    dB = capi.Mat.from_scipy(ctx, A)
+    assert dA.compare(dB, 1e-14) == 0
+    B2 = A.copy(); B2.data[7] += 1e-3
+    assert capi.Mat.from_scipy(ctx, B2).compare(dA, 1e-6) == 64
+    assert capi.Mat.from_scipy(ctx, sp.csr_matrix(A[:50])).compare(dA, 1e-6) & (1 | 8 | 64)
+    # delete zeros
+    dA.delete_zeros(1e-9)
+    Az = A.copy(); Az.data[np.abs(Az.data) < 1e-9] = 0; Az.eliminate_zeros()
+    G = dA.to_scipy()
+    assert G.nnz == Az.nnz and abs(G - Az).max() == 0
+    # sign
+    dA.sign(1e-9)
+    assert abs(dA.to_scipy() - Az.sign()).max() == 0
+    # identity / diagonal
+    d = rng.standard_normal(17)
+    assert abs(capi.Mat.diagonal(ctx, 17).to_scipy() - sp.identity(17)).max() == 0
+    assert abs(capi.Mat.diagonal(ctx, 17, capi.Vec(ctx, data=d)).to_scipy() - sp.diags(d)).max() == 0
+    # R^T diag(d) P
+    R = sp.random(30, 12, density=0.3, random_state=5, format="csr")
+    P = sp.random(30, 9, density=0.3, random_state=6, format="csr")
+    w = rng.standard_normal(30)
+    out = capi.rdp(ctx, capi.Mat.from_scipy(ctx, R), capi.Vec(ctx, data=w), capi.Mat.from_scipy(ctx, P)).to_scipy()
+    ref = (R.T @ sp.diags(w) @ P).tocsr()
+    assert abs(out - ref).max() <= 1e-14 * max(abs(ref).max(), 1.0)
