@@ -65,6 +65,9 @@ int pe_api_hexsequence_create_par(const int32_t *procs, int nx, int ny, int nz, 
                                   double svd_tol, pe_sequence **out);
 int pe_api_sequence_get_dofmap(pe_sequence *s, int level, int form, int32_t *ndofs, int64_t *gid, int32_t *owner,
                                int64_t *key, int64_t *true_start, int64_t *true_count, int64_t *global_count);
+/* SharingMap::Assemble (direction 0: local dof vector -> true dof vector, copies of a shared dof summed on its
+ * owner, SharingMap.cpp:768-780) / SharingMap::Distribute (direction 1: true -> local, :664-677), host vectors */
+int pe_api_sequence_dofmap_apply(pe_sequence *s, int level, int form, int direction, const double *in, double *out);
 int pe_api_sequence_true_operator(pe_sequence *s, int level, const char *what, int form, const int32_t *ess_attr,
                                   int nattr, pe_mat **out);
 

@@ -91,6 +91,20 @@ class Sequence:
         _chk(lib().pe_api_sequence_get_dofmap(self.h, level, form, None, _ptr(gid), _ptr(owner), _ptr(key), None, None, None))
         return dict(gid=gid, owner=owner, key=key, start=st.value, ntrue=nt.value, nglobal=ng.value)
 
+    def assemble_vector(self, level, form, local):
+        """SharingMap::Assemble: local dof vector -> true dof vector (copies summed on the owner)"""
+        m = self.dofmap(level, form)
+        x, out = _f64(local), np.empty(m["ntrue"])
+        _chk(lib().pe_api_sequence_dofmap_apply(self.h, level, form, 0, _ptr(x), _ptr(out)))
+        return out
+
+    def distribute_vector(self, level, form, true):
+        """SharingMap::Distribute: true dof vector -> local dof vector"""
+        m = self.dofmap(level, form)
+        x, out = _f64(true), np.empty(len(m["gid"]))
+        _chk(lib().pe_api_sequence_dofmap_apply(self.h, level, form, 1, _ptr(x), _ptr(out)))
+        return out
+
     def true_operator(self, ctx, level, what, form, ess_attr=None):
         """ComputeTrueP / ComputeTrueD (what = "P" | "D") as a device ParCSR matrix"""
         ess = None if ess_attr is None else _i32(ess_attr)

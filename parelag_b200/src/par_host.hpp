@@ -58,7 +58,7 @@ template <class T> inline std::vector<T> AllGather(const pe_host_comm *comm, con
 struct SharingMap
 {
     std::vector<int64_t> gid, key;
-    std::vector<int32_t> owner;
+    std::vector<int32_t> owner, sI, sJ;      // sI/sJ: ranks holding each item (CSR, own rank included)
     int64_t start = 0, ntrue = 0, global = 0;
     int rank = 0;
     std::vector<int32_t> true_to_local;   // owned true index -> local index
@@ -73,7 +73,7 @@ struct SharingMap
     {
         const int n = (int)key.size();
         gid.assign(n, -1); owner.assign(n, comm->rank); shared.assign(n, 0);
-        this->key = key;
+        this->key = key; this->sI = sI; this->sJ = sJ;
         rank = comm->rank;
         int64_t cnt = 0;
         if (pe_par_number_items(comm, n, key.data(), sI.data(), sJ.data(), gid.data(), owner.data(), &start, &cnt, &global))
@@ -86,6 +86,55 @@ struct SharingMap
             const int ns = sI[i + 1] - sI[i];
             if (ns > 1) shared[i] = owner[i] == rank ? 1 : -1;
         }
+    }
+    /// SharingMap::Assemble (SharingMap.cpp:768-780): true[t] = sum of the copies of t on all holders
+    void Assemble(const pe_host_comm *comm, const double *local_in, double *true_out) const
+    {
+        const int n = GetLocalSize();
+        std::fill(true_out, true_out + ntrue, 0.0);
+        std::vector<std::vector<char>> send(comm->size), recv;
+        for (int i = 0; i < n; ++i)
+        {
+            if (owner[i] == rank) true_out[gid[i] - start] += local_in[i];
+            else { Append(send[owner[i]], gid[i]); Append(send[owner[i]], local_in[i]); }
+        }
+        Exchange(comm, send, recv);
+        for (int r = 0; r < comm->size; ++r)       // fixed order: ranks ascending
+            for (size_t q = 0; q + 16 <= recv[r].size(); q += 16)
+            {
+                int64_t g; double v;
+                std::memcpy(&g, recv[r].data() + q, 8); std::memcpy(&v, recv[r].data() + q + 8, 8);
+                true_out[g - start] += v;
+            }
+    }
+    /// SharingMap::Distribute (SharingMap.cpp:664-677): local[i] = true value of item i (owners send to holders)
+    void Distribute(const pe_host_comm *comm, const double *true_in, double *local_out) const
+    {
+        const int n = GetLocalSize();
+        std::vector<std::vector<char>> send(comm->size), recv;
+        for (int i = 0; i < n; ++i)
+            if (owner[i] == rank)
+            {
+                local_out[i] = true_in[gid[i] - start];
+                for (int k = sI[i]; k < sI[i + 1]; ++k)
+                    if (sJ[k] != rank) { Append(send[sJ[k]], gid[i]); Append(send[sJ[k]], local_out[i]); }
+            }
+        Exchange(comm, send, recv);
+        std::unordered_map<int64_t, double> got;
+        for (int r = 0; r < comm->size; ++r)
+            for (size_t q = 0; q + 16 <= recv[r].size(); q += 16)
+            {
+                int64_t g; double v;
+                std::memcpy(&g, recv[r].data() + q, 8); std::memcpy(&v, recv[r].data() + q + 8, 8);
+                got[g] = v;
+            }
+        for (int i = 0; i < n; ++i)
+            if (owner[i] != rank)
+            {
+                auto it = got.find(gid[i]);
+                if (it == got.end()) throw std::runtime_error("SharingMap::Distribute: owner did not send a shared item");
+                local_out[i] = it->second;
+            }
     }
     /// identity map of a single rank
     void SetUpSerial(int n)

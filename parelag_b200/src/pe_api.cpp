@@ -79,6 +79,18 @@ extern "C" int pe_api_sequence_get_dofmap(pe_sequence *s, int level, int form, i
     if (global_count) *global_count = m->global;
     API_CATCH
 }
+/// SharingMap::Assemble (direction 0: local dof vector -> true dof vector, copies summed) and
+/// SharingMap::Distribute (direction 1: true -> local) on host vectors
+extern "C" int pe_api_sequence_dofmap_apply(pe_sequence *s, int level, int form, int direction, const double *in, double *out)
+{
+    API_TRY
+    auto &seq = *s->levels.at(level);
+    const par::SharingMap *m = seq.GetDofTrueDof(form);
+    PARELAG_TEST_FOR_EXCEPTION(!m || !seq.GetComm(), std::runtime_error, "pe_api_sequence_dofmap_apply: no dof <-> true dof map");
+    if (direction == 0) m->Assemble(seq.GetComm(), in, out);
+    else m->Distribute(seq.GetComm(), in, out);
+    API_CATCH
+}
 /// ComputeTrueP / ComputeTrueD as device ParCSR matrices (what = "P" or "D")
 extern "C" int pe_api_sequence_true_operator(pe_sequence *s, int level, const char *what, int form, const int32_t *ess_attr, int nattr,
                                              pe_mat **out)

@@ -103,6 +103,15 @@ def main():
         assert sends[int(p)][rank] == want
     M.free()
 
+    # ---- T3b: SharingMap::Assemble / Distribute on vectors
+    ones = S.assemble_vector(0, 2, np.ones(len(m["gid"])))
+    nshared_owned = int(((m["owner"] == rank) & np.isin(m["key"], list(set(both[0]) & set(both[1])))).sum()) if False else None
+    assert set(np.unique(ones).tolist()) <= {1.0, 2.0}                      # multiplicity of every true dof
+    assert int(sum(gather(float(ones.sum())))) == int(sum(gather(len(m["gid"]))))
+    tv = np.arange(m["start"], m["start"] + m["ntrue"], dtype=np.float64)   # true vector = its own global id
+    loc = S.distribute_vector(0, 2, tv)
+    assert np.array_equal(loc, m["gid"].astype(np.float64))
+
     # ---- T4: IgnoreNonLocalRange keeps the owner's rows only (D_2 : H(div) -> L2)
     D = sp.csr_matrix(seq_loc.D[2])
     m3 = maps[3]
