@@ -575,3 +575,173 @@ class BlockHierarchy(Hierarchy):
         if L.get("post") is not None:
             sol = L["post"].apply(rhs, sol, True)
         return sol
+
+
+def fgmres(A, prec, b, rtol=1e-6, atol=1e-6, max_iter=300, restart=50):
+    """mfem::FGMRESSolver::Mult (flexible, right-preconditioned; history = || r ||); restated, parity unpinned."""
+    Amul = (lambda v: matvec(A, v)) if sp.issparse(A) else A
+    b = np.asarray(b, dtype=np.float64)
+    n, m = len(b), restart
+    x, r = np.zeros(n), b.copy()
+    beta = float(np.sqrt(r @ r))
+    hist = [beta]
+    final_norm = max(rtol * beta, atol)
+    if beta <= final_norm:
+        return x, 0, True, hist
+
+    def gen_rot(dx, dy):
+        if dy == 0.0:
+            return 1.0, 0.0
+        if abs(dy) > abs(dx):
+            t = dx / dy
+            sn = 1.0 / np.sqrt(1.0 + t * t)
+            return t * sn, sn
+        t = dy / dx
+        cs = 1.0 / np.sqrt(1.0 + t * t)
+        return cs, t * cs
+    rot = lambda dx, dy, c, s: (c * dx + s * dy, -s * dx + c * dy)
+
+    def update(x, k, H, s, Z):
+        y = s[:k + 1].copy()
+        for i in range(k, -1, -1):
+            y[i] /= H[i, i]
+            for j in range(i - 1, -1, -1):
+                y[j] -= H[j, i] * y[i]
+        for j in range(k + 1):
+            x = x + y[j] * Z[j]
+        return x
+    j = 1
+    while j <= max_iter:
+        H = np.zeros((m + 1, m)); s = np.zeros(m + 1); cs = np.zeros(m + 1); sn = np.zeros(m + 1)
+        V, Z = [r / beta], []
+        s[0] = beta
+        i = 0
+        while i < m and j <= max_iter:
+            Z.append(prec(V[i]) if prec is not None else V[i].copy())
+            r = Amul(Z[i])
+            for k in range(i + 1):
+                H[k, i] = float(r @ V[k])
+                r = r - H[k, i] * V[k]
+            H[i + 1, i] = float(np.sqrt(r @ r))
+            V.append(r / H[i + 1, i])
+            for k in range(i):
+                H[k, i], H[k + 1, i] = rot(H[k, i], H[k + 1, i], cs[k], sn[k])
+            cs[i], sn[i] = gen_rot(H[i, i], H[i + 1, i])
+            H[i, i], H[i + 1, i] = rot(H[i, i], H[i + 1, i], cs[i], sn[i])
+            s[i], s[i + 1] = rot(s[i], s[i + 1], cs[i], sn[i])
+            resid = abs(s[i + 1])
+            hist.append(float(resid))
+            if resid <= final_norm:
+                return update(x, i, H, s, Z), j, True, hist
+            i += 1; j += 1
+        x = update(x, i - 1, H, s, Z)
+        r = b - Amul(x)
+        beta = float(np.sqrt(r @ r))
+        if beta <= final_norm:
+            return x, j, True, hist
+    return x, max_iter, False, hist
+
+
+def bicgstab(A, prec, b, rtol=1e-6, atol=1e-6, max_iter=300):
+    """mfem::BiCGSTABSolver::Mult; history[i] = ||r|| after iteration i; restated, parity unpinned."""
+    Amul = (lambda v: matvec(A, v)) if sp.issparse(A) else A
+    M = prec if prec is not None else (lambda v: v.copy())
+    b = np.asarray(b, dtype=np.float64)
+    x, r = np.zeros_like(b), b.copy()
+    rt = r.copy()
+    resid = float(np.sqrt(r @ r))
+    hist = [resid]
+    goal = max(resid * rtol, atol)
+    if resid <= goal:
+        return x, 0, True, hist
+    rho_2 = alpha = omega = 1.0
+    p = v = None
+    for i in range(1, max_iter + 1):
+        rho_1 = float(rt @ r)
+        if rho_1 == 0.0:
+            return x, i, False, hist
+        if i == 1:
+            p = r.copy()
+        else:
+            beta = (rho_1 / rho_2) * (alpha / omega)
+            p = p - omega * v
+            p = r + beta * p
+        phat = M(p)
+        v = Amul(phat)
+        alpha = rho_1 / float(rt @ v)
+        s = r - alpha * v
+        resid = float(np.sqrt(s @ s))
+        if resid < goal:
+            hist.append(resid)
+            return x + alpha * phat, i, True, hist
+        shat = M(s)
+        t = Amul(shat)
+        omega = float(t @ s) / float(t @ t)
+        x = x + alpha * phat
+        x = x + omega * shat
+        r = s - omega * t
+        rho_2 = rho_1
+        resid = float(np.sqrt(r @ r))
+        hist.append(resid)
+        if resid < goal:
+            return x, i, True, hist
+        if omega == 0.0:
+            return x, i, False, hist
+    return x, max_iter, False, hist
+
+
+def minres(A, prec, b, rtol=1e-6, atol=1e-6, max_iter=300):
+    """mfem::MINRESSolver::Mult (van der Vorst Fig. 6.9 with an SPD preconditioner); history = |eta|;
+    restated, parity unpinned."""
+    Amul = (lambda v: matvec(A, v)) if sp.issparse(A) else A
+    b = np.asarray(b, dtype=np.float64)
+    x = np.zeros_like(b)
+    v1 = b.copy()
+    u1 = prec(v1) if prec is not None else None
+    z = u1 if prec is not None else v1
+    eta = beta = float(np.sqrt(z @ v1))
+    hist = [eta]
+    goal = max(rtol * eta, atol)
+    gamma0 = gamma1 = 1.0
+    sigma0 = sigma1 = 0.0
+    v0 = np.zeros_like(b); w0 = np.zeros_like(b); w1 = np.zeros_like(b)
+    if eta <= goal:
+        return x, 0, True, hist
+    for it in range(1, max_iter + 1):
+        v1 = v1 / beta
+        if prec is not None:
+            u1 = u1 / beta
+        z = u1 if prec is not None else v1
+        q = Amul(z)
+        alpha = float(z @ q)
+        if it > 1:
+            q = q - beta * v0
+        v0 = q - alpha * v1
+        delta = gamma1 * alpha - gamma0 * sigma1 * beta
+        rho3 = sigma0 * beta
+        rho2 = sigma1 * alpha + gamma0 * gamma1 * beta
+        if prec is None:
+            beta = float(np.sqrt(v0 @ v0))
+        else:
+            q = prec(v0)
+            beta = float(np.sqrt(v0 @ q))
+        rho1 = float(np.hypot(delta, beta))
+        if it == 1:
+            w0 = z / rho1
+        elif it == 2:
+            w0 = z / rho1 - (rho2 / rho1) * w1
+        else:
+            w0 = -(rho3 / rho1) * w0 - (rho2 / rho1) * w1
+            w0 = w0 + z / rho1
+        gamma0, gamma1 = gamma1, delta / rho1
+        x = x + gamma1 * eta * w0
+        sigma0, sigma1 = sigma1, beta / rho1
+        eta = -sigma1 * eta
+        hist.append(abs(eta))
+        if abs(eta) <= goal:
+            return x, it, True, hist
+        if prec is not None:
+            u1, q = q, u1
+        v0, v1 = v1, v0
+        w0, w1 = w1, w0
+    return x, max_iter, False, hist

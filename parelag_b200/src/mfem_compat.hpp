@@ -229,6 +229,11 @@ private:
     mutable bool host_valid_ = false, dev_valid_ = false;
 };
 
+/// z = a*x + b*y  (mfem::add)
+inline void add(double a, const Vector &x, double b, const Vector &y, Vector &z)
+{
+    if (z.Size()) PE_CALL(pe_vec_add3(a, x.Read(), b, y.Read(), z.Write()));
+}
 /// z = x + a*y  (mfem::add)
 inline void add(const Vector &x, double a, const Vector &y, Vector &z)
 {

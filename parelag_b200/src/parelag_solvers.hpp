@@ -232,9 +232,11 @@ public:
         : Solver(A->Height(), A->Width(), false), A_(std::move(A)), Prec_(std::move(Prec))
     {
         const std::string name = params.Get("Solver name", "PCG");
-        PARELAG_TEST_FOR_EXCEPTION(name != "PCG" && name != "CG" && name != "GMRES", std::runtime_error,
-                                   "KrylovSolver: solver \"" << name << "\" is not available on the GPU path in this round (PCG, GMRES)");
+        PARELAG_TEST_FOR_EXCEPTION(name != "PCG" && name != "CG" && name != "GMRES" && name != "FGMRES" && name != "MINRES" && name != "BICGSTAB",
+                                   std::runtime_error, "KrylovSolver::KrylovSolver(...): Bad solver type (\"" << name << "\").\n\n"
+                                   "Valid choices are \"CG\", \"GMRES\", \"FGMRES\", \"BiCGSTAB\", \"MINRES\".");
         gmres_ = name == "GMRES";
+        method_ = name == "FGMRES" ? 1 : (name == "MINRES" ? 2 : (name == "BICGSTAB" ? 3 : 0));
         restart_ = params.Get("Restart size", 50);
         print_level_ = params.Get("Print level", -1);
         rel_tol_ = params.Get("Relative tolerance", 0.0);
@@ -248,7 +250,7 @@ public:
     /// tests of mfem::CGSolver::Mult) live in HBM.  Once the stopping test fires the step lengths
     /// become 0, so x equals the result of the early exit; there is no host synchronisation and
     /// the enclosing V-cycle can be captured in a CUDA graph.
-    bool DeviceResident() const { return !gmres_ && max_iter_ >= 1 && max_iter_ <= 10 && print_level_ < 0 && !final_paragraph_; }
+    bool DeviceResident() const { return !gmres_ && method_ == 0 && max_iter_ >= 1 && max_iter_ <= 10 && print_level_ < 0 && !final_paragraph_; }
     bool CaptureSafe() const override
     {
         return DeviceResident() && (!Prec_ || SolverCaptureSafe(Prec_.get())) &&
@@ -257,6 +259,9 @@ public:
     void Mult(const mfem::Vector &b, mfem::Vector &x) const override
     {
         if (gmres_) { MultGMRES(b, x); return; }
+        if (method_ == 1) { MultFGMRES(b, x); return; }
+        if (method_ == 2) { MultMINRES(b, x); return; }
+        if (method_ == 3) { MultBiCGSTAB(b, x); return; }
         if (DeviceResident()) { MultDeviceResident(b, x); return; }
         const int n = Height();
         r_.SetSize(n); d_.SetSize(n); z_.SetSize(n);
@@ -380,6 +385,173 @@ private:
         }
         final_norm_ = beta; final_iter_ = max_iter_; converged_ = false;
     }
+    /// mfem::FGMRESSolver::Mult restated (flexible, right-preconditioned; monitor || r ||)
+    void MultFGMRES(const mfem::Vector &b, mfem::Vector &x) const
+    {
+        const int n = Height(), m = restart_;
+        r_.SetSize(n);
+        mfem::Vector &r = r_;
+        history_.clear(); stats_on_device_ = false; converged_ = false; final_iter_ = 0;
+        std::vector<double> H((size_t)(m + 1) * m, 0.0), s(m + 1), cs(m + 1), sn(m + 1);
+        auto h = [&](int i, int j) -> double & { return H[(size_t)j * (m + 1) + i]; };
+        auto norm = [](const mfem::Vector &v) { return std::sqrt(v * v); };
+        if (this->iterative_mode) { A_->Mult(x, r); mfem::add(b, -1.0, r, r); }
+        else { x = 0.0; r = b; }
+        double beta = norm(r), resid = beta;
+        history_.push_back(beta);
+        const double final_norm = std::max(rel_tol_ * beta, abs_tol_);
+        if (beta <= final_norm) { final_norm_ = beta; converged_ = true; return; }
+        if ((int)v_.size() < m + 1) v_.resize(m + 1);
+        if ((int)zz_.size() < m + 1) zz_.resize(m + 1);
+        auto update = [&](int k)
+        {
+            std::vector<double> y(s.begin(), s.begin() + k + 1);
+            for (int i = k; i >= 0; --i)
+            {
+                y[i] /= h(i, i);
+                for (int j = i - 1; j >= 0; --j) y[j] -= h(j, i) * y[i];
+            }
+            for (int j = 0; j <= k; ++j) x.Add(y[j], zz_[j]);
+        };
+        for (int j = 1; j <= max_iter_;)
+        {
+            v_[0].Set(1.0 / beta, r);
+            std::fill(s.begin(), s.end(), 0.0);
+            s[0] = beta;
+            int i;
+            for (i = 0; i < m && j <= max_iter_; ++i, ++j)
+            {
+                zz_[i].SetSize(n);
+                if (Prec_) Prec_->Mult(v_[i], zz_[i]); else zz_[i] = v_[i];
+                A_->Mult(zz_[i], r);
+                for (int k = 0; k <= i; ++k) { h(k, i) = r * v_[k]; r.Add(-h(k, i), v_[k]); }
+                h(i + 1, i) = norm(r);
+                v_[i + 1].Set(1.0 / h(i + 1, i), r);
+                for (int k = 0; k < i; ++k) ApplyPlaneRotation(h(k, i), h(k + 1, i), cs[k], sn[k]);
+                GeneratePlaneRotation(h(i, i), h(i + 1, i), cs[i], sn[i]);
+                ApplyPlaneRotation(h(i, i), h(i + 1, i), cs[i], sn[i]);
+                ApplyPlaneRotation(s[i], s[i + 1], cs[i], sn[i]);
+                resid = std::fabs(s[i + 1]);
+                history_.push_back(resid);
+                if (print_level_ == 1) std::printf("   Pass : %2d   Iteration : %3d  || r || = %g\n", (j - 1) / m + 1, j, resid);
+                if (resid <= final_norm) { update(i); final_norm_ = resid; final_iter_ = j; converged_ = true; return; }
+            }
+            update(i - 1);
+            A_->Mult(x, r);
+            mfem::add(b, -1.0, r, r);
+            beta = norm(r);
+            if (beta <= final_norm) { final_norm_ = beta; final_iter_ = j; converged_ = true; return; }
+        }
+        final_norm_ = beta; final_iter_ = max_iter_; converged_ = false;
+    }
+    /// mfem::BiCGSTABSolver::Mult restated; history[i] = ||r|| after iteration i
+    void MultBiCGSTAB(const mfem::Vector &b, mfem::Vector &x) const
+    {
+        const int n = Height();
+        mfem::Vector &r = r_, &p = d_, &v = z_;
+        r.SetSize(n); p.SetSize(n); v.SetSize(n);
+        if ((int)v_.size() < 5) v_.resize(5);
+        mfem::Vector &rtilde = v_[0], &phat = v_[1], &sv = v_[2], &shat = v_[3], &t = v_[4];
+        for (int q = 0; q < 5; ++q) v_[q].SetSize(n);
+        history_.clear(); stats_on_device_ = false; converged_ = false; final_iter_ = 0;
+        auto norm = [](const mfem::Vector &w) { return std::sqrt(w * w); };
+        if (this->iterative_mode) { A_->Mult(x, r); mfem::add(b, -1.0, r, r); }
+        else { x = 0.0; r = b; }
+        rtilde = r;
+        double resid = norm(r), rho_1 = 0, rho_2 = 1, alpha = 1, beta, omega = 1;
+        history_.push_back(resid);
+        const double tol_goal = std::max(resid * rel_tol_, abs_tol_);
+        if (resid <= tol_goal) { final_norm_ = resid; converged_ = true; return; }
+        for (int i = 1; i <= max_iter_; ++i)
+        {
+            rho_1 = rtilde * r;
+            if (rho_1 == 0.0) { final_norm_ = resid; final_iter_ = i; return; }
+            if (i == 1) p = r;
+            else
+            {
+                beta = (rho_1 / rho_2) * (alpha / omega);
+                mfem::add(p, -omega, v, p);
+                mfem::add(r, beta, p, p);
+            }
+            if (Prec_) Prec_->Mult(p, phat); else phat = p;
+            A_->Mult(phat, v);
+            alpha = rho_1 / (rtilde * v);
+            mfem::add(r, -alpha, v, sv);
+            resid = norm(sv);
+            if (resid < tol_goal)
+            {
+                x.Add(alpha, phat);
+                history_.push_back(resid);
+                final_norm_ = resid; final_iter_ = i; converged_ = true; return;
+            }
+            if (Prec_) Prec_->Mult(sv, shat); else shat = sv;
+            A_->Mult(shat, t);
+            omega = (t * sv) / (t * t);
+            x.Add(alpha, phat);
+            x.Add(omega, shat);
+            mfem::add(sv, -omega, t, r);
+            rho_2 = rho_1;
+            resid = norm(r);
+            history_.push_back(resid);
+            if (print_level_ == 1) std::printf("   Iteration : %3d   ||r|| = %g\n", i, resid);
+            if (resid < tol_goal) { final_norm_ = resid; final_iter_ = i; converged_ = true; return; }
+            if (omega == 0.0) { final_norm_ = resid; final_iter_ = i; return; }
+        }
+        final_norm_ = resid; final_iter_ = max_iter_;
+    }
+    /// mfem::MINRESSolver::Mult restated (van der Vorst, Fig. 6.9, with an SPD preconditioner); history = |eta|
+    void MultMINRES(const mfem::Vector &b, mfem::Vector &x) const
+    {
+        const int n = Height();
+        if ((int)v_.size() < 6) v_.resize(6);
+        for (int q = 0; q < 6; ++q) v_[q].SetSize(n);
+        mfem::Vector *v0 = &v_[0], *v1 = &v_[1], *w0 = &v_[2], *w1 = &v_[3], *q = &v_[4], *u1 = &v_[5];
+        history_.clear(); stats_on_device_ = false; converged_ = true; final_iter_ = 0;
+        if (!this->iterative_mode) { *v1 = b; x = 0.0; }
+        else { A_->Mult(x, *v1); mfem::add(b, -1.0, *v1, *v1); }
+        if (Prec_) Prec_->Mult(*v1, *u1);
+        mfem::Vector *z = Prec_ ? u1 : v1;
+        double beta, eta, gamma0 = 1.0, gamma1 = 1.0, sigma0 = 0.0, sigma1 = 0.0, alpha, delta, rho1, rho2, rho3;
+        eta = beta = std::sqrt((*z) * (*v1));
+        history_.push_back(eta);
+        const double norm_goal = std::max(rel_tol_ * eta, abs_tol_);
+        int it = 0;
+        if (eta > norm_goal)
+        {
+            bool done = false;
+            for (it = 1; it <= max_iter_; ++it)
+            {
+                *v1 *= 1.0 / beta;
+                if (Prec_) *u1 *= 1.0 / beta;
+                z = Prec_ ? u1 : v1;
+                A_->Mult(*z, *q);
+                alpha = (*z) * (*q);
+                if (it > 1) q->Add(-beta, *v0);
+                mfem::add(*q, -alpha, *v1, *v0);
+                delta = gamma1 * alpha - gamma0 * sigma1 * beta;
+                rho3 = sigma0 * beta;
+                rho2 = sigma1 * alpha + gamma0 * gamma1 * beta;
+                if (!Prec_) beta = std::sqrt((*v0) * (*v0));
+                else { Prec_->Mult(*v0, *q); beta = std::sqrt((*v0) * (*q)); }
+                rho1 = std::hypot(delta, beta);
+                if (it == 1) w0->Set(1.0 / rho1, *z);
+                else if (it == 2) mfem::add(1.0 / rho1, *z, -rho2 / rho1, *w1, *w0);
+                else { mfem::add(-rho3 / rho1, *w0, -rho2 / rho1, *w1, *w0); w0->Add(1.0 / rho1, *z); }
+                gamma0 = gamma1; gamma1 = delta / rho1;
+                x.Add(gamma1 * eta, *w0);
+                sigma0 = sigma1; sigma1 = beta / rho1;
+                eta = -sigma1 * eta;
+                history_.push_back(std::fabs(eta));
+                if (print_level_ == 1) std::printf("MINRES: iteration %3d: ||r||_B = %g\n", it, std::fabs(eta));
+                if (std::fabs(eta) <= norm_goal) { done = true; break; }
+                if (Prec_) std::swap(u1, q);
+                std::swap(v0, v1);
+                std::swap(w0, w1);
+            }
+            if (!done) { converged_ = false; --it; }
+        }
+        final_iter_ = it; final_norm_ = std::fabs(eta);
+    }
     static void GeneratePlaneRotation(double &dx, double &dy, double &cs, double &sn)
     {
         if (dy == 0.0) { cs = 1.0; sn = 0.0; }
@@ -442,7 +614,8 @@ private:
     double rel_tol_ = 0.0, abs_tol_ = 0.0;
     bool final_paragraph_ = false, gmres_ = false;
     int restart_ = 50;
-    mutable std::vector<mfem::Vector> v_;       // Krylov basis of GMRES
+    int method_ = 0;                            // 0 PCG/GMRES, 1 FGMRES, 2 MINRES, 3 BiCGStab
+    mutable std::vector<mfem::Vector> v_, zz_;  // Krylov bases of (F)GMRES / work vectors
     mutable mfem::Vector r_, d_, z_;
     mutable std::vector<double> history_;
     mutable bool converged_ = false;

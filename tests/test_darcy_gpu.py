@@ -58,3 +58,53 @@ def test_gmres_block_preconditioners(sess, hier, block, amge_prec):
     # the computed solution solves the saddle-point system
     assert np.linalg.norm(A0.mult(x) - b) <= 5e-2 * np.linalg.norm(b)
     solver.free(); S.free()
+
+
+def test_spe10_shaped_darcy_block_ldu(sess):
+    """configs "MultigridTestSPE10-shaped": anisotropic cells (20 x 10 x 2) and a synthetic lognormal
+    permeability (4 decades) in the H(div) mass matrix; GMRES + Block LDU with AMGe-GS on A00
+    (examples/example_parameterlists/spe10_example_parameters.xml, BoomerAMG replaced by l1-GS)."""
+    dims, L = (8, 8, 4), (160.0, 80.0, 8.0)
+    rng = np.random.default_rng(13)
+    kinv = 10.0 ** (-np.clip(rng.normal(-1.0, 1.5, size=dims[0] * dims[1] * dims[2]), -4.0, 2.0))   # 1/k per cell
+    mesh, seqs = amge.build_hierarchy(dims, 2, L=L, beta=kinv, jstart=2)
+    S = api.Sequence.hex(dims, 2, L=L, beta=kinv, jstart=2)
+    # coarse spaces under 4-decade coefficients: P of H(div) and L2 vs the oracle
+    for j in (2, 3):
+        P, Po = S.get_csr(0, "P", j), sp.csr_matrix(seqs[0].P[j])
+        assert abs(P - Po).max() <= 1e-10 * abs(Po).max()
+    M, B, Bt = S.assemble_darcy(sess, 0)
+    nu, npr = M.info()[0], B.info()[0]
+    b = np.concatenate([np.zeros(nu), np.ones(npr)])            # unit source
+    Mo, Bo = drivers.darcy_blocks(seqs[0])
+    A0 = orc.BlockOp([[Mo, sp.csr_matrix(Bo.T)], [Bo, None]])
+
+    def amge_gs(Mx):
+        H = drivers.amge_pcg_solver(seqs, 2, np.zeros(6, dtype=np.int32), Mx, hiptmair=False)
+        return H.mult
+    negS = sp.csr_matrix(orc.schur_complement(Mo, sp.csr_matrix(Bo.T), Bo, None, 1.0, "DIAGONAL") * (-1.0))
+    Sg = orc.Smoother(negS, type=2)
+    inv = amge_gs(Mo)
+    ldu = orc.BlockLDU(A0, inv, inv, inv, lambda r: Sg.apply(r, np.zeros_like(r), False), 0.775)
+    xo, ito, convo, histo = orc.gmres(A0.mult, lambda r: ldu.apply(r, np.zeros_like(r), False), b, rtol=1e-6, atol=1e-6,
+                                      max_iter=300, restart=50)
+    lib = drivers.library_entries(2)                            # Gauss-Seidel, PCG-GS (+ unused Hiptmair entries)
+    lib["AMGe-GS"] = ("AMGe", {"Maximum levels": -1, "Forms": [2], "PreSmoother": "Gauss-Seidel", "PostSmoother": "Gauss-Seidel",
+                               "Coarse solver": "PCG-GS2", "Cycle type": "V-cycle"})
+    lib["PCG-GS2"] = ("Krylov", {"Solver name": "PCG", "Preconditioner": "Gauss-Seidel", "Print level": -1, "Maximum iterations": 3,
+                                 "Relative tolerance": 1e-4, "Absolute tolerance": 1e-4})
+    lib["Block-LDU-AMGe-GS"] = ("Block LDU", {"Damping Factor": 0.775, "A00_1 Inverse": "AMGe-GS", "A00_2 Inverse": "AMGe-GS",
+                                              "A00_3 Inverse": "AMGe-GS", "Alpha": 1.0, "S Type": "Diagonal", "S Inverse": "Gauss-Seidel"})
+    lib["GMRES-Block-LDU-AMGe-GS"] = ("Krylov", {"Solver name": "GMRES", "Preconditioner": "Block-LDU-AMGe-GS", "Print level": -1,
+                                                 "Maximum iterations": 300, "Relative tolerance": 1e-6, "Absolute tolerance": 1e-6,
+                                                 "Restart size": 50})
+    solver = api.BlockSolver(api.library_xml(lib), "GMRES-Block-LDU-AMGe-GS", [[M, Bt], [B, None]], S, 0, [2, 3],
+                             ess_attr=np.zeros((2, 6), dtype=np.int32))
+    x = solver.mult(b)
+    hist, it, conv = solver.history()
+    assert conv and convo and abs(it - ito) <= 1, (it, ito)
+    m = min(len(hist), len(histo))
+    ho = np.array(histo[:m])
+    sel = ho > 1e-7 * ho[0]
+    assert (np.abs(hist[:m] - ho)[sel] / ho[sel]).max() < 1e-7
+    solver.free(); S.free()

@@ -157,3 +157,34 @@ def test_vcycle_persistent_program_matches_direct(sess, hier, gs_kernel):
     assert np.linalg.norm(outs[True] - outs[False]) <= 1e-13 * np.linalg.norm(zo)
     assert np.linalg.norm(outs[True] - zo) <= 1e-11 * np.linalg.norm(zo)
     S.free()
+
+
+@pytest.mark.parametrize("name", ["GMRES", "FGMRES", "BICGSTAB", "MINRES"])
+def test_other_krylov_solvers(sess, hier, name):
+    """KrylovSolver "Solver name" = GMRES / FGMRES / BICGSTAB / MINRES (mfem::*Solver::Mult restated) with an
+    l1-Jacobi preconditioner (SPD, order independent) on the H1 system: monitored norm history vs the oracle."""
+    mesh, seqs = hier
+    ess = np.ones(6, dtype=np.int32)
+    A, marker = drivers.system_matrix(seqs[0], 0, ess)
+    rng = np.random.default_rng(17)
+    b = rng.standard_normal(A.shape[0]); b[marker] = 0.0
+    So = orc.Smoother(A, type=1)
+    prec = lambda r: So.apply(r, np.zeros_like(r), False)
+    fn = {"GMRES": orc.gmres, "FGMRES": orc.fgmres, "BICGSTAB": orc.bicgstab, "MINRES": orc.minres}[name]
+    kw = dict(rtol=1e-8, atol=1e-12, max_iter=200)
+    if name in ("GMRES", "FGMRES"):
+        kw["restart"] = 20
+    xo, ito, convo, histo = fn(A, prec, b, **kw)
+    lib = {"L1J": ("Hypre", {"Type": "L1 Jacobi", "Sweeps": 1}),
+           "K": ("Krylov", {"Solver name": name, "Preconditioner": "L1J", "Print level": -1, "Maximum iterations": 200,
+                            "Relative tolerance": 1e-8, "Absolute tolerance": 1e-12, "Restart size": 20})}
+    solver = api.Solver(api.library_xml(lib), "K", A, None, 0, 0, ess)
+    x = solver.mult(b)
+    hist, it, conv = solver.history()
+    assert conv and convo and abs(it - ito) <= 1, (name, it, ito, conv, convo)
+    m = min(len(hist), len(histo))
+    ho = np.array(histo[:m])
+    sel = ho > 1e-6 * ho[0]
+    assert (np.abs(hist[:m] - ho)[sel] / ho[sel]).max() < 1e-8
+    assert np.linalg.norm(x - xo) <= 1e-6 * np.linalg.norm(xo)
+    solver.free()
