@@ -368,7 +368,7 @@ def main():
         for _ in range(args.steps):
             solver.prec_mult_device(r_dev, z_dev)
         ctx.profile(False)
-        names = {0: "k_spmv", 1: "k_gs_set", 2: "k_jacobi_update"}
+        names = {0: "k_sell_spmv", 1: "k_sell_gs", 2: "k_jacobi_update", 3: "k_gs_set (coarse levels)"}
         prof = {names[i]: ctx.profile_get(i) for i in names}
         dom = max(prof, key=lambda k: prof[k][1])
         cnt, pms, pbytes = prof[dom]

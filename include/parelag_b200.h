@@ -74,8 +74,10 @@ int64_t pe_ctx_launch_count(const pe_ctx *ctx);
 int pe_ctx_timer_start(pe_ctx *ctx);
 int pe_ctx_timer_stop(pe_ctx *ctx, float *ms);
 /* per-kernel CUDA-event profiling on the context's stream (roofline in bench.py): enable=1
- * resets and starts, 0 stops.  kernel ids: 0 = SpMV (k_spmv), 1 = Gauss-Seidel set
- * (k_gs_set), 2 = Jacobi update.  total_bytes = algorithmic bytes of the launches. */
+ * resets and starts, 0 stops.  kernel ids: 0 = SpMV (all variants), 1 = k_sell_gs colour launches of the
+ * bandwidth-bound class (>= 64 MB algorithmic bytes: the fine level), 2 = Jacobi update, 3 = the other
+ * Gauss-Seidel launches (coarse levels: k_gs_set<TPR>, small k_sell_gs).  total_bytes = algorithmic bytes
+ * of the launches. */
 int pe_ctx_profile(pe_ctx *ctx, int enable);
 int pe_ctx_profile_get(pe_ctx *ctx, int kernel_id, int64_t *count, double *total_ms, double *total_bytes);
 /* process-wide tuning knobs (tests force either kernel family; defaults in brackets):

@@ -647,7 +647,7 @@ static int launch_gs_set(pe_smoother *s, int k0, int k1, const double *f, double
         int c = 0;
         while (s->set_starts[c] != k0) ++c;
         const int b0 = s->set_rb[c], b1 = s->set_rb[c + 1];
-        if (ctx->prof) PE_TRY(pe_prof_begin(ctx, 1, 12.0 * (double)(s->set_pI[c + 1] - s->set_pI[c]) + 4.0 * rows + 32.0 * rows));
+        if (ctx->prof) PE_TRY(pe_prof_begin(ctx, 3, 12.0 * (double)(s->set_pI[c + 1] - s->set_pI[c]) + 4.0 * rows + 32.0 * rows));
         k_gs_set_stream<<<b1 - b0, 256, 0, ctx->stream>>>(b0, s->P.rb, s->P.I, s->P.J, s->P.A, s->perm_d, s->A->diag.ncols,
                                                          f, u, s->A->x_ext_d, s->l1_d);
         PE_LAUNCHED(ctx);
@@ -661,7 +661,7 @@ static int launch_gs_set(pe_smoother *s, int k0, int k1, const double *f, double
     if (ctx->prof)
     {
         const double nnz_set = (double)(s->pI_at(k1) - s->pI_at(k0));
-        PE_TRY(pe_prof_begin(ctx, 1, 12.0 * nnz_set + 4.0 * rows + 32.0 * rows));
+        PE_TRY(pe_prof_begin(ctx, 3, 12.0 * nnz_set + 4.0 * rows + 32.0 * rows));
     }
     switch (tpr) {
     case 1: LAUNCH(1); break;
@@ -713,7 +713,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
                 {
                     const int c = pass == 0 ? cc : s->nsets - 1 - cc;
                     if (s->slice_starts[c + 1] == s->slice_starts[c]) continue;
-                    PE_TRY(pe_prof_begin(ctx, 1, s->set_bytes[c]));
+                    PE_TRY(pe_prof_begin(ctx, s->set_bytes[c] >= 64e6 ? 1 : 3, s->set_bytes[c]));
                     PE_TRY(pe_launch_sell_gs(ctx, s->S, s->slice_starts[c], s->slice_starts[c + 1], s->npad, s->fp_d, s->up_d,
                                              ghosts ? A->x_ext_d : nullptr, s->l1p_d));
                     PE_TRY(pe_prof_end(ctx));
