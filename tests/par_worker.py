@@ -27,7 +27,13 @@ def main():
     comm = par.HostComm()
     api.set_host_comm(comm)
 
-    # ---- T1: true numbering of shared items
+    # ---- T1: true numbering of shared items (two-rank layout)
+    if size == 2:
+        t1_numbering(comm, rank)
+    run_boxes(comm, rank, size)
+
+
+def t1_numbering(comm, rank):
     keys = [100, 101, 102, 200 + rank]                      # 100..102 held by both ranks, one private item each
     sharers = [[0, 1], [0, 1], [0, 1], [rank]]
     if rank == 1:
@@ -39,11 +45,14 @@ def main():
     assert sorted(set(allk[0].values()) | set(allk[1].values())) == list(range(5))
     assert all(o == 0 for k, o in zip(keys, owner) if k < 200)
 
-    # ---- T2: box-decomposed hierarchy (topology + fine dof maps), 2 x 1 x 1 boxes of 4^3 hexahedra
+
+
+def run_boxes(comm, rank, size):
+    # ---- T2: box-decomposed hierarchy (topology + fine dof maps), 2x1x1 / 2x2x1 / 2x2x2 boxes of 4^3 hexahedra
     n, lev = 4, 3
-    procs = (2, 1, 1)
+    procs = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[size]
     S = api.Sequence.hex_par(procs, (n, n, n), lev, L=(1.0, 1.0, 1.0), jstart=1, svd_tol=-1.0)
-    N = (2 * n, n, n)
+    N = (procs[0] * n, procs[1] * n, procs[2] * n)
     expect = {1: N[0] * (N[1] + 1) * (N[2] + 1) + (N[0] + 1) * N[1] * (N[2] + 1) + (N[0] + 1) * (N[1] + 1) * N[2],
               2: (N[0] + 1) * N[1] * N[2] + N[0] * (N[1] + 1) * N[2] + N[0] * N[1] * (N[2] + 1),
               3: N[0] * N[1] * N[2]}
@@ -56,20 +65,28 @@ def main():
         assert sum(counts) == expect[form]
         assert m["start"] == sum(counts[:rank])
         both = gather(dict(zip(m["key"].tolist(), m["gid"].tolist())))
-        for k, g in both[rank].items():
-            if k in both[1 - rank]:
-                assert both[1 - rank][k] == g
-        allg = set(both[0].values()) | set(both[1].values())
+        holders = {}
+        for r in range(size):
+            for k, g in both[r].items():
+                if k in both[rank]:
+                    assert both[rank][k] == g                # one true id per key on every holder
+                holders.setdefault(k, []).append(r)
+        allg = set()
+        for r in range(size):
+            allg |= set(both[r].values())
         assert allg == set(range(expect[form]))
-        # interface faces / edges are owned by rank 0
-        shared = set(both[0]) & set(both[1])
-        assert len(shared) == {1: 2 * n * (n + 1), 2: n * n, 3: 0}[form]
-        assert all(m["owner"][i] == 0 for i, k in enumerate(m["key"].tolist()) if k in shared)
+        # a shared dof is owned by the smallest rank holding it
+        for i, k in enumerate(m["key"].tolist()):
+            assert m["owner"][i] == min(holders[k]), (form, k, m["owner"][i], holders[k])
+        if size == 2:
+            shared = set(both[0]) & set(both[1])
+            assert len(shared) == {1: 2 * n * (n + 1), 2: n * n, 3: 0}[form]
     # pseudo boundary attribute on the interface: the coarse facets of both sides match one to one
     FB = S.get_csr(1, "FB")
-    iface_attr = 7 if rank == 0 else 6                        # x+ face of rank 0, x- face of rank 1
-    ncf = int((FB.indices == iface_attr).sum())
-    assert ncf == (n // 2) ** 2 and FB.shape[1] == 12, (ncf, FB.shape)
+    if size == 2:
+        iface_attr = 7 if rank == 0 else 6                    # x+ face of rank 0, x- face of rank 1
+        ncf = int((FB.indices == iface_attr).sum())
+        assert ncf == (n // 2) ** 2 and FB.shape[1] == 12, (ncf, FB.shape)
 
     # ---- T3: Assemble(dofTrueDof, A_local, dofTrueDof) == the single-domain operator
     mesh_loc = amge.HexMesh(n, n, n, L=(1.0, 1.0, 1.0))
@@ -83,7 +100,7 @@ def main():
     _, blk = par.parcsr_rows_to_global(d)
     blocks = gather((d["first_row"], blk))
     A_true = sp.vstack([b for _, b in sorted(blocks, key=lambda t: t[0])]).tocsr()
-    mesh_g = amge.HexMesh(*N, L=(2.0, 1.0, 1.0))
+    mesh_g = amge.HexMesh(*N, L=tuple(float(p) for p in procs))
     seq_g = amge.fine_sequence(mesh_g, jstart=1)
     A_g, _ = drivers.system_matrix(seq_g, 2, np.zeros(6, dtype=np.int32))
     # true id -> global face number of the undecomposed mesh (the dof key carries it)
@@ -105,8 +122,7 @@ def main():
 
     # ---- T3b: SharingMap::Assemble / Distribute on vectors
     ones = S.assemble_vector(0, 2, np.ones(len(m["gid"])))
-    nshared_owned = int(((m["owner"] == rank) & np.isin(m["key"], list(set(both[0]) & set(both[1])))).sum()) if False else None
-    assert set(np.unique(ones).tolist()) <= {1.0, 2.0}                      # multiplicity of every true dof
+    assert set(np.unique(ones).tolist()) <= {1.0, 2.0}                      # a face has at most two holders
     assert int(sum(gather(float(ones.sum())))) == int(sum(gather(len(m["gid"]))))
     tv = np.arange(m["start"], m["start"] + m["ntrue"], dtype=np.float64)   # true vector = its own global id
     loc = S.distribute_vector(0, 2, tv)
