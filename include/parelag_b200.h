@@ -82,8 +82,17 @@ int pe_ctx_profile(pe_ctx *ctx, int enable);
 int pe_ctx_profile_get(pe_ctx *ctx, int kernel_id, int64_t *count, double *total_ms, double *total_bytes);
 /* process-wide tuning knobs (tests force either kernel family; defaults in brackets):
  * PE_TUNE_SELL_MIN_ROWS [200000]: multicolour Gauss-Seidel uses the colour-ordered SELL-32 streaming
- * kernel for matrices with at least this many rows and the lanes-per-row CSR kernel below it. */
-enum { PE_TUNE_SELL_MIN_ROWS = 0, PE_TUNE_COUNT = 4 };
+ * kernel for matrices with at least this many rows and the lanes-per-row CSR kernel below it.
+ * PE_TUNE_SELL_GROUP [0]: entries per load group of the SELL kernels (0 = chosen from the slice widths;
+ * 4, 8 or 12 forces one).  Results do not depend on it (the summation order of a row is fixed).
+ * PE_TUNE_PDL [1]: launch the solve-path kernels with programmatic stream serialization (single rank):
+ * the matrix prologue of a kernel overlaps the tail of its predecessor.
+ * PE_TUNE_GATHER_KEEP_PCT [0]: percentage (0, 25, 50, 60, 75, 90, 100) of the u-gather lines of the SELL
+ * Gauss-Seidel kernel that get L2 priority evict_last (the rest evict_unchanged); 0 = normal priority.
+ * The colour-ordered iterate is re-read by every colour launch while 30-50x its size streams through
+ * L2; keeping a fixed fraction resident turns an all-miss cyclic pattern into that fraction of hits.
+ * Read when a smoother is created. */
+enum { PE_TUNE_SELL_MIN_ROWS = 0, PE_TUNE_SELL_GROUP = 1, PE_TUNE_PDL = 2, PE_TUNE_GATHER_KEEP_PCT = 3, PE_TUNE_COUNT = 4 };
 int pe_set_tuning(int key, int value);
 int pe_get_tuning(int key);
 /* write a scratch buffer larger than L2 (bench hygiene) */

@@ -130,6 +130,9 @@ class Ctx:
 
 
 TUNE_SELL_MIN_ROWS = 0
+TUNE_SELL_GROUP = 1
+TUNE_PDL = 2
+TUNE_GATHER_KEEP_PCT = 3
 
 
 def set_tuning(key, value):

@@ -127,7 +127,7 @@ extern "C" int pe_ctx_destroy(pe_ctx *c)
     return 0;
 }
 
-static int g_tuning[PE_TUNE_COUNT] = {200000, 0, 0, 0};
+static int g_tuning[PE_TUNE_COUNT] = {200000, 0, 1, 0};
 extern "C" int pe_set_tuning(int key, int value)
 {
     PE_CHECK(key >= 0 && key < PE_TUNE_COUNT, "bad tuning key");
@@ -338,33 +338,38 @@ extern "C" int pe_vec_download(const pe_vec *v, double *host)
 // elementwise kernels: grid-stride, 2 doubles per thread per step via double2 when aligned
 __global__ void k_fill(double *x, int64_t n, double v)
 {
+    pdl_trigger(); pdl_wait();   // operands come from the preceding kernel (see pe_launch_k)
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t s = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += s) x[i] = v;
 }
-__global__ void k_axpby(int64_t n, double a, const double *__restrict__ x, double b,
-                        double *__restrict__ y)
+__global__ void k_axpby(int64_t n, double a, const double *x, double b,
+                        double *y)
 {
+    pdl_trigger(); pdl_wait();   // operands come from the preceding kernel (see pe_launch_k)
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t s = (int64_t)gridDim.x * blockDim.x;
     if (b == 0.0) { for (; i < n; i += s) y[i] = a * x[i]; }
     else { for (; i < n; i += s) y[i] = a * x[i] + b * y[i]; }
 }
-__global__ void k_add3(int64_t n, double a, const double *__restrict__ x, double b,
-                       const double *__restrict__ y, double *z)
+__global__ void k_add3(int64_t n, double a, const double *x, double b,
+                       const double *y, double *z)
 {
+    pdl_trigger(); pdl_wait();   // operands come from the preceding kernel (see pe_launch_k)
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t s = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += s) z[i] = a * x[i] + b * y[i];
 }
 __global__ void k_scale(int64_t n, double a, double *x)
 {
+    pdl_trigger(); pdl_wait();   // operands come from the preceding kernel (see pe_launch_k)
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t s = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += s) x[i] *= a;
 }
-__global__ void k_mul(int64_t n, const double *__restrict__ d, double *x)
+__global__ void k_mul(int64_t n, const double *d, double *x)
 {
+    pdl_trigger(); pdl_wait();   // operands come from the preceding kernel (see pe_launch_k)
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t s = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += s) x[i] *= d[i];
@@ -388,7 +393,7 @@ extern "C" int pe_vec_fill(pe_vec *v, double value)
         PE_CUDA(cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)v->n, v->ctx->stream));
         return 0;
     }
-    k_fill<<<ew_grid(v->n), 256, 0, v->ctx->stream>>>(v->d, v->n, value);
+    PE_CUDA(pe_launch_k(v->ctx, k_fill, ew_grid(v->n), 256, v->d, v->n, value));
     PE_LAUNCHED(v->ctx);
     return 0;
 }
@@ -416,7 +421,7 @@ extern "C" int pe_vec_axpby(double a, const pe_vec *x, double b, pe_vec *y)
         pe_rec_push(y->ctx, o, (b == 0.0 ? 16.0 : 24.0) * x->n);
         return 0;
     }
-    k_axpby<<<ew_grid(x->n), 256, 0, y->ctx->stream>>>(x->n, a, x->d, b, y->d);
+    PE_CUDA(pe_launch_k(y->ctx, k_axpby, ew_grid(x->n), 256, x->n, a, x->d, b, y->d));
     PE_LAUNCHED(y->ctx);
     return 0;
 }
@@ -430,7 +435,7 @@ extern "C" int pe_vec_add3(double a, const pe_vec *x, double b, const pe_vec *y,
         pe_rec_push(z->ctx, o, 24.0 * x->n);
         return 0;
     }
-    k_add3<<<ew_grid(x->n), 256, 0, z->ctx->stream>>>(x->n, a, x->d, b, y->d, z->d);
+    PE_CUDA(pe_launch_k(z->ctx, k_add3, ew_grid(x->n), 256, x->n, a, x->d, b, y->d, z->d));
     PE_LAUNCHED(z->ctx);
     return 0;
 }
@@ -443,7 +448,7 @@ extern "C" int pe_vec_scale(pe_vec *x, double a)
         pe_rec_push(x->ctx, o, 16.0 * x->n);
         return 0;
     }
-    k_scale<<<ew_grid(x->n), 256, 0, x->ctx->stream>>>(x->n, a, x->d);
+    PE_CUDA(pe_launch_k(x->ctx, k_scale, ew_grid(x->n), 256, x->n, a, x->d));
     PE_LAUNCHED(x->ctx);
     return 0;
 }
@@ -457,16 +462,17 @@ extern "C" int pe_vec_mul(const pe_vec *d, pe_vec *x)
         pe_rec_push(x->ctx, o, 24.0 * x->n);
         return 0;
     }
-    k_mul<<<ew_grid(x->n), 256, 0, x->ctx->stream>>>(x->n, d->d, x->d);
+    PE_CUDA(pe_launch_k(x->ctx, k_mul, ew_grid(x->n), 256, x->n, d->d, x->d));
     PE_LAUNCHED(x->ctx);
     return 0;
 }
 
 // deterministic two-stage dot: fixed grid, fixed in-block tree, fixed final order
 #define DOT_THREADS 256
-__global__ void k_dot_stage1(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+__global__ void k_dot_stage1(int64_t n, const double *x, const double *y,
                              double *partials)
 {
+    pdl_trigger(); pdl_wait();   // operands come from the preceding kernel (see pe_launch_k)
     __shared__ double sh[DOT_THREADS];
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t s = (int64_t)gridDim.x * blockDim.x;
@@ -482,6 +488,7 @@ __global__ void k_dot_stage1(int64_t n, const double *__restrict__ x, const doub
 }
 __global__ void k_dot_stage2(int nparts, const double *partials, double *out)
 {
+    pdl_trigger(); pdl_wait();   // operands come from the preceding kernel (see pe_launch_k)
     __shared__ double sh[DOT_THREADS];
     double acc = 0.0;
     for (int i = threadIdx.x; i < nparts; i += DOT_THREADS) acc += partials[i];
@@ -500,9 +507,9 @@ extern "C" int pe_vec_dot(const pe_vec *x, const pe_vec *y, double *out)
     if (c->rec) pe_rec_fail(c, "pe_vec_dot (host-synchronising)", 0);
     int grid = ew_grid(x->n);
     if (grid > PE_MAX_PARTIALS) grid = PE_MAX_PARTIALS;
-    k_dot_stage1<<<grid, DOT_THREADS, 0, c->stream>>>(x->n, x->d, y->d, c->partials_d);
+    PE_CUDA(pe_launch_k(c, k_dot_stage1, grid, DOT_THREADS, x->n, x->d, y->d, c->partials_d));
     PE_LAUNCHED(c);
-    k_dot_stage2<<<1, DOT_THREADS, 0, c->stream>>>(grid, c->partials_d, c->scalar_d);
+    PE_CUDA(pe_launch_k(c, k_dot_stage2, 1, DOT_THREADS, grid, c->partials_d, c->scalar_d));
     PE_LAUNCHED(c);
     PE_TRY(pe_allreduce_sum(c, c->scalar_d, 1));
     PE_CUDA(cudaMemcpyAsync(c->scalar_h, c->scalar_d, sizeof(double), cudaMemcpyDeviceToHost,
@@ -549,22 +556,24 @@ extern "C" int pe_vec_dot_dev(const pe_vec *x, const pe_vec *y, double *slots_d,
     }
     int grid = ew_grid(x->n);
     if (grid > PE_MAX_PARTIALS) grid = PE_MAX_PARTIALS;
-    k_dot_stage1<<<grid, DOT_THREADS, 0, c->stream>>>(x->n, x->d, y->d, c->partials_d);
+    PE_CUDA(pe_launch_k(c, k_dot_stage1, grid, DOT_THREADS, x->n, x->d, y->d, c->partials_d));
     PE_LAUNCHED(c);
-    k_dot_stage2<<<1, DOT_THREADS, 0, c->stream>>>(grid, c->partials_d, slots_d + out_slot);
+    PE_CUDA(pe_launch_k(c, k_dot_stage2, 1, DOT_THREADS, grid, c->partials_d, slots_d + out_slot));
     PE_LAUNCHED(c);
     return pe_allreduce_sum(c, slots_d + out_slot, 1);
 }
-__global__ void k_axpy_dev(int64_t n, const double *__restrict__ a, double sign, const double *__restrict__ x, double *__restrict__ y)
+__global__ void k_axpy_dev(int64_t n, const double *a, double sign, const double *x, double *y)
 {
+    pdl_trigger(); pdl_wait();   // operands come from the preceding kernel (see pe_launch_k)
     const double s = sign * a[0];
     if (s == 0.0) return;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t st = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += st) y[i] += s * x[i];
 }
-__global__ void k_xpby_dev(int64_t n, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ y)
+__global__ void k_xpby_dev(int64_t n, const double *x, const double *b, double *y)
 {
+    pdl_trigger(); pdl_wait();   // operands come from the preceding kernel (see pe_launch_k)
     const double s = b[0];
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t st = (int64_t)gridDim.x * blockDim.x;
@@ -580,7 +589,7 @@ extern "C" int pe_vec_axpy_dev(const double *slots_d, int a_slot, double sign, c
         pe_rec_push(y->ctx, o, 24.0 * x->n);
         return 0;
     }
-    k_axpy_dev<<<ew_grid(x->n), 256, 0, y->ctx->stream>>>(x->n, slots_d + a_slot, sign, x->d, y->d);
+    PE_CUDA(pe_launch_k(y->ctx, k_axpy_dev, ew_grid(x->n), 256, x->n, slots_d + a_slot, sign, x->d, y->d));
     PE_LAUNCHED(y->ctx);
     return 0;
 }
@@ -594,12 +603,13 @@ extern "C" int pe_vec_xpby_dev(const pe_vec *x, const double *slots_d, int b_slo
         pe_rec_push(y->ctx, o, 24.0 * x->n);
         return 0;
     }
-    k_xpby_dev<<<ew_grid(x->n), 256, 0, y->ctx->stream>>>(x->n, x->d, slots_d + b_slot, y->d);
+    PE_CUDA(pe_launch_k(y->ctx, k_xpby_dev, ew_grid(x->n), 256, x->n, x->d, slots_d + b_slot, y->d));
     PE_LAUNCHED(y->ctx);
     return 0;
 }
 __global__ void k_pcg_scalar_step(double *s, int phase, int iter, int max_iter, double rel, double abs_tol)
 {
+    pdl_trigger(); pdl_wait();   // operands come from the preceding kernel (see pe_launch_k)
     pe_pcg_scalar_step_dev(s, phase, iter, max_iter, rel, abs_tol);
 }
 extern "C" int pe_pcg_scalar_step(pe_ctx *ctx, double *slots_d, int phase, int iter, int max_iter, double rel_tol, double abs_tol)
@@ -611,7 +621,7 @@ extern "C" int pe_pcg_scalar_step(pe_ctx *ctx, double *slots_d, int phase, int i
         pe_rec_push(ctx, o, 0.0);
         return 0;
     }
-    k_pcg_scalar_step<<<1, 1, 0, ctx->stream>>>(slots_d, phase, iter, max_iter, rel_tol, abs_tol);
+    PE_CUDA(pe_launch_k(ctx, k_pcg_scalar_step, 1, 1, slots_d, phase, iter, max_iter, rel_tol, abs_tol));
     PE_LAUNCHED(ctx);
     return 0;
 }

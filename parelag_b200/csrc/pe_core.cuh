@@ -110,6 +110,34 @@ static inline PeOp pe_op(int32_t type)
     o.type = type;
     return o;
 }
+// ---- programmatic dependent launch (PDL).  A kernel launched through pe_launch_k may start while
+// its predecessor on the stream is still draining: everything it does before pdl_wait() must touch
+// only data no kernel of the sequence writes (matrix arrays, index lists, l1 norms); pdl_wait()
+// returns once the predecessor has completed and its writes are visible.  Every kernel launched
+// this way executes pdl_wait() in at least one thread, so completion stays transitive along the
+// stream.  Without the launch attribute both instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pe_launch_k(pe_ctx *ctx, void (*kern)(KArgs...), int grid, int block, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    if (ctx->nranks == 1 && pe_get_tuning(PE_TUNE_PDL) != 0)
+    {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
 int pe_prof_begin(pe_ctx *ctx, int id, double bytes);
 int pe_prof_end(pe_ctx *ctx);
 #define PE_MAX_PARTIALS 4096
@@ -117,6 +145,7 @@ int pe_prof_end(pe_ctx *ctx);
 // sliced-ELL copy of a CSR block (pe_sell.cu): slices of 32 rows, column-major inside a slice
 struct DevSELL {
     int32_t nslices = 0, nrows = 0;   // nrows: rows that receive output (<= nslices*32)
+    int32_t wmax = 0;                 // widest slice (selects the entry-group size of the kernels)
     int64_t nstored = 0;              // stored entries incl. padding
     int32_t *soff = nullptr;          // nslices+1 slice offsets, in units of 32 entries
     int32_t *J = nullptr;
@@ -138,13 +167,16 @@ struct DevCSR {
 };
 void pe_sell_free(DevSELL &m);
 int pe_sell_build(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, const int32_t *rowmap_d, int32_t nslices,
-                  const int32_t *colpos_d, int32_t ext_base, DevSELL &out);
+                  const int32_t *colpos_d, int32_t ext_base, DevSELL &out,
+                  std::vector<int32_t> *soff_host = nullptr);
 int pe_sell_for_spmv(pe_ctx *ctx, DevCSR &m);
 void pe_mat_values_changed(struct pe_mat *A);   // drop cached transposes / SELL copies after an in-place edit
 int pe_launch_sell_spmv(pe_ctx *ctx, const DevSELL &S, double alpha, const double *x, double beta,
                         const double *yin, double *yout);
-int pe_launch_sell_gs(pe_ctx *ctx, const DevSELL &S, int s0, int s1, int ext_base, const double *f, double *u,
-                      const double *uext, const double *l1);
+int pe_launch_sell_gs(pe_ctx *ctx, const DevSELL &S, int s0, int s1, int wmax, int ext_base, const double *f, double *u,
+                      const double *uext, const double *l1, uint64_t pol_gather);
+// L2 cache policy word for the u-gathers: keep_pct % of the lines evict_last, the rest unchanged (0: evict_normal)
+int pe_make_gather_policy(pe_ctx *ctx, int keep_pct, uint64_t *pol);
 int pe_launch_perm_in(pe_ctx *ctx, int n, const int *pos, const double *b, const double *x, double *fp, double *up);
 int pe_launch_perm_out(pe_ctx *ctx, int n, const int *pos, const double *up, double *x);
 #define PE_STREAM_NNZ 2048      // target non-zeros per CTA

@@ -14,6 +14,7 @@
 //  * Chebyshev: hypre_ParCSRRelax_Cheby with D^{-1/2} scaling, eigenvalue bounds from
 //    10 CG steps (hypre_ParCSRMaxEigEstimateCG) started from hypre's LCG random vector.
 #include "pe_core.cuh"
+#include "pe_stream.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -42,7 +43,9 @@ struct pe_smoother {
     DevSELL S;
     int32_t npad = 0;                   // padded length of the colour-ordered vectors
     std::vector<int32_t> slice_starts;  // nsets+1: first slice of every colour
+    std::vector<int32_t> set_wmax;      // widest slice of every colour (selects the kernel's entry-group size)
     std::vector<double> set_bytes;      // algorithmic bytes of one colour launch
+    uint64_t pol_gather = 0;            // L2 policy word of the u-gathers (PE_TUNE_GATHER_KEEP_PCT at creation)
     bool skip_turn = false;             // the backward pass may start at the second-to-last colour (see build_gs_schedule)
     int32_t *pos_d = nullptr;           // row -> colour-ordered position
     double *l1p_d = nullptr, *fp_d = nullptr, *up_d = nullptr;
@@ -102,29 +105,44 @@ template <int TPR, bool GENERAL>
 __global__ void __launch_bounds__(256)
 k_gs_set(int k0, int k1, const int *__restrict__ pI, const int *__restrict__ pJ,
          const double *__restrict__ pA, const int *__restrict__ perm, int ncd,
-         const double *__restrict__ f, double *u, const double *__restrict__ uext,
+         const double *f, double *u, const double *uext,
          const double *__restrict__ l1, const uint8_t *__restrict__ before, int forward,
-         const double *__restrict__ uold, double c1, double c2)
+         const double *uold, double c1, double c2)
 {
+    // PDL: the row extent, the first (col,val) of every lane, the row's position and its l1 norm are
+    // matrix data -- fetched while the preceding colour is still draining; f, u, uext, uold after the wait
+    pdl_trigger();
     const int lane = threadIdx.x & (TPR - 1);
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / TPR;
     const int k = k0 + gid;
-    if (k >= k1) return;
-    const int lo = pI[k], hi = pI[k + 1];
+    if (k >= k1) { pdl_wait(); return; }
+    const int lo = ld_nc_s32_pro(pI + k), hi = ld_nc_s32_pro(pI + k + 1);
+    const int i = ld_nc_s32_pro(perm + k);
+    const double d = ld_nc_f64_pro(l1 + i);
+    int q = lo + lane;
+    int cn = 0; double an = 0.0;
+    if (q < hi) { cn = ld_nc_s32_pro(pJ + q); an = ld_nc_f64_pro(pA + q); }
+    if ((cn ^ __double2hiint(an) ^ __double2loint(an) ^ __double2hiint(d)) == 0x5bd1e995) pdl_trigger();   // pins the loads ahead of the wait
+    pdl_wait();
+    double fi = 0.0, ui = 0.0;
+    if (lane == 0) { fi = f[i]; ui = u[i]; }     // issued with the gathers, not after the reduction
     double s = 0.0, s2 = 0.0;
-    for (int q = lo + lane; q < hi; q += TPR) {
-        int c = pJ[q];
-        double a = pA[q];
+    while (q < hi) {
+        const int c = cn;
+        const double a = an;
+        const int qn = q + TPR;
+        if (qn < hi) { cn = pJ[qn]; an = pA[qn]; }
         if (c < ncd) {
             double uc = u[c];
             s += a * uc;
             if (GENERAL) {
-                bool vis = forward ? (before[q] != 0) : (before[q] == 0 && c != perm[k]);
+                bool vis = forward ? (before[q] != 0) : (before[q] == 0 && c != i);
                 if (vis) s2 += a * (uold[c] - uc);
             }
         } else {
             s += a * uext[c - ncd];
         }
+        q = qn;
     }
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) {
@@ -132,11 +150,9 @@ k_gs_set(int k0, int k1, const int *__restrict__ pI, const int *__restrict__ pJ,
         if (GENERAL) s2 += __shfl_down_sync(0xffffffffu, s2, o, TPR);
     }
     if (lane == 0) {
-        int i = perm[k];
-        double d = l1[i];
         if (d != 0.0) {
-            if (GENERAL) u[i] += (c1 * (f[i] - s) + c2 * s2) / d;
-            else u[i] += (f[i] - s) / d;
+            if (GENERAL) u[i] = ui + (c1 * (fi - s) + c2 * s2) / d;
+            else u[i] = ui + (fi - s) / d;
         }
     }
 }
@@ -350,12 +366,18 @@ static int build_gs_schedule(pe_smoother *s)
         PE_CUDA(cudaMemsetAsync(s->l1p_d, 0, sizeof(double) * np, ctx->stream));
         PE_CUDA(cudaMemsetAsync(s->fp_d, 0, sizeof(double) * np, ctx->stream));
         PE_CUDA(cudaMemsetAsync(s->up_d, 0, sizeof(double) * np, ctx->stream));
-        PE_TRY(pe_sell_build(ctx, A->diag, &A->offd, rowmap_d, nslices, s->pos_d, s->npad, s->S));
+        std::vector<int32_t> soff_h;
+        PE_TRY(pe_sell_build(ctx, A->diag, &A->offd, rowmap_d, nslices, s->pos_d, s->npad, s->S, &soff_h));
+        s->set_wmax.assign(nsets, 0);
+        for (int c = 0; c < nsets; ++c)
+            for (int k = s->slice_starts[c]; k < s->slice_starts[c + 1]; ++k)
+                s->set_wmax[c] = std::max(s->set_wmax[c], soff_h[k + 1] - soff_h[k]);
 
         // l1 in colour order (padded rows keep 0 => never updated)
         PE_TRY(pe_launch_perm_in(ctx, n, s->pos_d, s->l1_d, nullptr, s->l1p_d, s->up_d));
         PE_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(rowmap_d);
+        PE_TRY(pe_make_gather_policy(ctx, pe_get_tuning(PE_TUNE_GATHER_KEEP_PCT), &s->pol_gather));
         s->use_sell = true;
         return 0;
     }
@@ -657,7 +679,7 @@ static int launch_gs_set(pe_smoother *s, int k0, int k1, const double *f, double
     int tpr = s->tpr;
     int grid = pe_grid_for((int64_t)rows * tpr, 256);
     int ncd = s->A->diag.ncols;
-#define LAUNCH(T) k_gs_set<T, GENERAL><<<grid, 256, 0, ctx->stream>>>(k0, k1, s->P.I, s->P.J, s->P.A, s->perm_d, ncd, f, u, s->A->x_ext_d, s->l1_d, s->before_d, forward, s->w_d, c1, c2)
+#define LAUNCH(T) PE_CUDA(pe_launch_k(ctx, k_gs_set<T, GENERAL>, grid, 256, k0, k1, s->P.I, s->P.J, s->P.A, s->perm_d, ncd, f, u, s->A->x_ext_d, s->l1_d, s->before_d, forward, s->w_d, c1, c2))
     if (ctx->prof)
     {
         const double nnz_set = (double)(s->pI_at(k1) - s->pI_at(k0));
@@ -714,8 +736,8 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
                     const int c = pass == 0 ? cc : s->nsets - 1 - cc;
                     if (s->slice_starts[c + 1] == s->slice_starts[c]) continue;
                     PE_TRY(pe_prof_begin(ctx, s->set_bytes[c] >= 64e6 ? 1 : 3, s->set_bytes[c]));
-                    PE_TRY(pe_launch_sell_gs(ctx, s->S, s->slice_starts[c], s->slice_starts[c + 1], s->npad, s->fp_d, s->up_d,
-                                             ghosts ? A->x_ext_d : nullptr, s->l1p_d));
+                    PE_TRY(pe_launch_sell_gs(ctx, s->S, s->slice_starts[c], s->slice_starts[c + 1], s->set_wmax[c], s->npad, s->fp_d, s->up_d,
+                                             ghosts ? A->x_ext_d : nullptr, s->l1p_d, s->pol_gather));
                     PE_TRY(pe_prof_end(ctx));
                 }
             PE_TRY(pe_launch_perm_out(ctx, n, s->pos_d, s->up_d, x->d));

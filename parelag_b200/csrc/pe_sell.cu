@@ -15,6 +15,7 @@
 #include "pe_core.cuh"
 #include "pe_stream.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
 
 // ---------------------------------------------------------------------------
 // build
@@ -77,7 +78,7 @@ void pe_sell_free(DevSELL &m)
 // rowmap_d: nslices*32 source rows (-1 = padding row) or null for the identity over diag.nrows;
 // colpos_d: new index of every diag column or null; ghost column j becomes ext_base + j.
 int pe_sell_build(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, const int32_t *rowmap_d, int32_t nslices,
-                  const int32_t *colpos_d, int32_t ext_base, DevSELL &out)
+                  const int32_t *colpos_d, int32_t ext_base, DevSELL &out, std::vector<int32_t> *soff_host)
 {
     cudaStream_t st = ctx->stream;
     if (!rowmap_d) nslices = (diag.nrows + 31) / 32;
@@ -95,10 +96,14 @@ int pe_sell_build(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, const int
     PE_CUDA(cudaMalloc(&tmp, tb));
     PE_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, out.soff, out.soff, nslices + 1, st));
     ctx->launches++;
-    int32_t total = 0;
-    PE_CUDA(cudaMemcpyAsync(&total, out.soff + nslices, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> soff_h((size_t)nslices + 1);
+    PE_CUDA(cudaMemcpyAsync(soff_h.data(), out.soff, sizeof(int32_t) * (size_t)(nslices + 1), cudaMemcpyDeviceToHost, st));
     PE_CUDA(cudaStreamSynchronize(st));
     cudaFree(tmp);
+    const int32_t total = soff_h[nslices];
+    out.wmax = 0;
+    for (int32_t k = 0; k < nslices; ++k) out.wmax = std::max(out.wmax, soff_h[k + 1] - soff_h[k]);
+    if (soff_host) soff_host->swap(soff_h);
     out.nstored = (int64_t)total * 32;
     PE_CUDA(cudaMalloc(&out.J, sizeof(int32_t) * (size_t)(out.nstored > 0 ? out.nstored : 1)));
     PE_CUDA(cudaMalloc(&out.A, sizeof(double) * (size_t)(out.nstored > 0 ? out.nstored : 1)));
@@ -128,38 +133,130 @@ int pe_sell_for_spmv(pe_ctx *ctx, DevCSR &m)
 }
 
 // ---------------------------------------------------------------------------
+// Entry groups.  A thread walks its row in groups of G entries: the (col,val) loads of a whole
+// group are issued back to back, then the G gathers, and the loads of group g+1 are in flight
+// while the gathers of group g are outstanding.  The last group is predicated on the slice
+// width (warp-uniform), so a row costs ceil(w/G)+2 dependent memory round trips instead of one
+// per tail entry.  SINGLE: every slice of the launch has w <= G -- one group, no loop; this is
+// what short rows (RT0: 11, D: 2, D^T: 4) need to keep enough bytes in flight.  The products are
+// accumulated in entry order in every variant, so the result does not depend on G.
+// ---------------------------------------------------------------------------
+template <int G, bool PRO = false>
+__device__ __forceinline__ void sell_load_group(const int *j, const double *a, int q, int w, uint64_t pol,
+                                                int (&c)[G], double (&v)[G])
+{
+#pragma unroll
+    for (int k = 0; k < G; ++k)
+        if (q + k < w)
+        {
+            c[k] = PRO ? ld_stream_s32_pro(j + (q + k) * 32, pol) : ld_stream_s32(j + (q + k) * 32, pol);
+            v[k] = PRO ? ld_stream_f64_pro(a + (q + k) * 32, pol) : ld_stream_f64(a + (q + k) * 32, pol);
+        }
+}
+
+// pdl_wait() has acquire semantics only: ptxas is free to sink the (independent) prologue loads
+// below it, which would serialise them behind the predecessor kernel.  Making a harmless
+// instruction depend on every loaded word pins the loads ahead of the wait: the gathers need the
+// column indices anyway, so nothing is lost when there is no predecessor to overlap with.
+template <int G>
+__device__ __forceinline__ void sell_pin_group_then_wait(const int (&c)[G], const double (&v)[G], int w)
+{
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < G; ++k) if (k < w) t ^= c[k] ^ __double2hiint(v[k]) ^ __double2loint(v[k]);
+    if (t == 0x5bd1e995) pdl_trigger();      // a second trigger is a no-op
+    pdl_wait();
+}
+
+// ---------------------------------------------------------------------------
 // SpMV: yout = alpha * A x + beta * yin   (thread per row, warp per slice)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int G, bool SINGLE>
+__global__ void __launch_bounds__(256, ((SINGLE || G <= 4) ? 4 : 2))
 k_sell_spmv(int nslices, int nrows, const int *__restrict__ soff, const int *__restrict__ J,
-            const double *__restrict__ A, const double *__restrict__ x, double alpha, double beta,
+            const double *__restrict__ A, const double *x, double alpha, double beta,
             const double *yin, double *yout)
 {
+    // x, yin, f, u, uext are written by preceding kernels that may still be draining when this one
+    // starts (PDL): they are plain pointers (no __restrict__/ld.global.nc) and only read after pdl_wait()
+    pdl_trigger();
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (s >= nslices) return;
-    const int o0 = soff[s], w = soff[s + 1] - o0;
+    if (s >= nslices) { pdl_wait(); return; }
+    const int o0 = ld_nc_s32_pro(soff + s), w = ld_nc_s32_pro(soff + s + 1) - o0;
     const int *j = J + (int64_t)o0 * 32 + lane;
     const double *a = A + (int64_t)o0 * 32 + lane;
     const uint64_t pol = l2_evict_first_policy();
     double acc = 0.0;
-    int q = 0;
-    for (; q + 4 <= w; q += 4)
-    {
-        const int c0 = ld_stream_s32(j + (q + 0) * 32, pol), c1 = ld_stream_s32(j + (q + 1) * 32, pol);
-        const int c2 = ld_stream_s32(j + (q + 2) * 32, pol), c3 = ld_stream_s32(j + (q + 3) * 32, pol);
-        const double a0 = ld_stream_f64(a + (q + 0) * 32, pol), a1 = ld_stream_f64(a + (q + 1) * 32, pol);
-        const double a2 = ld_stream_f64(a + (q + 2) * 32, pol), a3 = ld_stream_f64(a + (q + 3) * 32, pol);
-        const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-        acc += a0 * x0; acc += a1 * x1; acc += a2 * x2; acc += a3 * x3;
-    }
-    for (; q < w; ++q) acc += ld_stream_f64(a + q * 32, pol) * __ldg(x + ld_stream_s32(j + q * 32, pol));
+    int c[G]; double v[G];
+    sell_load_group<G, true>(j, a, 0, w, pol, c, v);
+    sell_pin_group_then_wait<G>(c, v, w);    // x (and yin) come from the preceding kernel
     const int row = s * 32 + lane;
+    const double yv = (beta != 0.0 && row < nrows) ? yin[row] : 0.0;   // issued with the first gathers, not after them
+    for (int q = 0; q < w; q += G)
+    {
+        double xv[G], b[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) if (q + k < w) { xv[k] = x[c[k]]; b[k] = v[k]; }
+        if (!SINGLE && q + G < w) sell_load_group<G>(j, a, q + G, w, pol, c, v);
+#pragma unroll
+        for (int k = 0; k < G; ++k) if (q + k < w) acc = __fma_rn(b[k], xv[k], acc);   // explicit: same rounding in every variant
+        if (SINGLE) break;
+    }
     if (row < nrows)
     {
-        double v = alpha * acc;
-        if (beta != 0.0) v += beta * yin[row];
-        yout[row] = v;
+        double r = alpha * acc;
+        if (beta != 0.0) r += beta * yv;
+        yout[row] = r;
     }
+}
+
+// ---------------------------------------------------------------------------
+// L2 policy of the gathers (PE_TUNE_GATHER_KEEP_PCT)
+// ---------------------------------------------------------------------------
+__global__ void k_make_policy(int pct, uint64_t *out)
+{
+    uint64_t p;
+    switch (pct)
+    {
+    case 25: asm("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, 0.25;" : "=l"(p)); break;
+    case 50: asm("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, 0.5;" : "=l"(p)); break;
+    case 60: asm("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, 0.6;" : "=l"(p)); break;
+    case 75: asm("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, 0.75;" : "=l"(p)); break;
+    case 90: asm("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, 0.9;" : "=l"(p)); break;
+    case 100: asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); break;
+    default: asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); break;
+    }
+    *out = p;
+}
+int pe_make_gather_policy(pe_ctx *ctx, int keep_pct, uint64_t *pol)
+{
+    uint64_t *d = nullptr;
+    PE_CUDA(cudaMalloc(&d, sizeof(uint64_t)));
+    k_make_policy<<<1, 1, 0, ctx->stream>>>(keep_pct, d);
+    PE_LAUNCHED(ctx);
+    PE_CUDA(cudaMemcpyAsync(pol, d, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PE_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return 0;
+}
+__device__ __forceinline__ double ld_hint_f64(const double *p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+
+// group size for slices up to wmax entries wide (0 <= forced: PE_TUNE_SELL_GROUP)
+static void sell_pick_group(int wmax, int &G, bool &single)
+{
+    const int forced = pe_get_tuning(PE_TUNE_SELL_GROUP);
+    if (forced == 4 || forced == 8 || forced == 12) G = forced;
+    else if (wmax <= 4) G = 4;
+    else if (wmax <= 8) G = 8;
+    else if (wmax <= 12) G = 12;
+    else if (wmax <= 24) G = 8;
+    else G = 4;
+    single = wmax <= G;
 }
 
 int pe_launch_sell_spmv(pe_ctx *ctx, const DevSELL &S, double alpha, const double *x, double beta,
@@ -173,8 +270,14 @@ int pe_launch_sell_spmv(pe_ctx *ctx, const DevSELL &S, double alpha, const doubl
         pe_rec_push(ctx, o, -1.0);
         return 0;
     }
-    k_sell_spmv<<<pe_grid_for((int64_t)S.nslices * 32, 256), 256, 0, ctx->stream>>>(S.nslices, S.nrows, S.soff, S.J, S.A,
-                                                                                   x, alpha, beta, yin, yout);
+    const int grid = pe_grid_for((int64_t)S.nslices * 32, 256);
+    int G; bool single;
+    sell_pick_group(S.wmax, G, single);
+#define PE_SPMV(GG, SS) PE_CUDA(pe_launch_k(ctx, k_sell_spmv<GG, SS>, grid, 256, S.nslices, S.nrows, S.soff, S.J, S.A, x, alpha, beta, yin, yout))
+    if (G == 4) { if (single) PE_SPMV(4, true); else PE_SPMV(4, false); }
+    else if (G == 8) { if (single) PE_SPMV(8, true); else PE_SPMV(8, false); }
+    else { if (single) PE_SPMV(12, true); else PE_SPMV(12, false); }
+#undef PE_SPMV
     PE_LAUNCHED(ctx);
     return 0;
 }
@@ -185,51 +288,43 @@ int pe_launch_sell_spmv(pe_ctx *ctx, const DevSELL &S, double alpha, const doubl
 // >= ext_base address the halo.  Rows of one colour are mutually independent, so no thread
 // reads a value another thread of this launch writes.
 // ---------------------------------------------------------------------------
-template <bool OFFD>
-__global__ void __launch_bounds__(256)
+template <int G, bool SINGLE, bool OFFD>
+__global__ void __launch_bounds__(256, ((SINGLE || G <= 4) ? 4 : 2))
 k_sell_gs(int s0, int s1, const int *__restrict__ soff, const int *__restrict__ J, const double *__restrict__ A,
-          int ext_base, const double *__restrict__ f, double *u, const double *__restrict__ uext,
-          const double *__restrict__ l1)
+          int ext_base, const double *f, double *u, const double *uext,
+          const double *__restrict__ l1, uint64_t pol_u)
 {
+    pdl_trigger();
     const int s = s0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (s >= s1) return;
-    const int o0 = soff[s], w = soff[s + 1] - o0;
+    if (s >= s1) { pdl_wait(); return; }
+    const int o0 = ld_nc_s32_pro(soff + s), w = ld_nc_s32_pro(soff + s + 1) - o0;
     const int *j = J + (int64_t)o0 * 32 + lane;
     const double *a = A + (int64_t)o0 * 32 + lane;
     const int row = s * 32 + lane;
-    const double d = l1[row], fr = f[row];
     const uint64_t pol = l2_evict_first_policy();
+    const double d = ld_stream_f64_pro(l1 + row, pol);       // l1, f: read once per sweep -> streaming, like the matrix
     double acc = 0.0;
-    int q = 0;
-#define PE_GATHER(c) ((OFFD && (c) >= ext_base) ? uext[(c) - ext_base] : u[(c)])
-    // groups of 4 entries, software-pipelined: the (col,val) loads of group g+1 are in flight
-    // while the gathers of group g are outstanding
-    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    if (w >= 4)
+#define PE_GATHER(cc) ((OFFD && (cc) >= ext_base) ? uext[(cc) - ext_base] : ld_hint_f64(u + (cc), pol_u))
+    int c[G]; double v[G];
+    sell_load_group<G, true>(j, a, 0, w, pol, c, v);
+    sell_pin_group_then_wait<G>(c, v, w);    // u, f (and the halo) come from the preceding kernels
+    const double fr = ld_hint_f64(f + row, pol), ur = u[row];   // issued with the first gathers: one round trip less at the end
+    for (int q = 0; q < w; q += G)
     {
-        c0 = ld_stream_s32(j, pol); c1 = ld_stream_s32(j + 32, pol); c2 = ld_stream_s32(j + 64, pol); c3 = ld_stream_s32(j + 96, pol);
-        a0 = ld_stream_f64(a, pol); a1 = ld_stream_f64(a + 32, pol); a2 = ld_stream_f64(a + 64, pol); a3 = ld_stream_f64(a + 96, pol);
+        double uv[G], b[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) if (q + k < w) { uv[k] = PE_GATHER(c[k]); b[k] = v[k]; }
+        if (!SINGLE && q + G < w) sell_load_group<G>(j, a, q + G, w, pol, c, v);
+#pragma unroll
+        for (int k = 0; k < G; ++k) if (q + k < w) acc = __fma_rn(b[k], uv[k], acc);   // explicit: same rounding in every variant
+        if (SINGLE) break;
     }
-    for (; q + 4 <= w; q += 4)
-    {
-        const double u0 = PE_GATHER(c0), u1 = PE_GATHER(c1), u2 = PE_GATHER(c2), u3 = PE_GATHER(c3);
-        const double b0 = a0, b1 = a1, b2 = a2, b3 = a3;
-        if (q + 8 <= w)
-        {
-            const int *jn = j + (q + 4) * 32; const double *an = a + (q + 4) * 32;
-            c0 = ld_stream_s32(jn, pol); c1 = ld_stream_s32(jn + 32, pol); c2 = ld_stream_s32(jn + 64, pol); c3 = ld_stream_s32(jn + 96, pol);
-            a0 = ld_stream_f64(an, pol); a1 = ld_stream_f64(an + 32, pol); a2 = ld_stream_f64(an + 64, pol); a3 = ld_stream_f64(an + 96, pol);
-        }
-        acc += b0 * u0; acc += b1 * u1; acc += b2 * u2; acc += b3 * u3;
-    }
-    for (; q < w; ++q) { const int c = ld_stream_s32(j + q * 32, pol); acc += ld_stream_f64(a + q * 32, pol) * PE_GATHER(c); }
 #undef PE_GATHER
-    if (d != 0.0) u[row] += (fr - acc) / d;
+    if (d != 0.0) u[row] = ur + (fr - acc) / d;
 }
 
-int pe_launch_sell_gs(pe_ctx *ctx, const DevSELL &S, int s0, int s1, int ext_base, const double *f, double *u,
-                      const double *uext, const double *l1)
+int pe_launch_sell_gs(pe_ctx *ctx, const DevSELL &S, int s0, int s1, int wmax, int ext_base, const double *f, double *u,
+                      const double *uext, const double *l1, uint64_t pol_gather)
 {
     if (s1 <= s0) return 0;
     if (ctx->rec)
@@ -240,26 +335,38 @@ int pe_launch_sell_gs(pe_ctx *ctx, const DevSELL &S, int s0, int s1, int ext_bas
         return 0;
     }
     const int grid = pe_grid_for((int64_t)(s1 - s0) * 32, 256);
-    if (uext) k_sell_gs<true><<<grid, 256, 0, ctx->stream>>>(s0, s1, S.soff, S.J, S.A, ext_base, f, u, uext, l1);
-    else k_sell_gs<false><<<grid, 256, 0, ctx->stream>>>(s0, s1, S.soff, S.J, S.A, ext_base, f, u, uext, l1);
+    int G; bool single;
+    sell_pick_group(wmax > 0 ? wmax : S.wmax, G, single);
+#define PE_GS(GG, SS, OO) PE_CUDA(pe_launch_k(ctx, k_sell_gs<GG, SS, OO>, grid, 256, s0, s1, S.soff, S.J, S.A, ext_base, f, u, uext, l1, pol_gather))
+#define PE_GS2(GG, SS) do { if (uext) PE_GS(GG, SS, true); else PE_GS(GG, SS, false); } while (0)
+    if (G == 4) { if (single) PE_GS2(4, true); else PE_GS2(4, false); }
+    else if (G == 8) { if (single) PE_GS2(8, true); else PE_GS2(8, false); }
+    else { if (single) PE_GS2(12, true); else PE_GS2(12, false); }
+#undef PE_GS2
+#undef PE_GS
     PE_LAUNCHED(ctx);
     return 0;
 }
 
 // colour-ordered <-> caller numbering
-__global__ void k_sell_perm_in(int n, const int *__restrict__ pos, const double *__restrict__ b,
-                               const double *__restrict__ x, double *fp, double *up)
+__global__ void k_sell_perm_in(int n, const int *__restrict__ pos, const double *b,
+                               const double *x, double *fp, double *up)
 {
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = i < n ? pos[i] : 0;
+    pdl_wait();
     if (i >= n) return;
-    const int p = pos[i];
     fp[p] = b[i];
     up[p] = x ? x[i] : 0.0;
 }
-__global__ void k_sell_perm_out(int n, const int *__restrict__ pos, const double *__restrict__ up, double *x)
+__global__ void k_sell_perm_out(int n, const int *__restrict__ pos, const double *up, double *x)
 {
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] = up[pos[i]];
+    const int p = i < n ? pos[i] : 0;
+    pdl_wait();
+    if (i < n) x[i] = up[p];
 }
 int pe_launch_perm_in(pe_ctx *ctx, int n, const int *pos, const double *b, const double *x, double *fp, double *up)
 {
@@ -270,7 +377,7 @@ int pe_launch_perm_in(pe_ctx *ctx, int n, const int *pos, const double *b, const
         pe_rec_push(ctx, o, 0.0);   // renumbering is our overhead, not algorithmic traffic
         return 0;
     }
-    k_sell_perm_in<<<pe_grid_for(n, 256), 256, 0, ctx->stream>>>(n, pos, b, x, fp, up);
+    PE_CUDA(pe_launch_k(ctx, k_sell_perm_in, pe_grid_for(n, 256), 256, n, pos, b, x, fp, up));
     PE_LAUNCHED(ctx);
     return 0;
 }
@@ -283,7 +390,7 @@ int pe_launch_perm_out(pe_ctx *ctx, int n, const int *pos, const double *up, dou
         pe_rec_push(ctx, o, 0.0);
         return 0;
     }
-    k_sell_perm_out<<<pe_grid_for(n, 256), 256, 0, ctx->stream>>>(n, pos, up, x);
+    PE_CUDA(pe_launch_k(ctx, k_sell_perm_out, pe_grid_for(n, 256), 256, n, pos, up, x));
     PE_LAUNCHED(ctx);
     return 0;
 }

@@ -26,19 +26,25 @@ template <int TPR>
 __global__ void __launch_bounds__(256)
 k_spmv(int n, const int *__restrict__ dI, const int *__restrict__ dJ, const double *__restrict__ dA,
        const int *__restrict__ oI, const int *__restrict__ oJ, const double *__restrict__ oA,
-       const double *__restrict__ x, const double *__restrict__ xext,
+       const double *x, const double *xext,
        double alpha, double beta, const double *yin, double *yout)
 {
+    // PDL (pe_launch_k): the first row extent is fetched before the wait; x, xext, yin after it
+    pdl_trigger();
     const int lane = threadIdx.x & (TPR - 1);
     const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / TPR;
     const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / TPR;
+    int lo = 0, hi = 0;
+    if (gid < n) { lo = dI[gid]; hi = dI[gid + 1]; }
+    if ((lo ^ hi) == 0x5bd1e995 && hi == -7) pdl_trigger();      // pins the two loads ahead of the wait
+    pdl_wait();
     for (int64_t row = gid; row < n; row += ngroups) {
-        int lo = dI[row], hi = dI[row + 1];
+        if (row != gid) { lo = dI[row]; hi = dI[row + 1]; }
         double s = 0.0;
-        for (int k = lo + lane; k < hi; k += TPR) s += ld_stream_f64(dA + k) * __ldg(x + ld_stream_s32(dJ + k));
+        for (int k = lo + lane; k < hi; k += TPR) s += ld_stream_f64(dA + k) * x[ld_stream_s32(dJ + k)];
         if (oI) {
             int olo = oI[row], ohi = oI[row + 1];
-            for (int k = olo + lane; k < ohi; k += TPR) s += ld_stream_f64(oA + k) * __ldg(xext + ld_stream_s32(oJ + k));
+            for (int k = olo + lane; k < ohi; k += TPR) s += ld_stream_f64(oA + k) * xext[ld_stream_s32(oJ + k)];
         }
 #pragma unroll
         for (int w = TPR / 2; w > 0; w >>= 1) s += __shfl_down_sync(0xffffffffu, s, w, TPR);
@@ -57,13 +63,16 @@ k_spmv(int n, const int *__restrict__ dI, const int *__restrict__ dJ, const doub
 #define SU 8
 __global__ void __launch_bounds__(256)
 k_spmv_stream(const int *__restrict__ rb, const int *__restrict__ I, const int *__restrict__ J,
-              const double *__restrict__ A, const double *__restrict__ x, double alpha, double beta,
+              const double *__restrict__ A, const double *x, double alpha, double beta,
               const double *yin, double *yout)
 {
     __shared__ double prod[PE_STREAM_CAP];
+    pdl_trigger();
     const int tid = threadIdx.x;
     const int r0 = rb[blockIdx.x], r1 = rb[blockIdx.x + 1];
     const int k0 = I[r0], k1 = I[r1];
+    if ((k0 ^ k1) == 0x5bd1e995 && k1 == -7) pdl_trigger();      // pins the row-block extent ahead of the wait
+    pdl_wait();
     for (int base = k0; base < k1; base += 256 * SU)
     {
         int c[SU]; double a[SU];
@@ -75,7 +84,7 @@ k_spmv_stream(const int *__restrict__ rb, const int *__restrict__ I, const int *
             a[u] = k < k1 ? ld_stream_f64(A + k) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < SU; ++u) if (c[u] >= 0) a[u] *= __ldg(x + c[u]);
+        for (int u = 0; u < SU; ++u) if (c[u] >= 0) a[u] *= x[c[u]];
 #pragma unroll
         for (int u = 0; u < SU; ++u) { const int k = base + u * 256 + tid; if (k < k1) prod[k - k0] = a[u]; }
     }
@@ -120,7 +129,7 @@ int pe_launch_spmv(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, int tpr,
     if (!oI && diag.nrb > 0)
     {
         PE_TRY(pe_prof_begin(ctx, 0, 12.0 * (double)diag.nnz + 4.0 * (n + 1) + 8.0 * diag.ncols + 8.0 * n + (beta != 0.0 ? 8.0 * n : 0.0)));
-        k_spmv_stream<<<diag.nrb, 256, 0, ctx->stream>>>(diag.rb, diag.I, diag.J, diag.A, x, alpha, beta, yin, yout);
+        PE_CUDA(pe_launch_k(ctx, k_spmv_stream, diag.nrb, 256, diag.rb, diag.I, diag.J, diag.A, x, alpha, beta, yin, yout));
         PE_LAUNCHED(ctx);
         PE_TRY(pe_prof_end(ctx));
         return 0;
@@ -129,7 +138,7 @@ int pe_launch_spmv(pe_ctx *ctx, const DevCSR &diag, const DevCSR *offd, int tpr,
     int64_t cap = (int64_t)PE_SM_COUNT * 8 * 8;     // 8 CTAs of 256 threads per SM, x8 waves
     int grid = (int)std::min<int64_t>((threads + 255) / 256, cap);
     if (grid < 1) grid = 1;
-#define LAUNCH(T) k_spmv<T><<<grid, 256, 0, ctx->stream>>>(n, diag.I, diag.J, diag.A, oI, oJ, oA, x, xext, alpha, beta, yin, yout)
+#define LAUNCH(T) PE_CUDA(pe_launch_k(ctx, k_spmv<T>, grid, 256, n, diag.I, diag.J, diag.A, oI, oJ, oA, x, xext, alpha, beta, yin, yout))
     const double nnz_all = (double)diag.nnz + (oI ? (double)offd->nnz : 0.0);
     PE_TRY(pe_prof_begin(ctx, 0, 12.0 * nnz_all + 4.0 * (n + 1) + 8.0 * diag.ncols + 8.0 * n + (beta != 0.0 ? 8.0 * n : 0.0)));
     switch (tpr) {

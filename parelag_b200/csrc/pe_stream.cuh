@@ -25,6 +25,33 @@ __device__ __forceinline__ int ld_stream_s32(const int *p, uint64_t pol)
     return v;
 }
 
+// "Prologue" variants: volatile, so the compiler keeps them ahead of griddepcontrol.wait (pdl_wait)
+// -- they fetch immutable matrix data while the preceding kernel is still draining.
+__device__ __forceinline__ double ld_stream_f64_pro(const double *p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int ld_stream_s32_pro(const int *p, uint64_t pol)
+{
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int ld_nc_s32_pro(const int *p)
+{
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_nc_f64_pro(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // scalar recurrences of mfem::CGSolver::Mult, one phase per call (single thread)
 //  phase 0: DOT = (d, r) before the loop        phase 1: DOT = (z, d) before the loop
 //  phase 2: DOT = (r, z) in iteration `iter`    phase 3: DOT = (d, z) in iteration `iter`

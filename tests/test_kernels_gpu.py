@@ -149,6 +149,54 @@ def test_gauss_seidel_multicolor(ctx, weights, gs_kernel, dims):
     assert _rel(dx.download(), so.apply(b, x0, True)) < 1e-13
 
 
+def _stencil27(n):
+    t = sp.diags([np.ones(n - 1), np.ones(n), np.ones(n - 1)], [-1, 0, 1])
+    A = sp.kron(sp.kron(t, t), t).tocsr()
+    A.data[:] = -1.0
+    return (A + sp.diags(np.full(n ** 3, 27.0))).tocsr()
+
+
+@pytest.mark.parametrize("maker", [lambda: laplace3d(21, 20, 19), lambda: _stencil27(13),
+                                   lambda: sp.csr_matrix(aggregation_P(12, 10, 8))])
+def test_sell_group_size_and_pdl_do_not_change_results(ctx, maker):
+    """The SELL kernels' entry-group size (4/8/12, single-group or pipelined) and programmatic dependent
+    launch are scheduling choices: SpMV and multicolour GS results are bit-identical across them and match
+    the oracle (7-point: w<=7 single group of 8; 27-point: w=27 pipelined groups; P: w<=2)."""
+    A = maker()
+    square = A.shape[0] == A.shape[1]
+    rng = np.random.default_rng(11)
+    x, b = rng.standard_normal(A.shape[1]), rng.standard_normal(A.shape[0])
+    old = [capi.get_tuning(k) for k in (capi.TUNE_SELL_MIN_ROWS, capi.TUNE_SELL_GROUP, capi.TUNE_PDL)]
+    capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, 0)
+    results = []
+    try:
+        for group, pdl in [(0, 1), (0, 0), (4, 1), (8, 1), (12, 1), (12, 0)]:
+            capi.set_tuning(capi.TUNE_SELL_GROUP, group)
+            capi.set_tuning(capi.TUNE_PDL, pdl)
+            dA = capi.Mat.from_scipy(ctx, A)
+            dx, dy = capi.Vec(ctx, data=x), capi.Vec(ctx, A.shape[0])
+            for _ in range(3):                      # back-to-back launches: the overlap PDL allows
+                dA.spmv(dx, dy, alpha=1.0, beta=0.0)
+            out = [dy.download()]
+            if square:
+                s = capi.Smoother(ctx, dA, type=2, sweeps=2, ordering=capi.GS_MULTICOLOR)
+                du, db = capi.Vec(ctx, data=x), capi.Vec(ctx, data=b)
+                s.apply(db, du, True)
+                out.append(du.download())
+            results.append(out)
+    finally:
+        for k, v in zip((capi.TUNE_SELL_MIN_ROWS, capi.TUNE_SELL_GROUP, capi.TUNE_PDL), old):
+            capi.set_tuning(k, v)
+    assert _rel(results[0][0], orc.matvec(A, x)) < RTOL_SPMV
+    if square:
+        oorder, _ = orc.multicolor_order(A)
+        so = orc.Smoother(A, type=2, sweeps=2, order=oorder)
+        assert _rel(results[0][1], so.apply(b, x, True)) < 1e-13
+    for r in results[1:]:
+        for a0, a1 in zip(results[0], r):
+            assert np.array_equal(a0, a1)
+
+
 @pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_chebyshev(ctx, order):
     A = laplace3d(9, 9, 9)
