@@ -11,7 +11,7 @@ all: $(LIB) oracle
 
 $(LIB): $(OBJ)
 	@mkdir -p $(dir $@)
-	$(NVCC) -shared $(ARCH) -o $@ $(OBJ) -lcudart -ldl
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJ) -lcudart -ldl -lgomp
 
 build/%.o: %.cu $(wildcard parelag_b200/csrc/*.cuh) $(wildcard include/*.h)
 	@mkdir -p $(dir $@)
@@ -19,7 +19,7 @@ build/%.o: %.cu $(wildcard parelag_b200/csrc/*.cuh) $(wildcard include/*.h)
 
 build/%.o: %.cpp $(wildcard parelag_b200/src/*.hpp) $(wildcard include/*.h)
 	@mkdir -p $(dir $@)
-	g++ -O2 -std=c++17 -fPIC -Wall -Iinclude -Iparelag_b200/src -c $< -o $@
+	g++ -O3 -std=c++17 -fopenmp -fPIC -Wall -Wno-misleading-indentation -Iinclude -Iparelag_b200/src -c $< -o $@
 
 oracle: oracle/libsolve_oracle.so
 

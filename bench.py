@@ -253,6 +253,11 @@ def main():
         S = api.Sequence.hex((n, n, n), levels, jstart=args.jstart)
     ctx.sync()
     t_coarsen = time.perf_counter() - t0
+    import ctypes
+    st6 = (ctypes.c_double * 6)()
+    capi.lib().pe_local_stage_seconds(st6, 1)
+    ext_stages = {"h2d_s": st6[0], "kernel_s": st6[1], "d2h_s": st6[2], "h2d_GB": st6[3] / 1e9, "d2h_GB": st6[4] / 1e9,
+                  "calls": int(st6[5])}
     t0 = time.perf_counter()
     A = S.assemble_system(ctx, 0, 2, ESS)
     ctx.sync()
@@ -300,7 +305,8 @@ def main():
                "Coarsen: DofAgglomeration", "Coarsen: traces prepare (host)", "Coarsen: batched traces (H2D + kernels + D2H)",
                "Coarsen: traces commit (host)", "Coarsen: extension prepare (host)",
                "Coarsen: batched extension (H2D + kernels + D2H)", "Coarsen: extension commit (host)",
-               "Coarsen: finalize P and D", "Coarsen: project targets"):
+               "Coarsen: finalize P and D", "Coarsen: project targets", "Host arena reserve (parallel first touch)",
+               "Fine sequence: dof handlers", "Fine sequence: D and mass pools", "Fine sequence: targets"):
         v = api.timer(nm)
         if v > 0:
             timers[nm] = v
@@ -466,7 +472,10 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "setup_s": {"sequence_all_levels": t_coarsen, "assemble_system": t_assemble, "build_solver": t_build,
-                            "total": t_coarsen + t_assemble + t_build, "timers": timers},
+                            "total": t_coarsen + t_assemble + t_build, "timers": timers,
+                            "batched_extension_stages": ext_stages,
+                            "host_peak_rss_GB": __import__("resource").getrusage(__import__("resource").RUSAGE_SELF).ru_maxrss / 1e6,
+                            "host_cores": os.cpu_count()},
                 "spmv_fine_operator": spmv,
                 "pcg": {"iterations": iters, "converged": conv, "seconds_host_buffers": t_solve,
                         "Br_r_first": float(hist[0]), "Br_r_last": float(hist[-1])}}

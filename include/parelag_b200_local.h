@@ -82,6 +82,13 @@ typedef struct pe_extension_batch {
 } pe_extension_batch;
 
 int pe_batched_traces(pe_ctx *ctx, const pe_trace_batch *batch);
+/* wall-clock split of the pe_batched_extension calls so far (setup profiling): out6 = {H2D staging s, kernel s,
+ * D2H s, bytes uploaded, bytes downloaded, calls}; reset != 0 clears the counters */
+int pe_local_stage_seconds(double *out6, int reset);
+/* enable != 0 opens a scope in which the batched calls keep device copies of their constant inputs (entity mass
+ * pools, agglomerate tables, D_j) keyed by host address -- the caller guarantees they do not change or move until
+ * the scope is closed with enable == 0, which frees the copies (one scope per DeRhamSequence::Coarsen()). */
+int pe_local_cache(pe_ctx *ctx, int enable);
 int pe_batched_extension(pe_ctx *ctx, const pe_extension_batch *batch);
 
 #ifdef __cplusplus

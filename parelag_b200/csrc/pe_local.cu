@@ -19,6 +19,8 @@
 // sizes, so no tensor cores.  SVD sign convention: largest-magnitude
 // entry of every retained singular vector is positive (first on ties).
 #include "pe_core.cuh"
+#include <chrono>
+#include <map>
 #include "../../include/parelag_b200_local.h"
 #include <algorithm>
 #include <cmath>
@@ -674,18 +676,46 @@ __global__ void __launch_bounds__(LT) k_extension(ExtArgs a)
 // ---------------------------------------------------------------------------
 namespace
 {
+// wall-clock split of the batched calls (pe_local_stage_seconds): [0] H2D staging incl. cudaMalloc,
+// [1] kernel, [2] D2H of the results, [3] bytes uploaded, [4] bytes downloaded, [5] calls
+static double g_stage[6] = {0, 0, 0, 0, 0, 0};
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// Device copies of inputs that stay constant over one Coarsen() (entity mass pools, agglomerate tables, the
+// fine D_j): uploaded once per pe_local_cache(1) ... pe_local_cache(0) scope and shared by the per-form,
+// per-codimension batched calls, keyed by host address and size.  At 144^3 hexahedra the 24 extension
+// calls of the first level re-sent 31 GB without it.
+static bool g_cache_on = false;
+static std::map<std::pair<const void *, size_t>, void *> g_cache;
 struct DevBuf
 {
     std::vector<void *> ptrs;
     cudaStream_t st;
     explicit DevBuf(cudaStream_t s) : st(s) {}
     ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
+    // constant input: served from the cache when a scope is open
+    template <class T> int upc(const T *h, size_t n, const T **out)
+    {
+        const size_t bytes = sizeof(T) * n;
+        if (!g_cache_on || !h || bytes < ((size_t)1 << 16)) return up(h, n, out);
+        auto key = std::make_pair((const void *)h, bytes);
+        auto it = g_cache.find(key);
+        if (it == g_cache.end())
+        {
+            T *d = nullptr;
+            PE_CUDA(cudaMalloc(&d, bytes));
+            PE_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st));
+            g_stage[3] += (double)bytes;
+            it = g_cache.emplace(key, (void *)d).first;
+        }
+        *out = static_cast<const T *>(it->second);
+        return 0;
+    }
     template <class T> int up(const T *h, size_t n, const T **out)
     {
         T *d = nullptr;
         PE_CUDA(cudaMalloc(&d, sizeof(T) * (n > 0 ? n : 1)));
         ptrs.push_back(d);
-        if (n > 0 && h) PE_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+        if (n > 0 && h) { PE_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, st)); g_stage[3] += (double)(sizeof(T) * n); }
         *out = d;
         return 0;
     }
@@ -696,6 +726,26 @@ struct DevBuf
         return 0;
     }
 };
+}
+
+extern "C" int pe_local_cache(pe_ctx *ctx, int enable)
+{
+    PE_CHECK(ctx, "bad arguments");
+    if (!enable)
+    {
+        PE_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (auto &kv : g_cache) cudaFree(kv.second);
+        g_cache.clear();
+    }
+    g_cache_on = enable != 0;
+    return 0;
+}
+
+extern "C" int pe_local_stage_seconds(double *out6, int reset)
+{
+    if (out6) for (int i = 0; i < 6; ++i) out6[i] = g_stage[i];
+    if (reset) for (int i = 0; i < 6; ++i) g_stage[i] = 0.0;
+    return 0;
 }
 
 extern "C" int pe_batched_traces(pe_ctx *ctx, const pe_trace_batch *b)
@@ -714,7 +764,7 @@ extern "C" int pe_batched_traces(pe_ctx *ctx, const pe_trace_batch *b)
     PE_TRY(D.up(b->J, (size_t)nadof, &a.J));
     PE_TRY(D.up(b->pv, (size_t)b->ndofs, &a.pv));
     PE_TRY(D.up(b->diagM, (size_t)nadof, &a.diagM));
-    PE_TRY(D.up(b->T, (size_t)b->ldT * b->nT, &a.T));
+    PE_TRY(D.upc(b->T, (size_t)b->ldT * b->nT, &a.T));
     PE_TRY(D.up(b->out_off, (size_t)b->nAE + 1, (const long long **)&a.out_off));
     const size_t out_n = (size_t)b->out_off[b->nAE];
     PE_TRY(D.alloc(out_n, &a.out));
@@ -739,16 +789,23 @@ extern "C" int pe_batched_traces(pe_ctx *ctx, const pe_trace_batch *b)
 
 static int up_pool(DevBuf &D, const pe_blockpool_view &h, PoolV &d)
 {
-    PE_TRY(D.up(h.off, (size_t)h.n + 1, (const long long **)&d.off));
-    PE_TRY(D.up(h.size, (size_t)h.n, &d.size));
-    PE_TRY(D.up(h.rdoff, (size_t)h.n + 1, &d.rdoff));
-    PE_TRY(D.up(h.vals, (size_t)(h.n > 0 ? h.off[h.n] : 0), &d.vals));
+    PE_TRY(D.upc(h.off, (size_t)h.n + 1, (const long long **)&d.off));
+    PE_TRY(D.upc(h.size, (size_t)h.n, &d.size));
+    PE_TRY(D.up(h.rdoff, (size_t)h.n + 1, &d.rdoff));       // a temporary of the caller
+    PE_TRY(D.upc(h.vals, (size_t)(h.n > 0 ? h.off[h.n] : 0), &d.vals));
     return 0;
 }
-static int up_csr(DevBuf &D, const pe_csr_view &h, CsrV &d)
+static int up_csr(DevBuf &D, const pe_csr_view &h, CsrV &d, bool constant = false)
 {
-    PE_TRY(D.up(h.I, (size_t)h.nrows + 1, &d.I));
     const size_t nnz = h.nrows > 0 && h.I ? (size_t)h.I[h.nrows] : 0;
+    if (constant)
+    {
+        PE_TRY(D.upc(h.I, (size_t)h.nrows + 1, &d.I));
+        PE_TRY(D.upc(h.J, nnz, &d.J));
+        PE_TRY(D.upc(h.A, nnz, &d.A));
+        return 0;
+    }
+    PE_TRY(D.up(h.I, (size_t)h.nrows + 1, &d.I));
     PE_TRY(D.up(h.J, nnz, &d.J));
     PE_TRY(D.up(h.A, nnz, &d.A));
     return 0;
@@ -767,32 +824,34 @@ extern "C" int pe_batched_extension(pe_ctx *ctx, const pe_extension_batch *b)
     PE_CHECK(ctx && b, "bad arguments");
     if (b->nAE == 0) return 0;
     cudaStream_t st = ctx->stream;
+    const double t_begin = now_s();
     DevBuf D(st);
     ExtArgs a{};
     const int nAE = b->nAE;
     a.nAE = nAE; a.facet = b->facet; a.compute_null = b->compute_null;
     a.nT = b->nT; a.ldT = b->ldT; a.svd_tol = b->svd_tol; a.smallest_entry = b->smallest_entry;
-    PE_TRY(D.up(b->uI, (size_t)nAE + 1, &a.uI)); PE_TRY(D.up(b->uJ, (size_t)b->uI[nAE], &a.uJ)); PE_TRY(D.up(b->uNint, (size_t)nAE, &a.uN));
-    PE_TRY(D.up(b->pI, (size_t)nAE + 1, &a.pI)); PE_TRY(D.up(b->pJ, (size_t)b->pI[nAE], &a.pJ)); PE_TRY(D.up(b->pNint, (size_t)nAE, &a.pN));
-    PE_TRY(D.up(b->aeI, (size_t)nAE + 1, &a.aeI)); PE_TRY(D.up(b->aeJ, (size_t)b->aeI[nAE], &a.aeJ));
+    // constant over the Coarsen() scope: DofAgglomeration tables, AE -> entity table, mass pools, slots, fine D_j
+    PE_TRY(D.upc(b->uI, (size_t)nAE + 1, &a.uI)); PE_TRY(D.upc(b->uJ, (size_t)b->uI[nAE], &a.uJ)); PE_TRY(D.upc(b->uNint, (size_t)nAE, &a.uN));
+    PE_TRY(D.upc(b->pI, (size_t)nAE + 1, &a.pI)); PE_TRY(D.upc(b->pJ, (size_t)b->pI[nAE], &a.pJ)); PE_TRY(D.upc(b->pNint, (size_t)nAE, &a.pN));
+    PE_TRY(D.upc(b->aeI, (size_t)nAE + 1, &a.aeI)); PE_TRY(D.upc(b->aeJ, (size_t)b->aeI[nAE], &a.aeJ));
     PE_TRY(up_pool(D, b->Mu, a.Mu)); PE_TRY(up_pool(D, b->Mp, a.Mp));
-    PE_TRY(D.up(b->slot_u, (size_t)b->Mu.rdoff[b->Mu.n], &a.slot_u));
-    PE_TRY(D.up(b->slot_p, (size_t)b->Mp.rdoff[b->Mp.n], &a.slot_p));
-    PE_TRY(up_csr(D, b->Dj, a.Dj));
+    PE_TRY(D.upc(b->slot_u, (size_t)b->Mu.rdoff[b->Mu.n], &a.slot_u));
+    PE_TRY(D.upc(b->slot_p, (size_t)b->Mp.rdoff[b->Mp.n], &a.slot_p));
+    PE_TRY(up_csr(D, b->Dj, a.Dj, true));
     PE_TRY(D.up(b->cbI, (size_t)nAE + 1, &a.cbI)); PE_TRY(D.up(b->cbJ, (size_t)b->cbI[nAE], &a.cbJ));
     PE_TRY(up_rowpool(D, b->Pj, a.Pj));
-    PE_TRY(up_csr(D, b->Pj1, a.Pj1));
+    PE_TRY(up_csr(D, b->Pj1, a.Pj1, true));                 // the finished P of form j+1
     PE_TRY(D.up(b->pnI, (size_t)nAE + 1, &a.pnI)); PE_TRY(D.up(b->pnJ, (size_t)b->pnI[nAE], &a.pnJ));
     if (b->facet) PE_TRY(D.up(b->pvc, (size_t)nAE, &a.pvc));
     else
     {
-        PE_TRY(D.up(b->qI, (size_t)nAE + 1, &a.qI)); PE_TRY(D.up(b->qJ, (size_t)b->qI[nAE], &a.qJ));
+        PE_TRY(D.upc(b->qI, (size_t)nAE + 1, &a.qI)); PE_TRY(D.upc(b->qJ, (size_t)b->qI[nAE], &a.qJ));
         PE_TRY(up_pool(D, b->Mq, a.Mq));
-        PE_TRY(D.up(b->slot_q, (size_t)b->Mq.rdoff[b->Mq.n], &a.slot_q));
-        PE_TRY(up_csr(D, b->Dj1, a.Dj1));
+        PE_TRY(D.upc(b->slot_q, (size_t)b->Mq.rdoff[b->Mq.n], &a.slot_q));
+        PE_TRY(up_csr(D, b->Dj1, a.Dj1, true));
         PE_TRY(up_rowpool(D, b->Dc, a.Dc));
     }
-    PE_TRY(D.up(b->T, (size_t)b->ldT * b->nT, &a.T));
+    PE_TRY(D.upc(b->T, (size_t)b->ldT * b->nT, &a.T));
     PE_TRY(D.up(b->out_off, (size_t)nAE + 1, (const long long **)&a.out_off));
     const size_t out_n = (size_t)b->out_off[nAE];
     PE_TRY(D.alloc(out_n, &a.out));
@@ -817,13 +876,19 @@ extern "C" int pe_batched_extension(pe_ctx *ctx, const pe_extension_batch *b)
     PE_CHECK(smem <= 220 * 1024, "pe_batched_extension: agglomerate too large for shared memory ("
                                      + std::to_string(smem) + " bytes needed)");
     PE_CUDA(cudaFuncSetAttribute(k_extension, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PE_CUDA(cudaStreamSynchronize(st));
+    const double t_up = now_s();
     k_extension<<<nAE, LT, smem, st>>>(a);
     PE_LAUNCHED(ctx);
+    PE_CUDA(cudaStreamSynchronize(st));
+    const double t_kern = now_s();
     PE_CUDA(cudaMemcpyAsync(b->out, a.out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, st));
     PE_CUDA(cudaMemcpyAsync(b->k_out, a.k_out, sizeof(int) * (size_t)nAE, cudaMemcpyDeviceToHost, st));
     std::vector<int> info(nAE);
     PE_CUDA(cudaMemcpyAsync(info.data(), a.info_out, sizeof(int) * (size_t)nAE, cudaMemcpyDeviceToHost, st));
     PE_CUDA(cudaStreamSynchronize(st));
+    g_stage[0] += t_up - t_begin; g_stage[1] += t_kern - t_up; g_stage[2] += now_s() - t_kern;
+    g_stage[4] += (double)(sizeof(double) * out_n); g_stage[5] += 1.0;
     for (int e = 0; e < nAE; ++e)
         PE_CHECK(info[e] == 0, "pe_batched_extension: singular local system on agglomerate " + std::to_string(e)
                                    + " (code " + std::to_string(info[e]) + "); a bad topology (e.g. a torus-shaped agglomerate) can cause this");

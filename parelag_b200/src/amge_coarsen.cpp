@@ -13,6 +13,7 @@
 #include "amge_par.hpp"
 #include "parelag_b200_local.h"
 #include <cstring>
+#include <malloc.h>
 
 namespace parelag
 {
@@ -118,6 +119,13 @@ struct Coarsener
         C->topo = ctopo; C->nforms = nf; C->jstart = S.jstart; C->svd_tol = S.svd_tol; C->is_fe = false;
         C->dof.resize(nf); C->targets.resize(nf); C->ntargets = S.ntargets;
         agg.resize(nf); Ppool.resize(nf); Dcpool.resize(nf); Pfinal.resize(nf);
+        // the batched kernels of all forms and codimensions share one device copy of the level's constant inputs
+        struct CacheScope
+        {
+            pe_ctx *c;
+            explicit CacheScope(pe_ctx *ctx) : c(ctx) { pe_local_cache(c, 1); }
+            ~CacheScope() { pe_local_cache(c, 0); }
+        } cache_scope(ctx);
         {
             Timer t = TimeManager::AddTimer("Coarsen: DofAgglomeration");
             for (int j = S.jstart; j < nf; ++j) agg[j] = std::make_unique<DofAgglomeration>(S.topo, *S.dof[j]);
@@ -469,12 +477,49 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchy(int nx, i
     return BuildHexSequenceHierarchyPar(nullptr, nullptr, nx, ny, nz, Lx, Ly, Lz, alpha, beta, jstart, nlevels, svd_tol);
 }
 
+/// Host memory for the setup phase.  Building a hierarchy allocates (and re-allocates while vectors grow)
+/// several KB per fine element; in a container every fresh page costs a serialised page fault, which at
+/// 144^3 hexahedra was more than half of the setup time.  ReserveHostArena grows the malloc heap once by
+/// `bytes`, touches the pages from all host threads (page faults do run in parallel) and hands the block
+/// back to the heap, untrimmed: the setup's std::vectors are then carved out of already-resident memory.
+/// mmap-backed malloc is disabled while the arena is in use so that large blocks come from the heap too.
+void ReserveHostArena(size_t bytes)
+{
+    if (getenv("PE_NO_HOST_ARENA") || bytes < ((size_t)64 << 20)) return;
+    Timer t = TimeManager::AddTimer("Host arena reserve (parallel first touch)");
+    if (!getenv("PE_HOST_ARENA_KEEP_MMAP")) mallopt(M_MMAP_MAX, 0);
+    mallopt(M_TRIM_THRESHOLD, -1);
+    mallopt(M_TOP_PAD, 64 << 20);
+    char *p = static_cast<char *>(malloc(bytes));
+    if (!p) return;
+#pragma omp parallel for schedule(static)
+    for (size_t k = 0; k < bytes; k += 4096) p[k] = 0;
+    free(p);
+}
+/// back to the default policy (blocks already carved from the heap stay where they are)
+void ReleaseHostArena()
+{
+    if (getenv("PE_NO_HOST_ARENA")) return;
+    mallopt(M_MMAP_MAX, 65536);
+    mallopt(M_TRIM_THRESHOLD, 128 * 1024);
+    mallopt(M_TOP_PAD, 0);
+}
+
 std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const pe_host_comm *comm, const int *procs, int nx, int ny, int nz,
                                                                            double Lx, double Ly, double Lz, const double *alpha,
                                                                            const double *beta, int jstart, int nlevels, double svd_tol)
 {
     const bool parallel = comm && comm->size > 1;
     const int one[3] = {1, 1, 1};
+    // ~2 KB of entity mass blocks per fine element plus integer tables, interpolation rows and staging buffers
+    // (peak RSS of the 144^3 setup: 26 GB = 8.7 KB per element).
+    // The heap policy stays in force afterwards (system assembly and BuildSolver stage gigabytes through
+    // host vectors as well); ReleaseHostArena() restores glibc's defaults for a caller that wants them back.
+    // Sized below the footprint on purpose (4 KB per element, at most 16 GB): measured on the B200 host (64 GB
+    // container), a 24 GB arena next to the CUDA driver's own pinned staging pushed the process into reclaim and
+    // every cudaMemcpy/cudaMalloc slowed down (setup 40 s), while 12 GB gave 27 s (44 s without an arena).
+    const size_t bpe = getenv("PE_HOST_ARENA_BPE") ? (size_t)atoll(getenv("PE_HOST_ARENA_BPE")) : (size_t)4000;
+    ReserveHostArena(std::min((size_t)nx * ny * nz * bpe, (size_t)16 << 30));
     BoxDecomposition box(parallel ? procs : one, parallel ? comm->rank : 0, nx, ny, nz);
     PARELAG_TEST_FOR_EXCEPTION(parallel && box.nranks() != comm->size, std::runtime_error,
                                "BuildHexSequenceHierarchyPar: the process grid does not match the communicator size");

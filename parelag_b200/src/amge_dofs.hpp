@@ -153,40 +153,44 @@ public:
         sep.assign(nd, 0);
         for (int c = 1; c < ncod; ++c)
             for (int d : AE_dof[c].J) sep[d] = c;
-        std::vector<int> local(nd, -1);
         for (int c = 0; c < ncod; ++c)
         {
             const HostCSR &A = AE_dof[c];
             I[c] = A.I;
             J[c] = A.J;
             nint[c].assign(A.nrows, 0);
-            for (int a = 0; a < A.nrows; ++a)
-            {
-                int *b = J[c].data() + A.I[a], *e = J[c].data() + A.I[a + 1];
-                if (dof.mcb > c)
-                {
-                    std::sort(b, e, [&](int x, int y) { return sep[x] != sep[y] ? sep[x] < sep[y] : x < y; });
-                    int cnt = 0;
-                    for (int *p = b; p != e; ++p) cnt += (sep[*p] == c);
-                    nint[c][a] = cnt;
-                }
-                else nint[c][a] = (int)(e - b);
-            }
+            const bool has_bdr = dof.mcb > c;
             // ADof_rDof: AE-local index of every entity-local dof copy (rDof) of member entities
             const HostCSR &ED = dof.entity_dof[c];
             const HostCSR &AEe = topo->AEntityEntity(c);
             slot[c].assign(ED.J.size(), -1);
             ent_AE[c].assign(ED.nrows, -1);
-            for (int a = 0; a < AEe.nrows; ++a)
+            // agglomerates are independent (an entity belongs to at most one AE of its codimension):
+            // every thread sorts and numbers its own agglomerates with a private scratch map
+#pragma omp parallel
             {
-                for (int k = I[c][a]; k < I[c][a + 1]; ++k) local[J[c][k]] = k - I[c][a];
-                for (int k = AEe.I[a]; k < AEe.I[a + 1]; ++k)
+                std::vector<int> local(nd, -1);
+#pragma omp for schedule(static)
+                for (int a = 0; a < A.nrows; ++a)
                 {
-                    const int ent = AEe.J[k];
-                    ent_AE[c][ent] = a;
-                    for (int r = ED.I[ent]; r < ED.I[ent + 1]; ++r) slot[c][r] = local[ED.J[r]];
+                    int *b = J[c].data() + A.I[a], *e = J[c].data() + A.I[a + 1];
+                    if (has_bdr)
+                    {
+                        std::sort(b, e, [&](int x, int y) { return sep[x] != sep[y] ? sep[x] < sep[y] : x < y; });
+                        int cnt = 0;
+                        for (int *p = b; p != e; ++p) cnt += (sep[*p] == c);
+                        nint[c][a] = cnt;
+                    }
+                    else nint[c][a] = (int)(e - b);
+                    for (int k = I[c][a]; k < I[c][a + 1]; ++k) local[J[c][k]] = k - I[c][a];
+                    for (int k = AEe.I[a]; k < AEe.I[a + 1]; ++k)
+                    {
+                        const int ent = AEe.J[k];
+                        ent_AE[c][ent] = a;
+                        for (int r = ED.I[ent]; r < ED.I[ent + 1]; ++r) slot[c][r] = local[ED.J[r]];
+                    }
+                    for (int k = I[c][a]; k < I[c][a + 1]; ++k) local[J[c][k]] = -1;
                 }
-                for (int k = I[c][a]; k < I[c][a + 1]; ++k) local[J[c][k]] = -1;
             }
         }
     }

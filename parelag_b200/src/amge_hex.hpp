@@ -111,15 +111,20 @@ inline void place(double *C, int n, int o, const double *B, int m, double s)
 }
 inline void fill_pool(BlockPool &P, int count, const double *blk, int m, const double *w = nullptr)
 {
-    // one allocation per pool: the fine element pools are gigabytes at 144^3 hexahedra
-    P.vals.reserve(P.vals.size() + (size_t)count * m * m);
-    P.size.reserve(P.size.size() + (size_t)count);
-    P.off.reserve(P.off.size() + (size_t)count);
+    // one allocation per pool (the fine element pools are gigabytes at 144^3 hexahedra), filled in parallel
+    const size_t n0 = P.size.size(), v0 = P.vals.size(), mm = (size_t)m * m;
+    P.size.resize(n0 + (size_t)count, m);
+    P.off.resize(n0 + (size_t)count + 1);
+    P.vals.resize(v0 + (size_t)count * mm);
+    double *vals = P.vals.data() + v0;
+    int64_t *off = P.off.data() + n0 + 1;
+#pragma omp parallel for schedule(static)
     for (int e = 0; e < count; ++e)
     {
-        double *d = P.add(m);
+        off[e] = (int64_t)(v0 + (size_t)(e + 1) * mm);
         const double s = w ? w[e] : 1.0;
-        for (int q = 0; q < m * m; ++q) d[q] = s * blk[q];
+        double *d = vals + (size_t)e * mm;
+        for (size_t q = 0; q < mm; ++q) d[q] = s * blk[q];
     }
 }
 } // namespace hexfe
@@ -134,6 +139,7 @@ inline void BuildFineHexSequence(const StructuredHexMesh &mesh, const std::share
     const int nel = (int)mesh.nel();
     S.topo = topo; S.nforms = 4; S.jstart = jstart; S.is_fe = true;
     S.dof.resize(4);
+    Timer t_dofs = TimeManager::AddTimer("Fine sequence: dof handlers");
     for (int j = 0; j < 4; ++j)
     {
         auto dh = std::make_shared<DofHandlerX>(3 - j, topo);
@@ -143,6 +149,8 @@ inline void BuildFineHexSequence(const StructuredHexMesh &mesh, const std::share
         dh->ComputeBoundaryMask();
         S.dof[j] = dh;
     }
+    t_dofs.Stop();
+    Timer t_pools = TimeManager::AddTimer("Fine sequence: D and mass pools");
     D.resize(3);
     D[0] = topo->GetB(2);
     D[1] = topo->GetB(1);
@@ -190,6 +198,8 @@ inline void BuildFineHexSequence(const StructuredHexMesh &mesh, const std::share
         double one = 1.0;
         fill_pool(S.M[{0, 3}], mesh.nv(), &one, 1);
     }
+    t_pools.Stop();
+    Timer t_targets = TimeManager::AddTimer("Fine sequence: targets");
     S.l2const.assign(nel, 1.0);
     S.facet_area.assign(mesh.nf(), 0.0);
     std::fill(S.facet_area.begin(), S.facet_area.begin() + mesh.nfx(), hy * hz);

@@ -7,6 +7,9 @@
 // required; host in this round).  All tables are kept in canonical CSR form (ascending
 // column indices per row) -- the numbering convention shared with oracle/amge.py.
 #pragma once
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -22,33 +25,63 @@ namespace parelag
 {
 namespace hostcsr
 {
-/// C = A*B, rows sorted ascending, exact cancellations (|c| < tol) dropped when drop_tol >= 0
+/// C = A*B, rows sorted ascending, exact cancellations (|c| < tol) dropped when drop_tol >= 0.
+/// Rows are independent: every thread owns a contiguous row range with its own marker/accumulator,
+/// row products land in per-thread buffers and are stitched together in row order, so the result
+/// (pattern, value bits) does not depend on the thread count.
 inline HostCSR Mult(const HostCSR &A, const HostCSR &B, double drop_tol = -1.0)
 {
     PARELAG_TEST_FOR_EXCEPTION(A.ncols != B.nrows, std::logic_error, "hostcsr::Mult: size mismatch");
     HostCSR C;
     C.nrows = A.nrows; C.ncols = B.ncols;
     C.I.assign(A.nrows + 1, 0);
-    std::vector<int> marker(B.ncols, -1), cols;
-    std::vector<double> acc(B.ncols, 0.0);
-    for (int i = 0; i < A.nrows; ++i)
+    int nt = 1;
+#ifdef _OPENMP
+    nt = std::max(1, std::min(omp_get_max_threads(), A.nrows / 4096 + 1));
+#endif
+    std::vector<std::vector<int>> Jt(nt);
+    std::vector<std::vector<double>> At(nt);
+    std::vector<int> r0(nt + 1, 0);
+    for (int t = 0; t <= nt; ++t) r0[t] = (int)((int64_t)A.nrows * t / nt);
+#pragma omp parallel num_threads(nt)
     {
-        cols.clear();
-        for (int ka = A.I[i]; ka < A.I[i + 1]; ++ka)
+#ifdef _OPENMP
+        const int t = omp_get_thread_num();
+#else
+        const int t = 0;
+#endif
+        std::vector<int> marker(B.ncols, -1), cols;
+        std::vector<double> acc(B.ncols, 0.0);
+        std::vector<int> &Jo = Jt[t];
+        std::vector<double> &Ao = At[t];
+        for (int i = r0[t]; i < r0[t + 1]; ++i)
         {
-            const int k = A.J[ka];
-            const double a = A.A[ka];
-            for (int kb = B.I[k]; kb < B.I[k + 1]; ++kb)
+            cols.clear();
+            for (int ka = A.I[i]; ka < A.I[i + 1]; ++ka)
             {
-                const int j = B.J[kb];
-                if (marker[j] != i) { marker[j] = i; cols.push_back(j); acc[j] = a * B.A[kb]; }
-                else acc[j] += a * B.A[kb];
+                const int k = A.J[ka];
+                const double a = A.A[ka];
+                for (int kb = B.I[k]; kb < B.I[k + 1]; ++kb)
+                {
+                    const int j = B.J[kb];
+                    if (marker[j] != i) { marker[j] = i; cols.push_back(j); acc[j] = a * B.A[kb]; }
+                    else acc[j] += a * B.A[kb];
+                }
             }
+            std::sort(cols.begin(), cols.end());
+            int cnt = 0;
+            for (int j : cols)
+                if (drop_tol < 0.0 || std::fabs(acc[j]) >= drop_tol) { Jo.push_back(j); Ao.push_back(acc[j]); ++cnt; }
+            C.I[i + 1] = cnt;
         }
-        std::sort(cols.begin(), cols.end());
-        for (int j : cols)
-            if (drop_tol < 0.0 || std::fabs(acc[j]) >= drop_tol) { C.J.push_back(j); C.A.push_back(acc[j]); }
-        C.I[i + 1] = (int)C.J.size();
+    }
+    for (int i = 0; i < A.nrows; ++i) C.I[i + 1] += C.I[i];
+    C.J.resize((size_t)C.I[A.nrows]); C.A.resize((size_t)C.I[A.nrows]);
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+    for (int t = 0; t < nt; ++t)
+    {
+        std::copy(Jt[t].begin(), Jt[t].end(), C.J.begin() + C.I[r0[t]]);
+        std::copy(At[t].begin(), At[t].end(), C.A.begin() + C.I[r0[t]]);
     }
     return C;
 }
