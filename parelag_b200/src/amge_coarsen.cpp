@@ -14,6 +14,8 @@
 #include "parelag_b200_local.h"
 #include <cstring>
 #include <malloc.h>
+#include <thread>
+#include <cstdio>
 
 namespace parelag
 {
@@ -483,16 +485,39 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchy(int nx, i
 /// `bytes`, touches the pages from all host threads (page faults do run in parallel) and hands the block
 /// back to the heap, untrimmed: the setup's std::vectors are then carved out of already-resident memory.
 /// mmap-backed malloc is disabled while the arena is in use so that large blocks come from the heap too.
-void ReserveHostArena(size_t bytes)
+static size_t HostMemAvailable()
 {
+    size_t avail = (size_t)64 << 30;
+    if (FILE *f = fopen("/proc/meminfo", "r"))
+    {
+        char line[256];
+        while (fgets(line, sizeof line, f))
+        {
+            unsigned long long kb = 0;
+            if (sscanf(line, "MemAvailable: %llu kB", &kb) == 1) { avail = (size_t)kb << 10; break; }
+        }
+        fclose(f);
+    }
+    return avail;
+}
+
+/// `sharers`: processes of this node that reserve an arena at the same time (ranks of the communicator)
+void ReserveHostArena(size_t bytes, int sharers)
+{
+    if (sharers < 1) sharers = 1;
+    // never more than a fifth of what the node has left, split between the ranks
+    bytes = std::min(bytes, HostMemAvailable() / 5 / (size_t)sharers);
     if (getenv("PE_NO_HOST_ARENA") || bytes < ((size_t)64 << 20)) return;
+    // explicit thread count: launchers (torchrun) export OMP_NUM_THREADS=1, which would serialise the first touch
+    int nthreads = (int)std::thread::hardware_concurrency() / sharers;
+    if (nthreads < 1) nthreads = 1;
     Timer t = TimeManager::AddTimer("Host arena reserve (parallel first touch)");
     if (!getenv("PE_HOST_ARENA_KEEP_MMAP")) mallopt(M_MMAP_MAX, 0);
     mallopt(M_TRIM_THRESHOLD, -1);
     mallopt(M_TOP_PAD, 64 << 20);
     char *p = static_cast<char *>(malloc(bytes));
     if (!p) return;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(nthreads)
     for (size_t k = 0; k < bytes; k += 4096) p[k] = 0;
     free(p);
 }
@@ -518,8 +543,12 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
     // Sized below the footprint on purpose (4 KB per element, at most 16 GB): measured on the B200 host (64 GB
     // container), a 24 GB arena next to the CUDA driver's own pinned staging pushed the process into reclaim and
     // every cudaMemcpy/cudaMalloc slowed down (setup 40 s), while 12 GB gave 27 s (44 s without an arena).
+    // With the arena the heap is never trimmed, so the peak footprint grows from ~9 to ~12 KB per element: ranks
+    // that share a node only use it when that still leaves a quarter of the node's memory free.
     const size_t bpe = getenv("PE_HOST_ARENA_BPE") ? (size_t)atoll(getenv("PE_HOST_ARENA_BPE")) : (size_t)4000;
-    ReserveHostArena(std::min((size_t)nx * ny * nz * bpe, (size_t)16 << 30));
+    const size_t nel_all = (size_t)nx * ny * nz, sharers = parallel ? (size_t)comm->size : 1;
+    if (nel_all * 12000 * sharers <= HostMemAvailable() / 4 * 3)
+        ReserveHostArena(std::min(nel_all * bpe, (size_t)16 << 30), (int)sharers);
     BoxDecomposition box(parallel ? procs : one, parallel ? comm->rank : 0, nx, ny, nz);
     PARELAG_TEST_FOR_EXCEPTION(parallel && box.nranks() != comm->size, std::runtime_error,
                                "BuildHexSequenceHierarchyPar: the process grid does not match the communicator size");
