@@ -197,6 +197,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sell-min-rows", type=int, default=None,
                     help="tuning: levels with fewer rows use the lanes-per-row CSR Gauss-Seidel kernel (library default 200000)")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU halo exchange: NVLink peer-memory stores (default) or ncclSend/ncclRecv")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket 2 extra V-cycles with cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     args = ap.parse_args()
@@ -231,6 +233,7 @@ def main():
     procs = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world)
     if procs is None:
         raise SystemExit("bench.py: --gpus must be 1, 2, 4 or 8")
+    capi.set_tuning(capi.TUNE_P2P_HALO, 1 if args.halo == "p2p" else 0)
     if world > 1:
         # one box per GPU: the library's own NCCL communicator carries the data path, a gloo group the
         # setup-time host exchanges (MPI in the reference)
@@ -461,8 +464,10 @@ def main():
                                         % (n, ndofs, nlev, args.ordering)) if world == 1 else
                                        ("3DHdivWeakScaling layout (configs[4]): %dx%dx%d boxes of %d^3 hexahedra, one box per GPU, "
                                         "H(div) A=M2+D2^T M3 D2, %d RT0 true dofs in total, %d-level AMGe, Hiptmair(hybrid l1-GS,"
-                                        "hybrid l1-GS) %s order, PCG-GS coarse solver, NCCL ParCSR halo exchange"
-                                        % (procs + (n, ndofs_global, nlev, args.ordering))),
+                                        "hybrid l1-GS) %s order, PCG-GS coarse solver, ParCSR halo exchange by %s"
+                                        % (procs + (n, ndofs_global, nlev, args.ordering,
+                                                    "NVLink peer-memory stores + device flags (CUDA IPC)" if capi.lib().pe_ctx_p2p_enabled(ctx.h)
+                                                    else "NCCL send/recv"))),
                            "l2_policy": "inputs larger than L2 (hierarchy working set %.1f GB)" %
                                         (sum(12.0 * li[1] for li in level_info) / 1e9),
                            "parallelism": ("single GPU" if world == 1 else

@@ -68,6 +68,8 @@ int pe_nccl_get_unique_id(void *id128);
 const char *pe_last_error(void);
 int pe_ctx_rank(const pe_ctx *ctx);
 int pe_ctx_nranks(const pe_ctx *ctx);
+/* 1 when the halo exchange of this context goes through NVLink peer memory (PE_TUNE_P2P_HALO), 0 = NCCL send/recv */
+int pe_ctx_p2p_enabled(const pe_ctx *ctx);
 /* number of kernels this library has launched on ctx since creation */
 int64_t pe_ctx_launch_count(const pe_ctx *ctx);
 /* stream-ordered CUDA-event timer on the context's stream (milliseconds) */
@@ -85,14 +87,19 @@ int pe_ctx_profile_get(pe_ctx *ctx, int kernel_id, int64_t *count, double *total
  * kernel for matrices with at least this many rows and the lanes-per-row CSR kernel below it.
  * PE_TUNE_SELL_GROUP [0]: entries per load group of the SELL kernels (0 = chosen from the slice widths;
  * 4, 8 or 12 forces one).  Results do not depend on it (the summation order of a row is fixed).
- * PE_TUNE_PDL [1]: launch the solve-path kernels with programmatic stream serialization (single rank):
+ * PE_TUNE_PDL [1]: launch the solve-path kernels with programmatic stream serialization (single rank, and
+ * multi-rank when the halo exchange runs over peer memory):
  * the matrix prologue of a kernel overlaps the tail of its predecessor.
  * PE_TUNE_GATHER_KEEP_PCT [0]: percentage (0, 25, 50, 60, 75, 90, 100) of the u-gather lines of the SELL
  * Gauss-Seidel kernel that get L2 priority evict_last (the rest evict_unchanged); 0 = normal priority.
  * The colour-ordered iterate is re-read by every colour launch while 30-50x its size streams through
  * L2; keeping a fixed fraction resident turns an all-miss cyclic pattern into that fraction of hits.
- * Read when a smoother is created. */
-enum { PE_TUNE_SELL_MIN_ROWS = 0, PE_TUNE_SELL_GROUP = 1, PE_TUNE_PDL = 2, PE_TUNE_GATHER_KEEP_PCT = 3, PE_TUNE_COUNT = 4 };
+ * Read when a smoother is created.
+ * PE_TUNE_P2P_HALO [1]: multi-rank, one node: ParCSR halo exchange by direct stores into the neighbours' ghost
+ * buffers over NVLink peer memory (CUDA IPC) with device-side arrival flags instead of ncclSend/ncclRecv.
+ * Read at pe_ctx_set_host_comm; falls back to NCCL when a rank cannot map a peer. */
+enum { PE_TUNE_SELL_MIN_ROWS = 0, PE_TUNE_SELL_GROUP = 1, PE_TUNE_PDL = 2, PE_TUNE_GATHER_KEEP_PCT = 3, PE_TUNE_P2P_HALO = 4,
+       PE_TUNE_COUNT = 6 };
 int pe_set_tuning(int key, int value);
 int pe_get_tuning(int key);
 /* write a scratch buffer larger than L2 (bench hygiene) */

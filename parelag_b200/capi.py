@@ -133,6 +133,7 @@ TUNE_SELL_MIN_ROWS = 0
 TUNE_SELL_GROUP = 1
 TUNE_PDL = 2
 TUNE_GATHER_KEEP_PCT = 3
+TUNE_P2P_HALO = 4
 
 
 def set_tuning(key, value):

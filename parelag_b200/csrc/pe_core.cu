@@ -117,6 +117,7 @@ extern "C" int pe_ctx_destroy(pe_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->comm_stream);
+    pe_p2p_shutdown(c);
     if (c->nccl) g_nccl.CommDestroy(c->nccl);
     cudaFree(c->partials_d); cudaFree(c->scalar_d); cudaFreeHost(c->scalar_h);
     if (c->flush_d) cudaFree(c->flush_d);
@@ -127,7 +128,7 @@ extern "C" int pe_ctx_destroy(pe_ctx *c)
     return 0;
 }
 
-static int g_tuning[PE_TUNE_COUNT] = {200000, 0, 1, 0};
+static int g_tuning[PE_TUNE_COUNT] = {200000, 0, 1, 0, 1, 0};
 extern "C" int pe_set_tuning(int key, int value)
 {
     PE_CHECK(key >= 0 && key < PE_TUNE_COUNT, "bad tuning key");
@@ -144,6 +145,7 @@ extern "C" int pe_ctx_sync(pe_ctx *c)
 }
 extern "C" int pe_ctx_rank(const pe_ctx *c) { return c->rank; }
 extern "C" int pe_ctx_nranks(const pe_ctx *c) { return c->nranks; }
+extern "C" int pe_ctx_p2p_enabled(const pe_ctx *c) { return c->p2p_base ? 1 : 0; }
 extern "C" int64_t pe_ctx_launch_count(const pe_ctx *c) { return c->launches; }
 
 extern "C" int pe_ctx_timer_start(pe_ctx *c)
@@ -720,6 +722,14 @@ static int upload_block(pe_ctx *ctx, DevCSR &m, int32_t nrows, int32_t ncols, co
     return 0;
 }
 
+// ghost / reverse-receive buffers live in the peer-visible halo arena when there is one (pe_p2p.cu)
+static int halo_buffer_alloc(pe_ctx *ctx, size_t n, double **out)
+{
+    *out = static_cast<double *>(pe_p2p_alloc(ctx, sizeof(double) * (n > 0 ? n : 1)));
+    if (!*out) PE_CUDA(cudaMalloc(out, sizeof(double) * (n > 0 ? n : 1)));
+    return 0;
+}
+
 extern "C" int pe_mat_upload(pe_ctx *ctx, const pe_parcsr_host *H, pe_mat **out)
 {
     PE_CHECK(ctx && H && out, "bad arguments");
@@ -745,8 +755,8 @@ extern "C" int pe_mat_upload(pe_ctx *ctx, const pe_parcsr_host *H, pe_mat **out)
         PE_CUDA(cudaMalloc(&M->send_map_d, sizeof(int32_t) * (size_t)(nsend > 0 ? nsend : 1)));
         PE_CUDA(cudaMemcpyAsync(M->send_map_d, M->send_map_elmts.data(), sizeof(int32_t) * (size_t)nsend,
                                 cudaMemcpyHostToDevice, ctx->stream));
-        PE_CUDA(cudaMalloc(&M->send_buf_d, sizeof(double) * (size_t)(nsend > 0 ? nsend : 1)));
-        PE_CUDA(cudaMalloc(&M->x_ext_d, sizeof(double) * (size_t)H->num_cols_offd));
+        PE_TRY(halo_buffer_alloc(ctx, (size_t)(nsend > 0 ? nsend : 1), &M->send_buf_d));
+        PE_TRY(halo_buffer_alloc(ctx, (size_t)H->num_cols_offd, &M->x_ext_d));
     } else if (H->num_sends > 0) {
         // a rank may own columns others need while having no ghosts itself
         M->send_procs.assign(H->send_procs, H->send_procs + H->num_sends);
@@ -756,7 +766,7 @@ extern "C" int pe_mat_upload(pe_ctx *ctx, const pe_parcsr_host *H, pe_mat **out)
         PE_CUDA(cudaMalloc(&M->send_map_d, sizeof(int32_t) * (size_t)(nsend > 0 ? nsend : 1)));
         PE_CUDA(cudaMemcpyAsync(M->send_map_d, M->send_map_elmts.data(), sizeof(int32_t) * (size_t)nsend,
                                 cudaMemcpyHostToDevice, ctx->stream));
-        PE_CUDA(cudaMalloc(&M->send_buf_d, sizeof(double) * (size_t)(nsend > 0 ? nsend : 1)));
+        PE_TRY(halo_buffer_alloc(ctx, (size_t)(nsend > 0 ? nsend : 1), &M->send_buf_d));
     }
     M->tpr = pe_choose_tpr(M->diag.nnz + M->offd.nnz, M->diag.nrows);
     M->distributed = ctx->nranks > 1 && (H->global_num_rows != H->num_rows || H->global_num_cols != H->num_cols_diag ||
@@ -821,11 +831,12 @@ extern "C" int pe_mat_free(pe_mat *A)
     if (!A) return 0;
     cudaStreamSynchronize(A->ctx->stream);
     cudaStreamSynchronize(A->ctx->comm_stream);
+    pe_p2p_unlink(A);
     devcsr_free(A->diag);
     devcsr_free(A->offd);
     if (A->send_map_d) cudaFree(A->send_map_d);
-    if (A->send_buf_d) cudaFree(A->send_buf_d);
-    if (A->x_ext_d) cudaFree(A->x_ext_d);
+    if (A->send_buf_d && !pe_p2p_owns(A->ctx, A->send_buf_d)) cudaFree(A->send_buf_d);   // arena blocks are not returned
+    if (A->x_ext_d && !pe_p2p_owns(A->ctx, A->x_ext_d)) cudaFree(A->x_ext_d);
     if (A->T) pe_mat_free(A->T);
     devcsr_free(A->offdT);
     if (A->unpack_rows_d) cudaFree(A->unpack_rows_d);
@@ -847,6 +858,15 @@ __global__ void k_pack(int n, const int32_t *__restrict__ map, const double *__r
     if (i < n) buf[i] = x[map[i]];
 }
 
+// peer-memory path (pe_p2p.cu): linked at the first exchange of a matrix outside graph capture -- a collective
+// step, like the exchange itself
+static int p2p_ready(pe_mat *A)
+{
+    pe_ctx *c = A->ctx;
+    if (A->p2p_state == 0 && c->p2p_base && !c->capturing) PE_TRY(pe_p2p_link(A));
+    return 0;
+}
+
 int pe_halo_exchange(pe_mat *A, const double *x_d)
 {
     pe_ctx *c = A->ctx;
@@ -854,6 +874,8 @@ int pe_halo_exchange(pe_mat *A, const double *x_d)
     int nsend = A->send_map_starts.empty() ? 0 : A->send_map_starts.back();
     int nrecv = A->recv_vec_starts.empty() ? 0 : A->recv_vec_starts.back();
     if (nsend == 0 && nrecv == 0) return 0;
+    PE_TRY(p2p_ready(A));
+    if (A->p2p_state == 1) return pe_p2p_push(A, 0, x_d);
     if (nsend > 0) {
         k_pack<<<pe_grid_for(nsend, 256), 256, 0, c->stream>>>(nsend, A->send_map_d, x_d, A->send_buf_d);
         PE_LAUNCHED(c);
@@ -880,6 +902,13 @@ int pe_halo_wait(pe_mat *A)
 {
     pe_ctx *c = A->ctx;
     if (c->nranks == 1) return 0;
+    if (A->p2p_state == 1)
+    {
+        const int nsend = A->send_map_starts.empty() ? 0 : A->send_map_starts.back();
+        const int nrecv = A->recv_vec_starts.empty() ? 0 : A->recv_vec_starts.back();
+        if (nsend == 0 && nrecv == 0) return 0;
+        return pe_p2p_wait(A, 0);
+    }
     PE_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
     return 0;
 }
@@ -893,6 +922,13 @@ int pe_reverse_halo_add(pe_mat *A, double alpha, double *y_d)
     int nsend = A->send_map_starts.empty() ? 0 : A->send_map_starts.back();
     int nrecv = A->recv_vec_starts.empty() ? 0 : A->recv_vec_starts.back();
     if (nsend == 0 && nrecv == 0) return 0;
+    PE_TRY(p2p_ready(A));
+    if (A->p2p_state == 1)
+    {
+        PE_TRY(pe_p2p_push(A, 1, A->x_ext_d));
+        PE_TRY(pe_p2p_wait(A, 1));
+        return pe_launch_unpack_add(c, A, alpha, y_d);
+    }
     PE_CUDA(cudaEventRecord(c->ev_pack, c->stream));
     PE_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
     PE_NCCL(g_nccl.GroupStart());

@@ -86,6 +86,10 @@ struct pe_ctx {
     pe_recorder *rec = nullptr;          // non-null while a program is being recorded
     double pending_bytes = 0.0;          // algorithmic bytes announced by the last pe_prof_begin
     const struct pe_host_comm *hcomm = nullptr;   // setup-time host communicator (borrowed)
+    // peer-visible halo arena (pe_p2p.cu): my block and every rank's block mapped through CUDA IPC
+    char *p2p_base = nullptr;
+    size_t p2p_size = 0, p2p_used = 0;
+    std::vector<char *> p2p_peer;
     // optional per-kernel CUDA-event profiling (bench.py roofline): id 0 SpMV, 1 GS set, 2 Jacobi
     bool prof = false;
     struct ProfRec { int id; double bytes; cudaEvent_t e0, e1; };
@@ -128,7 +132,9 @@ static inline cudaError_t pe_launch_k(pe_ctx *ctx, void (*kern)(KArgs...), int g
     cfg.dynamicSmemBytes = 0;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
-    if (ctx->nranks == 1 && pe_get_tuning(PE_TUNE_PDL) != 0)
+    // multi-rank: only when the halo exchange is made of ordinary kernels (peer-memory path); the NCCL path forks to
+    // a communication stream with events around its launches
+    if ((ctx->nranks == 1 || ctx->p2p_base) && pe_get_tuning(PE_TUNE_PDL) != 0)
     {
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -211,7 +217,18 @@ struct pe_mat {
     bool offdT_built = false, unpack_built = false;
     int n_unpack = 0;        // reverse exchange: distinct target rows, CSR of receive-buffer slots per row
     int *unpack_rows_d = nullptr, *unpack_I_d = nullptr, *unpack_pos_d = nullptr;
+    // peer-memory halo exchange (pe_p2p.cu): 0 = not linked yet, 1 = linked, -1 = NCCL path
+    int p2p_state = 0;
+    struct PeP2PDir *p2p[2] = {nullptr, nullptr};   // forward (ghost fill), reverse (MatvecT partial sums)
 };
+int pe_p2p_init(pe_ctx *ctx);
+void pe_p2p_shutdown(pe_ctx *ctx);
+void *pe_p2p_alloc(pe_ctx *ctx, size_t bytes);
+bool pe_p2p_owns(const pe_ctx *ctx, const void *p);
+int pe_p2p_link(pe_mat *A);
+void pe_p2p_unlink(pe_mat *A);
+int pe_p2p_push(pe_mat *A, int dir, const double *src);
+int pe_p2p_wait(pe_mat *A, int dir);
 int pe_rap_distributed(pe_ctx *ctx, const pe_mat *A, const pe_mat *P, pe_mat **Ac);
 int pe_spmv_t_distributed(pe_ctx *ctx, double alpha, pe_mat *A, const pe_vec *x, double beta, pe_vec *y);
 int pe_launch_unpack_add(pe_ctx *ctx, pe_mat *A, double alpha, double *y_d);

@@ -20,7 +20,7 @@ extern "C" int pe_ctx_set_host_comm(pe_ctx *ctx, const pe_host_comm *comm)
 {
     PE_CHECK(ctx, "null context");
     ctx->hcomm = comm;
-    return 0;
+    return pe_p2p_init(ctx);      // collective: maps the ranks' halo arenas into each other (NVLink peer memory)
 }
 
 // ---------------------------------------------------------------------------------------------

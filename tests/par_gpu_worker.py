@@ -105,9 +105,13 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     ids = [capi.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
+    halo = os.environ.get("PE_TEST_HALO", "p2p")
+    capi.set_tuning(capi.TUNE_P2P_HALO, 1 if halo == "p2p" else 0)
     ctx = api.session(rank, size, local, ids[0])
     comm = par.HostComm()
     api.set_host_comm(comm)
+    # the path under test is the one that runs: NVLink peer-memory halo (CUDA IPC arenas mapped) or NCCL send/recv
+    assert capi.lib().pe_ctx_p2p_enabled(ctx.h) == (1 if halo == "p2p" else 0), "halo path %s not active" % halo
 
     n, lev, form = 4, 3, 2
     procs = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[size]
@@ -214,7 +218,7 @@ def main():
     assert np.abs(xs2 - xo[mine2]).max() <= 1e-4 * np.abs(xo).max()
     dist.barrier()
     if rank == 0:
-        print("PAR_GPU_WORKER_OK ranks=%d PCG its (l1-Jacobi) %d, (hybrid l1-GS) %d" % (size, it, it2))
+        print("PAR_GPU_WORKER_OK halo=%s ranks=%d PCG its (l1-Jacobi) %d, (hybrid l1-GS) %d" % (halo, size, it, it2))
     dist.destroy_process_group()
 
 

@@ -17,11 +17,13 @@ def _ngpus():
         return 0
 
 
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_box_decomposed_hierarchy_matches_single_domain(nranks):
+def test_box_decomposed_hierarchy_matches_single_domain(nranks, halo):
+    """halo: ParCSR halo exchange over NVLink peer memory (pe_p2p.cu) or ncclSend/ncclRecv -- same checks"""
     if _ngpus() < nranks:
         pytest.skip("needs %d GPUs" % nranks)
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env = dict(os.environ, OMP_NUM_THREADS="1", PE_TEST_HALO=halo)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nranks, "--master-addr",
            "127.0.0.1", "--master-port", str(29540 + nranks), os.path.join(ROOT, "tests", "par_gpu_worker.py")]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
