@@ -859,7 +859,9 @@ __global__ void k_pack(int n, const int32_t *__restrict__ map, const double *__r
 }
 
 // peer-memory path (pe_p2p.cu): linked at the first exchange of a matrix outside graph capture -- a collective
-// step, like the exchange itself
+// step, like the exchange itself.  Only ranks that have a neighbour for this matrix get here (the others returned
+// above), and pe_p2p_link gathers over ALL ranks: as with hypre's comm packages on a connected partition, a matrix
+// either couples every rank to some neighbour or none (true for all level operators of a box decomposition).
 static int p2p_ready(pe_mat *A)
 {
     pe_ctx *c = A->ctx;

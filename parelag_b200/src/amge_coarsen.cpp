@@ -289,22 +289,44 @@ struct Coarsener
         const HostCSR &Dj = *fine.GetDerivativeOperator(j);
         b.Dj = csr_view(Dj);
         // coarse dofs on the boundary of every agglomerate, PV / NullSpace dofs of form j+1
-        std::vector<int> cbI(nAE + 1, 0), cbJ, pvc(nAE, -1), pnI(nAE + 1, 0), pnJ, tmp;
-        for (int a = 0; a < nAE; ++a)
+        // two passes (count, fill) over the agglomerates, both thread-parallel; the tables come out in agglomerate
+        // order whatever the thread count
+        std::vector<int> cbI(nAE + 1, 0), cbJ, pvc(nAE, -1), pnI(nAE + 1, 0), pnJ;
+        for (int small = ucd.GetMaxCodimensionBaseForDof(); small > cdom; --small) (void)C->topo->GetConnectivity(cdom, small);   // fill the cache serially
+        int bad_pv = -1, unsorted = -1;
+#pragma omp parallel
         {
-            ucd.GetDofsOnBdr(cdom, a, tmp);
-            PARELAG_ASSERT(std::is_sorted(tmp.begin(), tmp.end()));
-            cbJ.insert(cbJ.end(), tmp.begin(), tmp.end());
-            cbI[a + 1] = (int)cbJ.size();
-            if (facet)
+            std::vector<int> tmp;
+#pragma omp for schedule(static)
+            for (int a = 0; a < nAE; ++a)
             {
-                pcd.GetTypedInteriorDofs(cdom, a, DOF_RANGET, tmp);
-                PARELAG_TEST_FOR_EXCEPTION(tmp.size() != 1, std::runtime_error, "hFacetExtension: expected exactly one PV dof of form " << j + 1 << " per agglomerate");
-                pvc[a] = tmp[0];
+                ucd.GetDofsOnBdr(cdom, a, tmp);
+                if (!std::is_sorted(tmp.begin(), tmp.end())) unsorted = a;
+                cbI[a + 1] = (int)tmp.size();
+                if (facet)
+                {
+                    pcd.GetTypedInteriorDofs(cdom, a, DOF_RANGET, tmp);
+                    if (tmp.size() != 1) bad_pv = a; else pvc[a] = tmp[0];
+                }
+                pcd.GetTypedInteriorDofs(cdom, a, DOF_NULLSPACE, tmp);
+                pnI[a + 1] = (int)tmp.size();
             }
-            pcd.GetTypedInteriorDofs(cdom, a, DOF_NULLSPACE, tmp);
-            pnJ.insert(pnJ.end(), tmp.begin(), tmp.end());
-            pnI[a + 1] = (int)pnJ.size();
+        }
+        PARELAG_ASSERT(unsorted < 0);
+        PARELAG_TEST_FOR_EXCEPTION(bad_pv >= 0, std::runtime_error, "hFacetExtension: expected exactly one PV dof of form " << j + 1 << " per agglomerate");
+        for (int a = 0; a < nAE; ++a) { cbI[a + 1] += cbI[a]; pnI[a + 1] += pnI[a]; }
+        cbJ.resize((size_t)cbI[nAE]); pnJ.resize((size_t)pnI[nAE]);
+#pragma omp parallel
+        {
+            std::vector<int> tmp;
+#pragma omp for schedule(static)
+            for (int a = 0; a < nAE; ++a)
+            {
+                ucd.GetDofsOnBdr(cdom, a, tmp);
+                std::copy(tmp.begin(), tmp.end(), cbJ.begin() + cbI[a]);
+                pcd.GetTypedInteriorDofs(cdom, a, DOF_NULLSPACE, tmp);
+                std::copy(tmp.begin(), tmp.end(), pnJ.begin() + pnI[a]);
+            }
         }
         b.cbI = cbI.data(); b.cbJ = cbJ.data(); b.pvc = pvc.data(); b.pnI = pnI.data(); b.pnJ = pnJ.data();
         b.Pj = Ppool[j].view();

@@ -11,11 +11,21 @@
 namespace parelag
 {
 /// one dense (row-major) matrix per entity: the "DG-like" block-diagonal mass matrices M_[idx]
+/// allocator whose construct() default-initialises: resize() of a gigabyte pool does not zero-fill it serially
+/// before the (parallel) fill writes every entry anyway
+template <class T> struct default_init_allocator : std::allocator<T>
+{
+    template <class U> struct rebind { using other = default_init_allocator<U>; };
+    using std::allocator<T>::allocator;
+    template <class U> void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... Args> void construct(U *p, Args &&...args) { ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...); }
+};
+
 struct BlockPool
 {
     std::vector<int64_t> off{0};   // value offset of block e (size n+1)
     std::vector<int> size;         // order of block e
-    std::vector<double> vals;
+    std::vector<double, default_init_allocator<double>> vals;
     int n() const { return (int)size.size(); }
     double *add(int m)
     {

@@ -85,6 +85,52 @@ inline HostCSR Mult(const HostCSR &A, const HostCSR &B, double drop_tol = -1.0)
     }
     return C;
 }
+/// boolean product: pattern of A*B with unit values, rows sorted ascending (same threading scheme as Mult)
+inline HostCSR MultPattern(const HostCSR &A, const HostCSR &B)
+{
+    PARELAG_TEST_FOR_EXCEPTION(A.ncols != B.nrows, std::logic_error, "hostcsr::MultPattern: size mismatch");
+    HostCSR C;
+    C.nrows = A.nrows; C.ncols = B.ncols;
+    C.I.assign(A.nrows + 1, 0);
+    int nt = 1;
+#ifdef _OPENMP
+    nt = std::max(1, std::min(omp_get_max_threads(), A.nrows / 4096 + 1));
+#endif
+    std::vector<std::vector<int>> Jt(nt);
+    std::vector<int> r0(nt + 1, 0);
+    for (int t = 0; t <= nt; ++t) r0[t] = (int)((int64_t)A.nrows * t / nt);
+#pragma omp parallel num_threads(nt)
+    {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num();
+#else
+        const int t = 0;
+#endif
+        std::vector<int> marker(B.ncols, -1);
+        std::vector<int> &Jo = Jt[t];
+        for (int i = r0[t]; i < r0[t + 1]; ++i)
+        {
+            const size_t first = Jo.size();
+            for (int ka = A.I[i]; ka < A.I[i + 1]; ++ka)
+            {
+                const int k = A.J[ka];
+                for (int kb = B.I[k]; kb < B.I[k + 1]; ++kb)
+                {
+                    const int j = B.J[kb];
+                    if (marker[j] != i) { marker[j] = i; Jo.push_back(j); }
+                }
+            }
+            std::sort(Jo.begin() + first, Jo.end());
+            C.I[i + 1] = (int)(Jo.size() - first);
+        }
+    }
+    for (int i = 0; i < A.nrows; ++i) C.I[i + 1] += C.I[i];
+    C.J.resize((size_t)C.I[A.nrows]);
+    C.A.assign((size_t)C.I[A.nrows], 1.0);
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+    for (int t = 0; t < nt; ++t) std::copy(Jt[t].begin(), Jt[t].end(), C.J.begin() + C.I[r0[t]]);
+    return C;
+}
 inline HostCSR Transpose(const HostCSR &A)
 {
     HostCSR T;
@@ -246,9 +292,11 @@ public:
         auto key = std::make_pair(big, small);
         auto it = conn_.find(key);
         if (it != conn_.end()) return it->second;
-        HostCSR C = hostcsr::Abs(B_[big]);
-        for (int c = big + 1; c < small; ++c) C = hostcsr::Mult(C, hostcsr::Abs(B_[c]));
-        return conn_.emplace(key, hostcsr::Ones(std::move(C))).first->second;
+        // |B_big| ... |B_{small-1}| has no cancellations, so the table is the boolean product of the patterns;
+        // the chain reuses the cached (big, small-1) table
+        if (small == big + 1) return conn_.emplace(key, hostcsr::Ones(B_[big])).first->second;
+        const HostCSR &head = GetConnectivity(big, small - 1);
+        return conn_.emplace(key, hostcsr::MultPattern(head, B_[small - 1])).first->second;
     }
 
     /// CoarsenLocalPartitioning(partitioning, check_topology = false,

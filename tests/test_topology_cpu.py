@@ -13,7 +13,8 @@ def same(A, B):
             and np.array_equal(A.data, B.data))
 
 
-@pytest.mark.parametrize("dims,nlev", [((4, 4, 4), 3), ((4, 6, 2), 2), ((8, 4, 4), 3)])
+# the last case is large enough (> 4096 rows per table) for the row-parallel host SpGEMM to use several threads
+@pytest.mark.parametrize("dims,nlev", [((4, 4, 4), 3), ((4, 6, 2), 2), ((8, 4, 4), 3), ((24, 16, 16), 3)])
 def test_topology_hierarchy_bit_exact(dims, nlev):
     S = api.Sequence.hex(dims, nlev, svd_tol=-1.0)
     mesh = amge.HexMesh(*dims)
@@ -54,3 +55,17 @@ def test_fine_sequence_matrices_bit_exact():
         from oracle import drivers
         assert np.array_equal(S.get_bdr_mask(0, j), drivers.bdr_mask(seq.dof[j]))
     S.free()
+
+
+def test_host_tables_do_not_depend_on_the_thread_count():
+    """hostcsr::Mult / DofAgglomeration / pool fill run under OpenMP with per-thread buffers stitched in row
+    order: the bit-exact table tests above must also pass single-threaded and with more threads than cores."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for nt in ("1", "5"):
+        env = dict(os.environ, OMP_NUM_THREADS=nt)
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.join(root, "tests", "test_topology_cpu.py"),
+                            "-k", "bit_exact"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, "OMP_NUM_THREADS=%s\n%s" % (nt, r.stdout[-2000:])
