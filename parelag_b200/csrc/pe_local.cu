@@ -685,8 +685,6 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 // per-codimension batched calls, keyed by host address and size.  At 144^3 hexahedra the 24 extension
 // calls of the first level re-sent 31 GB without it.
 static bool g_cache_on = false;
-struct RowPoolMirror { int *J = nullptr; double *A = nullptr; size_t cap = 0, filled = 0; };
-static std::map<const void *, RowPoolMirror> g_rowpools;   // see up_rowpool
 static std::map<std::pair<const void *, size_t>, void *> g_cache;
 struct DevBuf
 {
@@ -738,8 +736,6 @@ extern "C" int pe_local_cache(pe_ctx *ctx, int enable)
         PE_CUDA(cudaStreamSynchronize(ctx->stream));
         for (auto &kv : g_cache) cudaFree(kv.second);
         g_cache.clear();
-        for (auto &kv : g_rowpools) { if (kv.second.J) cudaFree(kv.second.J); if (kv.second.A) cudaFree(kv.second.A); }
-        g_rowpools.clear();
     }
     g_cache_on = enable != 0;
     return 0;
@@ -814,47 +810,15 @@ static int up_csr(DevBuf &D, const pe_csr_view &h, CsrV &d, bool constant = fals
     PE_TRY(D.up(h.A, nnz, &d.A));
     return 0;
 }
-// Row pools (P_j, coarse D_j under construction) are append-only on the host: rows are written once and their
-// entries land at the end of J/A.  Inside a cache scope the device keeps the pool and every call uploads only the
-// entries appended since the previous one (plus the row start/len tables).  Keyed by the address of the `start`
-// table, which never moves while the pool lives (J/A do, as they grow).
+// Row pools (P_j, coarse D_j under construction) change between calls and are sent every time.  (An incremental
+// device mirror that uploaded only the appended entries was measured and removed: when the extension of form j runs,
+// P_j holds only the trace rows, so the pools are a small part of the 17 GB the level uploads.)
 static int up_rowpool(DevBuf &D, const pe_rowpool_view &h, RowPoolV &d)
 {
     PE_TRY(D.up(h.start, (size_t)h.nrows, (const long long **)&d.start));
     PE_TRY(D.up(h.len, (size_t)h.nrows, &d.len));
-    const size_t n = (size_t)h.pool_size;
-    if (!g_cache_on || !h.start || h.nrows == 0)
-    {
-        PE_TRY(D.up(h.J, n, &d.J));
-        PE_TRY(D.up(h.A, n, &d.A));
-        return 0;
-    }
-    RowPoolMirror &m = g_rowpools[(const void *)h.start];
-    if (m.filled > n) m.filled = 0;                              // not the pool we mirrored: start over
-    if (n > m.cap)
-    {
-        const size_t cap = std::max<size_t>(n + n / 2, 1 << 16);
-        int *J = nullptr; double *A = nullptr;
-        PE_CUDA(cudaMalloc(&J, sizeof(int) * cap));
-        PE_CUDA(cudaMalloc(&A, sizeof(double) * cap));
-        if (m.filled > 0)
-        {
-            PE_CUDA(cudaMemcpyAsync(J, m.J, sizeof(int) * m.filled, cudaMemcpyDeviceToDevice, D.st));
-            PE_CUDA(cudaMemcpyAsync(A, m.A, sizeof(double) * m.filled, cudaMemcpyDeviceToDevice, D.st));
-            PE_CUDA(cudaStreamSynchronize(D.st));
-        }
-        if (m.J) cudaFree(m.J);
-        if (m.A) cudaFree(m.A);
-        m.J = J; m.A = A; m.cap = cap;
-    }
-    if (n > m.filled)
-    {
-        PE_CUDA(cudaMemcpyAsync(m.J + m.filled, h.J + m.filled, sizeof(int) * (n - m.filled), cudaMemcpyHostToDevice, D.st));
-        PE_CUDA(cudaMemcpyAsync(m.A + m.filled, h.A + m.filled, sizeof(double) * (n - m.filled), cudaMemcpyHostToDevice, D.st));
-        g_stage[3] += 12.0 * (double)(n - m.filled);
-        m.filled = n;
-    }
-    d.J = m.J; d.A = m.A;
+    PE_TRY(D.up(h.J, (size_t)h.pool_size, &d.J));
+    PE_TRY(D.up(h.A, (size_t)h.pool_size, &d.A));
     return 0;
 }
 
