@@ -1203,3 +1203,47 @@ def upscaling_errors(form, nref=1, base=(2, 2, 2)):
     dd = Ds[0] @ diff
     e_en = float(np.sqrt(dd @ (Ws[0] @ dd)))
     return e_l2, e_en, seqs
+
+
+def upscaling_form2_amge(nref=2, base=(2, 2, 2)):
+    """examples/Upscaling2FormAMGe.cpp:44-48,86-145,225-296,307-444 with --meshfile none (the structured
+    2x2x2-hexahedra cube, nref parallel refinements, nref+1 levels): H(div) problem A = M_2 + D_2^T W D_2,
+    all boundary attributes essential with zero data, right-hand side (f, v) with f = e_z
+    (VectorFEDomainLFIntegrator) restricted level by level with P^T; every level is solved and the errors
+    ||P..P u_H - u_h||_M and ||D(P..P u_H - u_h)||_W against the fine solution are reported for the
+    coarsest level first (UpscalingPieces.cpp:143-166).  Returns [(u_err, du_err) coarsest, ..., level 1]."""
+    import scipy.sparse.linalg as spl
+    dims = tuple(b * 2 ** nref for b in base)
+    mesh, seqs = build_hierarchy(dims, nref + 1)
+    ess = np.ones(6, dtype=int)
+    nx, ny, nz = dims
+    hz = mesh.h[2]
+    form = 2
+    f = seqs[0]
+    # RT0 basis of a z-face has unit normal flux: (e_z, phi) = hz/2 per adjacent element
+    b = np.zeros(f.dof[form].ndofs)
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz + 1), indexing="ij")
+    adjacent = np.where((k == 0) | (k == nz), 1.0, 2.0)
+    b[mesh.fz(i.ravel(), j.ravel(), k.ravel())] = (hz / 2.0) * adjacent.ravel()
+    sols, rhs = [], b
+    for lev, s in enumerate(seqs):
+        M, W, D = s.mass_operator(form), s.mass_operator(form + 1), s.D[form]
+        A = _canon(M + D.T @ W @ D)
+        marker = s.dof[form].mark_bdr_dofs(ess)
+        keep = sp.diags((~marker).astype(float))
+        A = keep @ A @ keep + sp.diags(marker.astype(float))
+        r = rhs.copy()
+        r[marker] = 0.0
+        sols.append(spl.spsolve(A.tocsc(), r))
+        if lev + 1 < len(seqs):
+            rhs = s.P[form].T @ rhs
+    M0, W0, D0 = f.mass_operator(form), f.mass_operator(form + 1), f.D[form]
+    out = []
+    for lev in range(len(seqs) - 1, 0, -1):
+        u = sols[lev]
+        for q in range(lev - 1, -1, -1):
+            u = seqs[q].P[form] @ u
+        d = u - sols[0]
+        dd = D0 @ d
+        out.append((float(np.sqrt(d @ (M0 @ d))), float(np.sqrt(dd @ (W0 @ dd)))))
+    return out
