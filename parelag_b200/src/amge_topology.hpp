@@ -228,27 +228,44 @@ inline HostCSR findMinimalIntersectionSets(const HostCSR &Z, double skipDiagEntr
 inline HostCSR MinimalIntersectionSetsFromMembership(const HostCSR &memb)
 {
     const int n = memb.nrows;
-    std::unordered_map<std::string, int> ids;
-    ids.reserve((size_t)n);
     std::vector<int> mis_of(n, -1);
     std::vector<double> sign_of(n, 0.0);
-    std::string key;
+    // open-addressing table of MIS ids keyed by the (agglomerate, relative sign) signature; a slot is verified against
+    // the signature of the set's first entity, so hash collisions cannot merge sets
+    size_t cap = 16;
+    while (cap < (size_t)n * 2) cap <<= 1;
+    std::vector<int> table(cap, -1), first_entity;
+    first_entity.reserve((size_t)n / 4 + 16);
+    auto relsign = [&](int k, double s0) { return ((memb.A[k] > 0 ? 1.0 : -1.0) * s0 > 0) ? 1u : 0u; };
     int current = 0;
     for (int i = 0; i < n; ++i)
     {
         const int lo = memb.I[i], hi = memb.I[i + 1];
         if (hi == lo) continue;                       // diag(Z) < 0.5: belongs to no MIS
         const double s0 = memb.A[lo] > 0 ? 1.0 : -1.0;
-        key.clear();
+        uint64_t h = 0x9e3779b97f4a7c15ull ^ (uint64_t)(hi - lo);
         for (int k = lo; k < hi; ++k)
         {
-            const int a = memb.J[k];
-            key.append(reinterpret_cast<const char *>(&a), sizeof(int));
-            key.push_back((memb.A[k] > 0 ? 1.0 : -1.0) * s0 > 0 ? '+' : '-');
+            h ^= ((uint64_t)(uint32_t)memb.J[k] << 1) | relsign(k, s0);
+            h *= 0xff51afd7ed558ccdull;
+            h ^= h >> 33;
         }
-        auto it = ids.find(key);
-        if (it == ids.end()) { it = ids.emplace(key, current++).first; }
-        mis_of[i] = it->second;
+        size_t slot = (size_t)h & (cap - 1);
+        int id = -1;
+        for (;; slot = (slot + 1) & (cap - 1))
+        {
+            const int cand = table[slot];
+            if (cand < 0) break;
+            const int f = first_entity[cand], flo = memb.I[f], fhi = memb.I[f + 1];
+            if (fhi - flo != hi - lo) continue;
+            const double f0 = memb.A[flo] > 0 ? 1.0 : -1.0;
+            bool same = true;
+            for (int k = 0; k < hi - lo && same; ++k)
+                same = memb.J[lo + k] == memb.J[flo + k] && relsign(lo + k, s0) == relsign(flo + k, f0);
+            if (same) { id = cand; break; }
+        }
+        if (id < 0) { id = current++; table[slot] = id; first_entity.push_back(i); }
+        mis_of[i] = id;
         sign_of[i] = s0;      // orientation relative to the first entity of the set (whose s0-normalised pattern is all '+' ... )
     }
     // orientation of entity i relative to the first entity f of its set: Z_fi / Z_ff = s0(i) * s0(f)
