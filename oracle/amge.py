@@ -300,6 +300,95 @@ class HexMesh:
         return np.stack([i * self.h[0], j * self.h[1], k * self.h[2]], axis=1)
 
 
+class DeformedHexMesh(HexMesh):
+    """HexMesh whose vertices have been moved: every cell is a trilinear hexahedron (mfem's isoparametric Q1 map).
+    Numbering, orientation and boundary attributes are those of the index grid.  This is the geometry of
+    examples/3DHdivWeakScaling.cpp:148-158 (uniformly refined unit cube, then y += exp(z)/2, x += sin(y)).
+    Provides what the lowest-order H(div)-L2 part of DeRhamSequence3D_FE needs (DeRhamSequenceFE.cpp:633-684):
+    cell volumes (MassIntegrator, P0), RT0 element mass matrices (VectorFEMassIntegrator: contravariant Piola map,
+    Gauss rule of order OrderW + 2 = 4, i.e. 3 points per direction), the facet weight |N| at the facet centre
+    (VolumetricFEMassIntegrator on the RT trace element, one-point rule; InterpolatePV_HdivTraces, :810-857)
+    and the normal N itself (RT_HexahedronElement::Project of a constant field)."""
+
+    def __init__(self, nx, ny, nz, deform, L=(1.0, 1.0, 1.0)):
+        super().__init__(nx, ny, nz, L=L)
+        self.X = np.asarray(deform(HexMesh.vertex_coords(self)), dtype=np.float64)
+
+    def vertex_coords(self):
+        return self.X
+
+    @staticmethod
+    def _gauss(n):
+        x, w = np.polynomial.legendre.leggauss(n)
+        return 0.5 * (x + 1.0), 0.5 * w
+
+    def _corner(self, a, b, c):
+        nx, ny, nz = self.dims
+        i, j, k = self._grid(nx, ny, nz)
+        return self.X[self.vx(i + a, j + b, k + c)]
+
+    def jacobian_columns(self, xh, yh, zh):
+        """dr/dxh, dr/dyh, dr/dzh of the trilinear map at one reference point, for all cells: three (nel, 3) arrays"""
+        sx, sy, sz, d = (1 - xh, xh), (1 - yh, yh), (1 - zh, zh), (-1.0, 1.0)
+        abc = [(a, b, c) for a in (0, 1) for b in (0, 1) for c in (0, 1)]
+        rx = sum(self._corner(a, b, c) * (d[a] * sy[b] * sz[c]) for a, b, c in abc)
+        ry = sum(self._corner(a, b, c) * (sx[a] * d[b] * sz[c]) for a, b, c in abc)
+        rz = sum(self._corner(a, b, c) * (sx[a] * sy[b] * d[c]) for a, b, c in abc)
+        return rx, ry, rz
+
+    def cell_volumes(self):
+        g, w = self._gauss(2)                      # det J is quadratic per variable: exact
+        v = np.zeros(self.nel)
+        for a, wa in zip(g, w):
+            for b, wb in zip(g, w):
+                for c, wc in zip(g, w):
+                    rx, ry, rz = self.jacobian_columns(a, b, c)
+                    v += wa * wb * wc * np.einsum("ei,ei->e", rx, np.cross(ry, rz))
+        return v
+
+    def rt0_element_mass(self, npts=3):
+        """(nel, 6, 6), local order x-,x+,y-,y+,z-,z+, every basis function with unit flux along the +index axis:
+        v = J vhat / det J, vhat_{x-} = (1-xh, 0, 0), vhat_{x+} = (xh, 0, 0), ..."""
+        g, w = self._gauss(npts)
+        M = np.zeros((self.nel, 6, 6))
+        for a, wa in zip(g, w):
+            for b, wb in zip(g, w):
+                for c, wc in zip(g, w):
+                    rx, ry, rz = self.jacobian_columns(a, b, c)
+                    det = np.einsum("ei,ei->e", rx, np.cross(ry, rz))
+                    V = [rx * (1 - a), rx * a, ry * (1 - b), ry * b, rz * (1 - c), rz * c]
+                    for p in range(6):
+                        for q in range(6):
+                            M[:, p, q] += (wa * wb * wc) * np.einsum("ei,ei->e", V[p], V[q]) / det
+        return M
+
+    def facet_normals(self):
+        """dr/du x dr/dv at the centre of every facet, oriented along the +index axis (nf_total, 3)"""
+        nx, ny, nz = self.dims
+        X = self.X
+
+        def mean_tangents(c):
+            t1 = 0.5 * ((c(1, 0) - c(0, 0)) + (c(1, 1) - c(0, 1)))
+            t2 = 0.5 * ((c(0, 1) - c(0, 0)) + (c(1, 1) - c(1, 0)))
+            return t1, t2
+        i, j, k = self._grid(nx + 1, ny, nz)
+        ty, tz = mean_tangents(lambda b, c: X[self.vx(i, j + b, k + c)])
+        Nx = np.cross(ty, tz)
+        i, j, k = self._grid(nx, ny + 1, nz)
+        tx, tz = mean_tangents(lambda a, c: X[self.vx(i + a, j, k + c)])
+        Ny = np.cross(tz, tx)
+        i, j, k = self._grid(nx, ny, nz + 1)
+        tx, ty = mean_tangents(lambda a, b: X[self.vx(i + a, j + b, k)])
+        Nz = np.cross(tx, ty)
+        return np.concatenate([Nx, Ny, Nz], axis=0)
+
+    def facet_area(self):
+        return np.linalg.norm(self.facet_normals(), axis=1)
+
+    def ridge_length(self):
+        raise NotImplementedError("deformed meshes carry the H(div)-L2 part of the sequence only (jstart = 2)")
+
+
 class DofHandler:
     """Common part of DofHandlerFE / DofHandlerALG: entity_dof[c] for c <= max_codim_base."""
 
@@ -1029,6 +1118,8 @@ def fine_sequence(mesh, topo=None, upscaling_order=0, alpha=None, beta=None, jst
     (SetUpscalingTargets).  alpha / beta: optional per-element weights of the L2 and
     H(div) element mass matrices (ReplaceMassIntegrator in the drivers)."""
     topo = topo or mesh.topology()
+    if isinstance(mesh, DeformedHexMesh):
+        return _fine_sequence_deformed(mesh, topo, alpha, beta, jstart)
     seq = Sequence(topo, 4)
     seq.mesh = mesh
     seq.jstart = jstart
@@ -1114,10 +1205,38 @@ def fine_sequence(mesh, topo=None, upscaling_order=0, alpha=None, beta=None, jst
     return seq
 
 
-def build_hierarchy(dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9):
+def _fine_sequence_deformed(mesh, topo, alpha, beta, jstart):
+    """H(div)-L2 part of DeRhamSequence3D_FE on trilinear hexahedra (forms 2 and 3; jformStart = 2)."""
+    assert jstart >= 2, "deformed meshes: forms 2 and 3 only"
+    seq = Sequence(topo, 4)
+    seq.mesh = mesh
+    seq.jstart = jstart
+    for j in range(4):
+        dh = DofHandler(3 - j, topo)
+        dh.ndofs = topo.n[3 - j]
+        for c in range(3 - j + 1):
+            dh.entity_dof[c] = sp.identity(topo.n[c], format="csr") if c == 3 - j else topo.conn(c, 3 - j)
+        seq.dof[j] = dh
+    vol = mesh.cell_volumes()
+    a_el = np.ones(mesh.nel) if alpha is None else np.asarray(alpha, dtype=np.float64)
+    b_el = np.ones(mesh.nel) if beta is None else np.asarray(beta, dtype=np.float64)
+    # DivergenceInterpolator2 (bilinIntegrators.hpp:272-290): L2 projection of the divergence = net flux / volume
+    seq.D = [topo.B[2].copy(), topo.B[1].copy(), _canon(sp.diags(1.0 / vol) @ topo.B[0])]
+    seq.M[(3, 0)] = sp.diags(vol * a_el).tocsr()
+    seq.M[(2, 0)] = sp.block_diag(list(mesh.rt0_element_mass() * b_el[:, None, None]), format="csr")
+    N = mesh.facet_normals()
+    seq.M[(2, 1)] = sp.diags(1.0 / np.linalg.norm(N, axis=1)).tocsr()
+    seq.l2_const = np.ones(mesh.nel)
+    seq.targets[3] = np.ones((mesh.nel, 1))
+    seq.targets[2] = N.copy()            # fluxes of e_x, e_y, e_z
+    return seq
+
+
+def build_hierarchy(dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9, deform=None):
     """Drivers' steps 3-4 (examples/MultigridTest2Form.cpp:248-375): agglomerate the
-    topology nlevels-1 times by derefinement, then Coarsen() level by level."""
-    mesh = HexMesh(*dims, L=L)
+    topology nlevels-1 times by derefinement, then Coarsen() level by level.  deform: optional map of the
+    (nv, 3) vertex coordinates (trilinear hexahedra; needs jstart >= 2)."""
+    mesh = HexMesh(*dims, L=L) if deform is None else DeformedHexMesh(*dims, deform=deform, L=L)
     topos = [mesh.topology()]
     d = dims
     for _ in range(nlevels - 1):
@@ -1243,6 +1362,53 @@ def upscaling_form2_amge(nref=2, base=(2, 2, 2)):
         u = sols[lev]
         for q in range(lev - 1, -1, -1):
             u = seqs[q].P[form] @ u
+        d = u - sols[0]
+        dd = D0 @ d
+        out.append((float(np.sqrt(d @ (M0 @ d))), float(np.sqrt(dd @ (W0 @ dd)))))
+    return out
+
+
+def weak_scaling_deformation(X):
+    """examples/3DHdivWeakScaling.cpp:148-158: y += exp(z)/2, then x += sin(y)"""
+    X = np.array(X, dtype=np.float64)
+    X[:, 1] += 0.5 * np.exp(X[:, 2])
+    X[:, 0] += np.sin(X[:, 1])
+    return X
+
+
+def hdiv_weak_scaling_errors(nref=2, base=(1, 1, 1)):
+    """examples/3DHdivWeakScaling.cpp on one rank (--nref_parallel nref): the unit cube of base cells refined nref
+    times, deformed (weak_scaling_deformation), nref+1 levels; H(div) problem A = M_2 + D_2^T W D_2 with
+    essential (zero) data on attributes 2-5, natural data -1 on attribute 1 (z = 0), 0 on attribute 6
+    (:53-66,175-180,240-245); every level is solved and the errors against the fine solution are reported,
+    coarsest level first (UpscalingPieces.cpp:143-166).  Returns [(u_err, du_err), ...]."""
+    import scipy.sparse.linalg as spl
+    dims = tuple(b * 2 ** nref for b in base)
+    mesh, seqs = build_hierarchy(dims, nref + 1, jstart=2, deform=weak_scaling_deformation)
+    ess = np.array([0, 1, 1, 1, 1, 0])
+    nx, ny, nz = dims
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    b = np.zeros(seqs[0].dof[2].ndofs)
+    b[mesh.fz(i.ravel(), j.ravel(), 0)] = 1.0           # (f, v.n), f = -1, outward normal -z, dof oriented +z
+    sols, rhs = [], b
+    for lev, s in enumerate(seqs):
+        M, W, D = s.mass_operator(2), s.mass_operator(3), s.D[2]
+        A = _canon(M + D.T @ W @ D)
+        marker = s.dof[2].mark_bdr_dofs(ess)
+        keep = sp.diags((~marker).astype(float))
+        A = keep @ A @ keep + sp.diags(marker.astype(float))
+        r = rhs.copy()
+        r[marker] = 0.0
+        sols.append(spl.spsolve(A.tocsc(), r))
+        if lev + 1 < len(seqs):
+            rhs = s.P[2].T @ rhs
+    f = seqs[0]
+    M0, W0, D0 = f.mass_operator(2), f.mass_operator(3), f.D[2]
+    out = []
+    for lev in range(len(seqs) - 1, 0, -1):
+        u = sols[lev]
+        for q in range(lev - 1, -1, -1):
+            u = seqs[q].P[2] @ u
         d = u - sols[0]
         dd = D0 @ d
         out.append((float(np.sqrt(d @ (M0 @ d))), float(np.sqrt(dd @ (W0 @ dd)))))
