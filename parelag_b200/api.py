@@ -58,12 +58,18 @@ class Sequence:
         _chk(lib().pe_api_sequence_set_bdr_mask(self.h, level, form, len(mask), _ptr(mask)))
 
     @staticmethod
-    def hex(dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9):
-        """Full coarsening path on a structured hex mesh (svd_tol < 0: topology only)."""
+    def hex(dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9, coords=None):
+        """Full coarsening path on a structured hex mesh (svd_tol < 0: topology only).  coords: optional (nv, 3)
+        moved vertices (trilinear hexahedra, index-grid numbering; needs jstart >= 2)."""
         S = Sequence.__new__(Sequence)
         S.h = C.c_void_p()
         a = None if alpha is None else _f64(alpha)
         b = None if beta is None else _f64(beta)
+        if coords is not None:
+            X = _f64(np.ascontiguousarray(coords).ravel())
+            _chk(lib().pe_api_hexsequence_create_deformed(dims[0], dims[1], dims[2], _ptr(X), _ptr(a), _ptr(b), jstart, nlevels,
+                                                          C.c_double(svd_tol), C.byref(S.h)))
+            return S
         _chk(lib().pe_api_hexsequence_create(dims[0], dims[1], dims[2], C.c_double(L[0]), C.c_double(L[1]),
                                              C.c_double(L[2]), _ptr(a), _ptr(b), jstart, nlevels,
                                              C.c_double(svd_tol), C.byref(S.h)))

@@ -496,9 +496,9 @@ HostCSR DeRhamSequence::ComputeMassOperator(int jform) const
 
 std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchy(int nx, int ny, int nz, double Lx, double Ly, double Lz,
                                                                         const double *alpha, const double *beta, int jstart,
-                                                                        int nlevels, double svd_tol)
+                                                                        int nlevels, double svd_tol, const double *vertex_coords)
 {
-    return BuildHexSequenceHierarchyPar(nullptr, nullptr, nx, ny, nz, Lx, Ly, Lz, alpha, beta, jstart, nlevels, svd_tol);
+    return BuildHexSequenceHierarchyPar(nullptr, nullptr, nx, ny, nz, Lx, Ly, Lz, alpha, beta, jstart, nlevels, svd_tol, vertex_coords);
 }
 
 /// Host memory for the setup phase.  Building a hierarchy allocates (and re-allocates while vectors grow)
@@ -554,7 +554,8 @@ void ReleaseHostArena()
 
 std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const pe_host_comm *comm, const int *procs, int nx, int ny, int nz,
                                                                            double Lx, double Ly, double Lz, const double *alpha,
-                                                                           const double *beta, int jstart, int nlevels, double svd_tol)
+                                                                           const double *beta, int jstart, int nlevels, double svd_tol,
+                                                                           const double *vertex_coords)
 {
     const bool parallel = comm && comm->size > 1;
     const int one[3] = {1, 1, 1};
@@ -576,6 +577,11 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
                                "BuildHexSequenceHierarchyPar: the process grid does not match the communicator size");
     // Lx, Ly, Lz: extent of THIS rank's box (every box has the same shape)
     StructuredHexMesh mesh(nx, ny, nz, Lx, Ly, Lz);
+    if (vertex_coords)
+    {
+        PARELAG_TEST_FOR_EXCEPTION(parallel, std::runtime_error, "moved vertices are supported on a single rank");
+        mesh.coords.assign(vertex_coords, vertex_coords + (size_t)3 * mesh.nv());
+    }
     if (parallel)
     {
         for (int a = 0; a < 3; ++a) for (int sd = 0; sd < 2; ++sd) mesh.iface[2 * a + sd] = box.interface(a, sd);

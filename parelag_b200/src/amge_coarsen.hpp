@@ -8,14 +8,16 @@ namespace parelag
 /// mesh: fine topology, nlevels-1 derefinement agglomerations
 /// (MFEMRefinedMeshPartitioner + CoarsenLocalPartitioning), fine DeRhamSequence with the
 /// order-0 upscaling targets, then Coarsen() level by level.  Timers use the reference's names.
+/// vertex_coords (nv x 3, optional, single rank): moved vertices -> trilinear hexahedra (needs jstart >= 2).
 std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchy(int nx, int ny, int nz, double Lx, double Ly, double Lz,
                                                                         const double *alpha, const double *beta, int jstart,
-                                                                        int nlevels, double svd_tol);
+                                                                        int nlevels, double svd_tol, const double *vertex_coords = nullptr);
 /// The same on one box of a P[0] x P[1] x P[2] box decomposition (one rank <-> one box <-> one GPU,
 /// the reference's one-MPI-rank-per-partition model): nx, ny, nz and Lx, Ly, Lz describe THIS
 /// rank's box; every rank coarsens its own box (elements never migrate) and the levels are glued
 /// by the dof <-> true-dof SharingMaps built at the end (amge_par.hpp).  comm == NULL: serial.
 std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const pe_host_comm *comm, const int *procs, int nx, int ny, int nz,
                                                                            double Lx, double Ly, double Lz, const double *alpha,
-                                                                           const double *beta, int jstart, int nlevels, double svd_tol);
+                                                                           const double *beta, int jstart, int nlevels, double svd_tol,
+                                                                           const double *vertex_coords = nullptr);
 } // namespace parelag

@@ -8,6 +8,8 @@
 // then y-, then z-normal; ridges: x-, y-, z-edges; peaks: vertices.  Every facet / ridge
 // is oriented along its positive axis.  Boundary attributes as mfem::Mesh::Make3D
 // (z=0:1, y=0:2, x=L:3, y=L:4, x=0:5, z=L:6).  Same conventions as oracle/amge.py.
+// Optional vertex coordinates turn the cells into trilinear hexahedra (examples/3DHdivWeakScaling.cpp:148-158);
+// the H(div)-L2 part of the sequence (forms 2 and 3) is then built by quadrature, see BuildFineHexSequenceDeformed.
 #pragma once
 #include "amge_dofs.hpp"
 
@@ -23,6 +25,9 @@ struct StructuredHexMesh
     /// x0/y0/z0: origin of the box
     bool iface[6] = {false, false, false, false, false, false};
     double x0 = 0.0, y0 = 0.0, z0 = 0.0;
+    /// optional: moved vertices (nv x 3, row-major, index-grid numbering) -> trilinear hexahedra
+    std::vector<double> coords;
+    bool deformed() const { return !coords.empty(); }
     StructuredHexMesh(int nx_, int ny_, int nz_, double Lx = 1.0, double Ly = 1.0, double Lz = 1.0)
         : nx(nx_), ny(ny_), nz(nz_), hx(Lx / nx_), hy(Ly / ny_), hz(Lz / nz_) {}
     bool any_interface() const { for (bool b : iface) if (b) return true; return false; }
@@ -129,12 +134,139 @@ inline void fill_pool(BlockPool &P, int count, const double *blk, int m, const d
 }
 } // namespace hexfe
 
+/// H(div)-L2 part (forms 2, 3) of DeRhamSequence3D_FE at lowest order on trilinear hexahedra
+/// (DeRhamSequenceFE.cpp:633-684).  Per cell: volume (MassIntegrator on P0: 2-point Gauss rule, exact), RT0 mass
+/// matrix (VectorFEMassIntegrator, contravariant Piola map v = J vhat / det J, Gauss rule of order OrderW + 2 = 4:
+/// 3 points per direction), D_2 = net flux / volume (DivergenceInterpolator2, bilinIntegrators.hpp:272-290).
+/// Per facet: N = dr/du x dr/dv at the centre, oriented along the +index axis; trace mass 1/|N|
+/// (VolumetricFEMassIntegrator, one-point rule), PV-trace weight |N| (InterpolatePV_HdivTraces,
+/// DeRhamSequenceFE.cpp:810-857), targets = fluxes N.e_c of the constant fields (RT_HexahedronElement::Project).
+/// Local dof order of a cell: x-, x+, y-, y+, z-, z+ (ascending facet id), every basis function with unit flux
+/// along the +index axis.  Same arithmetic as oracle/amge.py:DeformedHexMesh.
+inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const std::shared_ptr<AgglomeratedTopology> &topo,
+                                         const double *alpha, const double *beta, int jstart, SequenceData &S, std::vector<HostCSR> &D)
+{
+    PARELAG_TEST_FOR_EXCEPTION(jstart < 2, std::runtime_error,
+                               "deformed hexahedral meshes carry the H(div)-L2 part of the sequence only: use jformStart >= 2");
+    PARELAG_TEST_FOR_EXCEPTION((int64_t)mesh.coords.size() != (int64_t)3 * mesh.nv(), std::runtime_error,
+                               "vertex coordinates: expected nv x 3 values");
+    using hexfe::fill_pool;
+    const int nel = (int)mesh.nel(), nf = mesh.nf();
+    S.topo = topo; S.nforms = 4; S.jstart = jstart; S.is_fe = true;
+    S.dof.resize(4);
+    for (int j = 0; j < 4; ++j)
+    {
+        auto dh = std::make_shared<DofHandlerX>(3 - j, topo);
+        dh->ndofs = topo->GetNumberLocalEntities(3 - j);
+        for (int c = 0; c <= 3 - j; ++c)
+            dh->entity_dof[c] = (c == 3 - j) ? hostcsr::Identity(topo->GetNumberLocalEntities(c)) : topo->GetConnectivity(c, 3 - j);
+        dh->ComputeBoundaryMask();
+        S.dof[j] = dh;
+    }
+    const double *X = mesh.coords.data();
+    auto vtx = [&](int i, int j, int k) { return X + (size_t)3 * mesh.vx(i, j, k); };
+    const double s35 = std::sqrt(0.6), s13 = 1.0 / std::sqrt(3.0);
+    const double g3[3] = {0.5 * (1.0 - s35), 0.5, 0.5 * (1.0 + s35)}, w3[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+    const double g2[2] = {0.5 * (1.0 - s13), 0.5 * (1.0 + s13)}, w2[2] = {0.5, 0.5};
+    std::vector<double> vol(nel, 0.0);
+    BlockPool &M30 = S.M[{3, 0}], &M20 = S.M[{2, 0}], &M21 = S.M[{2, 1}];
+    {
+        double one = 1.0;
+        fill_pool(M30, nel, &one, 1);
+        double zero36[36] = {0};
+        fill_pool(M20, nel, zero36, 6);
+        fill_pool(M21, nf, &one, 1);
+    }
+    double *m30 = M30.vals.data(), *m20 = M20.vals.data(), *m21 = M21.vals.data();
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < nel; ++e)
+    {
+        const int i = e % mesh.nx, j = (e / mesh.nx) % mesh.ny, k = e / (mesh.nx * mesh.ny);
+        const double *c[2][2][2];
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int cc = 0; cc < 2; ++cc) c[a][b][cc] = vtx(i + a, j + b, k + cc);
+        auto jac = [&](double xh, double yh, double zh, double *rx, double *ry, double *rz) {
+            const double sx[2] = {1 - xh, xh}, sy[2] = {1 - yh, yh}, sz[2] = {1 - zh, zh}, d[2] = {-1.0, 1.0};
+            for (int t = 0; t < 3; ++t) rx[t] = ry[t] = rz[t] = 0.0;
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int cc = 0; cc < 2; ++cc)
+                for (int t = 0; t < 3; ++t)
+                {
+                    const double x = c[a][b][cc][t];
+                    rx[t] += x * (d[a] * sy[b] * sz[cc]);
+                    ry[t] += x * (sx[a] * d[b] * sz[cc]);
+                    rz[t] += x * (sx[a] * sy[b] * d[cc]);
+                }
+        };
+        auto det3 = [](const double *rx, const double *ry, const double *rz) {
+            return rx[0] * (ry[1] * rz[2] - ry[2] * rz[1]) + rx[1] * (ry[2] * rz[0] - ry[0] * rz[2]) + rx[2] * (ry[0] * rz[1] - ry[1] * rz[0]);
+        };
+        double rx[3], ry[3], rz[3], v = 0.0;
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int cc = 0; cc < 2; ++cc)
+        {
+            jac(g2[a], g2[b], g2[cc], rx, ry, rz);
+            v += w2[a] * w2[b] * w2[cc] * det3(rx, ry, rz);
+        }
+        vol[e] = v;
+        m30[e] = v * (alpha ? alpha[e] : 1.0);
+        double Me[36] = {0};
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int cc = 0; cc < 3; ++cc)
+        {
+            jac(g3[a], g3[b], g3[cc], rx, ry, rz);
+            const double det = det3(rx, ry, rz), w = w3[a] * w3[b] * w3[cc];
+            double V[6][3];
+            for (int t = 0; t < 3; ++t)
+            {
+                V[0][t] = rx[t] * (1 - g3[a]); V[1][t] = rx[t] * g3[a];
+                V[2][t] = ry[t] * (1 - g3[b]); V[3][t] = ry[t] * g3[b];
+                V[4][t] = rz[t] * (1 - g3[cc]); V[5][t] = rz[t] * g3[cc];
+            }
+            for (int p = 0; p < 6; ++p) for (int q = 0; q < 6; ++q)
+                Me[p * 6 + q] += w * (V[p][0] * V[q][0] + V[p][1] * V[q][1] + V[p][2] * V[q][2]) / det;
+        }
+        const double be = beta ? beta[e] : 1.0;
+        for (int q = 0; q < 36; ++q) m20[(size_t)e * 36 + q] = be * Me[q];
+    }
+    // facet normals at the facet centres
+    std::vector<double> N((size_t)3 * nf);
+    auto mean_normal = [](const double *c00, const double *c10, const double *c01, const double *c11, double *n) {
+        double t1[3], t2[3];      // mean tangents along the first / second in-plane index
+        for (int t = 0; t < 3; ++t) { t1[t] = 0.5 * ((c10[t] - c00[t]) + (c11[t] - c01[t])); t2[t] = 0.5 * ((c01[t] - c00[t]) + (c11[t] - c10[t])); }
+        n[0] = t1[1] * t2[2] - t1[2] * t2[1]; n[1] = t1[2] * t2[0] - t1[0] * t2[2]; n[2] = t1[0] * t2[1] - t1[1] * t2[0];
+    };
+    for (int k = 0; k < mesh.nz; ++k) for (int j = 0; j < mesh.ny; ++j) for (int i = 0; i <= mesh.nx; ++i)      // x-faces: (y, z)
+        mean_normal(vtx(i, j, k), vtx(i, j + 1, k), vtx(i, j, k + 1), vtx(i, j + 1, k + 1), &N[(size_t)3 * mesh.fx(i, j, k)]);
+    for (int k = 0; k < mesh.nz; ++k) for (int j = 0; j <= mesh.ny; ++j) for (int i = 0; i < mesh.nx; ++i)      // y-faces: (z, x)
+        mean_normal(vtx(i, j, k), vtx(i, j, k + 1), vtx(i + 1, j, k), vtx(i + 1, j, k + 1), &N[(size_t)3 * mesh.fy(i, j, k)]);
+    for (int k = 0; k <= mesh.nz; ++k) for (int j = 0; j < mesh.ny; ++j) for (int i = 0; i < mesh.nx; ++i)      // z-faces: (x, y)
+        mean_normal(vtx(i, j, k), vtx(i + 1, j, k), vtx(i, j + 1, k), vtx(i + 1, j + 1, k), &N[(size_t)3 * mesh.fz(i, j, k)]);
+    S.facet_area.assign(nf, 0.0);
+    for (int f = 0; f < nf; ++f)
+    {
+        S.facet_area[f] = std::sqrt(N[3 * f] * N[3 * f] + N[3 * f + 1] * N[3 * f + 1] + N[3 * f + 2] * N[3 * f + 2]);
+        m21[f] = 1.0 / S.facet_area[f];
+    }
+    D.resize(3);
+    D[0] = topo->GetB(2);
+    D[1] = topo->GetB(1);
+    D[2] = topo->GetB(0);
+    for (int e = 0; e < nel; ++e)
+        for (int q = D[2].I[e]; q < D[2].I[e + 1]; ++q) D[2].A[q] *= (1.0 / vol[e]);
+    S.l2const.assign(nel, 1.0);
+    S.ridge_length.clear();
+    S.targets.resize(4); S.ntargets = {4, 3, 3, 1};
+    S.targets[3].assign(nel, 1.0);
+    S.targets[2].assign((size_t)3 * nf, 0.0);
+    for (int f = 0; f < nf; ++f) for (int cc = 0; cc < 3; ++cc) S.targets[2][(size_t)cc * nf + f] = N[3 * f + cc];
+    S.targets[1].assign((size_t)3 * mesh.ne(), 0.0);      // forms below jformStart are not coarsened
+    S.targets[0].assign((size_t)4 * mesh.nv(), 0.0);
+}
+
 /// fills SequenceData + D_ for the fine level; alpha / beta: optional per-element weights
 /// of the L2 and H(div) element mass matrices (ReplaceMassIntegrator in the drivers)
 inline void BuildFineHexSequence(const StructuredHexMesh &mesh, const std::shared_ptr<AgglomeratedTopology> &topo,
                                  const double *alpha, const double *beta, int jstart, SequenceData &S, std::vector<HostCSR> &D)
 {
     using namespace hexfe;
+    if (mesh.deformed()) { BuildFineHexSequenceDeformed(mesh, topo, alpha, beta, jstart, S, D); return; }
     const double hx = mesh.hx, hy = mesh.hy, hz = mesh.hz, vol = hx * hy * hz;
     const int nel = (int)mesh.nel();
     S.topo = topo; S.nforms = 4; S.jstart = jstart; S.is_fe = true;

@@ -149,6 +149,16 @@ extern "C" int pe_api_hexsequence_create(int nx, int ny, int nz, double Lx, doub
     *out = s;
     API_CATCH
 }
+extern "C" int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const double *vertex_xyz, const double *alpha,
+                                                  const double *beta, int jstart, int nlevels, double svd_tol, pe_sequence **out)
+{
+    API_TRY
+    PARELAG_TEST_FOR_EXCEPTION(!vertex_xyz, std::runtime_error, "pe_api_hexsequence_create_deformed: vertex coordinates missing");
+    auto s = new pe_sequence();
+    s->levels = BuildHexSequenceHierarchy(nx, ny, nz, 1.0, 1.0, 1.0, alpha, beta, jstart, nlevels, svd_tol, vertex_xyz);
+    *out = s;
+    API_CATCH
+}
 static HostCSR pool_as_csr(const BlockPool &P)
 {
     HostCSR M;

@@ -57,6 +57,40 @@ def test_fine_sequence_matrices_bit_exact():
     S.free()
 
 
+def test_deformed_fine_sequence_matches_oracle():
+    """Trilinear hexahedra (the 3DHdivWeakScaling vertex map, examples/3DHdivWeakScaling.cpp:148-158): the host-built
+    H(div)-L2 part of the fine sequence -- cell volumes, RT0 mass matrices by mfem's 3-point Gauss rule, facet trace
+    masses, D_2 = flux / volume, flux targets, boundary masks -- against the oracle, which reproduces the reference's
+    golden on this mesh (tests/test_goldens_cpu.py).  Tolerance 1e-14 relative: same formulas, different summation order."""
+    dims = (4, 4, 4)
+    rng = np.random.default_rng(5)
+    nel = 64
+    alpha, beta = rng.uniform(0.5, 2, nel), rng.uniform(0.1, 10, nel)
+    mesh = amge.DeformedHexMesh(*dims, deform=amge.weak_scaling_deformation)
+    seq = amge.fine_sequence(mesh, alpha=alpha, beta=beta, jstart=2)
+    S = api.Sequence.hex(dims, 1, alpha=alpha, beta=beta, jstart=2, svd_tol=-1.0, coords=mesh.vertex_coords())
+    for j in (2,):
+        D, Do = S.get_csr(0, "D", j), seq.D[j].tocsr()
+        Do.sort_indices()
+        assert np.array_equal(D.indptr, Do.indptr) and np.array_equal(D.indices, Do.indices)
+        assert abs(D - Do).max() <= 1e-14 * abs(Do).max()
+    for (j, c) in ((3, 0), (2, 0), (2, 1)):
+        Me, Mo = S.get_csr(0, "Me", j, c), seq.M[(j, c)]
+        assert Me.shape == Mo.shape and abs(Me - Mo).max() <= 1e-14 * abs(Mo).max(), (j, c)
+    for j in (2, 3):
+        M, Mo = S.get_csr(0, "M", j), seq.mass_operator(j)
+        assert abs(M - Mo).max() <= 1e-14 * abs(Mo).max()
+        assert np.abs(S.get_targets(0, j) - seq.targets[j]).max() <= 1e-14 * np.abs(seq.targets[j]).max()
+        from oracle import drivers
+        assert np.array_equal(S.get_bdr_mask(0, j), drivers.bdr_mask(seq.dof[j]))
+    # the RT0 mass matrices of moved cells couple all six faces (no longer block diagonal per axis)
+    blk = S.get_csr(0, "Me", 2, 0)[:6, :6].toarray()
+    assert abs(blk[0, 2]) > 1e-3 * abs(blk[0, 0])
+    S.free()
+    with pytest.raises(Exception):
+        api.Sequence.hex(dims, 1, jstart=0, svd_tol=-1.0, coords=mesh.vertex_coords())     # forms 0, 1 need more geometry
+
+
 def test_host_tables_do_not_depend_on_the_thread_count():
     """hostcsr::Mult / DofAgglomeration / pool fill run under OpenMP with per-thread buffers stitched in row
     order: the bit-exact table tests above must also pass single-threaded and with more threads than cores."""
