@@ -385,8 +385,113 @@ class DeformedHexMesh(HexMesh):
     def facet_area(self):
         return np.linalg.norm(self.facet_normals(), axis=1)
 
+    # ---- H(curl) part (lowest-order Nedelec: unit circulation along the +index axis of every edge)
+    def edge_vectors(self):
+        """end point minus start point of every ridge (ne_total, 3): x-, y-, z-edges"""
+        nx, ny, nz = self.dims
+        X = self.X
+        i, j, k = self._grid(nx, ny + 1, nz + 1)
+        tx = X[self.vx(i + 1, j, k)] - X[self.vx(i, j, k)]
+        i, j, k = self._grid(nx + 1, ny, nz + 1)
+        ty = X[self.vx(i, j + 1, k)] - X[self.vx(i, j, k)]
+        i, j, k = self._grid(nx + 1, ny + 1, nz)
+        tz = X[self.vx(i, j, k + 1)] - X[self.vx(i, j, k)]
+        return np.concatenate([tx, ty, tz], axis=0)
+
     def ridge_length(self):
-        raise NotImplementedError("deformed meshes carry the H(div)-L2 part of the sequence only (jstart = 2)")
+        return np.linalg.norm(self.edge_vectors(), axis=1)
+
+    def nd0_element_mass(self, npts=3):
+        """(nel, 12, 12): VectorFEMassIntegrator with the covariant Piola map w = J^-T what, Gauss rule of order
+        OrderW + 2 = 4.  Local order = ascending edge id: x-edges (j,k),(j+1,k),(j,k+1),(j+1,k+1), y-edges
+        (i,k),(i+1,k),(i,k+1),(i+1,k+1), z-edges (i,j),(i+1,j),(i,j+1),(i+1,j+1)."""
+        phi = lambda c, t: (1.0 - t) if c == 0 else t
+        g, w = self._gauss(npts)
+        M = np.zeros((self.nel, 12, 12))
+        pairs = ((0, 0), (1, 0), (0, 1), (1, 1))
+        for a, wa in zip(g, w):
+            for b, wb in zip(g, w):
+                for c, wc in zip(g, w):
+                    rx, ry, rz = self.jacobian_columns(a, b, c)
+                    J = np.stack([rx, ry, rz], axis=2)
+                    det = np.linalg.det(J)
+                    JinvT = np.transpose(np.linalg.inv(J), (0, 2, 1))
+                    W = ([np.array([phi(p, b) * phi(q, c), 0.0, 0.0]) for p, q in pairs]
+                         + [np.array([0.0, phi(p, a) * phi(q, c), 0.0]) for p, q in pairs]
+                         + [np.array([0.0, 0.0, phi(p, a) * phi(q, b)]) for p, q in pairs])
+                    V = [JinvT @ wv for wv in W]
+                    for p in range(12):
+                        for q in range(12):
+                            M[:, p, q] += (wa * wb * wc) * det * np.einsum("ei,ei->e", V[p], V[q])
+        return M
+
+    def _facet_corner_fn(self, axis):
+        """corner(u, v) of every facet of one axis; in-plane axes (u, v): x-faces (y, z), y-faces (x, z), z-faces (x, y)"""
+        nx, ny, nz = self.dims
+        X = self.X
+        if axis == 0:
+            i, j, k = self._grid(nx + 1, ny, nz)
+            return lambda u, v: X[self.vx(i, j + u, k + v)]
+        if axis == 1:
+            i, j, k = self._grid(nx, ny + 1, nz)
+            return lambda u, v: X[self.vx(i + u, j, k + v)]
+        i, j, k = self._grid(nx, ny, nz + 1)
+        return lambda u, v: X[self.vx(i + u, j + v, k)]
+
+    @staticmethod
+    def _facet_map(c, u, v):
+        """tangent map (n, 3, 2), its pseudo-inverse transposed G = J (J^T J)^-1 (covariant map of 2D Nedelec shapes
+        into the facet's tangent plane) and the surface weight sqrt(det J^T J) at the reference point (u, v)"""
+        tu = (c(1, 0) - c(0, 0)) * (1 - v) + (c(1, 1) - c(0, 1)) * v
+        tv = (c(0, 1) - c(0, 0)) * (1 - u) + (c(1, 1) - c(1, 0)) * u
+        Jf = np.stack([tu, tv], axis=2)
+        JtJ = np.einsum("eji,ejk->eik", Jf, Jf)
+        G = np.einsum("eij,ejk->eik", Jf, np.linalg.inv(JtJ))
+        return Jf, G, np.sqrt(np.linalg.det(JtJ))
+
+    def nd0_facet_mass(self, npts=2):
+        """three arrays (nf_axis, 4, 4): ND_3D_FacetMassIntegrator (bilinIntegrators.cpp:106-157), Gauss rule of order
+        OrderW + 2 = 3.  Local order = ascending edge id: the two edges along u (at v = 0, 1), then the two along v."""
+        phi = lambda c, t: (1.0 - t) if c == 0 else t
+        g, w = self._gauss(npts)
+        out = []
+        for axis in range(3):
+            c = self._facet_corner_fn(axis)
+            M = np.zeros((c(0, 0).shape[0], 4, 4))
+            for u, wu in zip(g, w):
+                for v, wv in zip(g, w):
+                    _, G, wt = self._facet_map(c, u, v)
+                    W = [np.array([phi(0, v), 0.0]), np.array([phi(1, v), 0.0]), np.array([0.0, phi(0, u)]), np.array([0.0, phi(1, u)])]
+                    V = [G @ x for x in W]
+                    for p in range(4):
+                        for q in range(4):
+                            M[:, p, q] += (wu * wv) * wt * np.einsum("ei,ei->e", V[p], V[q])
+            out.append(M)
+        return out
+
+    def boundary_tangent_rhs_bottom(self, f):
+        """VectorFEBoundaryTangentLFIntegrator on boundary attribute 1 (z-index 0): (n x f, w) with the outward normal,
+        2x2 Gauss rule (order 2 * el.GetOrder() = 2); returns the Nedelec load vector"""
+        phi = lambda c, t: (1.0 - t) if c == 0 else t
+        nx, ny, nz = self.dims
+        X = self.X
+        g, w = self._gauss(2)
+        b = np.zeros(sum(self.ne))
+        i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        i, j = i.ravel(), j.ravel()
+        c = lambda a, bb: X[self.vx(i + a, j + bb, 0)]
+        edges = [self.ex(i, j, 0), self.ex(i, j + 1, 0), self.ey(i, j, 0), self.ey(i + 1, j, 0)]
+        f = np.asarray(f, dtype=np.float64)
+        for u, wu in zip(g, w):
+            for v, wv in zip(g, w):
+                Jf, G, wt = self._facet_map(c, u, v)
+                n = np.cross(Jf[:, :, 0], Jf[:, :, 1])
+                n = -n / np.linalg.norm(n, axis=1)[:, None]            # outward: -(t_x x t_y)
+                nxf = np.cross(n, f[None, :])
+                W = [np.array([phi(0, v), 0.0]), np.array([phi(1, v), 0.0]), np.array([0.0, phi(0, u)]), np.array([0.0, phi(1, u)])]
+                for e, x in zip(edges, W):
+                    np.add.at(b, e, (wu * wv) * wt * np.einsum("ei,ei->e", G @ x, nxf))
+        return b
 
 
 class DofHandler:
@@ -1206,8 +1311,8 @@ def fine_sequence(mesh, topo=None, upscaling_order=0, alpha=None, beta=None, jst
 
 
 def _fine_sequence_deformed(mesh, topo, alpha, beta, jstart):
-    """H(div)-L2 part of DeRhamSequence3D_FE on trilinear hexahedra (forms 2 and 3; jformStart = 2)."""
-    assert jstart >= 2, "deformed meshes: forms 2 and 3 only"
+    """H(curl)-H(div)-L2 part of DeRhamSequence3D_FE on trilinear hexahedra (forms 1, 2, 3; jformStart >= 1)."""
+    assert jstart >= 1, "deformed meshes: forms 1, 2 and 3 only"
     seq = Sequence(topo, 4)
     seq.mesh = mesh
     seq.jstart = jstart
@@ -1229,6 +1334,12 @@ def _fine_sequence_deformed(mesh, topo, alpha, beta, jstart):
     seq.l2_const = np.ones(mesh.nel)
     seq.targets[3] = np.ones((mesh.nel, 1))
     seq.targets[2] = N.copy()            # fluxes of e_x, e_y, e_z
+    if jstart <= 1:
+        seq.M[(1, 0)] = sp.block_diag(list(mesh.nd0_element_mass()), format="csr")
+        seq.M[(1, 1)] = sp.block_diag([sp.block_diag(list(m), format="csr") for m in mesh.nd0_facet_mass()], format="csr")
+        t = mesh.edge_vectors()
+        seq.M[(1, 2)] = sp.diags(1.0 / np.linalg.norm(t, axis=1)).tocsr()   # VolumetricFEMassIntegrator on the edges
+        seq.targets[1] = t.copy()        # circulations of e_x, e_y, e_z
     return seq
 
 
@@ -1409,6 +1520,41 @@ def hdiv_weak_scaling_errors(nref=2, base=(1, 1, 1)):
         u = sols[lev]
         for q in range(lev - 1, -1, -1):
             u = seqs[q].P[2] @ u
+        d = u - sols[0]
+        dd = D0 @ d
+        out.append((float(np.sqrt(d @ (M0 @ d))), float(np.sqrt(dd @ (W0 @ dd)))))
+    return out
+
+
+def hcurl_weak_scaling_errors(nref=2, base=(1, 1, 1)):
+    """examples/3DHcurlWeakScaling.cpp on one rank (--nref_parallel nref): the deformed cube of
+    hdiv_weak_scaling_errors, H(curl) problem A = M_1 + D_1^T M_2 D_1, essential (zero) data on attributes 2-5,
+    natural data (n x f, v), f = (1, 1, 1), on attribute 1 (:181-184,247-256).  Errors against the fine solution,
+    coarsest level first.  All levels are solved directly here; the reference solves iteratively (rtol 1e-6)."""
+    import scipy.sparse.linalg as spl
+    dims = tuple(b * 2 ** nref for b in base)
+    mesh, seqs = build_hierarchy(dims, nref + 1, jstart=1, deform=weak_scaling_deformation)
+    ess = np.array([0, 1, 1, 1, 1, 0])
+    rhs = mesh.boundary_tangent_rhs_bottom((1.0, 1.0, 1.0))
+    sols = []
+    for lev, s in enumerate(seqs):
+        M, W, D = s.mass_operator(1), s.mass_operator(2), s.D[1]
+        A = _canon(M + D.T @ W @ D)
+        marker = s.dof[1].mark_bdr_dofs(ess)
+        keep = sp.diags((~marker).astype(float))
+        A = keep @ A @ keep + sp.diags(marker.astype(float))
+        r = rhs.copy()
+        r[marker] = 0.0
+        sols.append(spl.spsolve(A.tocsc(), r))
+        if lev + 1 < len(seqs):
+            rhs = s.P[1].T @ rhs
+    f = seqs[0]
+    M0, W0, D0 = f.mass_operator(1), f.mass_operator(2), f.D[1]
+    out = []
+    for lev in range(len(seqs) - 1, 0, -1):
+        u = sols[lev]
+        for q in range(lev - 1, -1, -1):
+            u = seqs[q].P[1] @ u
         d = u - sols[0]
         dd = D0 @ d
         out.append((float(np.sqrt(d @ (M0 @ d))), float(np.sqrt(dd @ (W0 @ dd)))))
