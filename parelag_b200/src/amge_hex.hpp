@@ -134,7 +134,7 @@ inline void fill_pool(BlockPool &P, int count, const double *blk, int m, const d
 }
 } // namespace hexfe
 
-/// H(div)-L2 part (forms 2, 3) of DeRhamSequence3D_FE at lowest order on trilinear hexahedra
+/// H(curl)-H(div)-L2 part (forms 1, 2, 3) of DeRhamSequence3D_FE at lowest order on trilinear hexahedra
 /// (DeRhamSequenceFE.cpp:633-684).  Per cell: volume (MassIntegrator on P0: 2-point Gauss rule, exact), RT0 mass
 /// matrix (VectorFEMassIntegrator, contravariant Piola map v = J vhat / det J, Gauss rule of order OrderW + 2 = 4:
 /// 3 points per direction), D_2 = net flux / volume (DivergenceInterpolator2, bilinIntegrators.hpp:272-290).
@@ -142,12 +142,18 @@ inline void fill_pool(BlockPool &P, int count, const double *blk, int m, const d
 /// (VolumetricFEMassIntegrator, one-point rule), PV-trace weight |N| (InterpolatePV_HdivTraces,
 /// DeRhamSequenceFE.cpp:810-857), targets = fluxes N.e_c of the constant fields (RT_HexahedronElement::Project).
 /// Local dof order of a cell: x-, x+, y-, y+, z-, z+ (ascending facet id), every basis function with unit flux
-/// along the +index axis.  Same arithmetic as oracle/amge.py:DeformedHexMesh.
+/// along the +index axis.  With jformStart = 1 also the Nedelec part: element mass matrices (covariant Piola map
+/// w = J^-T what, same Gauss rule; local order = ascending edge id: x-edges (j,k),(j+1,k),(j,k+1),(j+1,k+1), y-edges
+/// (i,k),(i+1,k),(i,k+1),(i+1,k+1), z-edges (i,j),(i+1,j),(i,j+1),(i+1,j+1)), facet mass matrices of the tangential
+/// traces (ND_3D_FacetMassIntegrator, bilinIntegrators.cpp:106-157, 2x2 Gauss rule; local order: the two edges along the
+/// first in-plane axis, then the two along the second; in-plane axes x-faces (y,z), y-faces (x,z), z-faces (x,y)), edge
+/// masses 1/|t|, PV-trace weights |t| and circulation targets t.e_c with t = end point - start point.
+/// Same arithmetic as oracle/amge.py:DeformedHexMesh.
 inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const std::shared_ptr<AgglomeratedTopology> &topo,
                                          const double *alpha, const double *beta, int jstart, SequenceData &S, std::vector<HostCSR> &D)
 {
-    PARELAG_TEST_FOR_EXCEPTION(jstart < 2, std::runtime_error,
-                               "deformed hexahedral meshes carry the H(div)-L2 part of the sequence only: use jformStart >= 2");
+    PARELAG_TEST_FOR_EXCEPTION(jstart < 1, std::runtime_error,
+                               "deformed hexahedral meshes carry the H(curl)-H(div)-L2 part of the sequence only: use jformStart >= 1");
     PARELAG_TEST_FOR_EXCEPTION((int64_t)mesh.coords.size() != (int64_t)3 * mesh.nv(), std::runtime_error,
                                "vertex coordinates: expected nv x 3 values");
     using hexfe::fill_pool;
@@ -176,6 +182,14 @@ inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const st
         double zero36[36] = {0};
         fill_pool(M20, nel, zero36, 6);
         fill_pool(M21, nf, &one, 1);
+    }
+    const bool with_curl = jstart <= 1;
+    double *m10 = nullptr;
+    if (with_curl)
+    {
+        std::vector<double> z144(144, 0.0);
+        fill_pool(S.M[{1, 0}], nel, z144.data(), 12);
+        m10 = S.M[{1, 0}].vals.data();
     }
     double *m30 = M30.vals.data(), *m20 = M20.vals.data(), *m21 = M21.vals.data();
 #pragma omp parallel for schedule(static)
@@ -221,6 +235,26 @@ inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const st
             }
             for (int p = 0; p < 6; ++p) for (int q = 0; q < 6; ++q)
                 Me[p * 6 + q] += w * (V[p][0] * V[q][0] + V[p][1] * V[q][1] + V[p][2] * V[q][2]) / det;
+            if (with_curl)
+            {
+                // rows of J^-1 = gradients of the reference coordinates: J^-T what = what_x grad(xh) + ...
+                const double gx[3] = {(ry[1] * rz[2] - ry[2] * rz[1]) / det, (ry[2] * rz[0] - ry[0] * rz[2]) / det, (ry[0] * rz[1] - ry[1] * rz[0]) / det};
+                const double gy[3] = {(rz[1] * rx[2] - rz[2] * rx[1]) / det, (rz[2] * rx[0] - rz[0] * rx[2]) / det, (rz[0] * rx[1] - rz[1] * rx[0]) / det};
+                const double gz[3] = {(rx[1] * ry[2] - rx[2] * ry[1]) / det, (rx[2] * ry[0] - rx[0] * ry[2]) / det, (rx[0] * ry[1] - rx[1] * ry[0]) / det};
+                const double pa[2] = {1 - g3[a], g3[a]}, pb[2] = {1 - g3[b], g3[b]}, pc[2] = {1 - g3[cc], g3[cc]};
+                const int pr[4][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}};
+                double Wv[12][3];
+                for (int t4 = 0; t4 < 4; ++t4)
+                    for (int t = 0; t < 3; ++t)
+                    {
+                        Wv[t4][t] = pb[pr[t4][0]] * pc[pr[t4][1]] * gx[t];
+                        Wv[4 + t4][t] = pa[pr[t4][0]] * pc[pr[t4][1]] * gy[t];
+                        Wv[8 + t4][t] = pa[pr[t4][0]] * pb[pr[t4][1]] * gz[t];
+                    }
+                double *Mn = m10 + (size_t)e * 144;
+                for (int p = 0; p < 12; ++p) for (int q = 0; q < 12; ++q)
+                    Mn[p * 12 + q] += w * det * (Wv[p][0] * Wv[q][0] + Wv[p][1] * Wv[q][1] + Wv[p][2] * Wv[q][2]);
+            }
         }
         const double be = beta ? beta[e] : 1.0;
         for (int q = 0; q < 36; ++q) m20[(size_t)e * 36 + q] = be * Me[q];
@@ -244,6 +278,58 @@ inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const st
         S.facet_area[f] = std::sqrt(N[3 * f] * N[3 * f] + N[3 * f + 1] * N[3 * f + 1] + N[3 * f + 2] * N[3 * f + 2]);
         m21[f] = 1.0 / S.facet_area[f];
     }
+    const int ne = mesh.ne();
+    std::vector<double> T((size_t)3 * ne, 0.0);     // edge vectors
+    if (with_curl)
+    {
+        // tangential-trace mass matrices of the facets, 2x2 Gauss rule
+        double z16[16] = {0};
+        fill_pool(S.M[{1, 1}], nf, z16, 4);
+        double *m11 = S.M[{1, 1}].vals.data();
+        auto facet_mass = [&](const double *c00, const double *c10, const double *c01, const double *c11, double *Mf) {
+            for (int q = 0; q < 16; ++q) Mf[q] = 0.0;
+            for (int iu = 0; iu < 2; ++iu) for (int iv = 0; iv < 2; ++iv)
+            {
+                const double u = g2[iu], v = g2[iv];
+                double tu[3], tv[3];
+                for (int t = 0; t < 3; ++t)
+                {
+                    tu[t] = (c10[t] - c00[t]) * (1 - v) + (c11[t] - c01[t]) * v;
+                    tv[t] = (c01[t] - c00[t]) * (1 - u) + (c11[t] - c10[t]) * u;
+                }
+                const double a11 = tu[0] * tu[0] + tu[1] * tu[1] + tu[2] * tu[2], a22 = tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2];
+                const double a12 = tu[0] * tv[0] + tu[1] * tv[1] + tu[2] * tv[2], dt = a11 * a22 - a12 * a12;
+                // G = J (J^T J)^-1: columns = dual tangents
+                double Gu[3], Gv[3];
+                for (int t = 0; t < 3; ++t) { Gu[t] = (a22 * tu[t] - a12 * tv[t]) / dt; Gv[t] = (a11 * tv[t] - a12 * tu[t]) / dt; }
+                const double wt = w2[iu] * w2[iv] * std::sqrt(dt);
+                double Wv[4][3];
+                for (int t = 0; t < 3; ++t) { Wv[0][t] = (1 - v) * Gu[t]; Wv[1][t] = v * Gu[t]; Wv[2][t] = (1 - u) * Gv[t]; Wv[3][t] = u * Gv[t]; }
+                for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q)
+                    Mf[p * 4 + q] += wt * (Wv[p][0] * Wv[q][0] + Wv[p][1] * Wv[q][1] + Wv[p][2] * Wv[q][2]);
+            }
+        };
+        for (int k = 0; k < mesh.nz; ++k) for (int j = 0; j < mesh.ny; ++j) for (int i = 0; i <= mesh.nx; ++i)      // (u,v) = (y,z)
+            facet_mass(vtx(i, j, k), vtx(i, j + 1, k), vtx(i, j, k + 1), vtx(i, j + 1, k + 1), m11 + (size_t)16 * mesh.fx(i, j, k));
+        for (int k = 0; k < mesh.nz; ++k) for (int j = 0; j <= mesh.ny; ++j) for (int i = 0; i < mesh.nx; ++i)      // (u,v) = (x,z)
+            facet_mass(vtx(i, j, k), vtx(i + 1, j, k), vtx(i, j, k + 1), vtx(i + 1, j, k + 1), m11 + (size_t)16 * mesh.fy(i, j, k));
+        for (int k = 0; k <= mesh.nz; ++k) for (int j = 0; j < mesh.ny; ++j) for (int i = 0; i < mesh.nx; ++i)      // (u,v) = (x,y)
+            facet_mass(vtx(i, j, k), vtx(i + 1, j, k), vtx(i, j + 1, k), vtx(i + 1, j + 1, k), m11 + (size_t)16 * mesh.fz(i, j, k));
+        // edges
+        auto edge = [&](int id, const double *p0, const double *p1) { for (int t = 0; t < 3; ++t) T[(size_t)3 * id + t] = p1[t] - p0[t]; };
+        for (int k = 0; k <= mesh.nz; ++k) for (int j = 0; j <= mesh.ny; ++j) for (int i = 0; i < mesh.nx; ++i) edge(mesh.ex(i, j, k), vtx(i, j, k), vtx(i + 1, j, k));
+        for (int k = 0; k <= mesh.nz; ++k) for (int j = 0; j < mesh.ny; ++j) for (int i = 0; i <= mesh.nx; ++i) edge(mesh.ey(i, j, k), vtx(i, j, k), vtx(i, j + 1, k));
+        for (int k = 0; k < mesh.nz; ++k) for (int j = 0; j <= mesh.ny; ++j) for (int i = 0; i <= mesh.nx; ++i) edge(mesh.ez(i, j, k), vtx(i, j, k), vtx(i, j, k + 1));
+        double one = 1.0;
+        fill_pool(S.M[{1, 2}], ne, &one, 1);
+        double *m12 = S.M[{1, 2}].vals.data();
+        S.ridge_length.assign(ne, 0.0);
+        for (int e = 0; e < ne; ++e)
+        {
+            S.ridge_length[e] = std::sqrt(T[3 * e] * T[3 * e] + T[3 * e + 1] * T[3 * e + 1] + T[3 * e + 2] * T[3 * e + 2]);
+            m12[e] = 1.0 / S.ridge_length[e];
+        }
+    }
     D.resize(3);
     D[0] = topo->GetB(2);
     D[1] = topo->GetB(1);
@@ -251,12 +337,13 @@ inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const st
     for (int e = 0; e < nel; ++e)
         for (int q = D[2].I[e]; q < D[2].I[e + 1]; ++q) D[2].A[q] *= (1.0 / vol[e]);
     S.l2const.assign(nel, 1.0);
-    S.ridge_length.clear();
+    if (!with_curl) S.ridge_length.clear();
     S.targets.resize(4); S.ntargets = {4, 3, 3, 1};
     S.targets[3].assign(nel, 1.0);
     S.targets[2].assign((size_t)3 * nf, 0.0);
     for (int f = 0; f < nf; ++f) for (int cc = 0; cc < 3; ++cc) S.targets[2][(size_t)cc * nf + f] = N[3 * f + cc];
-    S.targets[1].assign((size_t)3 * mesh.ne(), 0.0);      // forms below jformStart are not coarsened
+    S.targets[1].assign((size_t)3 * ne, 0.0);             // forms below jformStart are not coarsened
+    if (with_curl) for (int e = 0; e < ne; ++e) for (int cc = 0; cc < 3; ++cc) S.targets[1][(size_t)cc * ne + e] = T[3 * e + cc];
     S.targets[0].assign((size_t)4 * mesh.nv(), 0.0);
 }
 

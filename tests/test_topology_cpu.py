@@ -83,12 +83,24 @@ def test_deformed_fine_sequence_matches_oracle():
         assert np.abs(S.get_targets(0, j) - seq.targets[j]).max() <= 1e-14 * np.abs(seq.targets[j]).max()
         from oracle import drivers
         assert np.array_equal(S.get_bdr_mask(0, j), drivers.bdr_mask(seq.dof[j]))
+    S.free()
+    # with jformStart = 1 also the Nedelec part: element / facet / edge mass matrices, circulation targets
+    seq = amge.fine_sequence(mesh, jstart=1)
+    S = api.Sequence.hex(dims, 1, jstart=1, svd_tol=-1.0, coords=mesh.vertex_coords())
+    for (j, c) in ((1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (3, 0)):
+        Me, Mo = S.get_csr(0, "Me", j, c), seq.M[(j, c)]
+        assert Me.shape == Mo.shape and abs(Me - Mo).max() <= 1e-13 * abs(Mo).max(), (j, c)
+    M, Mo = S.get_csr(0, "M", 1), seq.mass_operator(1)
+    assert abs(M - Mo).max() <= 1e-13 * abs(Mo).max()
+    assert np.abs(S.get_targets(0, 1) - seq.targets[1]).max() <= 1e-14 * np.abs(seq.targets[1]).max()
+    D1, D1o = S.get_csr(0, "D", 1), seq.D[1].tocsr()
+    assert abs(D1 - D1o).max() == 0
     # the RT0 mass matrices of moved cells couple all six faces (no longer block diagonal per axis)
     blk = S.get_csr(0, "Me", 2, 0)[:6, :6].toarray()
     assert abs(blk[0, 2]) > 1e-3 * abs(blk[0, 0])
     S.free()
     with pytest.raises(Exception):
-        api.Sequence.hex(dims, 1, jstart=0, svd_tol=-1.0, coords=mesh.vertex_coords())     # forms 0, 1 need more geometry
+        api.Sequence.hex(dims, 1, jstart=0, svd_tol=-1.0, coords=mesh.vertex_coords())     # form 0 needs more geometry
 
 
 def test_host_tables_do_not_depend_on_the_thread_count():
