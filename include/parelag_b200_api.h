@@ -53,9 +53,9 @@ int pe_api_hexsequence_create(int nx, int ny, int nz, double Lx, double Ly, doub
                               const double *alpha, const double *beta, int jform_start, int nlevels,
                               double svd_tol, pe_sequence **out);
 /* The same on trilinear hexahedra: vertex_xyz[nv x 3] (index-grid numbering, x fastest) replaces the axis-aligned
- * vertices -- the geometry of examples/3DHdivWeakScaling.cpp:148-158 and 3DHcurlWeakScaling.cpp.  The H(curl)-H(div)-L2
- * part of the sequence is built by quadrature (mfem's rules: DeRhamSequenceFE.cpp:633-684, bilinIntegrators.cpp:64-157),
- * so jform_start must be >= 1.  Single rank. */
+ * vertices -- the geometry of examples/3DHdivWeakScaling.cpp:148-158 and 3DHcurlWeakScaling.cpp.  The mass matrices of
+ * all four forms are built by quadrature (mfem's rules: DeRhamSequenceFE.cpp:633-684, bilinIntegrators.cpp:64-157).
+ * Single rank. */
 int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const double *vertex_xyz, const double *alpha,
                                        const double *beta, int jform_start, int nlevels, double svd_tol, pe_sequence **out);
 /* ---- multi-rank (one rank <-> one box of a P0 x P1 x P2 box decomposition <-> one GPU).

@@ -469,6 +469,39 @@ class DeformedHexMesh(HexMesh):
             out.append(M)
         return out
 
+    # ---- H1 part (trilinear nodal basis)
+    def h1_element_mass(self, npts=3):
+        """(nel, 8, 8): MassIntegrator, Gauss rule of order 2 + OrderW = 4; local order = ascending vertex id
+        (i fastest, then j, then k)"""
+        phi = lambda c, t: (1.0 - t) if c == 0 else t
+        g, w = self._gauss(npts)
+        M = np.zeros((self.nel, 8, 8))
+        for a, wa in zip(g, w):
+            for b, wb in zip(g, w):
+                for c, wc in zip(g, w):
+                    rx, ry, rz = self.jacobian_columns(a, b, c)
+                    det = np.einsum("ei,ei->e", rx, np.cross(ry, rz))
+                    sh = np.array([phi(p, a) * phi(q, b) * phi(r, c) for r in (0, 1) for q in (0, 1) for p in (0, 1)])
+                    M += (wa * wb * wc) * det[:, None, None] * np.outer(sh, sh)[None, :, :]
+        return M
+
+    def h1_facet_mass(self, npts=2):
+        """three arrays (nf_axis, 4, 4): MassIntegrator on the bilinear faces, Gauss rule of order 2 + OrderW = 3;
+        local order = ascending vertex id (first in-plane axis fastest)"""
+        phi = lambda c, t: (1.0 - t) if c == 0 else t
+        g, w = self._gauss(npts)
+        out = []
+        for axis in range(3):
+            c = self._facet_corner_fn(axis)
+            M = np.zeros((c(0, 0).shape[0], 4, 4))
+            for u, wu in zip(g, w):
+                for v, wv in zip(g, w):
+                    _, _, wt = self._facet_map(c, u, v)
+                    sh = np.array([phi(p, u) * phi(q, v) for q in (0, 1) for p in (0, 1)])
+                    M += (wu * wv) * wt[:, None, None] * np.outer(sh, sh)[None, :, :]
+            out.append(M)
+        return out
+
     def boundary_tangent_rhs_bottom(self, f):
         """VectorFEBoundaryTangentLFIntegrator on boundary attribute 1 (z-index 0): (n x f, w) with the outward normal,
         2x2 Gauss rule (order 2 * el.GetOrder() = 2); returns the Nedelec load vector"""
@@ -1311,8 +1344,8 @@ def fine_sequence(mesh, topo=None, upscaling_order=0, alpha=None, beta=None, jst
 
 
 def _fine_sequence_deformed(mesh, topo, alpha, beta, jstart):
-    """H(curl)-H(div)-L2 part of DeRhamSequence3D_FE on trilinear hexahedra (forms 1, 2, 3; jformStart >= 1)."""
-    assert jstart >= 1, "deformed meshes: forms 1, 2 and 3 only"
+    """DeRhamSequence3D_FE at lowest order on trilinear hexahedra (DeRhamSequenceFE.cpp:633-684): mass matrices by
+    mfem's Gauss rules, topological D_0, D_1, D_2 = flux / volume, order-0 upscaling targets."""
     seq = Sequence(topo, 4)
     seq.mesh = mesh
     seq.jstart = jstart
@@ -1340,6 +1373,15 @@ def _fine_sequence_deformed(mesh, topo, alpha, beta, jstart):
         t = mesh.edge_vectors()
         seq.M[(1, 2)] = sp.diags(1.0 / np.linalg.norm(t, axis=1)).tocsr()   # VolumetricFEMassIntegrator on the edges
         seq.targets[1] = t.copy()        # circulations of e_x, e_y, e_z
+    if jstart <= 0:
+        seq.M[(0, 0)] = sp.block_diag(list(mesh.h1_element_mass()), format="csr")
+        seq.M[(0, 1)] = sp.block_diag([sp.block_diag(list(m), format="csr") for m in mesh.h1_facet_mass()], format="csr")
+        L = mesh.ridge_length()
+        M1D_ = np.array([[1.0 / 3.0, 1.0 / 6.0], [1.0 / 6.0, 1.0 / 3.0]])
+        seq.M[(0, 2)] = sp.block_diag([l * M1D_ for l in L], format="csr")      # straight edges: exact
+        seq.M[(0, 3)] = sp.identity(mesh.nv, format="csr")
+        X = mesh.vertex_coords()
+        seq.targets[0] = np.stack([np.ones(mesh.nv), X[:, 2], X[:, 1], X[:, 0]], axis=1)   # 1, z, y, x
     return seq
 
 

@@ -60,7 +60,7 @@ class Sequence:
     @staticmethod
     def hex(dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9, coords=None):
         """Full coarsening path on a structured hex mesh (svd_tol < 0: topology only).  coords: optional (nv, 3)
-        moved vertices (trilinear hexahedra, index-grid numbering; needs jstart >= 1)."""
+        moved vertices (trilinear hexahedra, index-grid numbering)."""
         S = Sequence.__new__(Sequence)
         S.h = C.c_void_p()
         a = None if alpha is None else _f64(alpha)

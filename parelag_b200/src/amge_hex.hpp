@@ -134,7 +134,7 @@ inline void fill_pool(BlockPool &P, int count, const double *blk, int m, const d
 }
 } // namespace hexfe
 
-/// H(curl)-H(div)-L2 part (forms 1, 2, 3) of DeRhamSequence3D_FE at lowest order on trilinear hexahedra
+/// DeRhamSequence3D_FE at lowest order on trilinear hexahedra (all four forms)
 /// (DeRhamSequenceFE.cpp:633-684).  Per cell: volume (MassIntegrator on P0: 2-point Gauss rule, exact), RT0 mass
 /// matrix (VectorFEMassIntegrator, contravariant Piola map v = J vhat / det J, Gauss rule of order OrderW + 2 = 4:
 /// 3 points per direction), D_2 = net flux / volume (DivergenceInterpolator2, bilinIntegrators.hpp:272-290).
@@ -148,12 +148,12 @@ inline void fill_pool(BlockPool &P, int count, const double *blk, int m, const d
 /// traces (ND_3D_FacetMassIntegrator, bilinIntegrators.cpp:106-157, 2x2 Gauss rule; local order: the two edges along the
 /// first in-plane axis, then the two along the second; in-plane axes x-faces (y,z), y-faces (x,z), z-faces (x,y)), edge
 /// masses 1/|t|, PV-trace weights |t| and circulation targets t.e_c with t = end point - start point.
+/// With jformStart = 0 also the H1 part: trilinear nodal mass matrices of the cells (3-point rule) and facets (2-point
+/// rule), exact edge mass matrices |t| [1/3 1/6; 1/6 1/3], unit vertex masses, targets 1, z, y, x at the moved vertices.
 /// Same arithmetic as oracle/amge.py:DeformedHexMesh.
 inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const std::shared_ptr<AgglomeratedTopology> &topo,
                                          const double *alpha, const double *beta, int jstart, SequenceData &S, std::vector<HostCSR> &D)
 {
-    PARELAG_TEST_FOR_EXCEPTION(jstart < 1, std::runtime_error,
-                               "deformed hexahedral meshes carry the H(curl)-H(div)-L2 part of the sequence only: use jformStart >= 1");
     PARELAG_TEST_FOR_EXCEPTION((int64_t)mesh.coords.size() != (int64_t)3 * mesh.nv(), std::runtime_error,
                                "vertex coordinates: expected nv x 3 values");
     using hexfe::fill_pool;
@@ -183,7 +183,14 @@ inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const st
         fill_pool(M20, nel, zero36, 6);
         fill_pool(M21, nf, &one, 1);
     }
-    const bool with_curl = jstart <= 1;
+    const bool with_curl = jstart <= 1, with_h1 = jstart <= 0;
+    double *m00 = nullptr;
+    if (with_h1)
+    {
+        double z64[64] = {0};
+        fill_pool(S.M[{0, 0}], nel, z64, 8);
+        m00 = S.M[{0, 0}].vals.data();
+    }
     double *m10 = nullptr;
     if (with_curl)
     {
@@ -254,6 +261,14 @@ inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const st
                 double *Mn = m10 + (size_t)e * 144;
                 for (int p = 0; p < 12; ++p) for (int q = 0; q < 12; ++q)
                     Mn[p * 12 + q] += w * det * (Wv[p][0] * Wv[q][0] + Wv[p][1] * Wv[q][1] + Wv[p][2] * Wv[q][2]);
+            }
+            if (with_h1)
+            {
+                const double pa[2] = {1 - g3[a], g3[a]}, pb[2] = {1 - g3[b], g3[b]}, pc[2] = {1 - g3[cc], g3[cc]};
+                double sh[8];
+                for (int r = 0; r < 2; ++r) for (int q = 0; q < 2; ++q) for (int p = 0; p < 2; ++p) sh[4 * r + 2 * q + p] = pa[p] * pb[q] * pc[r];
+                double *Mh = m00 + (size_t)e * 64;
+                for (int p = 0; p < 8; ++p) for (int q = 0; q < 8; ++q) Mh[p * 8 + q] += w * det * sh[p] * sh[q];
             }
         }
         const double be = beta ? beta[e] : 1.0;
@@ -330,6 +345,47 @@ inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const st
             m12[e] = 1.0 / S.ridge_length[e];
         }
     }
+    if (with_h1)
+    {
+        double z16[16] = {0};
+        fill_pool(S.M[{0, 1}], nf, z16, 4);
+        double *m01 = S.M[{0, 1}].vals.data();
+        auto facet_mass_h1 = [&](const double *c00, const double *c10, const double *c01, const double *c11, double *Mf) {
+            for (int q = 0; q < 16; ++q) Mf[q] = 0.0;
+            for (int iu = 0; iu < 2; ++iu) for (int iv = 0; iv < 2; ++iv)
+            {
+                const double u = g2[iu], v = g2[iv];
+                double tu[3], tv[3];
+                for (int t = 0; t < 3; ++t)
+                {
+                    tu[t] = (c10[t] - c00[t]) * (1 - v) + (c11[t] - c01[t]) * v;
+                    tv[t] = (c01[t] - c00[t]) * (1 - u) + (c11[t] - c10[t]) * u;
+                }
+                const double a11 = tu[0] * tu[0] + tu[1] * tu[1] + tu[2] * tu[2], a22 = tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2];
+                const double a12 = tu[0] * tv[0] + tu[1] * tv[1] + tu[2] * tv[2];
+                const double wt = w2[iu] * w2[iv] * std::sqrt(a11 * a22 - a12 * a12);
+                const double sh[4] = {(1 - u) * (1 - v), u * (1 - v), (1 - u) * v, u * v};
+                for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q) Mf[p * 4 + q] += wt * sh[p] * sh[q];
+            }
+        };
+        for (int k = 0; k < mesh.nz; ++k) for (int j = 0; j < mesh.ny; ++j) for (int i = 0; i <= mesh.nx; ++i)
+            facet_mass_h1(vtx(i, j, k), vtx(i, j + 1, k), vtx(i, j, k + 1), vtx(i, j + 1, k + 1), m01 + (size_t)16 * mesh.fx(i, j, k));
+        for (int k = 0; k < mesh.nz; ++k) for (int j = 0; j <= mesh.ny; ++j) for (int i = 0; i < mesh.nx; ++i)
+            facet_mass_h1(vtx(i, j, k), vtx(i + 1, j, k), vtx(i, j, k + 1), vtx(i + 1, j, k + 1), m01 + (size_t)16 * mesh.fy(i, j, k));
+        for (int k = 0; k <= mesh.nz; ++k) for (int j = 0; j < mesh.ny; ++j) for (int i = 0; i < mesh.nx; ++i)
+            facet_mass_h1(vtx(i, j, k), vtx(i + 1, j, k), vtx(i, j + 1, k), vtx(i + 1, j + 1, k), m01 + (size_t)16 * mesh.fz(i, j, k));
+        double z4[4] = {0};
+        fill_pool(S.M[{0, 2}], ne, z4, 2);
+        double *m02 = S.M[{0, 2}].vals.data();
+        for (int e = 0; e < ne; ++e)
+        {
+            const double l = S.ridge_length[e];
+            m02[4 * e] = m02[4 * e + 3] = l * (1.0 / 3.0);
+            m02[4 * e + 1] = m02[4 * e + 2] = l * (1.0 / 6.0);
+        }
+        double one = 1.0;
+        fill_pool(S.M[{0, 3}], mesh.nv(), &one, 1);
+    }
     D.resize(3);
     D[0] = topo->GetB(2);
     D[1] = topo->GetB(1);
@@ -345,6 +401,17 @@ inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const st
     S.targets[1].assign((size_t)3 * ne, 0.0);             // forms below jformStart are not coarsened
     if (with_curl) for (int e = 0; e < ne; ++e) for (int cc = 0; cc < 3; ++cc) S.targets[1][(size_t)cc * ne + e] = T[3 * e + cc];
     S.targets[0].assign((size_t)4 * mesh.nv(), 0.0);
+    if (with_h1)
+    {
+        const size_t nv = (size_t)mesh.nv();
+        for (size_t v = 0; v < nv; ++v)
+        {
+            S.targets[0][v] = 1.0;
+            S.targets[0][nv + v] = X[3 * v + 2];
+            S.targets[0][2 * nv + v] = X[3 * v + 1];
+            S.targets[0][3 * nv + v] = X[3 * v];
+        }
+    }
 }
 
 /// fills SequenceData + D_ for the fine level; alpha / beta: optional per-element weights

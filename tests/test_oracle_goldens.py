@@ -81,3 +81,12 @@ def test_solve_oracle_vcycle_converges_on_amge_hierarchy():
     x, it, conv, hist = orc.pcg(A, H.mult, b, rtol=1e-8, atol=0.0, max_iter=50)
     assert conv and it <= 12
     assert np.linalg.norm(b - A @ x) <= 1e-6 * np.linalg.norm(b)
+
+
+def test_check_invariants_on_trilinear_hexahedra():
+    """DeRhamSequence::CheckInvariants identities (M_c = P^T M P, D D = 0, D P = P D_c, Pi P = I, targets reproduced) on
+    the three-level hierarchy of the moved-vertex mesh of examples/3DHdivWeakScaling.cpp, all four forms"""
+    mesh, seqs = amge.build_hierarchy((4, 4, 4), 3, jstart=0, deform=amge.weak_scaling_deformation)
+    for s in seqs[:-1]:
+        for k, v in amge.check_invariants(s).items():
+            assert v < 1e-9, (k, v)

@@ -99,8 +99,35 @@ def test_deformed_fine_sequence_matches_oracle():
     blk = S.get_csr(0, "Me", 2, 0)[:6, :6].toarray()
     assert abs(blk[0, 2]) > 1e-3 * abs(blk[0, 0])
     S.free()
-    with pytest.raises(Exception):
-        api.Sequence.hex(dims, 1, jstart=0, svd_tol=-1.0, coords=mesh.vertex_coords())     # form 0 needs more geometry
+    # all four forms (jformStart = 0): H1 cell / facet / edge / vertex mass matrices, targets 1, z, y, x
+    seq = amge.fine_sequence(mesh, jstart=0)
+    S = api.Sequence.hex(dims, 1, jstart=0, svd_tol=-1.0, coords=mesh.vertex_coords())
+    for (j, c) in ((0, 0), (0, 1), (0, 2), (0, 3)):
+        Me, Mo = S.get_csr(0, "Me", j, c), seq.M[(j, c)]
+        assert Me.shape == Mo.shape and abs(Me - Mo).max() <= 1e-13 * abs(Mo).max(), (j, c)
+    assert np.abs(S.get_targets(0, 0) - seq.targets[0]).max() <= 1e-14
+    S.free()
+
+
+def test_identity_vertex_map_reproduces_the_closed_form_pools():
+    """Quadrature path with unmoved vertices == closed-form path (anisotropic box): checks every local ordering and
+    orientation convention of the trilinear-hexahedra code against the structured one, in the product and in the oracle."""
+    dims, L = (4, 2, 6), (1.0, 2.0, 0.75)
+    ref = api.Sequence.hex(dims, 1, L=L, svd_tol=-1.0)
+    X = amge.HexMesh(*dims, L=L).vertex_coords()
+    S = api.Sequence.hex(dims, 1, svd_tol=-1.0, coords=X)
+    so = amge.fine_sequence(amge.DeformedHexMesh(*dims, deform=lambda Y: Y, L=L), jstart=0)
+    sr = amge.fine_sequence(amge.HexMesh(*dims, L=L), jstart=0)
+    for j in range(4):
+        for c in range(4 - j):
+            A, B = S.get_csr(0, "Me", j, c), ref.get_csr(0, "Me", j, c)
+            assert abs(A - B).max() <= 1e-13 * abs(B).max(), (j, c)
+            assert abs(so.M[(j, c)] - sr.M[(j, c)]).max() <= 1e-13 * abs(sr.M[(j, c)]).max(), (j, c)
+        assert np.abs(S.get_targets(0, j) - ref.get_targets(0, j)).max() <= 1e-14
+        assert np.abs(so.targets[j] - sr.targets[j]).max() <= 1e-14
+    for j in range(3):
+        assert abs(S.get_csr(0, "D", j) - ref.get_csr(0, "D", j)).max() <= 1e-13 * abs(ref.get_csr(0, "D", j)).max()
+    S.free(); ref.free()
 
 
 def test_host_tables_do_not_depend_on_the_thread_count():
