@@ -23,8 +23,7 @@ def test_deformed_mesh_coarsen_matches_oracle_and_reference_golden():
     dims, nlev = (4, 4, 4), 3
     mesh, seqs = amge.build_hierarchy(dims, nlev, jstart=2, deform=amge.weak_scaling_deformation)
     S = api.Sequence.hex(dims, nlev, jstart=2, coords=mesh.vertex_coords())
-    compare_levels(S, seqs, tol=1e-10)
-    # the reference's experiment with the product's P, D and mass operators
+    # (1) sign- and basis-invariant check first: the reference's experiment with the product's P, D and mass operators
     ess = np.array([0, 1, 1, 1, 1, 0])
     i, j = np.meshgrid(np.arange(dims[0]), np.arange(dims[1]), indexing="ij")
     rhs = np.zeros(S.get_csr(0, "M", 2).shape[0])
@@ -51,5 +50,7 @@ def test_deformed_mesh_coarsen_matches_oracle_and_reference_golden():
         dd = D0 @ d
         u_err.append("%.4e" % np.sqrt(d @ (M0 @ d)))
         du_err.append("%.4e" % np.sqrt(dd @ (W0 @ dd)))
-    assert u_err == REF["3DHdivWeakScaling"]["u_errors"] and du_err == REF["3DHdivWeakScaling"]["du_errors"]
+    assert u_err == REF["3DHdivWeakScaling"]["u_errors"] and du_err == REF["3DHdivWeakScaling"]["du_errors"], (u_err, du_err)
+    # (2) entry-wise comparison with the oracle (needs identical SVD sign choices: see README.md, ties)
+    compare_levels(S, seqs, tol=1e-10)
     S.free()
