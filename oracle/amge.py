@@ -705,14 +705,22 @@ class DofAgg:
 # ----------------------------------------------------------------------------
 # dense helpers
 # ----------------------------------------------------------------------------
+SIGN_TIE_REL = 1e-6
+
+
 def fix_sign(U):
-    """Canonical sign: largest-magnitude entry of each column positive (first on ties)."""
+    """Canonical sign: the first entry (in index order) whose magnitude is within a relative
+    SIGN_TIE_REL of the column's largest magnitude is positive.  Equal to "largest-magnitude entry
+    positive" when that entry is unique; independent of rounding when congruent fine entities give
+    entries of equal magnitude (the reference's sign is LAPACK's, i.e. arbitrary: every quantity
+    the reference's tests pin is invariant under it)."""
     U = np.array(U, dtype=np.float64, copy=True)
     for j in range(U.shape[1]):
         col = U[:, j]
         if col.size == 0:
             continue
-        p = int(np.argmax(np.abs(col)))
+        a = np.abs(col)
+        p = int(np.argmax(a >= a.max() * (1.0 - SIGN_TIE_REL)))
         if col[p] < 0:
             U[:, j] = -col
     return U

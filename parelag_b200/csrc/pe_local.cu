@@ -17,7 +17,8 @@
 // systems (order 7..60) are solved by Gaussian elimination with partial pivoting and the
 // thin SVDs (<= 8 columns) by one-sided Jacobi, both in FP64 FMA -- far below DMMA tile
 // sizes, so no tensor cores.  SVD sign convention: largest-magnitude
-// entry of every retained singular vector is positive (first on ties).
+// entry of every retained singular vector is positive; near-ties (relative 1e-6) go to the
+// smallest index (warp_sign_pivot).
 #include "pe_core.cuh"
 #include <chrono>
 #include <map>
@@ -89,6 +90,25 @@ __device__ int cta_lu_solve(double *A, int n, int lda, double *R, int nrhs, int 
     return 0;
 }
 
+// Index of the entry that fixes the sign of a singular vector: the FIRST entry (in index order)
+// whose magnitude is within a relative 1e-6 of the largest one.  Identical to "largest-magnitude
+// entry" whenever that entry is unique; on (near-)ties -- congruent fine entities inside an
+// agglomerate give entries of equal magnitude up to rounding -- the choice no longer depends on the
+// last bits, which LAPACK (oracle/amge.py:fix_sign follows the same rule) and the Jacobi SVD need not share.
+#define PE_SIGN_TIE_REL 1e-6
+__device__ __forceinline__ int warp_sign_pivot(const double *col, int m, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    double best = 0.0;
+    for (int i = lane; i < m; i += 32) best = fmax(best, fabs(col[i]));
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(FULL, best, o));
+    const double thr = best * (1.0 - PE_SIGN_TIE_REL);
+    int bi = m;
+    for (int i = lane; i < m; i += 32) if (fabs(col[i]) >= thr) { bi = i; break; }
+    for (int o = 16; o > 0; o >>= 1) bi = min(bi, __shfl_xor_sync(FULL, bi, o));
+    return bi < m ? bi : 0;
+}
+
 // One-sided (Hestenes) Jacobi SVD of X (m x k, COLUMN-major, ldx >= m) by warp 0.
 // On exit: columns of X are the left singular vectors (sign-fixed) scaled to unit norm
 // where sigma > 0, ordered by descending sigma; sv[0..min(m,k)) the singular values.
@@ -147,13 +167,7 @@ __device__ void warp_jacobi_svd(double *X, int m, int k, int ldx, double *sv, in
     for (int p = 0; p < k; ++p)
     {
         const double s = sv[p];
-        double best = -1.0; int bi = 0;
-        for (int i = lane; i < m; i += 32) { double v = fabs(X[p * ldx + i]); if (v > best) { best = v; bi = i; } }
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            double ob = __shfl_xor_sync(FULL, best, o); int oi = __shfl_xor_sync(FULL, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
+        const int bi = warp_sign_pivot(X + p * ldx, m, lane);
         const double sgn = (m > 0 && X[p * ldx + bi] < 0.0) ? -1.0 : 1.0;
         const double sc = s > 0.0 ? sgn / s : 0.0;
         __syncwarp();
@@ -259,13 +273,7 @@ __global__ void __launch_bounds__(32) k_traces(TraceArgs a)
     // canonical sign again after the inverse row scaling (largest |entry| may have moved)
     for (int c = 1; c < nc; ++c)
     {
-        double best = -1.0; int bi = 0;
-        for (int i = lane; i < m; i += 32) { double v = fabs(Pl[c * ld + i]); if (v > best) { best = v; bi = i; } }
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            double ob = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
+        const int bi = warp_sign_pivot(Pl + c * ld, m, lane);
         if (Pl[c * ld + bi] < 0.0) for (int i = lane; i < m; i += 32) Pl[c * ld + i] = -Pl[c * ld + i];
         __syncwarp();
     }

@@ -1,5 +1,4 @@
-"""PENDING (see README.md in this directory; not collected: the file name does not start with test_).
-BASELINE configs[4] geometry (examples/3DHdivWeakScaling.cpp: trilinear hexahedra after y += exp(z)/2,
+"""BASELINE configs[4] geometry (examples/3DHdivWeakScaling.cpp: trilinear hexahedra after y += exp(z)/2,
 x += sin(y)) through the product path: Coarsen() on the GPU against the oracle, and the reference's own golden
 (examples/CMakeLists.txt:130-136) recomputed from the PRODUCT's operators."""
 import json
@@ -15,7 +14,7 @@ from oracle import amge
 from tests.test_coarsen_gpu import compare_levels
 
 pytestmark = pytest.mark.gpu
-REF = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "golden", "reference_upscaling_norms.json")))
+REF = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_upscaling_norms.json")))
 
 
 def test_deformed_mesh_coarsen_matches_oracle_and_reference_golden():
@@ -51,6 +50,8 @@ def test_deformed_mesh_coarsen_matches_oracle_and_reference_golden():
         u_err.append("%.4e" % np.sqrt(d @ (M0 @ d)))
         du_err.append("%.4e" % np.sqrt(dd @ (W0 @ dd)))
     assert u_err == REF["3DHdivWeakScaling"]["u_errors"] and du_err == REF["3DHdivWeakScaling"]["du_errors"], (u_err, du_err)
-    # (2) entry-wise comparison with the oracle (needs identical SVD sign choices: see README.md, ties)
-    compare_levels(S, seqs, tol=1e-10)
+    # (2) entry-wise comparison with the oracle (identical SVD sign choices: tie-robust rule, oracle fix_sign / warp_sign_pivot)
+    # 58 + 12 NullSpace dofs on this mesh; the level-1 interior ones come from a residual with sigma_2 |T| = 1.6e-4
+    # (oracle: singular values 1, 1.5e-2, 2e-12 of a residual of norm 1.1e-2): determined to ~1e-16 / 1.6e-4 * cond
+    compare_levels(S, seqs, tol=1e-10, null_tol=1e-8)
     S.free()
