@@ -244,7 +244,8 @@ int pe_spadd(pe_ctx *ctx, double a, const pe_mat *A, double b, const pe_mat *B, 
 int pe_mat_eliminate_rowcol(pe_ctx *ctx, pe_mat *A, const int32_t *marker_host);
 
 /* ---- src/hypreExtension utilities on device matrices
- * pe_mat_delete_zeros : hypre_ParCSRMatrixDeleteZeros (deleteZeros.c:16-47), in place, |a| < tol dropped
+ * pe_mat_delete_zeros : hypre_ParCSRMatrixDeleteZeros (deleteZeros.c:16-47), in place; entries with |a| <= tol are
+ *                       dropped as in hypre_CSRMatrixDeleteZeros (tol = 0: stored zeros only)
  * pe_mat_sign         : hypre_ParCSRDataTransformationSign (entries -> -1 / 0 / +1 with threshold tol)
  * pe_mat_diagonal     : hypre_IdentityCSRMatrix (d == NULL) / hypre_DiagonalCSRMatrix (hypre_CSRFactory.c:16-250)
  * pe_mat_norms        : {l1, linf, max, Frobenius} (hypre_ParCSRMatrixNorms.c:18-195), all-reduced over ranks

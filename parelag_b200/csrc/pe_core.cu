@@ -859,12 +859,15 @@ __global__ void k_pack(int n, const int32_t *__restrict__ map, const double *__r
 }
 
 // peer-memory path (pe_p2p.cu): linked at the first exchange of a matrix outside graph capture -- a collective
-// step, like the exchange itself.  Only ranks that have a neighbour for this matrix get here (the others returned
-// above), and pe_p2p_link gathers over ALL ranks: as with hypre's comm packages on a connected partition, a matrix
-// either couples every rank to some neighbour or none (true for all level operators of a box decomposition).
+// step over ALL ranks (pe_p2p_link gathers the buffer offsets of every rank), so every rank of a distributed
+// matrix enters it, also a rank that has no neighbour for this particular matrix (all ranks execute the same
+// sequence of exchanges); matrices that are not distributed at all (no comm package on any rank: global == local
+// size) never get here.
 static int p2p_ready(pe_mat *A)
 {
     pe_ctx *c = A->ctx;
+    // rank-local matrix on a multi-rank context (global == local sizes: the MPI_COMM_SELF case): nothing to link
+    if (A->global_num_rows == A->diag.nrows && A->global_num_cols == A->diag.ncols) return 0;
     if (A->p2p_state == 0 && c->p2p_base && !c->capturing) PE_TRY(pe_p2p_link(A));
     return 0;
 }
@@ -875,8 +878,8 @@ int pe_halo_exchange(pe_mat *A, const double *x_d)
     if (c->nranks == 1) return 0;
     int nsend = A->send_map_starts.empty() ? 0 : A->send_map_starts.back();
     int nrecv = A->recv_vec_starts.empty() ? 0 : A->recv_vec_starts.back();
-    if (nsend == 0 && nrecv == 0) return 0;
     PE_TRY(p2p_ready(A));
+    if (nsend == 0 && nrecv == 0) return 0;
     if (A->p2p_state == 1) return pe_p2p_push(A, 0, x_d);
     if (nsend > 0) {
         k_pack<<<pe_grid_for(nsend, 256), 256, 0, c->stream>>>(nsend, A->send_map_d, x_d, A->send_buf_d);
@@ -923,8 +926,8 @@ int pe_reverse_halo_add(pe_mat *A, double alpha, double *y_d)
     if (c->nranks == 1) return 0;
     int nsend = A->send_map_starts.empty() ? 0 : A->send_map_starts.back();
     int nrecv = A->recv_vec_starts.empty() ? 0 : A->recv_vec_starts.back();
-    if (nsend == 0 && nrecv == 0) return 0;
     PE_TRY(p2p_ready(A));
+    if (nsend == 0 && nrecv == 0) return 0;
     if (A->p2p_state == 1)
     {
         PE_TRY(pe_p2p_push(A, 1, A->x_ext_d));

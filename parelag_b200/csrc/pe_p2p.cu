@@ -230,6 +230,9 @@ int pe_p2p_link(pe_mat *A)
     u64 *fwd_ack = flags, *fwd_flag = flags + ns, *rev_ack = flags + ns + nr, *rev_flag = flags + ns + 2 * nr;
     u64 *seq = flags + 2 * ns + 2 * nr;
     unsigned int *done = reinterpret_cast<unsigned int *>(seq + 2);
+    // From here on a failure of ONE rank (asymmetric comm package, allocation) must not leave the others on the
+    // peer path spinning on flags nobody publishes: build locally, then vote (as pe_p2p_init does).
+    auto build = [&]() -> int {
     for (int dir = 0; dir < 2; ++dir)
     {
         PeP2PDir *d = new PeP2PDir();
@@ -267,6 +270,13 @@ int pe_p2p_link(pe_mat *A)
         d->seq_d = seq + dir;
         d->done_d = done + dir;
     }
+    return 0;
+    };
+    int built = build() == 0 ? 1 : 0;
+    std::vector<int> votes((size_t)hc->size, 0);
+    PE_CHECK(hc->allgather(hc->user, &built, (int64_t)sizeof(int), votes.data()) == 0, "pe_p2p_link: host allgather failed");
+    for (int r = 0; r < hc->size; ++r) built &= votes[r];
+    if (!built) { pe_p2p_unlink(A); return 0; }       // everybody keeps NCCL for this matrix (state stays -1)
     A->p2p_state = 1;
     return 0;
 }

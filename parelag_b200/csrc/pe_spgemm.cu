@@ -114,9 +114,12 @@ k_spgemm_smem(int nlist, const int *__restrict__ list,
             for (int kb = blo + tid; kb < bhi; kb += GT) {
                 bool added;
                 int s = table_insert(keys, TABLE - 1, BJ[kb], added);
-                if (NUMERIC) atomicAdd(vals + s, a * BA[kb]);
+                if (NUMERIC) atomicAdd(vals + s, a * BA[kb]);   // columns of one B row are distinct: one add per slot and ka
                 else if (added) atomicAdd(&cnt[g], 1);
             }
+            // products are accumulated in the order of A's row entries (like the serial hypre RAP): the
+            // group finishes entry ka before anyone starts ka+1, so every C entry has ONE summation order
+            if (NUMERIC) { if (GT == 32) __syncwarp(); else __syncthreads(); }
         }
     }
     if (GT == 32) __syncwarp(); else __syncthreads();
@@ -184,6 +187,7 @@ k_spgemm_gmem(int nlist, const int *__restrict__ list, const long long *__restri
             if (NUMERIC) atomicAdd(vals + s, a * BA[kb]);
             else if (added) atomicAdd(&cnt, 1);
         }
+        if (NUMERIC) __syncthreads();                // fixed summation order, see k_spgemm_smem
     }
     __syncthreads();
     if (!NUMERIC) { if (tid == 0) rownnz[row] = cnt; return; }

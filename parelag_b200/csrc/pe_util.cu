@@ -4,13 +4,14 @@
 #include <cub/cub.cuh>
 #include <cmath>
 
-// ---- hypre_CSRMatrixDeleteZeros (deleteZeros.c:49-111): keep entries with |a| >= tol -----------------
+// ---- hypre_CSRMatrixDeleteZeros (hypre, called by hypre_ParCSRMatrixDeleteZeros, deleteZeros.c:16-47): entries with
+// |a| <= tol are deleted, i.e. |a| > tol is kept (tol = 0 removes the stored zeros) ---------------------------------
 __global__ void k_count_keep(int n, const int *__restrict__ I, const double *__restrict__ A, double tol, int *len)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     int c = 0;
-    for (int k = I[r]; k < I[r + 1]; ++k) c += fabs(A[k]) >= tol;
+    for (int k = I[r]; k < I[r + 1]; ++k) c += fabs(A[k]) > tol;
     len[r] = c;
 }
 __global__ void k_fill_keep(int n, const int *__restrict__ I, const int *__restrict__ J, const double *__restrict__ A, double tol,
@@ -19,7 +20,7 @@ __global__ void k_fill_keep(int n, const int *__restrict__ I, const int *__restr
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     int p = OI[r];
-    for (int k = I[r]; k < I[r + 1]; ++k) if (fabs(A[k]) >= tol) { OJ[p] = J[k]; OA[p] = A[k]; ++p; }
+    for (int k = I[r]; k < I[r + 1]; ++k) if (fabs(A[k]) > tol) { OJ[p] = J[k]; OA[p] = A[k]; ++p; }
 }
 static int compress_block(pe_ctx *ctx, DevCSR &m, double tol)
 {

@@ -11,6 +11,8 @@
 //   AMGeSolverFactory       src/linalg/factories/ParELAG_AMGeSolverFactory.cpp:26-209
 //   StationarySolver        src/linalg/solver_ops/ParELAG_StationarySolver.cpp:41-147
 #pragma once
+#include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include "parelag_core.hpp"
@@ -231,7 +233,8 @@ public:
     KrylovSolver(Op_Ptr A, std::shared_ptr<mfem::Solver> Prec, ParameterList &params)
         : Solver(A->Height(), A->Width(), false), A_(std::move(A)), Prec_(std::move(Prec))
     {
-        const std::string name = params.Get("Solver name", "PCG");
+        std::string name = params.Get("Solver name", "PCG");
+        std::transform(name.begin(), name.end(), name.begin(), ::toupper);      // ParELAG_KrylovSolver.cpp:38-40
         PARELAG_TEST_FOR_EXCEPTION(name != "PCG" && name != "CG" && name != "GMRES" && name != "FGMRES" && name != "MINRES" && name != "BICGSTAB",
                                    std::runtime_error, "KrylovSolver::KrylovSolver(...): Bad solver type (\"" << name << "\").\n\n"
                                    "Valid choices are \"CG\", \"GMRES\", \"FGMRES\", \"BiCGSTAB\", \"MINRES\".");
@@ -281,8 +284,14 @@ public:
         if (nom <= r0) { converged_ = true; final_norm_ = std::sqrt(nom); return; }
         A_->Mult(d_, z_);
         den = z_ * d_;
-        if (den <= 0.0) { final_norm_ = std::sqrt(nom); return; }
+        if (den <= 0.0)
+        {
+            // mfem::CGSolver::Mult: a non-positive (Ad, d) is reported, only an exact zero stops the iteration
+            if (print_level_ >= 0 && d_ * d_ > 0.0) std::printf("PCG: The operator is not positive definite. (Ad, d) = %g\n", den);
+            if (den == 0.0) { final_norm_ = std::sqrt(nom); return; }
+        }
         int i = 1;
+        bool stopped_early = false;
         while (true)
         {
             alpha = nom / den;
@@ -299,10 +308,14 @@ public:
             else { d_ *= beta; d_ += r_; }
             A_->Mult(d_, z_);
             den = d_ * z_;
-            if (den <= 0.0) break;
+            if (den <= 0.0)
+            {
+                if (print_level_ >= 0 && d_ * d_ > 0.0) std::printf("PCG: The operator is not positive definite. (Ad, d) = %g\n", den);
+                if (den == 0.0) { final_iter_ = i; converged_ = false; stopped_early = true; break; }
+            }
             nom = betanom;
         }
-        if (!converged_) final_iter_ = max_iter_;
+        if (!converged_ && !stopped_early) final_iter_ = max_iter_;
         final_norm_ = std::sqrt(std::fabs(betanom));
         if (final_paragraph_ || print_level_ >= 0)
             std::printf("PCG: %s after %d iterations, (B r, r) = %g, (B r_0, r_0) = %g\n",

@@ -277,11 +277,19 @@ def test_hypre_extension_utilities(ctx):
     B2 = A.copy(); B2.data[7] += 1e-3
     assert capi.Mat.from_scipy(ctx, B2).compare(dA, 1e-6) == 64
     assert capi.Mat.from_scipy(ctx, sp.csr_matrix(A[:50])).compare(dA, 1e-6) & (1 | 8 | 64)
-    # delete zeros
+    # delete zeros: hypre_CSRMatrixDeleteZeros deletes |a| <= tol (an entry equal to tol goes, tol = 0 removes the
+    # stored zeros only)
+    Z0 = A.copy(); Z0.data[3] = 0.0; Z0.data[11] = 0.0
+    dZ0 = capi.Mat.from_scipy(ctx, Z0)
+    dZ0.delete_zeros(0.0)
+    G0 = dZ0.to_scipy()
+    assert G0.nnz == A.nnz - 2 and abs(G0 - Z0).max() == 0
+    A.data[1] = 1e-9                                      # exactly tol: deleted
+    dA = capi.Mat.from_scipy(ctx, A)
     dA.delete_zeros(1e-9)
-    Az = A.copy(); Az.data[np.abs(Az.data) < 1e-9] = 0; Az.eliminate_zeros()
+    Az = A.copy(); Az.data[np.abs(Az.data) <= 1e-9] = 0; Az.eliminate_zeros()
     G = dA.to_scipy()
-    assert G.nnz == Az.nnz and abs(G - Az).max() == 0
+    assert G.nnz == Az.nnz and abs(G - Az).max() == 0 and G[A.nonzero()[0][1], A.nonzero()[1][1]] == 0
     # sign
     dA.sign(1e-9)
     assert abs(dA.to_scipy() - Az.sign()).max() == 0
