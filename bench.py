@@ -13,10 +13,17 @@ attributes essential.  A step = one application of the AMGe V-cycle
   python bench.py --gpus N --steps K --warmup W            (this implementation)
   python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
 
-N > 1: one process per GPU (torchrun), one mesh box per GPU (2x1x1, 2x2x1, 2x2x2 boxes of n^3
-hexahedra each -- the 3DHdivWeakScaling layout, configs[4]): every rank coarsens its own box, the
-levels are glued by SharingMaps, and the V-cycle exchanges the ParCSR halo with NCCL send/recv
-(weak scaling: per-GPU work is fixed, value = global dofs / max-over-ranks time).
+N > 1: one process per GPU (torchrun), one mesh box per GPU -- BASELINE configs[4], examples/3DHdivWeakScaling.cpp:
+the unit cube cut into 2x1x1, 2x2x1, 2x2x2 boxes of n^3 hexahedra each, vertices moved by y += exp(z)/2,
+x += sin(y) (trilinear hexahedra, :148-158), essential data on boundary attributes 2-5, natural on 1 and 6
+(:53-66).  Every rank coarsens its own box, the levels are glued by SharingMaps, and the V-cycle exchanges the
+ParCSR halo over NVLink peer memory (or NCCL send/recv).  Weak scaling: per-GPU work is fixed,
+value = global dofs / max-over-ranks time.
+
+Before anything is timed, at every N, a `parity` block checks the product against the oracle (tests/parity_checks.py):
+N = 1: Coarsen + V-cycle + PCG history on a small mesh, and one SpMV and one multicolour Gauss-Seidel sweep of the
+FULL-SIZE fine operator against oracle/solve_oracle.c; N > 1: the box-decomposed hierarchy (same geometry, 4^3
+hexahedra per box) against the oracle's single-domain hierarchy.  The oracle is only the checker there.
 """
 import argparse
 import json
@@ -160,24 +167,99 @@ def time_cpu_vcycles(H, n, steps, warmup, budget_s=25.0):
     return float(np.mean(ts)), len(ts)
 
 
+def host_threads():
+    """threads this process may really use (affinity / cgroup aware)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def product_level_operators(ctx, ns, lv):
+    """Level operators (A0, [P_l], [D_l]) of the bounded CPU sample, taken from the PRODUCT's hierarchy of the same
+    workload (inputs of the solve path; what is timed on the CPU is the oracle V-cycle over them)."""
+    import scipy.sparse as sp
+    from parelag_b200 import api
+    Ss = api.Sequence.hex((ns, ns, ns), lv, jstart=1)
+    As = Ss.assemble_system(ctx, 0, 2, ESS).to_scipy()
+    Ps, Ds = [], []
+    for l in range(lv):
+        D = Ss.get_csr(l, "D", 1)
+        m = Ss.get_bdr_mask(l, 1) != 0
+        Ds.append(sp.csr_matrix((np.where(m[D.indices], 0.0, D.data), D.indices, D.indptr), shape=D.shape))
+        if l + 1 < lv:
+            P = Ss.get_csr(l, "P", 2)
+            mc = Ss.get_bdr_mask(l + 1, 2) != 0
+            Ps.append(sp.csr_matrix((np.where(mc[P.indices], 0.0, P.data), P.indices, P.indptr), shape=P.shape))
+    Ss.free()
+    return As, Ps, Ds
+
+
+def levels_for(n, cap):
+    lv = 1
+    while n % (2 ** lv) == 0 and lv < cap:
+        lv += 1
+    return lv
+
+
+def cpu_setup_baseline(n=16, levels=4):
+    """Setup half of the metric on the CPU: the oracle's Coarsen() of all levels (oracle/amge.py: numpy + LAPACK
+    restatement of DeRhamSequence::Coarsen, one thread, Python loops over the agglomerates) on a bounded sample."""
+    from oracle import amge
+    t0 = time.perf_counter()
+    mesh, seqs = amge.build_hierarchy((n, n, n), levels, jstart=1)
+    t = time.perf_counter() - t0
+    nd = int(seqs[0].dof[2].ndofs)
+    return {"seconds": t, "sample": "oracle Coarsen() of %d levels on %d^3 hexahedra (%d RT0 dofs), forms 1-3" % (levels, n, nd),
+            "dofs_per_s": nd / t, "cores": 1, "kind": "port (numpy restatement, Python loops: an upper bound on the CPU time, "
+            "not a tuned C++ build)", "seconds_scaled_to_9020160_dofs": t * 9020160.0 / nd}
+
+
 def run_reference(args, rank):
+    """CPU arm: the oracle's V-cycle (hypre/MFEM arithmetic restated in C, oracle/solve_oracle.c) with all the host
+    threads this process may use -- one row block per thread = one MPI rank per core, hybrid Gauss-Seidel -- on a
+    bounded sample of the N = 1 workload (same operator, smoother, coarse solver; ref_n^3 instead of 144^3 hexahedra).
+    Level operators come from the product's hierarchy when a GPU is present (inputs only), else from the oracle's."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    n_s, levels = args.ref_n, args.ref_levels
-    H, ndofs = cpu_vcycle_setup(n_s, levels, cores, oracle_hierarchy_inputs)
+    cores = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(cores)          # a launcher (torchrun) exports OMP_NUM_THREADS=1
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    from oracle import solve as orc
+    got = orc.set_threads(cores)
+    assert got == cores, "OpenMP gives %d threads, %d requested" % (got, cores)
+    n_s = args.ref_n
+    inputs, src = oracle_hierarchy_inputs, "oracle"
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from parelag_b200 import api
+            ctx = api.session(rank=0, nranks=1, device=0)
+            inputs, src = (lambda ns, lv: product_level_operators(ctx, ns, lv)), "product"
+    except Exception:
+        pass
+    if src == "oracle":
+        n_s = min(n_s, 32)                               # the numpy coarsening oracle: minutes beyond that
+    levels = levels_for(n_s, args.levels)
+    H, ndofs = cpu_vcycle_setup(n_s, levels, cores, inputs)
     t, done = time_cpu_vcycles(H, ndofs, args.steps, min(args.warmup, 1), budget_s=120.0)
     value = ndofs / t
-    sample = ("H(div) AMGe V-cycle (Hiptmair l1-GS, PCG-GS coarse) on %d^3 hexahedra, %d RT0 dofs, %d levels; "
-              "hybrid GS with %d row blocks (= %d MPI ranks), oracle port of the hypre/MFEM kernels" %
-              (n_s, ndofs, levels, cores, cores))
+    setup = None if args.no_cpu_setup else cpu_setup_baseline()
+    sample = ("H(div) AMGe V-cycle (Hiptmair l1-GS, PCG-GS coarse) on %d^3 hexahedra, %d RT0 dofs, %d levels (level operators "
+              "from the %s); SpMV and hybrid GS with %d OpenMP threads = %d row blocks (one MPI rank per core), oracle "
+              "port of the hypre/MFEM kernels" % (n_s, ndofs, levels, src, cores, cores))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "MultigridTest2Form: H(div) AMGe V-cycle, bounded CPU sample %d^3" % n_s},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "MultigridTest2Form (configs[1]): H(div) A=M2+D2^T M3 D2, %d-level AMGe, Hiptmair(l1-GS,l1-GS), "
+                                   "PCG-GS coarse solver; bounded CPU sample %d^3 hexahedra (%d RT0 dofs) of the 144^3 workload"
+                                   % (levels, n_s, ndofs)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "omp_threads": got, "kind": "port", "sample": sample,
+                             "setup": setup},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os._exit(0)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -191,8 +273,10 @@ def main():
     ap.add_argument("--levels", type=int, default=5)
     ap.add_argument("--ordering", default="multicolor", choices=["multicolor", "natural"])
     ap.add_argument("--jstart", type=int, default=0, help="jformStart of the sequence (driver uses 0)")
-    ap.add_argument("--ref-n", type=int, default=32)
-    ap.add_argument("--ref-levels", type=int, default=4)
+    ap.add_argument("--ref-n", type=int, default=96, help="hexahedra per direction of the CPU arm's bounded sample")
+    ap.add_argument("--no-cpu-setup", action="store_true", help="skip the CPU setup baseline (oracle Coarsen on 16^3)")
+    ap.add_argument("--no-deform", action="store_true", help="N > 1: axis-aligned boxes instead of the configs[4] geometry")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block")
     ap.add_argument("--cpu-n", type=int, default=32, help="bounded sample of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sell-min-rows", type=int, default=None,
@@ -248,9 +332,33 @@ def main():
     if args.sell_min_rows is not None:
         capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, args.sell_min_rows)
 
+    # ---------------- parity block (the oracle is the checker; nothing of it is timed or shipped)
+    deformed = world > 1 and not args.no_deform
+    ess = np.array([0, 1, 1, 1, 1, 0], dtype=np.int32) if deformed else ESS     # 3DHdivWeakScaling.cpp:53-66
+    parity = None
+    host_group = api._host_comm.group if world > 1 else None
+    if not args.no_parity:
+        try:
+            from tests import parity_checks
+            if world > 1:
+                parity = dict(parity_checks.multi_rank(ctx, rank, world, deform=deformed, group=host_group), ok=True)
+            else:
+                parity = dict(parity_checks.single_rank_small(ctx), ok=True)
+        except AssertionError as e:
+            parity = {"ok": False, "failed": repr(e)[:400]}
+        if world > 1:
+            oks = [None] * world
+            dist.all_gather_object(oks, bool(parity["ok"]), group=host_group)
+            parity["ok"] = bool(all(oks))
+        api.lib().pe_api_timer_clear()
+
     # ---------------- setup (timed with the reference's timer names)
     t0 = time.perf_counter()
-    if world > 1:
+    if deformed:
+        X = api.box_vertex_coords(procs, api.rank_box(procs, rank), (n, n, n), api.weak_scaling_deformation)
+        S = api.Sequence.hex_par(procs, (n, n, n), levels, jstart=max(args.jstart, 1), coords=X)
+        del X
+    elif world > 1:
         S = api.Sequence.hex_par(procs, (n, n, n), levels, L=(1.0, 1.0, 1.0), jstart=args.jstart)
     else:
         S = api.Sequence.hex((n, n, n), levels, jstart=args.jstart)
@@ -262,7 +370,7 @@ def main():
     ext_stages = {"h2d_s": st6[0], "kernel_s": st6[1], "d2h_s": st6[2], "h2d_GB": st6[3] / 1e9, "d2h_GB": st6[4] / 1e9,
                   "calls": int(st6[5])}
     t0 = time.perf_counter()
-    A = S.assemble_system(ctx, 0, 2, ESS)
+    A = S.assemble_system(ctx, 0, 2, ess)
     ctx.sync()
     t_assemble = time.perf_counter() - t0
     ndofs = A.info()[0]                       # true dofs owned by this rank
@@ -289,9 +397,16 @@ def main():
     spmv = {"ms": ms_spmv, "GBs": b_spmv / ms_spmv / 1e6, "frac_of_measured_peak": b_spmv / ms_spmv / 1e6 / peak,
             "nnz": nnz0, "rows": ndofs}
 
+    # full-size kernel parity (N = 1): one SpMV and one multicolour GS sweep of THIS operator against solve_oracle.c
+    if parity is not None and parity.get("ok") and world == 1 and not args.profile_range:
+        try:
+            parity["full_size"] = parity_checks.full_size_kernels(ctx, A)
+        except AssertionError as e:
+            parity["ok"] = False
+            parity["failed"] = repr(e)[:400]
     t0 = time.perf_counter()
     solver = api.Solver(api.library_xml(library(args.ordering)), "PCG with Auxiliary Space Preconditioner",
-                        A, S, 0, 2, ESS)
+                        A, S, 0, 2, ess)
     ctx.sync()
     t_build = time.perf_counter() - t0
     nlev = solver.num_levels()
@@ -430,42 +545,29 @@ def main():
     if rank == 0:
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
-            def product_inputs(ns, lv):
-                # level operators of the bounded sample from the product's own hierarchy (inputs only)
-                Ss = api.Sequence.hex((ns, ns, ns), lv, jstart=1)
-                As = Ss.assemble_system(ctx, 0, 2, ESS).to_scipy()
-                import scipy.sparse as sp
-                Ps, Ds = [], []
-                for l in range(lv):
-                    D = Ss.get_csr(l, "D", 1)
-                    m = Ss.get_bdr_mask(l, 1) != 0
-                    D = sp.csr_matrix((np.where(m[D.indices], 0.0, D.data), D.indices, D.indptr), shape=D.shape)
-                    Ds.append(D)
-                    if l + 1 < lv:
-                        P = Ss.get_csr(l, "P", 2)
-                        mc = Ss.get_bdr_mask(l + 1, 2) != 0
-                        Ps.append(sp.csr_matrix((np.where(mc[P.indices], 0.0, P.data), P.indices, P.indptr), shape=P.shape))
-                return As, Ps, Ds
-            lv = 1
-            while args.cpu_n % (2 ** lv) == 0 and lv < levels:
-                lv += 1
-            H, nd = cpu_vcycle_setup(args.cpu_n, lv, 1, product_inputs)
+            from oracle import solve as orc
+            orc.set_threads(1)
+            lv = levels_for(args.cpu_n, levels)
+            H, nd = cpu_vcycle_setup(args.cpu_n, lv, 1, lambda ns, lvv: product_level_operators(ctx, ns, lvv))
             t_cpu, done = time_cpu_vcycles(H, nd, 30, 1, budget_s=20.0)
             cpu_baseline = {"value": nd / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
                             "sample": "same H(div) AMGe V-cycle (Hiptmair l1-GS natural order, PCG-GS coarse) on a "
                                       "%d^3-hexahedra sample (%d RT0 dofs, %d levels), %d cycles of %.3f s on one host core; "
                                       "oracle port of the hypre/MFEM kernels (oracle/solve_oracle.c)"
-                                      % (args.cpu_n, nd, lv, done, t_cpu)}
+                                      % (args.cpu_n, nd, lv, done, t_cpu),
+                            "setup": None if args.no_cpu_setup else cpu_setup_baseline()}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": ("MultigridTest2Form (configs[1]): H(div) A=M2+D2^T M3 D2, %d^3 hexahedra, "
                                         "%d RT0 dofs, %d-level AMGe, Hiptmair(l1-GS,l1-GS) %s order, PCG-GS coarse solver"
                                         % (n, ndofs, nlev, args.ordering)) if world == 1 else
-                                       ("3DHdivWeakScaling layout (configs[4]): %dx%dx%d boxes of %d^3 hexahedra, one box per GPU, "
+                                       ("3DHdivWeakScaling (configs[4]): unit cube in %dx%dx%d boxes of %d^3 hexahedra, one box per GPU, %s, "
                                         "H(div) A=M2+D2^T M3 D2, %d RT0 true dofs in total, %d-level AMGe, Hiptmair(hybrid l1-GS,"
                                         "hybrid l1-GS) %s order, PCG-GS coarse solver, ParCSR halo exchange by %s"
-                                        % (procs + (n, ndofs_global, nlev, args.ordering,
+                                        % (procs + (n, "deformed: trilinear hexahedra after y += exp(z)/2, x += sin(y), essential "
+                                                       "attributes 2-5" if deformed else "axis-aligned, all attributes essential",
+                                                    ndofs_global, nlev, args.ordering,
                                                     "NVLink peer-memory stores + device flags (CUDA IPC)" if capi.lib().pe_ctx_p2p_enabled(ctx.h)
                                                     else "NCCL send/recv"))),
                            "l2_policy": "inputs larger than L2 (hierarchy working set %.1f GB)" %
@@ -474,7 +576,7 @@ def main():
                                            "domain decomposition, %d ranks = %d GPUs, one mesh box each" % (world, world)),
                            "jform_start": args.jstart,
                            "levels": [{"rows": li[0], "nnz": li[1], "nnz_P": li[2]} for li in level_info]},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "setup_s": {"sequence_all_levels": t_coarsen, "assemble_system": t_assemble, "build_solver": t_build,
                             "total": t_coarsen + t_assemble + t_build, "timers": timers,

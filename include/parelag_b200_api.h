@@ -54,8 +54,7 @@ int pe_api_hexsequence_create(int nx, int ny, int nz, double Lx, double Ly, doub
                               double svd_tol, pe_sequence **out);
 /* The same on trilinear hexahedra: vertex_xyz[nv x 3] (index-grid numbering, x fastest) replaces the axis-aligned
  * vertices -- the geometry of examples/3DHdivWeakScaling.cpp:148-158 and 3DHcurlWeakScaling.cpp.  The mass matrices of
- * all four forms are built by quadrature (mfem's rules: DeRhamSequenceFE.cpp:633-684, bilinIntegrators.cpp:64-157).
- * Single rank. */
+ * all four forms are built by quadrature (mfem's rules: DeRhamSequenceFE.cpp:633-684, bilinIntegrators.cpp:64-157). */
 int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const double *vertex_xyz, const double *alpha,
                                        const double *beta, int jform_start, int nlevels, double svd_tol, pe_sequence **out);
 /* ---- multi-rank (one rank <-> one box of a P0 x P1 x P2 box decomposition <-> one GPU).
@@ -69,6 +68,12 @@ int pe_api_session_set_host_comm(const pe_host_comm *comm);
 int pe_api_hexsequence_create_par(const int32_t *procs, int nx, int ny, int nz, double Lx, double Ly, double Lz,
                                   const double *alpha, const double *beta, int jform_start, int nlevels,
                                   double svd_tol, pe_sequence **out);
+/* The box decomposition on trilinear hexahedra (examples/3DHdivWeakScaling.cpp:113-158: one box per rank, vertices moved
+ * after the refinement): vertex_xyz[nv x 3] are the vertices of THIS rank's box; copies of an interface vertex must be
+ * bitwise equal on all ranks that hold it. */
+int pe_api_hexsequence_create_par_deformed(const int32_t *procs, int nx, int ny, int nz, const double *vertex_xyz,
+                                           const double *alpha, const double *beta, int jform_start, int nlevels,
+                                           double svd_tol, pe_sequence **out);
 int pe_api_sequence_get_dofmap(pe_sequence *s, int level, int form, int32_t *ndofs, int64_t *gid, int32_t *owner,
                                int64_t *key, int64_t *true_start, int64_t *true_count, int64_t *global_count);
 /* SharingMap::Assemble (direction 0: local dof vector -> true dof vector, copies of a shared dof summed on its

@@ -52,7 +52,23 @@ def _csr(A):
             np.ascontiguousarray(A.data, dtype=np.float64))
 
 
+_THREADS = 1
+_T_CACHE = {}
+
+
+def set_threads(n):
+    """CPU-baseline timing legs only: n OpenMP threads for SpMV (rows are independent: same result) and for the
+    blocked hybrid Gauss-Seidel; A^T x goes through a cached explicit transpose (what hypre's MatvecT costs per
+    rank).  Returns the number of threads a parallel region really gets."""
+    global _THREADS
+    lib().orc_set_num_threads(int(n))
+    _THREADS = int(n)
+    _T_CACHE.clear()
+    return int(lib().orc_probe_threads())
+
+
 def matvec(A, x, alpha=1.0, beta=0.0, y=None, threads=False):
+    threads = threads or _THREADS > 1
     n, I, J, D = _csr(A)
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.zeros(n) if y is None else np.ascontiguousarray(y, dtype=np.float64).copy()
@@ -62,6 +78,11 @@ def matvec(A, x, alpha=1.0, beta=0.0, y=None, threads=False):
 
 
 def matvec_t(A, x, alpha=1.0, beta=0.0, y=None):
+    if _THREADS > 1:
+        key = id(A)
+        if key not in _T_CACHE:
+            _T_CACHE[key] = (A, sp.csr_matrix(A.T))       # keep A alive: id() stays unique
+        return matvec(_T_CACHE[key][1], x, alpha=alpha, beta=beta, y=y, threads=True)
     n, I, J, D = _csr(A)
     m = A.shape[1]
     x = np.ascontiguousarray(x, dtype=np.float64)

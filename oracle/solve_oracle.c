@@ -311,6 +311,38 @@ void orc_hypre_rand_vector(int n, int seed, double *v)
     }
 }
 
+/* thread control of the CPU-baseline timing legs (bench.py sets it explicitly: a launcher such as torchrun
+ * exports OMP_NUM_THREADS=1) */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : 1);
+#else
+    (void)n;
+#endif
+}
+int orc_get_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+/* number of threads a parallel region really gets (cgroup / affinity limits included) */
+int orc_probe_threads(void)
+{
+    int got = 1;
+#ifdef _OPENMP
+#pragma omp parallel
+    {
+#pragma omp single
+        got = omp_get_num_threads();
+    }
+#endif
+    return got;
+}
+
 /* multi-threaded SpMV used only by the CPU-baseline timing leg (rows are
  * independent, result identical to orc_csr_matvec). */
 void orc_csr_matvec_mt(int n, const int *I, const int *J, const double *A,

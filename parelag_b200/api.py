@@ -76,14 +76,19 @@ class Sequence:
         return S
 
     @staticmethod
-    def hex_par(procs, dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9):
+    def hex_par(procs, dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9, coords=None):
         """The same on THIS rank's box (dims hexahedra of extent L) of a procs[0] x procs[1] x procs[2] box
-        decomposition; needs set_host_comm()."""
+        decomposition; needs set_host_comm().  coords: optional (nv, 3) moved vertices of this rank's box."""
         S = Sequence.__new__(Sequence)
         S.h = C.c_void_p()
         a = None if alpha is None else _f64(alpha)
         b = None if beta is None else _f64(beta)
         P = _i32(procs)
+        if coords is not None:
+            X = _f64(np.ascontiguousarray(coords).ravel())
+            _chk(lib().pe_api_hexsequence_create_par_deformed(_ptr(P), dims[0], dims[1], dims[2], _ptr(X), _ptr(a), _ptr(b),
+                                                              jstart, nlevels, C.c_double(svd_tol), C.byref(S.h)))
+            return S
         _chk(lib().pe_api_hexsequence_create_par(_ptr(P), dims[0], dims[1], dims[2], C.c_double(L[0]), C.c_double(L[1]),
                                                  C.c_double(L[2]), _ptr(a), _ptr(b), jstart, nlevels,
                                                  C.c_double(svd_tol), C.byref(S.h)))
@@ -169,6 +174,32 @@ class Sequence:
         if self.h:
             lib().pe_api_sequence_free(self.h)
             self.h = None
+
+
+def rank_box(procs, rank):
+    """box coordinates of a rank in the procs[0] x procs[1] x procs[2] grid (x fastest, amge_par.hpp)"""
+    return (rank % procs[0], (rank // procs[0]) % procs[1], rank // (procs[0] * procs[1]))
+
+
+def box_vertex_coords(procs, rank_coords, dims, deform=None, domain=(1.0, 1.0, 1.0)):
+    """Vertices of one box of a procs[0] x procs[1] x procs[2] decomposition of a domain (index-grid numbering, x
+    fastest), computed from the GLOBAL vertex index so that copies of an interface vertex are bitwise equal on every
+    rank; deform: optional map of the (nv, 3) array (e.g. weak_scaling_deformation)."""
+    ax = []
+    for a in range(3):
+        ng = procs[a] * dims[a]
+        ax.append((np.arange(dims[a] + 1, dtype=np.float64) + rank_coords[a] * dims[a]) * (domain[a] / ng))
+    k, j, i = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+    X = np.stack([i.ravel(), j.ravel(), k.ravel()], axis=1)
+    return X if deform is None else deform(X)
+
+
+def weak_scaling_deformation(X):
+    """examples/3DHdivWeakScaling.cpp:148-158: y += exp(z)/2, then x += sin(y)"""
+    X = np.array(X, dtype=np.float64)
+    X[:, 1] += 0.5 * np.exp(X[:, 2])
+    X[:, 0] += np.sin(X[:, 1])
+    return X
 
 
 def library_xml(entries):

@@ -579,7 +579,9 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
     StructuredHexMesh mesh(nx, ny, nz, Lx, Ly, Lz);
     if (vertex_coords)
     {
-        PARELAG_TEST_FOR_EXCEPTION(parallel, std::runtime_error, "moved vertices are supported on a single rank");
+        // multi-rank: every rank passes the vertices of ITS box; copies of an interface vertex must be bitwise
+        // equal on the ranks that share it (compute them from the global vertex index), so that the shared facet
+        // and ridge mass matrices agree to the last bit, as they do on the reference's ParMesh
         mesh.coords.assign(vertex_coords, vertex_coords + (size_t)3 * mesh.nv());
     }
     if (parallel)

@@ -63,6 +63,19 @@ extern "C" int pe_api_hexsequence_create_par(const int32_t *procs, int nx, int n
     *out = s;
     API_CATCH
 }
+extern "C" int pe_api_hexsequence_create_par_deformed(const int32_t *procs, int nx, int ny, int nz, const double *vertex_xyz,
+                                                      const double *alpha, const double *beta, int jstart, int nlevels, double svd_tol,
+                                                      pe_sequence **out)
+{
+    API_TRY
+    PARELAG_TEST_FOR_EXCEPTION(!g_have_host_comm, std::runtime_error, "pe_api_hexsequence_create_par_deformed: call pe_api_session_set_host_comm first");
+    PARELAG_TEST_FOR_EXCEPTION(!vertex_xyz, std::runtime_error, "pe_api_hexsequence_create_par_deformed: vertex coordinates missing");
+    auto s = new pe_sequence();
+    const int P[3] = {procs[0], procs[1], procs[2]};
+    s->levels = BuildHexSequenceHierarchyPar(&g_host_comm, P, nx, ny, nz, 1.0, 1.0, 1.0, alpha, beta, jstart, nlevels, svd_tol, vertex_xyz);
+    *out = s;
+    API_CATCH
+}
 extern "C" int pe_api_sequence_get_dofmap(pe_sequence *s, int level, int form, int32_t *ndofs, int64_t *gid, int32_t *owner,
                                           int64_t *key, int64_t *true_start, int64_t *true_count, int64_t *global_count)
 {

@@ -145,6 +145,30 @@ def run_boxes(comm, rank, size):
     assert abs(D_perm - D_g).max() <= 1e-13 * abs(D_g).max()
     Dm.free()
     S.free()
+
+    # ---- T5: the 3DHdivWeakScaling geometry (trilinear hexahedra, examples/3DHdivWeakScaling.cpp:148-158) on the box
+    # decomposition: every rank builds the fine sequence of ITS box from its own vertices; the assembled H(div) operator
+    # equals the single-domain operator of the undecomposed deformed mesh
+    Lg = tuple(float(p) for p in procs)
+    X = api.box_vertex_coords(procs, api.rank_box(procs, rank), (n, n, n), api.weak_scaling_deformation, domain=Lg)
+    Sd = api.Sequence.hex_par(procs, (n, n, n), lev, jstart=1, svd_tol=-1.0, coords=X)
+    Ml, Wl, Dl = Sd.get_csr(0, "M", 2), Sd.get_csr(0, "M", 3), Sd.get_csr(0, "D", 2)
+    A_loc = sp.csr_matrix(Ml + Dl.T @ Wl @ Dl)
+    md = Sd.dofmap(0, 2)
+    assert np.array_equal(md["gid"], m["gid"])                                 # numbering does not depend on the geometry
+    Md = par.assemble(comm, 0, A_loc, md["gid"], md["owner"], md["gid"], md["owner"], rr, md["nglobal"], rr, md["nglobal"])
+    _, blk = par.parcsr_rows_to_global(Md.arrays())
+    A_true = sp.vstack([b for _, b in sorted(gather((Md.arrays()["first_row"], blk)), key=lambda t: t[0])]).tocsr()
+    mesh_d = amge.DeformedHexMesh(*N, deform=amge.weak_scaling_deformation, L=Lg)
+    assert np.array_equal(mesh_d.vertex_coords()[mesh_d.vx(*[rank_off for rank_off in (api.rank_box(procs, rank)[0] * n,
+                                                                                      api.rank_box(procs, rank)[1] * n,
+                                                                                      api.rank_box(procs, rank)[2] * n)])], X[0])
+    seq_d = amge.fine_sequence(mesh_d, jstart=1)
+    A_d = sp.csr_matrix(seq_d.mass_operator(2) + seq_d.D[2].T @ seq_d.mass_operator(3) @ seq_d.D[2])
+    A_dp = (Pm.T @ A_true @ Pm).tocsr()
+    assert abs(A_dp - A_d).max() <= 1e-13 * abs(A_d).max()
+    Md.free()
+    Sd.free()
     dist.barrier()
     if rank == 0:
         print("PAR_WORKER_OK")

@@ -10,7 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                        "--ref-n", "16", "--ref-levels", "3"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+                        "--ref-n", "16"], cwd=ROOT,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"),      # what torchrun exports: the arm must override it
+                       capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -18,6 +20,9 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "vcycle_dofs_per_s" and d["unit"] == "DOFs/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    threads = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == threads and d["cpu_baseline"]["omp_threads"] == threads
+    assert d["cpu_baseline"]["setup"]["seconds"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "DOFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

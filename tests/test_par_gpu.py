@@ -17,13 +17,14 @@ def _ngpus():
         return 0
 
 
-@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+@pytest.mark.parametrize("halo,deform", [("p2p", 0), ("nccl", 0), ("p2p", 1)])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_box_decomposed_hierarchy_matches_single_domain(nranks, halo):
-    """halo: ParCSR halo exchange over NVLink peer memory (pe_p2p.cu) or ncclSend/ncclRecv -- same checks"""
+def test_box_decomposed_hierarchy_matches_single_domain(nranks, halo, deform):
+    """halo: ParCSR halo exchange over NVLink peer memory (pe_p2p.cu) or ncclSend/ncclRecv -- same checks;
+    deform = 1: the trilinear hexahedra of examples/3DHdivWeakScaling.cpp:148-158 (BASELINE configs[4])"""
     if _ngpus() < nranks:
         pytest.skip("needs %d GPUs" % nranks)
-    env = dict(os.environ, OMP_NUM_THREADS="1", PE_TEST_HALO=halo)
+    env = dict(os.environ, OMP_NUM_THREADS="1", PE_TEST_HALO=halo, PE_TEST_DEFORM=str(deform))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nranks, "--master-addr",
            "127.0.0.1", "--master-port", str(29540 + nranks), os.path.join(ROOT, "tests", "par_gpu_worker.py")]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
