@@ -175,24 +175,42 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def product_level_operators(ctx, ns, lv):
+def product_level_operators(ctx, ns, lv, deformed=False):
     """Level operators (A0, [P_l], [D_l]) of the bounded CPU sample, taken from the PRODUCT's hierarchy of the same
-    workload (inputs of the solve path; what is timed on the CPU is the oracle V-cycle over them)."""
+    workload (inputs of the solve path; what is timed on the CPU is the oracle V-cycle over them).  deformed: one box
+    of the configs[4] geometry (the unit cube after the 3DHdivWeakScaling vertex map, essential attributes 2-5)."""
     import scipy.sparse as sp
     from parelag_b200 import api
-    Ss = api.Sequence.hex((ns, ns, ns), lv, jstart=1)
-    As = Ss.assemble_system(ctx, 0, 2, ESS).to_scipy()
+    if deformed:
+        X = api.box_vertex_coords((1, 1, 1), (0, 0, 0), (ns, ns, ns), api.weak_scaling_deformation)
+        Ss = api.Sequence.hex((ns, ns, ns), lv, jstart=1, coords=X)
+        ess = np.array([0, 1, 1, 1, 1, 0], dtype=np.int32)
+    else:
+        Ss = api.Sequence.hex((ns, ns, ns), lv, jstart=1)
+        ess = ESS
+    As = Ss.assemble_system(ctx, 0, 2, ess).to_scipy()
+    bit = sum(1 << a for a in range(6) if ess[a])
     Ps, Ds = [], []
     for l in range(lv):
         D = Ss.get_csr(l, "D", 1)
-        m = Ss.get_bdr_mask(l, 1) != 0
+        m = (Ss.get_bdr_mask(l, 1) & bit) != 0
         Ds.append(sp.csr_matrix((np.where(m[D.indices], 0.0, D.data), D.indices, D.indptr), shape=D.shape))
         if l + 1 < lv:
             P = Ss.get_csr(l, "P", 2)
-            mc = Ss.get_bdr_mask(l + 1, 2) != 0
+            mc = (Ss.get_bdr_mask(l + 1, 2) & bit) != 0
             Ps.append(sp.csr_matrix((np.where(mc[P.indices], 0.0, P.data), P.indices, P.indptr), shape=P.shape))
     Ss.free()
     return As, Ps, Ds
+
+
+def workload_name(gpus, n, ndofs_box, levels, deformed):
+    """the part of config.workload both arms share"""
+    if gpus > 1 and deformed:
+        return ("3DHdivWeakScaling (configs[4]): one box of %d^3 trilinear hexahedra per GPU (unit cube after y += exp(z)/2, "
+                "x += sin(y), essential attributes 2-5), H(div) A=M2+D2^T M3 D2, %d-level AMGe, Hiptmair(l1-GS,l1-GS), "
+                "PCG-GS coarse solver" % (n, levels))
+    return ("MultigridTest2Form (configs[1]): H(div) A=M2+D2^T M3 D2, %d^3 hexahedra, %d RT0 dofs, %d-level AMGe, "
+            "Hiptmair(l1-GS,l1-GS), PCG-GS coarse solver" % (n, ndofs_box, levels))
 
 
 def levels_for(n, cap):
@@ -228,18 +246,27 @@ def run_reference(args, rank):
     from oracle import solve as orc
     got = orc.set_threads(cores)
     assert got == cores, "OpenMP gives %d threads, %d requested" % (got, cores)
+    deformed = args.gpus > 1 and not args.no_deform     # the N > 1 arm runs configs[4]: sample = ONE box of it
     n_s = args.ref_n
+    if n_s <= 0:
+        # the full per-GPU size when the host has the memory for the oracle's copies of the hierarchy (~60 GB at 144^3)
+        avail = 0
+        try:
+            avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) >> 20
+        except Exception:
+            pass
+        n_s = args.n if avail >= 120 else 96
     inputs, src = oracle_hierarchy_inputs, "oracle"
     try:
         import torch
         if torch.cuda.is_available():
             from parelag_b200 import api
             ctx = api.session(rank=0, nranks=1, device=0)
-            inputs, src = (lambda ns, lv: product_level_operators(ctx, ns, lv)), "product"
+            inputs, src = (lambda ns, lv: product_level_operators(ctx, ns, lv, deformed)), "product"
     except Exception:
         pass
     if src == "oracle":
-        n_s = min(n_s, 32)                               # the numpy coarsening oracle: minutes beyond that
+        n_s, deformed = min(n_s, 32), False              # the numpy coarsening oracle: minutes beyond that
     levels = levels_for(n_s, args.levels)
     H, ndofs = cpu_vcycle_setup(n_s, levels, cores, inputs)
     t, done = time_cpu_vcycles(H, ndofs, args.steps, min(args.warmup, 1), budget_s=120.0)
@@ -251,9 +278,9 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "MultigridTest2Form (configs[1]): H(div) A=M2+D2^T M3 D2, %d-level AMGe, Hiptmair(l1-GS,l1-GS), "
-                                   "PCG-GS coarse solver; bounded CPU sample %d^3 hexahedra (%d RT0 dofs) of the 144^3 workload"
-                                   % (levels, n_s, ndofs)},
+            "config": {"workload": workload_name(args.gpus, n_s, ndofs, levels, deformed),
+                       "sample": "one box (%d^3 hexahedra, %d RT0 dofs) of the workload, %d host threads" % (n_s, ndofs, cores),
+                       "gs_order": "natural within a row block, one row block per thread (hypre's hybrid scheme)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "omp_threads": got, "kind": "port", "sample": sample,
                              "setup": setup},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -273,7 +300,8 @@ def main():
     ap.add_argument("--levels", type=int, default=5)
     ap.add_argument("--ordering", default="multicolor", choices=["multicolor", "natural"])
     ap.add_argument("--jstart", type=int, default=0, help="jformStart of the sequence (driver uses 0)")
-    ap.add_argument("--ref-n", type=int, default=96, help="hexahedra per direction of the CPU arm's bounded sample")
+    ap.add_argument("--ref-n", type=int, default=0,
+                    help="hexahedra per direction of the CPU arm's sample (0: --size if the host has >= 120 GB free, else 96)")
     ap.add_argument("--no-cpu-setup", action="store_true", help="skip the CPU setup baseline (oracle Coarsen on 16^3)")
     ap.add_argument("--no-deform", action="store_true", help="N > 1: axis-aligned boxes instead of the configs[4] geometry")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block")
@@ -516,22 +544,18 @@ def main():
     x_pin = torch.empty(ndofs, dtype=torch.float64).pin_memory()
     b_np, x_np = b_pin.numpy(), x_pin.numpy()
     b_np[:] = r_host
-    vsolver_xml = api.library_xml(library(args.ordering))
-    # the V-cycle as its own solver object shares nothing with the PCG solver; to avoid a second
-    # hierarchy the e2e leg times PCG's preconditioner through host buffers via a 1-iteration-free path:
-    # upload b, apply V-cycle, download x  ==  pe_api_solver_mult on the AMGe solver.  We reuse the
-    # device vectors and time upload + V-cycle + download explicitly on the context's stream.
+    # the reference-facing call: mfem::Solver::Mult(B, X) of the AMGe Hierarchy with HOST vectors
+    # (pe_api_solver_prec_mult: H2D of b from pinned memory, V-cycle, D2H of x, all inside the call)
     for _ in range(2):
-        r_dev.upload(b_np); solver.prec_mult_device(r_dev, z_dev); x_np[:] = z_dev.download()
+        solver.prec_mult_into(b_np, x_np)
     barrier()
     ctx.sync()
     ctx.timer_start()
     for _ in range(args.steps):
-        capi._chk(capi.lib().pe_vec_upload(r_dev.h, capi._ptr(b_np)))
-        solver.prec_mult_device(r_dev, z_dev)
-        capi._chk(capi.lib().pe_vec_download(z_dev.h, capi._ptr(x_np)))
+        solver.prec_mult_into(b_np, x_np)
     ms_e2e = max_over_ranks(ctx.timer_stop()) / args.steps
     e2e = {"value": ndofs_global / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "call": "pe_api_solver_prec_mult (Hierarchy::Mult with pinned host vectors)",
            "h2d_bytes_per_step": 8 * ndofs_global, "d2h_bytes_per_step": 8 * ndofs_global}
 
     # ---------------- one full PCG solve (iterations, residual history) through host buffers
@@ -559,17 +583,15 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": ("MultigridTest2Form (configs[1]): H(div) A=M2+D2^T M3 D2, %d^3 hexahedra, "
-                                        "%d RT0 dofs, %d-level AMGe, Hiptmair(l1-GS,l1-GS) %s order, PCG-GS coarse solver"
-                                        % (n, ndofs, nlev, args.ordering)) if world == 1 else
-                                       ("3DHdivWeakScaling (configs[4]): unit cube in %dx%dx%d boxes of %d^3 hexahedra, one box per GPU, %s, "
-                                        "H(div) A=M2+D2^T M3 D2, %d RT0 true dofs in total, %d-level AMGe, Hiptmair(hybrid l1-GS,"
-                                        "hybrid l1-GS) %s order, PCG-GS coarse solver, ParCSR halo exchange by %s"
-                                        % (procs + (n, "deformed: trilinear hexahedra after y += exp(z)/2, x += sin(y), essential "
-                                                       "attributes 2-5" if deformed else "axis-aligned, all attributes essential",
-                                                    ndofs_global, nlev, args.ordering,
-                                                    "NVLink peer-memory stores + device flags (CUDA IPC)" if capi.lib().pe_ctx_p2p_enabled(ctx.h)
-                                                    else "NCCL send/recv"))),
+                "config": {"workload": workload_name(world, n, ndofs, nlev, deformed) if (world == 1 or deformed) else
+                                       ("3DHdivWeakScaling layout, axis-aligned: %dx%dx%d boxes of %d^3 hexahedra, one box per GPU, all "
+                                        "attributes essential, H(div) A=M2+D2^T M3 D2, %d-level AMGe, Hiptmair(l1-GS,l1-GS), PCG-GS "
+                                        "coarse solver" % (procs + (n, nlev))),
+                           "boxes": "%dx%dx%d" % procs, "global_true_dofs": ndofs_global,
+                           "gs_order": "%s within a rank, frozen ghosts across ranks (hypre's hybrid scheme)" % args.ordering,
+                           "halo": (None if world == 1 else
+                                    "NVLink peer-memory stores + device flags (CUDA IPC)" if capi.lib().pe_ctx_p2p_enabled(ctx.h)
+                                    else "NCCL send/recv"),
                            "l2_policy": "inputs larger than L2 (hierarchy working set %.1f GB)" %
                                         (sum(12.0 * li[1] for li in level_info) / 1e9),
                            "parallelism": ("single GPU" if world == 1 else

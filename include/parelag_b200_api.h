@@ -125,6 +125,9 @@ int pe_api_solver_mult(pe_solver *s, const double *b_host, double *x_host, int n
 int pe_api_solver_mult_device(pe_solver *s, const pe_vec *b, pe_vec *x, int iterative_mode);
 /* Krylov solvers: apply the preconditioner alone (e.g. one AMGe V-cycle) on device vectors */
 int pe_api_solver_prec_mult_device(pe_solver *s, const pe_vec *b, pe_vec *x);
+/* the same with HOST buffers: mfem::Solver::Mult(B, X) of the preconditioner object (the AMGe Hierarchy,
+ * ParELAG_Hierarchy.cpp:109-136) as a host-side driver calls it; H2D of b and D2H of x inside the call */
+int pe_api_solver_prec_mult(pe_solver *s, const double *b_host, double *x_host, int n);
 /* Krylov solvers: "(B r, r)" history (what MFEM prints), iteration count, convergence flag */
 int pe_api_solver_get_history(const pe_solver *s, double *hist, int capacity, int *count,
                               int *iterations, int *converged);

@@ -263,6 +263,10 @@ class Solver:
     def prec_mult_device(self, b, x):
         _chk(lib().pe_api_solver_prec_mult_device(self.h, b.h, x.h))
 
+    def prec_mult_into(self, b, x):
+        """Mult of the preconditioner (one AMGe V-cycle) with caller-owned host buffers: H2D, V-cycle, D2H in the call."""
+        _chk(lib().pe_api_solver_prec_mult(self.h, _ptr(b), _ptr(x), self.n))
+
     def mult_into(self, b, x, iterative_mode=False):
         """Mult with caller-owned host buffers (e.g. pinned): H2D of b, D2H into x inside the call."""
         _chk(lib().pe_api_solver_mult(self.h, _ptr(b), _ptr(x), self.n, 1 if iterative_mode else 0))

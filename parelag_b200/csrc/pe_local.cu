@@ -222,11 +222,11 @@ struct TraceArgs
     int max_m;
 };
 
-__global__ void __launch_bounds__(32) k_traces(TraceArgs a)
+// sm: the CTA's workspace -- dynamic shared memory (k_traces) or, for agglomerated entities too large for it, a
+// slab of global memory (k_traces_gmem; __syncwarp/__syncthreads order global accesses inside the CTA as well)
+__device__ __forceinline__ void traces_one(const TraceArgs &a, int ae, double *sm)
 {
-    extern __shared__ double sm[];
-    const int ae = blockIdx.x, lane = threadIdx.x;
-    if (ae >= a.nAE) return;
+    const int lane = threadIdx.x;
     const int s = a.I[ae], m = a.I[ae + 1] - s, nT = a.nT, nc_max = nT + 1;
     double *X = sm;                       // m x nT column-major (ld = max_m)
     double *pvl = X + a.max_m * (nT > 0 ? nT : 1);
@@ -303,6 +303,16 @@ __global__ void __launch_bounds__(32) k_traces(TraceArgs a)
     for (int t = lane; t < nT; t += 32) sv_out[t] = t < nsv ? sv[t] : 0.0;
     if (lane == 0) { a.ndofs_out[ae] = nc; a.info_out[ae] = info; }
 }
+__global__ void __launch_bounds__(32) k_traces(TraceArgs a)
+{
+    extern __shared__ double sm[];
+    if (blockIdx.x < a.nAE) traces_one(a, blockIdx.x, sm);
+}
+__global__ void __launch_bounds__(32) k_traces_gmem(TraceArgs a, double *work, size_t stride)
+{
+    double *sm = work + (size_t)blockIdx.x * stride;
+    for (int ae = blockIdx.x; ae < a.nAE; ae += gridDim.x) { traces_one(a, ae, sm); __syncthreads(); }
+}
 
 // ---------------------------------------------------------------------------
 // extension (facet / ridge / peak)
@@ -361,11 +371,11 @@ __device__ void cta_assemble(double *Mall, int n, const PoolV &P, const int *slo
     }
 }
 
-__global__ void __launch_bounds__(LT) k_extension(ExtArgs a)
+// sm: the CTA's workspace -- dynamic shared memory (k_extension) or a slab of global memory (k_extension_gmem) for
+// agglomerates whose local matrices do not fit (coarse levels carrying many dofs per entity)
+__device__ __forceinline__ void extension_one(const ExtArgs &a, int ae, double *sm)
 {
-    extern __shared__ double sm[];
-    const int ae = blockIdx.x, tid = threadIdx.x;
-    if (ae >= a.nAE) return;
+    const int tid = threadIdx.x;
     const int us = a.uI[ae], nua = a.uI[ae + 1] - us, nui = a.uN[ae], nub = nua - nui;
     const int ps = a.pI[ae], npa = a.pI[ae + 1] - ps, npi = a.pN[ae];
     const int qs = a.facet ? 0 : a.qI[ae], nqa = a.facet ? 0 : a.qI[ae + 1] - qs;
@@ -678,6 +688,17 @@ __global__ void __launch_bounds__(LT) k_extension(ExtArgs a)
     }
     if (tid == 0) { a.k_out[ae] = k; a.info_out[ae] = info ? info : (info2 ? 1000 + info2 : 0); }
 }
+// list: the agglomerates of this launch (null: all of them)
+__global__ void __launch_bounds__(LT) k_extension(ExtArgs a, const int *__restrict__ list, int nlist)
+{
+    extern __shared__ double sm[];
+    if ((int)blockIdx.x < nlist) extension_one(a, list ? list[blockIdx.x] : (int)blockIdx.x, sm);
+}
+__global__ void __launch_bounds__(LT) k_extension_gmem(ExtArgs a, const int *__restrict__ list, int nlist, double *work, size_t stride)
+{
+    double *sm = work + (size_t)blockIdx.x * stride;
+    for (int i = blockIdx.x; i < nlist; i += gridDim.x) { extension_one(a, list[i], sm); __syncthreads(); }
+}
 
 // ---------------------------------------------------------------------------
 // host wrappers: upload the batch description, run, download the results
@@ -781,9 +802,20 @@ extern "C" int pe_batched_traces(pe_ctx *ctx, const pe_trace_batch *b)
     PE_TRY(D.alloc((size_t)b->nAE, &a.info_out));
     const int nT1 = b->nT > 0 ? b->nT : 1, ncm = b->nT + 1;
     size_t smem = sizeof(double) * ((size_t)max_m * nT1 + 2 * (size_t)max_m + nT1 + 2 * (size_t)max_m * ncm + (size_t)ncm * ncm + (size_t)max_m * ncm);
-    PE_CHECK(smem <= 200 * 1024, "pe_batched_traces: agglomerated entity too large for shared memory");
-    PE_CUDA(cudaFuncSetAttribute(k_traces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_traces<<<b->nAE, 32, smem, st>>>(a);
+    if (smem <= 200 * 1024)
+    {
+        PE_CUDA(cudaFuncSetAttribute(k_traces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_traces<<<b->nAE, 32, smem, st>>>(a);
+    }
+    else
+    {
+        // agglomerated entity too large for shared memory (coarse levels with many dofs per entity): global workspace
+        const int grid = std::min(b->nAE, 148 * 16);
+        const size_t stride = (smem / sizeof(double) + 31) & ~(size_t)31;
+        double *work = nullptr;
+        PE_TRY(D.alloc(stride * (size_t)grid, &work));
+        k_traces_gmem<<<grid, 32, 0, st>>>(a, work, stride);
+    }
     PE_LAUNCHED(ctx);
     PE_CUDA(cudaMemcpyAsync(b->out, a.out, sizeof(double) * out_n, cudaMemcpyDeviceToHost, st));
     PE_CUDA(cudaMemcpyAsync(b->ndofs_out, a.ndofs_out, sizeof(int) * (size_t)b->nAE, cudaMemcpyDeviceToHost, st));
@@ -869,27 +901,74 @@ extern "C" int pe_batched_extension(pe_ctx *ctx, const pe_extension_batch *b)
     PE_CUDA(cudaMemsetAsync(a.out, 0, sizeof(double) * out_n, st));
     PE_TRY(D.alloc((size_t)nAE, &a.k_out));
     PE_TRY(D.alloc((size_t)nAE, &a.info_out));
-    for (int e = 0; e < nAE; ++e)
+    // Workspace of one agglomerate as a function of the size bounds of its launch.  Agglomerates that fit into shared
+    // memory go to k_extension (carve-up from the maxima over THAT set); the others -- coarse levels carrying many dofs
+    // per entity, e.g. the NullSpace dofs of a deformed mesh -- to k_extension_gmem with a workspace slab in HBM.
+    struct Bounds { int mxu = 0, mxp = 0, mxq = 0, mxui = 0, mxpi = 0, mxcb = 0, mxrt = 0; };
+    auto grow = [&](Bounds &B, int e) {
+        B.mxu = std::max(B.mxu, b->uI[e + 1] - b->uI[e]); B.mxui = std::max(B.mxui, b->uNint[e]);
+        B.mxp = std::max(B.mxp, b->pI[e + 1] - b->pI[e]); B.mxpi = std::max(B.mxpi, b->pNint[e]);
+        if (!b->facet) B.mxq = std::max(B.mxq, b->qI[e + 1] - b->qI[e]);
+        B.mxcb = std::max(B.mxcb, b->cbI[e + 1] - b->cbI[e]); B.mxrt = std::max(B.mxrt, b->pnI[e + 1] - b->pnI[e]);
+    };
+    const int nTa = a.nT;
+    auto bytes_of = [nTa](const Bounds &B) -> size_t {
+        const size_t nmax = (size_t)B.mxui + B.mxpi + 1, rmax = (size_t)B.mxcb + B.mxrt + nTa, cmax = (size_t)B.mxrt + nTa, lbmax = B.mxcb + cmax;
+        const size_t nT1 = nTa > 0 ? nTa : 1;
+        // the functional / solve scratch reuses R (n x nrhs) for an nc x nui matrix and MP for nua x nlb: covered by
+        // nmax*rmax >= cmax*mxui only if rmax >= cmax (true) and nmax >= mxui (true)
+        const size_t nd = (size_t)B.mxu * B.mxu + (size_t)B.mxp * B.mxp + (size_t)B.mxp * B.mxu + (size_t)B.mxpi * B.mxu + nmax * nmax + nmax * rmax
+                          + (size_t)B.mxu * B.mxcb + (size_t)B.mxp * B.mxcb + (size_t)B.mxui * nT1 + (size_t)B.mxui * (cmax > 0 ? cmax : 1)
+                          + (size_t)std::max(B.mxu, B.mxp) * (lbmax > 0 ? lbmax : 1) + lbmax * lbmax + (size_t)B.mxq * B.mxq + 2 * (size_t)B.mxq * B.mxpi + nT1;
+        return sizeof(double) * nd + sizeof(int) * ((size_t)B.mxu + B.mxp + B.mxq + B.mxcb) + 16;
+    };
+    const size_t SMEM_LIMIT = 220 * 1024;
+    Bounds all, fit, big;
+    std::vector<int> fit_list, big_list;
+    for (int e = 0; e < nAE; ++e) grow(all, e);
+    if (bytes_of(all) > SMEM_LIMIT)
     {
-        a.mxu = std::max(a.mxu, b->uI[e + 1] - b->uI[e]); a.mxui = std::max(a.mxui, b->uNint[e]);
-        a.mxp = std::max(a.mxp, b->pI[e + 1] - b->pI[e]); a.mxpi = std::max(a.mxpi, b->pNint[e]);
-        if (!b->facet) a.mxq = std::max(a.mxq, b->qI[e + 1] - b->qI[e]);
-        a.mxcb = std::max(a.mxcb, b->cbI[e + 1] - b->cbI[e]); a.mxrt = std::max(a.mxrt, b->pnI[e + 1] - b->pnI[e]);
+        for (int e = 0; e < nAE; ++e)
+        {
+            Bounds one; grow(one, e);
+            if (bytes_of(one) <= SMEM_LIMIT) { fit_list.push_back(e); grow(fit, e); } else { big_list.push_back(e); grow(big, e); }
+        }
+        if (bytes_of(fit) > SMEM_LIMIT)      // maxima attained by different agglomerates: keep it simple
+        {
+            big_list.resize(nAE); for (int e = 0; e < nAE; ++e) big_list[e] = e;
+            fit_list.clear(); big = all;
+        }
     }
-    const size_t nmax = (size_t)a.mxui + a.mxpi + 1, rmax = (size_t)a.mxcb + a.mxrt + a.nT, cmax = (size_t)a.mxrt + a.nT, lbmax = a.mxcb + cmax;
-    const size_t nT1 = a.nT > 0 ? a.nT : 1;
-    size_t nd = (size_t)a.mxu * a.mxu + (size_t)a.mxp * a.mxp + (size_t)a.mxp * a.mxu + (size_t)a.mxpi * a.mxu + nmax * nmax + nmax * rmax
-                + (size_t)a.mxu * a.mxcb + (size_t)a.mxp * a.mxcb + (size_t)a.mxui * nT1 + (size_t)a.mxui * (cmax > 0 ? cmax : 1)
-                + (size_t)std::max(a.mxu, a.mxp) * (lbmax > 0 ? lbmax : 1) + lbmax * lbmax + (size_t)a.mxq * a.mxq + 2 * (size_t)a.mxq * a.mxpi + nT1;
-    size_t smem = sizeof(double) * nd + sizeof(int) * ((size_t)a.mxu + a.mxp + a.mxq + a.mxcb) + 16;
-    // the functional / solve scratch reuses R (n x nrhs) for an nc x nui matrix and MP for nua x nlb: covered by
-    // nmax*rmax >= cmax*mxui only if rmax >= cmax (true) and nmax >= mxui (true)
-    PE_CHECK(smem <= 220 * 1024, "pe_batched_extension: agglomerate too large for shared memory ("
-                                     + std::to_string(smem) + " bytes needed)");
-    PE_CUDA(cudaFuncSetAttribute(k_extension, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto set_bounds = [&](const Bounds &B) { a.mxu = B.mxu; a.mxp = B.mxp; a.mxq = B.mxq; a.mxui = B.mxui; a.mxpi = B.mxpi; a.mxcb = B.mxcb; a.mxrt = B.mxrt; };
     PE_CUDA(cudaStreamSynchronize(st));
     const double t_up = now_s();
-    k_extension<<<nAE, LT, smem, st>>>(a);
+    if (big_list.empty())
+    {
+        set_bounds(all);
+        const size_t smem = bytes_of(all);
+        PE_CUDA(cudaFuncSetAttribute(k_extension, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_extension<<<nAE, LT, smem, st>>>(a, nullptr, nAE);
+    }
+    else
+    {
+        const int *list_d = nullptr;
+        if (!fit_list.empty())
+        {
+            set_bounds(fit);
+            const size_t smem = bytes_of(fit);
+            PE_TRY(D.up(fit_list.data(), fit_list.size(), &list_d));
+            PE_CUDA(cudaFuncSetAttribute(k_extension, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_extension<<<(int)fit_list.size(), LT, smem, st>>>(a, list_d, (int)fit_list.size());
+            PE_LAUNCHED(ctx);
+        }
+        set_bounds(big);
+        const size_t stride = (bytes_of(big) / sizeof(double) + 31) & ~(size_t)31;
+        const int grid = std::min((int)big_list.size(), 148 * 4);
+        double *work = nullptr;
+        PE_TRY(D.alloc(stride * (size_t)grid, &work));
+        PE_TRY(D.up(big_list.data(), big_list.size(), &list_d));
+        k_extension_gmem<<<grid, LT, 0, st>>>(a, list_d, (int)big_list.size(), work, stride);
+    }
     PE_LAUNCHED(ctx);
     PE_CUDA(cudaStreamSynchronize(st));
     const double t_kern = now_s();

@@ -473,6 +473,21 @@ extern "C" int pe_api_solver_prec_mult_device(pe_solver *s, const pe_vec *b, pe_
     PE_CALL(pe_vec_copy(s->x.Read(), x));
     API_CATCH
 }
+/// mfem::Solver::Mult of the PRECONDITIONER held by a Krylov solver (the AMGe Hierarchy: one V-cycle,
+/// Hierarchy.cpp:109-136) with HOST vectors: H2D of b, V-cycle, D2H of x inside the call -- what a driver that keeps its
+/// vectors on the host pays per preconditioner application.
+extern "C" int pe_api_solver_prec_mult(pe_solver *s, const double *b, double *x, int n)
+{
+    API_TRY
+    auto k = dynamic_cast<const KrylovSolver *>(s->solver.get());
+    PARELAG_TEST_FOR_EXCEPTION(!k || !k->GetPreconditioner(), std::runtime_error, "pe_api_solver_prec_mult: not a preconditioned Krylov solver");
+    PARELAG_TEST_FOR_EXCEPTION(n != s->solver->Height(), std::runtime_error, "pe_api_solver_prec_mult: wrong vector length");
+    s->b.SetSize(n); s->x.SetSize(n);
+    PE_CALL(pe_vec_upload(s->b.Write(), b));
+    k->GetPreconditioner()->Mult(s->b, s->x);
+    PE_CALL(pe_vec_download(s->x.Read(), x));
+    API_CATCH
+}
 extern "C" int pe_api_solver_get_history(const pe_solver *s, double *hist, int capacity, int *count, int *iterations, int *converged)
 {
     API_TRY
