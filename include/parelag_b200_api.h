@@ -121,6 +121,9 @@ int pe_api_solver_build_device(const char *xml_library, const char *solver_name,
 /* solver->Mult(B, X) with HOST buffers (H2D of b, D2H of x inside the call);
  * iterative_mode != 0 uses x as initial guess */
 int pe_api_solver_mult(pe_solver *s, const double *b_host, double *x_host, int n, int iterative_mode);
+/* solver->MultTranspose(B, X) with host buffers (HiptmairSmoother::MultTranspose, ParELAG_HiptmairSmoother.cpp:79-109;
+ * solvers without a transpose throw not_implemented_error like the reference) */
+int pe_api_solver_mult_transpose(pe_solver *s, const double *b_host, double *x_host, int n, int iterative_mode);
 /* solver->Mult on device-resident vectors (no copies) */
 int pe_api_solver_mult_device(pe_solver *s, const pe_vec *b, pe_vec *x, int iterative_mode);
 /* Krylov solvers: apply the preconditioner alone (e.g. one AMGe V-cycle) on device vectors */
@@ -128,7 +131,8 @@ int pe_api_solver_prec_mult_device(pe_solver *s, const pe_vec *b, pe_vec *x);
 /* the same with HOST buffers: mfem::Solver::Mult(B, X) of the preconditioner object (the AMGe Hierarchy,
  * ParELAG_Hierarchy.cpp:109-136) as a host-side driver calls it; H2D of b and D2H of x inside the call */
 int pe_api_solver_prec_mult(pe_solver *s, const double *b_host, double *x_host, int n);
-/* Krylov solvers: "(B r, r)" history (what MFEM prints), iteration count, convergence flag */
+/* Krylov solvers: "(B r, r)" history (what MFEM prints), iteration count, convergence flag; StationarySolver
+ * (ParELAG_StationarySolver.cpp:41-147): ||r_k|| per iteration */
 int pe_api_solver_get_history(const pe_solver *s, double *hist, int capacity, int *count,
                               int *iterations, int *converged);
 /* Hierarchy solvers: number of levels, and size / nnz of A on a level */

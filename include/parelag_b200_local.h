@@ -44,6 +44,13 @@ typedef struct pe_trace_batch {
     const int32_t *I, *J;       /* agglomerated entity -> fine dofs                   */
     const double *pv;           /* PV trace vector (ndofs)                            */
     const double *diagM;        /* agglomerate mass matrix diagonal, per (AE,dof) slot */
+    /* agglomerated entities whose mass matrix is NOT diagonal (coarse levels with several dofs per entity): the dense
+     * m x m block (row-major, symmetric) starts at denseM[dense_off[ae]]; dense_off[ae] < 0 = diagonal (diagM).  Such an
+     * entity takes SVD_Calculator::ComputeON(DenseMatrix&W, ...) (ParELAG_SVDCalculator.cpp:258-284): symmetric
+     * eigendecomposition of W (SymEigensolver::ComputeAll), X = W^{1/2}, SVD of X A, back-transform by W^{-1/2}.
+     * Both may be NULL when every entity is diagonal. */
+    const double *denseM;
+    const long long *dense_off;
     int32_t nT, ldT;            /* targets: column-major ldT x nT                     */
     const double *T;
     double svd_tol;             /* SVD_Tolerance_ (relative to pv.M.pv)               */

@@ -289,6 +289,48 @@ class Hiptmair:
         return x + matvec(self.Dm, auxx)
 
 
+    def apply_transpose(self, b, x, iterative_mode=True):
+        """HiptmairSmoother::MultTranspose (HiptmairSmoother.cpp:79-109): auxiliary correction first (from B itself in
+        preconditioner mode, from the residual otherwise), then the primary sweep."""
+        if not iterative_mode:
+            x = np.zeros_like(x)
+            auxb = matvec_t(self.Dm, b)
+        else:
+            auxb = matvec_t(self.Dm, matvec(self.A, x, alpha=-1.0, beta=1.0, y=b))
+        auxx = self.aux.apply(auxb, np.zeros(self.Dm.shape[1]), False)
+        x = x + matvec(self.Dm, auxx)
+        return self.primary.apply(b, x, True)
+
+
+def stationary(A, corrector, b, rtol=0.0, atol=0.0, max_iter=1, x0=None):
+    """StationarySolver::Mult (ParELAG_StationarySolver.cpp:41-147): x += S r, r -= A (S r) (the residual is updated,
+    not recomputed); stops on ||r|| < atol, accumulated ratio < rtol, a zero correction, or max_iter.
+    corrector(r) -> S r from a zero initial guess.  Returns (x, iterations, converged, [||r_k||])."""
+    b = np.asarray(b, dtype=np.float64)
+    if x0 is None:
+        x, r = np.zeros_like(b), b.copy()
+    else:
+        x = np.array(x0, dtype=np.float64)
+        r = -matvec(A, x) + b
+    nk1 = float(np.sqrt(r @ r))
+    hist, its, ratio, conv = [nk1], 0, 1.0, False
+    while its < max_iter:
+        its += 1
+        c = corrector(r)
+        x = x + c
+        r = r - matvec(A, c)
+        nk = float(np.sqrt(r @ r))
+        hist.append(nk)
+        ratio *= nk / nk1
+        if nk < atol or ratio < rtol:
+            conv = True
+            break
+        if nk / nk1 == 1.0:
+            break
+        nk1 = nk
+    return x, its, conv, hist
+
+
 class Hierarchy:
     """parelag::Hierarchy: levels[l] = dict(A=, P= (to level l from l+1, stored on l+1
     in the reference; here stored on the finer level l as 'P'), pre=, post=), coarsest

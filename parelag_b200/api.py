@@ -257,6 +257,12 @@ class Solver:
         _chk(lib().pe_api_solver_mult(self.h, _ptr(b), _ptr(x), self.n, 0 if x0 is None else 1))
         return x
 
+    def mult_transpose(self, b, x0=None):
+        b = _f64(b)
+        x = np.zeros(self.n) if x0 is None else _f64(x0).copy()
+        _chk(lib().pe_api_solver_mult_transpose(self.h, _ptr(b), _ptr(x), self.n, 0 if x0 is None else 1))
+        return x
+
     def mult_device(self, b, x, iterative_mode=False):
         _chk(lib().pe_api_solver_mult_device(self.h, b.h, x.h, 1 if iterative_mode else 0))
 

@@ -205,6 +205,71 @@ __device__ int cta_dof_functional(const double *P, int nu, int nc, int ldp, cons
     return cta_lu_solve(cM, nc, nc, F, nu, nu, s_piv, tid, nt);
 }
 
+// Symmetric eigendecomposition W = V diag(lambda) V^T by cyclic Jacobi rotations, one warp
+// (SymEigensolver::ComputeAll -- dsyevx in the reference, ParELAG_Eigensolver.cpp:57-135; every use on this path goes
+// through W^{1/2} and W^{-1/2}, which do not depend on the choice of eigenvectors inside a cluster).
+// W: m x m row-major, overwritten (diagonal = eigenvalues on exit); V: m x m row-major, columns = eigenvectors.
+__device__ void warp_jacobi_eig(double *W, double *V, int m, int lane)
+{
+    for (int i = lane; i < m * m; i += 32) V[i] = (i / m == i % m) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 60; ++sweep)
+    {
+        double off = 0.0;
+        for (int p = 0; p < m - 1; ++p)
+            for (int q = p + 1; q < m; ++q)
+            {
+                const double apq = W[p * m + q], app = W[p * m + p], aqq = W[q * m + q];
+                if (apq == 0.0) continue;
+                const double r = fabs(apq) / sqrt(fabs(app * aqq));
+                if (r > off) off = r;
+                if (r < 1e-17) { __syncwarp(); if (lane == 0) { W[p * m + q] = 0.0; W[q * m + p] = 0.0; } __syncwarp(); continue; }
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(1.0 + theta * theta));
+                const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                __syncwarp();                                   // everybody has read app, aqq, apq
+                for (int k = lane; k < m; k += 32)              // columns p, q  (W <- W J)
+                {
+                    const double wkp = W[k * m + p], wkq = W[k * m + q];
+                    W[k * m + p] = c * wkp - sn * wkq; W[k * m + q] = sn * wkp + c * wkq;
+                    const double vkp = V[k * m + p], vkq = V[k * m + q];
+                    V[k * m + p] = c * vkp - sn * vkq; V[k * m + q] = sn * vkp + c * vkq;
+                }
+                __syncwarp();
+                for (int k = lane; k < m; k += 32)              // rows p, q  (W <- J^T W)
+                {
+                    const double wpk = W[p * m + k], wqk = W[q * m + k];
+                    W[p * m + k] = c * wpk - sn * wqk; W[q * m + k] = sn * wpk + c * wqk;
+                }
+                __syncwarp();
+            }
+        if (off < 1e-15) break;
+    }
+}
+// x <- V diag(f(lambda)) V^T x for the columns of X (m x k column-major, ldx); f = sqrt (inv = false) or 1/sqrt;
+// y: scratch of m doubles; lambda = diagonal of Wd
+__device__ void warp_apply_sqrt(const double *V, const double *Wd, int m, double *X, int k, int ldx, double *y, bool inv, int lane)
+{
+    for (int t = 0; t < k; ++t)
+    {
+        for (int c = lane; c < m; c += 32)
+        {
+            double s = 0.0;
+            for (int i = 0; i < m; ++i) s += V[i * m + c] * X[t * ldx + i];
+            const double l = sqrt(Wd[c * m + c]);
+            y[c] = inv ? s / l : s * l;
+        }
+        __syncwarp();
+        for (int i = lane; i < m; i += 32)
+        {
+            double s = 0.0;
+            for (int c = 0; c < m; ++c) s += V[i * m + c] * y[c];
+            X[t * ldx + i] = s;
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------
 // traces
 // ---------------------------------------------------------------------------
@@ -213,6 +278,9 @@ struct TraceArgs
     int nAE;
     const int *I, *J;
     const double *pv, *diagM;     // pv per fine dof; diagM per ADof
+    const double *denseM;         // dense mass blocks of the entities that have one (dense_off[ae] >= 0)
+    const long long *dense_off;
+    int max_md;                   // largest such block
     int nT, ldT;
     const double *T;
     double svd_tol;
@@ -235,28 +303,60 @@ __device__ __forceinline__ void traces_one(const TraceArgs &a, int ae, double *s
     double *Pl = sv + (nT > 0 ? nT : 1);  // m x nc_max column-major (ld = max_m)
     double *MP = Pl + a.max_m * nc_max;
     double *cM = MP + a.max_m * nc_max;
+    double *Mm = cM + nc_max * nc_max;        // dense entities only: mass block, working copy, eigenvectors, scratch
+    double *Me = Mm + a.max_md * a.max_md;
+    double *V = Me + a.max_md * a.max_md;
+    double *ys = V + a.max_md * a.max_md;
     __shared__ int s_piv;
     const int ld = a.max_m;
+    const bool dense = a.dense_off && a.dense_off[ae] >= 0;
     double pvMpv = 0.0;
-    for (int i = lane; i < m; i += 32)
+    if (dense)
     {
-        const int d = a.J[s + i];
-        pvl[i] = a.pv[d]; dg[i] = a.diagM[s + i];
-        pvMpv += pvl[i] * dg[i] * pvl[i];
-        for (int t = 0; t < nT; ++t) X[t * ld + i] = a.T[(size_t)t * a.ldT + d];
+        const double *Mg = a.denseM + a.dense_off[ae];
+        for (int i = lane; i < m * m; i += 32) { const double v = Mg[i]; Mm[i] = v; Me[i] = v; }
+        for (int i = lane; i < m; i += 32)
+        {
+            const int d = a.J[s + i];
+            pvl[i] = a.pv[d];
+            for (int t = 0; t < nT; ++t) X[t * ld + i] = a.T[(size_t)t * a.ldT + d];
+        }
+        __syncwarp();
+        for (int i = lane; i < m; i += 32)            // dg <- M pv (scratch)
+        {
+            double sacc = 0.0;
+            for (int c = 0; c < m; ++c) sacc += Mm[i * m + c] * pvl[c];
+            dg[i] = sacc;
+            pvMpv += pvl[i] * sacc;
+        }
     }
+    else
+        for (int i = lane; i < m; i += 32)
+        {
+            const int d = a.J[s + i];
+            pvl[i] = a.pv[d]; dg[i] = a.diagM[s + i];
+            pvMpv += pvl[i] * dg[i] * pvl[i];
+            for (int t = 0; t < nT; ++t) X[t * ld + i] = a.T[(size_t)t * a.ldT + d];
+        }
     for (int o = 16; o > 0; o >>= 1) pvMpv += __shfl_xor_sync(0xffffffffu, pvMpv, o);
     __syncwarp();
-    // Deflate: t += (-(pv.M.t)/(pv.M.pv)) pv ; then scale rows by sqrt(diag M)
+    // Deflate: t += (-(pv.M.t)/(pv.M.pv)) pv ; then the weighted SVD: rows scaled by sqrt(diag M), or X = M^{1/2}
     const double sc = -1.0 / pvMpv;
     for (int t = 0; t < nT; ++t)
     {
         double dot = 0.0;
-        for (int i = lane; i < m; i += 32) dot += pvl[i] * dg[i] * X[t * ld + i];
+        if (dense) for (int i = lane; i < m; i += 32) dot += dg[i] * X[t * ld + i];
+        else for (int i = lane; i < m; i += 32) dot += pvl[i] * dg[i] * X[t * ld + i];
         for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        for (int i = lane; i < m; i += 32) X[t * ld + i] = (X[t * ld + i] + (dot * sc) * pvl[i]) * sqrt(dg[i]);
+        if (dense) for (int i = lane; i < m; i += 32) X[t * ld + i] = X[t * ld + i] + (dot * sc) * pvl[i];
+        else for (int i = lane; i < m; i += 32) X[t * ld + i] = (X[t * ld + i] + (dot * sc) * pvl[i]) * sqrt(dg[i]);
     }
     __syncwarp();
+    if (dense && nT > 0)
+    {
+        warp_jacobi_eig(Me, V, m, lane);
+        warp_apply_sqrt(V, Me, m, X, nT, ld, ys, false, lane);
+    }
     if (nT > 0) warp_jacobi_svd(X, m, nT, ld, sv, lane);
     const double s_max_tol = pvMpv * a.svd_tol;
     int k = 0;
@@ -264,24 +364,37 @@ __device__ __forceinline__ void traces_one(const TraceArgs &a, int ae, double *s
     while (k < nsv && !(sv[k] < s_max_tol)) ++k;
     const int nc = k + 1;
     const double sq = sqrt(pvMpv);
+    if (dense && k > 0) warp_apply_sqrt(V, Me, m, X, k, ld, ys, true, lane);
     for (int i = lane; i < m; i += 32)
     {
         Pl[i] = pvl[i];
-        for (int c = 0; c < k; ++c) Pl[(c + 1) * ld + i] = X[c * ld + i] / sqrt(dg[i]) * sq;
+        if (dense) for (int c = 0; c < k; ++c) Pl[(c + 1) * ld + i] = X[c * ld + i];
+        else for (int c = 0; c < k; ++c) Pl[(c + 1) * ld + i] = X[c * ld + i] / sqrt(dg[i]);
     }
     __syncwarp();
-    // canonical sign again after the inverse row scaling (largest |entry| may have moved)
+    // canonical sign again after the inverse scaling (largest |entry| may have moved), then the scaling by sqrt(pv.M.pv)
     for (int c = 1; c < nc; ++c)
     {
         const int bi = warp_sign_pivot(Pl + c * ld, m, lane);
-        if (Pl[c * ld + bi] < 0.0) for (int i = lane; i < m; i += 32) Pl[c * ld + i] = -Pl[c * ld + i];
+        const double sg = Pl[c * ld + bi] < 0.0 ? -sq : sq;
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) Pl[c * ld + i] *= sg;
         __syncwarp();
     }
     double *out = a.out + a.out_off[ae];
     double *p_out = out, *mass_out = out + (size_t)m * nc_max, *func_out = mass_out + nc_max * nc_max, *sv_out = func_out + (size_t)nc_max * m;
     for (int idx = lane; idx < m * nc; idx += 32) { int i = idx % m, c = idx / m; p_out[c * m + i] = Pl[c * ld + i]; }
-    // mass = P^T diag(M) P (symmetrised), functional = (P^T M P)^{-1} P^T M
-    for (int idx = lane; idx < m * nc; idx += 32) { int i = idx % m, c = idx / m; MP[c * m + i] = dg[i] * Pl[c * ld + i]; }
+    // mass = P^T M P (symmetrised), functional = (P^T M P)^{-1} P^T M
+    if (dense)
+        for (int idx = lane; idx < m * nc; idx += 32)
+        {
+            int i = idx % m, c = idx / m;
+            double sacc = 0.0;
+            for (int q = 0; q < m; ++q) sacc += Mm[i * m + q] * Pl[c * ld + q];
+            MP[c * m + i] = sacc;
+        }
+    else
+        for (int idx = lane; idx < m * nc; idx += 32) { int i = idx % m, c = idx / m; MP[c * m + i] = dg[i] * Pl[c * ld + i]; }
     __syncwarp();
     for (int idx = lane; idx < nc * nc; idx += 32)
     {
@@ -793,6 +906,23 @@ extern "C" int pe_batched_traces(pe_ctx *ctx, const pe_trace_batch *b)
     PE_TRY(D.up(b->J, (size_t)nadof, &a.J));
     PE_TRY(D.up(b->pv, (size_t)b->ndofs, &a.pv));
     PE_TRY(D.up(b->diagM, (size_t)nadof, &a.diagM));
+    a.max_md = 0;
+    if (b->denseM && b->dense_off)
+    {
+        size_t total = 0;
+        for (int e = 0; e < b->nAE; ++e)
+            if (b->dense_off[e] >= 0)
+            {
+                const int m = b->I[e + 1] - b->I[e];
+                a.max_md = std::max(a.max_md, m);
+                total = std::max(total, (size_t)b->dense_off[e] + (size_t)m * m);
+            }
+        if (a.max_md > 0)
+        {
+            PE_TRY(D.up(b->denseM, total, &a.denseM));
+            PE_TRY(D.up(b->dense_off, (size_t)b->nAE, (const long long **)&a.dense_off));
+        }
+    }
     PE_TRY(D.upc(b->T, (size_t)b->ldT * b->nT, &a.T));
     PE_TRY(D.up(b->out_off, (size_t)b->nAE + 1, (const long long **)&a.out_off));
     const size_t out_n = (size_t)b->out_off[b->nAE];
@@ -801,7 +931,8 @@ extern "C" int pe_batched_traces(pe_ctx *ctx, const pe_trace_batch *b)
     PE_TRY(D.alloc((size_t)b->nAE, &a.ndofs_out));
     PE_TRY(D.alloc((size_t)b->nAE, &a.info_out));
     const int nT1 = b->nT > 0 ? b->nT : 1, ncm = b->nT + 1;
-    size_t smem = sizeof(double) * ((size_t)max_m * nT1 + 2 * (size_t)max_m + nT1 + 2 * (size_t)max_m * ncm + (size_t)ncm * ncm + (size_t)max_m * ncm);
+    size_t smem = sizeof(double) * ((size_t)max_m * nT1 + 2 * (size_t)max_m + nT1 + 2 * (size_t)max_m * ncm + (size_t)ncm * ncm + (size_t)max_m * ncm
+                                    + 3 * (size_t)a.max_md * a.max_md + (size_t)a.max_md);
     if (smem <= 200 * 1024)
     {
         PE_CUDA(cudaFuncSetAttribute(k_traces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -197,13 +197,20 @@ struct Coarsener
         }
         Timer tprep = TimeManager::AddTimer("Coarsen: traces prepare (host)");
         const std::vector<double> pv = pv_traces(S, codim);
-        // agglomerate mass matrix: the entities of codimension `codim` carry disjoint dofs,
-        // so M_d is block diagonal with the entity blocks; the GPU path needs it diagonal
+        // agglomerate mass matrix M_d: the entities of codimension `codim` carry disjoint dofs, so the block of an
+        // agglomerated entity is block diagonal with the blocks of its members.  Diagonal blocks take the row-scaled
+        // SVD (SVDCalculator.cpp:247-256); an agglomerated entity with a member block that has a non-zero off-diagonal
+        // entry (coarse levels with several dofs per entity: the coarse trace mass is (pv.M.pv) I only up to rounding)
+        // takes the dense-weighted SVD (:258-284) like the reference (IsDiagonal, DeRhamSequence.cpp:1857-1868)
         const BlockPool &Me = S.M.at({j, codim});
         const auto rdoff = Me.rdof_offsets();
         std::vector<double> diagM(ag.J[codim].size(), 0.0);
+        std::vector<long long> dense_off(nAE, -1);
+        std::vector<double> denseM;
         const HostCSR &AEe = S.topo->AEntityEntity(codim);
         for (int a = 0; a < nAE; ++a)
+        {
+            bool dense = false;
             for (int k = AEe.I[a]; k < AEe.I[a + 1]; ++k)
             {
                 const int e = AEe.J[k], m = Me.size[e];
@@ -212,11 +219,23 @@ struct Coarsener
                     for (int y = 0; y < m; ++y)
                     {
                         if (x == y) diagM[ag.I[codim][a] + ag.slot[codim][rdoff[e] + x]] += blk[x * m + x];
-                        else
-                            PARELAG_TEST_FOR_EXCEPTION(std::fabs(blk[x * m + y]) > 1e-10 * std::fabs(blk[x * m + x]), not_implemented_error,
-                                                       "ComputeCoarseTraces: non-diagonal trace mass matrix (dense-weighted SVD) is not available on the GPU path");
+                        else if (blk[x * m + y] != 0.0) dense = true;
                     }
             }
+            if (!dense) continue;
+            const int s0 = ag.I[codim][a], ma = ag.I[codim][a + 1] - s0;
+            dense_off[a] = (long long)denseM.size();
+            denseM.resize(denseM.size() + (size_t)ma * ma, 0.0);
+            double *Md = denseM.data() + dense_off[a];
+            for (int k = AEe.I[a]; k < AEe.I[a + 1]; ++k)
+            {
+                const int e = AEe.J[k], m = Me.size[e];
+                const double *blk = Me.block(e);
+                for (int x = 0; x < m; ++x)
+                    for (int y = 0; y < m; ++y)
+                        Md[(size_t)ag.slot[codim][rdoff[e] + x] * ma + ag.slot[codim][rdoff[e] + y]] += blk[x * m + y];
+            }
+        }
         const int nT = S.ntargets[j];
         std::vector<long long> off(nAE + 1, 0);
         for (int a = 0; a < nAE; ++a)
@@ -228,7 +247,9 @@ struct Coarsener
         std::vector<int> ndofs(nAE);
         pe_trace_batch b{};
         b.nAE = nAE; b.ndofs = S.dof[j]->ndofs; b.I = ag.I[codim].data(); b.J = ag.J[codim].data();
-        b.pv = pv.data(); b.diagM = diagM.data(); b.nT = nT; b.ldT = S.dof[j]->ndofs; b.T = S.targets[j].data();
+        b.pv = pv.data(); b.diagM = diagM.data(); b.nT = nT;
+        if (!denseM.empty()) { b.denseM = denseM.data(); b.dense_off = dense_off.data(); }
+        C->stats["trace_dense_mass_" + std::to_string(j)] = (long long)std::count_if(dense_off.begin(), dense_off.end(), [](long long o) { return o >= 0; }); b.ldT = S.dof[j]->ndofs; b.T = S.targets[j].data();
         b.svd_tol = S.svd_tol; b.out_off = off.data(); b.out = out.data(); b.ndofs_out = ndofs.data();
         tprep.Stop();
         {

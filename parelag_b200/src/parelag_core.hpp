@@ -274,6 +274,7 @@ private:
     {
         if (type == "bool") pl.Set(name, value == "true" || value == "1");
         else if (type == "int") pl.Set(name, std::stoi(value));
+        else if (type == "size_t") pl.Set(name, (size_t)std::stoull(value));   // ParELAG_SimpleXMLParameterListReader.cpp:244
         else if (type == "double") pl.Set(name, std::stod(value));
         else if (type == "string") pl.Set(name, value);
         else if (type == "vector(int)" || type == "vector_int")

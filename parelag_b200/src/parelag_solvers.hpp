@@ -1049,65 +1049,102 @@ class AMGeSolverFactory : public SolverFactory
 };
 
 // ------------------------------------------------------------------ Stationary iteration
+/// ParELAG_StationarySolver.cpp:41-147: Richardson iteration x += S r with any Solver S as corrector.  The residual is
+/// UPDATED (r -= A c), not recomputed; at least one correction is applied; stops when ||r_k|| < atol, when the
+/// accumulated ratio ||r_k|| / ||r_0|| < rtol, on a zero correction (||r_k|| / ||r_{k-1}|| == 1), or after MaxIts.
 class StationarySolver : public Solver
 {
 public:
-    StationarySolver(Op_Ptr A, std::shared_ptr<mfem::Solver> S, double rtol, double atol, int maxit, bool print)
+    StationarySolver(Op_Ptr A, std::shared_ptr<mfem::Solver> S, double rtol, double atol, size_t maxit, bool print)
         : Solver(A->Height(), A->Width(), true), A_(std::move(A)), Solver_(std::move(S)), RelTol_(rtol), AbsTol_(atol), MaxIts_(maxit), Print_(print) {}
     void Mult(const mfem::Vector &rhs, mfem::Vector &sol) const override
     {
-        const int n = Height();
-        Resid_.SetSize(n); Corr_.SetSize(n);
-        if (this->IsPreconditioner()) sol = 0.0;
-        auto A_hyp = std::dynamic_pointer_cast<mfem::HypreParMatrix>(A_);
-        mg_utils::ComputeResidual(*A_hyp, sol, rhs, Resid_);
-        double r0 = std::sqrt(Resid_ * Resid_), r = r0;
-        int it = 0;
-        while (it < MaxIts_ && r > std::max(RelTol_ * r0, AbsTol_))
+        Solver_->iterative_mode = false;
+        Resid_.SetSize(A_->Height()); Corr_.SetSize(A_->Width()); Tmp_.SetSize(A_->Height());
+        if (this->IsPreconditioner()) { Resid_ = rhs; sol = 0.0; }
+        else { A_->Mult(sol, Resid_); Resid_ *= -1.0; Resid_ += rhs; }
+        double norm_k_1 = std::sqrt(Resid_ * Resid_), norm_k = norm_k_1, norm_ratio = 1.0;      // Vector dot = global sum
+        History_.assign(1, norm_k_1);
+        if (Print_) std::cout << "    Iteration 0: ||r|| = " << norm_k_1 << std::endl;
+        size_t its = 0;
+        Converged_ = false;
+        while (its < MaxIts_)
         {
-            const bool mode = Solver_->iterative_mode;
-            Solver_->iterative_mode = false;
+            ++its;
+            Corr_ = 0.0; Tmp_ = 0.0;
             Solver_->Mult(Resid_, Corr_);
-            Solver_->iterative_mode = mode;
             sol += Corr_;
-            mg_utils::ComputeResidual(*A_hyp, sol, rhs, Resid_);
-            r = std::sqrt(Resid_ * Resid_);
-            ++it;
-            if (Print_) std::printf("  Stationary iteration %3d : ||r|| = %g\n", it, r);
+            A_->Mult(Corr_, Tmp_);
+            Resid_ -= Tmp_;
+            norm_k = std::sqrt(Resid_ * Resid_);
+            History_.push_back(norm_k);
+            norm_ratio *= norm_k / norm_k_1;
+            if (Print_) std::cout << "    Iteration " << its << ": ||r|| = " << norm_k << "  (" << norm_ratio << ")" << std::endl;
+            if (norm_k < AbsTol_ || norm_ratio < RelTol_) { Converged_ = true; break; }
+            if (norm_k / norm_k_1 == 1.0) { std::cout << "WARNING: Computed a zero correction! Stopping..." << std::endl; break; }
+            norm_k_1 = norm_k;
         }
-        NumIts_ = it; FinalNorm_ = r;
+        NumIts_ = (int)its; FinalNorm_ = norm_k;
+        if (Print_)
+            std::cout << '\n' << std::string(50, '*') << '\n' << "*  Solver Status: " << (Converged_ ? "Converged" : "Not converged") << '\n'
+                      << "*  Solver Iterations: " << its << '\n' << "*  Final norm: " << norm_k << '\n' << std::string(50, '*') << std::endl;
     }
+    void MultTranspose(const mfem::Vector &, mfem::Vector &) const override { PARELAG_NOT_IMPLEMENTED(); }
     int GetNumIterations() const { return NumIts_; }
     double GetFinalNorm() const { return FinalNorm_; }
+    bool GetConverged() const { return Converged_; }
+    /// ||r_k||, k = 0, 1, ... (what "Print Iterations" prints)
+    const std::vector<double> &GetResidualHistory() const { return History_; }
 private:
     void _do_set_operator(const Op_Ptr &op) override { A_ = op; }
     Op_Ptr A_;
     std::shared_ptr<mfem::Solver> Solver_;
     double RelTol_, AbsTol_;
-    int MaxIts_;
+    size_t MaxIts_;
     bool Print_;
-    mutable mfem::Vector Resid_, Corr_;
+    mutable mfem::Vector Resid_, Corr_, Tmp_;
+    mutable std::vector<double> History_;
     mutable int NumIts_ = 0;
     mutable double FinalNorm_ = 0.0;
+    mutable bool Converged_ = false;
 };
 
+/// ParELAG_StationarySolverFactory.hpp:27-107 (parameters "Solver", "Maximum Iterations" (size_t, default 1),
+/// "Absolute Tolerance", "Relative Tolerance", "Print Iterations")
 class StationarySolverFactory : public SolverFactory
 {
     std::unique_ptr<mfem::Solver> _do_build_solver(const Op_Ptr &op, SolverState &state) const override
     {
+        PARELAG_ASSERT(Fact_);
         auto my_state = dynamic_cast<NestedSolverState *>(&state);
         PARELAG_ASSERT(my_state);
         auto s_state = std::shared_ptr<SolverState>{Fact_->GetDefaultState()};
+        if (my_state->IsSubState("Solver")) s_state->MergeState(*my_state->GetSubState("Solver"));
         s_state->MergeState(*my_state);
         std::shared_ptr<mfem::Solver> s = Fact_->BuildSolver(op, *s_state);
+        s->iterative_mode = false;
         auto &p = GetParameters();
-        return make_unique<StationarySolver>(op, s, p.Get("Relative tolerance", 0.0), p.Get("Absolute tolerance", 0.0),
-                                             p.Get("Maximum iterations", 10), p.Get("Print level", -1) > 0);
+        return make_unique<StationarySolver>(op, s, p.Get<double>("Relative Tolerance"), p.Get<double>("Absolute Tolerance"),
+                                             MaxIterations(p), p.Get<bool>("Print Iterations"));
     }
-    void _do_set_default_parameters() override {}
+    /// "Maximum Iterations" is a size_t in the reference; an XML file may also carry it as "int"
+    static size_t MaxIterations(ParameterList &p)
+    {
+        try { return p.Get<size_t>("Maximum Iterations"); }
+        catch (const std::exception &) { return (size_t)std::max(p.Get<int>("Maximum Iterations"), 0); }
+    }
+    void _do_set_default_parameters() override
+    {
+        auto &p = GetParameters();
+        if (!p.IsParameter("Maximum Iterations")) p.Set("Maximum Iterations", (size_t)1);
+        p.Get("Absolute Tolerance", 0.0);
+        p.Get("Relative Tolerance", 0.0);
+        p.Get("Print Iterations", false);
+    }
     void _do_initialize(const ParameterList &) override
     {
-        Fact_ = GetSolverLibrary().GetSolverFactory(GetParameters().Get<std::string>("Solver"));
+        PARELAG_ASSERT(HasValidSolverLibrary());
+        Fact_ = GetSolverLibrary().GetSolverFactory(GetParameters().Get("Solver", "INVALID"));
     }
     std::shared_ptr<SolverFactory> Fact_;
 };

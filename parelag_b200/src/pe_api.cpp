@@ -441,6 +441,21 @@ extern "C" int pe_api_solver_mult(pe_solver *s, const double *b, double *x, int 
     PE_CALL(pe_vec_download(s->x.Read(), x));
     API_CATCH
 }
+/// solver->MultTranspose(B, X) with host buffers (e.g. HiptmairSmoother::MultTranspose, HiptmairSmoother.cpp:79-109)
+extern "C" int pe_api_solver_mult_transpose(pe_solver *s, const double *b, double *x, int n, int iterative_mode)
+{
+    API_TRY
+    PARELAG_TEST_FOR_EXCEPTION(n != s->solver->Height(), std::runtime_error, "pe_api_solver_mult_transpose: wrong vector length");
+    s->b.SetSize(n); s->x.SetSize(n);
+    PE_CALL(pe_vec_upload(s->b.Write(), b));
+    if (iterative_mode) PE_CALL(pe_vec_upload(s->x.Write(), x));
+    const bool saved = s->solver->iterative_mode;
+    s->solver->iterative_mode = iterative_mode != 0;
+    s->solver->MultTranspose(s->b, s->x);
+    s->solver->iterative_mode = saved;
+    PE_CALL(pe_vec_download(s->x.Read(), x));
+    API_CATCH
+}
 namespace
 {
 // a non-owning mfem::Vector over an existing pe_vec
@@ -491,8 +506,18 @@ extern "C" int pe_api_solver_prec_mult(pe_solver *s, const double *b, double *x,
 extern "C" int pe_api_solver_get_history(const pe_solver *s, double *hist, int capacity, int *count, int *iterations, int *converged)
 {
     API_TRY
+    if (auto st = dynamic_cast<const StationarySolver *>(s->solver.get()))
+    {
+        // StationarySolver: ||r_k|| per iteration (what "Print Iterations" prints)
+        const auto &h = st->GetResidualHistory();
+        if (count) *count = (int)h.size();
+        for (int i = 0; i < capacity && i < (int)h.size(); ++i) hist[i] = h[i];
+        if (iterations) *iterations = st->GetNumIterations();
+        if (converged) *converged = st->GetConverged() ? 1 : 0;
+        return 0;
+    }
     auto k = dynamic_cast<const KrylovSolver *>(s->solver.get());
-    PARELAG_TEST_FOR_EXCEPTION(!k, std::runtime_error, "pe_api_solver_get_history: not a Krylov solver");
+    PARELAG_TEST_FOR_EXCEPTION(!k, std::runtime_error, "pe_api_solver_get_history: not a Krylov or stationary solver");
     const auto &h = k->GetResidualHistory();
     if (count) *count = (int)h.size();
     for (int i = 0; i < capacity && i < (int)h.size(); ++i) hist[i] = h[i];

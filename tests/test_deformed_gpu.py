@@ -55,3 +55,40 @@ def test_deformed_mesh_coarsen_matches_oracle_and_reference_golden():
     # (oracle: singular values 1, 1.5e-2, 2e-12 of a residual of norm 1.1e-2): determined to ~1e-16 / 1.6e-4 * cond
     compare_levels(S, seqs, tol=1e-10, null_tol=1e-8)
     S.free()
+
+
+def test_deformed_mesh_hcurl_levels_take_the_dense_weighted_trace_svd():
+    """Three levels with forms 1-3 on the deformed mesh and variable coefficients: on level 1 the agglomerated edges
+    and facets carry several dofs per member entity, their trace mass block is no longer diagonal, and
+    ComputeCoarseTraces takes SVD_Calculator::ComputeON(DenseMatrix&W, ...) (ParELAG_SVDCalculator.cpp:258-284:
+    SymEigensolver::ComputeAll, X = W^{1/2}) -- in the product a Jacobi eigensolver inside k_traces.  The large local
+    problems of level 1 also take the global-workspace variant of the extension kernel."""
+    api.session()
+    dims, nlev = (4, 4, 4), 3
+    rng = np.random.default_rng(11)
+    alpha, beta = rng.uniform(0.5, 2.0, 64), 10.0 ** rng.uniform(-1, 1, 64)
+    dense = {"n": 0}
+    orig = amge.svd_on_weighted
+
+    def spy(M, A):
+        dense["n"] += int(np.any(M - np.diag(np.diag(M))))
+        return orig(M, A)
+    amge.svd_on_weighted = spy
+    try:
+        mesh, seqs = amge.build_hierarchy(dims, nlev, jstart=1, alpha=alpha, beta=beta, deform=amge.weak_scaling_deformation)
+    finally:
+        amge.svd_on_weighted = orig
+    assert dense["n"] > 0                                       # the oracle really takes the dense-weighted path
+    S = api.Sequence.hex(dims, nlev, jstart=1, alpha=alpha, beta=beta, coords=mesh.vertex_coords())
+    assert S.stat(2, "trace_dense_mass_1") + S.stat(2, "trace_dense_mass_2") == dense["n"]
+    compare_levels(S, seqs, tol=1e-10, null_tol=1e-7)
+    # CheckInvariants on the product's own operators (DeRhamSequence.cpp:694-970)
+    for l in range(nlev - 1):
+        for j in (1, 2, 3):
+            P = S.get_csr(l, "P", j)
+            Mf, Mc = S.get_csr(l, "M", j), S.get_csr(l + 1, "M", j)
+            assert abs(Mc - P.T @ Mf @ P).max() <= 1e-11 * abs(Mc).max(), ("M_c = P^T M P", l, j)
+            if j < 3:
+                Df, Dc, Pn = S.get_csr(l, "D", j), S.get_csr(l + 1, "D", j), S.get_csr(l, "P", j + 1)
+                assert abs(Df @ P - Pn @ Dc).max() <= 1e-11 * max(abs(Df @ P).max(), 1.0), ("D P = P D", l, j)
+    S.free()

@@ -188,3 +188,68 @@ def test_other_krylov_solvers(sess, hier, name):
     assert (np.abs(hist[:m] - ho)[sel] / ho[sel]).max() < 1e-8
     assert np.linalg.norm(x - xo) <= 1e-6 * np.linalg.norm(xo)
     solver.free()
+
+
+def test_stationary_solver_matches_reference_iteration(sess, hier):
+    """"Stationary Iteration" factory (ParELAG_StationarySolverFactory.hpp:27-107) around an l1-Jacobi corrector:
+    ||r_k|| history, iteration count and stopping rule of ParELAG_StationarySolver.cpp:41-147 (updated residual, at
+    least one correction, accumulated-ratio test) against the oracle's restatement."""
+    mesh, seqs = hier
+    ess = np.ones(6, dtype=np.int32)
+    A, marker = drivers.system_matrix(seqs[0], 0, ess)
+    rng = np.random.default_rng(23)
+    b = rng.standard_normal(A.shape[0]); b[marker] = 0.0
+    So = orc.Smoother(A, type=1)
+    corr = lambda r: So.apply(r, np.zeros_like(r), False)
+    for rtol, maxit in ((0.0, 7), (0.3, 200)):
+        xo, ito, convo, histo = orc.stationary(A, corr, b, rtol=rtol, atol=0.0, max_iter=maxit)
+        lib = {"L1J": ("Hypre", {"Type": "L1 Jacobi", "Sweeps": 1}),
+               "SI": ("Stationary Iteration", {"Solver": "L1J", "Maximum Iterations": maxit, "Relative Tolerance": rtol,
+                                               "Absolute Tolerance": 0.0, "Print Iterations": False})}
+        solver = api.Solver(api.library_xml(lib), "SI", A, None, 0, 0, ess)
+        x = solver.mult(b)
+        hist, it, conv = solver.history()
+        assert it == ito and conv == convo and len(hist) == len(histo), (it, ito, conv, convo)
+        assert np.max(np.abs(hist - np.array(histo)) / np.array(histo)) < 1e-12
+        assert np.linalg.norm(x - xo) <= 1e-12 * np.linalg.norm(xo)
+        # solver mode (initial guess given): the residual of the guess starts the iteration
+        x1 = solver.mult(b, x0=xo)
+        xo1 = orc.stationary(A, corr, b, rtol=rtol, atol=0.0, max_iter=maxit, x0=xo)[0]
+        assert np.linalg.norm(x1 - xo1) <= 1e-12 * np.linalg.norm(xo1)
+        solver.free()
+    # the default is ONE iteration (factory default "Maximum Iterations" = 1)
+    lib = {"L1J": ("Hypre", {"Type": "L1 Jacobi", "Sweeps": 1}), "SI": ("Stationary Iteration", {"Solver": "L1J"})}
+    solver = api.Solver(api.library_xml(lib), "SI", A, None, 0, 0, ess)
+    x = solver.mult(b)
+    assert solver.history()[1] == 1 and np.linalg.norm(x - corr(b)) <= 1e-13 * np.linalg.norm(x)
+    solver.free()
+
+
+def test_hiptmair_mult_transpose(sess, hier):
+    """HiptmairSmoother::MultTranspose (ParELAG_HiptmairSmoother.cpp:79-109): auxiliary-space correction first, primary
+    sweep last; preconditioner mode restricts B itself, solver mode the residual."""
+    mesh, seqs = hier
+    ess = np.ones(6, dtype=np.int32)
+    for form in (1, 2):
+        A, marker = drivers.system_matrix(seqs[0], form, ess)
+        D = seqs[0].get_D(form - 1, ess)
+        kw = lambda M: dict(type=1)
+        Ho = orc.Hiptmair(A, D, kw, kw)
+        lib = {"L1J": ("Hypre", {"Type": "L1 Jacobi", "Sweeps": 1}),
+               "HIP": ("Hiptmair", {"Primary Smoother": "L1J", "Auxiliary Smoother": "L1J"})}
+        S = make_sequence(seqs[:1])
+        solver = api.Solver(api.library_xml(lib), "HIP", A, S, 0, form, ess)
+        rng = np.random.default_rng(31 + form)
+        b = rng.standard_normal(A.shape[0]); b[marker] = 0.0
+        x0 = rng.standard_normal(A.shape[0]); x0[marker] = 0.0
+        xt = solver.mult_transpose(b)
+        xo = Ho.apply_transpose(b, np.zeros_like(b), False)
+        assert np.linalg.norm(xt - xo) <= 1e-12 * np.linalg.norm(xo), form
+        xt = solver.mult_transpose(b, x0=x0)
+        xo = Ho.apply_transpose(b, x0, True)
+        assert np.linalg.norm(xt - xo) <= 1e-12 * np.linalg.norm(xo), form
+        # and it is the transpose sequence, not Mult
+        xm = solver.mult(b, x0=x0)
+        assert np.linalg.norm(xm - Ho.apply(b, x0, True)) <= 1e-12 * np.linalg.norm(xm)
+        assert np.linalg.norm(xm - xt) > 1e-6 * np.linalg.norm(xm)
+        solver.free(); S.free()
