@@ -97,9 +97,14 @@ int pe_ctx_profile_get(pe_ctx *ctx, int kernel_id, int64_t *count, double *total
  * Read when a smoother is created.
  * PE_TUNE_P2P_HALO [1]: multi-rank, one node: ParCSR halo exchange by direct stores into the neighbours' ghost
  * buffers over NVLink peer memory (CUDA IPC) with device-side arrival flags instead of ncclSend/ncclRecv.
- * Read at pe_ctx_set_host_comm; falls back to NCCL when a rank cannot map a peer. */
+ * Read at pe_ctx_set_host_comm; falls back to NCCL when a rank cannot map a peer.
+ * PE_TUNE_FUSED_GS_MAX_MB [24]: a multicolour Gauss-Seidel sweep whose LARGEST colour moves fewer algorithmic megabytes than
+ * this runs as ONE persistent cooperative kernel (all colours of the forward and backward pass, grid barriers in
+ * between, the colour-order renumbering of the SELL path included) instead of one launch per colour: on the coarse
+ * levels a colour is a few thousand rows and a launch costs more than its work.  0 = one launch per colour.
+ * Results are bit-identical (same rows, same summation order).  Read when a smoother is created. */
 enum { PE_TUNE_SELL_MIN_ROWS = 0, PE_TUNE_SELL_GROUP = 1, PE_TUNE_PDL = 2, PE_TUNE_GATHER_KEEP_PCT = 3, PE_TUNE_P2P_HALO = 4,
-       PE_TUNE_COUNT = 6 };
+       PE_TUNE_FUSED_GS_MAX_MB = 5, PE_TUNE_COUNT = 6 };
 int pe_set_tuning(int key, int value);
 int pe_get_tuning(int key);
 /* write a scratch buffer larger than L2 (bench hygiene) */

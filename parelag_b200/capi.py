@@ -134,6 +134,7 @@ TUNE_SELL_GROUP = 1
 TUNE_PDL = 2
 TUNE_GATHER_KEEP_PCT = 3
 TUNE_P2P_HALO = 4
+TUNE_FUSED_GS_MAX_MB = 5
 
 
 def set_tuning(key, value):

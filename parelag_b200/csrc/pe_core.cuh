@@ -229,7 +229,10 @@ int pe_p2p_link(pe_mat *A);
 void pe_p2p_unlink(pe_mat *A);
 int pe_p2p_push(pe_mat *A, int dir, const double *src);
 int pe_p2p_wait(pe_mat *A, int dir);
-int pe_rap_distributed(pe_ctx *ctx, const pe_mat *A, const pe_mat *P, pe_mat **Ac);
+int pe_rap_distributed(pe_ctx *ctx, const pe_mat *R, const pe_mat *A, const pe_mat *P, pe_mat **Ac);
+int pe_spgemm_distributed(pe_ctx *ctx, const pe_mat *A, const pe_mat *B, pe_mat **C);
+int pe_transpose_distributed(pe_ctx *ctx, const pe_mat *A, pe_mat **out);
+int pe_spadd_distributed(pe_ctx *ctx, double a, const pe_mat *A, double b, const pe_mat *B, pe_mat **out);
 int pe_spmv_t_distributed(pe_ctx *ctx, double alpha, pe_mat *A, const pe_vec *x, double beta, pe_vec *y);
 int pe_launch_unpack_add(pe_ctx *ctx, pe_mat *A, double alpha, double *y_d);
 int pe_reverse_halo_add(pe_mat *A, double alpha, double *y_d);

@@ -1,6 +1,7 @@
 // pe_par.cu -- device side of the multi-rank path: ParCSR transpose-SpMV with the reverse halo
-// exchange (hypre_ParCSRMatrixMatvecT) and the distributed Galerkin product P^T A P
-// (hypre_BoomerAMGBuildCoarseOperator behind mfem::RAP, Hierarchy.cpp:365).
+// exchange (hypre_ParCSRMatrixMatvecT), the distributed Galerkin product R^T A P
+// (hypre_BoomerAMGBuildCoarseOperator behind mfem::RAP, Hierarchy.cpp:365,400-544), the distributed product A B
+// (hypre_ParMatmul behind mfem::ParMult), transpose and a A + b B (hypre_ParCSRMatrixAdd2).
 //
 // Distributed RAP = local device SpGEMMs on an extended index space + one row exchange:
 //   1. fetch the rows of P that belong to A's ghost columns (neighbour exchange, host comm);
@@ -117,24 +118,49 @@ static int exchange(const pe_host_comm *hc, const std::vector<std::vector<char>>
 template <class T> static void put(std::vector<char> &b, const T &v) { const char *c = (const char *)&v; b.insert(b.end(), c, c + sizeof(T)); }
 
 // ---------------------------------------------------------------------------------------------
-// distributed P^T A P
+// extended product  A^ B^  (the common first half of hypre_ParMatmul and of the Galerkin product):
+//   rows of B that belong to A's ghost columns are fetched from their owners; B^ = [own rows ; fetched rows] with the
+//   columns [own columns of B | G], G = sorted union of all ghost columns; A^ = [A_diag | A_offd]
 // ---------------------------------------------------------------------------------------------
-int pe_rap_distributed(pe_ctx *ctx, const pe_mat *A, const pe_mat *P, pe_mat **Ac)
+struct ExtProduct
+{
+    DevCSR AB;                       // nA x (ncl + |G|)
+    std::vector<int64_t> G, cstart;  // ghost columns (global ids, ascending); column ownership ranges of B
+    int ncl = 0;
+    int64_t c0 = 0, c1 = 0;
+    int nce() const { return ncl + (int)G.size(); }
+    void col_ids(int me, std::vector<int64_t> &gid, std::vector<int32_t> &own) const
+    {
+        gid.resize((size_t)nce()); own.assign((size_t)nce(), me);
+        for (int j = 0; j < ncl; ++j) gid[j] = c0 + j;
+        for (size_t j = 0; j < G.size(); ++j)
+        {
+            gid[ncl + j] = G[j];
+            own[ncl + j] = (int32_t)(std::upper_bound(cstart.begin(), cstart.end(), G[j]) - cstart.begin()) - 1;
+        }
+    }
+};
+
+static int col_partition(const pe_host_comm *hc, const pe_mat *M, std::vector<int64_t> &start)
+{
+    start.assign((size_t)hc->size + 1, 0);
+    int64_t mine = M->first_col_diag;
+    PE_CHECK(hc->allgather(hc->user, &mine, (int64_t)sizeof(int64_t), start.data()) == 0, "host communicator: allgather failed");
+    start[hc->size] = M->global_num_cols;
+    return 0;
+}
+
+static int ext_product(pe_ctx *ctx, const pe_mat *A, const pe_mat *B, ExtProduct &X)
 {
     const pe_host_comm *hc = ctx->hcomm;
-    PE_CHECK(hc, "distributed RAP needs a host communicator (pe_ctx_set_host_comm)");
-    PE_CHECK(A->diag.nrows == A->diag.ncols && A->diag.ncols == P->diag.nrows, "pe_rap: size mismatch");
+    PE_CHECK(hc, "distributed sparse products need a host communicator (pe_ctx_set_host_comm)");
+    PE_CHECK(A->diag.ncols == B->diag.nrows, "distributed product: size mismatch");
     cudaStream_t st = ctx->stream;
-    const int np = hc->size, me = hc->rank;
-    const int nA = A->diag.nrows, ngA = A->offd.ncols, ncl = P->diag.ncols;
-    // ownership ranges of the coarse space
-    std::vector<int64_t> cstart((size_t)np + 1);
-    {
-        int64_t mine = P->first_col_diag;
-        PE_CHECK(hc->allgather(hc->user, &mine, (int64_t)sizeof(int64_t), cstart.data()) == 0, "host communicator: allgather failed");
-        cstart[np] = P->global_num_cols;
-    }
-    // 1. rows of P the neighbours need (their ghost columns of A = my send_map_elmts), as (len, [gcol, val]...)
+    const int np = hc->size;
+    const int nA = A->diag.nrows, nB = B->diag.nrows, ngA = A->offd.ncols, ncl = B->diag.ncols;
+    X.ncl = ncl; X.c0 = B->first_col_diag; X.c1 = X.c0 + ncl;
+    PE_TRY(col_partition(hc, B, X.cstart));
+    // 1. rows of B the neighbours need (their ghost columns of A = my send_map_elmts), as (len, [gcol, val]...)
     std::vector<std::vector<char>> send(np), recv;
     {
         const int nsend = A->send_map_starts.empty() ? 0 : A->send_map_starts.back();
@@ -142,7 +168,7 @@ int pe_rap_distributed(pe_ctx *ctx, const pe_mat *A, const pe_mat *P, pe_mat **A
         std::vector<int32_t> I, J; std::vector<double> V;
         if (nsend > 0)
         {
-            PE_TRY(merge_rows(ctx, P->diag, P->offd, A->send_map_d, nsend, nullptr, ncl, ncl + P->offd.ncols, sel));
+            PE_TRY(merge_rows(ctx, B->diag, B->offd, A->send_map_d, nsend, nullptr, ncl, ncl + B->offd.ncols, sel));
             PE_TRY(download_csr(ctx, sel, I, J, V));
             devcsr_free(sel);
         }
@@ -154,15 +180,16 @@ int pe_rap_distributed(pe_ctx *ctx, const pe_mat *A, const pe_mat *P, pe_mat **A
                 put<int64_t>(b, (int64_t)(I[k + 1] - I[k]));
                 for (int q = I[k]; q < I[k + 1]; ++q)
                 {
-                    const int64_t g = J[q] < ncl ? P->first_col_diag + J[q] : P->col_map_offd[(size_t)(J[q] - ncl)];
+                    const int64_t g = J[q] < ncl ? B->first_col_diag + J[q] : B->col_map_offd[(size_t)(J[q] - ncl)];
                     put<int64_t>(b, g); put<double>(b, V[q]);
                 }
             }
         }
         PE_TRY(exchange(hc, send, recv));
     }
-    // 2. ghost coarse columns G = P's own ghosts + those of the fetched rows
-    std::vector<int64_t> G(P->col_map_offd.begin(), P->col_map_offd.end());
+    // 2. ghost columns G = B's own ghosts + those of the fetched rows
+    std::vector<int64_t> &G = X.G;
+    G.assign(B->col_map_offd.begin(), B->col_map_offd.end());
     std::vector<int32_t> eI(1, 0);
     std::vector<int64_t> eG; std::vector<double> eV;
     for (size_t r = 0; r < A->recv_procs.size(); ++r)
@@ -177,71 +204,197 @@ int pe_rap_distributed(pe_ctx *ctx, const pe_mat *A, const pe_mat *P, pe_mat **A
             eI.push_back((int32_t)eG.size());
             ++rows;
         }
-        PE_CHECK(rows == A->recv_vec_starts[r + 1] - A->recv_vec_starts[r], "pe_rap: neighbour sent a wrong number of P rows");
+        PE_CHECK(rows == A->recv_vec_starts[r + 1] - A->recv_vec_starts[r], "distributed product: neighbour sent a wrong number of rows");
     }
-    PE_CHECK((int)eI.size() - 1 == ngA, "pe_rap: fetched P rows do not cover A's ghost columns");
-    const int64_t c0 = P->first_col_diag, c1 = c0 + ncl;
+    PE_CHECK((int)eI.size() - 1 == ngA, "distributed product: fetched rows do not cover the left factor's ghost columns");
+    const int64_t c0 = X.c0, c1 = X.c1;
     for (int64_t g : eG) if (g < c0 || g >= c1) G.push_back(g);
     std::sort(G.begin(), G.end());
     G.erase(std::unique(G.begin(), G.end()), G.end());
-    const int ng = (int)G.size(), nce = ncl + ng;
+    const int nce = X.nce();
     auto gpos = [&](int64_t g) { return ncl + (int)(std::lower_bound(G.begin(), G.end(), g) - G.begin()); };
-    std::vector<int32_t> omap(P->col_map_offd.size()), eJ(eG.size());
-    for (size_t j = 0; j < omap.size(); ++j) omap[j] = gpos(P->col_map_offd[j]);
+    std::vector<int32_t> omap(B->col_map_offd.size()), eJ(eG.size());
+    for (size_t j = 0; j < omap.size(); ++j) omap[j] = gpos(B->col_map_offd[j]);
     for (size_t q = 0; q < eG.size(); ++q) eJ[q] = (eG[q] >= c0 && eG[q] < c1) ? (int32_t)(eG[q] - c0) : gpos(eG[q]);
-    // 3. P^ = [own rows ; fetched rows] on the device
+    // 3. B^ = [own rows ; fetched rows] on the device
     int *omap_d = nullptr;
     PE_CUDA(cudaMalloc(&omap_d, sizeof(int) * (omap.size() ? omap.size() : 1)));
     if (!omap.empty()) PE_CUDA(cudaMemcpyAsync(omap_d, omap.data(), sizeof(int) * omap.size(), cudaMemcpyHostToDevice, st));
-    DevCSR Ploc, Phat, Ahat, AP, PlocT, C;
-    PE_TRY(merge_rows(ctx, P->diag, P->offd, nullptr, nA, omap_d, 0, nce, Ploc));
+    DevCSR Bloc, Bhat, Ahat;
+    PE_TRY(merge_rows(ctx, B->diag, B->offd, nullptr, nB, omap_d, 0, nce, Bloc));
     PE_CUDA(cudaStreamSynchronize(st));
     cudaFree(omap_d);
     {
         const int64_t nnz_ext = (int64_t)eG.size();
-        PE_TRY(devcsr_alloc(Phat, nA + ngA, nce, Ploc.nnz + nnz_ext));
-        PE_CUDA(cudaMemcpyAsync(Phat.I, Ploc.I, sizeof(int) * (size_t)(nA + 1), cudaMemcpyDeviceToDevice, st));
-        if (Ploc.nnz)
+        PE_TRY(devcsr_alloc(Bhat, nB + ngA, nce, Bloc.nnz + nnz_ext));
+        PE_CUDA(cudaMemcpyAsync(Bhat.I, Bloc.I, sizeof(int) * (size_t)(nB + 1), cudaMemcpyDeviceToDevice, st));
+        if (Bloc.nnz)
         {
-            PE_CUDA(cudaMemcpyAsync(Phat.J, Ploc.J, sizeof(int) * (size_t)Ploc.nnz, cudaMemcpyDeviceToDevice, st));
-            PE_CUDA(cudaMemcpyAsync(Phat.A, Ploc.A, sizeof(double) * (size_t)Ploc.nnz, cudaMemcpyDeviceToDevice, st));
+            PE_CUDA(cudaMemcpyAsync(Bhat.J, Bloc.J, sizeof(int) * (size_t)Bloc.nnz, cudaMemcpyDeviceToDevice, st));
+            PE_CUDA(cudaMemcpyAsync(Bhat.A, Bloc.A, sizeof(double) * (size_t)Bloc.nnz, cudaMemcpyDeviceToDevice, st));
         }
         std::vector<int32_t> eIs(eI.begin() + 1, eI.end());
-        for (auto &v : eIs) v += (int32_t)Ploc.nnz;
-        if (ngA) PE_CUDA(cudaMemcpyAsync(Phat.I + nA + 1, eIs.data(), sizeof(int) * (size_t)ngA, cudaMemcpyHostToDevice, st));
+        for (auto &v : eIs) v += (int32_t)Bloc.nnz;
+        if (ngA) PE_CUDA(cudaMemcpyAsync(Bhat.I + nB + 1, eIs.data(), sizeof(int) * (size_t)ngA, cudaMemcpyHostToDevice, st));
         if (nnz_ext)
         {
-            PE_CUDA(cudaMemcpyAsync(Phat.J + Ploc.nnz, eJ.data(), sizeof(int) * (size_t)nnz_ext, cudaMemcpyHostToDevice, st));
-            PE_CUDA(cudaMemcpyAsync(Phat.A + Ploc.nnz, eV.data(), sizeof(double) * (size_t)nnz_ext, cudaMemcpyHostToDevice, st));
+            PE_CUDA(cudaMemcpyAsync(Bhat.J + Bloc.nnz, eJ.data(), sizeof(int) * (size_t)nnz_ext, cudaMemcpyHostToDevice, st));
+            PE_CUDA(cudaMemcpyAsync(Bhat.A + Bloc.nnz, eV.data(), sizeof(double) * (size_t)nnz_ext, cudaMemcpyHostToDevice, st));
         }
         PE_CUDA(cudaStreamSynchronize(st));
     }
-    // 4. A^ = [A_diag | A_offd], C^ = Ploc^T (A^ P^)
-    PE_TRY(merge_rows(ctx, A->diag, A->offd, nullptr, nA, nullptr, nA, nA + ngA, Ahat));
-    PE_TRY(pe_devcsr_spgemm(ctx, Ahat, Phat, AP));
-    devcsr_free(Ahat); devcsr_free(Phat);
-    PE_TRY(pe_devcsr_transpose(ctx, Ploc, PlocT));
-    devcsr_free(Ploc);
-    PE_TRY(pe_devcsr_spgemm(ctx, PlocT, AP, C));
-    devcsr_free(PlocT); devcsr_free(AP);
-    // 5. assemble: ghost rows go to their owners
+    devcsr_free(Bloc);
+    // 4. A^ = [A_diag | A_offd];  AB = A^ B^
+    PE_TRY(merge_rows(ctx, A->diag, A->offd, nullptr, nA, nullptr, nB, nB + ngA, Ahat));
+    PE_TRY(pe_devcsr_spgemm(ctx, Ahat, Bhat, X.AB));
+    devcsr_free(Ahat); devcsr_free(Bhat);
+    return 0;
+}
+
+// local CSR on extended index spaces -> ParCSR (rows: global ids / owners; mode 0 = contributions to rows of other ranks
+// are sent to their owners and summed, 1 = all rows are mine)
+static int finish_parcsr(pe_ctx *ctx, DevCSR &C, int mode, const std::vector<int64_t> &rgid, const std::vector<int32_t> &rown,
+                         const std::vector<int64_t> &cgid, const std::vector<int32_t> &cown, int64_t r0, int64_t r1, int64_t rglob,
+                         int64_t c0, int64_t c1, int64_t cglob, pe_mat **out)
+{
     std::vector<int32_t> CI, CJ; std::vector<double> CA;
     PE_TRY(download_csr(ctx, C, CI, CJ, CA));
     devcsr_free(C);
-    std::vector<int64_t> gid((size_t)nce);
-    std::vector<int32_t> own((size_t)nce, me);
-    for (int j = 0; j < ncl; ++j) gid[j] = c0 + j;
-    for (int j = 0; j < ng; ++j)
-    {
-        gid[ncl + j] = G[j];
-        own[ncl + j] = (int32_t)(std::upper_bound(cstart.begin(), cstart.end(), G[j]) - cstart.begin()) - 1;
-    }
     pe_parcsr_owned *M = nullptr;
-    PE_TRY(pe_par_assemble(hc, 0, nce, nce, CI.data(), CJ.data(), CA.data(), gid.data(), own.data(), gid.data(), own.data(),
-                           c0, c1, P->global_num_cols, c0, c1, P->global_num_cols, &M));
-    const int rc = pe_mat_upload(ctx, pe_parcsr_owned_view(M), Ac);
+    PE_TRY(pe_par_assemble(ctx->hcomm, mode, (int32_t)rgid.size(), (int32_t)cgid.size(), CI.data(), CJ.data(), CA.data(), rgid.data(), rown.data(),
+                           cgid.data(), cown.data(), r0, r1, rglob, c0, c1, cglob, &M));
+    const int rc = pe_mat_upload(ctx, pe_parcsr_owned_view(M), out);
     pe_parcsr_owned_free(M);
     return rc;
+}
+static void own_rows(const pe_mat *A, int me, std::vector<int64_t> &gid, std::vector<int32_t> &own)
+{
+    gid.resize((size_t)A->diag.nrows); own.assign((size_t)A->diag.nrows, me);
+    for (int i = 0; i < A->diag.nrows; ++i) gid[i] = A->first_row_index + i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C = A B for distributed operands (hypre_ParMatmul behind mfem::ParMult, SchurComplementFactory.cpp:133)
+// ---------------------------------------------------------------------------------------------
+int pe_spgemm_distributed(pe_ctx *ctx, const pe_mat *A, const pe_mat *B, pe_mat **C)
+{
+    ExtProduct X;
+    PE_TRY(ext_product(ctx, A, B, X));
+    std::vector<int64_t> rgid, cgid; std::vector<int32_t> rown, cown;
+    own_rows(A, ctx->hcomm->rank, rgid, rown);
+    X.col_ids(ctx->hcomm->rank, cgid, cown);
+    return finish_parcsr(ctx, X.AB, 1, rgid, rown, cgid, cown, A->first_row_index, A->first_row_index + A->diag.nrows, A->global_num_rows,
+                         X.c0, X.c1, B->global_num_cols, C);
+}
+
+// ---------------------------------------------------------------------------------------------
+// distributed R^T A P (hypre_BoomerAMGBuildCoarseOperator behind mfem::RAP; R = P: Hierarchy.cpp:365, R != P: the
+// off-diagonal blocks of the blocked hierarchy, Hierarchy.cpp:400-544):
+//   C^ = (R^ own rows)^T (A^ P^), R^ = [R_diag | R_offd]; rows of C^ that belong to ghost coarse dofs of R are
+//   contributions to other ranks' rows: Assemble sends them to their owners and sums
+// ---------------------------------------------------------------------------------------------
+int pe_rap_distributed(pe_ctx *ctx, const pe_mat *R, const pe_mat *A, const pe_mat *P, pe_mat **Ac)
+{
+    const pe_host_comm *hc = ctx->hcomm;
+    PE_CHECK(hc, "distributed RAP needs a host communicator (pe_ctx_set_host_comm)");
+    if (!R) R = P;
+    PE_CHECK(R->diag.nrows == A->diag.nrows && A->diag.ncols == P->diag.nrows, "pe_rap: size mismatch");
+    ExtProduct X;
+    PE_TRY(ext_product(ctx, A, P, X));
+    const int ncr = R->diag.ncols, ngr = R->offd.ncols;
+    DevCSR Rloc, RlocT, C;
+    PE_TRY(merge_rows(ctx, R->diag, R->offd, nullptr, R->diag.nrows, nullptr, ncr, ncr + ngr, Rloc));
+    PE_TRY(pe_devcsr_transpose(ctx, Rloc, RlocT));
+    devcsr_free(Rloc);
+    PE_TRY(pe_devcsr_spgemm(ctx, RlocT, X.AB, C));
+    devcsr_free(RlocT); devcsr_free(X.AB);
+    std::vector<int64_t> rstart;
+    PE_TRY(col_partition(hc, R, rstart));
+    std::vector<int64_t> rgid((size_t)ncr + ngr), cgid;
+    std::vector<int32_t> rown((size_t)ncr + ngr, hc->rank), cown;
+    for (int j = 0; j < ncr; ++j) rgid[j] = R->first_col_diag + j;
+    for (int j = 0; j < ngr; ++j)
+    {
+        rgid[ncr + j] = R->col_map_offd[(size_t)j];
+        rown[ncr + j] = (int32_t)(std::upper_bound(rstart.begin(), rstart.end(), rgid[ncr + j]) - rstart.begin()) - 1;
+    }
+    X.col_ids(hc->rank, cgid, cown);
+    return finish_parcsr(ctx, C, 0, rgid, rown, cgid, cown, R->first_col_diag, R->first_col_diag + ncr, R->global_num_cols,
+                         X.c0, X.c1, P->global_num_cols, Ac);
+}
+
+// ---------------------------------------------------------------------------------------------
+// A^T for a distributed A (hypre_ParCSRMatrixTranspose): the transposed ghost columns are rows of other ranks
+// ---------------------------------------------------------------------------------------------
+int pe_transpose_distributed(pe_ctx *ctx, const pe_mat *A, pe_mat **out)
+{
+    const pe_host_comm *hc = ctx->hcomm;
+    PE_CHECK(hc, "distributed transpose needs a host communicator (pe_ctx_set_host_comm)");
+    const int nc = A->diag.ncols, ng = A->offd.ncols;
+    DevCSR Aloc, T;
+    PE_TRY(merge_rows(ctx, A->diag, A->offd, nullptr, A->diag.nrows, nullptr, nc, nc + ng, Aloc));
+    PE_TRY(pe_devcsr_transpose(ctx, Aloc, T));
+    devcsr_free(Aloc);
+    std::vector<int64_t> cstart;
+    PE_TRY(col_partition(hc, A, cstart));
+    std::vector<int64_t> rgid((size_t)nc + ng), cgid; std::vector<int32_t> rown((size_t)nc + ng, hc->rank), cown;
+    for (int j = 0; j < nc; ++j) rgid[j] = A->first_col_diag + j;
+    for (int j = 0; j < ng; ++j)
+    {
+        rgid[nc + j] = A->col_map_offd[(size_t)j];
+        rown[nc + j] = (int32_t)(std::upper_bound(cstart.begin(), cstart.end(), rgid[nc + j]) - cstart.begin()) - 1;
+    }
+    own_rows(A, hc->rank, cgid, cown);
+    return finish_parcsr(ctx, T, 0, rgid, rown, cgid, cown, A->first_col_diag, A->first_col_diag + nc, A->global_num_cols,
+                         A->first_row_index, A->first_row_index + A->diag.nrows, A->global_num_rows, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// C = a A + b B for distributed operands with the same row and column partition (hypre_ParCSRMatrixAdd2,
+// src/hypreExtension/parcsr-add.c: merge diag and offd, add, split again)
+// ---------------------------------------------------------------------------------------------
+int pe_devcsr_spadd(pe_ctx *ctx, double a, const DevCSR &A, double b, const DevCSR &B, DevCSR &C);   // pe_spgemm.cu
+int pe_spadd_distributed(pe_ctx *ctx, double a, const pe_mat *A, double b, const pe_mat *B, pe_mat **out)
+{
+    const pe_host_comm *hc = ctx->hcomm;
+    PE_CHECK(hc, "distributed matrix addition needs a host communicator (pe_ctx_set_host_comm)");
+    PE_CHECK(A->diag.nrows == B->diag.nrows && A->diag.ncols == B->diag.ncols && A->first_col_diag == B->first_col_diag &&
+             A->global_num_cols == B->global_num_cols, "pe_spadd: operands are partitioned differently");
+    cudaStream_t st = ctx->stream;
+    const int n = A->diag.nrows, nc = A->diag.ncols;
+    std::vector<int64_t> U(A->col_map_offd.begin(), A->col_map_offd.end());
+    U.insert(U.end(), B->col_map_offd.begin(), B->col_map_offd.end());
+    std::sort(U.begin(), U.end());
+    U.erase(std::unique(U.begin(), U.end()), U.end());
+    auto remap = [&](const pe_mat *M, DevCSR &L) -> int
+    {
+        std::vector<int32_t> om(M->col_map_offd.size());
+        for (size_t j = 0; j < om.size(); ++j) om[j] = nc + (int32_t)(std::lower_bound(U.begin(), U.end(), M->col_map_offd[j]) - U.begin());
+        int *om_d = nullptr;
+        PE_CUDA(cudaMalloc(&om_d, sizeof(int) * (om.size() ? om.size() : 1)));
+        if (!om.empty()) PE_CUDA(cudaMemcpyAsync(om_d, om.data(), sizeof(int) * om.size(), cudaMemcpyHostToDevice, st));
+        const int rc = merge_rows(ctx, M->diag, M->offd, nullptr, n, om_d, 0, nc + (int)U.size(), L);
+        cudaStreamSynchronize(st);
+        cudaFree(om_d);
+        return rc;
+    };
+    DevCSR LA, LB, C;
+    PE_TRY(remap(A, LA));
+    PE_TRY(remap(B, LB));
+    PE_TRY(pe_devcsr_spadd(ctx, a, LA, b, LB, C));
+    devcsr_free(LA); devcsr_free(LB);
+    std::vector<int64_t> cstart;
+    PE_TRY(col_partition(hc, A, cstart));
+    std::vector<int64_t> rgid, cgid((size_t)nc + U.size()); std::vector<int32_t> rown, cown((size_t)nc + U.size(), hc->rank);
+    own_rows(A, hc->rank, rgid, rown);
+    for (int j = 0; j < nc; ++j) cgid[j] = A->first_col_diag + j;
+    for (size_t j = 0; j < U.size(); ++j)
+    {
+        cgid[nc + j] = U[j];
+        cown[nc + j] = (int32_t)(std::upper_bound(cstart.begin(), cstart.end(), U[j]) - cstart.begin()) - 1;
+    }
+    return finish_parcsr(ctx, C, 1, rgid, rown, cgid, cown, A->first_row_index, A->first_row_index + n, A->global_num_rows,
+                         A->first_col_diag, A->first_col_diag + nc, A->global_num_cols, out);
 }
 
 // ---------------------------------------------------------------------------------------------

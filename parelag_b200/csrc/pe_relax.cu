@@ -49,6 +49,12 @@ struct pe_smoother {
     bool skip_turn = false;             // the backward pass may start at the second-to-last colour (see build_gs_schedule)
     int32_t *pos_d = nullptr;           // row -> colour-ordered position
     double *l1p_d = nullptr, *fp_d = nullptr, *up_d = nullptr;
+    // fused sweep (PE_TUNE_FUSED_GS_MAX_MB): all colours of a symmetric sweep in one cooperative kernel
+    bool fused = false;
+    int fused_grid = 0, fused_nsteps = 0;
+    int2 *fused_steps_d = nullptr;      // per step: row range of the set-ordered copy / slice range of the SELL copy
+    unsigned *fused_bar_d = nullptr;    // {arrivals, generation}
+    double fused_bytes = 0.0;           // algorithmic bytes of one fused sweep
     // Chebyshev
     double max_eig = 0, min_eig = 0;
     double coefs[5] = {0, 0, 0, 0, 0};
@@ -157,6 +163,113 @@ k_gs_set(int k0, int k1, const int *__restrict__ pI, const int *__restrict__ pJ,
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fused symmetric sweep: every colour of the forward and of the backward pass in ONE persistent kernel with a grid-wide
+// barrier between colours.  On the coarse levels a colour is a few hundred to a few thousand rows: a launch per colour
+// costs 3-10x the colour's work.  The rows a step touches, their lanes and the summation order are those of the
+// per-colour kernels (k_gs_set<TPR, false>, k_sell_gs), so the result is bit-identical.  u is read and written past the
+// (non-coherent) L1 (ld/st.global.cg); a colour's updates are published by __threadfence + the barrier's release.
+// Launched cooperatively (all CTAs resident); grid <= SMs x occupancy.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bar[0] = arrivals of the current barrier, bar[1] = generation; reusable across launches (graph replays)
+__device__ __forceinline__ void grid_barrier(unsigned *bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        const unsigned gen = ld_acquire_gpu_u32(bar + 1);
+        if (atomicAdd(bar, 1u) == gridDim.x - 1) { atomicExch(bar, 0u); __threadfence(); st_release_gpu_u32(bar + 1, gen + 1); }
+        else while (ld_acquire_gpu_u32(bar + 1) == gen) { }
+    }
+    __syncthreads();
+}
+
+template <int TPR>
+__global__ void __launch_bounds__(256)
+k_gs_sweep(int nsteps, const int2 *__restrict__ steps, const int *__restrict__ pI, const int *__restrict__ pJ,
+           const double *__restrict__ pA, const int *__restrict__ perm, int ncd,
+           const double *f, double *u, const double *uext, const double *__restrict__ l1, unsigned *bar)
+{
+    pdl_wait();
+    const int lane = threadIdx.x & (TPR - 1);
+    const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) / TPR, gstride = (gridDim.x * blockDim.x) / TPR;
+    for (int t = 0; t < nsteps; ++t)
+    {
+        const int2 st = steps[t];
+        for (int k = st.x + g0; k < st.y; k += gstride)
+        {
+            const int lo = pI[k], hi = pI[k + 1], i = perm[k];
+            const double d = l1[i];
+            double fi = 0.0, ui = 0.0;
+            if (lane == 0) { fi = f[i]; ui = __ldcg(u + i); }
+            double s = 0.0;
+            for (int q = lo + lane; q < hi; q += TPR)
+            {
+                const int c = pJ[q];
+                const double a = pA[q];
+                s += a * (c < ncd ? __ldcg(u + c) : uext[c - ncd]);
+            }
+#pragma unroll
+            for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
+            if (lane == 0 && d != 0.0) __stcg(u + i, ui + (fi - s) / d);
+        }
+        if (t + 1 < nsteps) grid_barrier(bar);
+    }
+}
+
+// SELL variant: vectors in colour order; steps[0] and the last step are the renumbering passes
+// (x.y < 0: renumber in, x.y == -2: renumber out), the others slice ranges [x, y) of one colour
+__global__ void __launch_bounds__(256)
+k_sell_gs_sweep(int nsteps, const int2 *__restrict__ steps, const int *__restrict__ soff, const int *__restrict__ J,
+                const double *__restrict__ A, int ext_base, int n, const int *__restrict__ pos, const double *b,
+                double *x, int zero_guess, double *f, double *u, const double *uext, const double *__restrict__ l1, unsigned *bar)
+{
+    pdl_wait();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, w0 = tid >> 5, nw = nthr >> 5;
+    for (int t = 0; t < nsteps; ++t)
+    {
+        const int2 st = steps[t];
+        if (st.y == -1)
+            for (int i = tid; i < n; i += nthr) { const int p = pos[i]; __stcg(f + p, b[i]); __stcg(u + p, zero_guess ? 0.0 : x[i]); }
+        else if (st.y == -2)
+            for (int i = tid; i < n; i += nthr) x[i] = __ldcg(u + pos[i]);
+        else
+            for (int sl = st.x + w0; sl < st.y; sl += nw)
+            {
+                const int o0 = soff[sl], w = soff[sl + 1] - o0;
+                const int *j = J + (int64_t)o0 * 32 + lane;
+                const double *a = A + (int64_t)o0 * 32 + lane;
+                const int row = sl * 32 + lane;
+                const double d = l1[row], fr = __ldcg(f + row), ur = __ldcg(u + row);
+                double acc = 0.0;
+                for (int q = 0; q < w; q += 4)
+                {
+                    int c[4]; double v[4], uv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (q + k < w) { c[k] = j[(q + k) * 32]; v[k] = a[(q + k) * 32]; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (q + k < w) uv[k] = (uext && c[k] >= ext_base) ? uext[c[k] - ext_base] : __ldcg(u + c[k]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (q + k < w) acc = __fma_rn(v[k], uv[k], acc);
+                }
+                if (d != 0.0) __stcg(u + row, ur + (fr - acc) / d);
+            }
+        if (t + 1 < nsteps) grid_barrier(bar);
+    }
+}
+
 // Streaming variant of one GS set (same structure as k_spmv_stream): CTA b owns rows
 // [rb[b], rb[b+1]) of the set-ordered matrix; row blocks never straddle a set boundary.
 __global__ void __launch_bounds__(256)
@@ -259,6 +372,7 @@ static void build_colors(int n, const int *I, const int *J, std::vector<int> &co
 
 #include <cub/cub.cuh>
 
+static int fused_setup(pe_smoother *s);
 static int build_gs_schedule(pe_smoother *s)
 {
     pe_ctx *ctx = s->ctx;
@@ -626,6 +740,7 @@ extern "C" int pe_smoother_create(pe_ctx *ctx, pe_mat *A, int type, int sweeps, 
     if (type == 2 || type == 4 || type == 6) {
         if (!(damping == 1.0 && omega == 1.0)) PE_CUDA(cudaMalloc(&s->w_d, nb));
         PE_TRY(build_gs_schedule(s));
+        PE_TRY(fused_setup(s));
     } else if (type == 16) {
         PE_CUDA(cudaMalloc(&s->w_d, nb));
         PE_CUDA(cudaMalloc(&s->z_d, nb));
@@ -652,9 +767,112 @@ extern "C" int pe_smoother_free(pe_smoother *s)
     if (s->l1p_d) cudaFree(s->l1p_d);
     if (s->fp_d) cudaFree(s->fp_d);
     if (s->up_d) cudaFree(s->up_d);
+    if (s->fused_steps_d) cudaFree(s->fused_steps_d);
+    if (s->fused_bar_d) cudaFree(s->fused_bar_d);
     pe_sell_free(s->S);
     devcsr_free(s->P);
     delete s;
+    return 0;
+}
+
+// ---- fused sweep: schedule and launch
+static int fused_setup(pe_smoother *s)
+{
+    pe_ctx *ctx = s->ctx;
+    const int limit_mb = pe_get_tuning(PE_TUNE_FUSED_GS_MAX_MB);
+    const bool general = !(s->weight == 1.0 && s->omega == 1.0);
+    if (limit_mb <= 0 || general || s->nsets < 2 || !(s->type == 2 || s->type == 4 || s->type == 6)) return 0;
+    const int nsets = s->nsets;
+    std::vector<double> bytes(nsets, 0.0);
+    std::vector<int2> steps;
+    int max_units = 1;                       // rows (CSR) or slices (SELL) of the largest step
+    for (int c = 0; c < nsets; ++c)
+    {
+        const double rows = s->set_starts[c + 1] - s->set_starts[c];
+        bytes[c] = s->use_sell ? s->set_bytes[c] : 12.0 * (double)(s->set_pI[c + 1] - s->set_pI[c]) + 36.0 * rows;
+        if (bytes[c] >= 1e6 * limit_mb) return 0;                 // a bandwidth-bound colour: keep one launch per colour
+    }
+    if (s->use_sell) steps.push_back(make_int2(-1, -1));
+    s->fused_bytes = 0.0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int cc = (pass == 1 && s->skip_turn) ? 1 : 0; cc < nsets; ++cc)
+        {
+            const int c = pass == 0 ? cc : nsets - 1 - cc;
+            const int a = s->use_sell ? s->slice_starts[c] : s->set_starts[c], b = s->use_sell ? s->slice_starts[c + 1] : s->set_starts[c + 1];
+            if (b <= a) continue;
+            steps.push_back(make_int2(a, b));
+            max_units = std::max(max_units, b - a);
+            s->fused_bytes += bytes[c];
+        }
+    if (s->use_sell) steps.push_back(make_int2(-2, -2));
+    int nsm = 0, occ = 0, coop = 0;
+    PE_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+    PE_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    if (!coop) return 0;
+    const void *kern = nullptr;
+    if (s->use_sell) kern = (const void *)k_sell_gs_sweep;
+    else switch (s->tpr) {
+        case 1: kern = (const void *)k_gs_sweep<1>; break;
+        case 2: kern = (const void *)k_gs_sweep<2>; break;
+        case 4: kern = (const void *)k_gs_sweep<4>; break;
+        case 8: kern = (const void *)k_gs_sweep<8>; break;
+        case 16: kern = (const void *)k_gs_sweep<16>; break;
+        default: kern = (const void *)k_gs_sweep<32>; break;
+    }
+    PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+    if (occ < 1) return 0;
+    const int64_t threads = s->use_sell ? (int64_t)max_units * 32 : (int64_t)max_units * s->tpr;
+    int64_t want = (threads + 255) / 256;
+    if (s->use_sell) want = std::max<int64_t>(want, ((int64_t)s->A->diag.nrows + 255) / 256 / 4);   // the renumbering passes
+    s->fused_grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)nsm * std::min(occ, 4)));
+    s->fused_nsteps = (int)steps.size();
+    PE_CUDA(cudaMalloc(&s->fused_steps_d, sizeof(int2) * steps.size()));
+    PE_CUDA(cudaMemcpy(s->fused_steps_d, steps.data(), sizeof(int2) * steps.size(), cudaMemcpyHostToDevice));
+    PE_CUDA(cudaMalloc(&s->fused_bar_d, 2 * sizeof(unsigned)));
+    PE_CUDA(cudaMemset(s->fused_bar_d, 0, 2 * sizeof(unsigned)));
+    s->fused = true;
+    return 0;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cooperative(pe_ctx *ctx, void (*kern)(KArgs...), int grid, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+static int launch_fused_sweep(pe_smoother *s, const double *b, double *x, bool zero_guess)
+{
+    pe_ctx *ctx = s->ctx;
+    pe_mat *A = s->A;
+    if (ctx->prof) PE_TRY(pe_prof_begin(ctx, 3, s->fused_bytes));
+    if (s->use_sell)
+        PE_CUDA(launch_cooperative(ctx, k_sell_gs_sweep, s->fused_grid, s->fused_nsteps, s->fused_steps_d, s->S.soff, s->S.J, s->S.A, s->npad,
+                                   A->diag.nrows, s->pos_d, b, x, zero_guess ? 1 : 0, s->fp_d, s->up_d, A->offd.nnz > 0 ? A->x_ext_d : nullptr,
+                                   s->l1p_d, s->fused_bar_d));
+    else
+    {
+#define LAUNCH(T) PE_CUDA(launch_cooperative(ctx, k_gs_sweep<T>, s->fused_grid, s->fused_nsteps, s->fused_steps_d, s->P.I, s->P.J, s->P.A, s->perm_d, \
+                                             A->diag.ncols, b, x, A->x_ext_d, s->l1_d, s->fused_bar_d))
+        switch (s->tpr) {
+        case 1: LAUNCH(1); break;
+        case 2: LAUNCH(2); break;
+        case 4: LAUNCH(4); break;
+        case 8: LAUNCH(8); break;
+        case 16: LAUNCH(16); break;
+        default: LAUNCH(32); break;
+        }
+#undef LAUNCH
+    }
+    PE_LAUNCHED(ctx);
+    PE_TRY(pe_prof_end(ctx));
     return 0;
 }
 
@@ -729,6 +947,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
         {
             const bool zero_guess = !iterative_mode && sweep == 0;
             PE_TRY(sweep_halo(A, x->d, zero_guess));
+            if (s->fused && !ctx->rec) { PE_TRY(launch_fused_sweep(s, b->d, x->d, zero_guess)); continue; }
             PE_TRY(pe_launch_perm_in(ctx, n, s->pos_d, b->d, zero_guess ? nullptr : x->d, s->fp_d, s->up_d));
             for (int pass = 0; pass < 2; ++pass)
                 for (int cc = (pass == 1 && s->skip_turn) ? 1 : 0; cc < s->nsets; ++cc)
@@ -772,6 +991,7 @@ extern "C" int pe_smoother_apply(pe_smoother *s, const pe_vec *b, pe_vec *x, int
             PE_TRY(sweep_halo(A, x->d, !iterative_mode && sweep == 0));
             bool general = !(s->weight == 1.0 && s->omega == 1.0);
             double c1 = s->omega * s->weight, c2 = s->omega * (1.0 - s->weight);
+            if (s->fused && !ctx->rec) { PE_TRY(launch_fused_sweep(s, b->d, x->d, false)); continue; }
             for (int pass = 0; pass < 2; ++pass) {
                 if (general) PE_CUDA(cudaMemcpyAsync(s->w_d, x->d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
                 for (int cc = (pass == 1 && s->skip_turn) ? 1 : 0; cc < s->nsets; ++cc) {

@@ -326,7 +326,11 @@ int pe_devcsr_spgemm(pe_ctx *ctx, const DevCSR &A, const DevCSR &B, DevCSR &C)
 
 extern "C" int pe_spgemm(pe_ctx *ctx, const pe_mat *A, const pe_mat *B, pe_mat **C)
 {
-    PE_CHECK(A->offd.nnz == 0 && B->offd.nnz == 0, "pe_spgemm: distributed product not supported yet (local blocks only)");
+    if (A->distributed || B->distributed)
+    {
+        PE_CHECK(A->distributed && B->distributed, "pe_spgemm: A and B must both be distributed matrices");
+        return pe_spgemm_distributed(ctx, A, B, C);
+    }
     DevCSR c;
     PE_TRY(pe_devcsr_spgemm(ctx, A->diag, B->diag, c));
     PE_TRY(pe_mat_wrap_local(ctx, c, C));
@@ -340,8 +344,8 @@ extern "C" int pe_rap(pe_ctx *ctx, const pe_mat *R, const pe_mat *A, const pe_ma
     if (A->distributed || P->distributed)
     {
         PE_CHECK(A->distributed && P->distributed, "pe_rap: A and P must both be distributed matrices");
-        PE_CHECK(!R || R == P, "pe_rap: the distributed product supports R == P only");
-        return pe_rap_distributed(ctx, A, P, Ac);
+        PE_CHECK(!R || R->distributed, "pe_rap: R must be a distributed matrix as well");
+        return pe_rap_distributed(ctx, R, A, P, Ac);
     }
     const pe_mat *Rm = R ? R : P;
     PE_CHECK(Rm->diag.nrows == A->diag.nrows && A->diag.ncols == P->diag.nrows, "pe_rap: size mismatch");
@@ -422,17 +426,16 @@ __global__ void k_spadd_fill(int n, double a, const int *__restrict__ AI, const 
         else { CJ[p] = BJ[kb]; CA[p] = b * BA[kb]; ++p; }
     }
 }
-extern "C" int pe_spadd(pe_ctx *ctx, double a, const pe_mat *A, double b, const pe_mat *B, pe_mat **Cout)
+int pe_devcsr_spadd(pe_ctx *ctx, double a, const DevCSR &A, double b, const DevCSR &B, DevCSR &C)
 {
-    PE_CHECK(A->offd.nnz == 0 && B->offd.nnz == 0, "pe_spadd: local blocks only");
-    PE_CHECK(A->diag.nrows == B->diag.nrows && A->diag.ncols == B->diag.ncols, "pe_spadd: size mismatch");
+    PE_CHECK(A.nrows == B.nrows && A.ncols == B.ncols, "pe_spadd: size mismatch");
     cudaStream_t st = ctx->stream;
-    int n = A->diag.nrows;
+    int n = A.nrows;
     int *len;
     PE_CUDA(cudaMalloc(&len, sizeof(int) * (size_t)(n + 1)));
     PE_CUDA(cudaMemsetAsync(len, 0, sizeof(int) * (size_t)(n + 1), st));
-    if (n > 0) { k_spadd_count<<<pe_grid_for(n, 256), 256, 0, st>>>(n, A->diag.I, A->diag.J, B->diag.I, B->diag.J, len); PE_LAUNCHED(ctx); }
-    DevCSR C;
+    if (n > 0) { k_spadd_count<<<pe_grid_for(n, 256), 256, 0, st>>>(n, A.I, A.J, B.I, B.J, len); PE_LAUNCHED(ctx); }
+    C = DevCSR();
     PE_CUDA(cudaMalloc(&C.I, sizeof(int) * (size_t)(n + 1)));
     void *tmp = nullptr; size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, len, C.I, n + 1, st);
@@ -443,10 +446,22 @@ extern "C" int pe_spadd(pe_ctx *ctx, double a, const pe_mat *A, double b, const 
     PE_CUDA(cudaMemcpyAsync(&nnz, C.I + n, sizeof(int), cudaMemcpyDeviceToHost, st));
     PE_CUDA(cudaStreamSynchronize(st));
     cudaFree(tmp); cudaFree(len);
-    C.nrows = n; C.ncols = A->diag.ncols; C.nnz = nnz;
+    C.nrows = n; C.ncols = A.ncols; C.nnz = nnz;
     PE_CUDA(cudaMalloc(&C.J, sizeof(int) * (size_t)(nnz > 0 ? nnz : 1)));
     PE_CUDA(cudaMalloc(&C.A, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)));
-    if (n > 0) { k_spadd_fill<<<pe_grid_for(n, 256), 256, 0, st>>>(n, a, A->diag.I, A->diag.J, A->diag.A, b, B->diag.I, B->diag.J, B->diag.A, C.I, C.J, C.A); PE_LAUNCHED(ctx); }
+    if (n > 0) { k_spadd_fill<<<pe_grid_for(n, 256), 256, 0, st>>>(n, a, A.I, A.J, A.A, b, B.I, B.J, B.A, C.I, C.J, C.A); PE_LAUNCHED(ctx); }
+    return 0;
+}
+extern "C" int pe_spadd(pe_ctx *ctx, double a, const pe_mat *A, double b, const pe_mat *B, pe_mat **Cout)
+{
+    if (A->distributed || B->distributed)
+    {
+        PE_CHECK(A->distributed && B->distributed, "pe_spadd: A and B must both be distributed matrices");
+        return pe_spadd_distributed(ctx, a, A, b, B, Cout);
+    }
+    PE_CHECK(A->offd.nnz == 0 && B->offd.nnz == 0, "pe_spadd: local blocks only");
+    DevCSR C;
+    PE_TRY(pe_devcsr_spadd(ctx, a, A->diag, b, B->diag, C));
     PE_TRY(pe_mat_wrap_local(ctx, C, Cout));
     return 0;
 }

@@ -244,7 +244,7 @@ int pe_devcsr_transpose(pe_ctx *ctx, const DevCSR &A, DevCSR &T)
 
 extern "C" int pe_mat_transpose(pe_ctx *ctx, const pe_mat *A, pe_mat **out)
 {
-    PE_CHECK(A->offd.nnz == 0, "pe_mat_transpose: distributed transpose not supported yet (local block only)");
+    if (A->distributed) return pe_transpose_distributed(ctx, A, out);
     DevCSR T;
     PE_TRY(pe_devcsr_transpose(ctx, A->diag, T));
     PE_TRY(pe_mat_wrap_local(ctx, T, out));

@@ -305,13 +305,19 @@ public:
     {
         std::transform(Type_.begin(), Type_.end(), Type_.begin(), ::toupper);
     }
-    /// "DIAGONAL": A11 - alpha A10 diag(A00)^{-1} A01; "ABSROWSUM": the same with absolute row sums
-    std::unique_ptr<mfem::Operator> BuildOperator(MfemBlockOperator &op, SolverState &) const
+    /// "MASS": sequence.ComputeTrueM(forms.front()); "DIAGONAL": A11 - alpha A10 diag(A00)^{-1} A01; "ABSROWSUM": the
+    /// same with absolute row sums (ParELAG_SchurComplementFactory.cpp:36-177)
+    std::unique_ptr<mfem::Operator> BuildOperator(MfemBlockOperator &op, SolverState &state) const
     {
         PARELAG_ASSERT(op.GetNumBlockRows() == 2);
         PARELAG_ASSERT(op.GetNumBlockCols() == 2);
-        PARELAG_TEST_FOR_EXCEPTION(Type_ == "MASS", not_implemented_error,
-                                   "SchurComplementFactory: type \"MASS\" (ComputeTrueM) is not available on the GPU path in this round");
+        if (Type_ == "MASS")
+        {
+            // "Assume the state has just the important form up front" (SchurComplementFactory.cpp:43-50)
+            auto form = state.GetForms().front();
+            auto &sequence = state.GetDeRhamSequence();
+            return sequence.ComputeTrueM(form);
+        }
         PARELAG_TEST_FOR_EXCEPTION(Type_ != "DIAGONAL" && Type_ != "ABSROWSUM", std::runtime_error,
                                    "Schur complement type = \"" << Type_ << "\" is invalid.\nValid types are \"MASS\" and \"DIAGONAL\"");
         auto blk = [&](int i, int j) { return op.IsZeroBlock(i, j) ? nullptr : dynamic_cast<mfem::HypreParMatrix *>(&op.GetBlock(i, j)); };

@@ -96,6 +96,33 @@ public:
         pe_parcsr_owned_free(M);
         return out;
     }
+    /// Assemble(range map, A, domain map) (SharingMap.cpp:975-1011): the contributions of all holders of a shared dof
+    /// are summed on its owner (E_r^T A E_d), as a device ParCSR matrix
+    std::unique_ptr<mfem::HypreParMatrix> Assemble(const par::SharingMap &range, const HostCSR &A, const par::SharingMap &domain) const
+    {
+        pe_parcsr_owned *M = nullptr;
+        PE_CALL(pe_par_assemble(Comm_, 0, A.nrows, A.ncols, A.I.data(), A.J.data(), A.A.data(), range.gid.data(), range.owner.data(),
+                                domain.gid.data(), domain.owner.data(), range.start, range.start + range.ntrue, range.global,
+                                domain.start, domain.start + domain.ntrue, domain.global, &M));
+        std::unique_ptr<mfem::HypreParMatrix> out;
+        try { out = make_unique<mfem::HypreParMatrix>(*pe_parcsr_owned_view(M)); }
+        catch (...) { pe_parcsr_owned_free(M); throw; }
+        pe_parcsr_owned_free(M);
+        return out;
+    }
+    /// ComputeTrueM(jform) (DeRhamSequence.cpp:1100-1107): Assemble(dofTrueDof, ComputeMassOperator(jform), dofTrueDof)
+    std::unique_ptr<mfem::HypreParMatrix> ComputeTrueM(int jform) const
+    {
+        const HostCSR M = ComputeMassOperator(jform);
+        if (IsParallel()) return Assemble(*DofTrueDof_.at(jform), M, *DofTrueDof_.at(jform));
+        return make_unique<mfem::HypreParMatrix>(M.View());
+    }
+    /// Assemble(dofTrueDof(range form), A, dofTrueDof(domain form)) for a local operator between two forms (e.g. B = W D)
+    std::unique_ptr<mfem::HypreParMatrix> AssembleTrue(int range_form, const HostCSR &A, int domain_form) const
+    {
+        if (IsParallel()) return Assemble(*DofTrueDof_.at(range_form), A, *DofTrueDof_.at(domain_form));
+        return make_unique<mfem::HypreParMatrix>(A.View());
+    }
     DofHandler *GetDofHandler(int jform) const { return RawDof_.at(jform) ? RawDof_[jform] : Dof_.at(jform).get(); }
     void SetDofHandler(int jform, std::unique_ptr<DofHandler> d) { Dof_.at(jform) = std::move(d); }
 

@@ -195,12 +195,18 @@ def multi_rank(ctx, rank, size, deform=False, n=4, lev=3, group=None):
     perms = {j: [true_to_oracle(S.dofmap(l, j), okeys[j][l]) for l in range(lev)] for j in (1, 2)}
 
     # ---- ComputeTrueP / ComputeTrueD on every level == single-domain P / D
+    # Deformed geometry: level 1 carries NullSpace dofs (singular vectors of target residuals); what is built FROM them
+    # (P of level 1 -> 2, D of level 2) is determined to eps / (sigma |T|) only -- two backward-stable local solvers
+    # differ by ~1e-10 there (tests/test_coarsen_gpu.py:compare_levels, null_tol).  Level 0 keeps 1e-12.
+    loose = 1e-8 if deform else 1e-12
     for l in range(lev - 1):
         Pg, _ = gather_matrix(S.true_operator(ctx, l, "P", form, ess))
-        same_pattern_and_values(permuted(Pg, perms[2][l], perms[2][l + 1]), sp.csr_matrix(seqs[l].get_P(form, ess)), 1e-12, "P level %d" % l)
+        same_pattern_and_values(permuted(Pg, perms[2][l], perms[2][l + 1]), sp.csr_matrix(seqs[l].get_P(form, ess)),
+                                1e-12 if l == 0 else loose, "P level %d" % l)
     for l in range(lev):
         Dg, _ = gather_matrix(S.true_operator(ctx, l, "D", form - 1, ess))
-        same_pattern_and_values(permuted(Dg, perms[2][l], perms[1][l]), sp.csr_matrix(seqs[l].get_D(form - 1, ess)), 1e-12, "D level %d" % l)
+        same_pattern_and_values(permuted(Dg, perms[2][l], perms[1][l]), sp.csr_matrix(seqs[l].get_D(form - 1, ess)),
+                                1e-12 if l <= 1 else loose, "D level %d" % l)
 
     # ---- assembled system (shared essential dofs carry the number of holders on the diagonal, as in
     # the reference driver: EliminateRowCol on the local matrix, then Assemble)

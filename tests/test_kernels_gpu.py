@@ -149,6 +149,39 @@ def test_gauss_seidel_multicolor(ctx, weights, gs_kernel, dims):
     assert _rel(dx.download(), so.apply(b, x0, True)) < 1e-13
 
 
+@pytest.mark.parametrize("ordering", ["multicolor", "natural"])
+@pytest.mark.parametrize("maker", [lambda: laplace3d(21, 20, 19), lambda: _stencil27(11)])
+def test_fused_sweep_kernel_is_bit_identical_to_per_colour_launches(ctx, gs_kernel, ordering, maker):
+    """PE_TUNE_FUSED_GS_MAX_MB: the whole symmetric sweep (all colours / level sets, forward and backward, the SELL
+    renumbering included) as ONE cooperative kernel with grid barriers -- same rows, same lanes, same summation order
+    as one launch per colour, so the iterates are bit-identical; and both equal the oracle's sequential sweep."""
+    A = maker()
+    n = A.shape[0]
+    rng = np.random.default_rng(3)
+    b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    dA = capi.Mat.from_scipy(ctx, A)
+    old = capi.get_tuning(capi.TUNE_FUSED_GS_MAX_MB)
+    out = {}
+    try:
+        for fused in (0, 24):
+            capi.set_tuning(capi.TUNE_FUSED_GS_MAX_MB, fused)
+            s = capi.Smoother(ctx, dA, type=2, sweeps=2, ordering=capi.GS_MULTICOLOR if ordering == "multicolor" else capi.GS_NATURAL)
+            order, starts = s.order()
+            for mode in (True, False):
+                dx, db = capi.Vec(ctx, data=x0), capi.Vec(ctx, data=b)
+                l0 = ctx.launch_count()
+                s.apply(db, dx, mode)
+                out[(fused, mode)] = (dx.download(), ctx.launch_count() - l0)
+            s.free()
+    finally:
+        capi.set_tuning(capi.TUNE_FUSED_GS_MAX_MB, old)
+    for mode in (True, False):
+        assert np.array_equal(out[(0, mode)][0], out[(24, mode)][0])
+        assert out[(24, mode)][1] == 2 and out[(0, mode)][1] > 2 * (len(starts) - 2)      # one launch per sweep
+    so = orc.Smoother(A, type=2, sweeps=2, order=order if ordering == "multicolor" else None)
+    assert _rel(out[(24, True)][0], so.apply(b, x0, True)) < 1e-13
+
+
 def _stencil27(n):
     t = sp.diags([np.ones(n - 1), np.ones(n), np.ones(n - 1)], [-1, 0, 1])
     A = sp.kron(sp.kron(t, t), t).tocsr()
