@@ -167,14 +167,21 @@ class Topology:
         return self.coarser
 
 
-def refined_partition(dims_fine):
-    """MFEMRefinedMeshPartitioner: agglomerate = parent element of one uniform
-    refinement.  On the lexicographic structured grid: AE(i,j,k) = (i//2, j//2, k//2)."""
+def refined_partition(dims_fine, ratio=(2, 2, 2)):
+    """MFEMRefinedMeshPartitioner: agglomerate = parent element of one uniform refinement; on the lexicographic
+    structured grid AE(i,j,k) = (i//2, j//2, k//2).  Grids that are not a multiple of the ratio take the logical
+    Cartesian agglomeration (LogicalPartitioner.hpp:46-103 with CoarsenLogicalCartesianOperator,
+    CartesianPartitioner.hpp:113-131): same coarse index = same agglomerate, ragged last blocks, parts numbered in the
+    order the scan of the fine elements meets them (= lexicographic order of the coarse indices)."""
     nx, ny, nz = dims_fine
-    assert nx % 2 == 0 and ny % 2 == 0 and nz % 2 == 0
-    cx, cy = nx // 2, ny // 2
+    rx, ry, rz = ratio
+    cx, cy = -(-nx // rx), -(-ny // ry)
     k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
-    return (((k // 2) * cy + (j // 2)) * cx + (i // 2)).ravel()
+    return (((k // rz) * cy + (j // ry)) * cx + (i // rx)).ravel()
+
+
+def coarse_dims(d, ratio=(2, 2, 2)):
+    return tuple(-(-a // r) for a, r in zip(d, ratio))
 
 
 # ----------------------------------------------------------------------------
@@ -1402,7 +1409,7 @@ def build_hierarchy(dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jst
     d = dims
     for _ in range(nlevels - 1):
         topos.append(topos[-1].coarsen(refined_partition(d)))
-        d = (d[0] // 2, d[1] // 2, d[2] // 2)
+        d = coarse_dims(d)
     seqs = [fine_sequence(mesh, topos[0], alpha=alpha, beta=beta, jstart=jstart)]
     for l in range(nlevels - 1):
         seqs[l].svd_tol = svd_tol

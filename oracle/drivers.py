@@ -105,16 +105,16 @@ def darcy_blocks(seq):
 
 
 def darcy_library_entries(block="Block Jacobi", ordering="natural", coarse_its=5, coarse_tol=1e-4, rtol=1e-6, atol=1e-6,
-                          max_iter=300, restart=50, amge=True):
+                          max_iter=300, restart=50, amge=True, smoother="L1 Gauss-Seidel", s_type="Diagonal"):
     """Parameter list modelled on examples/example_parameterlists/darcy_example_parameters.xml with the
     hypre black boxes (BoomerAMG) replaced by the hot-path l1-Gauss-Seidel smoother."""
-    lib = {"Gauss-Seidel": ("Hypre", {"Type": "L1 Gauss-Seidel", "Sweeps": 1, "Damping Factor": 1.0, "Omega": 1.0,
+    lib = {"Gauss-Seidel": ("Hypre", {"Type": smoother, "Sweeps": 1, "Damping Factor": 1.0, "Omega": 1.0,
                                       "GS ordering": ordering})}
     if block == "Block LDU":
         lib["Blk"] = ("Block LDU", {"Damping Factor": 1.0, "A00_1 Inverse": "Gauss-Seidel", "A00_2 Inverse": "Gauss-Seidel",
-                                    "A00_3 Inverse": "Gauss-Seidel", "S Inverse": "Gauss-Seidel", "Alpha": 1.0, "S Type": "Diagonal"})
+                                    "A00_3 Inverse": "Gauss-Seidel", "S Inverse": "Gauss-Seidel", "Alpha": 1.0, "S Type": s_type})
     else:
-        lib["Blk"] = (block, {"A00 Inverse": "Gauss-Seidel", "A11 Inverse": "Gauss-Seidel", "Alpha": 1.0, "S Type": "Diagonal"})
+        lib["Blk"] = (block, {"A00 Inverse": "Gauss-Seidel", "A11 Inverse": "Gauss-Seidel", "Alpha": 1.0, "S Type": s_type})
     lib["GMRES-Blk"] = ("Krylov", {"Solver name": "GMRES", "Preconditioner": "Blk", "Print level": -1, "Maximum iterations": coarse_its,
                                    "Relative tolerance": coarse_tol, "Absolute tolerance": coarse_tol, "Restart size": restart})
     lib["AMGe-Blk"] = ("AMGe", {"Maximum levels": -1, "Forms": [2, 3], "PreSmoother": "Blk", "PostSmoother": "Blk",
@@ -125,18 +125,20 @@ def darcy_library_entries(block="Block Jacobi", ordering="natural", coarse_its=5
     return lib
 
 
-def darcy_solver(seqs, block="Block Jacobi", ordering="natural", coarse_its=5, coarse_tol=1e-4, restart=50, amge=True):
-    """The same solver on the oracle side: returns (A: BlockOp, prec: r -> z)."""
+def darcy_solver(seqs, block="Block Jacobi", ordering="natural", coarse_its=5, coarse_tol=1e-4, restart=50, amge=True,
+                 smoother_type=2, s_type="DIAGONAL"):
+    """The same solver on the oracle side: returns (A: BlockOp, prec: r -> z).  s_type "MASS": the second diagonal
+    operator is ComputeTrueM(forms.front()) of the level's sequence (SchurComplementFactory.cpp:43-50)."""
     M, B = darcy_blocks(seqs[0])
     A0 = orc.BlockOp([[M, sp.csr_matrix(B.T)], [B, None]])
 
     def gs(Mx):
-        S = orc.Smoother(Mx, type=2, order=gs_order(Mx, ordering))
+        S = orc.Smoother(Mx, type=smoother_type, order=gs_order(Mx, ordering) if smoother_type == 2 else None)
         return lambda r: S.apply(r, np.zeros_like(r), False)
 
     def make_smoother(l, A):
         A00, A01, A10, A11 = A.blocks[0][0], A.blocks[0][1], A.blocks[1][0], A.blocks[1][1]
-        negS = sp.csr_matrix(orc.schur_complement(A00, A01, A10, A11, 1.0, "DIAGONAL") * (-1.0))
+        negS = sp.csr_matrix(orc.schur_complement(A00, A01, A10, A11, 1.0, s_type) * (-1.0))
         if block == "Block Jacobi":
             return orc.BlockJacobi(A, [gs(A00), gs(negS)])
         if block == "Block GS":

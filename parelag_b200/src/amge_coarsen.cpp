@@ -619,8 +619,13 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
     for (int l = 0; l + 1 < nlevels; ++l)
     {
         Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level " + std::to_string(l + 1));
-        topo[l + 1] = topo[l]->CoarsenLocalPartitioning(RefinedHexPartition(dx, dy, dz));
-        dx /= 2; dy /= 2; dz /= 2;
+        // derefinement by two per direction; grids that are not a multiple of two (60 x 220 x 85) take the logical
+        // Cartesian agglomeration with ragged last blocks (single rank: the boxes of a decomposition must cut their
+        // interfaces in the same way)
+        PARELAG_TEST_FOR_EXCEPTION(parallel && (dx % 2 || dy % 2 || dz % 2), std::runtime_error,
+                                   "BuildHexSequenceHierarchyPar: box dimensions must be divisible by 2^(levels-1) on more than one rank");
+        topo[l + 1] = topo[l]->CoarsenLocalPartitioning(CartesianHexPartition(dx, dy, dz));
+        dx = (dx + 1) / 2; dy = (dy + 1) / 2; dz = (dz + 1) / 2;
     }
     std::vector<std::shared_ptr<DeRhamSequence>> seq(nlevels);
     {

@@ -386,4 +386,20 @@ inline std::vector<int> RefinedHexPartition(int nx, int ny, int nz)
             for (int i = 0; i < nx; ++i) p[(size_t)i + (size_t)nx * (j + (size_t)ny * k)] = ((k / 2) * cy + (j / 2)) * cx + (i / 2);
     return p;
 }
+/// Logical Cartesian agglomeration (LogicalPartitioner::Partition with CoarsenLogicalCartesianOperator,
+/// src/partitioning/LogicalPartitioner.hpp:46-103, CartesianPartitioner.hpp:113-131): elements with the same coarse index
+/// (i/rx, j/ry, k/rz) form an agglomerate, also when the grid is not a multiple of the ratio (ragged last blocks: the
+/// 60 x 220 x 85 SPE10 grid).  The reference numbers the parts in the order its flood fill meets them while scanning the
+/// elements in storage order; on the lexicographic grid that is the lexicographic order of the coarse indices.
+/// Coarse dimensions: ceil(n / r).
+inline std::vector<int> CartesianHexPartition(int nx, int ny, int nz, int rx = 2, int ry = 2, int rz = 2)
+{
+    PARELAG_TEST_FOR_EXCEPTION(rx < 1 || ry < 1 || rz < 1, std::runtime_error, "CartesianHexPartition(): bad coarsening ratio");
+    const int cx = (nx + rx - 1) / rx, cy = (ny + ry - 1) / ry;
+    std::vector<int> p((size_t)nx * ny * nz);
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) p[(size_t)i + (size_t)nx * (j + (size_t)ny * k)] = ((k / rz) * cy + (j / ry)) * cx + (i / rx);
+    return p;
+}
 } // namespace parelag

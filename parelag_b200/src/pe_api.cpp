@@ -297,7 +297,6 @@ extern "C" int pe_api_sequence_assemble_darcy(pe_sequence *s, int level, pe_mat 
     API_TRY
     auto &seq = *s->levels.at(level);
     PARELAG_TEST_FOR_EXCEPTION(!seq.data, std::runtime_error, "assemble_darcy: sequence has no mass matrices");
-    PARELAG_TEST_FOR_EXCEPTION(seq.IsParallel(), not_implemented_error, "assemble_darcy: single rank only in this round");
     pe_ctx *ctx = Device::Get();
     Timer t = TimeManager::AddTimer("Assemble linear system");
     const int nf = seq.GetNumberOfForms(), uform = nf - 2, pform = nf - 1;
@@ -317,6 +316,24 @@ extern "C" int pe_api_sequence_assemble_darcy(pe_sequence *s, int level, pe_mat 
     pe_mat *M = mass(uform), *W = mass(pform), *D = upload(*seq.GetDerivativeOperator(uform)), *B = nullptr, *Bt = nullptr;
     PE_CALL(pe_spgemm(ctx, W, D, &B));
     pe_mat_free(W); pe_mat_free(D);
+    if (seq.IsParallel())
+    {
+        // the rank-local blocks become ParCSR matrices on true dofs: Assemble(dofTrueDof, ., dofTrueDof)
+        // (examples/MultigridTestDarcy.cpp: pM, pB; SharingMap.cpp:975-1011); B^T by the distributed transpose
+        auto download = [&](pe_mat *m)
+        {
+            int32_t nr = 0, nc = 0; int64_t nnz = 0;
+            PE_CALL(pe_mat_info(m, &nr, &nc, nullptr, &nnz, nullptr));
+            HostCSR L;
+            L.nrows = nr; L.ncols = nc; L.I.resize(nr + 1); L.J.resize(nnz); L.A.resize(nnz);
+            PE_CALL(pe_mat_download(m, L.I.data(), L.J.data(), L.A.data(), nullptr, nullptr, nullptr, nullptr));
+            pe_mat_free(m);
+            return L;
+        };
+        const HostCSR Ml = download(M), Bl = download(B);
+        M = seq.AssembleTrue(uform, Ml, uform)->Release();
+        B = seq.AssembleTrue(pform, Bl, uform)->Release();
+    }
     PE_CALL(pe_mat_transpose(ctx, B, &Bt));
     *M_out = M; *B_out = B; *Bt_out = Bt;
     API_CATCH

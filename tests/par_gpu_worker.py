@@ -29,7 +29,10 @@ def main():
     api.set_host_comm(comm)
     # the path under test is the one that runs: NVLink peer-memory halo (CUDA IPC arenas mapped) or NCCL send/recv
     assert capi.lib().pe_ctx_p2p_enabled(ctx.h) == (1 if halo == "p2p" else 0), "halo path %s not active" % halo
-    rep = parity_checks.multi_rank(ctx, rank, size, deform=os.environ.get("PE_TEST_DEFORM", "0") == "1")
+    if os.environ.get("PE_TEST_CASE", "hdiv") == "darcy":
+        rep = parity_checks.multi_rank_darcy(ctx, rank, size)
+    else:
+        rep = parity_checks.multi_rank(ctx, rank, size, deform=os.environ.get("PE_TEST_DEFORM", "0") == "1")
     dist.barrier()
     if rank == 0:
         print("PAR_GPU_WORKER_OK halo=%s %s" % (halo, rep))

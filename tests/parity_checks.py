@@ -298,3 +298,49 @@ def multi_rank(ctx, rank, size, deform=False, n=4, lev=3, group=None):
     return {"ranks": int(size), "boxes": "%dx%dx%d of %d^3 hexahedra%s" % (procs + (n, ", trilinear (3DHdivWeakScaling map)" if deform else "")),
             "levels": int(lev), "pcg_history_max_rel": float(rel.max()), "pcg_iterations": [int(it), int(ito)],
             "hybrid_gs_pcg_iterations": int(it2)}
+
+
+def multi_rank_darcy(ctx, rank, size, n=4, lev=3, group=None):
+    """configs "MultigridTestDarcy" on the box decomposition: [[M B^T][B 0]] assembled on true dofs (SharingMap
+    Assemble), blocked AMGe hierarchy (P_i^T A_ij P_j by the distributed triple product with R != P), Block Jacobi
+    smoother with the DIAGONAL Schur complement (distributed A10 diag(A00)^{-1} A01 and ParCSR addition), GMRES -- against
+    the oracle's single-domain solver.  Smoothers are l1-Jacobi: independent of the partition, so the monitored norms of
+    the two runs agree to rounding."""
+    global _GROUP
+    _GROUP = group
+    procs = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[size]
+    N = tuple(n * p for p in procs)
+    S = api.Sequence.hex_par(procs, (n, n, n), lev, L=(1.0, 1.0, 1.0), jstart=2)
+    mesh_g, seqs = amge.build_hierarchy(N, lev, L=tuple(float(p) for p in procs), jstart=2)
+    okeys = {j: oracle_dof_keys(seqs, j) for j in (2, 3)}
+    perms = {j: [true_to_oracle(S.dofmap(l, j), okeys[j][l]) for l in range(lev)] for j in (2, 3)}
+    M, B, Bt = S.assemble_darcy(ctx, 0)
+    Mo, Bo = drivers.darcy_blocks(seqs[0])
+    Mg, _ = gather_matrix(M)
+    Bg, _ = gather_matrix(B)
+    Btg, _ = gather_matrix(Bt)
+    for X, Y, pr, pc, what in ((Mg, Mo, 2, 2, "M"), (Bg, Bo, 3, 2, "B"), (Btg, sp.csr_matrix(Bo.T), 2, 3, "B^T")):
+        Xp = permuted(X.v, perms[pr][0], perms[pc][0])
+        assert abs(Xp - sp.csr_matrix(Y)).max() <= 1e-13 * abs(Y).max(), what
+    m2, m3 = S.dofmap(0, 2), S.dofmap(0, 3)
+    mine2 = perms[2][0][m2["start"]:m2["start"] + m2["ntrue"]]
+    mine3 = perms[3][0][m3["start"]:m3["start"] + m3["ntrue"]]
+    nu_g = len(perms[2][0])
+    rng = np.random.default_rng(5)
+    bg = np.concatenate([rng.standard_normal(nu_g), rng.standard_normal(len(perms[3][0]))])
+    A0, prec = drivers.darcy_solver(seqs, block="Block Jacobi", smoother_type=1)
+    xo, ito, convo, histo = orc.gmres(A0.mult, prec, bg, rtol=1e-6, atol=1e-6, max_iter=300, restart=50)
+    xml = api.library_xml(drivers.darcy_library_entries(block="Block Jacobi", smoother="L1 Jacobi"))
+    solver = api.BlockSolver(xml, "GMRES-AMGe-Blk", [[M, Bt], [B, None]], S, 0, [2, 3])
+    x = solver.mult(np.concatenate([bg[mine2], bg[nu_g + mine3]]))
+    hist, it, conv = solver.history()
+    assert conv and convo and abs(it - ito) <= 1, (it, ito, conv, convo)
+    mlen = min(len(hist), len(histo))
+    ho = np.array(histo[:mlen])
+    sel = ho > 1e-8 * ho[0]
+    rel = np.abs(hist[:mlen] - ho)[sel] / ho[sel]
+    assert rel.max() < 1e-8, rel
+    agree(np.abs(x - np.concatenate([xo[mine2], xo[nu_g + mine3]])).max() <= 1e-6 * np.abs(xo).max(), "GMRES solution")
+    solver.free(); S.free()
+    return {"ranks": int(size), "boxes": "%dx%dx%d of %d^3 hexahedra" % (procs + (n,)), "gmres_history_max_rel": float(rel.max()),
+            "gmres_iterations": [int(it), int(ito)]}

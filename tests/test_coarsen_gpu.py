@@ -120,6 +120,19 @@ def test_coarsen_jform_start_and_rectangular_domain(sess):
     S.free()
 
 
+def test_coarsen_ragged_cartesian_grid(sess):
+    """A grid that is not a multiple of the coarsening ratio (the shape of the 60 x 220 x 85 SPE10 grid): logical
+    Cartesian agglomeration with thin last blocks (LogicalPartitioner.hpp:46-103), anisotropic cells, lognormal
+    coefficient in the H(div) mass matrix."""
+    dims, L = (6, 5, 3), (120.0, 50.0, 6.0)
+    rng = np.random.default_rng(19)
+    kinv = 10.0 ** (-np.clip(rng.normal(-1.0, 1.5, size=dims[0] * dims[1] * dims[2]), -4.0, 2.0))
+    mesh, seqs = amge.build_hierarchy(dims, 3, L=L, beta=kinv, jstart=2)
+    S = api.Sequence.hex(dims, 3, L=L, beta=kinv, jstart=2)
+    compare_levels(S, seqs, tol=1e-10, null_tol=1e-8)
+    S.free()
+
+
 def test_invariants_on_device_result(sess):
     """DeRhamSequence::CheckInvariants on the product's own output."""
     dims = (8, 8, 8)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
-from parelag_b200 import api
+from parelag_b200 import api, capi
 from oracle import amge, drivers, solve as orc
 
 pytestmark = pytest.mark.gpu
@@ -107,4 +107,30 @@ def test_spe10_shaped_darcy_block_ldu(sess):
     ho = np.array(histo[:m])
     sel = ho > 1e-7 * ho[0]
     assert (np.abs(hist[:m] - ho)[sel] / ho[sel]).max() < 1e-7
+    solver.free(); S.free()
+
+
+def test_mass_schur_complement(sess, hier):
+    """"S Type" = "MASS" (SchurComplementFactory.cpp:43-50): the second diagonal operator of the block preconditioner is
+    sequence.ComputeTrueM(forms.front()) -- DofHandler-assembled mass matrix of that form -- negated by the default
+    "Use Negative S".  2x2 system on the L2 space (forms 3, 3) so that the block sizes match."""
+    mesh, seqs = hier
+    S = api.Sequence.hex((8, 8, 8), 3, jstart=2)
+    W = sp.csr_matrix(seqs[0].mass_operator(3))
+    n = W.shape[0]
+    rng = np.random.default_rng(41)
+    K = sp.csr_matrix(sp.diags(rng.uniform(1.0, 2.0, n)) @ W)
+    blocks = [[K, sp.csr_matrix(0.1 * W)], [sp.csr_matrix(0.1 * W), sp.csr_matrix(3.0 * W)]]
+    A0 = orc.BlockOp(blocks)
+    J0, J1 = orc.Smoother(K, type=1), orc.Smoother(sp.csr_matrix(-W), type=1)
+    bj = orc.BlockJacobi(A0, [lambda r: J0.apply(r, np.zeros_like(r), False), lambda r: J1.apply(r, np.zeros_like(r), False)])
+    b = rng.standard_normal(2 * n)
+    lib = {"J": ("Hypre", {"Type": "L1 Jacobi", "Sweeps": 1}),
+           "Blk": ("Block Jacobi", {"A00 Inverse": "J", "A11 Inverse": "J", "S Type": "Mass"})}
+    dev = [[capi.Mat.from_scipy(sess, blocks[i][j]) for j in range(2)] for i in range(2)]
+    solver = api.BlockSolver(api.library_xml(lib), "Blk", dev, S, 0, [3, 3])
+    x = solver.mult(b)
+    xo = bj.apply(b, np.zeros_like(b), False)
+    assert np.linalg.norm(x - xo) <= 1e-13 * np.linalg.norm(xo)
+    assert np.linalg.norm(x[n:] + orc.Smoother(W, type=1).apply(b[n:], np.zeros(n), False)) <= 1e-13 * np.linalg.norm(x)   # -W, not 3W
     solver.free(); S.free()

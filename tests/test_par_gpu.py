@@ -29,3 +29,16 @@ def test_box_decomposed_hierarchy_matches_single_domain(nranks, halo, deform):
            "127.0.0.1", "--master-port", str(29540 + nranks), os.path.join(ROOT, "tests", "par_gpu_worker.py")]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "PAR_GPU_WORKER_OK" in r.stdout, r.stdout[-4000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_box_decomposed_darcy_matches_single_domain(nranks):
+    """mixed (Darcy) system on the box decomposition: distributed block assembly, blocked hierarchy (R != P triple
+    products), DIAGONAL Schur complement (distributed A B and a A + b B), GMRES history vs the single-domain oracle"""
+    if _ngpus() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    env = dict(os.environ, OMP_NUM_THREADS="1", PE_TEST_HALO="p2p", PE_TEST_CASE="darcy")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nranks, "--master-addr",
+           "127.0.0.1", "--master-port", str(29560 + nranks), os.path.join(ROOT, "tests", "par_gpu_worker.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "PAR_GPU_WORKER_OK" in r.stdout, r.stdout[-4000:] + r.stderr[-4000:]

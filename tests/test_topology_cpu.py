@@ -14,7 +14,10 @@ def same(A, B):
 
 
 # the last case is large enough (> 4096 rows per table) for the row-parallel host SpGEMM to use several threads
-@pytest.mark.parametrize("dims,nlev", [((4, 4, 4), 3), ((4, 6, 2), 2), ((8, 4, 4), 3), ((24, 16, 16), 3)])
+# (6, 5, 3), (15, 11, 7): not multiples of two -- logical Cartesian agglomeration with ragged last blocks
+# (LogicalPartitioner.hpp:46-103; the shape of the 60 x 220 x 85 SPE10 grid, whose third level is 15 x 55 x 22)
+@pytest.mark.parametrize("dims,nlev", [((4, 4, 4), 3), ((4, 6, 2), 2), ((8, 4, 4), 3), ((24, 16, 16), 3), ((6, 5, 3), 3),
+                                       ((15, 11, 7), 4)])
 def test_topology_hierarchy_bit_exact(dims, nlev):
     S = api.Sequence.hex(dims, nlev, svd_tol=-1.0)
     mesh = amge.HexMesh(*dims)
@@ -29,7 +32,7 @@ def test_topology_hierarchy_bit_exact(dims, nlev):
             for c in range(4):
                 assert same(S.get_csr(l, "AE", c), topo.AE_entity[c]), (l, c)
             topo = ctopo
-            d = (d[0] // 2, d[1] // 2, d[2] // 2)
+            d = amge.coarse_dims(d)
     S.free()
 
 
