@@ -57,6 +57,15 @@ int pe_api_hexsequence_create(int nx, int ny, int nz, double Lx, double Ly, doub
  * all four forms are built by quadrature (mfem's rules: DeRhamSequenceFE.cpp:633-684, bilinIntegrators.cpp:64-157). */
 int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const double *vertex_xyz, const double *alpha,
                                        const double *beta, int jform_start, int nlevels, double svd_tol, pe_sequence **out);
+/* Unstructured tetrahedral meshes (BASELINE configs[0], examples/MultigridTest0Form.cpp:147-375 on meshes/cube456.mesh):
+ * the given mesh (0-based vertex numbers; boundary triangles with 1-based attributes) is refined nref times (red
+ * refinement, children of element e = 8e .. 8e+7), the finest mesh is level 0 of the sequence and the nlevels - 1 <= nref
+ * coarser levels are built by derefinement agglomeration (MFEMRefinedMeshPartitioner.cpp:48-66) and Coarsen().
+ * Lowest-order Whitney forms with MFEM's dof meaning; mass matrices in closed form (parelag_b200/src/amge_tet.hpp).
+ * pe_api_tetsequence_create_from_file reads the NETGEN neutral format of meshes/cube456.mesh (mfem::Mesh(imesh, 1, 1)). */
+int pe_api_tetsequence_create(int nv, const double *vertex_xyz, int nel, const int32_t *tets, int nbdr, const int32_t *bdr_triangles,
+                              const int32_t *bdr_attributes, int nref, int nlevels, int jform_start, double svd_tol, pe_sequence **out);
+int pe_api_tetsequence_create_from_file(const char *mesh_file, int nref, int nlevels, int jform_start, double svd_tol, pe_sequence **out);
 /* ---- multi-rank (one rank <-> one box of a P0 x P1 x P2 box decomposition <-> one GPU).
  * pe_api_session_set_host_comm: the setup-time host communicator (MPI_Comm in the reference).
  * pe_api_hexsequence_create_par: as pe_api_hexsequence_create for THIS rank's box (nx,ny,nz hexahedra

@@ -76,6 +76,24 @@ class Sequence:
         return S
 
     @staticmethod
+    def tet(V, T, Btri, Battr, nref, nlevels, jstart=0, svd_tol=1e-9):
+        """Full coarsening path on a tetrahedral mesh refined nref times (V: (nv,3); T: (nel,4) 0-based; Btri: (nb,3);
+        Battr: (nb,) 1-based boundary attributes); svd_tol < 0: topology and fine sequence only."""
+        S = Sequence.__new__(Sequence)
+        S.h = C.c_void_p()
+        X, Tt, Bt, Ba = _f64(np.ascontiguousarray(V).ravel()), _i32(np.ascontiguousarray(T).ravel()), _i32(np.ascontiguousarray(Btri).ravel()), _i32(Battr)
+        _chk(lib().pe_api_tetsequence_create(len(X) // 3, _ptr(X), len(Tt) // 4, _ptr(Tt), len(Ba), _ptr(Bt), _ptr(Ba), nref, nlevels, jstart,
+                                             C.c_double(svd_tol), C.byref(S.h)))
+        return S
+
+    @staticmethod
+    def tet_from_file(path, nref, nlevels, jstart=0, svd_tol=1e-9):
+        S = Sequence.__new__(Sequence)
+        S.h = C.c_void_p()
+        _chk(lib().pe_api_tetsequence_create_from_file(path.encode(), nref, nlevels, jstart, C.c_double(svd_tol), C.byref(S.h)))
+        return S
+
+    @staticmethod
     def hex_par(procs, dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9, coords=None):
         """The same on THIS rank's box (dims hexahedra of extent L) of a procs[0] x procs[1] x procs[2] box
         decomposition; needs set_host_comm().  coords: optional (nv, 3) moved vertices of this rank's box."""

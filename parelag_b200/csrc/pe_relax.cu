@@ -207,12 +207,15 @@ k_gs_sweep(int nsteps, const int2 *__restrict__ steps, const int *__restrict__ p
     for (int t = 0; t < nsteps; ++t)
     {
         const int2 st = steps[t];
-        for (int k = st.x + g0; k < st.y; k += gstride)
+        // the trip count is uniform over the CTA (kb does not depend on the thread): the full-mask shuffles below are
+        // executed by every lane, rows past the end of the colour are predicated off
+        for (int kb = st.x; kb < st.y; kb += gstride)
         {
-            const int lo = pI[k], hi = pI[k + 1], i = perm[k];
-            const double d = l1[i];
-            double fi = 0.0, ui = 0.0;
-            if (lane == 0) { fi = f[i]; ui = __ldcg(u + i); }
+            const int k = kb + g0;
+            const bool on = k < st.y;
+            int lo = 0, hi = 0, i = 0;
+            double d = 0.0, fi = 0.0, ui = 0.0;
+            if (on) { lo = pI[k]; hi = pI[k + 1]; i = perm[k]; d = l1[i]; if (lane == 0) { fi = f[i]; ui = __ldcg(u + i); } }
             double s = 0.0;
             for (int q = lo + lane; q < hi; q += TPR)
             {
@@ -222,7 +225,7 @@ k_gs_sweep(int nsteps, const int2 *__restrict__ steps, const int *__restrict__ p
             }
 #pragma unroll
             for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
-            if (lane == 0 && d != 0.0) __stcg(u + i, ui + (fi - s) / d);
+            if (on && lane == 0 && d != 0.0) __stcg(u + i, ui + (fi - s) / d);
         }
         if (t + 1 < nsteps) grid_barrier(bar);
     }

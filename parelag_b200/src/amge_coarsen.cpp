@@ -673,4 +673,56 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
     }
     return seq;
 }
+std::vector<std::shared_ptr<DeRhamSequence>> BuildTetSequenceHierarchy(const TetMesh &coarse_mesh, int nref, int nlevels, const double *alpha,
+                                                                        const double *beta, int jstart, double svd_tol)
+{
+    PARELAG_TEST_FOR_EXCEPTION(nlevels < 1 || nlevels - 1 > nref, std::runtime_error,
+                               "BuildTetSequenceHierarchy: " << nlevels << " levels need at least " << nlevels - 1 << " refinements");
+    TetMesh mesh = coarse_mesh;
+    {
+        Timer t = TimeManager::AddTimer("Mesh refinement");
+        for (int r = 0; r < nref; ++r) mesh = mesh.Refine();
+    }
+    const size_t nel_all = (size_t)mesh.nel();
+    if (nel_all * 6000 <= HostMemAvailable() / 4 * 3) ReserveHostArena(std::min(nel_all * (size_t)2000, (size_t)16 << 30), 1);
+    std::vector<std::shared_ptr<AgglomeratedTopology>> topo(nlevels);
+    {
+        Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level 0");
+        topo[0] = mesh.Topology();
+    }
+    int n = mesh.nel();
+    for (int l = 0; l + 1 < nlevels; ++l)
+    {
+        Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level " + std::to_string(l + 1));
+        std::vector<int> part((size_t)n);
+        for (int e = 0; e < n; ++e) part[e] = e / 8;
+        topo[l + 1] = topo[l]->CoarsenLocalPartitioning(part);
+        n /= 8;
+    }
+    std::vector<std::shared_ptr<DeRhamSequence>> seq(nlevels);
+    {
+        Timer t = TimeManager::AddTimer("DeRhamSequence Construction -- Level 0");
+        seq[0] = std::make_shared<DeRhamSequence>(4);
+        seq[0]->data = std::make_shared<SequenceData>();
+        std::vector<HostCSR> D;
+        BuildFineTetSequence(mesh, topo[0], alpha, beta, jstart, *seq[0]->data, D);
+        for (int j = 0; j < 3; ++j) seq[0]->SetD(j, D[j]);
+        for (int j = 0; j < 4; ++j) seq[0]->SetDofHandlerRaw(j, seq[0]->data->dof[j].get());
+    }
+    if (svd_tol < 0.0)
+        for (int l = 1; l < nlevels; ++l)
+        {
+            seq[l] = std::make_shared<DeRhamSequence>(4);
+            seq[l]->data = std::make_shared<SequenceData>();
+            seq[l]->data->topo = topo[l];
+        }
+    else
+        for (int l = 0; l + 1 < nlevels; ++l)
+        {
+            Timer t = TimeManager::AddTimer("DeRhamSequence Construction -- Level " + std::to_string(l + 1));
+            seq[l]->SetSVDTol(svd_tol);
+            seq[l + 1] = seq[l]->Coarsen();
+        }
+    return seq;
+}
 } // namespace parelag

@@ -1,6 +1,7 @@
 // amge_coarsen.hpp -- entry points of the coarsening path (see amge_coarsen.cpp)
 #pragma once
 #include "amge_hex.hpp"
+#include "amge_tet.hpp"
 
 namespace parelag
 {
@@ -20,4 +21,9 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
                                                                            double Lx, double Ly, double Lz, const double *alpha,
                                                                            const double *beta, int jstart, int nlevels, double svd_tol,
                                                                            const double *vertex_coords = nullptr);
+/// The same on an unstructured tetrahedral mesh (examples/MultigridTest0Form.cpp:147-375, BASELINE configs[0]): the coarse
+/// mesh is refined `nref` times (serial + parallel refinements of the driver), the finest mesh is level 0 and the
+/// nlevels - 1 <= nref coarser levels come from derefinement (MFEMRefinedMeshPartitioner: partition = element / 8).
+std::vector<std::shared_ptr<DeRhamSequence>> BuildTetSequenceHierarchy(const TetMesh &coarse_mesh, int nref, int nlevels, const double *alpha,
+                                                                        const double *beta, int jstart, double svd_tol);
 } // namespace parelag

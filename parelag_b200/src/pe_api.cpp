@@ -172,6 +172,26 @@ extern "C" int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const 
     *out = s;
     API_CATCH
 }
+extern "C" int pe_api_tetsequence_create(int nv, const double *vertex_xyz, int nel, const int32_t *tets, int nbdr, const int32_t *bdr_triangles,
+                                         const int32_t *bdr_attributes, int nref, int nlevels, int jstart, double svd_tol, pe_sequence **out)
+{
+    API_TRY
+    PARELAG_TEST_FOR_EXCEPTION(!vertex_xyz || !tets || nv < 4 || nel < 1, std::runtime_error, "pe_api_tetsequence_create: empty mesh");
+    auto s = new pe_sequence();
+    const TetMesh mesh = TetMesh::FromArrays(nv, vertex_xyz, nel, tets, nbdr, bdr_triangles, bdr_attributes);
+    s->levels = BuildTetSequenceHierarchy(mesh, nref, nlevels, nullptr, nullptr, jstart, svd_tol);
+    *out = s;
+    API_CATCH
+}
+extern "C" int pe_api_tetsequence_create_from_file(const char *mesh_file, int nref, int nlevels, int jstart, double svd_tol, pe_sequence **out)
+{
+    API_TRY
+    auto s = new pe_sequence();
+    const TetMesh mesh = TetMesh::ReadNetgenNeutral(mesh_file);
+    s->levels = BuildTetSequenceHierarchy(mesh, nref, nlevels, nullptr, nullptr, jstart, svd_tol);
+    *out = s;
+    API_CATCH
+}
 static HostCSR pool_as_csr(const BlockPool &P)
 {
     HostCSR M;
