@@ -69,6 +69,38 @@ def library(ordering, form=2):
     }
 
 
+def library_h1(ordering):
+    """examples/testing_helpers/Create0FormParameterList.hpp with the hot-path-only coarse solver"""
+    hyp = ("Hypre", {"Type": "L1 Gauss-Seidel", "Sweeps": 1, "Damping Factor": 1.0, "Omega": 1.0, "GS ordering": ordering})
+    return {
+        "Gauss-Seidel": hyp,
+        "PCG-GS": ("Krylov", {"Solver name": "PCG", "Preconditioner": "Gauss-Seidel", "Print level": -1, "Maximum iterations": 3,
+                              "Relative tolerance": 1e-4, "Absolute tolerance": 1e-4}),
+        "AMGe-GS_0": ("AMGe", {"Maximum levels": -1, "Forms": [0], "PreSmoother": "Gauss-Seidel", "PostSmoother": "Gauss-Seidel",
+                               "Coarse solver": "PCG-GS", "Cycle type": "V-cycle"}),
+        "PCG with Auxiliary Space Preconditioner": (
+            "Krylov", {"Solver name": "PCG", "Preconditioner": "AMGe-GS_0", "Print level": -1, "Maximum iterations": 300,
+                       "Relative tolerance": 1e-6, "Absolute tolerance": 1e-6}),
+    }
+
+
+def library_darcy(ordering):
+    """examples/example_parameterlists/darcy_example_parameters.xml: GMRES(50) preconditioned by the blocked AMGe
+    (Forms 2 3) with a Block Jacobi smoother (A00: l1-GS, S = -(B diag(M)^-1 B^T): l1-GS); coarse solver GMRES + the same"""
+    gs = ("Hypre", {"Type": "L1 Gauss-Seidel", "Sweeps": 1, "Damping Factor": 1.0, "Omega": 1.0, "GS ordering": ordering})
+    return {
+        "Gauss-Seidel": gs,
+        "Blk": ("Block Jacobi", {"A00 Inverse": "Gauss-Seidel", "A11 Inverse": "Gauss-Seidel", "Alpha": 1.0, "S Type": "Diagonal"}),
+        "GMRES-Blk": ("Krylov", {"Solver name": "GMRES", "Preconditioner": "Blk", "Print level": -1, "Maximum iterations": 5,
+                                 "Relative tolerance": 1e-4, "Absolute tolerance": 1e-4, "Restart size": 50}),
+        "AMGe-Blk": ("AMGe", {"Maximum levels": -1, "Forms": [2, 3], "PreSmoother": "Blk", "PostSmoother": "Blk",
+                              "Coarse solver": "GMRES-Blk", "Cycle type": "V-cycle"}),
+        "GMRES with blocked AMGe": ("Krylov", {"Solver name": "GMRES", "Preconditioner": "AMGe-Blk", "Print level": -1,
+                                               "Maximum iterations": 300, "Relative tolerance": 1e-6, "Absolute tolerance": 1e-6,
+                                               "Restart size": 50}),
+    }
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -213,6 +245,21 @@ def workload_name(gpus, n, ndofs_box, levels, deformed):
             "Hiptmair(l1-GS,l1-GS), PCG-GS coarse solver" % (n, ndofs_box, levels))
 
 
+def other_workload_name(cfg, n, ndofs, levels, args):
+    if cfg == "cfg1":
+        return ("MultigridTest0Form (configs[0]): H1 Laplacian A=D0^T M1 D0 on meshes/cube456.mesh refined %d times (tetrahedra), "
+                "%d dofs, %d-level AMGe by derefinement, l1-GS smoothers, PCG-GS coarse solver" % (args.nref, ndofs, levels))
+    if cfg == "hcurl":
+        return ("MultigridTest1Form (configs[2]): H(curl) A=M1+D1^T M2 D1, %d^3 hexahedra, %d Nedelec dofs, %d-level AMGe, "
+                "Hiptmair(l1-GS,l1-GS) with the H1 auxiliary space, PCG-GS coarse solver" % (n, ndofs, levels))
+    if cfg == "darcy":
+        return ("MultigridTestDarcy (configs[1]): mixed system [[M B^T][B 0]], %d^3 hexahedra, %d dofs (RT0 + L2), %d-level blocked "
+                "AMGe (Forms 2 3), Block Jacobi smoother (l1-GS on M and on the DIAGONAL Schur complement), GMRES(50)" % (n, ndofs, levels))
+    return ("MultigridTestSPE10-shaped (configs[3]): 60x220x85 cells of 20x10x2, synthetic lognormal permeability (4+ decades), mixed "
+            "system [[M B^T][B 0]], %d dofs, %d-level blocked AMGe (logical Cartesian agglomeration with ragged blocks), "
+            "Block Jacobi smoother, GMRES(50)" % (ndofs, levels))
+
+
 def levels_for(n, cap):
     lv = 1
     while n % (2 ** lv) == 0 and lv < cap:
@@ -305,10 +352,18 @@ def main():
     ap.add_argument("--no-cpu-setup", action="store_true", help="skip the CPU setup baseline (oracle Coarsen on 16^3)")
     ap.add_argument("--no-deform", action="store_true", help="N > 1: axis-aligned boxes instead of the configs[4] geometry")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block")
+    ap.add_argument("--config", default="hdiv", choices=["hdiv", "cfg1", "hcurl", "darcy", "spe10"],
+                    help="N = 1 workload: hdiv = BASELINE configs[1] MultigridTest2Form (the headline), cfg1 = configs[0] "
+                         "MultigridTest0Form (H1 on meshes/cube456.mesh, --nref refinements, 3 levels), hcurl = configs[2] "
+                         "MultigridTest1Form (--size 192), darcy = configs[1] MultigridTestDarcy (--size 136, 4 levels), "
+                         "spe10 = configs[3] (60x220x85 cells, synthetic lognormal permeability, mixed Darcy)")
+    ap.add_argument("--nref", type=int, default=4, help="cfg1: uniform refinements of cube456.mesh (driver: 2 serial + 2 parallel)")
     ap.add_argument("--cpu-n", type=int, default=32, help="bounded sample of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sell-min-rows", type=int, default=None,
                     help="tuning: levels with fewer rows use the lanes-per-row CSR Gauss-Seidel kernel (library default 200000)")
+    ap.add_argument("--gs-slabs", type=int, default=None, help="tuning: PE_TUNE_GS_SLABS (slab-major multicolour order on >= 4M-row levels)")
+    ap.add_argument("--fused-gs-mb", type=int, default=None, help="tuning: PE_TUNE_FUSED_GS_MAX_MB (0 = one launch per colour)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo exchange: NVLink peer-memory stores (default) or ncclSend/ncclRecv")
     ap.add_argument("--profile-range", action="store_true",
@@ -321,6 +376,9 @@ def main():
         run_reference(args, rank)
         return
     args.warmup = max(args.warmup, 3)
+    # host threads of the setup (OpenMP in the host integer work): torchrun exports OMP_NUM_THREADS=1, which made the
+    # multi-rank setup single-threaded; every rank gets its share of the cores instead (set before libgomp is loaded)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // max(world, 1)))
 
     import torch
     dist = None
@@ -359,13 +417,28 @@ def main():
     api.lib().pe_api_timer_clear()
     if args.sell_min_rows is not None:
         capi.set_tuning(capi.TUNE_SELL_MIN_ROWS, args.sell_min_rows)
+    if args.gs_slabs is not None:
+        capi.set_tuning(capi.TUNE_GS_SLABS, args.gs_slabs)
+    if args.fused_gs_mb is not None:
+        capi.set_tuning(capi.TUNE_FUSED_GS_MAX_MB, args.fused_gs_mb)
 
+    cfg = args.config
+    if world > 1 and cfg != "hdiv":
+        raise SystemExit("bench.py: --config %s is a single-GPU workload" % cfg)
+    mixed = cfg in ("darcy", "spe10")
+    form = {"hdiv": 2, "hcurl": 1, "cfg1": 0}.get(cfg, 2)
+    if cfg == "hcurl" and args.n == 144:
+        n, levels = 192, 4
+    if cfg == "darcy" and args.n == 144:
+        n, levels = 136, 4
+    if cfg == "spe10":
+        levels = 4
     # ---------------- parity block (the oracle is the checker; nothing of it is timed or shipped)
     deformed = world > 1 and not args.no_deform
     ess = np.array([0, 1, 1, 1, 1, 0], dtype=np.int32) if deformed else ESS     # 3DHdivWeakScaling.cpp:53-66
     parity = None
     host_group = api._host_comm.group if world > 1 else None
-    if not args.no_parity:
+    if not args.no_parity and cfg == "hdiv":
         try:
             from tests import parity_checks
             if world > 1:
@@ -388,6 +461,19 @@ def main():
         del X
     elif world > 1:
         S = api.Sequence.hex_par(procs, (n, n, n), levels, L=(1.0, 1.0, 1.0), jstart=args.jstart)
+    elif cfg == "cfg1":
+        levels = 3
+        S = api.Sequence.tet_from_file(os.path.join(ROOT, "tests", "golden", "cube456.mesh"), args.nref, levels, jstart=0)
+    elif cfg == "hcurl":
+        S = api.Sequence.hex((n, n, n), levels, jstart=0)
+    elif cfg == "darcy":
+        S = api.Sequence.hex((n, n, n), levels, jstart=2)
+    elif cfg == "spe10":
+        # SPE10-shaped (InversePermeabilityFunction.cpp:254-259: 60 x 220 x 85 cells of 20 x 10 x 2 ft); synthetic
+        # lognormal permeability (the data set is not available offline): log10 k ~ N(-1, 1.5^2) clipped to [-4, 2]
+        dims, Lspe = (60, 220, 85), (1200.0, 2200.0, 170.0)
+        kinv = 10.0 ** (-np.clip(np.random.default_rng(13).normal(-1.0, 1.5, size=dims[0] * dims[1] * dims[2]), -4.0, 2.0))
+        S = api.Sequence.hex(dims, levels, L=Lspe, beta=kinv, jstart=2)
     else:
         S = api.Sequence.hex((n, n, n), levels, jstart=args.jstart)
     ctx.sync()
@@ -398,10 +484,18 @@ def main():
     ext_stages = {"h2d_s": st6[0], "kernel_s": st6[1], "d2h_s": st6[2], "h2d_GB": st6[3] / 1e9, "d2h_GB": st6[4] / 1e9,
                   "calls": int(st6[5])}
     t0 = time.perf_counter()
-    A = S.assemble_system(ctx, 0, 2, ess)
+    blocks = None
+    if mixed:
+        Mb, Bb, Btb = S.assemble_darcy(ctx, 0)
+        blocks = [[Mb, Btb], [Bb, None]]
+        A = Mb                                # the SpMV figure is taken on the H(div) mass block
+        ndofs = Mb.info()[0] + Bb.info()[0]
+    else:
+        A = S.assemble_system(ctx, 0, form, ess)
+        ndofs = A.info()[0]                   # true dofs owned by this rank
     ctx.sync()
     t_assemble = time.perf_counter() - t0
-    ndofs = A.info()[0]                       # true dofs owned by this rank
+    nrows0 = A.info()[0]
     nnz0 = A.info()[3] + A.info()[4]
 
     def sum_over_ranks(v):
@@ -414,31 +508,39 @@ def main():
     peak, peak_src = peaks()
     # ---------------- SpMV alone on the fine operator (the "SpMV HBM GB/s vs peak" part of the metric)
     A2 = A
-    xs, ys = capi.Vec(ctx, data=np.random.default_rng(99 + rank).standard_normal(ndofs)), capi.Vec(ctx, ndofs)
+    xs, ys = capi.Vec(ctx, data=np.random.default_rng(99 + rank).standard_normal(nrows0)), capi.Vec(ctx, nrows0)
     for _ in range(3):
         A2.spmv(xs, ys)
     ctx.sync(); ctx.timer_start()
     for _ in range(20):
         A2.spmv(xs, ys)
     ms_spmv = ctx.timer_stop() / 20
-    b_spmv = 12.0 * nnz0 + 4.0 * (ndofs + 1) + 16.0 * ndofs
+    b_spmv = 12.0 * nnz0 + 4.0 * (nrows0 + 1) + 16.0 * nrows0
     spmv = {"ms": ms_spmv, "GBs": b_spmv / ms_spmv / 1e6, "frac_of_measured_peak": b_spmv / ms_spmv / 1e6 / peak,
-            "nnz": nnz0, "rows": ndofs}
+            "nnz": nnz0, "rows": nrows0}
 
     # full-size kernel parity (N = 1): one SpMV and one multicolour GS sweep of THIS operator against solve_oracle.c
-    if parity is not None and parity.get("ok") and world == 1 and not args.profile_range:
+    if parity is not None and parity.get("ok") and world == 1 and cfg == "hdiv" and not args.profile_range:
         try:
             parity["full_size"] = parity_checks.full_size_kernels(ctx, A)
         except AssertionError as e:
             parity["ok"] = False
             parity["failed"] = repr(e)[:400]
     t0 = time.perf_counter()
-    solver = api.Solver(api.library_xml(library(args.ordering)), "PCG with Auxiliary Space Preconditioner",
-                        A, S, 0, 2, ess)
+    if mixed:
+        solver = api.BlockSolver(api.library_xml(library_darcy(args.ordering)), "GMRES with blocked AMGe", blocks, S, 0, [2, 3])
+    elif cfg == "cfg1":
+        solver = api.Solver(api.library_xml(library_h1(args.ordering)), "PCG with Auxiliary Space Preconditioner", A, S, 0, 0, ess)
+    else:
+        solver = api.Solver(api.library_xml(library(args.ordering, form)), "PCG with Auxiliary Space Preconditioner",
+                            A, S, 0, form, ess)
     ctx.sync()
     t_build = time.perf_counter() - t0
-    nlev = solver.num_levels()
-    level_info = [solver.level_info(l) for l in range(nlev)]
+    try:
+        nlev = solver.num_levels()
+        level_info = [solver.level_info(l) for l in range(nlev)]
+    except Exception:                         # blocked hierarchy: the level operators are block operators
+        nlev, level_info = levels, []
     # the reference's TimeManager names (examples/MultigridTest2Form.cpp:248-375, AMGeSolverFactory.cpp)
     timers = {}
     for l in range(levels):
@@ -568,7 +670,7 @@ def main():
     line = None
     if rank == 0:
         cpu_baseline = None
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and cfg == "hdiv":
             from oracle import solve as orc
             orc.set_threads(1)
             lv = levels_for(args.cpu_n, levels)
@@ -583,7 +685,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(world, n, ndofs, nlev, deformed) if (world == 1 or deformed) else
+                "config": {"workload": other_workload_name(cfg, n, ndofs, nlev, args) if cfg != "hdiv" else
+                                       workload_name(world, n, ndofs, nlev, deformed) if (world == 1 or deformed) else
                                        ("3DHdivWeakScaling layout, axis-aligned: %dx%dx%d boxes of %d^3 hexahedra, one box per GPU, all "
                                         "attributes essential, H(div) A=M2+D2^T M3 D2, %d-level AMGe, Hiptmair(l1-GS,l1-GS), PCG-GS "
                                         "coarse solver" % (procs + (n, nlev))),
@@ -597,6 +700,8 @@ def main():
                            "parallelism": ("single GPU" if world == 1 else
                                            "domain decomposition, %d ranks = %d GPUs, one mesh box each" % (world, world)),
                            "jform_start": args.jstart,
+                           "tuning": {"sell_min_rows": capi.get_tuning(capi.TUNE_SELL_MIN_ROWS), "gs_slabs": capi.get_tuning(capi.TUNE_GS_SLABS),
+                                      "fused_gs_max_mb": capi.get_tuning(capi.TUNE_FUSED_GS_MAX_MB), "pdl": capi.get_tuning(capi.TUNE_PDL)},
                            "levels": [{"rows": li[0], "nnz": li[1], "nnz_P": li[2]} for li in level_info]},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
                 "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -102,9 +102,15 @@ int pe_ctx_profile_get(pe_ctx *ctx, int kernel_id, int64_t *count, double *total
  * this runs as ONE persistent cooperative kernel (all colours of the forward and backward pass, grid barriers in
  * between, the colour-order renumbering of the SELL path included) instead of one launch per colour: on the coarse
  * levels a colour is a few thousand rows and a launch costs more than its work.  0 = one launch per colour.
- * Results are bit-identical (same rows, same summation order).  Read when a smoother is created. */
+ * Results are bit-identical (same rows, same summation order).  Read when a smoother is created.
+ * PE_TUNE_GS_SLABS [0]: multicolour Gauss-Seidel on matrices with at least 4 million rows: the rows are cut into this many
+ * contiguous pieces of the matrix graph (breadth-first levels from row 0, equal row counts) and the sweep visits
+ * (slab 0: colours 0..C-1), (slab 1: colours 0..C-1), ... -- still Gauss-Seidel in an order made of independent sets,
+ * but the iterate of one slab (tens of MB) stays in L2 across its C colour launches instead of being re-read from
+ * HBM by every colour of the whole matrix (each colour gathers (C-1)/C of the vector).  0 or 1 = colour-major order.
+ * Read when a smoother is created. */
 enum { PE_TUNE_SELL_MIN_ROWS = 0, PE_TUNE_SELL_GROUP = 1, PE_TUNE_PDL = 2, PE_TUNE_GATHER_KEEP_PCT = 3, PE_TUNE_P2P_HALO = 4,
-       PE_TUNE_FUSED_GS_MAX_MB = 5, PE_TUNE_COUNT = 6 };
+       PE_TUNE_FUSED_GS_MAX_MB = 5, PE_TUNE_GS_SLABS = 6, PE_TUNE_COUNT = 7 };
 int pe_set_tuning(int key, int value);
 int pe_get_tuning(int key);
 /* write a scratch buffer larger than L2 (bench hygiene) */

@@ -135,6 +135,7 @@ TUNE_PDL = 2
 TUNE_GATHER_KEEP_PCT = 3
 TUNE_P2P_HALO = 4
 TUNE_FUSED_GS_MAX_MB = 5
+TUNE_GS_SLABS = 6
 
 
 def set_tuning(key, value):

@@ -373,6 +373,45 @@ static void build_colors(int n, const int *I, const int *J, std::vector<int> &co
     }
 }
 
+// PE_TUNE_GS_SLABS: slab index of every row = quantile of its breadth-first level in the matrix graph (start: row 0;
+// rows the search does not reach -- eliminated boundary rows are isolated -- continue the level count)
+static void build_slabs(int n, const int *I, const int *J, int nslabs, std::vector<int> &slab)
+{
+    std::vector<int> level(n, -1), frontier, next;
+    std::vector<int64_t> count;
+    int lev = 0, seed = 0;
+    int64_t visited = 0;
+    while (visited < n)
+    {
+        while (seed < n && level[seed] >= 0) ++seed;
+        frontier.assign(1, seed);
+        level[seed] = lev;
+        while (!frontier.empty())
+        {
+            count.push_back((int64_t)frontier.size());
+            visited += (int64_t)frontier.size();
+            next.clear();
+            for (int i : frontier)
+                for (int k = I[i]; k < I[i + 1]; ++k)
+                {
+                    const int j = J[k];
+                    if (j < n && level[j] < 0) { level[j] = lev + 1; next.push_back(j); }
+                }
+            frontier.swap(next);
+            ++lev;
+        }
+    }
+    std::vector<int> slab_of_level(count.size());
+    int64_t before = 0;
+    for (size_t l = 0; l < count.size(); ++l)
+    {
+        slab_of_level[l] = (int)std::min<int64_t>(nslabs - 1, before * nslabs / std::max(n, 1));
+        before += count[l];
+    }
+    slab.resize(n);
+    for (int i = 0; i < n; ++i) slab[i] = slab_of_level[level[i]];
+}
+
 #include <cub/cub.cuh>
 
 static int fused_setup(pe_smoother *s);
@@ -404,6 +443,15 @@ static int build_gs_schedule(pe_smoother *s)
             }
     } else {
         build_colors(n, I.data(), J.data(), key, nsets);
+        const int nslabs = pe_get_tuning(PE_TUNE_GS_SLABS);
+        if (nslabs > 1 && n >= 4000000 && nsets >= 2)
+        {
+            // slab-major order: set = slab * colours + colour (rows of one set are still mutually independent)
+            std::vector<int> slab;
+            build_slabs(n, I.data(), J.data(), nslabs, slab);
+            for (int i = 0; i < n; ++i) key[i] += slab[i] * nsets;
+            nsets *= nslabs;
+        }
     }
     // stable counting sort of rows by set id
     s->nsets = nsets;
@@ -735,7 +783,8 @@ extern "C" int pe_smoother_create(pe_ctx *ctx, pe_mat *A, int type, int sweeps, 
     size_t nb = sizeof(double) * (size_t)(n > 0 ? n : 1);
     PE_CUDA(cudaMalloc(&s->l1_d, nb));
     PE_CUDA(cudaMalloc(&s->v_d, nb));
-    if (type == 6) PE_CHECK(damping == 1.0 && omega == 1.0, "type 6 (Gauss-Seidel) supports weight = omega = 1 only");
+    // type 6 (hybrid symmetric Gauss-Seidel, hypre_BoomerAMGRelax): the update of types 2/4 with the diagonal entry in
+    // the place of the l1 norm, relaxation weight and omega included (c1 = omega w, c2 = omega (1 - w) on a saved copy)
     int l1opt = (type == 0 || type == 6 || type == 16) ? 0 : type;
     const int *oI = A->offd.nnz > 0 ? A->offd.I : nullptr;
     k_l1_norms<<<pe_grid_for(n, 256), 256, 0, ctx->stream>>>(n, A->diag.I, A->diag.J, A->diag.A, oI, A->offd.A, l1opt, s->l1_d);

@@ -130,20 +130,22 @@ def gs_kernel(request):
 
 
 @pytest.mark.parametrize("dims", [(11, 6, 7), (21, 20, 19)])
+@pytest.mark.parametrize("stype", [2, 6])
 @pytest.mark.parametrize("weights", [(1.0, 1.0), (0.9, 1.2)])
-def test_gauss_seidel_multicolor(ctx, weights, gs_kernel, dims):
+def test_gauss_seidel_multicolor(ctx, weights, gs_kernel, dims, stype):
+    """stype 6 = hypre's "Gauss-Seidel" (division by the diagonal entry) with relaxation weight and omega"""
     A = laplace3d(*dims)
     n = A.shape[0]
     rng = np.random.default_rng(5)
     b, x0 = rng.standard_normal(n), rng.standard_normal(n)
     dA = capi.Mat.from_scipy(ctx, A)
-    s = capi.Smoother(ctx, dA, type=2, sweeps=2, damping=weights[0], omega=weights[1],
+    s = capi.Smoother(ctx, dA, type=stype, sweeps=2, damping=weights[0], omega=weights[1],
                       ordering=capi.GS_MULTICOLOR)
     order, starts = s.order()
     oorder, ncol = orc.multicolor_order(A)
     assert len(starts) - 1 == ncol
     assert np.array_equal(order, oorder)          # integer parity: bit-exact colouring
-    so = orc.Smoother(A, type=2, sweeps=2, damping=weights[0], omega=weights[1], order=oorder)
+    so = orc.Smoother(A, type=stype, sweeps=2, damping=weights[0], omega=weights[1], order=oorder)
     dx, db = capi.Vec(ctx, data=x0), capi.Vec(ctx, data=b)
     s.apply(db, dx, True)
     assert _rel(dx.download(), so.apply(b, x0, True)) < 1e-13
