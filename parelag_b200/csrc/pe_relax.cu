@@ -886,9 +886,16 @@ static int fused_setup(pe_smoother *s)
     return 0;
 }
 
+// The grid never exceeds what is resident at once (fused_setup), nothing else runs on the device while the kernel does
+// (the stream is serial; the kernel never triggers its dependents early, and its PDL predecessor completes on its own),
+// so an ordinary launch through pe_launch_k -- programmatic dependent launch included -- is enough for the grid barrier.
+// Inside a CUDA graph the cooperative attribute proved expensive (measured: 16 fused launches per V-cycle cost +1.4 ms
+// as cooperative nodes); PE_FUSED_COOP=1 forces it for debugging.
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_cooperative(pe_ctx *ctx, void (*kern)(KArgs...), int grid, Args... args)
 {
+    static const bool coop = getenv("PE_FUSED_COOP") && atoi(getenv("PE_FUSED_COOP")) != 0;
+    if (!coop) return pe_launch_k(ctx, kern, grid, 256, args...);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3(256, 1, 1);
