@@ -1,7 +1,7 @@
 # Build the C-ABI shared library (CUDA, sm_100a) and the oracle (test infrastructure).
 NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v --expt-relaxed-constexpr
+NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -fopenmp -Xcompiler -Wall -Xptxas -v --expt-relaxed-constexpr
 CSRC      := $(wildcard parelag_b200/csrc/*.cu)
 HSRC      := $(wildcard parelag_b200/src/*.cpp)
 OBJ       := $(patsubst %.cu,build/%.o,$(CSRC)) $(patsubst %.cpp,build/%.o,$(HSRC))

@@ -98,17 +98,20 @@ int pe_ctx_profile_get(pe_ctx *ctx, int kernel_id, int64_t *count, double *total
  * PE_TUNE_P2P_HALO [1]: multi-rank, one node: ParCSR halo exchange by direct stores into the neighbours' ghost
  * buffers over NVLink peer memory (CUDA IPC) with device-side arrival flags instead of ncclSend/ncclRecv.
  * Read at pe_ctx_set_host_comm; falls back to NCCL when a rank cannot map a peer.
- * PE_TUNE_FUSED_GS_MAX_MB [24]: a multicolour Gauss-Seidel sweep whose LARGEST colour moves fewer algorithmic megabytes than
- * this runs as ONE persistent cooperative kernel (all colours of the forward and backward pass, grid barriers in
- * between, the colour-order renumbering of the SELL path included) instead of one launch per colour: on the coarse
- * levels a colour is a few thousand rows and a launch costs more than its work.  0 = one launch per colour.
- * Results are bit-identical (same rows, same summation order).  Read when a smoother is created.
- * PE_TUNE_GS_SLABS [0]: multicolour Gauss-Seidel on matrices with at least 4 million rows: the rows are cut into this many
- * contiguous pieces of the matrix graph (breadth-first levels from row 0, equal row counts) and the sweep visits
- * (slab 0: colours 0..C-1), (slab 1: colours 0..C-1), ... -- still Gauss-Seidel in an order made of independent sets,
- * but the iterate of one slab (tens of MB) stays in L2 across its C colour launches instead of being re-read from
- * HBM by every colour of the whole matrix (each colour gathers (C-1)/C of the vector).  0 or 1 = colour-major order.
- * Read when a smoother is created. */
+ * PE_TUNE_FUSED_GS_MAX_MB [0 = off]: a multicolour Gauss-Seidel sweep whose LARGEST colour moves fewer algorithmic megabytes
+ * than this runs as ONE persistent kernel (all colours of the forward and backward pass, grid barriers in between, the
+ * colour-order renumbering of the SELL path included) instead of one launch per colour.  Results are bit-identical (same
+ * rows, same summation order).  Measured on B200 (profiles/README.md, round 2): inside the CUDA graph with programmatic
+ * dependent launch a colour launch costs ~2.5 us, a grid-barrier step ~4.2 us -- the V-cycle got slower (7.46 -> 8.29 ms
+ * at 24 MB), so the default is off; the kernels stay for devices / drivers where launches are dearer.
+ * Read when a smoother is created.
+ * PE_TUNE_GS_SLABS [0 = off]: multicolour Gauss-Seidel on matrices with at least 4 million rows: the rows are cut into this
+ * many contiguous pieces of the matrix graph (breadth-first levels from row 0, equal row counts) and the sweep visits
+ * (slab 0: colours 0..C-1), (slab 1: colours 0..C-1), ... -- still Gauss-Seidel in an order made of independent sets.
+ * The idea: the iterate of one slab stays in L2 across its C colour launches instead of being re-read from HBM by
+ * every colour (each colour gathers (C-1)/C of the vector: the 1.2x DRAM traffic over the algorithmic bytes).  Measured
+ * (round 2): 4 slabs 9.38 ms, 8 slabs 9.76 ms against 7.46 ms -- the smaller launches cost more than the gathers save
+ * and the L2 hit rate of the gathers did not rise; default off.  Read when a smoother is created. */
 enum { PE_TUNE_SELL_MIN_ROWS = 0, PE_TUNE_SELL_GROUP = 1, PE_TUNE_PDL = 2, PE_TUNE_GATHER_KEEP_PCT = 3, PE_TUNE_P2P_HALO = 4,
        PE_TUNE_FUSED_GS_MAX_MB = 5, PE_TUNE_GS_SLABS = 6, PE_TUNE_COUNT = 7 };
 int pe_set_tuning(int key, int value);

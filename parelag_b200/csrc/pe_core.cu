@@ -128,7 +128,7 @@ extern "C" int pe_ctx_destroy(pe_ctx *c)
     return 0;
 }
 
-static int g_tuning[PE_TUNE_COUNT] = {200000, 0, 1, 0, 1, 24, 0};
+static int g_tuning[PE_TUNE_COUNT] = {200000, 0, 1, 0, 1, 0, 0};
 extern "C" int pe_set_tuning(int key, int value)
 {
     PE_CHECK(key >= 0 && key < PE_TUNE_COUNT, "bad tuning key");

@@ -182,7 +182,7 @@ def test_fused_sweep_kernel_is_bit_identical_to_per_colour_launches(ctx, gs_kern
         capi.set_tuning(capi.TUNE_FUSED_GS_MAX_MB, old)
     for mode in (True, False):
         assert np.array_equal(out[(0, mode)][0], out[(24, mode)][0])
-        assert out[(24, mode)][1] == 2 and out[(0, mode)][1] > 2 * (len(starts) - 2)      # one launch per sweep
+        assert out[(24, mode)][1] == 2 and out[(0, mode)][1] > 2 * (len(starts) - 2)      # one launch per sweep vs per set
     so = orc.Smoother(A, type=2, sweeps=2, order=order if ordering == "multicolor" else None)
     assert _rel(out[(24, True)][0], so.apply(b, x0, True)) < 1e-13
 
