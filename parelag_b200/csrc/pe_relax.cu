@@ -490,7 +490,15 @@ static int build_gs_schedule(pe_smoother *s)
     // PE_TUNE_SELL_MIN_ROWS rows a colour is a few thousand rows and latency-bound, where the
     // lanes-per-row CSR kernel (k_gs_set<TPR>: one coalesced load of the row, shuffle reduction, no
     // renumbering passes) has the shorter dependent chain.
-    if (s->ordering == PE_GS_ORDER_MULTICOLOR && !general && n >= pe_get_tuning(PE_TUNE_SELL_MIN_ROWS))
+    // A second condition on the rows PER COLOUR: irregular coarse operators (the NullSpace dofs of the deformed configs[4]
+    // mesh: 25-50 entries per row) need 40-50 colours, so a 430 k-row level has < 10 k rows per colour -- one thread per
+    // row leaves the GPU empty there, while the lanes-per-row kernel has 32 lanes per row in flight.  Measured on one
+    // box of configs[4] (144^3, profiles/README.md round 2): V-cycle 17.3 ms with the row rule alone, 15.1 ms when the
+    // 430 k-row level (9.5 k rows per colour) takes the CSR kernel, 17.0 ms when the 2.6 M-row level (65 k rows per
+    // colour) takes it as well.  The row threshold 0 (tests) forces the SELL path.
+    const int sell_min = pe_get_tuning(PE_TUNE_SELL_MIN_ROWS);
+    const bool enough_per_colour = sell_min <= 0 || (int64_t)n >= (int64_t)nsets * 32768;
+    if (s->ordering == PE_GS_ORDER_MULTICOLOR && !general && n >= sell_min && enough_per_colour)
     {
         // colour-ordered, slice-padded numbering
         s->slice_starts.assign(nsets + 1, 0);
