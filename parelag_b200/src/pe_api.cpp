@@ -587,14 +587,26 @@ extern "C" int pe_api_solver_level_info(const pe_solver *s, int level, int64_t *
 {
     API_TRY
     auto h = const_cast<Hierarchy *>(as_hierarchy(s));
-    auto A = std::dynamic_pointer_cast<mfem::HypreParMatrix>(h->GetLevel(level).Get<Op_Ptr>("A"));
-    if (nrows) *nrows = A->M();
-    if (nnz) *nnz = A->NNZ();
+    // a level operator is a ParCSR matrix or (blocked hierarchy) an MfemBlockOperator of ParCSR blocks: sum over blocks
+    auto count = [](const Op_Ptr &op, int64_t *rows, int64_t *entries)
+    {
+        if (auto A = std::dynamic_pointer_cast<mfem::HypreParMatrix>(op)) { *rows = A->M(); *entries = A->NNZ(); return; }
+        auto B = std::dynamic_pointer_cast<MfemBlockOperator>(op);
+        PARELAG_TEST_FOR_EXCEPTION(!B, std::runtime_error, "pe_api_solver_level_info: level operator is neither ParCSR nor a block operator");
+        *rows = B->Height(); *entries = 0;
+        for (size_t i = 0; i < B->GetNumBlockRows(); ++i)
+            for (size_t j = 0; j < B->GetNumBlockCols(); ++j)
+                if (!B->IsZeroBlock(i, j))
+                    if (auto blk = dynamic_cast<mfem::HypreParMatrix *>(&B->GetBlock(i, j))) *entries += blk->NNZ();
+    };
+    int64_t r = 0, e = 0;
+    count(h->GetLevel(level).Get<Op_Ptr>("A"), &r, &e);
+    if (nrows) *nrows = r;
+    if (nnz) *nnz = e;
     if (nnz_P)
     {
         *nnz_P = 0;
-        if (h->GetLevel(level).IsKey("P"))
-            *nnz_P = std::dynamic_pointer_cast<mfem::HypreParMatrix>(h->GetLevel(level).Get<Op_Ptr>("P"))->NNZ();
+        if (h->GetLevel(level).IsKey("P")) { int64_t pr = 0; count(h->GetLevel(level).Get<Op_Ptr>("P"), &pr, nnz_P); }
     }
     API_CATCH
 }
@@ -603,6 +615,7 @@ extern "C" int pe_api_solver_level_matrix(const pe_solver *s, int level, int32_t
     API_TRY
     auto h = const_cast<Hierarchy *>(as_hierarchy(s));
     auto M = std::dynamic_pointer_cast<mfem::HypreParMatrix>(h->GetLevel(level).Get<Op_Ptr>("A"));
+    PARELAG_TEST_FOR_EXCEPTION(!M, std::runtime_error, "pe_api_solver_level_matrix: the level operator is not a ParCSR matrix");
     PE_CALL(pe_mat_download(M->Handle(), I, J, A, nullptr, nullptr, nullptr, nullptr));
     API_CATCH
 }
