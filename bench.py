@@ -101,6 +101,25 @@ def library_darcy(ordering):
     }
 
 
+def library_darcy_ldu(ordering):
+    """examples/example_parameterlists/spe10_example_parameters.xml: GMRES(50) preconditioned by Block LDU whose A00
+    inverses are AMGe V-cycles on the H(div) mass block (Forms 2) and whose Schur-complement inverse is an AMGe V-cycle
+    on S = -(B diag(M)^-1 B^T) (Forms 3) -- the file's BoomerAMG inverses replaced by the hot-path solvers"""
+    gs = ("Hypre", {"Type": "L1 Gauss-Seidel", "Sweeps": 1, "Damping Factor": 1.0, "Omega": 1.0, "GS ordering": ordering})
+    pcg = ("Krylov", {"Solver name": "PCG", "Preconditioner": "Gauss-Seidel", "Print level": -1, "Maximum iterations": 3,
+                      "Relative tolerance": 1e-4, "Absolute tolerance": 1e-4})
+    amge = lambda form: ("AMGe", {"Maximum levels": -1, "Forms": [form], "PreSmoother": "Gauss-Seidel", "PostSmoother": "Gauss-Seidel",
+                                  "Coarse solver": "PCG-GS", "Cycle type": "V-cycle"})
+    return {
+        "Gauss-Seidel": gs, "PCG-GS": pcg, "AMGe-GS_2": amge(2), "AMGe-GS_3": amge(3),
+        "Block-LDU-AMGe": ("Block LDU", {"Damping Factor": 0.775, "A00_1 Inverse": "AMGe-GS_2", "A00_2 Inverse": "AMGe-GS_2",
+                                         "A00_3 Inverse": "AMGe-GS_2", "Alpha": 1.0, "S Type": "Diagonal", "S Inverse": "AMGe-GS_3"}),
+        "GMRES with Block LDU": ("Krylov", {"Solver name": "GMRES", "Preconditioner": "Block-LDU-AMGe", "Print level": -1,
+                                            "Maximum iterations": 300, "Relative tolerance": 1e-6, "Absolute tolerance": 1e-6,
+                                            "Restart size": 50}),
+    }
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -245,6 +264,12 @@ def workload_name(gpus, n, ndofs_box, levels, deformed):
             "Hiptmair(l1-GS,l1-GS), PCG-GS coarse solver" % (n, ndofs_box, levels))
 
 
+MIXED_SOLVER_NAME = {"ldu": "Block LDU with AMGe V-cycles (l1-GS) on M (Forms 2) and on the DIAGONAL Schur complement (Forms 3); step = one "
+                            "preconditioner application (3 + 1 V-cycles)",
+                     "blocked": "blocked AMGe (Forms 2 3) with a Block Jacobi smoother (l1-GS on M and on the Schur complement); step = one "
+                                "blocked V-cycle"}
+
+
 def other_workload_name(cfg, n, ndofs, levels, args):
     if cfg == "cfg1":
         return ("MultigridTest0Form (configs[0]): H1 Laplacian A=D0^T M1 D0 on meshes/cube456.mesh refined %d times (tetrahedra), "
@@ -253,11 +278,11 @@ def other_workload_name(cfg, n, ndofs, levels, args):
         return ("MultigridTest1Form (configs[2]): H(curl) A=M1+D1^T M2 D1, %d^3 hexahedra, %d Nedelec dofs, %d-level AMGe, "
                 "Hiptmair(l1-GS,l1-GS) with the H1 auxiliary space, PCG-GS coarse solver" % (n, ndofs, levels))
     if cfg == "darcy":
-        return ("MultigridTestDarcy (configs[1]): mixed system [[M B^T][B 0]], %d^3 hexahedra, %d dofs (RT0 + L2), %d-level blocked "
-                "AMGe (Forms 2 3), Block Jacobi smoother (l1-GS on M and on the DIAGONAL Schur complement), GMRES(50)" % (n, ndofs, levels))
+        return ("MultigridTestDarcy (configs[1]): mixed system [[M B^T][B 0]], %d^3 hexahedra, %d dofs (RT0 + L2), %d levels, GMRES(50) + %s"
+                % (n, ndofs, levels, MIXED_SOLVER_NAME[args.mixed_solver]))
     return ("MultigridTestSPE10-shaped (configs[3]): 60x220x85 cells of 20x10x2, synthetic lognormal permeability (4+ decades), mixed "
-            "system [[M B^T][B 0]], %d dofs, %d-level blocked AMGe (logical Cartesian agglomeration with ragged blocks), "
-            "Block Jacobi smoother, GMRES(50)" % (ndofs, levels))
+            "system [[M B^T][B 0]], %d dofs, %d levels (logical Cartesian agglomeration with ragged blocks), GMRES(50) + %s"
+            % (ndofs, levels, MIXED_SOLVER_NAME[args.mixed_solver]))
 
 
 def levels_for(n, cap):
@@ -360,6 +385,10 @@ def main():
                          "MultigridTest0Form (H1 on meshes/cube456.mesh, --nref refinements, 3 levels), hcurl = configs[2] "
                          "MultigridTest1Form (--size 192), darcy = configs[1] MultigridTestDarcy (--size 136, 4 levels), "
                          "spe10 = configs[3] (60x220x85 cells, synthetic lognormal permeability, mixed Darcy)")
+    ap.add_argument("--mixed-solver", default="ldu", choices=["ldu", "blocked"],
+                    help="darcy / spe10: GMRES + Block LDU with AMGe V-cycles on M and on the Schur complement (spe10_example_parameters.xml; a "
+                         "step = one application of that preconditioner), or GMRES + the blocked AMGe hierarchy with a Block Jacobi "
+                         "smoother (darcy_example_parameters.xml; a step = one blocked V-cycle)")
     ap.add_argument("--nref", type=int, default=4, help="cfg1: uniform refinements of cube456.mesh (driver: 2 serial + 2 parallel)")
     ap.add_argument("--cpu-n", type=int, default=32, help="bounded sample of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -534,7 +563,10 @@ def main():
             parity["ok"] = False
             parity["failed"] = repr(e)[:400]
     t0 = time.perf_counter()
-    if mixed:
+    if mixed and args.mixed_solver == "ldu":
+        solver = api.BlockSolver(api.library_xml(library_darcy_ldu(args.ordering)), "GMRES with Block LDU", blocks, S, 0, [2, 3],
+                                 ess_attr=np.zeros((2, 6), dtype=np.int32))
+    elif mixed:
         solver = api.BlockSolver(api.library_xml(library_darcy(args.ordering)), "GMRES with blocked AMGe", blocks, S, 0, [2, 3])
     elif cfg == "cfg1":
         solver = api.Solver(api.library_xml(library_h1(args.ordering)), "PCG with Auxiliary Space Preconditioner", A, S, 0, 0, ess)
