@@ -380,6 +380,8 @@ def main():
                     help="N = 1: run ONE box of the configs[4] workload (trilinear hexahedra, essential attributes 2-5) instead of "
                          "configs[1] -- the like-for-like base of the N > 1 weak-scaling lines")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block")
+    ap.add_argument("--no-weak-base", action="store_true",
+                    help="N = 1: skip the extra leg that times one box of configs[4] (the base of the N > 1 weak-scaling lines)")
     ap.add_argument("--config", default="hdiv", choices=["hdiv", "cfg1", "hcurl", "darcy", "spe10"],
                     help="N = 1 workload: hdiv = BASELINE configs[1] MultigridTest2Form (the headline), cfg1 = configs[0] "
                          "MultigridTest0Form (H1 on meshes/cube456.mesh, --nref refinements, 3 levels), hcurl = configs[2] "
@@ -706,6 +708,38 @@ def main():
     t_solve = time.perf_counter() - t0
     hist, iters, conv = solver.history()
 
+    # ---------------- like-for-like base of the N > 1 weak-scaling lines: ONE box of configs[4] on this GPU
+    weak_base = None
+    if world == 1 and cfg == "hdiv" and not deformed and not args.no_weak_base and not args.profile_range:
+        try:
+            solver.free(); S.free()
+            t0 = time.perf_counter()
+            Xd = api.box_vertex_coords((1, 1, 1), (0, 0, 0), (n, n, n), api.weak_scaling_deformation)
+            Sd = api.Sequence.hex((n, n, n), levels, jstart=1, coords=Xd)
+            del Xd
+            essd = np.array([0, 1, 1, 1, 1, 0], dtype=np.int32)
+            Ad = Sd.assemble_system(ctx, 0, 2, essd)
+            nd = Ad.info()[0]
+            sd = api.Solver(api.library_xml(library(args.ordering)), "PCG with Auxiliary Space Preconditioner", Ad, Sd, 0, 2, essd)
+            ctx.sync()
+            t_setup_d = time.perf_counter() - t0
+            rd, zd = capi.Vec(ctx, data=rng.standard_normal(nd)), capi.Vec(ctx, nd)
+            for _ in range(3):
+                sd.prec_mult_device(rd, zd)
+            ctx.sync(); ctx.timer_start()
+            for _ in range(10):
+                sd.prec_mult_device(rd, zd)
+            ms_d = ctx.timer_stop() / 10
+            sd.mult(rng.standard_normal(nd))
+            _, it_d, conv_d = sd.history()
+            weak_base = {"workload": workload_name(1, n, nd, sd.num_levels(), True), "ms_per_step": ms_d, "value": nd / (ms_d * 1e-3),
+                         "unit": UNIT, "steps": 10, "setup_s": t_setup_d, "pcg_iterations": it_d, "pcg_converged": conv_d,
+                         "levels": [{"rows": li[0], "nnz": li[1]} for li in (sd.level_info(l) for l in range(sd.num_levels()))],
+                         "note": "the N > 1 lines run this box per GPU: weak-scaling efficiency = value_N / (N x this value)"}
+            sd.free(); Sd.free()
+        except Exception as e:                    # the headline line must not depend on this leg
+            weak_base = {"failed": repr(e)[:300]}
+
     line = None
     if rank == 0:
         cpu_baseline = None
@@ -746,7 +780,7 @@ def main():
                            "tuning": {"sell_min_rows": capi.get_tuning(capi.TUNE_SELL_MIN_ROWS), "gs_slabs": capi.get_tuning(capi.TUNE_GS_SLABS),
                                       "fused_gs_max_mb": capi.get_tuning(capi.TUNE_FUSED_GS_MAX_MB), "pdl": capi.get_tuning(capi.TUNE_PDL)},
                            "levels": [{"rows": li[0], "nnz": li[1], "nnz_P": li[2]} for li in level_info]},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity": parity, "weak_scaling_base": weak_base,
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "setup_s": {"sequence_all_levels": t_coarsen, "assemble_system": t_assemble, "build_solver": t_build,
                             "total": t_coarsen + t_assemble + t_build, "timers": timers,
