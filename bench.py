@@ -635,7 +635,10 @@ def main():
     peak, peak_src = peaks()
     OPN = {1: "sell_spmv", 2: "sell_gs", 3: "csr_spmv", 4: "perm_in", 5: "perm_out", 6: "axpby", 7: "add3", 8: "fill",
            9: "copy", 10: "scale", 11: "mul", 12: "dot", 13: "dot_fin", 14: "axpy_dev", 15: "xpby_dev", 16: "pcg_step"}
-    prog = solver.program()
+    try:
+        prog = solver.program()
+    except Exception:                         # the preconditioner is not a Hierarchy (Block LDU of the mixed configs)
+        prog = None
     if prog is not None:
         # the whole V-cycle is ONE persistent kernel (k_program): its launch duration is the step;
         # algorithmic bytes = sum over the recorded ops (permutation ops count 0)
