@@ -198,15 +198,18 @@ def multi_rank(ctx, rank, size, deform=False, n=4, lev=3, group=None):
     # Deformed geometry: level 1 carries NullSpace dofs (singular vectors of target residuals); what is built FROM them
     # (P of level 1 -> 2, D of level 2) is determined to eps / (sigma |T|) only -- two backward-stable local solvers
     # differ by ~1e-10 there (tests/test_coarsen_gpu.py:compare_levels, null_tol).  Level 0 keeps 1e-12.
+    # Level 0 on the deformed geometry: 1e-11 (measured 1.0e-12 of the largest entry on the 2x2x1 boxes, 2e-13 on one box:
+    # the local saddle-point systems are built from quadrature mass matrices of strongly sheared cells).
     loose = 1e-8 if deform else 1e-12
+    tight = 1e-11 if deform else 1e-12
     for l in range(lev - 1):
         Pg, _ = gather_matrix(S.true_operator(ctx, l, "P", form, ess))
         same_pattern_and_values(permuted(Pg, perms[2][l], perms[2][l + 1]), sp.csr_matrix(seqs[l].get_P(form, ess)),
-                                1e-12 if l == 0 else loose, "P level %d" % l)
+                                tight if l == 0 else loose, "P level %d" % l)
     for l in range(lev):
         Dg, _ = gather_matrix(S.true_operator(ctx, l, "D", form - 1, ess))
         same_pattern_and_values(permuted(Dg, perms[2][l], perms[1][l]), sp.csr_matrix(seqs[l].get_D(form - 1, ess)),
-                                1e-12 if l <= 1 else loose, "D level %d" % l)
+                                tight if l <= 1 else loose, "D level %d" % l)
 
     # ---- assembled system (shared essential dofs carry the number of holders on the diagonal, as in
     # the reference driver: EliminateRowCol on the local matrix, then Assemble)
@@ -217,7 +220,7 @@ def multi_rank(ctx, rank, size, deform=False, n=4, lev=3, group=None):
     dm = Ap.diagonal()
     assert np.all(dm[marker] >= 1.0) and np.all(dm[marker] == np.round(dm[marker]))
     Ap = sp.csr_matrix(Ap - sp.diags(np.where(marker, dm - 1.0, 0.0)))
-    assert abs(Ap - Ao).max() <= 1e-12 * abs(Ao).max()
+    assert abs(Ap - Ao).max() <= tight * abs(Ao).max()
 
     # ---- ParCSR SpMV and MatvecT with halo exchange
     m2, m1 = S.dofmap(0, 2), S.dofmap(0, 1)
