@@ -501,7 +501,8 @@ def main():
         S = api.Sequence.hex_par(procs, (n, n, n), levels, L=(1.0, 1.0, 1.0), jstart=args.jstart)
     elif cfg == "cfg1":
         levels = 3
-        S = api.Sequence.tet_from_file(os.path.join(ROOT, "tests", "golden", "cube456.mesh"), args.nref, levels, jstart=0)
+        msh = np.load(os.path.join(ROOT, "tests", "golden", "cube456.npz"))      # arrays of meshes/cube456.mesh (tests/golden/make_cube456.py)
+        S = api.Sequence.tet(msh["vertices"], msh["tets"], msh["bdr_triangles"], msh["bdr_attributes"], args.nref, levels, jstart=0)
     elif cfg == "hcurl":
         S = api.Sequence.hex((n, n, n), levels, jstart=0)
     elif cfg == "darcy":

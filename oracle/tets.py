@@ -37,6 +37,26 @@ def read_netgen_neutral(path):
     return V, E[:, 1:] - 1, B[:, 1:] - 1, B[:, 0].copy()
 
 
+def load_npz(path):
+    """the arrays of tests/golden/cube456.npz (written by tests/golden/make_cube456.py from the reference's mesh file)"""
+    d = np.load(path)
+    return d["vertices"], d["tets"].astype(np.int64), d["bdr_triangles"].astype(np.int64), d["bdr_attributes"].astype(np.int64)
+
+
+def write_netgen_neutral(path, V, T, B, A, element_attribute=1):
+    """the inverse of read_netgen_neutral (1-based vertex numbers)"""
+    with open(path, "w") as f:
+        f.write("NETGEN_Neutral_Format\n%d\n" % len(V))
+        for x in V:
+            f.write("  %.17g  %.17g  %.17g\n" % tuple(x))
+        f.write("%d\n" % len(T))
+        for t in T:
+            f.write("   %d  %d %d %d %d\n" % ((element_attribute,) + tuple(int(v) + 1 for v in t)))
+        f.write("%d\n" % len(B))
+        for a, t in zip(A, B):
+            f.write("   %d  %d %d %d\n" % ((int(a),) + tuple(int(v) + 1 for v in t)))
+
+
 def cube_tets(n=1):
     """n x n x n cubes of the unit cube, each cut into 6 tetrahedra around the main diagonal (Kuhn); boundary
     attributes as mfem::Mesh::Make3D (z=0:1, y=0:2, x=1:3, y=1:4, x=0:5, z=1:6)"""

@@ -2,8 +2,8 @@
 host code (parelag_b200/src/amge_tet.hpp: mesh reader, red refinement, topology, Whitney mass matrices, targets) against the
 oracle (oracle/tets.py); integer tables bit-exact, values to 1e-13; and the oracle itself against the CheckInvariants
 identities (DeRhamSequence.cpp:694-970) and the dof counts SURVEY 8(d) quotes for configs[0].
-tests/golden/cube456.mesh is the reference's input mesh (meshes/cube456.mesh, NETGEN neutral format), kept as a fixture
-because /root/reference does not exist on the GPU box."""
+tests/golden/cube456.npz holds the arrays of the reference's input mesh meshes/cube456.mesh (written by
+tests/golden/make_cube456.py; /root/reference does not exist on the GPU box)."""
 import os
 
 import numpy as np
@@ -12,7 +12,7 @@ import pytest
 from parelag_b200 import api
 from oracle import amge, drivers, tets
 
-MESH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cube456.mesh")
+MESH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cube456.npz")
 
 
 def same(A, B):
@@ -24,7 +24,7 @@ def same(A, B):
 def test_cube456_counts_match_the_reference_configuration():
     """SURVEY 8(d) cfg 1: 141 vertices, 456 tets; after 2 refinements 5 739 H1 dofs (the coarsest level of the driver's
     3-level hierarchy), after 3: 42 309, and the mesh fills the unit cube with 6 boundary attributes."""
-    m = tets.TetMesh(*tets.read_netgen_neutral(MESH))
+    m = tets.TetMesh(*tets.load_npz(MESH))
     assert (m.nv, m.nel) == (141, 456) and abs(m.vol.sum() - 1.0) < 1e-12
     assert abs(m.facet_area()[m.bdr_face].sum() - 6.0) < 1e-12 and sorted(set(m.Battr.tolist())) == [1, 2, 3, 4, 5, 6]
     m2 = m.refine().refine()
@@ -54,7 +54,7 @@ def test_product_tet_tables_match_oracle(case):
         V, T, B, A = tets.cube_tets(2)
         nref, nlev = 2, 3
     else:
-        V, T, B, A = tets.read_netgen_neutral(MESH)
+        V, T, B, A = tets.load_npz(MESH)
         nref, nlev = 1, 2
     S = api.Sequence.tet(V, T, B, A, nref, nlev, svd_tol=-1.0)
     mesh = tets.TetMesh(V, T, B, A)
@@ -86,8 +86,20 @@ def test_product_tet_tables_match_oracle(case):
     S.free()
 
 
-def test_product_reads_the_mesh_file():
-    S = api.Sequence.tet_from_file(MESH, 0, 1, svd_tol=-1.0)
-    m = tets.TetMesh(*tets.read_netgen_neutral(MESH))
-    assert same(S.get_csr(0, "B", 0), m.topology().B[0])
+def test_product_reads_the_mesh_file(tmp_path):
+    """the product's NETGEN-neutral reader (what mfem::Mesh(imesh, 1, 1) does at examples/MultigridTest0Form.cpp:139-148):
+    the arrays are written in that format (and re-read by the oracle's reader), the product reads the file"""
+    V, T, B, A = tets.load_npz(MESH)
+    path = str(tmp_path / "cube456.mesh")
+    tets.write_netgen_neutral(path, V, T, B, A)
+    V2, T2, B2, A2 = tets.read_netgen_neutral(path)
+    assert np.array_equal(V2, V) and np.array_equal(T2, T) and np.array_equal(B2, B) and np.array_equal(A2, A)
+    S = api.Sequence.tet_from_file(path, 0, 1, svd_tol=-1.0)
+    m = tets.TetMesh(V, T, B, A)
+    topo = m.topology()
+    assert same(S.get_csr(0, "B", 0), topo.B[0]) and same(S.get_csr(0, "FB"), topo.facet_bdr)
+    assert np.array_equal(S.get_targets(0, 0)[:, 3], V[:, 0])        # vertex coordinates survive the round trip bit for bit
     S.free()
+    if os.path.exists("/root/reference/meshes/cube456.mesh"):          # this container only: the fixture equals the reference's file
+        Vr, Tr, Br, Ar = tets.read_netgen_neutral("/root/reference/meshes/cube456.mesh")
+        assert np.array_equal(Vr, V) and np.array_equal(Tr, T) and np.array_equal(Br, B) and np.array_equal(Ar, A)

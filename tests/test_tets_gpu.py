@@ -12,7 +12,7 @@ from oracle import amge, drivers, solve as orc, tets
 from tests.test_coarsen_gpu import compare_levels
 
 pytestmark = pytest.mark.gpu
-MESH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cube456.mesh")
+MESH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cube456.npz")
 
 
 @pytest.fixture(scope="module")
@@ -32,9 +32,9 @@ def test_coarsen_refined_kuhn_cubes_three_levels(sess):
 
 def test_cube456_h1_pcg_amge_history(sess):
     """configs[0] one refinement level down: cube456 refined twice, 3 levels"""
-    V, T, B, A = tets.read_netgen_neutral(MESH)
+    V, T, B, A = tets.load_npz(MESH)
     mesh, seqs = tets.build_hierarchy(tets.TetMesh(V, T, B, A), 2, 3)
-    S = api.Sequence.tet_from_file(MESH, 2, 3)
+    S = api.Sequence.tet(V, T, B, A, 2, 3)
     compare_levels(S, seqs)
     ess = np.ones(6, dtype=np.int32)
     Ao, marker = drivers.system_matrix(seqs[0], 0, ess)
