@@ -57,6 +57,24 @@ int pe_api_hexsequence_create(int nx, int ny, int nz, double Lx, double Ly, doub
  * all four forms are built by quadrature (mfem's rules: DeRhamSequenceFE.cpp:633-684, bilinIntegrators.cpp:64-157). */
 int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const double *vertex_xyz, const double *alpha,
                                        const double *beta, int jform_start, int nlevels, double svd_tol, pe_sequence **out);
+/* Options of the topology coarsening inside the sequence builders below and above (process-wide; what the reference's
+ * drivers take from their command lines):
+ *   partitioner 0 = derefinement by parent element (MFEMRefinedMeshPartitioner.cpp:48-90; logical Cartesian blocks on
+ *     grids that are not a multiple of two, LogicalPartitioner.hpp:46-103) -- the default;
+ *   1 = GeometricBoxPartitioner::doPartition (src/partitioning/GeometricBoxPartitioner.cpp:20-79; two levels,
+ *     num_partitions = elements / 16 as in testsuite/UpscalingGeneralForm.cpp:249-256,367-385 --geometric);
+ *   2 = element_partitioning[n] as given (two levels; testsuite/twentyseven.cpp:262-288).
+ *   check_topology = second argument of AgglomeratedTopology::CoarsenLocalPartitioning (Topology.cpp:685-739, 421-434):
+ *     report, mark and de-agglomerate agglomerated elements / facets / ridges that are disconnected, have holes or
+ *     tunnels or a pinched boundary (src/topology/AgglomeratedTopologyCheck.cpp).  Disconnected element partitions are
+ *     always split and empty ones removed (connectedComponents.cpp:23-87), as in the reference.
+ * pe_api_topology_log: the lines the reference prints during the topology coarsening (same text), collected since the
+ *   options were last set, newline separated; *needed = bytes including the terminator (call with buf = NULL first).
+ * pe_api_sequence_show_topology: AgglomeratedTopology::ShowMe of one level (Topology.cpp:310-352: entity counts and
+ *   Euler characteristic). */
+int pe_api_set_topology_options(int partitioner, int check_topology, const int32_t *element_partitioning, int n);
+int pe_api_topology_log(char *buf, int64_t capacity, int64_t *needed);
+int pe_api_sequence_show_topology(pe_sequence *s, int level, char *buf, int64_t capacity, int64_t *needed);
 /* Unstructured tetrahedral meshes (BASELINE configs[0], examples/MultigridTest0Form.cpp:147-375 on meshes/cube456.mesh):
  * the given mesh (0-based vertex numbers; boundary triangles with 1-based attributes) is refined nref times (red
  * refinement, children of element e = 8e .. 8e+7), the finest mesh is level 0 of the sequence and the nlevels - 1 <= nref

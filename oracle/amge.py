@@ -6,6 +6,9 @@ scipy, the same routines the reference calls) of
   * AgglomeratedTopology::CoarsenLocalPartitioning   src/topology/Topology.cpp:685-828
     with findMinimalIntersectionSets               src/structures/minimalIntersectionSet.cpp:43-130
   * MFEMRefinedMeshPartitioner::Partition            src/partitioning/MFEMRefinedMeshPartitioner.cpp:48-90
+  * GeometricBoxPartitioner::doPartition             src/partitioning/GeometricBoxPartitioner.cpp:20-79
+  * connectedComponents                              src/structures/connectedComponents.cpp:23-87
+  * AgglomeratedTopologyCheck, DeAgglomerateBad...   src/topology/AgglomeratedTopologyCheck.cpp:25-316, Topology.cpp:1151-1214
   * DofAgglomeration                                 src/amge/DOFAgglomeration.cpp:33-315,503-645
   * DofHandlerALG numbering / tables                 src/amge/DofHandler.cpp:694-1463
   * DeRhamSequence::Coarsen and helpers              src/amge/DeRhamSequence.cpp:572-692,1416-3048
@@ -28,7 +31,11 @@ checked against THESE tables.
 
 PARITY PIN: `upscaling_errors()` reproduces the reference's numbering- and
 sign-invariant golden values of testsuite/CMakeLists.txt:114-176 (form0, form1,
-form2); see tests/test_oracle_goldens.py.
+form2); see tests/test_oracle_goldens.py.  The topology checks (connectedComponents,
+AgglomeratedTopologyCheck, de-agglomeration) reproduce the messages of the reference's eight
+`twentyseven.exe` topology tests (testsuite/CMakeLists.txt:34-92) including the entity numbers,
+and the geometric box partitioner its two goldens (:187-193, :254-258); see
+tests/test_topology_check_cpu.py.
 
 SVD sign convention (both oracle and CUDA path): every retained left singular vector
 is scaled so that its largest-magnitude entry (first one on ties) is positive.
@@ -142,14 +149,28 @@ class Topology:
             self._conn[(big, small)] = C
         return self._conn[(big, small)]
 
-    def coarsen(self, partition):
-        """CoarsenLocalPartitioning(partition, check_topology=0, preserve_material=0)."""
-        partition = np.asarray(partition, dtype=np.int64)
-        nAE = int(partition.max()) + 1
+    def element_element(self):
+        """LocalElementElementTable (Topology.cpp:281-293): pattern of B_0 B_0^T"""
+        C = _canon(abs(self.B[0]) @ abs(self.B[0]).T)
+        C.data[:] = 1.0
+        return C
+
+    def coarsen(self, partition, check_topology=False):
+        """CoarsenLocalPartitioning(partition, check_topology, preserve_material=0) (Topology.cpp:685-828): disconnected
+        partitions are split and empty ones removed (connectedComponents), then, codimension by codimension, the
+        agglomerated entities are the minimal intersection sets; with check_topology every stage is followed by
+        ShowBadAgglomeratedEntities / MarkBadAgglomeratedEntities / DeAgglomerateBadAgglomeratedEntities
+        (AgglomeratedTopologyCheck.cpp, Topology.cpp:421-434,1151-1214).  The messages the reference prints are
+        collected in self.messages."""
+        partition = np.array(partition, dtype=np.int64)
+        nAE = connected_components(partition, self.element_element())
         self.partition = partition
+        self.messages = []
         AE_el = _canon(sp.csr_matrix((np.ones(len(partition)), (partition, np.arange(len(partition)))),
                                      shape=(nAE, len(partition))))
         AEe = [AE_el]
+        if check_topology:
+            AEe[0] = self._check_stage(AEe, 0)
         cB = []
         for icodim in range(self.ndim):
             AE_fc = mult_orientation(AEe[icodim], self.B[icodim])
@@ -158,6 +179,9 @@ class Topology:
                 Z = _canon(Z + self.facet_bdr @ self.facet_bdr.T)
             fc_AF = find_minimal_intersection_sets(Z, 0.5)
             AEe.append(_canon(fc_AF.T))
+            if check_topology:
+                AEe[icodim + 1] = self._check_stage(AEe, icodim + 1)
+                fc_AF = _canon(AEe[icodim + 1].T)
             cB.append(mult_orientation(AE_fc, fc_AF))
         cbdr = None
         if self.facet_bdr is not None:
@@ -165,6 +189,149 @@ class Topology:
         self.AE_entity = AEe
         self.coarser = Topology(cB, cbdr, self.ndim)
         return self.coarser
+
+    def _check_stage(self, AEe, codim):
+        """Topology.cpp:728-739 (codim 0) and CheckHFacetsTopology (:421-434)"""
+        self.messages += show_bad_agglomerated_entities(self, AEe, codim)
+        isbad = mark_bad_agglomerated_entities(self, AEe, codim)
+        if isbad.sum() == 0:
+            return AEe[codim]
+        new = deagglomerate_bad_entities(AEe[codim], isbad)
+        self.messages += ["Correcting agglomerated topology for icodim: %d" % codim,
+                          "  original number of agglomerates: %d" % AEe[codim].shape[0],
+                          "  number which were bad: %d" % int(isbad.sum()),
+                          "  number of new agglomerates after de-agglomeration: %d" % (new.shape[0] - AEe[codim].shape[0])]
+        return new
+
+    def show_me(self):
+        """AgglomeratedTopology::ShowMe (Topology.cpp:310-352), one rank: entity counts and the Euler characteristic"""
+        names = ["N_elements", "N_facets  ", "N_ridges  ", "N_peaks   "]
+        out = ["  %s = %10d%10d" % (names[c], self.n[c], self.n[c]) for c in range(self.ndim + 1)]
+        chi = sum(self.n[c] for c in range(self.ndim, -1, -2)) - sum(self.n[c] for c in range(self.ndim - 1, -1, -2))
+        out.append("Euler Characteristic = %10d%10d" % (chi, chi))
+        return out
+
+
+def connected_components(partition, conn):
+    """connectedComponents (src/structures/connectedComponents.cpp:23-87): every partition is split into its connected
+    components with respect to the element-element table; component c of partition p becomes offset[p] + c, components
+    numbered in the order a scan of the elements meets them, so empty partitions disappear and connected partitions keep
+    their relative order.  partition is rewritten in place; returns the number of agglomerates."""
+    n = len(partition)
+    if n == 0:
+        return 0
+    npart = int(partition.max()) + 1
+    comp = -np.ones(n, dtype=np.int64)
+    ncomp = np.zeros(npart, dtype=np.int64)
+    I, J = conn.indptr, conn.indices
+    for node in range(n):
+        if partition[node] < 0 or comp[node] >= 0:
+            continue
+        comp[node] = ncomp[partition[node]]
+        ncomp[partition[node]] += 1
+        stack = [node]
+        while stack:
+            i = stack.pop()
+            for k in J[I[i]:I[i + 1]]:
+                if partition[k] == partition[i] and comp[k] < 0:
+                    comp[k] = comp[i]
+                    stack.append(k)
+    offs = np.concatenate([[0], np.cumsum(ncomp)])
+    partition[:] = offs[partition] + comp
+    return int(offs[-1])
+
+
+def betti_numbers(topo, AEe, codim):
+    """AgglomeratedTopologyCheck::computeBettiNumbersAgglomeratedEntities (AgglomeratedTopologyCheck.cpp:242-316): for
+    every agglomerated entity of codimension codim the ranks of the boundary operators restricted to its fine entities
+    of every lower dimension; betti(l) = dim_k[i+1] - rank_k[i] - rank_k[i+1], l = nLowerDims - i - 1
+    (0: connected components, ..., top: holes)."""
+    nlow = topo.ndim - codim
+    if nlow == 0:
+        return np.zeros((0, 0), dtype=np.int64)
+    tabs = [AEe[codim]]
+    for i in range(nlow):
+        T = _canon(abs(tabs[i]) @ abs(topo.B[codim + i]))
+        T.data[:] = 1.0
+        tabs.append(T)
+    nAE = tabs[0].shape[0]
+    betti = np.zeros((nAE, nlow), dtype=np.int64)
+    for a in range(nAE):
+        ents = [row(t, a) for t in tabs]
+        dim_k = [len(e) for e in ents]
+        rank_k = [0] * (nlow + 1)
+        for i in range(nlow):
+            if dim_k[i] and dim_k[i + 1]:
+                d = topo.B[codim + i][ents[i]][:, ents[i + 1]].toarray()
+                rank_k[i] = int(np.linalg.matrix_rank(d, tol=1e-9))
+        for i in range(nlow):
+            betti[a, nlow - i - 1] = dim_k[i + 1] - rank_k[i] - rank_k[i + 1]
+    return betti
+
+
+def additional_topology_check(topo, AEe, codim, isbad, messages=None):
+    """AgglomeratedTopologyCheck::additionalTopologyCheck (AgglomeratedTopologyCheck.cpp:25-82): on the boundary of an
+    agglomerated element (codim 0) / agglomerated facet (codim 1) every boundary ridge (peak) must be adjacent to exactly
+    two boundary facets (ridges)"""
+    bf = _canon(AEe[codim] @ topo.B[codim])
+    bf.eliminate_zeros()
+    bf = abs(bf)
+    fe = abs(topo.B[codim + 1])
+    be = _canon(bf @ fe)
+    for a in range(bf.shape[0]):
+        rows_, cols_ = row(bf, a), row(be, a)
+        loc = fe[rows_][:, cols_]
+        twos = np.asarray(loc.sum(axis=0)).ravel()
+        if abs(twos.sum() - 2 * len(twos)) > 1e-10:
+            if messages is not None:
+                messages.append("    codim %d iAE %d has bad connectivity (eg boundary edge adjacent to >2 boundary faces)." % (codim, a))
+            isbad[a] = 1
+
+
+def mark_bad_agglomerated_entities(topo, AEe, codim):
+    """AgglomeratedTopologyCheck::MarkBadAgglomeratedEntities (AgglomeratedTopologyCheck.cpp:84-142)"""
+    betti = betti_numbers(topo, AEe, codim)
+    isbad = np.zeros(betti.shape[0], dtype=np.int64)
+    if codim <= 2 and betti.size:
+        isbad[betti[:, 0] != 1] = 1
+        if codim <= 1:
+            isbad[np.any(betti[:, 1:] != 0, axis=1)] = 1
+    if (topo.ndim == 2 and codim == 0) or (topo.ndim == 3 and codim in (0, 1)):
+        additional_topology_check(topo, AEe, codim, isbad)
+    return isbad
+
+
+def show_bad_agglomerated_entities(topo, AEe, codim):
+    """AgglomeratedTopologyCheck::ShowBadAgglomeratedEntities and showBadAgglomerated{Elements,Facets,Ridges}
+    (AgglomeratedTopologyCheck.cpp:144-240): the reference's messages, one list entry per line"""
+    betti = betti_numbers(topo, AEe, codim)
+    out = []
+    name = ["Element", "Facet", "Ridge"]
+    if codim <= 2:
+        for a in range(betti.shape[0]):
+            if betti[a, 0] != 1:
+                out.append("    %s %d is disconnected. The number of connected components is %d" % (name[codim], a, betti[a, 0]))
+            if codim <= 1:
+                for i in range(1, betti.shape[1]):
+                    if betti[a, i] != 0:
+                        what = "holes" if (codim == 1 or i == topo.ndim - 1) else "tunnels"
+                        out.append("    %s %d has %d %s." % (name[codim], a, betti[a, i], what))
+    if (topo.ndim == 2 and codim == 0) or (topo.ndim == 3 and codim in (0, 1)):
+        additional_topology_check(topo, AEe, codim, np.zeros(betti.shape[0], dtype=np.int64), out)
+    return out
+
+
+def deagglomerate_bad_entities(AEE, isbad):
+    """AgglomeratedTopology::DeAgglomerateBadAgglomeratedEntities (Topology.cpp:1151-1214): every fine entity of a bad
+    agglomerated entity becomes an agglomerated entity of its own, in place (later ones are renumbered)"""
+    I = [0]
+    for a in range(AEE.shape[0]):
+        lo, hi = AEE.indptr[a], AEE.indptr[a + 1]
+        if isbad[a]:
+            I.extend(range(lo + 1, hi + 1))
+        else:
+            I.append(hi)
+    return sp.csr_matrix((AEE.data.copy(), AEE.indices.copy(), np.array(I, dtype=AEE.indptr.dtype)), shape=(len(I) - 1, AEE.shape[1]))
 
 
 def refined_partition(dims_fine, ratio=(2, 2, 2)):
@@ -178,6 +345,28 @@ def refined_partition(dims_fine, ratio=(2, 2, 2)):
     cx, cy = -(-nx // rx), -(-ny // ry)
     k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
     return (((k // rz) * cy + (j // ry)) * cx + (i // rx)).ravel()
+
+
+def geometric_box_partition(centroids, bmin, bmax, num_partitions):
+    """GeometricBoxPartitioner::doPartition (src/partitioning/GeometricBoxPartitioner.cpp:20-79): the bounding box is cut
+    into round(extent / target_radius) boxes per direction, target_radius = (volume / num_partitions)^(1/dim); an element
+    belongs to the box that holds the mean of its vertices; partition = ix + nx (iy + ny iz).  Empty boxes keep their
+    number in the reference; here the partition is compacted (CoarsenLocalPartitioning needs contiguous ids)."""
+    centroids = np.asarray(centroids, dtype=np.float64)
+    bmin, bmax = np.asarray(bmin, dtype=np.float64), np.asarray(bmax, dtype=np.float64)
+    dim = centroids.shape[1]
+    ext = bmax - bmin
+    radius = (np.prod(ext) / float(num_partitions)) ** (1.0 / dim)
+    ndir = np.array([int(e / radius + 0.5) for e in ext], dtype=np.int64)
+    pr = ext / ndir
+    which = ((centroids - bmin) / pr).astype(np.int64)
+    part = which[:, 0].copy()
+    mult = 1
+    for a in range(1, dim):
+        mult *= ndir[a - 1]
+        part += mult * which[:, a]
+    _, compact = np.unique(part, return_inverse=True)
+    return compact.astype(np.int64)
 
 
 def coarse_dims(d, ratio=(2, 2, 2)):
@@ -305,6 +494,52 @@ class HexMesh:
         nx, ny, nz = self.dims
         i, j, k = self._grid(nx + 1, ny + 1, nz + 1)
         return np.stack([i * self.h[0], j * self.h[1], k * self.h[2]], axis=1)
+
+
+def mfem_hex_numbering(nx, ny, nz):
+    """Face and edge numbers mfem::Mesh gives the entities of its Cartesian hexahedral mesh (mfem::Mesh::Make3D without
+    space-filling-curve ordering; vertices and elements are lexicographic, x fastest, like HexMesh): faces and edges are
+    numbered in the order a scan over the elements meets them, local faces in the order z-, y-, x+, y+, x-, z+
+    (mfem::Geometry::Constants<CUBE>::FaceVert), local edges in the order of mfem's hexahedron edge table
+    (01 12 32 03 | 45 56 76 47 | 04 15 26 37 with vertices 0..3 counter-clockwise at z-, 4..7 above them).
+    AgglomeratedTopology numbers facets / ridges as the RT0 / Nedelec dofs of the mesh, i.e. by these numbers
+    (Topology.cpp:85-141), and the minimal intersection sets inherit the order (minimalIntersectionSet.cpp:96-127), so the
+    entity numbers in the reference's topology messages (testsuite/CMakeLists.txt:57-75) can be reproduced.
+    Returns (facet_perm, ridge_perm): lexicographic number -> mfem number."""
+    m = HexMesh(nx, ny, nz)
+    fperm = -np.ones(sum(m.nf), dtype=np.int64)
+    eperm = -np.ones(sum(m.ne), dtype=np.int64)
+    nfc = nec = 0
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                for f in (m.fz(i, j, k), m.fy(i, j, k), m.fx(i + 1, j, k), m.fy(i, j + 1, k), m.fx(i, j, k), m.fz(i, j, k + 1)):
+                    if fperm[f] < 0:
+                        fperm[f] = nfc
+                        nfc += 1
+                for e in (m.ex(i, j, k), m.ey(i + 1, j, k), m.ex(i, j + 1, k), m.ey(i, j, k),
+                          m.ex(i, j, k + 1), m.ey(i + 1, j, k + 1), m.ex(i, j + 1, k + 1), m.ey(i, j, k + 1),
+                          m.ez(i, j, k), m.ez(i + 1, j, k), m.ez(i + 1, j + 1, k), m.ez(i, j + 1, k)):
+                    if eperm[e] < 0:
+                        eperm[e] = nec
+                        nec += 1
+    return fperm, eperm
+
+
+def renumbered_topology(topo, facet_perm=None, ridge_perm=None):
+    """the same topology with facets / ridges renumbered (old number -> new number)"""
+    B = [b.copy() for b in topo.B]
+    fb = topo.facet_bdr
+    if facet_perm is not None:
+        Pf = sp.csr_matrix((np.ones(len(facet_perm)), (np.arange(len(facet_perm)), facet_perm)), shape=(len(facet_perm),) * 2)
+        B[0] = B[0] @ Pf
+        B[1] = Pf.T @ B[1]
+        fb = None if fb is None else Pf.T @ fb
+    if ridge_perm is not None:
+        Pr = sp.csr_matrix((np.ones(len(ridge_perm)), (np.arange(len(ridge_perm)), ridge_perm)), shape=(len(ridge_perm),) * 2)
+        B[1] = B[1] @ Pr
+        B[2] = Pr.T @ B[2]
+    return Topology(B, fb, topo.ndim)
 
 
 class DeformedHexMesh(HexMesh):
@@ -1400,16 +1635,38 @@ def _fine_sequence_deformed(mesh, topo, alpha, beta, jstart):
     return seq
 
 
-def build_hierarchy(dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9, deform=None):
+def hex_centroids(mesh):
+    X = mesh.vertex_coords()
+    nx, ny, nz = mesh.dims
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    c = np.zeros((len(i), 3))
+    for di in (0, 1):
+        for dj in (0, 1):
+            for dk in (0, 1):
+                c += X[mesh.vx(i + di, j + dj, k + dk)]
+    return c / 8.0
+
+
+def build_hierarchy(dims, nlevels, L=(1.0, 1.0, 1.0), alpha=None, beta=None, jstart=0, svd_tol=1e-9, deform=None, partitioner="derefine"):
     """Drivers' steps 3-4 (examples/MultigridTest2Form.cpp:248-375): agglomerate the
     topology nlevels-1 times by derefinement, then Coarsen() level by level.  deform: optional map of the
     (nv, 3) vertex coordinates (trilinear hexahedra; needs jstart >= 2)."""
     mesh = HexMesh(*dims, L=L) if deform is None else DeformedHexMesh(*dims, deform=deform, L=L)
     topos = [mesh.topology()]
     d = dims
-    for _ in range(nlevels - 1):
-        topos.append(topos[-1].coarsen(refined_partition(d)))
-        d = coarse_dims(d)
+    if partitioner == "geometric":
+        # testsuite/UpscalingGeneralForm.cpp:249-256,367-385: two levels only, number of partitions = half the element
+        # count of the once-coarser mesh ("coarsen more aggressively")
+        assert nlevels <= 2
+        if nlevels == 2:
+            X = mesh.vertex_coords()
+            nparts = max(1, (dims[0] * dims[1] * dims[2]) // 8 // 2)
+            topos.append(topos[-1].coarsen(geometric_box_partition(hex_centroids(mesh), X.min(axis=0), X.max(axis=0), nparts)))
+    else:
+        for _ in range(nlevels - 1):
+            topos.append(topos[-1].coarsen(refined_partition(d)))
+            d = coarse_dims(d)
     seqs = [fine_sequence(mesh, topos[0], alpha=alpha, beta=beta, jstart=jstart)]
     for l in range(nlevels - 1):
         seqs[l].svd_tol = svd_tol
@@ -1439,14 +1696,14 @@ def check_invariants(seq, tol=1e-9):
     return out
 
 
-def upscaling_errors(form, nref=1, base=(2, 2, 2)):
+def upscaling_errors(form, nref=1, base=(2, 2, 2), partitioner="derefine"):
     """testsuite/UpscalingGeneralForm.cpp (--form F --nref_parallel nref, default cube of
     2x2x2 hexes): A = M_F + D^T W D with essential (zero) data on attributes 2-5, a
     natural boundary term -1 on attribute 1; solve on every level; report
     ||u_h - P u_H||_M and ||D(u_h - P u_H)||_W on the finest level for the coarsest."""
     import scipy.sparse.linalg as spl
     dims = tuple(b * 2 ** nref for b in base)
-    mesh, seqs = build_hierarchy(dims, nref + 1)
+    mesh, seqs = build_hierarchy(dims, nref + 1, partitioner=partitioner)
     ess = np.array([0, 1, 1, 1, 1, 0])
     nx, ny, nz = dims
     hx, hy, hz = mesh.h

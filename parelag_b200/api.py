@@ -32,6 +32,24 @@ def set_host_comm(comm):
     _chk(lib().pe_api_session_set_host_comm(comm.ptr()))
 
 
+def set_topology_options(partitioner="derefine", check_topology=False, element_partitioning=None):
+    """process-wide options of the topology coarsening inside the sequence builders: partitioner "derefine" (default),
+    "geometric" (GeometricBoxPartitioner) or "user" (element_partitioning as given; two levels); check_topology = second
+    argument of CoarsenLocalPartitioning.  Clears the topology log."""
+    kind = {"derefine": 0, "geometric": 1, "user": 2}[partitioner]
+    part = None if element_partitioning is None else _i32(element_partitioning)
+    _chk(lib().pe_api_set_topology_options(kind, int(bool(check_topology)), _ptr(part), 0 if part is None else len(part)))
+
+
+def topology_log():
+    """the lines the reference prints during the topology coarsening (since the options were last set)"""
+    need = C.c_int64()
+    _chk(lib().pe_api_topology_log(None, C.c_int64(0), C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _chk(lib().pe_api_topology_log(buf, C.c_int64(need.value), None))
+    return [l for l in buf.value.decode().split("\n") if l]
+
+
 def _csr_args(M):
     M = M.tocsr()
     return (M.shape[0], M.shape[1], np.ascontiguousarray(M.indptr, dtype=np.int32),
@@ -187,6 +205,14 @@ class Sequence:
         v = C.c_int64()
         _chk(lib().pe_api_sequence_get_stat(self.h, level, name.encode(), C.byref(v)))
         return v.value
+
+    def show_topology(self, level):
+        """AgglomeratedTopology::ShowMe of one level: entity counts and Euler characteristic, as the reference prints them"""
+        need = C.c_int64()
+        _chk(lib().pe_api_sequence_show_topology(self.h, level, None, C.c_int64(0), C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _chk(lib().pe_api_sequence_show_topology(self.h, level, buf, C.c_int64(need.value), None))
+        return [l for l in buf.value.decode().split("\n") if l]
 
     def free(self):
         if self.h:

@@ -616,7 +616,45 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
         topo[0] = mesh.Topology();
     }
     int dx = nx, dy = ny, dz = nz;
-    for (int l = 0; l + 1 < nlevels; ++l)
+    const TopologyOptions &topt = GlobalTopologyOptions();
+    const bool custom = topt.partitioner != 0;
+    if (custom && nlevels > 1)
+    {
+        PARELAG_TEST_FOR_EXCEPTION(nlevels > 2 || parallel, std::runtime_error, "geometric / user element partitioning: two levels, single rank");
+        Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level 1");
+        const int nel = nx * ny * nz;
+        if (topt.partitioner == 2)
+        {
+            // testsuite/twentyseven.cpp:262-288: a hand-made partitioning of the elements
+            PARELAG_TEST_FOR_EXCEPTION((int)topt.user_partitioning.size() != nel, std::runtime_error,
+                                       "user element partitioning has " << topt.user_partitioning.size() << " entries, the mesh has " << nel << " elements");
+            topo[1] = CoarsenWithOptions(*topo[0], topt.user_partitioning);
+        }
+        else
+        {
+            // testsuite/UpscalingGeneralForm.cpp:249-256,367-385: one geometric box coarsening, half as many partitions as
+            // the once-coarser mesh has elements
+            std::vector<double> cen((size_t)3 * nel, 0.0), X;
+            if (mesh.deformed()) X = mesh.coords;
+            else
+            {
+                X.resize((size_t)3 * mesh.nv());
+                for (int k = 0; k <= nz; ++k) for (int j = 0; j <= ny; ++j) for (int i = 0; i <= nx; ++i)
+                { const int v = mesh.vx(i, j, k); X[3 * (size_t)v] = mesh.x0 + i * mesh.hx; X[3 * (size_t)v + 1] = mesh.y0 + j * mesh.hy; X[3 * (size_t)v + 2] = mesh.z0 + k * mesh.hz; }
+            }
+            double bmin[3] = {1e300, 1e300, 1e300}, bmax[3] = {-1e300, -1e300, -1e300};
+            for (size_t v = 0; v < X.size() / 3; ++v) for (int a = 0; a < 3; ++a) { bmin[a] = std::min(bmin[a], X[3 * v + a]); bmax[a] = std::max(bmax[a], X[3 * v + a]); }
+            for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i)
+            {
+                double *c = &cen[3 * (size_t)mesh.el(i, j, k)];
+                for (int dk = 0; dk < 2; ++dk) for (int dj = 0; dj < 2; ++dj) for (int di = 0; di < 2; ++di)
+                    for (int a = 0; a < 3; ++a) c[a] += X[3 * (size_t)mesh.vx(i + di, j + dj, k + dk) + a];
+                for (int a = 0; a < 3; ++a) c[a] /= 8.0;
+            }
+            topo[1] = CoarsenWithOptions(*topo[0], GeometricBoxPartition(cen.data(), nel, bmin, bmax, std::max(1, nel / 8 / 2)));
+        }
+    }
+    for (int l = 0; l + 1 < nlevels && !custom; ++l)
     {
         Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level " + std::to_string(l + 1));
         // derefinement by two per direction; grids that are not a multiple of two (60 x 220 x 85) take the logical
@@ -624,7 +662,7 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
         // interfaces in the same way)
         PARELAG_TEST_FOR_EXCEPTION(parallel && (dx % 2 || dy % 2 || dz % 2), std::runtime_error,
                                    "BuildHexSequenceHierarchyPar: box dimensions must be divisible by 2^(levels-1) on more than one rank");
-        topo[l + 1] = topo[l]->CoarsenLocalPartitioning(CartesianHexPartition(dx, dy, dz));
+        topo[l + 1] = CoarsenWithOptions(*topo[l], CartesianHexPartition(dx, dy, dz));
         dx = (dx + 1) / 2; dy = (dy + 1) / 2; dz = (dz + 1) / 2;
     }
     std::vector<std::shared_ptr<DeRhamSequence>> seq(nlevels);
@@ -676,7 +714,8 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
 std::vector<std::shared_ptr<DeRhamSequence>> BuildTetSequenceHierarchy(const TetMesh &coarse_mesh, int nref, int nlevels, const double *alpha,
                                                                         const double *beta, int jstart, double svd_tol)
 {
-    PARELAG_TEST_FOR_EXCEPTION(nlevels < 1 || nlevels - 1 > nref, std::runtime_error,
+    // derefinement agglomeration needs one refinement per coarsening; the geometric / given partitioners do not
+    PARELAG_TEST_FOR_EXCEPTION(nlevels < 1 || (GlobalTopologyOptions().partitioner == 0 && nlevels - 1 > nref), std::runtime_error,
                                "BuildTetSequenceHierarchy: " << nlevels << " levels need at least " << nlevels - 1 << " refinements");
     TetMesh mesh = coarse_mesh;
     {
@@ -691,12 +730,37 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildTetSequenceHierarchy(const Tet
         topo[0] = mesh.Topology();
     }
     int n = mesh.nel();
-    for (int l = 0; l + 1 < nlevels; ++l)
+    const TopologyOptions &topt = GlobalTopologyOptions();
+    const bool custom = topt.partitioner != 0;
+    if (custom && nlevels > 1)
+    {
+        PARELAG_TEST_FOR_EXCEPTION(nlevels > 2, std::runtime_error, "geometric / user element partitioning: two levels");
+        Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level 1");
+        if (topt.partitioner == 2)
+        {
+            PARELAG_TEST_FOR_EXCEPTION((int)topt.user_partitioning.size() != n, std::runtime_error,
+                                       "user element partitioning has " << topt.user_partitioning.size() << " entries, the mesh has " << n << " elements");
+            topo[1] = CoarsenWithOptions(*topo[0], topt.user_partitioning);
+        }
+        else
+        {
+            std::vector<double> cen((size_t)3 * n, 0.0);
+            double bmin[3] = {1e300, 1e300, 1e300}, bmax[3] = {-1e300, -1e300, -1e300};
+            for (int v = 0; v < mesh.nv(); ++v) for (int a = 0; a < 3; ++a) { bmin[a] = std::min(bmin[a], mesh.V[3 * (size_t)v + a]); bmax[a] = std::max(bmax[a], mesh.V[3 * (size_t)v + a]); }
+            for (int e = 0; e < n; ++e)
+            {
+                for (int q = 0; q < 4; ++q) for (int a = 0; a < 3; ++a) cen[3 * (size_t)e + a] += mesh.V[3 * (size_t)mesh.T[4 * e + q] + a];
+                for (int a = 0; a < 3; ++a) cen[3 * (size_t)e + a] /= 4.0;
+            }
+            topo[1] = CoarsenWithOptions(*topo[0], GeometricBoxPartition(cen.data(), n, bmin, bmax, std::max(1, n / 8 / 2)));
+        }
+    }
+    for (int l = 0; l + 1 < nlevels && !custom; ++l)
     {
         Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level " + std::to_string(l + 1));
         std::vector<int> part((size_t)n);
         for (int e = 0; e < n; ++e) part[e] = e / 8;
-        topo[l + 1] = topo[l]->CoarsenLocalPartitioning(part);
+        topo[l + 1] = CoarsenWithOptions(*topo[l], part);
         n /= 8;
     }
     std::vector<std::shared_ptr<DeRhamSequence>> seq(nlevels);

@@ -3,6 +3,9 @@
 //   AgglomeratedTopology::CoarsenLocalPartitioning   src/topology/Topology.cpp:685-828
 //   findMinimalIntersectionSets                      src/structures/minimalIntersectionSet.cpp:43-130
 //   MFEMRefinedMeshPartitioner::Partition            src/partitioning/MFEMRefinedMeshPartitioner.cpp:48-90
+//   connectedComponents                              src/structures/connectedComponents.cpp:23-87
+//   AgglomeratedTopologyCheck                        src/topology/AgglomeratedTopologyCheck.cpp:25-316
+//   DeAgglomerateBadAgglomeratedEntities             src/topology/Topology.cpp:1151-1214
 // These are O(n) integer graph operations that run once per level (bit-exact
 // required; host in this round).  All tables are kept in canonical CSR form (ascending
 // column indices per row) -- the numbering convention shared with oracle/amge.py.
@@ -13,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <iostream>
 #include <map>
 #include <memory>
 #include <numeric>
@@ -283,6 +287,205 @@ inline HostCSR MinimalIntersectionSetsFromMembership(const HostCSR &memb)
     return E;
 }
 
+/// connectedComponents (src/structures/connectedComponents.cpp:23-87): every partition is split into its connected
+/// components with respect to the element-element table (two elements are neighbours when they share a facet:
+/// LocalElementElementTable = B_0 W B_0^T, Topology.cpp:281-293; here the facets are walked directly).  Component c of
+/// partition p becomes offset[p] + c, the components of a partition numbered in the order a scan of the elements meets
+/// them: empty partitions disappear, connected partitions keep their relative order.  Returns the number of agglomerates.
+inline int ConnectedComponents(std::vector<int> &partitioning, const HostCSR &el_facet, const HostCSR &facet_el)
+{
+    const int n = (int)partitioning.size();
+    if (n == 0) return 0;
+    int npart = 0;
+    for (int p : partitioning) npart = std::max(npart, p + 1);
+    std::vector<int> component((size_t)n, -1), offset((size_t)npart + 1, 0), stack;
+    stack.reserve(1024);
+    for (int node = 0; node < n; ++node)
+    {
+        if (partitioning[node] < 0 || component[node] >= 0) continue;
+        component[node] = offset[partitioning[node] + 1]++;
+        stack.assign(1, node);
+        while (!stack.empty())
+        {
+            const int i = stack.back();
+            stack.pop_back();
+            for (int kf = el_facet.I[i]; kf < el_facet.I[i + 1]; ++kf)
+            {
+                const int f = el_facet.J[kf];
+                for (int ke = facet_el.I[f]; ke < facet_el.I[f + 1]; ++ke)
+                {
+                    const int k = facet_el.J[ke];
+                    if (partitioning[k] == partitioning[i] && component[k] < 0) { component[k] = component[i]; stack.push_back(k); }
+                }
+            }
+        }
+    }
+    for (int p = 0; p < npart; ++p) offset[p + 1] += offset[p];
+    for (int i = 0; i < n; ++i)
+        if (partitioning[i] >= 0) partitioning[i] = offset[partitioning[i]] + component[i];
+    return offset[npart];
+}
+
+/// AgglomeratedTopologyCheck (src/topology/AgglomeratedTopologyCheck.cpp): Betti numbers of the agglomerated entities,
+/// the boundary-connectivity check, the messages the reference prints and the de-agglomeration of bad entities.
+/// The functions take the fine boundary operators B and the agglomerated-entity tables built so far
+/// (AEntity_entity[0..codim]) instead of the topology object, so that CoarsenLocalPartitioning can call them stage by stage.
+struct AgglomeratedTopologyCheck
+{
+    /// numerical rank of a dense m x n matrix (row major, destroyed): Gaussian elimination with complete pivoting, pivots
+    /// below tol count as zero (mfem::DenseMatrix::Rank(1e-9) in the reference; the matrices are signed incidence matrices)
+    static int DenseRank(std::vector<double> &a, int m, int n, double tol)
+    {
+        int rank = 0;
+        std::vector<int> rows((size_t)m), cols((size_t)n);
+        std::iota(rows.begin(), rows.end(), 0);
+        std::iota(cols.begin(), cols.end(), 0);
+        for (; rank < std::min(m, n); ++rank)
+        {
+            int pi = -1, pj = -1;
+            double best = tol;
+            for (int i = rank; i < m; ++i)
+                for (int j = rank; j < n; ++j)
+                {
+                    const double v = std::fabs(a[(size_t)rows[i] * n + cols[j]]);
+                    if (v > best) { best = v; pi = i; pj = j; }
+                }
+            if (pi < 0) break;
+            std::swap(rows[rank], rows[pi]);
+            std::swap(cols[rank], cols[pj]);
+            const double *pr = &a[(size_t)rows[rank] * n];
+            const double piv = pr[cols[rank]];
+            for (int i = rank + 1; i < m; ++i)
+            {
+                double *ri = &a[(size_t)rows[i] * n];
+                const double f = ri[cols[rank]] / piv;
+                if (f == 0.0) continue;
+                for (int j = rank; j < n; ++j) ri[cols[j]] -= f * pr[cols[j]];
+            }
+        }
+        return rank;
+    }
+    /// computeBettiNumbersAgglomeratedEntities (:242-316): betti[a * nlow + l], l = 0 (connected components) .. nlow - 1
+    static std::vector<int> ComputeBettiNumbers(int ndim, const std::vector<HostCSR> &B, const std::vector<HostCSR> &AEe, int codim, int &nlow)
+    {
+        nlow = ndim - codim;
+        if (nlow <= 0) { nlow = 0; return {}; }
+        std::vector<HostCSR> tabs;
+        tabs.push_back(AEe[codim]);
+        for (int i = 0; i < nlow; ++i) tabs.push_back(hostcsr::MultPattern(tabs[i], B[codim + i]));
+        const int nAE = tabs[0].nrows;
+        std::vector<int> betti((size_t)nAE * nlow, 0), dim_k((size_t)nlow + 1), rank_k((size_t)nlow + 1);
+        std::vector<double> dloc;
+        std::vector<int> colpos;
+        for (int a = 0; a < nAE; ++a)
+        {
+            for (int i = 0; i <= nlow; ++i) dim_k[i] = tabs[i].I[a + 1] - tabs[i].I[a];
+            rank_k[nlow] = 0;
+            for (int i = 0; i < nlow; ++i)
+            {
+                rank_k[i] = 0;
+                if (dim_k[i] == 0 || dim_k[i + 1] == 0) continue;
+                const HostCSR &Bi = B[codim + i];
+                const int *rr = &tabs[i].J[tabs[i].I[a]], *cc = &tabs[i + 1].J[tabs[i + 1].I[a]];
+                dloc.assign((size_t)dim_k[i] * dim_k[i + 1], 0.0);
+                for (int r = 0; r < dim_k[i]; ++r)
+                    for (int k = Bi.I[rr[r]]; k < Bi.I[rr[r] + 1]; ++k)
+                    {
+                        const int *pos = std::lower_bound(cc, cc + dim_k[i + 1], Bi.J[k]);
+                        if (pos != cc + dim_k[i + 1] && *pos == Bi.J[k]) dloc[(size_t)r * dim_k[i + 1] + (pos - cc)] = Bi.A[k];
+                    }
+                rank_k[i] = DenseRank(dloc, dim_k[i], dim_k[i + 1], 1e-9);
+            }
+            for (int i = 0; i < nlow; ++i) betti[(size_t)a * nlow + (nlow - i - 1)] = dim_k[i + 1] - rank_k[i] - rank_k[i + 1];
+        }
+        return betti;
+    }
+    /// additionalTopologyCheck (:25-82): on the boundary of an agglomerated element (codim 0) / facet (codim 1) every
+    /// boundary ridge (peak) must be adjacent to exactly two boundary facets (ridges)
+    static void AdditionalTopologyCheck(const std::vector<HostCSR> &B, const std::vector<HostCSR> &AEe, int codim, std::vector<int> &isbad,
+                                        std::vector<std::string> *messages)
+    {
+        // interior entities cancel in the signed product; exact zeros are dropped
+        const HostCSR bf = hostcsr::Mult(AEe[codim], B[codim], 0.5);
+        const HostCSR &fe = B[codim + 1];
+        const HostCSR be = hostcsr::MultPattern(bf, fe);
+        std::vector<int> count((size_t)fe.ncols, 0);
+        for (int a = 0; a < bf.nrows; ++a)
+        {
+            // twos = (number of boundary facets adjacent to each boundary ridge); the reference tests their sum only
+            long sum = 0;
+            for (int k = bf.I[a]; k < bf.I[a + 1]; ++k) sum += fe.I[bf.J[k] + 1] - fe.I[bf.J[k]];
+            const long nridges = be.I[a + 1] - be.I[a];
+            if (sum != 2 * nridges)
+            {
+                if (messages)
+                    messages->push_back("    codim " + std::to_string(codim) + " iAE " + std::to_string(a) +
+                                        " has bad connectivity (eg boundary edge adjacent to >2 boundary faces).");
+                isbad[a] = 1;
+            }
+        }
+    }
+    static bool HasAdditionalCheck(int ndim, int codim) { return (ndim == 2 && codim == 0) || (ndim == 3 && (codim == 0 || codim == 1)); }
+    /// MarkBadAgglomeratedEntities (:84-142)
+    static bool MarkBadAgglomeratedEntities(int ndim, const std::vector<HostCSR> &B, const std::vector<HostCSR> &AEe, int codim, std::vector<int> &isbad)
+    {
+        int nlow;
+        const std::vector<int> betti = ComputeBettiNumbers(ndim, B, AEe, codim, nlow);
+        const int nAE = nlow ? (int)(betti.size() / nlow) : 0;
+        isbad.assign((size_t)nAE, 0);
+        if (codim <= 2)
+            for (int a = 0; a < nAE; ++a)
+            {
+                if (betti[(size_t)a * nlow] != 1) isbad[a] = 1;                                        // disconnected
+                if (codim <= 1)
+                    for (int i = 1; i < nlow; ++i) if (betti[(size_t)a * nlow + i] != 0) isbad[a] = 1;  // hole / tunnel
+            }
+        if (HasAdditionalCheck(ndim, codim)) AdditionalTopologyCheck(B, AEe, codim, isbad, nullptr);
+        return std::accumulate(isbad.begin(), isbad.end(), 0) > 0;
+    }
+    /// ShowBadAgglomeratedEntities and showBadAgglomerated{Elements,Facets,Ridges} (:144-240): the reference's lines
+    static void ShowBadAgglomeratedEntities(int ndim, const std::vector<HostCSR> &B, const std::vector<HostCSR> &AEe, int codim,
+                                            std::vector<std::string> &out)
+    {
+        int nlow;
+        const std::vector<int> betti = ComputeBettiNumbers(ndim, B, AEe, codim, nlow);
+        const int nAE = nlow ? (int)(betti.size() / nlow) : 0;
+        static const char *name[3] = {"Element", "Facet", "Ridge"};
+        if (codim <= 2)
+            for (int a = 0; a < nAE; ++a)
+            {
+                if (betti[(size_t)a * nlow] != 1)
+                    out.push_back(std::string("    ") + name[codim] + " " + std::to_string(a) + " is disconnected. The number of connected components is " +
+                                  std::to_string(betti[(size_t)a * nlow]));
+                if (codim <= 1)
+                    for (int i = 1; i < nlow; ++i)
+                        if (betti[(size_t)a * nlow + i] != 0)
+                            out.push_back(std::string("    ") + name[codim] + " " + std::to_string(a) + " has " + std::to_string(betti[(size_t)a * nlow + i]) +
+                                          ((codim == 1 || i == ndim - 1) ? " holes." : " tunnels."));
+            }
+        if (HasAdditionalCheck(ndim, codim))
+        {
+            std::vector<int> dummy((size_t)nAE, 0);
+            AdditionalTopologyCheck(B, AEe, codim, dummy, &out);
+        }
+    }
+    /// DeAgglomerateBadAgglomeratedEntities (Topology.cpp:1151-1214): every fine entity of a bad agglomerated entity becomes
+    /// an agglomerated entity of its own, in place (the later ones are renumbered)
+    static HostCSR DeAgglomerate(const HostCSR &AEE, const std::vector<int> &isbad)
+    {
+        HostCSR N;
+        N.ncols = AEE.ncols; N.J = AEE.J; N.A = AEE.A;
+        N.I.assign(1, 0);
+        for (int a = 0; a < AEE.nrows; ++a)
+        {
+            if (isbad[a]) for (int k = AEE.I[a] + 1; k <= AEE.I[a + 1]; ++k) N.I.push_back(k);
+            else N.I.push_back(AEE.I[a + 1]);
+        }
+        N.nrows = (int)N.I.size() - 1;
+        return N;
+    }
+};
+
 class AgglomeratedTopology : public std::enable_shared_from_this<AgglomeratedTopology>
 {
 public:
@@ -316,23 +519,55 @@ public:
         return conn_.emplace(key, hostcsr::MultPattern(head, B_[small - 1])).first->second;
     }
 
-    /// CoarsenLocalPartitioning(partitioning, check_topology = false,
-    /// preserve_material_interfaces = false, coarsefaces_algo = 0)
-    std::shared_ptr<AgglomeratedTopology> CoarsenLocalPartitioning(const std::vector<int> &partitioning)
+    /// messages of the last CoarsenLocalPartitioning(..., check_topology = true), one entry per line the reference prints
+    const std::vector<std::string> &Messages() const { return messages_; }
+    /// AgglomeratedTopology::ShowMe (Topology.cpp:310-352), one rank: entity counts (local, global) and the Euler characteristic
+    std::vector<std::string> ShowMe() const
+    {
+        static const char *name[4] = {"N_elements", "N_facets  ", "N_ridges  ", "N_peaks   "};
+        std::vector<std::string> out;
+        char buf[96];
+        for (int c = 0; c <= nDim_; ++c) { snprintf(buf, sizeof buf, "  %s = %10d%10d", name[c], n_[c], n_[c]); out.push_back(buf); }
+        int chi = 0;
+        for (int c = nDim_; c >= 0; c -= 2) chi += n_[c];
+        for (int c = nDim_ - 1; c >= 0; c -= 2) chi -= n_[c];
+        snprintf(buf, sizeof buf, "Euler Characteristic = %10d%10d", chi, chi);
+        out.push_back(buf);
+        return out;
+    }
+
+    /// CoarsenLocalPartitioning(partitioning, check_topology, preserve_material_interfaces, coarsefaces_algo = 0)
+    /// (Topology.cpp:685-828): disconnected partitions are split and empty ones removed, then, codimension by
+    /// codimension, the agglomerated entities are the minimal intersection sets; with check_topology every stage is
+    /// followed by Show / Mark / DeAgglomerate of the bad agglomerated entities (Topology.cpp:728-739, 421-434).
+    std::shared_ptr<AgglomeratedTopology> CoarsenLocalPartitioning(const std::vector<int> &partitioning, bool check_topology = false,
+                                                                   bool preserve_material_interfaces = false)
     {
         PARELAG_TEST_FOR_EXCEPTION((int)partitioning.size() != n_[0], std::runtime_error,
                                    "CoarsenLocalPartitioning(): partitioning has the wrong size");
         Partition_ = partitioning;
+        messages_.clear();
         int nAE = 0;
-        for (int p : partitioning) nAE = std::max(nAE, p + 1);
+        if (preserve_material_interfaces)
+        {
+            // connectedComponents.cpp:90-96: the material-aware form is a stub in the reference
+            messages_.push_back("WARNING: this form of connectedComponents not implemented yet.");
+            for (int p : Partition_) nAE = std::max(nAE, p + 1);
+        }
+        else
+        {
+            Timer t = TimeManager::AddTimer("Mesh Agglomeration: connected components");
+            nAE = ConnectedComponents(Partition_, B_[0], hostcsr::Transpose(B_[0]));
+        }
         // TransposeOrientation(partitioning, nAE): AE x element, +1
         HostCSR el_AE;
         el_AE.nrows = n_[0]; el_AE.ncols = nAE;
         el_AE.I.resize(n_[0] + 1); std::iota(el_AE.I.begin(), el_AE.I.end(), 0);
-        el_AE.J.assign(partitioning.begin(), partitioning.end());
+        el_AE.J.assign(Partition_.begin(), Partition_.end());
         el_AE.A.assign(n_[0], 1.0);
         AEntity_entity_.clear();
         AEntity_entity_.push_back(hostcsr::Transpose(el_AE));
+        if (check_topology) CheckStage(0);
         std::vector<HostCSR> cB;
         for (int icodim = 0; icodim < nDim_; ++icodim)
         {
@@ -350,6 +585,7 @@ public:
             }
             HostCSR fc_AF = MinimalIntersectionSetsFromMembership(fc_AE);
             AEntity_entity_.push_back(hostcsr::Transpose(fc_AF));
+            if (check_topology && CheckStage(icodim + 1)) fc_AF = hostcsr::Transpose(AEntity_entity_[icodim + 1]);
             cB.push_back(hostcsr::MultOrientation(AE_fc, fc_AF));
         }
         HostCSR cbdr;
@@ -362,6 +598,23 @@ public:
     }
 
 private:
+    /// Topology.cpp:728-739 (elements) and CheckHFacetsTopology (:421-434): report, mark and de-agglomerate the bad
+    /// agglomerated entities of one codimension; true when the table changed
+    bool CheckStage(int codim)
+    {
+        using ATC = AgglomeratedTopologyCheck;
+        ATC::ShowBadAgglomeratedEntities(nDim_, B_, AEntity_entity_, codim, messages_);
+        std::vector<int> isbad;
+        if (!ATC::MarkBadAgglomeratedEntities(nDim_, B_, AEntity_entity_, codim, isbad)) return false;
+        HostCSR fixed = ATC::DeAgglomerate(AEntity_entity_[codim], isbad);
+        messages_.push_back("Correcting agglomerated topology for icodim: " + std::to_string(codim));
+        messages_.push_back("  original number of agglomerates: " + std::to_string(AEntity_entity_[codim].nrows));
+        messages_.push_back("  number which were bad: " + std::to_string(std::accumulate(isbad.begin(), isbad.end(), 0)));
+        messages_.push_back("  number of new agglomerates after de-agglomeration: " + std::to_string(fixed.nrows - AEntity_entity_[codim].nrows));
+        AEntity_entity_[codim] = std::move(fixed);
+        return true;
+    }
+    std::vector<std::string> messages_;
     int nDim_;
     std::vector<HostCSR> B_;
     std::vector<int> n_;
@@ -401,5 +654,58 @@ inline std::vector<int> CartesianHexPartition(int nx, int ny, int nz, int rx = 2
         for (int j = 0; j < ny; ++j)
             for (int i = 0; i < nx; ++i) p[(size_t)i + (size_t)nx * (j + (size_t)ny * k)] = ((k / rz) * cy + (j / ry)) * cx + (i / rx);
     return p;
+}
+/// GeometricBoxPartitioner::doPartition (src/partitioning/GeometricBoxPartitioner.cpp:20-79): the bounding box is cut into
+/// round(extent / r) boxes per direction, r = (volume / num_partitions)^(1/3); an element belongs to the box that holds
+/// the mean of its vertices (centroids: n x 3); partition = ix + nx (iy + ny iz), compacted to contiguous ids (boxes that
+/// hold no element disappear).
+inline std::vector<int> GeometricBoxPartition(const double *centroids, int n, const double *bmin, const double *bmax, int num_partitions)
+{
+    PARELAG_TEST_FOR_EXCEPTION(num_partitions < 1, std::runtime_error, "GeometricBoxPartition(): bad number of partitions");
+    double vol = 1.0, ext[3];
+    for (int a = 0; a < 3; ++a) { ext[a] = bmax[a] - bmin[a]; vol *= ext[a]; }
+    const double radius = std::pow(vol / (double)num_partitions, 1.0 / 3.0);
+    int ndir[3];
+    double pr[3];
+    for (int a = 0; a < 3; ++a)
+    {
+        ndir[a] = (int)(ext[a] / radius + 0.5);
+        PARELAG_TEST_FOR_EXCEPTION(ndir[a] < 1, std::runtime_error, "GeometricBoxPartition(): degenerate bounding box");
+        pr[a] = ext[a] / (double)ndir[a];
+    }
+    std::vector<int> part((size_t)n);
+    for (int e = 0; e < n; ++e)
+    {
+        int w[3];
+        for (int a = 0; a < 3; ++a) w[a] = (int)((centroids[3 * (size_t)e + a] - bmin[a]) / pr[a]);
+        part[e] = w[0] + ndir[0] * (w[1] + ndir[1] * w[2]);
+    }
+    std::vector<int> ids(part);
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    for (int e = 0; e < n; ++e) part[e] = (int)(std::lower_bound(ids.begin(), ids.end(), part[e]) - ids.begin());
+    return part;
+}
+/// Process-wide options of the hierarchy builders (what the reference's drivers take from their command lines:
+/// testsuite/UpscalingGeneralForm.cpp --geometric, testsuite/twentyseven.cpp --partition / --check):
+/// partitioner 0 = derefinement / logical Cartesian (default), 1 = geometric boxes, 2 = the given element partitioning
+/// (1 and 2: two levels); check_topology = second argument of CoarsenLocalPartitioning; log = the lines the topology
+/// coarsening reported since the options were last set.
+struct TopologyOptions
+{
+    int partitioner = 0;
+    bool check_topology = false;
+    std::vector<int> user_partitioning;
+    std::vector<std::string> log;
+};
+inline TopologyOptions &GlobalTopologyOptions() { static TopologyOptions o; return o; }
+/// one coarsening step of the builders: CoarsenLocalPartitioning with the process-wide check flag; the reference's
+/// messages go to stdout (SerializedOutput at Topology.cpp:731, 426) and to the log
+inline std::shared_ptr<AgglomeratedTopology> CoarsenWithOptions(AgglomeratedTopology &fine, const std::vector<int> &partitioning)
+{
+    TopologyOptions &opt = GlobalTopologyOptions();
+    auto coarse = fine.CoarsenLocalPartitioning(partitioning, opt.check_topology);
+    for (const std::string &line : fine.Messages()) { std::cout << line << std::endl; opt.log.push_back(line); }
+    return coarse;
 }
 } // namespace parelag

@@ -172,6 +172,40 @@ extern "C" int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const 
     *out = s;
     API_CATCH
 }
+static int copy_lines(const std::vector<std::string> &lines, char *buf, int64_t capacity, int64_t *needed)
+{
+    std::string all;
+    for (const std::string &l : lines) { all += l; all += '\n'; }
+    if (needed) *needed = (int64_t)all.size() + 1;
+    if (buf && capacity > 0)
+    {
+        const size_t n = std::min((size_t)capacity - 1, all.size());
+        std::memcpy(buf, all.data(), n);
+        buf[n] = 0;
+    }
+    return 0;
+}
+extern "C" int pe_api_set_topology_options(int partitioner, int check_topology, const int32_t *element_partitioning, int n)
+{
+    API_TRY
+    PARELAG_TEST_FOR_EXCEPTION(partitioner < 0 || partitioner > 2, std::runtime_error,
+                               "pe_api_set_topology_options: partitioner 0 = derefinement / logical Cartesian, 1 = geometric boxes, 2 = given partitioning");
+    PARELAG_TEST_FOR_EXCEPTION(partitioner == 2 && (!element_partitioning || n <= 0), std::runtime_error,
+                               "pe_api_set_topology_options: partitioner 2 needs the element partitioning");
+    TopologyOptions &o = GlobalTopologyOptions();
+    o.partitioner = partitioner;
+    o.check_topology = check_topology != 0;
+    o.user_partitioning.clear();
+    if (partitioner == 2) o.user_partitioning.assign(element_partitioning, element_partitioning + n);
+    o.log.clear();
+    API_CATCH
+}
+extern "C" int pe_api_topology_log(char *buf, int64_t capacity, int64_t *needed)
+{
+    API_TRY
+    copy_lines(GlobalTopologyOptions().log, buf, capacity, needed);
+    API_CATCH
+}
 extern "C" int pe_api_tetsequence_create(int nv, const double *vertex_xyz, int nel, const int32_t *tets, int nbdr, const int32_t *bdr_triangles,
                                          const int32_t *bdr_attributes, int nref, int nlevels, int jstart, double svd_tol, pe_sequence **out)
 {
@@ -252,6 +286,14 @@ extern "C" int pe_api_sequence_get_bdr_mask(pe_sequence *s, int level, int form,
     PARELAG_ASSERT(d);
     if (ndofs) *ndofs = d->GetNDofs();
     if (mask) std::copy(d->GetBoundaryMask().begin(), d->GetBoundaryMask().end(), mask);
+    API_CATCH
+}
+extern "C" int pe_api_sequence_show_topology(pe_sequence *s, int level, char *buf, int64_t capacity, int64_t *needed)
+{
+    API_TRY
+    auto &seq = *s->levels.at(level);
+    PARELAG_ASSERT(seq.data && seq.data->topo);
+    copy_lines(seq.data->topo->ShowMe(), buf, capacity, needed);
     API_CATCH
 }
 extern "C" int pe_api_sequence_get_stat(pe_sequence *s, int level, const char *name, int64_t *value)
