@@ -63,7 +63,11 @@ int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const double *ver
  *     grids that are not a multiple of two, LogicalPartitioner.hpp:46-103) -- the default;
  *   1 = GeometricBoxPartitioner::doPartition (src/partitioning/GeometricBoxPartitioner.cpp:20-79; two levels,
  *     num_partitions = elements / 16 as in testsuite/UpscalingGeneralForm.cpp:249-256,367-385 --geometric);
- *   2 = element_partitioning[n] as given (two levels; testsuite/twentyseven.cpp:262-288).
+ *   2 = element_partitioning[n] as given (two levels; testsuite/twentyseven.cpp:262-288);
+ *   3 = LogicalPartitioner with LogicalCartesianMaterialId (src/partitioning/LogicalPartitioner.hpp:46-128,
+ *     CartesianPartitioner.hpp:133-150; examples/LogicalPartitionerDemo.cpp:203-226): element_partitioning[n] holds the
+ *     material id (element attribute) of every fine hexahedron; agglomeration by 2 x 2 x 2 logical blocks that keeps the
+ *     material ids apart, on every level.
  *   check_topology = second argument of AgglomeratedTopology::CoarsenLocalPartitioning (Topology.cpp:685-739, 421-434):
  *     report, mark and de-agglomerate agglomerated elements / facets / ridges that are disconnected, have holes or
  *     tunnels or a pinched boundary (src/topology/AgglomeratedTopologyCheck.cpp).  Disconnected element partitions are

@@ -155,7 +155,7 @@ class Topology:
         C.data[:] = 1.0
         return C
 
-    def coarsen(self, partition, check_topology=False):
+    def coarsen(self, partition, check_topology=False, preserve_material_interfaces=False):
         """CoarsenLocalPartitioning(partition, check_topology, preserve_material=0) (Topology.cpp:685-828): disconnected
         partitions are split and empty ones removed (connectedComponents), then, codimension by codimension, the
         agglomerated entities are the minimal intersection sets; with check_topology every stage is followed by
@@ -163,9 +163,13 @@ class Topology:
         (AgglomeratedTopologyCheck.cpp, Topology.cpp:421-434,1151-1214).  The messages the reference prints are
         collected in self.messages."""
         partition = np.array(partition, dtype=np.int64)
-        nAE = connected_components(partition, self.element_element())
-        self.partition = partition
         self.messages = []
+        if preserve_material_interfaces:        # connectedComponents.cpp:90-96: the material-aware form is a stub
+            self.messages.append("WARNING: this form of connectedComponents not implemented yet.")
+            nAE = int(partition.max()) + 1
+        else:
+            nAE = connected_components(partition, self.element_element())
+        self.partition = partition
         AE_el = _canon(sp.csr_matrix((np.ones(len(partition)), (partition, np.arange(len(partition)))),
                                      shape=(nAE, len(partition))))
         AEe = [AE_el]
@@ -1872,4 +1876,115 @@ def hcurl_weak_scaling_errors(nref=2, base=(1, 1, 1)):
         d = u - sols[0]
         dd = D0 @ d
         out.append((float(np.sqrt(d @ (M0 @ d))), float(np.sqrt(dd @ (W0 @ dd)))))
+    return out
+
+
+def logical_partition(elem_elem, logical, ratio):
+    """LogicalPartitioner::Partition with CoarsenLogicalCartesianOperatorMaterialId (src/partitioning/LogicalPartitioner.hpp:46-103,
+    CartesianPartitioner.hpp:133-150): flood fill over the element-element table; an element joins the partition of a
+    neighbour when both have the same coarse logical index (i / rx, j / ry, k / rz, material id); partitions are numbered
+    in the order a scan of the elements starts them.  logical: (n, 4) integer array (i, j, k, material id)."""
+    logical = np.asarray(logical, dtype=np.int64)
+    coarse = logical.copy()
+    coarse[:, :3] //= np.asarray(ratio, dtype=np.int64)
+    n = len(logical)
+    part = -np.ones(n, dtype=np.int64)
+    I, J = elem_elem.indptr, elem_elem.indices
+    nparts = 0
+    for e in range(n):
+        if part[e] >= 0:
+            continue
+        part[e] = nparts
+        queue = [e]
+        head = 0
+        while head < len(queue):
+            i = queue[head]
+            head += 1
+            for k in J[I[i]:I[i + 1]]:
+                if part[k] < 0 and np.array_equal(coarse[i], coarse[k]):
+                    part[k] = nparts
+                    queue.append(k)
+        nparts += 1
+    return part
+
+
+def logical_demo_material_ids(N=(12, 12, 12)):
+    """examples/LogicalPartitionerDemo.cpp:144-158: attribute 1 everywhere; in every layer k the four corner elements
+    and the element k Nx Ny + int(Nx Ny / 2 - Nx / 2) get an attribute of their own, counting up from 2"""
+    nx, ny, nz = N
+    mat = np.ones(nx * ny * nz, dtype=np.int64)
+    attr = 2
+    for kk in range(nz):
+        for e in (kk * nx * ny, kk * nx * ny + nx - 1, kk * nx * ny + nx * ny - 1, kk * nx * ny + nx * ny - nx,
+                  kk * nx * ny + int(0.5 * nx * ny - 0.5 * nx)):
+            mat[e] = attr
+            attr += 1
+    return mat
+
+
+def logical_demo_topologies(N=(12, 12, 12), nlevels=4, ratio=(2, 2, 2), material=None):
+    """examples/LogicalPartitionerDemo.cpp:203-226: LogicalPartitioner level after level,
+    CoarsenLocalPartitioning(partitioning, check_topology = 1, preserve_material_interfaces = 1).
+    Returns (mesh, [topology per level], [messages per coarsening step])."""
+    nx, ny, nz = N
+    mesh = HexMesh(nx, ny, nz)
+    mat = logical_demo_material_ids(N) if material is None else np.asarray(material, dtype=np.int64)
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    logical = np.stack([i.ravel(), j.ravel(), k.ravel(), mat], axis=1)
+    topos, messages = [mesh.topology()], []
+    for l in range(nlevels - 1):
+        t = topos[l]
+        part = logical_partition(t.element_element(), logical, ratio)
+        topos.append(t.coarsen(part, check_topology=True, preserve_material_interfaces=True))
+        messages.append(list(t.messages))
+        first = t.AE_entity[0].indices[t.AE_entity[0].indptr[:-1]]          # ComputeCoarseLogical: the first element decides
+        logical = logical[first].copy()
+        logical[:, :3] //= np.asarray(ratio, dtype=np.int64)
+    return mesh, topos, messages
+
+
+def h1_upscaling_errors(levels):
+    """examples/LogicalPartitionerDemo.cpp:330-470: A = M_0 + D_0^T M_1 D_0, zero essential data on the whole boundary,
+    right-hand side (1, v) restricted with P^T, every level solved; errors of the coarsest level first against the fine
+    solution.  levels: list of (M_0, M_1, D_0, boundary marker, P_0 or None) per level, fine first."""
+    import scipy.sparse.linalg as spl
+    M0, W0, D0 = levels[0][0], levels[0][1], levels[0][2]
+    rhs = np.asarray(M0.sum(axis=1)).ravel()
+    sols = []
+    for lev, (M, W, D, marker, P) in enumerate(levels):
+        keep = sp.diags((~marker).astype(float))
+        A = keep @ _canon(M + D.T @ W @ D) @ keep + sp.diags(marker.astype(float))
+        r = rhs.copy()
+        r[marker] = 0.0
+        sols.append(spl.spsolve(sp.csc_matrix(A), r))
+        if P is not None:
+            rhs = P.T @ rhs
+    out = []
+    for lev in range(len(levels) - 1, 0, -1):
+        u = sols[lev]
+        for q in range(lev - 1, -1, -1):
+            u = levels[q][4] @ u
+        d = u - sols[0]
+        dd = D0 @ d
+        out.append((float(np.sqrt(d @ (M0 @ d))), float(np.sqrt(dd @ (W0 @ dd)))))
+    return out
+
+
+def logical_partitioner_demo_errors(N=(12, 12, 12), nlevels=4, ratio=(2, 2, 2), return_all=False):
+    """examples/LogicalPartitionerDemo.cpp (--Nx 12 --Ny 12 --Nz 12, one rank): Cartesian mesh whose four corner
+    columns and one interior column carry a material id of their own per layer, logical Cartesian agglomeration by
+    2 x 2 x 2 with the material ids kept apart and the topology check on (agglomerates pierced by the interior column
+    have a tunnel and are de-agglomerated), all four forms coarsened (jFormStart = 0), then the H1 problem on every level.
+    Returns [(u_err, du_err) for the coarsest level, ..., level 1] against the fine solution."""
+    mesh, topos, messages = logical_demo_topologies(N, nlevels, ratio)
+    seqs = [fine_sequence(mesh, topos[0], jstart=0)]
+    for l in range(nlevels - 1):
+        seqs[l].svd_tol = 1e-9
+        seqs.append(seqs[l].coarsen())
+    ess = np.ones(6, dtype=int)
+    levels = [(s.mass_operator(0), s.mass_operator(1), s.D[0], s.dof[0].mark_bdr_dofs(ess), s.P[0] if l + 1 < nlevels else None)
+              for l, s in enumerate(seqs)]
+    out = h1_upscaling_errors(levels)
+    if return_all:
+        return out, topos, seqs, messages
     return out

@@ -34,9 +34,10 @@ def set_host_comm(comm):
 
 def set_topology_options(partitioner="derefine", check_topology=False, element_partitioning=None):
     """process-wide options of the topology coarsening inside the sequence builders: partitioner "derefine" (default),
-    "geometric" (GeometricBoxPartitioner) or "user" (element_partitioning as given; two levels); check_topology = second
+    "geometric" (GeometricBoxPartitioner), "user" (element_partitioning as given; two levels) or "logical"
+    (LogicalPartitioner; element_partitioning = material id of every fine element); check_topology = second
     argument of CoarsenLocalPartitioning.  Clears the topology log."""
-    kind = {"derefine": 0, "geometric": 1, "user": 2}[partitioner]
+    kind = {"derefine": 0, "geometric": 1, "user": 2, "logical": 3}[partitioner]
     part = None if element_partitioning is None else _i32(element_partitioning)
     _chk(lib().pe_api_set_topology_options(kind, int(bool(check_topology)), _ptr(part), 0 if part is None else len(part)))
 

@@ -717,7 +717,9 @@ __device__ __forceinline__ void extension_one(const ExtArgs &a, int ae, double *
     __syncthreads();
     // ---- solve all right-hand sides at once
     int info = 0;
-    if (nui > 0) info = cta_lu_solve(A, n, n, R, nrhs, nrhs, &s_piv, tid, LT);
+    // without interior u dofs only the facet stage still needs the solve: its last unknown is the multiplier that becomes
+    // the coarse derivative row of the PV dof (an agglomerated entity with a single member: [0 t; t 0] [p; lambda])
+    if (nui > 0 || a.facet) info = cta_lu_solve(A, n, n, R, nrhs, nrhs, &s_piv, tid, LT);
     __syncthreads();
     // ---- outputs
     double *out = a.out + a.out_off[ae];

@@ -618,7 +618,25 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
     int dx = nx, dy = ny, dz = nz;
     const TopologyOptions &topt = GlobalTopologyOptions();
     const bool custom = topt.partitioner != 0;
-    if (custom && nlevels > 1)
+    if (topt.partitioner == 3)
+    {
+        // examples/LogicalPartitionerDemo.cpp:203-226: logical Cartesian agglomeration by two per direction that keeps the
+        // material ids apart, level after level; CoarsenLocalPartitioning(partitioning, check, preserve_material = 1)
+        PARELAG_TEST_FOR_EXCEPTION(parallel, std::runtime_error, "logical partitioner with material ids: single rank");
+        const int nel = nx * ny * nz, ratio[3] = {2, 2, 2};
+        PARELAG_TEST_FOR_EXCEPTION((int)topt.user_partitioning.size() != nel, std::runtime_error,
+                                   "material ids: " << topt.user_partitioning.size() << " entries, the mesh has " << nel << " elements");
+        std::vector<LogicalCartesianMaterialId> logical((size_t)nel);
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i)
+        { const int e = mesh.el(i, j, k); logical[e] = LogicalCartesianMaterialId{i, j, k, topt.user_partitioning[e]}; }
+        for (int l = 0; l + 1 < nlevels; ++l)
+        {
+            Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level " + std::to_string(l + 1));
+            topo[l + 1] = CoarsenWithOptions(*topo[l], LogicalPartition(topo[l]->GetB(0), logical, ratio), true);
+            logical = ComputeCoarseLogical(topo[l]->AEntityEntity(0), logical, ratio);
+        }
+    }
+    else if (custom && nlevels > 1)
     {
         PARELAG_TEST_FOR_EXCEPTION(nlevels > 2 || parallel, std::runtime_error, "geometric / user element partitioning: two levels, single rank");
         Timer t = TimeManager::AddTimer("Mesh Agglomeration -- Level 1");

@@ -686,10 +686,65 @@ inline std::vector<int> GeometricBoxPartition(const double *centroids, int n, co
     for (int e = 0; e < n; ++e) part[e] = (int)(std::lower_bound(ids.begin(), ids.end(), part[e]) - ids.begin());
     return part;
 }
+/// LogicalPartitioner with LogicalCartesianMaterialId / CoarsenLogicalCartesianOperatorMaterialId
+/// (src/partitioning/LogicalPartitioner.hpp:46-128, CartesianPartitioner.hpp:30-36,133-150; examples/LogicalPartitionerDemo.cpp:
+/// 203-226): every element carries a logical index (i, j, k) and a material id; a flood fill over the element-element table
+/// (elements that share a facet) puts neighbours with the same COARSE logical index (i / rx, j / ry, k / rz, material id)
+/// into one partition, partitions numbered in the order a scan of the elements starts them.  Unlike CartesianHexPartition
+/// this keeps material ids apart and works level after level on the agglomerated topology.
+struct LogicalCartesianMaterialId
+{
+    int i, j, k, materialId;
+    bool operator==(const LogicalCartesianMaterialId &o) const { return i == o.i && j == o.j && k == o.k && materialId == o.materialId; }
+};
+inline LogicalCartesianMaterialId CoarsenLogical(const LogicalCartesianMaterialId &f, const int *ratio)
+{
+    return LogicalCartesianMaterialId{f.i / ratio[0], f.j / ratio[1], f.k / ratio[2], f.materialId};
+}
+inline std::vector<int> LogicalPartition(const HostCSR &el_facet, const std::vector<LogicalCartesianMaterialId> &fine_logical, const int *ratio)
+{
+    const int n = el_facet.nrows;
+    PARELAG_TEST_FOR_EXCEPTION((int)fine_logical.size() != n, std::runtime_error, "LogicalPartition(): one logical index per element");
+    const HostCSR facet_el = hostcsr::Transpose(el_facet);
+    std::vector<int> part((size_t)n, -1), queue;
+    queue.reserve((size_t)n);
+    int nparts = 0;
+    size_t head = 0;
+    for (int e = 0; e < n; ++e)
+    {
+        if (part[e] >= 0) continue;
+        part[e] = nparts++;
+        queue.push_back(e);
+        for (; head < queue.size(); ++head)
+        {
+            const int i = queue[head];
+            const LogicalCartesianMaterialId ci = CoarsenLogical(fine_logical[i], ratio);
+            for (int kf = el_facet.I[i]; kf < el_facet.I[i + 1]; ++kf)
+            {
+                const int f = el_facet.J[kf];
+                for (int ke = facet_el.I[f]; ke < facet_el.I[f + 1]; ++ke)
+                {
+                    const int k = facet_el.J[ke];
+                    if (part[k] < 0 && ci == CoarsenLogical(fine_logical[k], ratio)) { part[k] = part[i]; queue.push_back(k); }
+                }
+            }
+        }
+    }
+    return part;
+}
+/// LogicalPartitioner::ComputeCoarseLogical (:105-128): the coarse logical index of an agglomerate is that of its first element
+inline std::vector<LogicalCartesianMaterialId> ComputeCoarseLogical(const HostCSR &AE_element, const std::vector<LogicalCartesianMaterialId> &fine_logical,
+                                                                    const int *ratio)
+{
+    std::vector<LogicalCartesianMaterialId> c((size_t)AE_element.nrows);
+    for (int a = 0; a < AE_element.nrows; ++a) c[a] = CoarsenLogical(fine_logical[AE_element.J[AE_element.I[a]]], ratio);
+    return c;
+}
 /// Process-wide options of the hierarchy builders (what the reference's drivers take from their command lines:
 /// testsuite/UpscalingGeneralForm.cpp --geometric, testsuite/twentyseven.cpp --partition / --check):
 /// partitioner 0 = derefinement / logical Cartesian (default), 1 = geometric boxes, 2 = the given element partitioning
-/// (1 and 2: two levels); check_topology = second argument of CoarsenLocalPartitioning; log = the lines the topology
+/// (1 and 2: two levels), 3 = LogicalPartitioner with material ids (user_partitioning holds the material id of every fine
+/// element; examples/LogicalPartitionerDemo.cpp); check_topology = second argument of CoarsenLocalPartitioning; log = the lines the topology
 /// coarsening reported since the options were last set.
 struct TopologyOptions
 {
@@ -701,10 +756,11 @@ struct TopologyOptions
 inline TopologyOptions &GlobalTopologyOptions() { static TopologyOptions o; return o; }
 /// one coarsening step of the builders: CoarsenLocalPartitioning with the process-wide check flag; the reference's
 /// messages go to stdout (SerializedOutput at Topology.cpp:731, 426) and to the log
-inline std::shared_ptr<AgglomeratedTopology> CoarsenWithOptions(AgglomeratedTopology &fine, const std::vector<int> &partitioning)
+inline std::shared_ptr<AgglomeratedTopology> CoarsenWithOptions(AgglomeratedTopology &fine, const std::vector<int> &partitioning,
+                                                                bool preserve_material_interfaces = false)
 {
     TopologyOptions &opt = GlobalTopologyOptions();
-    auto coarse = fine.CoarsenLocalPartitioning(partitioning, opt.check_topology);
+    auto coarse = fine.CoarsenLocalPartitioning(partitioning, opt.check_topology, preserve_material_interfaces);
     for (const std::string &line : fine.Messages()) { std::cout << line << std::endl; opt.log.push_back(line); }
     return coarse;
 }

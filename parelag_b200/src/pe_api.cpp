@@ -188,15 +188,16 @@ static int copy_lines(const std::vector<std::string> &lines, char *buf, int64_t 
 extern "C" int pe_api_set_topology_options(int partitioner, int check_topology, const int32_t *element_partitioning, int n)
 {
     API_TRY
-    PARELAG_TEST_FOR_EXCEPTION(partitioner < 0 || partitioner > 2, std::runtime_error,
-                               "pe_api_set_topology_options: partitioner 0 = derefinement / logical Cartesian, 1 = geometric boxes, 2 = given partitioning");
-    PARELAG_TEST_FOR_EXCEPTION(partitioner == 2 && (!element_partitioning || n <= 0), std::runtime_error,
-                               "pe_api_set_topology_options: partitioner 2 needs the element partitioning");
+    PARELAG_TEST_FOR_EXCEPTION(partitioner < 0 || partitioner > 3, std::runtime_error,
+                               "pe_api_set_topology_options: partitioner 0 = derefinement / logical Cartesian, 1 = geometric boxes, 2 = given partitioning, "
+                               "3 = logical Cartesian with material ids");
+    PARELAG_TEST_FOR_EXCEPTION(partitioner >= 2 && (!element_partitioning || n <= 0), std::runtime_error,
+                               "pe_api_set_topology_options: partitioners 2 and 3 need the element partitioning / material ids");
     TopologyOptions &o = GlobalTopologyOptions();
     o.partitioner = partitioner;
     o.check_topology = check_topology != 0;
     o.user_partitioning.clear();
-    if (partitioner == 2) o.user_partitioning.assign(element_partitioning, element_partitioning + n);
+    if (partitioner >= 2) o.user_partitioning.assign(element_partitioning, element_partitioning + n);
     o.log.clear();
     API_CATCH
 }

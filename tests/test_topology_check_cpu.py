@@ -182,3 +182,43 @@ def test_connected_components_renumbering():
     part = np.array([3, 1, 3, 1])
     n = amge.connected_components(part, topo.element_element())
     assert n == 4 and part.tolist() == [2, 0, 3, 1]
+
+
+def cmake_regex_matches(pattern, out):
+    """PASS_REGULAR_EXPRESSION is a ;-separated list of alternatives"""
+    return any(re.search(alt, out) for alt in pattern.split(";"))
+
+
+def test_oracle_reproduces_the_logical_partitioner_golden():
+    """examples/CMakeLists.txt:104-110 (LogicalPartitionerDemo --Nx 12 --Ny 12 --Nz 12): four levels by the logical
+    Cartesian partitioner with material ids and the topology check on (the 4 x 4 x 4 blocks pierced by the interior material
+    column have a tunnel and are de-agglomerated), Coarsen() of all four forms over irregular agglomerates (single-element
+    agglomerates next to 8- and 64-element ones), H1 problem on every level: all six published numbers"""
+    out, topos, seqs, messages = amge.logical_partitioner_demo_errors(return_all=True)
+    text = "u l2-like errors: %s \nu energy-like errors: %s" % (" ".join("%.4e" % a for a, _ in out), " ".join("%.4e" % b for _, b in out))
+    assert cmake_regex_matches(GOLD["logical_partitioner"]["pass_regular_expression"], text), text
+    assert any("has 1 tunnels." in m for m in messages[1]) and any("has 1 tunnels." in m for m in messages[2])
+    for s in seqs[:-1]:
+        for k, v in amge.check_invariants(s).items():
+            assert v < 1e-9, (k, v)
+
+
+def test_product_logical_partitioner_matches_oracle():
+    """the product's LogicalPartitioner with material ids + topology check, four levels: tables and messages"""
+    N, nlev = (12, 12, 12), 4
+    mesh, topos, messages = amge.logical_demo_topologies(N, nlev)
+    api.set_topology_options("logical", True, amge.logical_demo_material_ids(N))
+    try:
+        S = api.Sequence.hex(N, nlev, svd_tol=-1.0)
+        assert api.topology_log() == [m for step in messages for m in step]
+        for l in range(nlev):
+            assert S.show_topology(l) == topos[l].show_me()
+            for c in range(3):
+                assert same(S.get_csr(l, "B", c), topos[l].B[c]), (l, c)
+            assert same(S.get_csr(l, "FB"), topos[l].facet_bdr)
+            if l + 1 < nlev:
+                for c in range(4):
+                    assert same(S.get_csr(l, "AE", c), topos[l].AE_entity[c]), (l, c)
+        S.free()
+    finally:
+        api.set_topology_options()
