@@ -1988,3 +1988,56 @@ def logical_partitioner_demo_errors(N=(12, 12, 12), nlevels=4, ratio=(2, 2, 2), 
     if return_all:
         return out, topos, seqs, messages
     return out
+
+
+def embedded_demo_errors(nref=2, return_all=False):
+    """examples/EmbeddedMeshPartitionerDemo.cpp with --mesh none --par_ref_levels 2 (structured path): the 2 x 2 x 2 cube
+    refined nref times, derefinement agglomeration (the material ids of the two coarse layers never cut a parent element)
+    with the topology check on (CoarsenLocalPartitioning(partitioning, 1, 0)), all four forms coarsened, then the H1
+    problem A = M_0 + D_0^T M_1 D_0 with ESSENTIAL DATA u = 1 on the whole boundary and no load: the boundary data of
+    the coarse levels is the cochain projection Pi of the fine data (:436-446), eliminated with EliminateRowCol (:483-487).
+    Returns [(u_err, du_err) for the coarsest level, ..., level 1] against the fine solution."""
+    import scipy.sparse.linalg as spl
+    n = 2 * 2 ** nref
+    dims = (n, n, n)
+    mesh = HexMesh(*dims)
+    topos = [mesh.topology()]
+    d = dims
+    messages = []
+    for _ in range(nref):
+        topos.append(topos[-1].coarsen(refined_partition(d), check_topology=True))
+        messages += topos[-2].messages
+        d = coarse_dims(d)
+    seqs = [fine_sequence(mesh, topos[0], jstart=0)]
+    for l in range(nref):
+        seqs[l].svd_tol = 1e-9
+        seqs.append(seqs[l].coarsen())
+    form = 0
+    ess = np.ones(6, dtype=int)
+    marker0 = seqs[0].dof[form].mark_bdr_dofs(ess)
+    ess_data = [np.where(marker0, 1.0, 0.0)]          # ProjectBdrCoefficient(1): nodal values on the boundary vertices
+    for l in range(nref):
+        ess_data.append(seqs[l].Pi[form] @ ess_data[l])
+    sols = []
+    for lev, s in enumerate(seqs):
+        M, W, D = s.mass_operator(form), s.mass_operator(form + 1), s.D[form]
+        A = _canon(M + D.T @ W @ D).tocsc()
+        marker = s.dof[form].mark_bdr_dofs(ess)
+        g = np.where(marker, ess_data[lev], 0.0)
+        r = -(A @ g)                                    # EliminateRowCol: rhs -= A[:, m] g_m, then rhs_m = g_m
+        keep = sp.diags((~marker).astype(float))
+        Ae = keep @ A @ keep + sp.diags(marker.astype(float))
+        r[marker] = g[marker]
+        sols.append(spl.spsolve(sp.csc_matrix(Ae), r))
+    M0, W0, D0 = seqs[0].mass_operator(form), seqs[0].mass_operator(form + 1), seqs[0].D[form]
+    out = []
+    for lev in range(len(seqs) - 1, 0, -1):
+        u = sols[lev]
+        for q in range(lev - 1, -1, -1):
+            u = seqs[q].P[form] @ u
+        dlt = u - sols[0]
+        dd = D0 @ dlt
+        out.append((float(np.sqrt(dlt @ (M0 @ dlt))), float(np.sqrt(dd @ (W0 @ dd)))))
+    if return_all:
+        return out, seqs, messages
+    return out

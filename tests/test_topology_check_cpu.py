@@ -222,3 +222,13 @@ def test_product_logical_partitioner_matches_oracle():
         S.free()
     finally:
         api.set_topology_options()
+
+
+def test_oracle_reproduces_the_embedded_mesh_partitioner_golden():
+    """examples/CMakeLists.txt:122-128 (EmbeddedMeshPartitionerDemo --mesh none --par_ref_levels 2): three levels on the 8^3
+    cube, H1 problem with essential data u = 1 on the whole boundary; the coarse boundary data is the cochain projection
+    Pi of the fine data -- pins the projector matrix (CochainProjector::ComputeProjector) on non-zero data"""
+    out, seqs, messages = amge.embedded_demo_errors(return_all=True)
+    text = "u l2-like errors: %s \nu energy-like errors: %s" % (" ".join("%.4e" % a for a, _ in out), " ".join("%.4e" % b for _, b in out))
+    assert cmake_regex_matches(GOLD["embedded_mesh_partitioner"]["pass_regular_expression"], text), text
+    assert messages == []          # the derefinement agglomerates pass the topology check
