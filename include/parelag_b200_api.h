@@ -1,6 +1,6 @@
 /*
  * parelag_b200_api.h -- C facade over the C++ mirror of ParElag's solver API
- * (parelag_b200/src/*.hpp: ParameterList-driven SolverLibrary / SolverFactory,
+ * (the headers under parelag_b200/src: ParameterList-driven SolverLibrary / SolverFactory,
  * mfem::Solver::Mult, DeRhamSequence coarse-operator interface).  It exists so that
  * non-C++ hosts (the ctypes tests, bench.py, a C driver) can drive exactly the code
  * path a C++ ParElag driver drives:
