@@ -226,6 +226,37 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def host_memory_gb():
+    """memory this node offers all ranks together: MemTotal, or the cgroup limit when that is lower.  A constant of the
+    box (not MemAvailable), so every rank and both arms of the bench derive the same box size from it."""
+    total = 0.0
+    try:
+        total = int([l for l in open("/proc/meminfo") if l.startswith("MemTotal")][0].split()[1]) / 1048576.0
+    except Exception:
+        return 0.0
+    for f in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(f).read().strip()
+            if v.isdigit() and 0 < int(v) < (1 << 60):
+                total = min(total, int(v) / float(1 << 30))
+        except Exception:
+            pass
+    return total
+
+
+def fit_box_size(n, world, per_rank_gb_at_144=60.0):
+    """N > 1 runs one box of n^3 trilinear hexahedra per rank; the setup of a 144^3 box peaks at 52 GB of host memory per
+    rank (profiles/r02_bench_n4_configs4.json).  When world x that does not fit into 3/4 of the node's memory the box
+    is shrunk in steps of 16 (5 levels need a multiple of 16) -- a guard against driving the node out of memory, stated in
+    config.workload when it fires."""
+    mem = host_memory_gb()
+    if world <= 1 or mem <= 0.0:
+        return n
+    while n > 48 and world * per_rank_gb_at_144 * (n / 144.0) ** 3 > 0.75 * mem:
+        n -= 16
+    return n
+
+
 def product_level_operators(ctx, ns, lv, deformed=False):
     """Level operators (A0, [P_l], [D_l]) of the bounded CPU sample, taken from the PRODUCT's hierarchy of the same
     workload (inputs of the solve path; what is timed on the CPU is the oracle V-cycle over them).  deformed: one box
@@ -320,6 +351,8 @@ def run_reference(args, rank):
     assert got == cores, "OpenMP gives %d threads, %d requested" % (got, cores)
     deformed = args.gpus > 1 and not args.no_deform     # the N > 1 arm runs configs[4]: sample = ONE box of it
     n_s = args.ref_n
+    if n_s <= 0 and fit_box_size(args.n, args.gpus) != args.n:
+        n_s = fit_box_size(args.n, args.gpus)            # the box size the GPU arm takes on this node (memory guard)
     if n_s <= 0:
         # the full per-GPU size when the host has the memory for the oracle's copies of the hierarchy (~60 GB at 144^3)
         avail = 0
@@ -434,6 +467,13 @@ def main():
 
     from parelag_b200 import api, capi
     n, levels = args.n, args.levels
+    if world > 1 and args.config == "hdiv":
+        fit = [fit_box_size(n, world)]
+        dist.broadcast_object_list(fit, src=0)           # one decision for all ranks
+        if fit[0] != n and rank == 0:
+            print("bench.py: %d ranks x %d^3 boxes do not fit the node's %.0f GB of host memory; running %d^3 boxes"
+                  % (world, n, host_memory_gb(), fit[0]), file=sys.stderr, flush=True)
+        n = fit[0]
     procs = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world)
     if procs is None:
         raise SystemExit("bench.py: --gpus must be 1, 2, 4 or 8")
