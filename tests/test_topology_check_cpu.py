@@ -232,3 +232,36 @@ def test_oracle_reproduces_the_embedded_mesh_partitioner_golden():
     text = "u l2-like errors: %s \nu energy-like errors: %s" % (" ".join("%.4e" % a for a, _ in out), " ".join("%.4e" % b for _, b in out))
     assert cmake_regex_matches(GOLD["embedded_mesh_partitioner"]["pass_regular_expression"], text), text
     assert messages == []          # the derefinement agglomerates pass the topology check
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_partitionings_product_equals_oracle(seed):
+    """fuzz: random (every third: perturbed blocky) partitionings of small Cartesian meshes with the topology check on --
+    disconnected parts, tunnels, holes, pinched boundaries, disconnected facets and ridges in arbitrary combination.
+    Product and oracle must report the same lines and produce the same tables bit for bit, and the repaired coarse topology
+    must still be a complex (B_c B_{c+1} = 0)."""
+    rng = np.random.default_rng(seed)
+    dims = tuple(int(x) for x in rng.integers(2, 5, size=3))
+    nel = dims[0] * dims[1] * dims[2]
+    part = rng.integers(0, int(rng.integers(1, max(2, nel // 3))), size=nel)
+    if seed % 3 == 0:
+        i, j, k = np.meshgrid(np.arange(dims[0]), np.arange(dims[1]), np.arange(dims[2]), indexing="ij")
+        part = ((i // 2) + 3 * (j // 2) + 9 * (k // 2)).transpose(2, 1, 0).ravel().copy()
+        part[rng.integers(0, nel, size=3)] = part[rng.integers(0, nel, size=3)]
+    topo = amge.HexMesh(*dims).topology()
+    coarse = topo.coarsen(part, check_topology=True)
+    for c in range(2):
+        assert abs(coarse.B[c] @ coarse.B[c + 1]).max() == 0
+    api.set_topology_options("user", True, part)
+    try:
+        S = api.Sequence.hex(dims, 2, svd_tol=-1.0)
+        assert api.topology_log() == topo.messages
+        assert S.show_topology(1) == coarse.show_me()
+        for c in range(4):
+            assert same(S.get_csr(0, "AE", c), topo.AE_entity[c]), c
+        for c in range(3):
+            assert same(S.get_csr(1, "B", c), coarse.B[c]), c
+        assert same(S.get_csr(1, "FB"), coarse.facet_bdr)
+        S.free()
+    finally:
+        api.set_topology_options()
