@@ -11,7 +11,7 @@
  *
  *   PARITY STATUS: "parity unpinned" for the individual kernels -- the reference
  *   ships no known-answer test for SpMV / relaxation / RAP / PCG.
- *   The end-to-end coarse-space goldens are pinned in oracle/amge_oracle.py.
+ *   The end-to-end coarse-space goldens are pinned in oracle/amge.py (tests/test_oracle_goldens.py, tests/test_goldens_cpu.py, tests/test_topology_check_cpu.py).
  *
  * Conventions: int32 indices, FP64 values, CSR (I,J,A); "diag"/"offd" are the two
  * blocks of a hypre ParCSR matrix; x_ext holds the ghost values of x (already
