@@ -468,12 +468,11 @@ def main():
     from parelag_b200 import api, capi
     n, levels = args.n, args.levels
     if world > 1 and args.config == "hdiv":
-        fit = [fit_box_size(n, world)]
-        dist.broadcast_object_list(fit, src=0)           # one decision for all ranks
-        if fit[0] != n and rank == 0:
+        fit = fit_box_size(n, world)                     # from MemTotal / the cgroup limit: the same on every rank of the node
+        if fit != n and rank == 0:
             print("bench.py: %d ranks x %d^3 boxes do not fit the node's %.0f GB of host memory; running %d^3 boxes"
-                  % (world, n, host_memory_gb(), fit[0]), file=sys.stderr, flush=True)
-        n = fit[0]
+                  % (world, n, host_memory_gb(), fit), file=sys.stderr, flush=True)
+        n = fit
     procs = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world)
     if procs is None:
         raise SystemExit("bench.py: --gpus must be 1, 2, 4 or 8")
