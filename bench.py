@@ -244,15 +244,15 @@ def host_memory_gb():
     return total
 
 
-def fit_box_size(n, world, per_rank_gb_at_144=60.0):
+def fit_box_size(n, world, per_rank_gb_at_144=56.0):
     """N > 1 runs one box of n^3 trilinear hexahedra per rank; the setup of a 144^3 box peaks at 52 GB of host memory per
-    rank (profiles/r02_bench_n4_configs4.json).  When world x that does not fit into 3/4 of the node's memory the box
+    rank (profiles/r02_bench_n4_configs4.json).  When world x 56 GB does not fit into 85 % of the node's memory the box
     is shrunk in steps of 16 (5 levels need a multiple of 16) -- a guard against driving the node out of memory, stated in
     config.workload when it fires."""
     mem = host_memory_gb()
     if world <= 1 or mem <= 0.0:
         return n
-    while n > 48 and world * per_rank_gb_at_144 * (n / 144.0) ** 3 > 0.75 * mem:
+    while n > 48 and world * per_rank_gb_at_144 * (n / 144.0) ** 3 > 0.85 * mem:
         n -= 16
     return n
 

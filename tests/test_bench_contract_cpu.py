@@ -34,11 +34,11 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 
 def test_multi_rank_box_size_respects_the_host_memory():
-    """N > 1: the per-rank box shrinks in steps of 16 when world x 60 GB would exceed 3/4 of the node's memory; both arms
+    """N > 1: the per-rank box shrinks in steps of 16 when world x 56 GB would exceed 85 % of the node's memory; both arms
     derive it from the same constant of the box"""
     import unittest.mock as mock
     import bench
-    for mem, want in ((2000.0, [144, 144, 144]), (512.0, [144, 144, 128]), (256.0, [144, 128, 96])):
+    for mem, want in ((2000.0, [144, 144, 144]), (512.0, [144, 144, 128]), (256.0, [144, 128, 112])):
         with mock.patch.object(bench, "host_memory_gb", lambda mem=mem: mem):
             assert [bench.fit_box_size(144, w) for w in (2, 4, 8)] == want
             assert bench.fit_box_size(144, 1) == 144
