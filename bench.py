@@ -311,6 +311,10 @@ def other_workload_name(cfg, n, ndofs, levels, args):
     if cfg == "darcy":
         return ("MultigridTestDarcy (configs[1]): mixed system [[M B^T][B 0]], %d^3 hexahedra, %d dofs (RT0 + L2), %d levels, GMRES(50) + %s"
                 % (n, ndofs, levels, MIXED_SOLVER_NAME[args.mixed_solver]))
+    if getattr(args, "perm_file", None):
+        return ("MultigridTestSPE10 (configs[3]): 60x220x85 cells of 20x10x2, SPE10 permeability tensor from %s, mixed system "
+                "[[M B^T][B 0]], %d dofs, %d levels (logical Cartesian agglomeration with ragged blocks), GMRES(50) + %s"
+                % (os.path.basename(args.perm_file), ndofs, levels, MIXED_SOLVER_NAME[args.mixed_solver]))
     return ("MultigridTestSPE10-shaped (configs[3]): 60x220x85 cells of 20x10x2, synthetic lognormal permeability (4+ decades), mixed "
             "system [[M B^T][B 0]], %d dofs, %d levels (logical Cartesian agglomeration with ragged blocks), GMRES(50) + %s"
             % (ndofs, levels, MIXED_SOLVER_NAME[args.mixed_solver]))
@@ -431,6 +435,8 @@ def main():
                     help="tuning: levels with fewer rows use the lanes-per-row CSR Gauss-Seidel kernel (library default 200000)")
     ap.add_argument("--gs-slabs", type=int, default=None, help="tuning: PE_TUNE_GS_SLABS (slab-major multicolour order on >= 4M-row levels)")
     ap.add_argument("--fused-gs-mb", type=int, default=None, help="tuning: PE_TUNE_FUSED_GS_MAX_MB (0 = one launch per colour)")
+    ap.add_argument("--perm-file", default=None,
+                    help="--config spe10: path of the SPE10 permeability file (spe_perm.dat); default: synthetic lognormal field")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo exchange: NVLink peer-memory stores (default) or ncclSend/ncclRecv")
     ap.add_argument("--profile-range", action="store_true",
@@ -550,8 +556,14 @@ def main():
         # SPE10-shaped (InversePermeabilityFunction.cpp:254-259: 60 x 220 x 85 cells of 20 x 10 x 2 ft); synthetic
         # lognormal permeability (the data set is not available offline): log10 k ~ N(-1, 1.5^2) clipped to [-4, 2]
         dims, Lspe = (60, 220, 85), (1200.0, 2200.0, 170.0)
-        kinv = 10.0 ** (-np.clip(np.random.default_rng(13).normal(-1.0, 1.5, size=dims[0] * dims[1] * dims[2]), -4.0, 2.0))
-        S = api.Sequence.hex(dims, levels, L=Lspe, beta=kinv, jstart=2)
+        if args.perm_file:
+            # the real data set when the user has it (data/spe_perm.dat, examples/MultigridTestSPE10.cpp:85,181-183): read
+            # and evaluated as the reference does, diagonal tensor coefficient (1/K_x, 1/K_y, 1/K_z) per cell
+            api.spe10_read(args.perm_file, dims, (20.0, 10.0, 2.0))
+            S = api.Sequence.spe10(dims, (20.0, 10.0, 2.0), levels, jstart=2)
+        else:
+            kinv = 10.0 ** (-np.clip(np.random.default_rng(13).normal(-1.0, 1.5, size=dims[0] * dims[1] * dims[2]), -4.0, 2.0))
+            S = api.Sequence.hex(dims, levels, L=Lspe, beta=kinv, jstart=2)
     else:
         S = api.Sequence.hex((n, n, n), levels, jstart=args.jstart)
     ctx.sync()

@@ -57,6 +57,26 @@ int pe_api_hexsequence_create(int nx, int ny, int nz, double Lx, double Ly, doub
  * all four forms are built by quadrature (mfem's rules: DeRhamSequenceFE.cpp:633-684, bilinIntegrators.cpp:64-157). */
 int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const double *vertex_xyz, const double *alpha,
                                        const double *beta, int jform_start, int nlevels, double svd_tol, pe_sequence **out);
+/* Diagonal tensor coefficient in the H(div) element mass matrices (a VectorFunctionCoefficient in VectorFEMassIntegrator,
+ * examples/MultigridTestSPE10.cpp:377-395): beta_xyz[3 * element + axis]; axis-aligned cells. */
+int pe_api_hexsequence_create_tensor(int nx, int ny, int nz, double Lx, double Ly, double Lz, const double *alpha, const double *beta_xyz,
+                                     int jform_start, int nlevels, double svd_tol, pe_sequence **out);
+/* The SPE10 permeability data set as the reference reads and evaluates it (src/SPE10/InversePermeabilityFunction.cpp;
+ * class InversePermeabilityFunction in parelag_b200/src/spe10.hpp, process-wide state like the reference's statics):
+ * pe_api_spe10_read = SetNumberCells + SetMeshSizes + ReadPermeabilityFile (the Nx x Ny x Nz corner of the 60 x 220 x 85
+ *   file with the three blocks K_x, K_y, K_z; reciprocals are stored; with a host communicator rank 0 reads and all receive);
+ * pe_api_spe10_set_constant = SetConstantInversePermeability; pe_api_spe10_set_slice = Set2DSlice (0 none, 1 XY, 2 XZ, 3 YZ);
+ * pe_api_spe10_inverse_permeability = InversePermeability at npoints points (out: npoints x 3; the data set's x and z
+ *   axes run against the mesh axes, :141-178); pe_api_spe10_data = the stored array (3 Nx Ny Nz numbers);
+ * pe_api_hexsequence_create_spe10 = the driver's mesh (nx x ny x nz cells of size hx x hy x hz) with the loaded inverse
+ *   permeability as the tensor coefficient of the H(div) mass matrix, then the coarsening path as above. */
+int pe_api_spe10_read(const char *perm_file, int Nx, int Ny, int Nz, double hx, double hy, double hz);
+int pe_api_spe10_set_constant(int Nx, int Ny, int Nz, double hx, double hy, double hz, double ipx, double ipy, double ipz);
+int pe_api_spe10_set_slice(int orientation, int npos);
+int pe_api_spe10_inverse_permeability(const double *xyz, int npoints, double *out);
+int pe_api_spe10_data(double *out, int64_t *count);
+int pe_api_hexsequence_create_spe10(int nx, int ny, int nz, double hx, double hy, double hz, int jform_start, int nlevels, double svd_tol,
+                                    pe_sequence **out);
 /* Options of the topology coarsening inside the sequence builders below and above (process-wide; what the reference's
  * drivers take from their command lines):
  *   partitioner 0 = derefinement by parent element (MFEMRefinedMeshPartitioner.cpp:48-90; logical Cartesian blocks on

@@ -1548,7 +1548,14 @@ def fine_sequence(mesh, topo=None, upscaling_order=0, alpha=None, beta=None, jst
     # form 3 (L2, cell values)
     seq.M[(3, 0)] = rep(np.array([[vol]]), nel, a_el)
     # form 2 (RT0, fluxes): element (local order x-,x+,y-,y+,z-,z+), facet
-    seq.M[(2, 0)] = rep(bd(hx / (hy * hz) * M1D, hy / (hx * hz) * M1D, hz / (hx * hy) * M1D), nel, b_el)
+    if b_el.ndim == 2:
+        # diagonal tensor coefficient (beta_x, beta_y, beta_z) per element (VectorFunctionCoefficient in
+        # VectorFEMassIntegrator, e.g. the SPE10 inverse permeability): the three axis blocks scale separately
+        assert b_el.shape == (nel, 3)
+        blocks = [sp.block_diag([hx / (hy * hz) * M1D * b[0], hy / (hx * hz) * M1D * b[1], hz / (hx * hy) * M1D * b[2]]) for b in b_el]
+        seq.M[(2, 0)] = sp.block_diag(blocks, format="csr")
+    else:
+        seq.M[(2, 0)] = rep(bd(hx / (hy * hz) * M1D, hy / (hx * hz) * M1D, hz / (hx * hy) * M1D), nel, b_el)
     seq.M[(2, 1)] = sp.diags(1.0 / mesh.facet_area()).tocsr()
     # form 1 (Nedelec, circulations): element (4 x-edges, 4 y-edges, 4 z-edges), facet, ridge
     K = np.kron(M1D, M1D)

@@ -42,6 +42,26 @@ def set_topology_options(partitioner="derefine", check_topology=False, element_p
     _chk(lib().pe_api_set_topology_options(kind, int(bool(check_topology)), _ptr(part), 0 if part is None else len(part)))
 
 
+def spe10_read(path, N=(60, 220, 85), h=(20.0, 10.0, 2.0)):
+    """InversePermeabilityFunction::SetNumberCells / SetMeshSizes / ReadPermeabilityFile"""
+    _chk(lib().pe_api_spe10_read(str(path).encode(), N[0], N[1], N[2], C.c_double(h[0]), C.c_double(h[1]), C.c_double(h[2])))
+
+
+def spe10_data():
+    n = C.c_int64()
+    _chk(lib().pe_api_spe10_data(None, C.byref(n)))
+    out = np.empty(n.value)
+    _chk(lib().pe_api_spe10_data(_ptr(out), None))
+    return out
+
+
+def spe10_inverse_permeability(x):
+    x = _f64(np.ascontiguousarray(x).reshape(-1, 3))
+    out = np.empty_like(x)
+    _chk(lib().pe_api_spe10_inverse_permeability(_ptr(x), len(x), _ptr(out)))
+    return out
+
+
 def topology_log():
     """the lines the reference prints during the topology coarsening (since the options were last set)"""
     need = C.c_int64()
@@ -92,6 +112,28 @@ class Sequence:
         _chk(lib().pe_api_hexsequence_create(dims[0], dims[1], dims[2], C.c_double(L[0]), C.c_double(L[1]),
                                              C.c_double(L[2]), _ptr(a), _ptr(b), jstart, nlevels,
                                              C.c_double(svd_tol), C.byref(S.h)))
+        return S
+
+    @staticmethod
+    def hex_tensor(dims, nlevels, beta_xyz, L=(1.0, 1.0, 1.0), alpha=None, jstart=0, svd_tol=1e-9):
+        """hex() with a diagonal tensor coefficient in the H(div) mass matrices: beta_xyz (nel, 3)"""
+        S = Sequence.__new__(Sequence)
+        S.h = C.c_void_p()
+        a = None if alpha is None else _f64(alpha)
+        b = _f64(np.ascontiguousarray(beta_xyz).reshape(-1))
+        assert len(b) == 3 * dims[0] * dims[1] * dims[2]
+        _chk(lib().pe_api_hexsequence_create_tensor(dims[0], dims[1], dims[2], C.c_double(L[0]), C.c_double(L[1]), C.c_double(L[2]),
+                                                    _ptr(a), _ptr(b), jstart, nlevels, C.c_double(svd_tol), C.byref(S.h)))
+        return S
+
+    @staticmethod
+    def spe10(dims, h, nlevels, jstart=2, svd_tol=1e-9):
+        """the mesh of examples/MultigridTestSPE10.cpp (dims cells of size h) with the loaded SPE10 inverse permeability
+        (spe10_read) as the tensor coefficient of the H(div) mass matrix"""
+        S = Sequence.__new__(Sequence)
+        S.h = C.c_void_p()
+        _chk(lib().pe_api_hexsequence_create_spe10(dims[0], dims[1], dims[2], C.c_double(h[0]), C.c_double(h[1]), C.c_double(h[2]),
+                                                   jstart, nlevels, C.c_double(svd_tol), C.byref(S.h)))
         return S
 
     @staticmethod

@@ -517,9 +517,9 @@ HostCSR DeRhamSequence::ComputeMassOperator(int jform) const
 
 std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchy(int nx, int ny, int nz, double Lx, double Ly, double Lz,
                                                                         const double *alpha, const double *beta, int jstart,
-                                                                        int nlevels, double svd_tol, const double *vertex_coords)
+                                                                        int nlevels, double svd_tol, const double *vertex_coords, int beta_components)
 {
-    return BuildHexSequenceHierarchyPar(nullptr, nullptr, nx, ny, nz, Lx, Ly, Lz, alpha, beta, jstart, nlevels, svd_tol, vertex_coords);
+    return BuildHexSequenceHierarchyPar(nullptr, nullptr, nx, ny, nz, Lx, Ly, Lz, alpha, beta, jstart, nlevels, svd_tol, vertex_coords, beta_components);
 }
 
 /// Host memory for the setup phase.  Building a hierarchy allocates (and re-allocates while vectors grow)
@@ -576,7 +576,7 @@ void ReleaseHostArena()
 std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const pe_host_comm *comm, const int *procs, int nx, int ny, int nz,
                                                                            double Lx, double Ly, double Lz, const double *alpha,
                                                                            const double *beta, int jstart, int nlevels, double svd_tol,
-                                                                           const double *vertex_coords)
+                                                                           const double *vertex_coords, int beta_components)
 {
     const bool parallel = comm && comm->size > 1;
     const int one[3] = {1, 1, 1};
@@ -689,7 +689,7 @@ std::vector<std::shared_ptr<DeRhamSequence>> BuildHexSequenceHierarchyPar(const 
         seq[0] = std::make_shared<DeRhamSequence>(4);
         seq[0]->data = std::make_shared<SequenceData>();
         std::vector<HostCSR> D;
-        BuildFineHexSequence(mesh, topo[0], alpha, beta, jstart, *seq[0]->data, D);
+        BuildFineHexSequence(mesh, topo[0], alpha, beta, jstart, *seq[0]->data, D, beta_components);
         for (int j = 0; j < 3; ++j) seq[0]->SetD(j, D[j]);
         for (int j = 0; j < 4; ++j) seq[0]->SetDofHandlerRaw(j, seq[0]->data->dof[j].get());
     }

@@ -416,10 +416,17 @@ inline void BuildFineHexSequenceDeformed(const StructuredHexMesh &mesh, const st
 
 /// fills SequenceData + D_ for the fine level; alpha / beta: optional per-element weights
 /// of the L2 and H(div) element mass matrices (ReplaceMassIntegrator in the drivers)
+/// beta_components = 3: beta holds (beta_x, beta_y, beta_z) per element, the diagonal tensor coefficient of the H(div)
+/// mass matrix (VectorFunctionCoefficient in VectorFEMassIntegrator, e.g. the SPE10 inverse permeability,
+/// examples/MultigridTestSPE10.cpp:377-395); on an axis-aligned cell it scales the three 2 x 2 axis blocks separately.
 inline void BuildFineHexSequence(const StructuredHexMesh &mesh, const std::shared_ptr<AgglomeratedTopology> &topo,
-                                 const double *alpha, const double *beta, int jstart, SequenceData &S, std::vector<HostCSR> &D)
+                                 const double *alpha, const double *beta, int jstart, SequenceData &S, std::vector<HostCSR> &D,
+                                 int beta_components = 1)
 {
     using namespace hexfe;
+    PARELAG_TEST_FOR_EXCEPTION(beta_components != 1 && beta_components != 3, std::runtime_error, "BuildFineHexSequence: beta has 1 or 3 components per element");
+    PARELAG_TEST_FOR_EXCEPTION(mesh.deformed() && beta && beta_components == 3, not_implemented_error,
+                               "BuildFineHexSequence: tensor coefficient on trilinear hexahedra");
     if (mesh.deformed()) { BuildFineHexSequenceDeformed(mesh, topo, alpha, beta, jstart, S, D); return; }
     const double hx = mesh.hx, hy = mesh.hy, hz = mesh.hz, vol = hx * hy * hz;
     const int nel = (int)mesh.nel();
@@ -451,7 +458,17 @@ inline void BuildFineHexSequence(const StructuredHexMesh &mesh, const std::share
     {
         double blk[36] = {0};
         place(blk, 6, 0, M1, 2, hx / (hy * hz)); place(blk, 6, 2, M1, 2, hy / (hx * hz)); place(blk, 6, 4, M1, 2, hz / (hx * hy));
-        fill_pool(S.M[{2, 0}], nel, blk, 6, beta);
+        fill_pool(S.M[{2, 0}], nel, blk, 6, beta_components == 1 ? beta : nullptr);
+        if (beta && beta_components == 3)
+        {
+            // diagonal tensor: block a (dofs 2a, 2a+1) of element e is scaled by beta[3 e + a]
+            double *vals = S.M[{2, 0}].vals.data() + (S.M[{2, 0}].vals.size() - (size_t)nel * 36);
+#pragma omp parallel for schedule(static)
+            for (int e = 0; e < nel; ++e)
+                for (int a = 0; a < 3; ++a)
+                    for (int x = 0; x < 2; ++x)
+                        for (int y = 0; y < 2; ++y) vals[(size_t)e * 36 + (size_t)(2 * a + x) * 6 + 2 * a + y] *= beta[3 * (size_t)e + a];
+        }
         double ax = 1.0 / (hy * hz), ay = 1.0 / (hx * hz), az = 1.0 / (hx * hy);
         fill_pool(S.M[{2, 1}], mesh.nfx(), &ax, 1); fill_pool(S.M[{2, 1}], mesh.nfy(), &ay, 1); fill_pool(S.M[{2, 1}], mesh.nfz(), &az, 1);
     }

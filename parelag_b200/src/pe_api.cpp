@@ -2,6 +2,7 @@
 #include "parelag_b200_api.h"
 #include "parelag_solvers.hpp"
 #include "amge_coarsen.hpp"
+#include "spe10.hpp"
 #include <cstring>
 
 void pe_set_error(const std::string &msg);   // csrc/pe_core.cu
@@ -170,6 +171,79 @@ extern "C" int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const 
     auto s = new pe_sequence();
     s->levels = BuildHexSequenceHierarchy(nx, ny, nz, 1.0, 1.0, 1.0, alpha, beta, jstart, nlevels, svd_tol, vertex_xyz);
     *out = s;
+    API_CATCH
+}
+extern "C" int pe_api_hexsequence_create_tensor(int nx, int ny, int nz, double Lx, double Ly, double Lz, const double *alpha, const double *beta_xyz,
+                                                int jstart, int nlevels, double svd_tol, pe_sequence **out)
+{
+    API_TRY
+    auto s = std::make_unique<pe_sequence>();
+    s->levels = BuildHexSequenceHierarchy(nx, ny, nz, Lx, Ly, Lz, alpha, beta_xyz, jstart, nlevels, svd_tol, nullptr, 3);
+    *out = s.release();
+    API_CATCH
+}
+// ---- SPE10 data set (src/SPE10/InversePermeabilityFunction.cpp)
+extern "C" int pe_api_spe10_read(const char *perm_file, int Nx, int Ny, int Nz, double hx, double hy, double hz)
+{
+    API_TRY
+    InversePermeabilityFunction::SetNumberCells(Nx, Ny, Nz);
+    InversePermeabilityFunction::SetMeshSizes(hx, hy, hz);
+    InversePermeabilityFunction::Set2DSlice(InversePermeabilityFunction::NONE, -1);
+    InversePermeabilityFunction::ReadPermeabilityFile(perm_file, g_host_comm.size > 1 ? &g_host_comm : nullptr);
+    API_CATCH
+}
+extern "C" int pe_api_spe10_set_constant(int Nx, int Ny, int Nz, double hx, double hy, double hz, double ipx, double ipy, double ipz)
+{
+    API_TRY
+    InversePermeabilityFunction::SetNumberCells(Nx, Ny, Nz);
+    InversePermeabilityFunction::SetMeshSizes(hx, hy, hz);
+    InversePermeabilityFunction::Set2DSlice(InversePermeabilityFunction::NONE, -1);
+    InversePermeabilityFunction::SetConstantInversePermeability(ipx, ipy, ipz);
+    API_CATCH
+}
+extern "C" int pe_api_spe10_set_slice(int orientation, int npos)
+{
+    API_TRY
+    PARELAG_TEST_FOR_EXCEPTION(orientation < 0 || orientation > 3, std::runtime_error, "pe_api_spe10_set_slice: orientation 0 = none, 1 = XY, 2 = XZ, 3 = YZ");
+    InversePermeabilityFunction::Set2DSlice((InversePermeabilityFunction::SliceOrientation)orientation, npos);
+    API_CATCH
+}
+extern "C" int pe_api_spe10_inverse_permeability(const double *xyz, int npoints, double *out)
+{
+    API_TRY
+    for (int p = 0; p < npoints; ++p)
+    {
+        out[3 * (size_t)p + 2] = 0.0;
+        InversePermeabilityFunction::InversePermeability(xyz + 3 * (size_t)p, out + 3 * (size_t)p);
+    }
+    API_CATCH
+}
+extern "C" int pe_api_spe10_data(double *out, int64_t *count)
+{
+    API_TRY
+    const std::vector<double> &d = InversePermeabilityFunction::Data();
+    if (count) *count = (int64_t)d.size();
+    if (out) std::copy(d.begin(), d.end(), out);
+    API_CATCH
+}
+extern "C" int pe_api_hexsequence_create_spe10(int nx, int ny, int nz, double hx, double hy, double hz, int jstart, int nlevels, double svd_tol,
+                                               pe_sequence **out)
+{
+    API_TRY
+    PARELAG_TEST_FOR_EXCEPTION(!InversePermeabilityFunction::Loaded(), std::runtime_error, "pe_api_hexsequence_create_spe10: read the permeability data first");
+    // the coefficient of the element mass matrices is evaluated inside the cells (quadrature points of VectorFEMassIntegrator):
+    // one value of the piecewise constant data per cell, taken at the cell centre
+    std::vector<double> kinv((size_t)3 * nx * ny * nz);
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i)
+            {
+                const double c[3] = {(i + 0.5) * hx, (j + 0.5) * hy, (k + 0.5) * hz};
+                InversePermeabilityFunction::InversePermeability(c, &kinv[3 * ((size_t)i + (size_t)nx * (j + (size_t)ny * k))]);
+            }
+    auto s = std::make_unique<pe_sequence>();
+    s->levels = BuildHexSequenceHierarchy(nx, ny, nz, nx * hx, ny * hy, nz * hz, nullptr, kinv.data(), jstart, nlevels, svd_tol, nullptr, 3);
+    *out = s.release();
     API_CATCH
 }
 static int copy_lines(const std::vector<std::string> &lines, char *buf, int64_t capacity, int64_t *needed)
