@@ -158,6 +158,15 @@ int pe_api_solver_build_block(const char *xml_library, const char *solver_name, 
                               pe_sequence *seq, int start_level, const int32_t *forms, const int32_t *ess_attr,
                               int nattr, pe_solver **out);
 
+/* Introspection of the ParameterList machinery (SimpleXMLParameterListReader::GetParameterList,
+ * src/utilities/ParELAG_SimpleXMLParameterListReader.cpp:55-297; SolverLibrary::GetSolverFactory):
+ * pe_api_parameterlist_dump: every parameter of the parsed document as "path/name<TAB>type<TAB>value", one per line, sorted;
+ * pe_api_library_factories: every entry of the "Preconditioner Library" sublist (or of the document itself) as
+ *   "name<TAB>Type<TAB>ok" when its factory can be created and initialised (nested factories included), else
+ *   "name<TAB>Type<TAB>error: ..." -- e.g. the hypre / direct black-box types that are outside the GPU path.
+ * *needed = bytes including the terminator (call with buf = NULL first).  No device needed. */
+int pe_api_parameterlist_dump(const char *xml, char *buf, int64_t capacity, int64_t *needed);
+int pe_api_library_factories(const char *xml, char *buf, int64_t capacity, int64_t *needed);
 /* SolverLibrary::CreateLibrary(xml) -> GetSolverFactory(name) -> BuildSolver(A, state).
  * xml: a <ParameterList name="Preconditioner Library"> document.  seq may be NULL for
  * solvers that need no sequence.  ess_attr[nattr]: essential boundary attribute marker

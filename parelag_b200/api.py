@@ -62,6 +62,24 @@ def spe10_inverse_permeability(x):
     return out
 
 
+def _lines(fn, *args):
+    need = C.c_int64()
+    _chk(fn(*args, None, C.c_int64(0), C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _chk(fn(*args, buf, C.c_int64(need.value), None))
+    return [l for l in buf.value.decode().split("\n") if l]
+
+
+def parameterlist_dump(xml):
+    """the parsed XML parameter list, one "path/name<TAB>type<TAB>value" line per parameter, sorted"""
+    return _lines(lib().pe_api_parameterlist_dump, xml.encode())
+
+
+def library_factories(xml):
+    """[(solver name, factory type, "ok" | "error: ...")] for every entry of the document's Preconditioner Library"""
+    return [tuple(l.split("\t", 2)) for l in _lines(lib().pe_api_library_factories, xml.encode())]
+
+
 def topology_log():
     """the lines the reference prints during the topology coarsening (since the options were last set)"""
     need = C.c_int64()

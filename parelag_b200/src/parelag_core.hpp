@@ -12,7 +12,9 @@
 // PARELAG_TEST_FOR_EXCEPTION / PARELAG_ASSERT) as the reference, so the reference's
 // drivers and tests read the same against this library.
 #pragma once
+#include <algorithm>
 #include <any>
+#include <cctype>
 #include <chrono>
 #include <functional>
 #include <iostream>
@@ -178,6 +180,36 @@ public:
         for (auto &kv : Sublists_) out.push_back(kv.first);
         return out;
     }
+    /// every parameter as "path/name<TAB>type<TAB>value", sublists separated by '/', lines in lexicographic order;
+    /// integers in decimal, floating point with 17 significant digits, bool true/false, vectors blank separated,
+    /// string lists comma separated (introspection for tests of the XML reader)
+    void Dump(std::vector<std::string> &out, const std::string &prefix = "") const
+    {
+        for (auto &kv : Params_)
+        {
+            std::ostringstream v;
+            v.precision(17);
+            std::string type = "?";
+            const std::any &a = kv.second;
+            if (auto p = std::any_cast<bool>(&a)) { type = "bool"; v << (*p ? "true" : "false"); }
+            else if (auto p = std::any_cast<char>(&a)) { type = "char"; v << (int)*p; }
+            else if (auto p = std::any_cast<int>(&a)) { type = "int"; v << *p; }
+            else if (auto p = std::any_cast<long>(&a)) { type = "long"; v << *p; }
+            else if (auto p = std::any_cast<unsigned long>(&a)) { type = "unsigned long"; v << *p; }
+            else if (auto p = std::any_cast<long long>(&a)) { type = "long long"; v << *p; }
+            else if (auto p = std::any_cast<unsigned long long>(&a)) { type = "unsigned long long"; v << *p; }
+            else if (auto p = std::any_cast<float>(&a)) { type = "float"; v << (double)*p; }
+            else if (auto p = std::any_cast<double>(&a)) { type = "double"; v << *p; }
+            else if (auto p = std::any_cast<long double>(&a)) { type = "long double"; v << (double)*p; }
+            else if (auto p = std::any_cast<std::string>(&a)) { type = "string"; v << *p; }
+            else if (auto p = std::any_cast<std::vector<int>>(&a)) { type = "vector(int)"; for (size_t q = 0; q < p->size(); ++q) v << (q ? " " : "") << (*p)[q]; }
+            else if (auto p = std::any_cast<std::vector<double>>(&a)) { type = "vector(double)"; for (size_t q = 0; q < p->size(); ++q) v << (q ? " " : "") << (*p)[q]; }
+            else if (auto p = std::any_cast<std::list<std::string>>(&a)) { type = "list(string)"; bool first = true; for (auto &t : *p) { v << (first ? "" : ",") << t; first = false; } }
+            out.push_back(prefix + kv.first + "\t" + type + "\t" + v.str());
+        }
+        for (auto &kv : Sublists_) kv.second->Dump(out, prefix + kv.first + "/");
+        if (prefix.empty()) std::sort(out.begin(), out.end());
+    }
     void Print(std::ostream &os, unsigned indent = 0) const noexcept
     {
         std::string pad(indent, ' ');
@@ -248,17 +280,27 @@ public:
     }
 
 private:
+    /// key = "value" pairs of a tag; blanks and line breaks may surround the '=' (examples/example_parameterlists/
+    /// 1form_example_parameters.xml writes name = "Type"), values are double-quoted and may contain any character but '"'
     static std::map<std::string, std::string> Attributes(const std::string &tag)
     {
         std::map<std::string, std::string> out;
-        size_t p = 0;
-        while ((p = tag.find('=', p)) != std::string::npos)
+        const size_t n = tag.size();
+        size_t p = tag.find_first_of(" \t\r\n");          // skip the element name
+        while (p != std::string::npos && p < n)
         {
-            size_t ks = tag.find_last_of(" \t\n", p);
-            std::string key = tag.substr(ks + 1, p - ks - 1);
-            size_t q0 = tag.find('"', p);
-            size_t q1 = tag.find('"', q0 + 1);
-            out[key] = tag.substr(q0 + 1, q1 - q0 - 1);
+            while (p < n && std::isspace((unsigned char)tag[p])) ++p;
+            size_t k0 = p;
+            while (p < n && !std::isspace((unsigned char)tag[p]) && tag[p] != '=') ++p;
+            const std::string key = tag.substr(k0, p - k0);
+            while (p < n && std::isspace((unsigned char)tag[p])) ++p;
+            if (key.empty() || p >= n || tag[p] != '=') break;
+            ++p;
+            while (p < n && std::isspace((unsigned char)tag[p])) ++p;
+            PARELAG_TEST_FOR_EXCEPTION(p >= n || tag[p] != '"', std::runtime_error, "XML: attribute \"" << key << "\" has no quoted value");
+            const size_t q1 = tag.find('"', p + 1);
+            PARELAG_TEST_FOR_EXCEPTION(q1 == std::string::npos, std::runtime_error, "XML: unterminated attribute value");
+            out[key] = tag.substr(p + 1, q1 - p - 1);
             p = q1 + 1;
         }
         return out;
@@ -272,18 +314,46 @@ private:
     }
     static void SetTyped(ParameterList &pl, const std::string &name, const std::string &type, const std::string &value)
     {
-        if (type == "bool") pl.Set(name, value == "true" || value == "1");
+        // add_parameter_to_list (ParELAG_SimpleXMLParameterListReader.cpp:207-297): names and values must not be empty;
+        // a bool is true iff its value is "true" in any letter case; the full list of arithmetic types
+        PARELAG_ASSERT(!name.empty());
+        PARELAG_ASSERT(!value.empty());
+        if (type == "bool")
+        {
+            std::string up = value;
+            std::transform(up.begin(), up.end(), up.begin(), [](unsigned char c) { return (char)std::toupper(c); });
+            pl.Set(name, up == "TRUE");
+        }
+        else if (type == "char") pl.Set(name, (char)std::stoi(value));
         else if (type == "int") pl.Set(name, std::stoi(value));
-        else if (type == "size_t") pl.Set(name, (size_t)std::stoull(value));   // ParELAG_SimpleXMLParameterListReader.cpp:244
+        else if (type == "long") pl.Set(name, std::stol(value));
+        else if (type == "unsigned long") pl.Set(name, std::stoul(value));
+        else if (type == "long long") pl.Set(name, std::stoll(value));
+        else if (type == "unsigned long long") pl.Set(name, std::stoull(value));
+        else if (type == "size_t") pl.Set(name, (size_t)std::stoull(value));
+        else if (type == "float") pl.Set(name, std::stof(value));
         else if (type == "double") pl.Set(name, std::stod(value));
+        else if (type == "long double") pl.Set(name, std::stold(value));
         else if (type == "string") pl.Set(name, value);
         else if (type == "vector(int)" || type == "vector_int")
         { std::vector<int> v; for (auto &t : Split(value)) v.push_back(std::stoi(t)); pl.Set(name, v); }
         else if (type == "vector(double)" || type == "vector_double")
         { std::vector<double> v; for (auto &t : Split(value)) v.push_back(std::stod(t)); pl.Set(name, v); }
         else if (type == "list(string)")
-        { std::list<std::string> v; std::string cur; for (char c : value) { if (c == ',') { v.push_back(cur); cur.clear(); } else cur += c; }
-          if (!cur.empty()) v.push_back(cur); pl.Set(name, v); }
+        {
+            // comma separated, every entry trimmed (trim_string, :363-380)
+            std::list<std::string> v; std::string cur;
+            auto push = [&v](const std::string &t)
+            {
+                size_t a = 0, b = t.size();
+                while (a < b && std::isspace((unsigned char)t[a])) ++a;
+                while (b > a && std::isspace((unsigned char)t[b - 1])) --b;
+                v.push_back(t.substr(a, b - a));
+            };
+            for (char c : value) { if (c == ',') { push(cur); cur.clear(); } else cur += c; }
+            if (!cur.empty()) push(cur);
+            pl.Set(name, v);
+        }
         else PARELAG_TEST_FOR_EXCEPTION(true, std::runtime_error, "XML: unknown parameter type \"" << type << "\"");
     }
 };
@@ -477,7 +547,8 @@ public:
         auto fact = cr->second();
         fact->SetSolverLibrary(shared_from_this());
         Cache_[name] = fact;          // before Initialize: nested lookups may recurse
-        fact->Initialize(e->second.second);
+        try { fact->Initialize(e->second.second); }
+        catch (...) { Cache_.erase(name); throw; }      // a factory whose initialisation failed must not be handed out later
         return fact;
     }
 private:

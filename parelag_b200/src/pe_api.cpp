@@ -381,6 +381,40 @@ extern "C" int pe_api_sequence_get_stat(pe_sequence *s, int level, const char *n
     API_CATCH
 }
 
+extern "C" int pe_api_parameterlist_dump(const char *xml, char *buf, int64_t capacity, int64_t *needed)
+{
+    API_TRY
+    SimpleXMLParameterListReader reader;
+    auto pl = reader.Parse(xml);
+    std::vector<std::string> lines;
+    pl->Dump(lines);
+    copy_lines(lines, buf, capacity, needed);
+    API_CATCH
+}
+extern "C" int pe_api_library_factories(const char *xml, char *buf, int64_t capacity, int64_t *needed)
+{
+    API_TRY
+    SimpleXMLParameterListReader reader;
+    auto pl = reader.Parse(xml);
+    const ParameterList &libpl = pl->IsSublist("Preconditioner Library") ? pl->Sublist("Preconditioner Library") : *pl;
+    auto lib = SolverLibrary::CreateLibrary(libpl);
+    std::vector<std::string> names = libpl.SublistNames(), lines;
+    std::sort(names.begin(), names.end());
+    for (const std::string &name : names)
+    {
+        const std::string type = libpl.Sublist(name).Get<std::string>("Type");
+        std::string status = "ok";
+        try { (void)lib->GetSolverFactory(name); }
+        catch (const std::exception &e)
+        {
+            status = std::string("error: ") + e.what();
+            std::replace(status.begin(), status.end(), '\n', ' ');
+        }
+        lines.push_back(name + "\t" + type + "\t" + status);
+    }
+    copy_lines(lines, buf, capacity, needed);
+    API_CATCH
+}
 extern "C" int pe_api_solver_build(const char *xml, const char *name, const pe_parcsr_host *A, pe_sequence *seq,
                                    int start_level, int form, const int32_t *ess_attr, int nattr, pe_solver **out)
 {

@@ -1,0 +1,109 @@
+"""The ParameterList machinery of the drop-in boundary on the CPU: SimpleXMLParameterListReader
+(src/utilities/ParELAG_SimpleXMLParameterListReader.cpp:55-380) and SolverLibrary::GetSolverFactory
+(src/linalg/factories/ParELAG_SolverLibrary.cpp:36-67) through the C ABI -- on a document that exercises the reader's rules,
+and on the reference's own example parameter lists (examples/example_parameterlists/*.xml) when the reference tree is present
+(this container; they are compared with an independent parse by xml.etree)."""
+import glob
+import os
+import xml.etree.ElementTree as ET
+
+import pytest
+
+from parelag_b200 import api, capi
+
+REF_LISTS = sorted(glob.glob("/root/reference/examples/example_parameterlists/*.xml"))
+SUPPORTED = {"AMGe", "Hypre", "Hiptmair", "Krylov", "Stationary", "Block GS", "Block Jacobi", "Block LDU"}
+
+
+def fmt(typ, val):
+    """the canonical form pe_api_parameterlist_dump prints"""
+    if typ == "bool":
+        return "true" if val.upper() == "TRUE" else "false"          # :223-236: "true" in any letter case
+    if typ in ("int", "long", "long long", "unsigned long", "unsigned long long", "size_t", "char"):
+        return str(int(val))
+    if typ in ("double", "float", "long double"):
+        return "%.17g" % float(val)
+    if typ in ("vector(int)", "vector_int"):
+        return " ".join(str(int(t)) for t in val.split())
+    if typ in ("vector(double)", "vector_double"):
+        return " ".join("%.17g" % float(t) for t in val.split())
+    if typ == "list(string)":
+        return ",".join(t.strip() for t in val.split(","))            # :272-286: comma separated, trimmed
+    return val
+
+
+def etree_dump(text):
+    names = {"vector_int": "vector(int)", "vector_double": "vector(double)", "size_t": "unsigned long"}
+    out = []
+
+    def walk(node, prefix):
+        for ch in node:
+            if ch.tag == "ParameterList":
+                walk(ch, prefix + ch.attrib["name"] + "/")
+            elif ch.tag == "Parameter":
+                t = ch.attrib["type"]
+                out.append("%s%s\t%s\t%s" % (prefix, ch.attrib["name"], names.get(t, t), fmt(t, ch.attrib["value"])))
+    walk(ET.fromstring(text), "")
+    return sorted(out)
+
+
+def test_reader_rules():
+    doc = """<?xml version="1.0"?>
+<!-- a comment with <tags> and = signs -->
+<ParameterList name="Default">
+  <Parameter name = "Type"   type="string" value="Hiptmair"/>
+  <Parameter name="flag a" type="bool" value="True"/> <Parameter name="flag b" type="bool" value="TRUE"/>
+  <Parameter name="flag c" type="bool" value="1"/>
+  <Parameter name="solvers" type="list(string)"
+             value="PCG-AMGe , GMRES with spaces,last"/>
+  <ParameterList name="Sub list">
+    <!--Parameter name="off" type="int" value="3"/-->
+    <Parameter name="n" type="int" value="-7"/> <Parameter name="big" type="size_t" value="5000000000"/>
+    <Parameter name="x" type="double" value="1e-6"/> <Parameter name="v" type="vector(int)" value="2 3"/>
+    <Parameter name="w" type="vector_double" value="0.5 1.5e3"/> <Parameter name="l" type="long long" value="-9000000000"/>
+    <ParameterList name="Empty"/>
+  </ParameterList>
+</ParameterList>"""
+    got = api.parameterlist_dump(doc)
+    assert got == sorted([
+        "Type\tstring\tHiptmair", "flag a\tbool\ttrue", "flag b\tbool\ttrue", "flag c\tbool\tfalse",
+        "solvers\tlist(string)\tPCG-AMGe,GMRES with spaces,last",
+        "Sub list/n\tint\t-7", "Sub list/big\tunsigned long\t5000000000", "Sub list/x\tdouble\t9.9999999999999995e-07",
+        "Sub list/v\tvector(int)\t2 3", "Sub list/w\tvector(double)\t0.5 1500", "Sub list/l\tlong long\t-9000000000"])
+    assert got == etree_dump(doc)
+    with pytest.raises(capi.PEError):
+        api.parameterlist_dump('<ParameterList name="x"><Parameter name="a" type="quaternion" value="1"/></ParameterList>')
+    with pytest.raises(capi.PEError):
+        api.parameterlist_dump('<ParameterList name="x"><Parameter name="a" type="int" value=""/></ParameterList>')
+
+
+def test_failed_factory_is_not_cached():
+    """a factory whose initialisation fails (unknown nested type) must fail again when asked for directly"""
+    lib = {"Outer": ("Krylov", {"Solver name": "PCG", "Preconditioner": "Inner"}), "Inner": ("BoomerAMG", {})}
+    rep = dict((n, s) for n, t, s in api.library_factories(api.library_xml(lib)))
+    assert rep["Inner"].startswith("error") and "BoomerAMG" in rep["Inner"]
+    assert rep["Outer"].startswith("error") and "BoomerAMG" in rep["Outer"]
+
+
+@pytest.mark.skipif(not REF_LISTS, reason="reference tree not present")
+@pytest.mark.parametrize("path", REF_LISTS, ids=[os.path.basename(p) for p in REF_LISTS])
+def test_reference_example_parameter_lists(path):
+    text = open(path).read()
+    assert api.parameterlist_dump(text) == etree_dump(text)
+    # every library entry: "ok" exactly when the types it depends on (transitively) are on the GPU path
+    root = ET.fromstring(text)
+    lib = next(ch for ch in root if ch.tag == "ParameterList" and ch.attrib["name"] == "Preconditioner Library")
+    types, deps = {}, {}
+    for e in lib:
+        types[e.attrib["name"]] = next(p.attrib["value"] for p in e if p.tag == "Parameter" and p.attrib["name"] == "Type")
+        deps[e.attrib["name"]] = [p.attrib["value"] for sub in e if sub.tag == "ParameterList" for p in sub.iter("Parameter")]
+
+    def closure_ok(name, seen=()):
+        if types[name] not in SUPPORTED:
+            return False
+        return all(closure_ok(d, seen + (name,)) for d in deps[name] if d in types and d != name and d not in seen)
+    for name, typ, status in api.library_factories(text):
+        assert typ == types[name]
+        assert (status == "ok") == closure_ok(name), (name, typ, status)
+        if status != "ok":
+            assert "unknown factory type" in status
