@@ -444,13 +444,12 @@ class Block2x2GaussSeidelSolverFactory : public BlockSolverFactory
         Op_Ptr A11 = SecondDiagonalOperator(*blop, *A11_state);
         inv_ops[1] = std::shared_ptr<mfem::Solver>{InvA11_Fact_->BuildSolver(A11, *A11_state)};
         inv_ops[1]->iterative_mode = false;
-        return make_unique<BlockTriangularSolver>(blop, inv_ops, S_Fact_ ? std::vector<Op_Ptr>{A11} : std::vector<Op_Ptr>{},
-                                                  BlockTriangularSolver::Triangle::LOWER_TRIANGLE);
+        return make_unique<BlockTriangularSolver>(blop, inv_ops, S_Fact_ ? std::vector<Op_Ptr>{A11} : std::vector<Op_Ptr>{}, tri_);
     }
     void _do_set_default_parameters() override
     {
         auto &p = GetParameters();
-        p.Get<bool>("Use Negative S", true); p.Get<double>("Alpha", 1.0); p.Get("S Type", "NONE");
+        p.Get<bool>("Use Negative S", true); p.Get<double>("Alpha", 1.0); p.Get("S Type", "NONE"); p.Get("Use triangle", "Lower");
     }
     void _do_initialize(const ParameterList &) override
     {
@@ -459,8 +458,15 @@ class Block2x2GaussSeidelSolverFactory : public BlockSolverFactory
         InvA00_Fact_ = GetSolverLibrary().GetSolverFactory(params.Get("A00 Inverse", "Default Hypre"));
         InvA11_Fact_ = GetSolverLibrary().GetSolverFactory(params.Get("A11 Inverse", "Default Hypre"));
         InitSchur();
+        // "Use triangle": Lower (default) or Upper, any letter case (ParELAG_Block2x2GaussSeidelSolverFactory.cpp:147-165)
+        std::string tri = params.Get("Use triangle", "Lower");
+        std::transform(tri.begin(), tri.end(), tri.begin(), ::toupper);
+        PARELAG_TEST_FOR_EXCEPTION(tri != "LOWER" && tri != "UPPER", std::runtime_error,
+                                   "Block2x2GaussSeidelSolverFactory: \"Use triangle\" = \"" << tri << "\" is invalid; valid options are \"Lower\" and \"Upper\"");
+        tri_ = tri == "LOWER" ? BlockTriangularSolver::Triangle::LOWER_TRIANGLE : BlockTriangularSolver::Triangle::UPPER_TRIANGLE;
     }
     std::shared_ptr<SolverFactory> InvA00_Fact_, InvA11_Fact_;
+    BlockTriangularSolver::Triangle tri_ = BlockTriangularSolver::Triangle::LOWER_TRIANGLE;
 };
 
 class Block2x2LDUSolverFactory : public BlockSolverFactory

@@ -107,3 +107,38 @@ def test_reference_example_parameter_lists(path):
         assert (status == "ok") == closure_ok(name), (name, typ, status)
         if status != "ok":
             assert "unknown factory type" in status
+
+
+def test_block_gs_use_triangle_parameter():
+    """ParELAG_Block2x2GaussSeidelSolverFactory.cpp:147-165: "Use triangle" = Lower | Upper in any letter case, else an error"""
+    gs = ("Hypre", {"Type": "Gauss-Seidel"})
+    for value, ok in (("Lower", True), ("upper", True), ("UPPER", True), ("diagonal", False)):
+        lib = {"GS": gs, "B": ("Block GS", {"A00 Inverse": "GS", "A11 Inverse": "GS", "Use triangle": value})}
+        rep = dict((n, s) for n, t, s in api.library_factories(api.library_xml(lib)))
+        assert (rep["B"] == "ok") == ok, (value, rep["B"])
+        if not ok:
+            assert "Use triangle" in rep["B"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/linalg"), reason="reference tree not present")
+def test_every_parameter_name_of_the_reference_factories_is_read():
+    """name-level parity of the ParameterList API: every parameter / sublist name the reference's solver factories and
+    solver operators on the GPU path read (string literals of Get / IsParameter / Sublist calls in src/linalg/factories
+    and src/linalg/solver_ops; hypre black boxes, direct, hybridization and PETSc wrappers excluded) is also read by the
+    product's classes"""
+    import re
+    skip = ("Hybridization", "Direct", "BoomerAMG", "AMS", "ADS", "Bramble", "PETSc", "Strumpack", "MLHiptmair")
+    pat = re.compile(r'(?:Get|IsParameter|IsSublist|Sublist|Set)(?:<[^>]*>)?\(\s*"([^"]+)"')
+    ref = {}
+    for d in ("factories", "solver_ops"):
+        for f in glob.glob("/root/reference/src/linalg/%s/*.[ch]pp" % d):
+            if not any(k in f for k in skip):
+                for m in pat.finditer(open(f).read()):
+                    ref.setdefault(m.group(1), os.path.basename(f))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prod = set()
+    for f in glob.glob(os.path.join(root, "parelag_b200", "src", "*.[ch]pp")):
+        prod.update(m.group(1) for m in pat.finditer(open(f).read()))
+    assert len(ref) > 40
+    missing = {n: f for n, f in ref.items() if n not in prod}
+    assert not missing, missing
