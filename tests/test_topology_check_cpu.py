@@ -265,3 +265,22 @@ def test_random_partitionings_product_equals_oracle(seed):
         S.free()
     finally:
         api.set_topology_options()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_oracle_coarsen_keeps_the_invariants_on_repaired_random_topologies(seed):
+    """Coarsen() of all four forms on the topology the check leaves behind for a random partitioning (single-element
+    agglomerates, L-shaped agglomerated facets, agglomerates of very different sizes): the CheckInvariants identities
+    (DeRhamSequence.cpp:694-970) must hold -- what the GPU path is compared with on such topologies"""
+    rng = np.random.default_rng(seed)
+    dims = tuple(int(x) for x in rng.integers(2, 5, size=3))
+    nel = dims[0] * dims[1] * dims[2]
+    part = rng.integers(0, int(rng.integers(1, max(2, nel // 3))), size=nel)
+    mesh = amge.HexMesh(*dims)
+    topo = mesh.topology()
+    topo.coarsen(part, check_topology=True)
+    seq = amge.fine_sequence(mesh, topo, jstart=0)
+    seq.svd_tol = 1e-9
+    seq.coarsen()
+    for k, v in amge.check_invariants(seq).items():
+        assert v < 1e-8, (k, v)
