@@ -104,7 +104,8 @@ int pe_api_sequence_show_topology(pe_sequence *s, int level, char *buf, int64_t 
  * refinement, children of element e = 8e .. 8e+7), the finest mesh is level 0 of the sequence and the nlevels - 1 <= nref
  * coarser levels are built by derefinement agglomeration (MFEMRefinedMeshPartitioner.cpp:48-66) and Coarsen().
  * Lowest-order Whitney forms with MFEM's dof meaning; mass matrices in closed form (parelag_b200/src/amge_tet.hpp).
- * pe_api_tetsequence_create_from_file reads the NETGEN neutral format of meshes/cube456.mesh (mfem::Mesh(imesh, 1, 1)). */
+ * pe_api_tetsequence_create_from_file reads the NETGEN neutral format of meshes/cube456.mesh or MFEM's own "MFEM mesh v1.0"
+ * format (straight-sided tetrahedra), recognised from the first line like mfem::Mesh(imesh, 1, 1). */
 int pe_api_tetsequence_create(int nv, const double *vertex_xyz, int nel, const int32_t *tets, int nbdr, const int32_t *bdr_triangles,
                               const int32_t *bdr_attributes, int nref, int nlevels, int jform_start, double svd_tol, pe_sequence **out);
 int pe_api_tetsequence_create_from_file(const char *mesh_file, int nref, int nlevels, int jform_start, double svd_tol, pe_sequence **out);

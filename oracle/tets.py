@@ -37,6 +37,39 @@ def read_netgen_neutral(path):
     return V, E[:, 1:] - 1, B[:, 1:] - 1, B[:, 0].copy()
 
 
+def write_mfem_mesh(path, V, T, B, A, element_attribute=1):
+    """MFEM mesh v1.0 (0-based vertex numbers; geometry type 4 = tetrahedron, 2 = triangle), with the comment block MFEM writes"""
+    with open(path, "w") as f:
+        f.write("MFEM mesh v1.0\n\n#\n# MFEM Geometry Types (see mesh/geom.hpp):\n#\n# POINT       = 0\n# SEGMENT     = 1\n"
+                "# TRIANGLE    = 2\n# SQUARE      = 3\n# TETRAHEDRON = 4\n# CUBE        = 5\n#\n\ndimension\n3\n\nelements\n%d\n" % len(T))
+        for t in T:
+            f.write("%d 4 %d %d %d %d\n" % ((element_attribute,) + tuple(int(v) for v in t)))
+        f.write("\nboundary\n%d\n" % len(B))
+        for a, t in zip(A, B):
+            f.write("%d 2 %d %d %d\n" % ((int(a),) + tuple(int(v) for v in t)))
+        f.write("\nvertices\n%d\n3\n" % len(V))
+        for x in V:
+            f.write("%.17g %.17g %.17g\n" % tuple(x))
+
+
+def read_mfem_mesh(path):
+    """MFEM mesh v1.0, straight-sided tetrahedra: the same four arrays as read_netgen_neutral"""
+    lines = open(path).read().split("\n")
+    assert lines[0].startswith("MFEM mesh v1.0")
+    tok = " ".join(l.split("#")[0] for l in lines[1:]).split()
+    p = 0
+    assert tok[p] == "dimension" and tok[p + 1] == "3"; p += 2
+    assert tok[p] == "elements"; ne = int(tok[p + 1]); p += 2
+    E = np.array(tok[p:p + 6 * ne], dtype=np.int64).reshape(ne, 6); p += 6 * ne
+    assert np.all(E[:, 1] == 4)
+    assert tok[p] == "boundary"; nb = int(tok[p + 1]); p += 2
+    Bd = np.array(tok[p:p + 5 * nb], dtype=np.int64).reshape(nb, 5); p += 5 * nb
+    assert np.all(Bd[:, 1] == 2)
+    assert tok[p] == "vertices"; nv = int(tok[p + 1]); assert tok[p + 2] == "3"; p += 3
+    V = np.array(tok[p:p + 3 * nv], dtype=np.float64).reshape(nv, 3)
+    return V, E[:, 2:], Bd[:, 2:], Bd[:, 0].copy()
+
+
 def load_npz(path):
     """the arrays of tests/golden/cube456.npz (written by tests/golden/make_cube456.py from the reference's mesh file)"""
     d = np.load(path)

@@ -16,6 +16,7 @@
 #pragma once
 #include <array>
 #include <fstream>
+#include <sstream>
 #include "amge_dofs.hpp"
 
 namespace parelag
@@ -69,6 +70,82 @@ struct TetMesh
         PARELAG_TEST_FOR_EXCEPTION(in.fail(), std::runtime_error, "mesh file " << path << ": truncated");
         m.Build();
         return m;
+    }
+
+    /// MFEM's own format, "MFEM mesh v1.0" (what mfem::Mesh(imesh, 1, 1) reads for the meshes distributed with MFEM):
+    /// comment lines start with '#'; sections `dimension`, `elements` (attribute, geometry type, vertices), `boundary`
+    /// (attribute, geometry type, vertices), `vertices` (count, space dimension, coordinates); 0-based vertex numbers.
+    /// Straight-sided tetrahedral meshes only: geometry types 4 (tetrahedron) for elements and 2 (triangle) for the boundary;
+    /// a `nodes` grid function (curved mesh) is rejected.
+    static TetMesh ReadMFEM(const std::string &path)
+    {
+        std::ifstream in(path);
+        PARELAG_TEST_FOR_EXCEPTION(!in.good(), std::runtime_error, "Cannot read mesh from input file: " << path);
+        // tokens without the comments
+        std::vector<std::string> tok;
+        bool first = true;
+        for (std::string line; std::getline(in, line);)
+        {
+            if (first)
+            {
+                first = false;
+                PARELAG_TEST_FOR_EXCEPTION(line.rfind("MFEM mesh v1.0", 0) != 0, std::runtime_error, "mesh file " << path << ": not an MFEM mesh v1.0 file");
+                continue;
+            }
+            const size_t hash = line.find('#');
+            if (hash != std::string::npos) line.erase(hash);
+            std::istringstream ls(line);
+            for (std::string t; ls >> t;) tok.push_back(t);
+        }
+        size_t p = 0;
+        auto next = [&]() -> const std::string &
+        {
+            PARELAG_TEST_FOR_EXCEPTION(p >= tok.size(), std::runtime_error, "mesh file " << path << ": truncated");
+            return tok[p++];
+        };
+        auto expect = [&](const char *word)
+        { const std::string &t = next(); PARELAG_TEST_FOR_EXCEPTION(t != word, std::runtime_error, "mesh file " << path << ": expected \"" << word << "\", found \"" << t << "\""); };
+        TetMesh m;
+        expect("dimension");
+        PARELAG_TEST_FOR_EXCEPTION(std::stoi(next()) != 3, std::runtime_error, "mesh file " << path << ": only 3-d meshes");
+        expect("elements");
+        const int ne = std::stoi(next());
+        m.T.resize((size_t)4 * ne);
+        for (int e = 0; e < ne; ++e)
+        {
+            (void)next();                                                  // element attribute
+            PARELAG_TEST_FOR_EXCEPTION(std::stoi(next()) != 4, not_implemented_error, "mesh file " << path << ": only tetrahedra (geometry type 4)");
+            for (int q = 0; q < 4; ++q) m.T[4 * (size_t)e + q] = std::stoi(next());
+        }
+        expect("boundary");
+        const int nb = std::stoi(next());
+        m.Btri.resize((size_t)3 * nb); m.Battr.resize(nb);
+        for (int b = 0; b < nb; ++b)
+        {
+            m.Battr[b] = std::stoi(next());
+            PARELAG_TEST_FOR_EXCEPTION(std::stoi(next()) != 2, not_implemented_error, "mesh file " << path << ": only triangular boundary elements (geometry type 2)");
+            for (int q = 0; q < 3; ++q) m.Btri[3 * (size_t)b + q] = std::stoi(next());
+        }
+        expect("vertices");
+        const int nv = std::stoi(next());
+        const std::string &vd = next();
+        PARELAG_TEST_FOR_EXCEPTION(vd == "nodes", not_implemented_error, "mesh file " << path << ": curved meshes (nodes grid function) are not supported");
+        PARELAG_TEST_FOR_EXCEPTION(std::stoi(vd) != 3, std::runtime_error, "mesh file " << path << ": vertices must have 3 coordinates");
+        m.V.resize((size_t)3 * nv);
+        for (auto &x : m.V) x = std::stod(next());
+        m.Build();
+        return m;
+    }
+    /// mfem::Mesh(imesh, 1, 1): the format is recognised from the first line
+    static TetMesh Read(const std::string &path)
+    {
+        std::ifstream in(path);
+        PARELAG_TEST_FOR_EXCEPTION(!in.good(), std::runtime_error, "Cannot read mesh from input file: " << path);
+        std::string line;
+        std::getline(in, line);
+        in.close();
+        if (line.rfind("MFEM mesh v1.0", 0) == 0) return ReadMFEM(path);
+        return ReadNetgenNeutral(path);
     }
 
     void Build()

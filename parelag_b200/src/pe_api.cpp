@@ -296,7 +296,7 @@ extern "C" int pe_api_tetsequence_create_from_file(const char *mesh_file, int nr
 {
     API_TRY
     auto s = new pe_sequence();
-    const TetMesh mesh = TetMesh::ReadNetgenNeutral(mesh_file);
+    const TetMesh mesh = TetMesh::Read(mesh_file);        // NETGEN neutral or MFEM mesh v1.0, by the first line
     s->levels = BuildTetSequenceHierarchy(mesh, nref, nlevels, nullptr, nullptr, jstart, svd_tol);
     *out = s;
     API_CATCH

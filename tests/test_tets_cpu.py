@@ -103,3 +103,27 @@ def test_product_reads_the_mesh_file(tmp_path):
     if os.path.exists("/root/reference/meshes/cube456.mesh"):          # this container only: the fixture equals the reference's file
         Vr, Tr, Br, Ar = tets.read_netgen_neutral("/root/reference/meshes/cube456.mesh")
         assert np.array_equal(Vr, V) and np.array_equal(Tr, T) and np.array_equal(Br, B) and np.array_equal(Ar, A)
+
+
+def test_product_reads_the_mfem_mesh_format(tmp_path):
+    """MFEM's own "MFEM mesh v1.0" format (comment block, 0-based vertices, geometry types): recognised from the first line
+    like mfem::Mesh(imesh, 1, 1); same tables as from the arrays; unsupported content is refused"""
+    from parelag_b200 import capi
+    V, T, B, A = tets.load_npz(MESH)
+    path = str(tmp_path / "cube456_mfem.mesh")
+    tets.write_mfem_mesh(path, V, T, B, A)
+    V2, T2, B2, A2 = tets.read_mfem_mesh(path)
+    assert np.array_equal(V2, V) and np.array_equal(T2, T) and np.array_equal(B2, B) and np.array_equal(A2, A)
+    S = api.Sequence.tet_from_file(path, 0, 1, svd_tol=-1.0)
+    R = api.Sequence.tet(V, T, B, A, 0, 1, svd_tol=-1.0)
+    for c in range(3):
+        assert same(S.get_csr(0, "B", c), R.get_csr(0, "B", c))
+    assert same(S.get_csr(0, "FB"), R.get_csr(0, "FB"))
+    assert np.array_equal(S.get_targets(0, 0), R.get_targets(0, 0))
+    for j in range(4):
+        assert abs(S.get_csr(0, "Me", j, 0) - R.get_csr(0, "Me", j, 0)).max() == 0
+    S.free(); R.free()
+    bad = str(tmp_path / "hex.mesh")
+    open(bad, "w").write("MFEM mesh v1.0\n\ndimension\n3\n\nelements\n1\n1 5 0 1 2 3 4 5 6 7\n\nboundary\n0\n\nvertices\n8\n3\n" + "0 0 0\n" * 8)
+    with pytest.raises(capi.PEError, match="only tetrahedra"):
+        api.Sequence.tet_from_file(bad, 0, 1, svd_tol=-1.0)
