@@ -76,13 +76,36 @@ private:
     pe_smoother *smoo_ = nullptr;
 };
 
+/// mfem::HypreDiagScale ("Hypre Jacobi", type 413 of ParELAG_HypreSmootherFactory.cpp:27-31): x = diag(A)^{-1} b
+/// (HYPRE_ParCSRDiagScale); the initial guess is ignored whatever iterative_mode says.  One Jacobi sweep with unit weight
+/// from a zero guess is exactly that.
+class HypreDiagScale : public Solver
+{
+public:
+    explicit HypreDiagScale(const Op_Ptr &A) : Solver(A->Height(), A->Width(), true)
+    {
+        ParameterList p("Hypre Jacobi");
+        p.Set("Sweeps", 1); p.Set("Damping Factor", 1.0); p.Set("Omega", 1.0);
+        jacobi_ = make_unique<HypreSmootherWrapper>(A, 0, p);
+        jacobi_->iterative_mode = false;
+    }
+    void Mult(const mfem::Vector &rhs, mfem::Vector &sol) const override { jacobi_->Mult(rhs, sol); }
+    void MultTranspose(const mfem::Vector &rhs, mfem::Vector &sol) const override { jacobi_->Mult(rhs, sol); }
+    bool CaptureSafe() const override { return true; }
+private:
+    void _do_set_operator(const Op_Ptr &) override { PARELAG_NOT_IMPLEMENTED(); }
+    std::unique_ptr<HypreSmootherWrapper> jacobi_;
+};
+
 class HypreSmootherFactory : public SolverFactory
 {
     std::unique_ptr<mfem::Solver> _do_build_solver(const Op_Ptr &op, SolverState &) const override
     {
         auto &params = GetParameters();
         const std::string name = params.Get("Type", "L1 Gauss-Seidel");
-        return make_unique<HypreSmootherWrapper>(op, TypeFromName(name), params);
+        const int type = TypeFromName(name);
+        if (type == 413) return make_unique<HypreDiagScale>(op);
+        return make_unique<HypreSmootherWrapper>(op, type, params);
     }
     void _do_set_default_parameters() override
     {
@@ -101,9 +124,11 @@ public:
         if (n == "Lumped Jacobi") return 5;
         if (n == "Gauss-Seidel") return 6;
         if (n == "Chebyshev") return 16;
+        if (n == "Hypre Jacobi") return 413;
         PARELAG_TEST_FOR_EXCEPTION(true, std::runtime_error,
                                    "HypreSmootherFactory: smoother type \"" << n << "\" is not supported on the GPU path "
-                                   "(supported: Jacobi, L1 Jacobi, L1 Gauss-Seidel, L1 Gauss-Seidel Truncated, Lumped Jacobi, Gauss-Seidel, Chebyshev)");
+                                   "(supported: Jacobi, L1 Jacobi, L1 Gauss-Seidel, L1 Gauss-Seidel Truncated, Lumped Jacobi, Gauss-Seidel, Chebyshev, "
+                                   "Hypre Jacobi)");
         return -1;
     }
 };

@@ -1,6 +1,6 @@
-"""The inputs of the reference's own unit test src/linalg/unit_test/block2x2_test.cpp through the product's block
-preconditioners (kept in a file of its own, last in collection order: written at the end of round 2 and not yet run on a
-GPU -- the oracle half and the residual the unit test prints are checked on the CPU)."""
+"""GPU tests written after the last GPU call of round 2 (collected last, not yet run on a GPU): the inputs of the
+reference's own unit test src/linalg/unit_test/block2x2_test.cpp through the product's block preconditioners (the oracle
+half and the residual the unit test prints are checked on the CPU), and the "Hypre Jacobi" diagonal scaling."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -41,4 +41,17 @@ def test_reference_block2x2_unit_test_inputs(sess, block):
     solver = api.BlockSolver(api.library_xml(lib), "Blk", dev, None, 0, [0, 0])
     x = solver.mult(b, x0=x0)
     assert np.abs(x - xo).max() <= 1e-13 * np.abs(xo).max(), (x, xo)
+    solver.free()
+
+
+def test_hypre_jacobi_is_diagonal_scaling(sess):
+    """"Hypre Jacobi" (type 413, ParELAG_HypreSmootherFactory.cpp:27-31 -> mfem::HypreDiagScale): x = diag(A)^{-1} b, the
+    initial guess is ignored"""
+    from tests.util import random_spd
+    A = random_spd(200, 0.05, 3)
+    b = np.random.default_rng(4).standard_normal(200)
+    solver = api.Solver(api.library_xml({"J": ("Hypre", {"Type": "Hypre Jacobi"})}), "J", A)
+    want = b / A.diagonal()
+    assert np.abs(solver.mult(b) - want).max() <= 1e-15 * np.abs(want).max()
+    assert np.abs(solver.mult(b, x0=np.ones(200)) - want).max() <= 1e-15 * np.abs(want).max()
     solver.free()
