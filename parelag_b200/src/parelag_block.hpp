@@ -96,6 +96,11 @@ public:
     const std::vector<offset_type> &ViewRowOffsets() const noexcept { return RowOffsets_; }
     const std::vector<offset_type> &ViewColumnOffsets() const noexcept { return ColOffsets_; }
     std::vector<offset_type> CopyRowOffsets() const { return RowOffsets_; }
+    /// CopyRowOffsetsAsMfemArray / CopyColumnOffsetsAsMfemArray (ParELAG_MfemBlockOperator.hpp:198-206)
+    void CopyRowOffsetsAsMfemArray(mfem::Array<offset_type> &row_offsets) const
+    { row_offsets.SetSize((int)RowOffsets_.size()); for (size_t i = 0; i < RowOffsets_.size(); ++i) row_offsets[(int)i] = RowOffsets_[i]; }
+    void CopyColumnOffsetsAsMfemArray(mfem::Array<offset_type> &col_offsets) const
+    { col_offsets.SetSize((int)ColOffsets_.size()); for (size_t i = 0; i < ColOffsets_.size(); ++i) col_offsets[(int)i] = ColOffsets_[i]; }
     std::vector<offset_type> CopyColumnOffsets() const { return ColOffsets_; }
 
 private:

@@ -76,6 +76,11 @@ public:
         for (auto &kv : Map()) os << kv.first << " : " << kv.second.total << " (" << kv.second.count << ")\n";
     }
     static void ClearAllData() { Map().clear(); }
+    /// IsTimer / DeleteTimer / ClearAllTimers / PrintSerial (ParELAG_TimeManager.hpp:52-135)
+    static bool IsTimer(const std::string &n) { return Map().count(n) > 0; }
+    static bool DeleteTimer(const std::string &n) { return Map().erase(n) > 0; }
+    static void ClearAllTimers() { Map().clear(); }
+    static void PrintSerial(std::ostream &os = std::cout) { Print(os); }
     class TimerT;
     static TimerT AddTimer(const std::string &n);
     static TimerT GetTimer(const std::string &n);
@@ -374,6 +379,11 @@ public:
         PARELAG_TEST_FOR_EXCEPTION(!p, bad_var_cast, "Level::Get(): wrong type for key \"" << key << "\".");
         return *p;
     }
+    /// the next finer level (ParELAG_Level.hpp: GetPreviousLevel / SetPreviousLevel)
+    std::shared_ptr<Level> GetPreviousLevel() { return PreviousLevel_.lock(); }
+    void SetPreviousLevel(const std::shared_ptr<Level> &PreviousLevel) { PreviousLevel_ = PreviousLevel; }
+    /// overwrite whatever the key holds (Set in the reference refuses to)
+    template <typename T> void Reset(const std::string &key, const T &value) { Data_[key] = std::any(value); }
     bool IsKey(const std::string &key) const noexcept { return Data_.count(key) > 0; }
     /// key exists and the stored shared_ptr<mfem::Operator> is non-null
     bool IsValidKey(const std::string &key) const noexcept
@@ -386,6 +396,7 @@ public:
 private:
     int ID_;
     std::unordered_map<std::string, std::any> Data_;
+    std::weak_ptr<Level> PreviousLevel_;
 };
 
 // ---------------------------------------------------------------- Solver
@@ -415,6 +426,7 @@ public:
     { auto it = Operators_.find(n); return it == Operators_.end() ? nullptr : it->second; }
     bool IsOperator(const std::string &n) const noexcept { return Operators_.count(n) > 0; }
     void SetVector(const std::string &n, const std::shared_ptr<mfem::Vector> &v) { Vectors_[n] = v; }
+    bool IsVector(const std::string &n) const noexcept { return Vectors_.count(n) > 0; }
     std::shared_ptr<mfem::Vector> GetVector(const std::string &n) const noexcept
     { auto it = Vectors_.find(n); return it == Vectors_.end() ? nullptr : it->second; }
     void SetBoundaryLabels(std::vector<std::vector<int>> labels) noexcept { BoundaryLabels_ = std::move(labels); }
@@ -431,6 +443,7 @@ public:
         return BoundaryLabels_[blockID];
     }
     void SetDeRhamSequence(const std::shared_ptr<DeRhamSequence> &seq) noexcept { Sequence_ = seq; }
+    bool HasDeRhamSequence() const noexcept { return (bool)Sequence_; }
     std::shared_ptr<DeRhamSequence> GetDeRhamSequencePtr() const noexcept { return Sequence_; }
     DeRhamSequence &GetDeRhamSequence() const { PARELAG_ASSERT(Sequence_); return *Sequence_; }
     void SetForms(std::vector<int> forms) noexcept { Forms_ = std::move(forms); }
@@ -534,6 +547,24 @@ public:
     void AddSolver(const std::string &name, std::shared_ptr<SolverFactory> fact) { Cache_[name] = std::move(fact); }
     bool IsSolver(const std::string &name) const noexcept { return Entries_.count(name) > 0 || Cache_.count(name) > 0; }
     void RegisterFactoryType(const std::string &type, creator_type c) { Creators_[type] = std::move(c); }
+    /// the reference's registry interface (ParELAG_SolverLibrary.hpp:177-224): names of the solvers in the library, and
+    /// adding / removing / listing factory types (a user type: AddNewSolverFactory("SuperCool", [] { return
+    /// std::make_shared<SuperCoolSolverFactory>(); }))
+    std::list<std::string> GetSolverNames() const
+    {
+        std::list<std::string> ret;
+        for (auto &e : Entries_) ret.push_back(e.first);
+        for (auto &c : Cache_) if (!Entries_.count(c.first)) ret.push_back(c.first);
+        return ret;
+    }
+    bool AddNewSolverFactory(const std::string &id, creator_type builder) { return Creators_.emplace(id, std::move(builder)).second; }
+    bool RemoveSolverFactory(const std::string &id) { return Creators_.erase(id) > 0; }
+    std::list<std::string> GetSolverFactoryNames() const
+    {
+        std::list<std::string> ret;
+        for (auto &c : Creators_) ret.push_back(c.first);
+        return ret;
+    }
     std::shared_ptr<SolverFactory> GetSolverFactory(const std::string &name) const
     {
         auto c = Cache_.find(name);

@@ -711,6 +711,30 @@ public:
     std::vector<std::shared_ptr<Level>>::const_iterator begin() const { return Levels_.begin(); }
     std::vector<std::shared_ptr<Level>>::const_iterator end() const { return Levels_.end(); }
     void SetImplicitTranspose(bool v) noexcept { ImplicitTranspose_ = v; }
+    /// Hierarchy::SetCycle (ParELAG_Hierarchy.cpp:57-106): how often a level recurses into the next coarser one (Mu = -1 skips
+    /// a level); a recorded cycle is dropped and re-recorded by the next Mult.  (The reference's one-argument form tests
+    /// `Mu >= 0` where its message says "Cannot set Mu<0 on every level"; the intended check is applied here.)
+    void SetCycle(int Mu)
+    {
+        PARELAG_TEST_FOR_EXCEPTION(Mu < 0, std::runtime_error, "Hierarchy::SetCycle(): Cannot set Mu<0 on every level.");
+        CycleMu_.assign(1, Mu);
+        DropRecordedCycle();
+    }
+    void SetCycle(int Mu, int LevelID)
+    {
+        PARELAG_TEST_FOR_EXCEPTION(LevelID < 0 || LevelID >= (int)Levels_.size(), std::runtime_error,
+                                   "Hierarchy::SetCycle(): LevelID=" << LevelID << " greater than current number of levels (" << Levels_.size() << ").");
+        if (CycleMu_.size() != Levels_.size()) CycleMu_ = std::vector<int>(Levels_.size(), CycleMu_.empty() ? 0 : CycleMu_[0]);
+        CycleMu_[LevelID] = Mu;
+        DropRecordedCycle();
+    }
+    void SetCycle(std::vector<int> Mus)
+    {
+        PARELAG_TEST_FOR_EXCEPTION(Mus.size() != Levels_.size(), std::runtime_error,
+                                   "Hierarchy::SetCycle(): Input vector has wrong size (" << Mus.size() << "). Correct size is " << Levels_.size() << ".");
+        CycleMu_.swap(Mus);
+        DropRecordedCycle();
+    }
     ~Hierarchy() override { pe_graph_free(graph_); pe_program_free(program_); }
     /// replay the V-cycle as one persistent program kernel (preferred) or one CUDA graph when
     /// every level solver is capture-safe (both default on)
@@ -863,6 +887,12 @@ private:
         graph_ = g; graph_rhs_ = rp; graph_sol_ = sp;
         PE_CALL(pe_graph_launch(ctx, graph_));
         return true;
+    }
+    void DropRecordedCycle() const
+    {
+        pe_graph_free(graph_); graph_ = nullptr;
+        pe_program_free(program_); program_ = nullptr;
+        graph_rhs_ = graph_sol_ = warm_rhs_ = warm_sol_ = nullptr;
     }
     void _do_set_operator(const Op_Ptr &) override { PARELAG_NOT_IMPLEMENTED(); }
     std::vector<std::shared_ptr<Level>> Levels_;
