@@ -71,6 +71,14 @@ public:
     virtual ~DeRhamSequence() = default;
 
     int GetNumberOfForms() const noexcept { return nForms_; }
+    /// the reference's short names (DeRhamSequence.hpp:100-160,329-364,458-461)
+    int GetNumForms() const noexcept { return nForms_; }
+    int GetNumDofs(int jform) const { return GetNumberOfDofs(jform); }
+    int GetNumTrueDofs(int jform) const { return GetNumberOfTrueDofs(jform); }
+    const HostCSR *GetD(int jform) const { return GetDerivativeOperator(jform); }
+    std::shared_ptr<DeRhamSequence> ViewFinerSequence() const { return FinerSequence_.lock(); }
+    template <typename... Ts> std::unique_ptr<mfem::HypreParMatrix> ComputeTrueDerivativeOperator(Ts &&...args) const { return ComputeTrueD(std::forward<Ts>(args)...); }
+    template <typename... Ts> std::unique_ptr<mfem::HypreParMatrix> ComputeTrueMassOperator(Ts &&...args) const { return ComputeTrueM(std::forward<Ts>(args)...); }
     int GetNumberOfDofs(int jform) const { auto d = GetDofHandler(jform); return d ? d->GetNDofs() : 0; }
     int GetNumberOfTrueDofs(int jform) const
     {
