@@ -142,6 +142,10 @@ int pe_api_sequence_get_csr(pe_sequence *s, int level, const char *what, int a, 
                             int32_t *nrows, int32_t *ncols, int64_t *nnz, int32_t *I, int32_t *J, double *A);
 int pe_api_sequence_get_targets(pe_sequence *s, int level, int form, int32_t *ndofs, int32_t *ntargets, double *out);
 int pe_api_sequence_get_bdr_mask(pe_sequence *s, int level, int form, int32_t *ndofs, uint32_t *mask);
+/* DeRhamSequence::CheckInvariants (DeRhamSequence.cpp:694-970) of one level against the next coarser one: D non-zero,
+ * D_{j+1} D_j = 0, D_f P_j = P_{j+1} D_c, M_c = P^T M_f P (levels that hold their mass matrices).  Non-zero return with the
+ * violated identity in pe_last_error(); *worst = the largest residual met.  Host work. */
+int pe_api_sequence_check_invariants(pe_sequence *s, int level, double *worst);
 int pe_api_sequence_get_stat(pe_sequence *s, int level, const char *name, int64_t *value);
 /* System assembly as in the drivers (examples/MultigridTest{0,1,2}Form.cpp:443-475), on the
  * device: A = [M_form +] D^T M_{form+1} D  (the mass term is skipped for form 0), essential

@@ -267,6 +267,13 @@ class Sequence:
         _chk(lib().pe_api_sequence_get_stat(self.h, level, name.encode(), C.byref(v)))
         return v.value
 
+    def check_invariants(self, level):
+        """DeRhamSequence::CheckInvariants of `level` against the next coarser one; raises PEError naming the violated
+        identity, returns the largest residual"""
+        w = C.c_double()
+        _chk(lib().pe_api_sequence_check_invariants(self.h, level, C.byref(w)))
+        return w.value
+
     def show_topology(self, level):
         """AgglomeratedTopology::ShowMe of one level: entity counts and Euler characteristic, as the reference prints them"""
         need = C.c_int64()

@@ -481,6 +481,96 @@ std::shared_ptr<DeRhamSequence> DeRhamSequence::Coarsen()
     return c.coarse;
 }
 
+namespace
+{
+constexpr double DEFAULT_EQUALITY_TOL = 1e-9, LOOSE_EQUALITY_TOL = 1e-6;       // DeRhamSequence.cpp:36-37
+double max_norm(const HostCSR &A) { double m = 0.0; for (double v : A.A) m = std::max(m, std::fabs(v)); return m; }
+/// largest |A - B| entry (AreAlmostEqual, ParELAG_MatrixUtils.cpp:33-110); both in canonical CSR form
+double max_difference(const HostCSR &A, const HostCSR &B, const std::string &Aname, const std::string &Bname)
+{
+    PARELAG_TEST_FOR_EXCEPTION(A.nrows != B.nrows || A.ncols != B.ncols, std::logic_error,
+                               "AreAlmostEqual(): Size(" << Aname << ") = " << A.nrows << "x" << A.ncols << ", Size(" << Bname << ") = "
+                               << B.nrows << "x" << B.ncols << ": sizes don't match!");
+    double err = 0.0;
+    for (int i = 0; i < A.nrows; ++i)
+    {
+        int ka = A.I[i], kb = B.I[i];
+        while (ka < A.I[i + 1] || kb < B.I[i + 1])
+        {
+            const int ja = ka < A.I[i + 1] ? A.J[ka] : INT32_MAX, jb = kb < B.I[i + 1] ? B.J[kb] : INT32_MAX;
+            if (ja == jb) err = std::max(err, std::fabs(A.A[ka++] - B.A[kb++]));
+            else if (ja < jb) err = std::max(err, std::fabs(A.A[ka++]));
+            else err = std::max(err, std::fabs(B.A[kb++]));
+        }
+    }
+    return err;
+}
+} // namespace
+
+double DeRhamSequence::CheckD() const
+{
+    const int j0 = data ? data->jstart : 0;
+    double worst = 0.0;
+    for (int j = j0; j < nForms_ - 1; ++j)
+    {
+        if (!D_[j]) { PARELAG_TEST_FOR_EXCEPTION((bool)data, std::runtime_error, "D_" << j << " is missing"); continue; }
+        PARELAG_TEST_FOR_EXCEPTION(D_[j]->nnz() == 0, std::runtime_error, "nnz(D_" << j << ") = 0!");
+        PARELAG_TEST_FOR_EXCEPTION(max_norm(*D_[j]) < LOOSE_EQUALITY_TOL, std::runtime_error, "maxNorm(D_" << j << ") = " << max_norm(*D_[j]));
+    }
+    for (int j = j0; j < nForms_ - 2; ++j)
+    {
+        if (!D_[j] || !D_[j + 1]) continue;
+        const double err = max_norm(hostcsr::Mult(*D_[j + 1], *D_[j]));
+        PARELAG_TEST_FOR_EXCEPTION(err > DEFAULT_EQUALITY_TOL, std::runtime_error, "||D_" << j + 1 << " * D_" << j << "|| = " << err);
+        worst = std::max(worst, err);
+    }
+    return worst;
+}
+
+double DeRhamSequence::CheckDP() const
+{
+    auto coarser = CoarserSequence_.lock();
+    if (!coarser) return 0.0;
+    const int j0 = data ? data->jstart : 0;
+    double worst = 0.0;
+    for (int j = j0; j < nForms_ - 1; ++j)
+    {
+        if (!P_[j] || !P_[j + 1] || !D_[j] || !coarser->D_[j]) continue;
+        const double err = max_difference(hostcsr::Mult(*D_[j], *P_[j]), hostcsr::Mult(*P_[j + 1], *coarser->D_[j]),
+                                          "D_{" + std::to_string(j) + ",fine}*P_" + std::to_string(j),
+                                          "P_" + std::to_string(j + 1) + "* D_{" + std::to_string(j) + ",coarse}");
+        PARELAG_TEST_FOR_EXCEPTION(err > LOOSE_EQUALITY_TOL, std::runtime_error,
+                                   "normInf(D_{" << j << ",fine}*P_" << j << " - P_" << j + 1 << "* D_{" << j << ",coarse}) = " << err);
+        worst = std::max(worst, err);
+    }
+    return worst;
+}
+
+double DeRhamSequence::CheckCoarseMassMatrix() const
+{
+    auto coarser = CoarserSequence_.lock();
+    if (!coarser || !data || !coarser->data) return 0.0;
+    double worst = 0.0;
+    for (int j = data->jstart; j < nForms_; ++j)
+    {
+        if (!P_[j] || !data->M.count({j, 0}) || !coarser->data->M.count({j, 0})) continue;
+        const HostCSR Mrap = hostcsr::Mult(hostcsr::Mult(hostcsr::Transpose(*P_[j]), ComputeMassOperator(j)), *P_[j]);
+        const double err = max_difference(coarser->ComputeMassOperator(j), Mrap, "Mcoarse_" + std::to_string(j), "Mrap_" + std::to_string(j));
+        PARELAG_TEST_FOR_EXCEPTION(err > LOOSE_EQUALITY_TOL, std::runtime_error, "normInf(Mcoarse_" << j << " - Mrap_" << j << ") = " << err);
+        worst = std::max(worst, err);
+    }
+    return worst;
+}
+
+double DeRhamSequence::CheckInvariants() const
+{
+    // the reference's order (DeRhamSequence.cpp:694-705)
+    const double m = CheckCoarseMassMatrix();
+    const double d = CheckD();
+    const double dp = CheckDP();
+    return std::max(m, std::max(d, dp));
+}
+
 HostCSR DeRhamSequence::ComputeMassOperator(int jform) const
 {
     PARELAG_ASSERT(data);

@@ -197,6 +197,16 @@ public:
     void SetSVDTol(double tol);
     void SetjformStart(int jform);
     std::shared_ptr<DeRhamSequence> Coarsen();
+    /// DeRhamSequence::CheckInvariants (DeRhamSequence.cpp:694-970), the identities that involve this level's and the
+    /// coarser level's local operators: CheckD (every D_j is there and non-zero, D_{j+1} D_j = 0 to 1e-9), CheckDP
+    /// (D_f P_j = P_{j+1} D_c to 1e-6) and CheckCoarseMassMatrix (M_c = P^T M_f P to 1e-6; levels that hold their mass
+    /// matrices).  A violation throws std::runtime_error naming the identity, as the reference's assertions do; the return
+    /// value is the largest residual met.  Forms below jformStart -- or, on a sequence with supplied operators, forms
+    /// whose operators are absent -- are skipped.  (The projector identities of CheckPi are covered by the tests.)
+    double CheckInvariants() const;
+    double CheckD() const;
+    double CheckDP() const;
+    double CheckCoarseMassMatrix() const;
     /// ComputeMassOperator(jform): rDof_dof^T M_e rDof_dof (DofHandler.cpp:270-281), host CSR
     HostCSR ComputeMassOperator(int jform) const;
     std::shared_ptr<SequenceData> data;       // null for sequences with externally supplied operators

@@ -371,6 +371,13 @@ extern "C" int pe_api_sequence_show_topology(pe_sequence *s, int level, char *bu
     copy_lines(seq.data->topo->ShowMe(), buf, capacity, needed);
     API_CATCH
 }
+extern "C" int pe_api_sequence_check_invariants(pe_sequence *s, int level, double *worst)
+{
+    API_TRY
+    const double w = s->levels.at(level)->CheckInvariants();
+    if (worst) *worst = w;
+    API_CATCH
+}
 extern "C" int pe_api_sequence_get_stat(pe_sequence *s, int level, const char *name, int64_t *value)
 {
     API_TRY

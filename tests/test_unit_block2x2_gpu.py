@@ -55,3 +55,17 @@ def test_hypre_jacobi_is_diagonal_scaling(sess):
     assert np.abs(solver.mult(b) - want).max() <= 1e-15 * np.abs(want).max()
     assert np.abs(solver.mult(b, x0=np.ones(200)) - want).max() <= 1e-15 * np.abs(want).max()
     solver.free()
+
+
+def test_product_check_invariants_after_coarsen(sess):
+    """DeRhamSequence::CheckInvariants (CheckCoarseMassMatrix, CheckD, CheckDP) on hierarchies the product coarsened itself"""
+    from oracle import amge
+    S = api.Sequence.hex((8, 8, 8), 3)
+    for l in range(2):
+        assert S.check_invariants(l) <= 1e-10
+    S.free()
+    X = amge.DeformedHexMesh(4, 4, 4, deform=amge.weak_scaling_deformation).vertex_coords()
+    S = api.Sequence.hex((4, 4, 4), 3, jstart=1, coords=X)
+    for l in range(2):
+        assert S.check_invariants(l) <= 1e-9
+    S.free()
