@@ -180,6 +180,23 @@ private:
 
 class HiptmairSmootherFactory : public SolverFactory
 {
+public:
+    /// constructors, setters and getters of ParELAG_HiptmairSmootherFactory.hpp:40-111: the smoother factories may be
+    /// handed over directly instead of being looked up in the library by name
+    explicit HiptmairSmootherFactory(const ParameterList &params = ParameterList()) { SetParameters(params); }
+    explicit HiptmairSmootherFactory(std::shared_ptr<SolverFactory> SmootherFact, const ParameterList &params = ParameterList())
+        : PrimaryFact_(std::move(SmootherFact)), AuxiliaryFact_(PrimaryFact_) { SetParameters(params); }
+    HiptmairSmootherFactory(std::shared_ptr<SolverFactory> PrimarySolverFactory, std::shared_ptr<SolverFactory> AuxiliarySolverFactory,
+                            const ParameterList &params = ParameterList())
+        : PrimaryFact_(std::move(PrimarySolverFactory)), AuxiliaryFact_(std::move(AuxiliarySolverFactory)) { SetParameters(params); }
+    void SetPrimaryFactory(std::shared_ptr<SolverFactory> PrimaryFact) noexcept { PrimaryFact_ = std::move(PrimaryFact); }
+    void SetAuxiliaryFactory(std::shared_ptr<SolverFactory> AuxFact) noexcept { AuxiliaryFact_ = std::move(AuxFact); }
+    void SetFactories(std::shared_ptr<SolverFactory> PrimaryFact, std::shared_ptr<SolverFactory> AuxFact) noexcept
+    { SetPrimaryFactory(std::move(PrimaryFact)); SetAuxiliaryFactory(std::move(AuxFact)); }
+    std::shared_ptr<SolverFactory> GetPrimarySmootherFactory() const noexcept { return PrimaryFact_; }
+    std::shared_ptr<SolverFactory> GetAuxiliarySmootherFactory() const noexcept { return AuxiliaryFact_; }
+
+private:
     std::unique_ptr<mfem::Solver> _do_build_solver(const Op_Ptr &op, SolverState &state) const override
     {
         auto my_state = dynamic_cast<NestedSolverState *>(&state);
@@ -239,7 +256,12 @@ class HiptmairSmootherFactory : public SolverFactory
         hypre_ParCSRMatrixFixZeroRows(*ret);
         return ret;
     }
-    void _do_set_default_parameters() override {}
+    void _do_set_default_parameters() override
+    {
+        auto &params = GetParameters();
+        params.Get("Primary Smoother", "Default Hypre");       // ParELAG_HiptmairSmootherFactory.cpp:26-31
+        params.Get("Auxiliary Smoother", "Default Hypre");
+    }
     void _do_initialize(const ParameterList &) override
     {
         PARELAG_ASSERT(HasValidSolverLibrary());

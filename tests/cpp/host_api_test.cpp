@@ -79,6 +79,39 @@ int main()
         CHECK(throws<std::out_of_range>([&] { (void)lib->GetSolverFactory("nope"); }));
         CHECK(fact->GetDefaultState() != nullptr);
     }
+    // ---- the scenario of the reference's own unit test of the library (src/linalg/unit_test/solver_lib_test.cpp): a library
+    //      filled from a ParameterList built in code, a Hiptmair factory created by hand and wired to the library, the
+    //      nested factories it resolves
+    {
+        ParameterList master("master");
+        master.Sublist("Solver1").Set("Type", "Hypre");
+        master.Sublist("Solver1").Sublist("Solver Parameters");
+        master.Sublist("Solver2").Set("Type", "Hiptmair");
+        master.Sublist("Solver2").Sublist("Solver Parameters").Set("Primary Smoother", "Solver1");
+        master.Sublist("Solver2").Sublist("Solver Parameters").Set("Auxiliary Smoother", "Solver1");
+        auto lib = SolverLibrary::CreateLibrary();
+        lib->Initialize(master);
+        auto names = lib->GetSolverNames();
+        CHECK((std::set<std::string>(names.begin(), names.end()) == std::set<std::string>{"Solver1", "Solver2"}));
+        auto hand_made = std::make_shared<HiptmairSmootherFactory>();
+        hand_made->SetSolverLibrary(lib);
+        ParameterList wiring;
+        wiring.Set("Primary Smoother", "Solver1");
+        wiring.Set("Auxiliary Smoother", "Solver1");
+        hand_made->Initialize(wiring);
+        CHECK(std::dynamic_pointer_cast<HypreSmootherFactory>(hand_made->GetPrimarySmootherFactory()) != nullptr);
+        CHECK(std::dynamic_pointer_cast<HypreSmootherFactory>(hand_made->GetAuxiliarySmootherFactory()) != nullptr);
+        CHECK(hand_made->GetPrimarySmootherFactory() == lib->GetSolverFactory("Solver1"));          // factories are shared
+        CHECK(std::dynamic_pointer_cast<HiptmairSmootherFactory>(lib->GetSolverFactory("Solver2")) != nullptr);
+        // the defaults name a "Default Hypre" entry (ParELAG_HiptmairSmootherFactory.cpp:26-31), absent from this library
+        auto defaults = std::make_shared<HiptmairSmootherFactory>();
+        defaults->SetSolverLibrary(lib);
+        CHECK(throws<std::out_of_range>([&] { defaults->Initialize(ParameterList()); }));
+        CHECK(defaults->GetParameters().Get<std::string>("Primary Smoother") == "Default Hypre");
+        // factories handed over directly
+        HiptmairSmootherFactory direct(lib->GetSolverFactory("Solver1"));
+        CHECK(direct.GetPrimarySmootherFactory() == direct.GetAuxiliarySmootherFactory());
+    }
     // ---- Level
     {
         auto fine = std::make_shared<Level>(0), coarse = std::make_shared<Level>(1);
