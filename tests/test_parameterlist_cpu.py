@@ -11,8 +11,13 @@ import pytest
 
 from parelag_b200 import api, capi
 
-REF_LISTS = sorted(glob.glob("/root/reference/examples/example_parameterlists/*.xml"))
-SUPPORTED = {"AMGe", "Hypre", "Hiptmair", "Krylov", "Stationary", "Block GS", "Block Jacobi", "Block LDU"}
+REF_LISTS = sorted(glob.glob("/root/reference/examples/example_parameterlists/*.xml") +
+                   glob.glob("/root/reference/src/linalg/MG/sample_parameterlists/*.xml") +
+                   glob.glob("/root/reference/src/linalg/unit_test/*.xml"))
+# parameters whose value names another entry of the library
+REFERENCES = {"Preconditioner", "Coarse solver", "PreSmoother", "PostSmoother", "Smoother", "Primary Smoother", "Auxiliary Smoother", "Solver",
+              "A00 Inverse", "A11 Inverse", "A00_1 Inverse", "A00_2 Inverse", "A00_3 Inverse", "S Inverse"}
+SUPPORTED = {"AMGe", "Hypre", "Hiptmair", "Krylov", "Stationary Iteration", "Block GS", "Block Jacobi", "Block LDU"}
 
 
 def fmt(typ, val):
@@ -92,21 +97,27 @@ def test_reference_example_parameter_lists(path):
     assert api.parameterlist_dump(text) == etree_dump(text)
     # every library entry: "ok" exactly when the types it depends on (transitively) are on the GPU path
     root = ET.fromstring(text)
-    lib = next(ch for ch in root if ch.tag == "ParameterList" and ch.attrib["name"] == "Preconditioner Library")
-    types, deps = {}, {}
+    lib = next((ch for ch in root if ch.tag == "ParameterList" and ch.attrib["name"] == "Preconditioner Library"), None)
+    if lib is None:
+        if root.attrib["name"] != "Preconditioner Library":
+            return                                      # a list without a solver library (src/linalg/unit_test/test.xml)
+        lib = root
+    types, deps, dangling = {}, {}, {}
     for e in lib:
         types[e.attrib["name"]] = next(p.attrib["value"] for p in e if p.tag == "Parameter" and p.attrib["name"] == "Type")
         deps[e.attrib["name"]] = [p.attrib["value"] for sub in e if sub.tag == "ParameterList" for p in sub.iter("Parameter")]
+        dangling[e.attrib["name"]] = [p.attrib["value"] for sub in e if sub.tag == "ParameterList" for p in sub.iter("Parameter")
+                                      if p.attrib["name"] in REFERENCES]
 
     def closure_ok(name, seen=()):
-        if types[name] not in SUPPORTED:
-            return False
+        if types[name] not in SUPPORTED or any(d not in types and d != "None" for d in dangling[name]):
+            return False                    # unknown type, or a reference to a solver that is not in the library
         return all(closure_ok(d, seen + (name,)) for d in deps[name] if d in types and d != name and d not in seen)
     for name, typ, status in api.library_factories(text):
         assert typ == types[name]
         assert (status == "ok") == closure_ok(name), (name, typ, status)
         if status != "ok":
-            assert "unknown factory type" in status
+            assert "unknown factory type" in status or "is not in the library" in status
 
 
 def test_block_gs_use_triangle_parameter():
