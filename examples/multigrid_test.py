@@ -2,7 +2,7 @@
 """The flow of the reference's drivers examples/MultigridTest{0,1,2}Form.cpp on this library, driven by a parameter list in
 the reference's XML layout ("Problem parameters" / "Output control" / "Preconditioner Library"):
 
-    python examples/multigrid_test.py --form 2 [-f examples/parameterlists/2form_gpu_parameters.xml] [--dry-run]
+    python examples/multigrid_test.py --form 2 [-f my_parameters.xml] [--dry-run] [--print-parameters]
 
 mesh ("TestingMesh": the cube of 2 x 2 x 2 hexahedra, examples/testing_helpers/Build3DHexMesh.hpp) -> serial + parallel
 refinements -> AgglomeratedTopology by derefinement -> DeRhamSequence, Coarsen() once per parallel refinement -> for every
@@ -21,6 +21,47 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from parelag_b200 import api  # noqa: E402
+
+
+def build_test_parameters(form, solvers=("PCG-AMGe",)):
+    """The default list, built in code like the reference's examples/testing_helpers/Create{0,1,2}FormParameterList.hpp
+    ("BuildTestParameters"): the cube refined once in serial and twice in parallel, PCG preconditioned by the AMGe
+    V-cycle with (Hiptmair) l1-Gauss-Seidel smoothers and the PCG-GS coarse solver of spe10_example_parameters.xml."""
+    def plist(name, body):
+        return ['<ParameterList name="%s">' % name] + ["  " + l for l in body] + ["</ParameterList>"]
+
+    def par(name, value):
+        if isinstance(value, bool):
+            t, v = "bool", "true" if value else "false"
+        elif isinstance(value, int):
+            t, v = "int", str(value)
+        elif isinstance(value, float):
+            t, v = "double", repr(value)
+        elif isinstance(value, (list, tuple)):
+            t, v = ("vector(int)", " ".join(str(x) for x in value)) if value and isinstance(value[0], int) else ("list(string)", ", ".join(value))
+        else:
+            t, v = "string", value
+        return '<Parameter name="%s" type="%s" value="%s"/>' % (name, t, v)
+
+    def solver(name, typ, params):
+        return plist(name, [par("Type", typ)] + plist("Solver Parameters", [par(k, v) for k, v in params.items()]))
+    smoother = "Hiptmair-GS-GS" if form > 0 else "Gauss-Seidel"
+    lib = solver("PCG-AMGe", "Krylov", {"Solver name": "PCG", "Preconditioner": "AMGe", "Print level": 1, "Maximum iterations": 300,
+                                        "Relative tolerance": 1e-6, "Absolute tolerance": 1e-6})
+    lib += solver("AMGe", "AMGe", {"Maximum levels": -1, "Forms": [form], "PreSmoother": smoother, "PostSmoother": smoother,
+                                   "Coarse solver": "PCG-GS", "Cycle type": "V-cycle"})
+    lib += solver("PCG-GS", "Krylov", {"Solver name": "PCG", "Preconditioner": "Gauss-Seidel", "Print level": -1, "Maximum iterations": 3,
+                                       "Relative tolerance": 1e-4, "Absolute tolerance": 1e-4})
+    if form > 0:
+        lib += solver("Hiptmair-GS-GS", "Hiptmair", {"Primary Smoother": "Gauss-Seidel", "Auxiliary Smoother": "Gauss-Seidel"})
+    lib += solver("Gauss-Seidel", "Hypre", {"Type": "L1 Gauss-Seidel", "Sweeps": 1, "GS ordering": "multicolor"})
+    doc = plist("Default",
+                plist("Problem parameters", [par("Mesh file", "TestingMesh"), par("Serial refinement levels", 1), par("Parallel refinement levels", 2),
+                                             par("Finite element order", 0), par("Upscaling order", 0), par("Start level", 0), par("Stop level", 0),
+                                             par("List of linear solvers", list(solvers))]) +
+                plist("Output control", [par("Visualize solution", False), par("Print timings", True), par("Show progress", True)]) +
+                plist("Preconditioner Library", lib))
+    return "\n".join(doc) + "\n"
 
 
 def read_parameters(xml):
@@ -63,11 +104,14 @@ def library_document(xml):
 def main():
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("--form", type=int, required=True, choices=[0, 1, 2], help="0: H1 (MultigridTest0Form), 1: H(curl), 2: H(div)")
-    ap.add_argument("-f", "--xml-file", default=None, help="XML parameter list (default: examples/parameterlists/<form>form_gpu_parameters.xml)")
+    ap.add_argument("-f", "--xml-file", default="BuildTestParameters", help="XML parameter list (default: the list build_test_parameters() builds)")
+    ap.add_argument("--print-parameters", action="store_true", help="print the parameter list in use and exit")
     ap.add_argument("--dry-run", action="store_true", help="parse and validate the parameter list, print the plan, no GPU")
     args = ap.parse_args()
-    path = args.xml_file or os.path.join(ROOT, "examples", "parameterlists", "%dform_gpu_parameters.xml" % args.form)
-    xml = open(path).read()
+    xml = build_test_parameters(args.form) if args.xml_file == "BuildTestParameters" else open(args.xml_file).read()
+    if args.print_parameters:
+        print(xml, end="")
+        return
     p = read_parameters(xml)
     prob = lambda k, d: p.get("Problem parameters/" + k, d)
     meshfile = prob("Mesh file", "TestingMesh")

@@ -19,11 +19,13 @@ def test_dry_run_of_the_shipped_parameter_lists(form):
 
 
 def test_a_list_that_needs_a_hypre_black_box_is_refused_with_the_reason(tmp_path):
-    xml = open(os.path.join(ROOT, "examples", "parameterlists", "2form_gpu_parameters.xml")).read()
+    r = subprocess.run([sys.executable, DRIVER, "--form", "2", "--print-parameters"], capture_output=True, text=True, timeout=300)
+    xml = r.stdout
+    assert '<Parameter name="Coarse solver" type="string" value="PCG-GS"/>' in xml
     xml = xml.replace('<Parameter name="Coarse solver" type="string" value="PCG-GS"/>',
                       '<Parameter name="Coarse solver" type="string" value="ADS Solver"/>')
-    xml = xml.replace('  <ParameterList name="Preconditioner Library">',
-                      '  <ParameterList name="Preconditioner Library">\n    <ParameterList name="ADS Solver">'
+    xml = xml.replace('<ParameterList name="Preconditioner Library">',
+                      '<ParameterList name="Preconditioner Library">\n    <ParameterList name="ADS Solver">'
                       '<Parameter name="Type" type="string" value="ADS"/></ParameterList>')
     path = tmp_path / "needs_ads.xml"
     path.write_text(xml)

@@ -23,5 +23,5 @@ PY
 timeout 300 python bench.py --config spe10 --perm-file /tmp/spe_perm_synthetic.dat --steps 10 --warmup 3 --no-cpu-baseline \
   > gpurun_out/pending_spe10_tensor.json 2> gpurun_out/pending_spe10_tensor.err
 tail -c 600 gpurun_out/pending_spe10_tensor.json
-# the example driver on its three shipped parameter lists
+# the example driver on its three default parameter lists
 for form in 0 1 2; do timeout 200 python examples/multigrid_test.py --form $form > gpurun_out/pending_example_form$form.log 2>&1; grep -E "Final residual|Error|error" gpurun_out/pending_example_form$form.log | head -3; done
