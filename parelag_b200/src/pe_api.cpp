@@ -58,10 +58,10 @@ extern "C" int pe_api_hexsequence_create_par(const int32_t *procs, int nx, int n
 {
     API_TRY
     PARELAG_TEST_FOR_EXCEPTION(!g_have_host_comm, std::runtime_error, "pe_api_hexsequence_create_par: call pe_api_session_set_host_comm first");
-    auto s = new pe_sequence();
+    auto s = std::make_unique<pe_sequence>();      // released only when the build succeeded
     const int P[3] = {procs[0], procs[1], procs[2]};
     s->levels = BuildHexSequenceHierarchyPar(&g_host_comm, P, nx, ny, nz, Lx, Ly, Lz, alpha, beta, jstart, nlevels, svd_tol);
-    *out = s;
+    *out = s.release();
     API_CATCH
 }
 extern "C" int pe_api_hexsequence_create_par_deformed(const int32_t *procs, int nx, int ny, int nz, const double *vertex_xyz,
@@ -71,10 +71,10 @@ extern "C" int pe_api_hexsequence_create_par_deformed(const int32_t *procs, int 
     API_TRY
     PARELAG_TEST_FOR_EXCEPTION(!g_have_host_comm, std::runtime_error, "pe_api_hexsequence_create_par_deformed: call pe_api_session_set_host_comm first");
     PARELAG_TEST_FOR_EXCEPTION(!vertex_xyz, std::runtime_error, "pe_api_hexsequence_create_par_deformed: vertex coordinates missing");
-    auto s = new pe_sequence();
+    auto s = std::make_unique<pe_sequence>();      // released only when the build succeeded
     const int P[3] = {procs[0], procs[1], procs[2]};
     s->levels = BuildHexSequenceHierarchyPar(&g_host_comm, P, nx, ny, nz, 1.0, 1.0, 1.0, alpha, beta, jstart, nlevels, svd_tol, vertex_xyz);
-    *out = s;
+    *out = s.release();
     API_CATCH
 }
 extern "C" int pe_api_sequence_get_dofmap(pe_sequence *s, int level, int form, int32_t *ndofs, int64_t *gid, int32_t *owner,
@@ -124,10 +124,10 @@ extern "C" int pe_api_sequence_true_operator(pe_sequence *s, int level, const ch
 extern "C" int pe_api_sequence_create(int nforms, int nlevels, pe_sequence **out)
 {
     API_TRY
-    auto s = new pe_sequence();
+    auto s = std::make_unique<pe_sequence>();      // released only when the build succeeded
     for (int l = 0; l < nlevels; ++l) s->levels.push_back(std::make_shared<DeRhamSequence>(nforms));
     for (int l = 0; l + 1 < nlevels; ++l) s->levels[l]->SetCoarserSequence(s->levels[l + 1]);
-    *out = s;
+    *out = s.release();
     API_CATCH
 }
 extern "C" int pe_api_sequence_set_P(pe_sequence *s, int level, int form, int nrows, int ncols,
@@ -158,9 +158,9 @@ extern "C" int pe_api_hexsequence_create(int nx, int ny, int nz, double Lx, doub
                                          int jstart, int nlevels, double svd_tol, pe_sequence **out)
 {
     API_TRY
-    auto s = new pe_sequence();
+    auto s = std::make_unique<pe_sequence>();      // released only when the build succeeded
     s->levels = BuildHexSequenceHierarchy(nx, ny, nz, Lx, Ly, Lz, alpha, beta, jstart, nlevels, svd_tol);
-    *out = s;
+    *out = s.release();
     API_CATCH
 }
 extern "C" int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const double *vertex_xyz, const double *alpha,
@@ -168,9 +168,9 @@ extern "C" int pe_api_hexsequence_create_deformed(int nx, int ny, int nz, const 
 {
     API_TRY
     PARELAG_TEST_FOR_EXCEPTION(!vertex_xyz, std::runtime_error, "pe_api_hexsequence_create_deformed: vertex coordinates missing");
-    auto s = new pe_sequence();
+    auto s = std::make_unique<pe_sequence>();      // released only when the build succeeded
     s->levels = BuildHexSequenceHierarchy(nx, ny, nz, 1.0, 1.0, 1.0, alpha, beta, jstart, nlevels, svd_tol, vertex_xyz);
-    *out = s;
+    *out = s.release();
     API_CATCH
 }
 extern "C" int pe_api_hexsequence_create_tensor(int nx, int ny, int nz, double Lx, double Ly, double Lz, const double *alpha, const double *beta_xyz,
@@ -286,19 +286,19 @@ extern "C" int pe_api_tetsequence_create(int nv, const double *vertex_xyz, int n
 {
     API_TRY
     PARELAG_TEST_FOR_EXCEPTION(!vertex_xyz || !tets || nv < 4 || nel < 1, std::runtime_error, "pe_api_tetsequence_create: empty mesh");
-    auto s = new pe_sequence();
+    auto s = std::make_unique<pe_sequence>();      // released only when the build succeeded
     const TetMesh mesh = TetMesh::FromArrays(nv, vertex_xyz, nel, tets, nbdr, bdr_triangles, bdr_attributes);
     s->levels = BuildTetSequenceHierarchy(mesh, nref, nlevels, nullptr, nullptr, jstart, svd_tol);
-    *out = s;
+    *out = s.release();
     API_CATCH
 }
 extern "C" int pe_api_tetsequence_create_from_file(const char *mesh_file, int nref, int nlevels, int jstart, double svd_tol, pe_sequence **out)
 {
     API_TRY
-    auto s = new pe_sequence();
+    auto s = std::make_unique<pe_sequence>();      // released only when the build succeeded
     const TetMesh mesh = TetMesh::Read(mesh_file);        // NETGEN neutral or MFEM mesh v1.0, by the first line
     s->levels = BuildTetSequenceHierarchy(mesh, nref, nlevels, nullptr, nullptr, jstart, svd_tol);
-    *out = s;
+    *out = s.release();
     API_CATCH
 }
 static HostCSR pool_as_csr(const BlockPool &P)
